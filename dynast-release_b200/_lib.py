@@ -1,0 +1,93 @@
+"""ctypes binding of libdynast_b200.so (include/dynast_b200.h). Fails loudly when the library is absent."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdynast_b200.so')
+
+
+class DynastB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+_vp, _i32, _i64, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32
+
+# name -> (restype, argtypes); kept in the order of include/dynast_b200.h
+PROTOTYPES = {
+    'dyn_last_error': (C.c_char_p, []),
+    'dyn_version': (_i32, []),
+    'dyn_ctx_create': (_i32, [_i32, C.POINTER(_vp)]),
+    'dyn_ctx_destroy': (_i32, [_vp]),
+    'dyn_ctx_sm_count': (_i32, [_vp]),
+    'dyn_tally_reads': (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'dyn_tally_reads_host':
+        (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'dyn_em_pc': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    'dyn_em_pc_host': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+}
+
+
+def load():
+    """Load the shared library (once). Raises DynastB200Error if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DynastB200Error(
+            f'{LIB_PATH} is missing: build it with `python build.py` (nvcc, sm_100a). '
+            'dynast_b200 has no CPU fallback.'
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().dyn_last_error()
+        raise DynastB200Error(f'dynast_b200 error {rc}: {msg.decode(errors="replace") if msg else ""}')
+
+
+class Context:
+    """One per GPU per process (dyn_ctx_create)."""
+
+    _cache = {}
+
+    def __init__(self, device: int = 0):
+        lib = load()
+        h = C.c_void_p()
+        check(lib.dyn_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+        self.lib = lib
+
+    @classmethod
+    def get(cls, device: int = 0) -> 'Context':
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+    @property
+    def sm_count(self) -> int:
+        return self.lib.dyn_ctx_sm_count(self.handle)
+
+    def close(self):
+        if self.handle:
+            self.lib.dyn_ctx_destroy(self.handle)
+            self.handle = None
+        Context._cache.pop(self.device, None)
+
+
+def ptr(arr):
+    """Data pointer of a numpy array / torch tensor / None."""
+    if arr is None:
+        return None
+    if hasattr(arr, 'data_ptr'):
+        return C.c_void_p(arr.data_ptr())
+    return C.c_void_p(arr.ctypes.data)

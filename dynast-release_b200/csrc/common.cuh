@@ -1,0 +1,74 @@
+// Shared helpers for the dynast_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dynast_b200.h"
+
+void dyn_set_error(const char *fmt, ...);
+
+#define DYN_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            dyn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return DYN_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define DYN_ARG(cond, msg)                 \
+    do {                                   \
+        if (!(cond)) {                     \
+            dyn_set_error("%s: %s", __func__, msg); \
+            return DYN_ERR_ARG;            \
+        }                                  \
+    } while (0)
+
+struct dyn_ctx {
+    int device;
+    int sm_count;
+    size_t smem_optin;      // max dynamic shared memory per block
+    cudaStream_t copy_stream[2];
+    cudaEvent_t ev[4];
+    // lazily grown device scratch (never shrinks); used by host-buffer entry points and sort temp
+    void *scratch[8];
+    size_t scratch_bytes[8];
+    // lazily built device tables
+    double *em_coef;        // binomial coefficient table (wrapped-int64 semantics), [em_coef_K][em_coef_N]
+    int em_coef_K, em_coef_N;
+};
+
+int dyn_ctx_scratch(dyn_ctx *ctx, int slot, size_t bytes, void **out);
+
+// ---- small device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared (SASS: UBLKCP), completion signalled on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

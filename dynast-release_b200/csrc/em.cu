@@ -1,0 +1,403 @@
+// Per-barcode binomial-mixture EM for p_c.
+//
+// Replaces dynast/estimation/p_c.py:32-172 (numba binomial_pmf / expectation_maximization /
+// expectation_maximization_nasc) as driven one barcode per task by estimate_p_c (p_c.py:206-227).
+//
+// One CTA per barcode (persistent grid, barcodes handed out by an atomic counter).  The reference's
+// arithmetic is reproduced operation for operation so that results are bit-identical, not merely
+// within tolerance (the M step is a FLOAT32 sequential sum in the reference -- reordering it moves
+// p_c by ~1e-6 relative, which is the whole parity budget):
+//   * binomial coefficients come from a table built with wrapping 64-bit integer products and one
+//     int64/int64 true division (p_c.py:45);
+//   * p**k is numba's square-and-multiply (numba/cpython/numbers.py int_power_impl);
+//   * every floating-point operation uses the explicit round-to-nearest intrinsics so that nvcc can
+//     never contract a multiply-add;
+//   * E step: unmasked cells never change, so columns are independent and run one per thread; each
+//     column's sums run in the reference's kp order;
+//   * M step: the two sequential float32 sums (row-major; cells that are zero for good are skipped,
+//     x + 0 == x exactly) run as two interleaved dependency chains on one lane.
+// The kernel is latency-bound on those serial chains, not HBM- or FP64-throughput-bound; parallelism
+// comes from many barcodes resident per SM.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kEmThreads = 64;
+constexpr int kMaxFactorialK = 66;   // k! == 0 (mod 2^64) for k >= 66 -> ZeroDivisionError in the reference
+
+struct EmParams {
+    const int32_t *k;
+    const int32_t *n;
+    const long long *count;
+    const long long *off;
+    long long n_barcodes;
+    const double *p_e;
+    double *p_c;
+    int32_t *status;
+    int32_t *iters;
+    const double *coef;   // [coef_K][coef_N]
+    int coef_K, coef_N;
+    int max_cells;        // dense capacity (cells) of the shared-memory layout
+    int max_K, max_N;     // pow-table capacities
+    unsigned long long *work_counter;
+};
+
+__global__ void em_coef_kernel(double *coef, int K, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    const long long k = i / N, n = i % N;
+    unsigned long long num = 1, den = 1;
+    for (long long j = 0; j < k; ++j) {
+        num *= (unsigned long long)(j + (n - k + 1));
+        den *= (unsigned long long)(j + 1);
+    }
+    coef[i] = __ddiv_rn((double)(long long)num, (double)(long long)den);
+}
+
+// per-barcode shape discovery: K = max k + 1, N = max n + 1; also global maxima
+__global__ void em_shape_kernel(const int32_t *k, const int32_t *n, const long long *off, long long B, int *maxima) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int K = 0, N = 0;
+    if (b < B) {
+        for (long long i = off[b]; i < off[b + 1]; ++i) {
+            K = max(K, k[i] + 1);
+            N = max(N, n[i] + 1);
+        }
+    }
+    // warp reduce then atomics
+    long long cells = (long long)K * N;
+    int c = cells > 0x7fffffffLL ? 0x7fffffff : (int)cells;
+    for (int d = 16; d; d >>= 1) {
+        K = max(K, __shfl_xor_sync(0xffffffffu, K, d));
+        N = max(N, __shfl_xor_sync(0xffffffffu, N, d));
+        c = max(c, __shfl_xor_sync(0xffffffffu, c, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(maxima + 0, K);
+        atomicMax(maxima + 1, N);
+        atomicMax(maxima + 2, c);
+    }
+}
+
+// numba int_power_impl: a ** b for float a, integer b. ok=false on 1.0 / 0.0.
+__device__ __forceinline__ double ipow(double a, int b, bool &ok) {
+    double r = 1.0;
+    unsigned e = b < 0 ? (unsigned)(-b) : (unsigned)b;
+    while (e) {
+        if (e & 1u) r = __dmul_rn(r, a);
+        e >>= 1;
+        a = __dmul_rn(a, a);
+    }
+    if (b < 0) {
+        if (r == 0.0) { ok = false; return 0.0; }
+        r = __ddiv_rn(1.0, r);
+    }
+    return r;
+}
+
+struct EmShared {
+    double p_c, prev;
+    double bis_r, bis_l;
+    int K, N, nact, ncols;
+    int fail;
+    int done;
+};
+
+template <bool NASC>
+__global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    // layout (capacities from p.max_cells / p.max_K / p.max_N)
+    float *v = reinterpret_cast<float *>(smem_raw);                         // [max_cells]
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(v + p.max_cells);          // [max_cells]; later: active list
+    double *powp = reinterpret_cast<double *>(cnt + p.max_cells);           // [max_K]
+    double *powq = powp + p.max_K;                                          // [max_K + max_N]
+    int *cols = reinterpret_cast<int *>(powq + p.max_K + p.max_N);          // [max_N] columns with masked cells
+    uint8_t *mask = reinterpret_cast<uint8_t *>(cols + p.max_N);            // [max_cells]
+    __shared__ EmShared sh;
+    __shared__ unsigned long long s_work;
+    __shared__ int s_scan[kEmThreads / 32];
+
+    const int tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_work = atomicAdd(p.work_counter, 1ull);
+        __syncthreads();
+        const long long b = (long long)s_work;
+        if (b >= p.n_barcodes) break;
+
+        const long long t0 = p.off[b], t1 = p.off[b + 1];
+        const double p_e = p.p_e[b];
+        // ---- shape
+        int K = 0, N = 0;
+        for (long long i = t0 + tid; i < t1; i += kEmThreads) {
+            K = max(K, p.k[i] + 1);
+            N = max(N, p.n[i] + 1);
+        }
+        for (int d = 16; d; d >>= 1) {
+            K = max(K, __shfl_xor_sync(0xffffffffu, K, d));
+            N = max(N, __shfl_xor_sync(0xffffffffu, N, d));
+        }
+        if ((tid & 31) == 0) { s_scan[tid >> 5] = K; }
+        __syncthreads();
+        if (tid == 0) {
+            int kk = 0;
+            for (int w = 0; w < kEmThreads / 32; ++w) kk = max(kk, s_scan[w]);
+            sh.K = kk;
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { s_scan[tid >> 5] = N; }
+        __syncthreads();
+        if (tid == 0) {
+            int nn = 0;
+            for (int w = 0; w < kEmThreads / 32; ++w) nn = max(nn, s_scan[w]);
+            sh.N = nn;
+            sh.fail = 0;
+            sh.done = 0;
+        }
+        __syncthreads();
+        K = sh.K; N = sh.N;
+        const int KN = K * N;
+        if (K == 0 || N == 0) {
+            if (tid == 0) { p.p_c[b] = 0.0; p.status[b] = DYN_EM_PC_LE_PE; if (p.iters) p.iters[b] = 0; }
+            continue;
+        }
+        if (K > kMaxFactorialK) {   // binomial_pmf(k >= 66, ..) divides by a wrapped-to-zero factorial
+            if (tid == 0) { p.p_c[b] = 0.0; p.status[b] = DYN_EM_ZERODIV; if (p.iters) p.iters[b] = 0; }
+            continue;
+        }
+        if (KN > p.max_cells || K > p.max_K || N > p.max_N || K > p.coef_K || N > p.coef_N) {
+            if (tid == 0) { p.p_c[b] = 0.0; p.status[b] = DYN_EM_UNSUPPORTED; if (p.iters) p.iters[b] = 0; }
+            continue;
+        }
+        // ---- dense histogram (duplicates summed, p_c.py:219)
+        for (int i = tid; i < KN; i += kEmThreads) { cnt[i] = 0; mask[i] = 0; }
+        __syncthreads();
+        for (long long i = t0 + tid; i < t1; i += kEmThreads) {
+            const long long c = p.count[i];
+            if (c < 0 || c > 0x7fffffffLL) sh.fail = DYN_EM_UNSUPPORTED;
+            atomicAdd(&cnt[p.k[i] * N + p.n[i]], (uint32_t)c);
+        }
+        // pow tables for p_e
+        {
+            bool ok = true;
+            for (int i = tid; i < K; i += kEmThreads) powp[i] = ipow(p_e, i, ok);
+            const double q = __dsub_rn(1.0, p_e);
+            for (int i = tid; i < K + N - 1; i += kEmThreads) powq[i] = ipow(q, i - (K - 1), ok);
+            if (!ok) sh.fail = DYN_EM_ZERODIV;
+        }
+        __syncthreads();
+        // ---- mask (p_c.py:138-143 / 64-68): one thread per column, suffix sums from the top row down
+        for (int n = tid; n < N; n += kEmThreads) {
+            long long s = 0;
+            bool any = false;
+            for (int k = K - 1; k >= 0; --k) {
+                const uint32_t c = cnt[k * N + n];
+                if (!NASC) s += c;
+                const double pm = __dmul_rn(__dmul_rn(p.coef[k * p.coef_N + n], powp[k]), powq[n - k + K - 1]);
+                const double expected = __dmul_rn((double)s, pm);
+                const bool m = expected > __dmul_rn(0.01, (double)c);
+                mask[k * N + n] = m;
+                any |= m;
+                if (NASC) s += c;
+            }
+            cols[n] = any ? 1 : 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < KN; i += kEmThreads) v[i] = (float)cnt[i];   // p_c.py:148
+        __syncthreads();
+        // ---- active list: row-major indices of cells that can ever be non-zero (non-zero or masked);
+        //      compacted list of columns owning masked cells.  Both by thread 0..: sizes are tiny.
+        if (tid == 0) {
+            int na = 0;
+            for (int i = 0; i < KN; ++i)
+                if (cnt[i] != 0 || mask[i]) cnt[na++] = (uint32_t)i;   // in place: na <= i, cnt[i] already consumed
+            sh.nact = na;
+            int nc = 0;
+            for (int n = 0; n < N; ++n)
+                if (cols[n]) cols[nc++] = n;
+            sh.ncols = nc;
+            sh.p_c = NASC ? 0.5 : 0.1;
+            sh.prev = sh.p_c;
+            sh.bis_r = 1.0;
+            sh.bis_l = 0.0;
+        }
+        __syncthreads();
+        const int nact = sh.nact, ncols = sh.ncols;
+        const uint32_t *act = cnt;   // reused as the active list
+
+        int iters = 0;
+        const int max_iters = NASC ? 0x7fffffff : 300;
+        while (!sh.fail && !sh.done && iters < max_iters) {
+            if (NASC && !(__dsub_rn(sh.bis_r, sh.bis_l) >= 1e-8)) break;
+            ++iters;
+            const double p_c = sh.p_c;
+            {
+                bool ok = true;
+                for (int i = tid; i < K; i += kEmThreads) powp[i] = ipow(p_c, i, ok);
+                const double q = __dsub_rn(1.0, p_c);
+                for (int i = tid; i < K + N - 1; i += kEmThreads) powq[i] = ipow(q, i - (K - 1), ok);
+                if (!ok) sh.fail = DYN_EM_ZERODIV;
+            }
+            __syncthreads();
+            // ---- E step: one thread per column that owns masked cells
+            for (int ci = tid; ci < ncols; ci += kEmThreads) {
+                const int n = cols[ci];
+                const double *cf = p.coef + n;
+                if (!NASC) {
+                    double den = 0.0;
+                    for (int kp = 0; kp < K; ++kp)
+                        if (!mask[kp * N + n])
+                            den = __dadd_rn(den, __dmul_rn(__dmul_rn(cf[kp * p.coef_N], powp[kp]), powq[n - kp + K - 1]));
+                    if (den > 0.0) {
+                        for (int k = 0; k < K; ++k) {
+                            if (!mask[k * N + n]) continue;
+                            const double pk = __dmul_rn(__dmul_rn(cf[k * p.coef_N], powp[k]), powq[n - k + K - 1]);
+                            double num = 0.0;
+                            for (int kp = 0; kp < K; ++kp)
+                                if (!mask[kp * N + n]) num = __dadd_rn(num, __dmul_rn(pk, (double)v[kp * N + n]));
+                            v[k * N + n] = __double2float_rn(__ddiv_rn(num, den));
+                        }
+                    }
+                } else {
+                    // Gauss-Seidel within the column, sums over kp IN the mask (p_c.py:80-88, as written)
+                    double den = 0.0;
+                    for (int kp = 0; kp < K; ++kp)
+                        if (mask[kp * N + n])
+                            den = __dadd_rn(den, __dmul_rn(__dmul_rn(cf[kp * p.coef_N], powp[kp]), powq[n - kp + K - 1]));
+                    if (den == 0.0) { sh.fail = DYN_EM_ZERODIV; continue; }
+                    for (int k = 0; k < K; ++k) {
+                        if (!mask[k * N + n]) continue;
+                        const double pk = __dmul_rn(__dmul_rn(cf[k * p.coef_N], powp[k]), powq[n - k + K - 1]);
+                        double num = 0.0;
+                        for (int kp = 0; kp < K; ++kp)
+                            if (mask[kp * N + n]) num = __dadd_rn(num, __dmul_rn(pk, (double)v[kp * N + n]));
+                        v[k * N + n] = __double2float_rn(__ddiv_rn(num, den));
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- M step
+            if (!NASC) {
+                // numba: (new_values * arange).sum() == float32 products, float32 sequential sum
+                if (tid == 0) {
+                    float sk = 0.0f, sn = 0.0f;
+                    for (int i = 0; i < nact; ++i) {
+                        const uint32_t cell = act[i];
+                        const float x = v[cell];
+                        sk = __fadd_rn(sk, __fmul_rn(x, (float)(cell / N)));
+                        sn = __fadd_rn(sn, __fmul_rn(x, (float)(cell % N)));
+                    }
+                    const double prev = sh.p_c;
+                    const double nw = sn > 0.0f ? (double)__fdiv_rn(sk, sn) : prev;
+                    sh.prev = prev;
+                    sh.p_c = nw;
+                    if (prev == nw) sh.done = 1;
+                }
+            } else {
+                if (tid == 0) {
+                    double sk = 0.0, sn = 0.0;
+                    for (int i = 0; i < nact; ++i) {
+                        const uint32_t cell = act[i];
+                        const double x = (double)v[cell];
+                        sk = __dadd_rn(sk, __dmul_rn((double)(cell / N), x));
+                        sn = __dadd_rn(sn, __dmul_rn((double)(cell % N), x));
+                    }
+                    const double prev = sh.p_c;
+                    const double nw = sn > 0.0 ? __ddiv_rn(sk, sn) : 0.0;
+                    sh.prev = prev;
+                    sh.p_c = nw;
+                    if (prev == nw) sh.done = 1;
+                    else if (nw < prev) sh.bis_r = prev;
+                    else sh.bis_l = prev;
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            int st = sh.fail;
+            if (!st && !NASC && sh.p_c <= p_e) st = DYN_EM_PC_LE_PE;
+            p.p_c[b] = sh.p_c;
+            p.status[b] = st;
+            if (p.iters) p.iters[b] = iters;
+        }
+    }
+}
+
+}  // namespace
+
+static size_t em_smem_bytes(int max_cells, int max_K, int max_N) {
+    size_t s = 0;
+    s += sizeof(float) * max_cells + sizeof(uint32_t) * max_cells;   // v, cnt/active list
+    s += sizeof(double) * (max_K + max_K + max_N);
+    s += sizeof(int) * max_N;
+    s += max_cells;
+    return (s + 15) & ~(size_t)15;
+}
+
+extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n, const int64_t *d_count,
+                         const int64_t *d_off, int64_t n_barcodes, const double *d_p_e, int nasc, double *d_p_c,
+                         int32_t *d_em_status, int32_t *d_iters, void *stream_) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n_barcodes >= 0, "negative n_barcodes");
+    if (n_barcodes == 0) return DYN_OK;
+    DYN_ARG(d_k && d_n && d_count && d_off && d_p_e && d_p_c && d_em_status, "null buffer");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    // shape discovery (one small kernel + a 12-byte read back: the only synchronisation of this call)
+    void *scr = nullptr;
+    int rc = dyn_ctx_scratch(ctx, 0, 64, &scr);
+    if (rc) return rc;
+    int *d_max = static_cast<int *>(scr);
+    unsigned long long *d_work = reinterpret_cast<unsigned long long *>(d_max + 4);
+    DYN_CUDA(cudaMemsetAsync(scr, 0, 64, stream));
+    em_shape_kernel<<<(unsigned)((n_barcodes + 127) / 128), 128, 0, stream>>>(
+        d_k, d_n, reinterpret_cast<const long long *>(d_off), n_barcodes, d_max);
+    DYN_CUDA(cudaGetLastError());
+    int h_max[3];
+    DYN_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaStreamSynchronize(stream));
+    int max_K = h_max[0] < 1 ? 1 : h_max[0], max_N = h_max[1] < 1 ? 1 : h_max[1];
+    long long max_cells = h_max[2] < 1 ? 1 : h_max[2];
+    if (max_K > kMaxFactorialK) max_K = kMaxFactorialK;   // larger K fail in-kernel with DYN_EM_ZERODIV
+
+    // shrink the dense capacity until the layout fits; barcodes beyond it report DYN_EM_UNSUPPORTED
+    while (em_smem_bytes((int)max_cells, max_K, max_N) > ctx->smem_optin - 1024 && max_cells > 64) max_cells /= 2;
+    const size_t smem = em_smem_bytes((int)max_cells, max_K, max_N);
+    if (smem > ctx->smem_optin - 1024) {
+        dyn_set_error("dyn_em_pc: histogram shape %d x %d does not fit shared memory", max_K, max_N);
+        return DYN_ERR_ARG;
+    }
+
+    // coefficient table
+    if (!ctx->em_coef || ctx->em_coef_K < max_K || ctx->em_coef_N < max_N) {
+        if (ctx->em_coef) DYN_CUDA(cudaFree(ctx->em_coef));
+        ctx->em_coef = nullptr;
+        const int K = max_K > 32 ? max_K : 32, N = max_N > 160 ? max_N : 160;
+        DYN_CUDA(cudaMalloc(&ctx->em_coef, sizeof(double) * (size_t)K * N));
+        ctx->em_coef_K = K;
+        ctx->em_coef_N = N;
+        em_coef_kernel<<<(K * N + 255) / 256, 256, 0, stream>>>(ctx->em_coef, K, N);
+        DYN_CUDA(cudaGetLastError());
+    }
+
+    EmParams p;
+    p.k = d_k; p.n = d_n;
+    p.count = reinterpret_cast<const long long *>(d_count);
+    p.off = reinterpret_cast<const long long *>(d_off);
+    p.n_barcodes = n_barcodes;
+    p.p_e = d_p_e; p.p_c = d_p_c; p.status = d_em_status; p.iters = d_iters;
+    p.coef = ctx->em_coef; p.coef_K = ctx->em_coef_K; p.coef_N = ctx->em_coef_N;
+    p.max_cells = (int)max_cells; p.max_K = max_K; p.max_N = max_N;
+    p.work_counter = d_work;
+
+    auto kern = nasc ? em_kernel<true> : em_kernel<false>;
+    DYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEmThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > n_barcodes) grid = n_barcodes;
+    kern<<<(unsigned)grid, kEmThreads, smem, stream>>>(p);
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}

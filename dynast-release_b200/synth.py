@@ -1,0 +1,128 @@
+"""Synthetic scSLAM-seq-like reads (SURVEY.md section 8d, config C2 generative model; follows the
+simulator in dynast/benchmarking/simulation.py:22-79 for the labelling model).
+
+This is the slow numpy/Python generator used for tests and small inputs; the bench generates the
+full-size configs on the GPU with the same per-read decisions (csrc/synth.cu)."""
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import records
+
+BASES = np.array(list('ACGT'))
+
+
+def make_reads(
+    n_reads: int,
+    seed: int = 2001,
+    read_len: int = 91,
+    n_barcodes: int = 100,
+    n_genes: int = 200,
+    n_contigs: int = 25,
+    p_c: float = 0.05,
+    p_e: float = 5e-4,
+    frac_n: float = 0.001,
+    umi_len: int = 12,
+    reads_per_umi: float = 2.0,
+):
+    """Returns dict(blob, rec_off, barcode_id, umi, gene_id, score, strand_gene, truth...) with one
+    single-end read per counting unit.  CIGAR mix: 70 % LM, 18 % aMbNcM, 8 % sS(L-s)M, 2 % one 1-3 nt D,
+    2 % one 1-3 nt I.  Reference bases iid uniform; labelled reads convert T->C per T w.p. p_c; every
+    base is substituted to each specific other base w.p. p_e; Phred 90 % in 36..40, 10 % in 2..27."""
+    rng = np.random.default_rng(seed)
+    units = []
+    L = read_len
+    gene_strand = rng.integers(0, 2, n_genes)
+    gene_contig = rng.integers(0, n_contigs, n_genes)
+    gene_pi = rng.beta(2, 5, n_genes)
+    bc_w = rng.lognormal(np.log(5000), 0.6, n_barcodes)
+    bc_w /= bc_w.sum()
+    gene_w = 1.0 / np.arange(1, n_genes + 1)**1.1
+    gene_w /= gene_w.sum()
+    n_groups = max(1, int(n_reads / reads_per_umi))
+    grp_bc = rng.choice(n_barcodes, n_groups, p=bc_w)
+    grp_gene = rng.choice(n_genes, n_groups, p=gene_w)
+    grp_umi = rng.integers(0, 4**umi_len, n_groups)
+    grp_of_read = rng.integers(0, n_groups, n_reads)
+    barcode_id = grp_bc[grp_of_read].astype(np.uint32)
+    gene_id = grp_gene[grp_of_read].astype(np.uint32)
+    umi = grp_umi[grp_of_read].astype(np.uint64)
+    pos = np.sort(rng.integers(0, 1 << 26, n_reads)).astype(np.int64)
+    score = np.zeros(n_reads, dtype=np.int32)
+    labelled = rng.random(n_reads) < gene_pi[gene_id]
+    kind = rng.choice(5, n_reads, p=[0.70, 0.18, 0.08, 0.02, 0.02])
+    for i in range(n_reads):
+        k = kind[i]
+        if k == 0:
+            cigar = [(0, L)]
+        elif k == 1:
+            a = int(rng.integers(10, L - 10))
+            cigar = [(0, a), (3, int(rng.integers(50, 5000))), (0, L - a)]
+        elif k == 2:
+            s = int(rng.integers(1, 20))
+            cigar = [(4, s), (0, L - s)]
+        elif k == 3:
+            a = int(rng.integers(10, L - 10))
+            cigar = [(0, a), (2, int(rng.integers(1, 4))), (0, L - a)]
+        else:
+            a = int(rng.integers(10, L - 10))
+            ins = int(rng.integers(1, 4))
+            cigar = [(0, a), (1, ins), (0, L - a - ins)]
+        n_ref = sum(n for op, n in cigar if op in (0, 2))
+        ref = rng.integers(0, 4, n_ref)
+        qual = np.where(rng.random(L) < 0.9, rng.integers(36, 41, L), rng.integers(2, 28, L))
+        seq = []
+        md = []
+        run = 0
+        ri = 0
+        nm = 0
+        strand_rev = gene_strand[gene_id[i]] == 1
+        conv_from, conv_to = (0, 2) if strand_rev else (3, 1)   # A>G on reverse-strand genes, T>C on forward
+        for op, n in cigar:
+            if op == 0:
+                for _ in range(n):
+                    g = int(ref[ri])
+                    ri += 1
+                    b = g
+                    if labelled[i] and g == conv_from and rng.random() < p_c:
+                        b = conv_to
+                    u = rng.random()
+                    if u < 3 * p_e:
+                        b = (g + 1 + int(u / p_e)) % 4
+                    if rng.random() < frac_n:
+                        seq.append('N')
+                        md.append(str(run))
+                        md.append('ACGT'[g])
+                        run = 0
+                        nm += 1
+                        continue
+                    seq.append('ACGT'[b])
+                    if b == g:
+                        run += 1
+                    else:
+                        md.append(str(run))
+                        md.append('ACGT'[g])
+                        run = 0
+                        nm += 1
+            elif op == 2:
+                md.append(str(run))
+                run = 0
+                md.append('^' + ''.join('ACGT'[int(x)] for x in ref[ri:ri + n]))
+                ri += n
+            elif op in (1, 4):
+                seq.extend('ACGT'[int(x)] for x in rng.integers(0, 4, n))
+        md.append(str(run))
+        flag = 16 if rng.random() < 0.5 else 0
+        score[i] = L - 2 * nm
+        units.append([records.pack_one(int(pos[i]), int(gene_contig[gene_id[i]]), flag, cigar, ''.join(seq), qual, ''.join(md))])
+    blob, rec_off = records.pack_units(units)
+    return dict(
+        blob=blob,
+        rec_off=rec_off,
+        barcode_id=barcode_id,
+        umi=umi,
+        gene_id=gene_id,
+        score=score,
+        gene_strand=gene_strand.astype(np.uint8),
+        labelled=labelled,
+    )

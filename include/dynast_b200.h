@@ -1,0 +1,153 @@
+/* dynast_b200 -- C-ABI of the B200-native count -> estimate hot path.
+ *
+ * dynast (the reference) has no FFI layer: its boundary is the Python operator API
+ * (dynast/preprocessing/__init__.py:2-31, dynast/estimation/__init__.py:2-10).  The functions below are
+ * what those operators bind to in this build (ctypes); every entry point names the
+ * reference function whose inner loop it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - pointers named d_* are DEVICE pointers (any allocator: cudaMalloc, torch, ...), h_* are HOST
+ *     pointers (pinned for best throughput).  The caller owns every buffer.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer entry
+ *     points are asynchronous on that stream; host-pointer entry points synchronise before returning.
+ *   - return value: 0 = ok, negative = error (dyn_last_error() returns a thread-local message).
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef DYNAST_B200_H
+#define DYNAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYN_OK 0
+#define DYN_ERR_CUDA (-1)
+#define DYN_ERR_ARG (-2)
+#define DYN_ERR_NOMEM (-3)
+#define DYN_ERR_FORMAT (-4)
+#define DYN_ERR_IO (-5)
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed read records (what the host BAM decoder writes into pinned memory and the tally reads).
+ *
+ * Read i occupies bytes [16*rec_off[i], 16*rec_off[i+1]) of the record blob:
+ *     dyn_read_hdr_t hdr;                      16 bytes
+ *     uint32_t cigar[n_cigar];                 BAM encoding: len << 4 | op   (MIDNSHP=X -> 0..8)
+ *     uint8_t  seq[(l_seq + 1) / 2];           BAM 4-bit codes "=ACMGRSVTWYHKDBN", high nibble first;
+ *                                              zero-padded to a multiple of 4 bytes
+ *     uint8_t  qual[l_seq];                    Phred
+ *     uint8_t  md[md_len];                     MD tag text, no terminator
+ *     zero padding to a multiple of 16 bytes
+ * If hdr.flag has DYN_REC_HAS_MATE, a second record (the first-seen mate of a read pair, same layout)
+ * follows inside the same [rec_off[i], rec_off[i+1]) range; the pair is one counting unit
+ * (bam.py:307-352).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t pos;      /* 0-based leftmost reference position (BAM pos) */
+    int32_t ref_id;   /* contig index in the BAM header */
+    uint16_t l_seq;   /* query length including soft clips */
+    uint16_t n_cigar;
+    uint16_t md_len;
+    uint16_t flag;    /* BAM flag bits 0..11 | DYN_REC_* */
+} dyn_read_hdr_t;
+
+#define DYN_REC_HAS_MATE 0x8000u
+
+/* Conversion record codes: (ref nibble << 4) | read nibble, both BAM 4-bit codes (A=1,C=2,G=4,T=8).
+ * One 64-bit record per mismatch: bits 0..31 genome_i (0-based), 32..39 code, 40..47 Phred,
+ * 48..63 reserved (0). */
+#define DYN_CONV_POS(rec) ((uint32_t)((rec) & 0xffffffffu))
+#define DYN_CONV_CODE(rec) ((uint8_t)(((rec) >> 32) & 0xff))
+#define DYN_CONV_QUAL(rec) ((uint8_t)(((rec) >> 40) & 0xff))
+
+/* Column order of the 16 per-read counters == conversion.py:44-63 (CONVERSION_IDX, BASE_IDX):
+ * AC AG AT CA CG CT GA GC GT TA TC TG A C G T */
+#define DYN_N_COUNTERS 16
+
+/* tally flags */
+#define DYN_TALLY_NASC 0x1u        /* --nasc: drop mate conversions inside the pair overlap (bam.py:339,396) */
+#define DYN_TALLY_EMIT_CONV 0x2u   /* also emit the per-mismatch records (conversions.csv rows) */
+
+/* status bits accumulated in *d_status by the tally (0 == clean) */
+#define DYN_ST_COUNTER_OVERFLOW 0x1u /* a counter exceeded 255: the reference raises when re-reading uint8 */
+#define DYN_ST_BAD_RECORD 0x2u       /* CIGAR / MD / seq disagree (pysam would raise) */
+#define DYN_ST_NON_ACGT_CONV 0x4u    /* a quality-passing mismatch involves an IUPAC code (reference: KeyError) */
+#define DYN_ST_CONV_CAPACITY 0x8u    /* conversion-record capacity exceeded */
+
+typedef struct dyn_ctx dyn_ctx_t;
+
+const char *dyn_last_error(void);
+int dyn_version(void);
+
+/* One context per GPU (per process). Owns scratch buffers and an internal stream pool. */
+int dyn_ctx_create(int device, dyn_ctx_t **ctx);
+int dyn_ctx_destroy(dyn_ctx_t *ctx);
+int dyn_ctx_sm_count(dyn_ctx_t *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1 + a3: per-read conversion tally.
+ * Replaces the inner loops of bam.parse_read_contig (bam.py:357-429: CIGAR/MD walk, reference base
+ * content, mismatch extraction) and conversion.count_conversions_part (conversion.py:403-432: quality
+ * and SNP filter, 12 conversion + 4 content counters).
+ *
+ *   d_records, d_rec_off      packed records (see above); rec_off has n_reads + 1 entries
+ *   d_snps, n_snps            sorted unique uint64 keys (conv_idx << 56 | ref_id << 32 | genome_i) of
+ *                             positions to ignore per conversion (conversion.py:395-398); may be NULL/0
+ *   quality                   count a mismatch only if Phred > quality (strict, conversion.py:424)
+ *   d_counts [n_reads][16] u8 output counters, column order above
+ *   d_conv_off [n_reads] u32, d_conv_n [n_reads] u16
+ *                             where read i's conversion records live in d_conv_rec / how many
+ *                             (all mismatches, NOT quality filtered: conversions.csv semantics, bam.py:405-419)
+ *   d_conv_rec [conv_capacity] u64, d_conv_read [conv_capacity] u32
+ *                             records and their owning read index; within a read in walk order
+ *   d_conv_total              u64: number of records written (device scalar)
+ *   d_status                  u32: DYN_ST_* bits (device scalar, OR-accumulated; caller zeroes)
+ * The conv outputs may be NULL when DYN_TALLY_EMIT_CONV is not set.
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_rec_off, int64_t n_reads,
+                    const uint64_t *d_snps, int64_t n_snps, int quality, uint32_t flags, uint8_t *d_counts,
+                    uint32_t *d_conv_off, uint16_t *d_conv_n, uint64_t *d_conv_rec, uint32_t *d_conv_read,
+                    int64_t conv_capacity, uint64_t *d_conv_total, uint32_t *d_status, void *stream);
+
+/* Host-buffer form of the same call (the end-to-end path): records are streamed from pinned host
+ * memory in chunks with cudaMemcpyAsync on two streams, results are copied back.  All pointers are
+ * host pointers; h_conv_* may be NULL. Returns after everything has landed. */
+int dyn_tally_reads_host(dyn_ctx_t *ctx, const void *h_records, const uint32_t *h_rec_off, int64_t n_reads,
+                         const uint64_t *h_snps, int64_t n_snps, int quality, uint32_t flags, uint8_t *h_counts,
+                         uint32_t *h_conv_off, uint16_t *h_conv_n, uint64_t *h_conv_rec, uint32_t *h_conv_read,
+                         int64_t conv_capacity, uint64_t *h_conv_total, uint32_t *h_status);
+
+/* ------------------------------------------------------------------------------------------------
+ * a12-a14: per-barcode binomial-mixture EM for p_c.
+ * Replaces p_c.expectation_maximization / expectation_maximization_nasc (p_c.py:49-172) as driven per
+ * barcode by estimate_p_c (p_c.py:206-227).
+ *
+ * Barcode b owns histogram triplets [d_off[b], d_off[b+1]) of (k = conversions, n = base content,
+ * count = reads); duplicate (k, n) are summed (csr_matrix semantics, p_c.py:219).
+ *   d_p_e [B] f64   background rate per barcode
+ *   nasc            0: expectation_maximization, 1: expectation_maximization_nasc
+ *   d_p_c [B] f64   result; d_em_status [B] i32: 0 ok, 1 'p_c <= p_e' (p_c.py:169), 2 arithmetic
+ *                   failure inside the reference (ZeroDivisionError), 3 shape not supported
+ *   d_iters [B] i32 iterations used (may be NULL)
+ * ------------------------------------------------------------------------------------------------ */
+#define DYN_EM_OK 0
+#define DYN_EM_PC_LE_PE 1
+#define DYN_EM_ZERODIV 2
+#define DYN_EM_UNSUPPORTED 3
+
+int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n, const int64_t *d_count, const int64_t *d_off,
+              int64_t n_barcodes, const double *d_p_e, int nasc, double *d_p_c, int32_t *d_em_status,
+              int32_t *d_iters, void *stream);
+
+int dyn_em_pc_host(dyn_ctx_t *ctx, const int32_t *h_k, const int32_t *h_n, const int64_t *h_count,
+                   const int64_t *h_off, int64_t n_barcodes, const double *h_p_e, int nasc, double *h_p_c,
+                   int32_t *h_em_status, int32_t *h_iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNAST_B200_H */

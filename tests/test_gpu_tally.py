@@ -1,0 +1,86 @@
+"""GPU: the CUDA tally (through the C-ABI, host-buffer form) is bit-exact against the C oracle and the
+reference fixtures."""
+import numpy as np
+import pytest
+
+from helpers import ref_path, ref_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(gpu, orc):
+    assert gpu['status'] == orc['status']
+    assert (gpu['counts'] == orc['counts']).all()
+    assert gpu['total'] == orc['total']
+    assert (gpu['conv_n'] == orc['conv_n']).all()
+    # placement of a read's records is not part of the contract (one atomic per tile); content is
+    for name in ('conv_rec', 'conv_read'):
+        g = np.concatenate([gpu[name][o:o + n] for o, n in zip(gpu['conv_off'], gpu['conv_n'])]) if gpu['total'] else gpu[name]
+        r = np.concatenate([orc[name][o:o + n] for o, n in zip(orc['conv_off'], orc['conv_n'])]) if orc['total'] else orc[name]
+        assert (g == r).all()
+
+
+@pytest.mark.parametrize('align,kw', [
+    ('SRR11683995_align', dict(umi_tag='UB', barcode_tag='CB', velocity=True)),
+])
+def test_fixture_bam_single_end(gpu_ctx, oracle_lib, align, kw):
+    from oracle import pack
+    from dynast_b200 import device, records as rec
+    blob, off, meta, refs = pack.units_from_bam(ref_path(align, 'Aligned.sortedByCoord.out.bam'), rec.pack_one,
+                                                rec.pack_units, **kw)
+    orc = pack.run_tally(blob, off, quality=27)
+    gpu = device.tally_reads_host(blob, off, quality=27)
+    _compare(gpu, orc)
+    # and against the fixture CSV directly
+    ali = {(r['read_id'], int(r['index'])): r for r in ref_rows('SRR11683995_count', 'alignments.csv')}
+    hit = 0
+    for i, m in enumerate(meta):
+        row = ali.get((m['read_id'], m['index']))
+        if row:
+            hit += 1
+            assert [int(row[b]) for b in 'ACGT'] == [int(x) for x in gpu['counts'][i, 12:16]]
+    assert hit == 250
+
+
+@pytest.mark.parametrize('n_reads,seed', [(1, 3), (31, 4), (257, 5), (20000, 6)])
+def test_synthetic_vs_oracle(gpu_ctx, oracle_lib, n_reads, seed):
+    from oracle import pack
+    from dynast_b200 import device, synth
+    d = synth.make_reads(n_reads, seed=seed)
+    for quality in (27, 0, 41):
+        orc = pack.run_tally(d['blob'], d['rec_off'], quality=quality)
+        gpu = device.tally_reads_host(d['blob'], d['rec_off'], quality=quality)
+        _compare(gpu, orc)
+
+
+def test_snp_filter(gpu_ctx, oracle_lib):
+    from oracle import pack
+    from dynast_b200 import device, records as rec, synth
+    d = synth.make_reads(5000, seed=11)
+    base = pack.run_tally(d['blob'], d['rec_off'], quality=27)
+    # declare every 3rd observed TC / AG mismatch position a SNP
+    pos, refl, readl, q = rec.decode_conv(base['conv_rec'])
+    hdr = d['blob'].view(np.uint8)
+    ref_ids = np.array([int(np.frombuffer(d['blob'][int(o) * 16 + 4:int(o) * 16 + 8].tobytes(), '<i4')[0])
+                        for o in d['rec_off'][:-1]])
+    keys = []
+    for j in range(0, len(pos), 3):
+        conv = refl[j] + readl[j]
+        if conv in rec.CONVERSION_COLUMNS:
+            keys.append((rec.CONVERSION_COLUMNS.index(conv) << 56) | (int(ref_ids[base['conv_read'][j]]) << 32) | int(pos[j]))
+    snps = np.unique(np.asarray(keys, dtype=np.uint64))
+    orc = pack.run_tally(d['blob'], d['rec_off'], quality=27, snps=snps)
+    gpu = device.tally_reads_host(d['blob'], d['rec_off'], quality=27, snps=snps)
+    assert orc['counts'][:, :12].sum() < base['counts'][:, :12].sum()
+    _compare(gpu, orc)
+
+
+def test_no_emit_and_empty(gpu_ctx, oracle_lib):
+    from oracle import pack
+    from dynast_b200 import device, synth
+    d = synth.make_reads(3000, seed=12)
+    orc = pack.run_tally(d['blob'], d['rec_off'])
+    gpu = device.tally_reads_host(d['blob'], d['rec_off'], emit_conv=False)
+    assert (gpu['counts'] == orc['counts']).all()
+    empty = device.tally_reads_host(np.zeros(0, np.uint8), np.zeros(1, np.uint32))
+    assert empty['counts'].shape == (0, 16) and empty['total'] == 0
