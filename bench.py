@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the count -> estimate hot path (contract: see the task statement / DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the device hot path over one batch of synthetic reads of BASELINE config C2
+(50 M single-end 91-nt reads, 10 k barcodes, TC conversions) per GPU.  `value` is reads/s with the
+packed records resident in HBM; `e2e` is the same work through the host-buffer C-ABI call
+(dyn_tally_reads_host: pinned host records -> H2D -> kernels -> D2H).  The p_c EM (config C4:
+1e5 barcodes x (k<=30, n<=150) histograms) is timed separately and reported under "em".
+For N > 1 launch with torchrun; every rank runs its own read range (weak scaling), rank 0 prints.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import numpy as np  # noqa: E402
+
+METRIC = 'aligned reads/s conversion counting; barcodes/s p_c EM'
+UNIT = 'reads/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--reads', type=int, default=50_000_000, help='reads per GPU (C2: 50 M)')
+    ap.add_argument('--barcodes', type=int, default=10_000)
+    ap.add_argument('--em-barcodes', type=int, default=100_000, help='C4: 1e5 barcodes (whole job)')
+    ap.add_argument('--cpu-sample-reads', type=int, default=8_000_000)
+    ap.add_argument('--cpu-sample-barcodes', type=int, default=4000)
+    ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-em', action='store_true')
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i',
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def build_em_batch_gpu(n_barcodes, seed, device):
+    """C4 histograms generated on the device with torch (setup, untimed). Returns CSR triplets."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    ks, ns, cs, offs = [], [], [], [0]
+    pes = rng.uniform(2e-4, 2e-3, n_barcodes)
+    chunk = 2000
+    for b0 in range(0, n_barcodes, chunk):
+        b1 = min(n_barcodes, b0 + chunk)
+        nb = b1 - b0
+        R = np.maximum(1000, rng.lognormal(np.log(3000), 0.5, nb).astype(np.int64))
+        pi = torch.from_numpy(rng.beta(2, 5, nb)).to(device)
+        pcb = torch.from_numpy(rng.uniform(0.02, 0.08, nb)).to(device)
+        peb = torch.from_numpy(pes[b0:b1]).to(device)
+        bid = torch.repeat_interleave(torch.arange(nb, device=device), torch.from_numpy(R).to(device))
+        n = torch.poisson(torch.full((bid.numel(),), 23.0, device=device), generator=g).clamp_(0, 150)
+        lab = torch.rand(bid.numel(), device=device, generator=g) < pi[bid]
+        p = torch.where(lab, pcb[bid], peb[bid])
+        k = torch.binomial(n.double(), p, generator=g).clamp_(0, 30).long()
+        n = n.long()
+        # adversarial 1 %: force one read to touch k = 30, n = 150 (int64-wrap region of the coefficient)
+        first = torch.cumsum(torch.from_numpy(R).to(device), 0) - torch.from_numpy(R).to(device)
+        adv = first[torch.arange(0, nb, 100, device=device)]
+        k[adv] = 30
+        n[adv] = 150
+        key = (bid * 31 + k) * 151 + n
+        uk, cnt = torch.unique(key, return_counts=True)
+        ub = uk // (31 * 151)
+        ks.append(((uk // 151) % 31).int())
+        ns.append((uk % 151).int())
+        cs.append(cnt.long())
+        per = torch.bincount(ub, minlength=nb).cpu().numpy()
+        for x in per:
+            offs.append(offs[-1] + int(x))
+    return (torch.cat(ks), torch.cat(ns), torch.cat(cs), torch.tensor(offs, dtype=torch.int64, device=device),
+            torch.from_numpy(pes).to(device))
+
+
+def cpu_tally_baseline(blob, rec_off, n_threads):
+    """C oracle (oracle/tally_oracle.c) over the host sample, split across threads (ctypes drops the GIL)."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle
+    lib = oracle.lib()
+    n = len(rec_off) - 1
+    counts = np.zeros((n, 16), dtype=np.uint8)
+    bounds = np.linspace(0, n, n_threads + 1).astype(np.int64)
+
+    def work(i):
+        st = C.c_uint32(0)
+        lib.dyn_oracle_tally(blob.ctypes.data, rec_off.ctypes.data, int(bounds[i]), int(bounds[i + 1]), None, 0, 27, 0,
+                             counts.ctypes.data, None, None, None, None, 0, None, C.byref(st))
+        return st.value
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as ex:
+        list(ex.map(work, range(n_threads)))
+    dt = time.perf_counter() - t0
+    return n / dt, counts
+
+
+def cpu_em_baseline(k, n, c, off, pe, n_threads):
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle
+    from helpers import oracle_em_batch
+    lib = oracle.lib()
+    B = len(off) - 1
+    bounds = np.linspace(0, B, n_threads + 1).astype(np.int64)
+
+    def work(i):
+        a, b = int(bounds[i]), int(bounds[i + 1])
+        o = off[a:b + 1] - off[a]
+        return oracle_em_batch(lib, k[off[a]:off[b]], n[off[a]:off[b]], c[off[a]:off[b]], o, pe[a:b])
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as ex:
+        res = list(ex.map(work, range(n_threads)))
+    dt = time.perf_counter() - t0
+    return B / dt, np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+
+
+def main():
+    args = parse_args()
+    import torch
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference' and rank != 0:
+        return 0
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device; dynast_b200 has no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1 and args.impl != 'reference':
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+
+    from dynast_b200 import pipeline
+    from dynast_b200._lib import Context
+    ctx = Context.get(local_rank)
+    n_cores = os.cpu_count() or 1
+    n_reads = args.reads
+    config = {
+        'workload': 'C2 synthetic scSLAM-seq-like 10x BAM records: 50M reads x 91 nt, 10k barcodes, TC, per GPU',
+        'reads_per_gpu': n_reads, 'barcodes_per_gpu': args.barcodes, 'read_len': 91, 'quality': 27,
+        'l2_policy': 'inputs (~8.8 GB packed records per step) are far larger than the 126 MB L2',
+        'parallelism': f'read-range x{world}',
+    }
+
+    # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
+    if args.impl == 'reference':
+        sample = min(n_reads, args.cpu_sample_reads)
+        batch = pipeline.SynthBatch(sample, seed=2001, n_barcodes=args.barcodes, device=local_rank, with_keys=False)
+        blob = batch.records.cpu().numpy()
+        rec_off = batch.rec_off.cpu().numpy().view(np.uint32)
+        del batch
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, _ = cpu_tally_baseline(blob, rec_off, n_cores)
+            if i >= args.warmup:
+                vals.append(v)
+        value = float(np.mean(vals))
+        line = {
+            'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sample / value,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'config': config,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': n_cores, 'kind': 'port',
+                             'sample': f'{sample} reads of the C2 workload per step; C restatement of the reference '
+                                       'tally (oracle/tally_oracle.c) on all host threads; the reference itself is '
+                                       'CPython + pysam and cannot run on this box'},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- workload (setup, untimed)
+    batch = pipeline.SynthBatch(n_reads, seed=2001 + rank, n_barcodes=args.barcodes, device=local_rank,
+                                barcode_base=rank * args.barcodes)
+    conv_cap = int(n_reads * 1.5) + 1024
+    out = pipeline.TallyBuffers(n_reads, conv_cap, device=local_rank)
+    alg_in = batch.algorithmic_input_bytes()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        pipeline.tally_reads(ctx, batch.records, batch.rec_off, out, quality=27, emit_conv=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    n_conv = int(out.scalars[0].item())
+    status = int(out.scalars[1].item()) & 0xffffffff
+    assert status == 0, f'tally status {status}'
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t_mark0 = sampler.mark()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    t_mark1 = sampler.mark()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if dist is not None:
+        t = torch.tensor([total_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n_reads / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (tally): algorithmic bytes / mean launch duration (CUDA events on
+    # the launching stream; the step is that one kernel plus an 32-byte memset)
+    alg_out = n_reads * (16 + 4 + 2) + n_conv * 12
+    alg_bytes = alg_in + alg_out
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (np.mean(kernel_ms) * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'kernel': 'tally_kernel', 'peak_source': peak_src,
+                'algorithmic_bytes_per_read': alg_bytes / n_reads}
+
+    # ---------------------------------------------------------------- e2e through the host-buffer C-ABI
+    e2e = None
+    if not args.skip_e2e:
+        import ctypes as C
+        from dynast_b200._lib import check, ptr
+        h_rec = batch.records.cpu().pin_memory()
+        h_off = batch.rec_off.cpu().pin_memory()
+        h_counts = torch.empty((n_reads, 16), dtype=torch.uint8).pin_memory()
+        h_conv_off = torch.empty(n_reads, dtype=torch.int32).pin_memory()
+        h_conv_n = torch.empty(n_reads, dtype=torch.int16).pin_memory()
+        h_conv_rec = torch.empty(conv_cap, dtype=torch.int64).pin_memory()
+        h_conv_read = torch.empty(conv_cap, dtype=torch.int32).pin_memory()
+        tot, st = C.c_uint64(0), C.c_uint32(0)
+
+        def e2e_step():
+            check(ctx.lib.dyn_tally_reads_host(
+                ctx.handle, ptr(h_rec), ptr(h_off), n_reads, None, 0, 27, pipeline.TALLY_EMIT_CONV, ptr(h_counts),
+                ptr(h_conv_off), ptr(h_conv_n), ptr(h_conv_rec), ptr(h_conv_read), conv_cap,
+                C.cast(C.byref(tot), C.c_void_p), C.cast(C.byref(st), C.c_void_p)))
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if dist is not None:
+            t = torch.tensor([dt], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert st.value == 0 and tot.value == n_conv
+        assert torch.equal(h_counts[:100000], out.counts[:100000].cpu())
+        e2e = {'value': world * n_reads / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(batch.n_bytes + 4 * (n_reads + 1)),
+               'd2h_bytes_per_step': int(n_reads * 22 + n_conv * 12 + 12), 'ms_per_step': dt * 1e3,
+               'timing': 'host perf_counter around the blocking C-ABI call, device synchronised on both sides'}
+        del h_rec, h_counts, h_conv_rec, h_conv_read
+
+    # ---------------------------------------------------------------- p_c EM (C4), barcodes split over ranks
+    em = None
+    if not args.skip_em:
+        nb = args.em_barcodes // world
+        k, n, c, off, pe = build_em_batch_gpu(nb, 2004 + rank, device)
+        for _ in range(2):
+            p_c, st_em, iters = pipeline.em_pc(ctx, k, n, c, off, pe)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record(stream)
+        for _ in range(reps):
+            p_c, st_em, iters = pipeline.em_pc(ctx, k, n, c, off, pe)
+        e1.record(stream)
+        barrier()
+        em_ms = e0.elapsed_time(e1) / reps
+        if dist is not None:
+            t = torch.tensor([em_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            em_ms = float(t.item())
+        em = {'metric': 'barcodes/s p_c EM', 'value': world * nb / (em_ms * 1e-3), 'unit': 'barcodes/s',
+              'barcodes': world * nb, 'ms': em_ms, 'ok_fraction': float((st_em == 0).float().mean().item()),
+              'mean_iters': float(iters.float().mean().item()), 'workload': 'C4: k<=30, n<=150, 1% adversarial full shape',
+              'dtype': 'f64 E step / f32 M step (as the reference)'}
+
+    # ---------------------------------------------------------------- CPU baseline beside it (rank 0, N = 1)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        sample = min(n_reads, args.cpu_sample_reads)
+        hi = int(batch.rec_off[sample].item()) & 0xffffffff
+        blob = batch.records[:hi * 16].cpu().numpy()
+        rec_off = batch.rec_off[:sample + 1].cpu().numpy().view(np.uint32)
+        v, cpu_counts = cpu_tally_baseline(blob, rec_off, n_cores)
+        same = bool((cpu_counts == out.counts[:sample].cpu().numpy()).all())
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': n_cores, 'kind': 'port',
+                        'sample': f'first {sample} reads of the same batch, C restatement of the reference tally '
+                                  f'(oracle/tally_oracle.c), {n_cores} threads; counters identical to the GPU: {same}'}
+        if em is not None:
+            sb = min(nb, args.cpu_sample_barcodes)
+            o = off[:sb + 1].cpu().numpy()
+            ve, cp, cs = cpu_em_baseline(k[:o[-1]].cpu().numpy(), n[:o[-1]].cpu().numpy(), c[:o[-1]].cpu().numpy(), o,
+                                         pe[:sb].cpu().numpy(), n_cores)
+            g_pc, g_st = p_c[:sb].cpu().numpy(), st_em[:sb].cpu().numpy()
+            okm = cs == 0
+            em['cpu_baseline'] = {'value': ve, 'unit': 'barcodes/s', 'cores': n_cores, 'kind': 'port',
+                                  'sample': f'{sb} barcodes, oracle/em_oracle.c',
+                                  'status_equal': bool((cs == g_st).all()),
+                                  'bit_exact': bool((cp[okm] == g_pc[okm]).all())}
+    sampler.stop()
+    clocks = sampler.summary(t_mark0, t_mark1)
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config, 'gpu_launches': args.steps,
+            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'em': em, 'clocks': clocks,
+            'conversions_per_read': n_conv / n_reads,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -26,6 +26,8 @@ PROTOTYPES = {
         (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'dyn_em_pc': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     'dyn_em_pc_host': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+    'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    'dyn_synth_fill': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -82,6 +84,16 @@ class Context:
             self.lib.dyn_ctx_destroy(self.handle)
             self.handle = None
         Context._cache.pop(self.device, None)
+
+
+class SynthParams(C.Structure):
+    """dyn_synth_params_t"""
+    _fields_ = [
+        ('seed', C.c_uint64), ('read_len', C.c_int32), ('n_barcodes', C.c_int32), ('n_genes', C.c_int32),
+        ('umi_len', C.c_int32), ('n_groups', C.c_int64), ('pos_span', C.c_int64), ('p_c', C.c_double),
+        ('p_e', C.c_double), ('frac_n', C.c_double), ('d_bc_cdf', C.c_void_p), ('d_gene_cdf', C.c_void_p),
+        ('d_gene_pi', C.c_void_p), ('d_gene_strand', C.c_void_p), ('d_gene_contig', C.c_void_p),
+    ]
 
 
 def ptr(arr):

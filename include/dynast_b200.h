@@ -147,6 +147,35 @@ int dyn_em_pc_host(dyn_ctx_t *ctx, const int32_t *h_k, const int32_t *h_n, const
                    const int64_t *h_off, int64_t n_barcodes, const double *h_p_e, int nasc, double *h_p_c,
                    int32_t *h_em_status, int32_t *h_iters);
 
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic input generator (bench / test utility; not on the timed path). Generates packed records
+ * for the BASELINE configs directly in HBM; every decision is a pure function of (seed, read index).
+ * Model: SURVEY.md section 8d (C2) after dynast/benchmarking/simulation.py:22-79.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t seed;
+    int32_t read_len;       /* 30..304 */
+    int32_t n_barcodes;
+    int32_t n_genes;
+    int32_t umi_len;        /* nt, 2 bits each in the u64 UMI key */
+    int64_t n_groups;       /* number of (barcode, gene, UMI) groups reads are drawn from */
+    int64_t pos_span;       /* reference span over which reads are laid out in order (0: 2^27) */
+    double p_c, p_e, frac_n;
+    const float *d_bc_cdf;        /* [n_barcodes] cumulative sampling weights */
+    const float *d_gene_cdf;      /* [n_genes] */
+    const float *d_gene_pi;       /* [n_genes] labelled fraction */
+    const uint8_t *d_gene_strand; /* [n_genes] 0 '+', 1 '-' */
+    const int32_t *d_gene_contig; /* [n_genes] */
+} dyn_synth_params_t;
+
+/* d_rec_off[0..n_reads] (16-byte units); the blob needs 16 * d_rec_off[n_reads] bytes. */
+int dyn_synth_offsets(dyn_ctx_t *ctx, const dyn_synth_params_t *params, int64_t n_reads, uint32_t *d_rec_off,
+                      void *stream);
+/* Writes the records and per-read keys (any key pointer may be NULL). */
+int dyn_synth_fill(dyn_ctx_t *ctx, const dyn_synth_params_t *params, int64_t n_reads, const uint32_t *d_rec_off,
+                   void *d_records, uint32_t *d_barcode, uint64_t *d_umi, uint32_t *d_gene, int32_t *d_score,
+                   uint8_t *d_strand, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
