@@ -11,7 +11,9 @@
 //   * the tile's bytes are one contiguous range of the record blob, fetched by ONE TMA 1-D bulk copy
 //     (cp.async.bulk -> UBLKCP) into shared memory and awaited on an mbarrier; 4 CTAs share an SM so
 //     while one CTA waits for its tile the others walk theirs (multi-buffering across CTAs);
-//   * match runs are counted 8 bases per 32-bit word with nibble one-hot masks + popc instead of per base;
+//   * base content = one fixed-trip pass over the whole query, 8 bases per 32-bit word with nibble one-hot
+//     bit planes (no popc, no masks), corrected per MD mismatch / deletion / clipped base, so lanes only
+//     diverge on the number of MD tokens;
 //   * counters leave as one 128-bit store per read (consecutive threads -> consecutive 16 B: coalesced);
 //   * mismatch records are placed with one global atomic per CTA tile (block scan of per-read counts),
 //     then written by a second, cheaper walk over the same shared-memory bytes.
@@ -57,26 +59,6 @@ struct Counters {
 
 __device__ __forceinline__ bool is_digit(uint32_t c) { return (c - '0') <= 9u; }
 
-// Count A/C/G/T among read bases [a, b) of a BAM nibble-packed sequence (4-byte aligned words).
-__device__ __forceinline__ void count_run(const uint32_t *seqw, int a, int b, Counters &cn) {
-    int w_first = a >> 3, w_last = (b - 1) >> 3;
-    for (int w = w_first; w <= w_last; ++w) {
-        uint32_t x = seqw[w];
-        // BAM stores the even base in the high nibble: swap nibbles so base i sits at bits 4*(i&7)
-        x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
-        int lo = max(a - (w << 3), 0), hi = min(b - (w << 3), 8);
-        uint32_t mask = (hi == 8 ? 0xffffffffu : ((1u << (4 * hi)) - 1u)) & ~((1u << (4 * lo)) - 1u);
-        uint32_t b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u,
-                 b3 = (x >> 3) & 0x11111111u;
-        uint32_t s = b0 + b1 + b2 + b3;                       // bits set per nibble (0..4)
-        uint32_t onehot = s & ~(s >> 1) & ~(s >> 2) & mask;   // exactly one bit: A, C, G or T
-        cn.a += __popc(b0 & onehot);
-        cn.c += __popc(b1 & onehot);
-        cn.g += __popc(b2 & onehot);
-        cn.t += __popc(b3 & onehot);
-    }
-}
-
 __device__ __forceinline__ bool snp_lookup(const unsigned long long *snps, long long n, unsigned long long key) {
     long long lo = 0, hi = n;
     while (lo < hi) {
@@ -87,7 +69,36 @@ __device__ __forceinline__ bool snp_lookup(const unsigned long long *snps, long 
     return lo < n && __ldg(snps + lo) == key;
 }
 
+// Count A/C/G/T over the WHOLE query of a record: a fixed-trip loop (same trip count for every lane
+// of a warp when read lengths agree), no masks (the packer zero-pads the last word and code 0 is not a
+// base), no popc in the loop: one-hot bit planes are summed per nibble and folded every 15 words.
+__device__ __forceinline__ uint32_t fold_nibbles(uint32_t acc) {
+    acc = (acc & 0x0f0f0f0fu) + ((acc >> 4) & 0x0f0f0f0fu);
+    return (acc * 0x01010101u) >> 24;
+}
+
+__device__ __forceinline__ void count_query(const uint32_t *seqw, int l_seq, Counters &cn) {
+    const int n_words = (l_seq + 7) >> 3;
+    for (int w0 = 0; w0 < n_words; w0 += 15) {
+        uint32_t aa = 0, ac = 0, ag = 0, at = 0;
+        const int w1 = min(n_words, w0 + 15);
+        for (int w = w0; w < w1; ++w) {
+            const uint32_t x = seqw[w];
+            const uint32_t b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u,
+                           b3 = (x >> 3) & 0x11111111u;
+            const uint32_t s = b0 + b1 + b2 + b3;
+            const uint32_t onehot = s & ~(s >> 1) & ~(s >> 2);
+            aa += b0 & onehot; ac += b1 & onehot; ag += b2 & onehot; at += b3 & onehot;
+        }
+        cn.a += fold_nibbles(aa); cn.c += fold_nibbles(ac); cn.g += fold_nibbles(ag); cn.t += fold_nibbles(at);
+    }
+}
+
 // Walk one record. EMIT == false: fill `cn`. EMIT == true: write mismatch records to out_rec/out_read.
+//
+// Content = bases of the whole query (count_query) - bases under I/S ops + per-mismatch correction
+// (+reference base, -read base) + deleted reference bases: the common path has no per-run work, so
+// lanes only diverge on the number of MD tokens, not on run lengths.
 template <bool EMIT>
 __device__ __forceinline__ void walk_record(const uint8_t *rec, const TallyParams &p, Counters &cn,
                                             unsigned long long *out_rec, uint32_t *out_read, uint32_t read_idx) {
@@ -102,7 +113,11 @@ __device__ __forceinline__ void walk_record(const uint8_t *rec, const TallyParam
     const uint8_t *qual = seqb + ((((l_seq + 1) >> 1) + 3) & ~3);
     const uint8_t *md = qual + l_seq;
 
-    int qpos = 0, mdp = 0, md_run = 0;
+    if (!EMIT) count_query(seqw, l_seq, cn);
+    // signed corrections on top of count_query
+    int da = 0, dc = 0, dg = 0, dt = 0;
+
+    int qpos = 0, mdp = 0, run = 0;
     uint32_t emitted = 0;
     bool bad = false;
 
@@ -112,90 +127,100 @@ __device__ __forceinline__ void walk_record(const uint8_t *rec, const TallyParam
         int len = (int)(c >> 4);
         if (op == 0 || op == 7 || op == 8) {  // M, =, X
             if (qpos + len > l_seq) { bad = true; break; }
-            while (len > 0) {
-                if (md_run == 0) {
-                    if (mdp >= md_len) { bad = true; break; }
-                    uint32_t ch = md[mdp];
-                    if (is_digit(ch)) {
-                        int v = 0;
-                        while (mdp < md_len && is_digit(ch = md[mdp])) { v = v * 10 + (int)(ch - '0'); ++mdp; }
-                        md_run = v;
-                        continue;
-                    }
-                    if (ch == '^') { bad = true; break; }
-                    // mismatch: MD letter is the reference base
-                    const uint32_t rn = kLetterCode[ch & 31];
-                    const uint32_t qn = (seqb[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
-                    if (!EMIT) {
-                        cn.a += (rn == 1); cn.c += (rn == 2); cn.g += (rn == 4); cn.t += (rn == 8);
-                    }
-                    if (rn != 15 && qn != 15 && rn != qn) {   // bam.py:389-390, 405
-                        const uint32_t q = qual[qpos];
-                        if (EMIT) {
-                            out_rec[emitted] = (unsigned long long)(uint32_t)rpos |
-                                               ((unsigned long long)((rn << 4) | qn) << 32) |
-                                               ((unsigned long long)q << 40);
-                            out_read[emitted] = read_idx;
-                            ++emitted;
-                        } else {
-                            ++cn.n_conv;
-                            if ((int)q > p.quality) {         // conversion.py:424 (strict)
-                                const bool r1 = __popc(rn) == 1, q1 = __popc(qn) == 1;
-                                if (r1 && q1) {
-                                    const int r = __ffs(rn) - 1, d = __ffs(qn) - 1;
-                                    const int idx = r * 3 + (d > r ? d - 1 : d);
-                                    bool snp = false;
-                                    if (p.n_snps > 0)
-                                        snp = snp_lookup(p.snps, p.n_snps,
-                                                         ((unsigned long long)idx << 56) |
-                                                             ((unsigned long long)ref_id << 32) | (uint32_t)rpos);
-                                    if (!snp) {
-                                        const uint32_t sh = (idx & 3) << 3, wi = idx >> 2;
-                                        uint32_t cur = wi == 0 ? cn.w0 : (wi == 1 ? cn.w1 : cn.w2);
-                                        if (((cur >> sh) & 0xff) == 0xff) cn.status |= DYN_ST_COUNTER_OVERFLOW;
-                                        else {
-                                            const uint32_t inc = 1u << sh;
-                                            cn.w0 += wi == 0 ? inc : 0u;
-                                            cn.w1 += wi == 1 ? inc : 0u;
-                                            cn.w2 += wi == 2 ? inc : 0u;
-                                        }
+            for (;;) {
+                if (run >= len) { run -= len; qpos += len; rpos += len; break; }
+                qpos += run; rpos += run; len -= run; run = 0;
+                if (mdp >= md_len) { bad = true; break; }
+                uint32_t ch = md[mdp];
+                if (is_digit(ch)) {
+                    int v = 0;
+                    do { v = v * 10 + (int)(ch - '0'); ++mdp; } while (mdp < md_len && is_digit(ch = md[mdp]));
+                    run = v;
+                    if (v == 0 && mdp >= md_len) { bad = true; break; }
+                    continue;
+                }
+                if (ch == '^') { bad = true; break; }
+                // mismatch: the MD letter is the reference base
+                const uint32_t rn = kLetterCode[ch & 31];
+                const uint32_t qn = (seqb[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
+                if (!EMIT) {
+                    da += (int)(rn == 1) - (int)(qn == 1); dc += (int)(rn == 2) - (int)(qn == 2);
+                    dg += (int)(rn == 4) - (int)(qn == 4); dt += (int)(rn == 8) - (int)(qn == 8);
+                }
+                if (rn != 15 && qn != 15 && rn != qn) {   // bam.py:389-390, 405
+                    const uint32_t q = qual[qpos];
+                    if (EMIT) {
+                        out_rec[emitted] = (unsigned long long)(uint32_t)rpos |
+                                           ((unsigned long long)((rn << 4) | qn) << 32) |
+                                           ((unsigned long long)q << 40);
+                        out_read[emitted] = read_idx;
+                        ++emitted;
+                    } else {
+                        ++cn.n_conv;
+                        if ((int)q > p.quality) {         // conversion.py:424 (strict)
+                            const bool r1 = __popc(rn) == 1, q1 = __popc(qn) == 1;
+                            if (r1 && q1) {
+                                const int r = __ffs(rn) - 1, d = __ffs(qn) - 1;
+                                const int idx = r * 3 + (d > r ? d - 1 : d);
+                                bool snp = false;
+                                if (p.n_snps > 0)
+                                    snp = snp_lookup(p.snps, p.n_snps,
+                                                     ((unsigned long long)idx << 56) |
+                                                         ((unsigned long long)ref_id << 32) | (uint32_t)rpos);
+                                if (!snp) {
+                                    const uint32_t sh = (idx & 3) << 3, wi = idx >> 2;
+                                    uint32_t cur = wi == 0 ? cn.w0 : (wi == 1 ? cn.w1 : cn.w2);
+                                    if (((cur >> sh) & 0xff) == 0xff) cn.status |= DYN_ST_COUNTER_OVERFLOW;
+                                    else {
+                                        const uint32_t inc = 1u << sh;
+                                        cn.w0 += wi == 0 ? inc : 0u;
+                                        cn.w1 += wi == 1 ? inc : 0u;
+                                        cn.w2 += wi == 2 ? inc : 0u;
                                     }
-                                } else {
-                                    cn.status |= DYN_ST_NON_ACGT_CONV;
                                 }
+                            } else {
+                                cn.status |= DYN_ST_NON_ACGT_CONV;
                             }
                         }
                     }
-                    ++mdp; ++qpos; ++rpos; --len;
-                    continue;
                 }
-                const int t = min(md_run, len);
-                if (!EMIT) count_run(seqw, qpos, qpos + t, cn);
-                qpos += t; rpos += t; md_run -= t; len -= t;
+                ++mdp; ++qpos; ++rpos; --len;
             }
         } else if (op == 2) {  // D: "^" + deleted reference bases; they count toward content (bam.py:359-360)
-            if (md_run == 0 && mdp < md_len && is_digit(md[mdp])) {
+            if (run == 0 && mdp < md_len && is_digit(md[mdp])) {
                 uint32_t ch;
                 int v = 0;
                 while (mdp < md_len && is_digit(ch = md[mdp])) { v = v * 10 + (int)(ch - '0'); ++mdp; }
-                md_run = v;
+                run = v;
             }
-            if (md_run != 0 || mdp >= md_len || md[mdp] != '^' || mdp + 1 + len > md_len) { bad = true; break; }
+            if (run != 0 || mdp >= md_len || md[mdp] != '^' || mdp + 1 + len > md_len) { bad = true; break; }
             ++mdp;
-            for (int j = 0; j < len; ++j) {
-                const uint32_t rn = kLetterCode[md[mdp + j] & 31];
-                if (!EMIT) { cn.a += (rn == 1); cn.c += (rn == 2); cn.g += (rn == 4); cn.t += (rn == 8); }
+            if (!EMIT) {
+                for (int j = 0; j < len; ++j) {
+                    const uint32_t rn = kLetterCode[md[mdp + j] & 31];
+                    da += (rn == 1); dc += (rn == 2); dg += (rn == 4); dt += (rn == 8);
+                }
             }
             mdp += len;
             rpos += len;
         } else if (op == 3) {  // N
             rpos += len;
-        } else if (op == 1 || op == 4) {  // I, S
+        } else if (op == 1 || op == 4) {  // I, S: query bases that are not aligned -> take them back out
+            if (qpos + len > l_seq) { bad = true; break; }
+            if (!EMIT) {
+                for (int j = qpos; j < qpos + len; ++j) {
+                    const uint32_t qn = (seqb[j >> 1] >> ((~j & 1) << 2)) & 0xf;
+                    da -= (qn == 1); dc -= (qn == 2); dg -= (qn == 4); dt -= (qn == 8);
+                }
+            }
             qpos += len;
-            if (qpos > l_seq) bad = true;
         }  // H, P: nothing
     }
-    if (!EMIT && bad) cn.status |= DYN_ST_BAD_RECORD;
+    if (!EMIT) {
+        if (bad) cn.status |= DYN_ST_BAD_RECORD;
+        cn.a = (uint32_t)max((int)cn.a + da, 0); cn.c = (uint32_t)max((int)cn.c + dc, 0);
+        cn.g = (uint32_t)max((int)cn.g + dg, 0); cn.t = (uint32_t)max((int)cn.t + dt, 0);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 4) tally_kernel(const TallyParams p) {
