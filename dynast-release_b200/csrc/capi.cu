@@ -94,6 +94,10 @@ extern "C" int dyn_tally_reads_host(dyn_ctx_t *ctx, const void *h_records, const
     if (n_reads == 0) return DYN_OK;
     DYN_ARG(h_records && h_rec_off && h_counts, "null buffer");
     const bool emit = (flags & DYN_TALLY_EMIT_CONV) != 0;
+    if ((flags >> 16) == 0) {   // mean record size hint for the staging buffer (DYN_TALLY_REC16_HINT)
+        const uint64_t avg16 = ((uint64_t)(h_rec_off[n_reads] - h_rec_off[0]) + n_reads - 1) / (uint64_t)n_reads;
+        flags |= (uint32_t)std::min<uint64_t>(avg16, 0xffff) << 16;
+    }
     if (emit) DYN_ARG(h_conv_off && h_conv_n && h_conv_rec && h_conv_read && h_conv_total, "null conversion buffer");
     DYN_CUDA(cudaSetDevice(ctx->device));
 

@@ -1,35 +1,52 @@
 // Per-read conversion tally (SURVEY.md section 8 rows a1 + a3).
 //
 // Replaces the inner loops of
-//   dynast/preprocessing/bam.py:357-429        CIGAR/MD walk, reference base content, mismatch records
+//   dynast/preprocessing/bam.py:297-429        CIGAR/MD walk, reference base content, paired-overlap
+//                                              rules, mismatch records
 //   dynast/preprocessing/conversion.py:403-432 quality / SNP filter and the 12 + 4 counters
 // which in the reference run as CPython per-base loops plus a CSV round trip.
 //
 // Design (HBM-bound integer/byte work, no tensor cores):
-//   * one thread per read ("warp per read batch": a warp owns 32 consecutive reads), persistent CTAs,
-//     a tile = up to 256 consecutive packed records;
-//   * the tile's bytes are one contiguous range of the record blob, fetched by ONE TMA 1-D bulk copy
-//     (cp.async.bulk -> UBLKCP) into shared memory and awaited on an mbarrier; 4 CTAs share an SM so
-//     while one CTA waits for its tile the others walk theirs (multi-buffering across CTAs);
-//   * the walk is organised so that the lanes of a warp stay converged (the first version, a per-read
-//     CIGAR/MD state machine, ran with 5.7 of 32 lanes active):
+//   * one thread per counting unit ("warp per read batch": a warp owns 32 consecutive reads); a tile is
+//     kThreads consecutive packed records = ONE contiguous byte range of the record blob, fetched by one
+//     TMA 1-D bulk copy (cp.async.bulk -> UBLKCP) into shared memory and awaited on an mbarrier.
+//     CTAs are small (128 threads, ~40 KB) so five or six share an SM: while one waits for its tile
+//     the others walk theirs (multi-buffering across CTAs, no intra-CTA pipeline state);
+//   * the walk keeps the lanes of a warp converged (v1, a per-read CIGAR/MD state machine, ran with
+//     5.7 of 32 lanes active; v3, per-lane event loops, spent 45 % of its instructions at 3 lanes):
 //       1. base content of the WHOLE query in a fixed-trip loop, 8 bases per 32-bit word with nibble
 //          one-hot bit planes (no popc, no masks);
-//       2. a short CIGAR pre-scan (clipped / inserted bases are taken back out);
-//       3. the MD string is scanned one byte per iteration with a warp-uniform trip count; it only
-//          LOCATES events: (aligned offset, reference base) of each mismatch goes to a per-thread slot
-//          list in shared memory, deleted bases are added to the content on the spot;
-//       4. events are resolved (offset -> query/reference position through the CIGAR, read base,
-//          Phred, quality/SNP filter) in a second warp-uniform loop;
+//       2. CIGAR pre-scan and a one-byte-per-iteration MD scan with warp-uniform trip counts that only
+//          LOCATE work: each mismatch (aligned offset, reference base) and each clipped / inserted query
+//          range becomes an event in the read's slot list; deleted reference bases are added on the spot;
+//       3. the warp's events are compacted (warp scan) and resolved LANE-BALANCED -- lane i takes event
+//          i, whoever's read it belongs to: offset -> query/reference position through the CIGAR, read
+//          base, Phred, quality / SNP filter; results flow back to the owner through shared-memory
+//          atomics on that read's private accumulators, the finished 64-bit mismatch record replaces
+//          the event in its slot;
 //   * counters leave as one 128-bit store per read (consecutive threads -> consecutive 16 B: coalesced);
 //   * mismatch records are placed with one global atomic per CTA tile (block scan of per-read counts)
-//     and written by replaying the event slots -- the MD string is parsed once.
+//     and copied out of the slots -- the MD string is parsed once;
+//   * paired units (bam.py:307-352, 393-419), reads with more events than slots and records larger
+//     than the staging buffer take a sequential per-thread walker (slow_unit) -- same results, no
+//     attempt at convergence; the single-end fast path is what the bench times.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kEvSlots = 8;   // mismatch events kept per read in shared memory; more -> slow path
+#ifndef DYN_TALLY_THREADS
+#define DYN_TALLY_THREADS 128
+#endif
+#ifndef DYN_TALLY_SLOTS
+#define DYN_TALLY_SLOTS 8
+#endif
+#ifndef DYN_TALLY_MIN_CTAS
+#define DYN_TALLY_MIN_CTAS 5
+#endif
+constexpr int kThreads = DYN_TALLY_THREADS;
+constexpr int kWarps = kThreads / 32;
+constexpr int kEvSlots = DYN_TALLY_SLOTS;   // events kept per read in shared memory; more -> sequential walker
+constexpr unsigned long long kEvRange = 1ull << 63;
 
 struct TallyParams {
     const uint8_t *records;
@@ -55,7 +72,6 @@ struct TallyParams {
 //   @ A B C D E F G H I J K L M N O | P Q R S T U V W X Y Z
 //   0 1 14 2 13 0 0 4 11 0 0 12 0 3 15 0 | 0 0 5 6 8 0 7 9 0 10 0 ...
 __device__ __forceinline__ uint32_t letter_code(uint32_t ch) {
-    // entries 0..15 and 16..31 packed little-nibble-first
     const unsigned long long lo = (0ull) | (1ull << 4) | (14ull << 8) | (2ull << 12) | (13ull << 16) | (0ull << 20) |
                                   (0ull << 24) | (4ull << 28) | (11ull << 32) | (0ull << 36) | (0ull << 40) |
                                   (12ull << 44) | (0ull << 48) | (3ull << 52) | (15ull << 56) | (0ull << 60);
@@ -65,15 +81,6 @@ __device__ __forceinline__ uint32_t letter_code(uint32_t ch) {
     const unsigned long long t = (i & 16) ? hi : lo;
     return (uint32_t)(t >> ((i & 15) << 2)) & 0xf;
 }
-
-struct Acc {
-    int a, c, g, t;           // reference base content
-    uint32_t w0, w1, w2;      // 12 conversion counters, 8 bits each
-    uint32_t n_conv;          // every mismatch (conversions.csv rows), unfiltered
-    uint32_t status;
-};
-
-__device__ __forceinline__ bool is_digit(uint32_t c) { return (c - '0') <= 9u; }
 
 __device__ __forceinline__ bool snp_lookup(const unsigned long long *snps, long long n, unsigned long long key) {
     long long lo = 0, hi = n;
@@ -90,8 +97,20 @@ __device__ __forceinline__ uint32_t fold_nibbles(uint32_t acc) {
     return (acc * 0x01010101u) >> 24;
 }
 
+// one-hot BAM base code -> 0..3 (A C G T), anything else -> -1
+__device__ __forceinline__ int base_idx(uint32_t code) { return __popc(code) == 1 ? __ffs((int)code) - 1 : -1; }
+
+// column of conversion ref -> read in conversion.py:44-57 (alphabetical AC AG AT CA ...)
+__device__ __forceinline__ int conv_idx(int r, int d) { return r * 3 + (d > r ? d - 1 : d); }
+
+__device__ __forceinline__ size_t pad4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+__device__ __forceinline__ size_t record_need(uint32_t l_seq, uint32_t n_cigar, uint32_t md_len) {
+    return 16 + 4 * (size_t)n_cigar + pad4(((size_t)l_seq + 1) >> 1) + l_seq + md_len;
+}
+
 // A/C/G/T over the whole query: fixed-trip, no masks (the packer zero-pads, code 0 is not a base).
-__device__ __forceinline__ void count_query(const uint32_t *seqw, int l_seq, Acc &cn) {
+__device__ __forceinline__ void count_query(const uint32_t *seqw, int l_seq, int &ca, int &cc, int &cg, int &ct) {
     const int n_words = (l_seq + 7) >> 3;
     for (int w0 = 0; w0 < n_words; w0 += 15) {
         uint32_t aa = 0, ac = 0, ag = 0, at = 0;
@@ -105,13 +124,13 @@ __device__ __forceinline__ void count_query(const uint32_t *seqw, int l_seq, Acc
             const uint32_t onehot = s & ~(s >> 1) & ~(s >> 2);
             aa += b0 & onehot; ac += b1 & onehot; ag += b2 & onehot; at += b3 & onehot;
         }
-        cn.a += (int)fold_nibbles(aa); cn.c += (int)fold_nibbles(ac);
-        cn.g += (int)fold_nibbles(ag); cn.t += (int)fold_nibbles(at);
+        ca += (int)fold_nibbles(aa); cc += (int)fold_nibbles(ac);
+        cg += (int)fold_nibbles(ag); ct += (int)fold_nibbles(at);
     }
 }
 
-// Subtract the bases of query range [a, b) (soft clips, insertions) from the content.
-__device__ __forceinline__ void uncount_range(const uint32_t *seqw, int a, int b, Acc &cn) {
+// A/C/G/T of query range [a, b) (soft clips, insertions).
+__device__ __forceinline__ void count_range(const uint32_t *seqw, int a, int b, int &ca, int &cc, int &cg, int &ct) {
     for (int w = a >> 3; w <= (b - 1) >> 3; ++w) {
         uint32_t x = seqw[w];
         x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);   // base i at bits 4*(i&7)
@@ -121,104 +140,300 @@ __device__ __forceinline__ void uncount_range(const uint32_t *seqw, int a, int b
                        b3 = (x >> 3) & 0x11111111u;
         const uint32_t s = b0 + b1 + b2 + b3;
         const uint32_t onehot = s & ~(s >> 1) & ~(s >> 2) & mask;
-        cn.a -= __popc(b0 & onehot); cn.c -= __popc(b1 & onehot);
-        cn.g -= __popc(b2 & onehot); cn.t -= __popc(b3 & onehot);
+        ca += __popc(b0 & onehot); cc += __popc(b1 & onehot);
+        cg += __popc(b2 & onehot); ct += __popc(b3 & onehot);
     }
 }
 
-// Aligned (M/=/X) offset -> query / reference position through the CIGAR.
-__device__ __forceinline__ bool map_offset(const uint32_t *cig, int n_cigar, int pos, int aoff, int &qpos, int &rpos) {
-    int q = 0, r = pos, acc = 0;
+// ---------------------------------------------------------------------------------------------------
+// Sequential walker (paired units, event overflow, oversized records). Generic pointers.
+// ---------------------------------------------------------------------------------------------------
+struct Walker {
+    const uint32_t *cig;
+    const uint8_t *seq, *qual, *md;
+    int n_cigar, l_seq, md_len, ref_id;
+    int ci, op_left, qpos, rpos, mdp, run;
+    int del[4];
+    bool bad;
+    // current aligned pair
+    int cq, cr;
+    uint32_t gn, rn, q;
+
+    // returns padded record size, 0 if the record does not fit `avail`
+    __device__ size_t init(const uint8_t *rec, size_t avail) {
+        bad = false;
+        ci = op_left = qpos = mdp = run = 0;
+        del[0] = del[1] = del[2] = del[3] = 0;
+        n_cigar = l_seq = md_len = 0;
+        rpos = 0; ref_id = 0;
+        cig = nullptr; seq = qual = md = nullptr;
+        if (avail < 16) { bad = true; return 0; }
+        const uint4 h = *reinterpret_cast<const uint4 *>(rec);
+        const uint32_t ls = h.z & 0xffff, nc = h.z >> 16, ml = h.w & 0xffff;
+        const size_t need = record_need(ls, nc, ml);
+        if (need > avail) { bad = true; return 0; }
+        rpos = (int)h.x; ref_id = (int)h.y;
+        l_seq = (int)ls; n_cigar = (int)nc; md_len = (int)ml;
+        cig = reinterpret_cast<const uint32_t *>(rec + 16);
+        seq = rec + 16 + 4 * (size_t)nc;
+        qual = seq + pad4(((size_t)ls + 1) >> 1);
+        md = qual + ls;
+        return (need + 15) & ~(size_t)15;
+    }
+    __device__ bool md_digit() const { return mdp < md_len && (uint32_t)(md[mdp] - '0') <= 9u; }
+    __device__ void md_number() {
+        while (run == 0 && md_digit())
+            while (md_digit()) run = run * 10 + (int)(md[mdp++] - '0');
+    }
+    // advance to the next aligned (M/=/X) pair
+    __device__ bool next() {
+        for (;;) {
+            if (bad) return false;
+            if (op_left == 0) {
+                if (ci >= n_cigar) return false;
+                const uint32_t c = cig[ci++];
+                const int op = (int)(c & 0xf), len = (int)(c >> 4);
+                if (op == 0 || op == 7 || op == 8) { op_left = len; continue; }
+                if (op == 2) {
+                    md_number();
+                    if (run != 0 || mdp >= md_len || md[mdp] != '^') { bad = true; return false; }
+                    ++mdp;
+                    for (int j = 0; j < len; ++j) {
+                        if (mdp >= md_len) { bad = true; return false; }
+                        const int b = base_idx(letter_code(md[mdp++]));
+                        if (b >= 0) ++del[b];
+                    }
+                    rpos += len;
+                } else if (op == 3) rpos += len;
+                else if (op == 1 || op == 4) { qpos += len; if (qpos > l_seq) { bad = true; return false; } }
+                continue;
+            }
+            if (qpos >= l_seq) { bad = true; return false; }
+            md_number();
+            rn = (seq[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
+            if (run > 0) { gn = rn; --run; }
+            else {
+                if (mdp >= md_len || md[mdp] == '^') { bad = true; return false; }
+                gn = letter_code(md[mdp++]);
+            }
+            cq = qpos; cr = rpos; q = qual[qpos];
+            ++qpos; ++rpos; --op_left;
+            return true;
+        }
+    }
+};
+
+// is reference position p an aligned (M/=/X) position of the record? (pysam get_reference_positions)
+__device__ bool has_aligned_pos(const uint32_t *cig, int n_cigar, int pos, int p) {
+    int r = pos;
     for (int ci = 0; ci < n_cigar; ++ci) {
         const uint32_t c = cig[ci];
-        const int op = c & 0xf, len = (int)(c >> 4);
-        if (op == 0 || op == 7 || op == 8) {
-            if (aoff < acc + len) { qpos = q + (aoff - acc); rpos = r + (aoff - acc); return true; }
-            acc += len; q += len; r += len;
-        } else if (op == 1 || op == 4) q += len;
+        const int op = (int)(c & 0xf), len = (int)(c >> 4);
+        if (op == 0 || op == 7 || op == 8) { if (p >= r && p < r + len) return true; r += len; }
         else if (op == 2 || op == 3) r += len;
     }
     return false;
 }
 
-struct RecView {
-    const uint32_t *cig;
-    const uint32_t *seqw;
-    const uint8_t *seqb, *qual, *md;
-    int pos, l_seq, n_cigar, md_len;
-    uint32_t ref_id;
+struct SlowOut {
+    int content[4];
+    uint32_t w0, w1, w2, n_conv, status;
 };
 
-// One mismatch event: reference code `rn` at aligned offset `aoff`.
-template <bool EMIT>
-__device__ __forceinline__ void do_event(const RecView &v, const TallyParams &p, int aoff, uint32_t rn, Acc &cn,
-                                         unsigned long long *out_rec, uint32_t *out_read, uint32_t read_idx,
-                                         uint32_t &emitted) {
-    int qpos, rpos;
-    if (!map_offset(v.cig, v.n_cigar, v.pos, aoff, qpos, rpos)) { if (!EMIT) cn.status |= DYN_ST_BAD_RECORD; return; }
-    const uint32_t qn = (v.seqb[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
-    if (!EMIT) {
-        // count_query took the read base for the reference base: put the reference base in instead
-        cn.a += (int)(rn == 1) - (int)(qn == 1); cn.c += (int)(rn == 2) - (int)(qn == 2);
-        cn.g += (int)(rn == 4) - (int)(qn == 4); cn.t += (int)(rn == 8) - (int)(qn == 8);
-    }
-    if (rn == 15 || qn == 15 || rn == qn) return;   // bam.py:389-390, 405
-    const uint32_t q = v.qual[qpos];
-    if (EMIT) {
-        out_rec[emitted] = (unsigned long long)(uint32_t)rpos | ((unsigned long long)((rn << 4) | qn) << 32) |
-                           ((unsigned long long)q << 40);
-        out_read[emitted] = read_idx;
-        ++emitted;
-        return;
-    }
-    ++cn.n_conv;
-    if ((int)q <= p.quality) return;                // conversion.py:424 (strict)
-    if (__popc(rn) != 1 || __popc(qn) != 1) { cn.status |= DYN_ST_NON_ACGT_CONV; return; }
-    const int r = __ffs(rn) - 1, d = __ffs(qn) - 1;
-    const int idx = r * 3 + (d > r ? d - 1 : d);
-    if (p.n_snps > 0 &&
-        snp_lookup(p.snps, p.n_snps,
-                   ((unsigned long long)idx << 56) | ((unsigned long long)v.ref_id << 32) | (uint32_t)rpos))
-        return;
+__device__ __forceinline__ void bump_counter(uint32_t &w0, uint32_t &w1, uint32_t &w2, int idx, uint32_t &status) {
     const uint32_t sh = (idx & 3) << 3, wi = idx >> 2;
-    const uint32_t cur = wi == 0 ? cn.w0 : (wi == 1 ? cn.w1 : cn.w2);
-    if (((cur >> sh) & 0xff) == 0xff) { cn.status |= DYN_ST_COUNTER_OVERFLOW; return; }
+    const uint32_t cur = wi == 0 ? w0 : (wi == 1 ? w1 : w2);
+    if (((cur >> sh) & 0xff) == 0xff) { status |= DYN_ST_COUNTER_OVERFLOW; return; }
     const uint32_t inc = 1u << sh;
-    cn.w0 += wi == 0 ? inc : 0u;
-    cn.w1 += wi == 1 ? inc : 0u;
-    cn.w2 += wi == 2 ? inc : 0u;
+    w0 += wi == 0 ? inc : 0u; w1 += wi == 1 ? inc : 0u; w2 += wi == 2 ? inc : 0u;
 }
 
-// Slow path for reads with more than kEvSlots mismatches: sequential MD scan, events handled inline
-// from slot `first_ev` on (the first kEvSlots were handled from the slot list).
 template <bool EMIT>
-__device__ __noinline__ void overflow_events(const RecView &v, const TallyParams &p, Acc &cn,
-                                             unsigned long long *out_rec, uint32_t *out_read, uint32_t read_idx,
-                                             uint32_t &emitted) {
-    int val = 0, aoff = 0, n_ev = 0;
-    bool in_del = false;
-    for (int j = 0; j < v.md_len; ++j) {
-        const uint32_t c = v.md[j];
-        if (is_digit(c)) { val = val * 10 + (int)(c - '0'); in_del = false; }
-        else if (c == '^') { aoff += val; val = 0; in_del = true; }
-        else if (!in_del) {
-            aoff += val; val = 0;
-            if (n_ev >= kEvSlots) do_event<EMIT>(v, p, aoff, letter_code(c), cn, out_rec, out_read, read_idx, emitted);
-            ++n_ev; ++aoff;
+__device__ __forceinline__ void slow_call(const TallyParams &p, SlowOut &o, int ref_id, int rpos, uint32_t gn, uint32_t rn,
+                                          uint32_t q, unsigned long long *out_rec, uint32_t *out_read, uint32_t read_idx) {
+    if (EMIT) {
+        out_rec[o.n_conv] = (unsigned long long)(uint32_t)rpos | ((unsigned long long)((gn << 4) | rn) << 32) |
+                            ((unsigned long long)q << 40);
+        out_read[o.n_conv] = read_idx;
+        ++o.n_conv;
+        return;
+    }
+    ++o.n_conv;
+    if ((int)q <= p.quality) return;                // conversion.py:424 (strict)
+    const int r = base_idx(gn), d = base_idx(rn);
+    if (r < 0 || d < 0) { o.status |= DYN_ST_NON_ACGT_CONV; return; }
+    const int idx = conv_idx(r, d);
+    if (p.n_snps > 0 &&
+        snp_lookup(p.snps, p.n_snps, ((unsigned long long)idx << 56) | ((unsigned long long)(uint32_t)ref_id << 32) | (uint32_t)rpos))
+        return;
+    bump_counter(o.w0, o.w1, o.w2, idx, o.status);
+}
+
+// One counting unit, sequentially. EMIT=false: content + counters + n_conv; EMIT=true: write the records.
+template <bool EMIT>
+__device__ __noinline__ void slow_unit(const uint8_t *rec, size_t unit_bytes, const TallyParams &p, uint32_t read_idx,
+                                       SlowOut &o, unsigned long long *out_rec, uint32_t *out_read) {
+    o.content[0] = o.content[1] = o.content[2] = o.content[3] = 0;
+    o.w0 = o.w1 = o.w2 = 0; o.n_conv = 0; o.status = 0;
+    const bool nasc = (p.flags & DYN_TALLY_NASC) != 0;
+    Walker rd;
+    const size_t rd_bytes = rd.init(rec, unit_bytes);
+    if (rd.bad) { o.status |= DYN_ST_BAD_RECORD; return; }
+    const bool has_mate = (reinterpret_cast<const uint16_t *>(rec)[7] & DYN_REC_HAS_MATE) != 0;
+    const uint8_t *mrec = rec + rd_bytes;
+    const size_t mate_avail = unit_bytes - rd_bytes;
+    const int rd_pos = rd.rpos;
+    bool bad = false;
+
+    if (has_mate) {
+        // content(mate) - overlap, floored at zero (Counter subtraction, bam.py:332-346)
+        Walker m;
+        m.init(mrec, mate_avail);
+        if (m.bad) { o.status |= DYN_ST_BAD_RECORD; return; }
+        int overlap[4] = {0, 0, 0, 0};
+        while (m.next()) {
+            const int b = base_idx(m.gn);
+            if (!EMIT && b >= 0) ++o.content[b];
+            if (!EMIT && m.gn != 15 && m.rn != 15 && b >= 0 && has_aligned_pos(rd.cig, rd.n_cigar, rd_pos, m.cr)) ++overlap[b];
+        }
+        bad |= m.bad;
+        if (!EMIT)
+            for (int b = 0; b < 4; ++b) o.content[b] = max(0, o.content[b] + m.del[b] - overlap[b]);
+    }
+
+    // the read's own walk; a second mate walker answers "does the mate hold a call at this position?"
+    {
+        Walker mm;
+        bool mm_live = false;
+        if (has_mate) { mm.init(mrec, mate_avail); mm_live = mm.next(); }
+        while (rd.next()) {
+            if (!EMIT) { const int b = base_idx(rd.gn); if (b >= 0) ++o.content[b]; }
+            if (rd.gn == 15 || rd.rn == 15) continue;          // bam.py:389-390
+            uint32_t rn = rd.rn, q = rd.q;
+            if (has_mate && !nasc) {
+                while (mm_live && mm.cr < rd.cr) mm_live = mm.next();
+                if (mm_live && mm.cr == rd.cr && mm.gn != 15 && mm.rn != 15 && mm.gn != mm.rn && mm.q > q) {
+                    rn = mm.rn; q = mm.q;                        // bam.py:395-403: mate wins only if strictly better
+                }
+            }
+            if (rd.gn != rn) slow_call<EMIT>(p, o, rd.ref_id, rd.cr, rd.gn, rn, q, out_rec, out_read, read_idx);
+        }
+        bad |= rd.bad | (has_mate && mm.bad);
+        if (!EMIT) for (int b = 0; b < 4; ++b) o.content[b] += rd.del[b];
+    }
+
+    // leftover mate calls, in the mate's walk order (bam.py:414-419)
+    if (has_mate) {
+        Walker m, r2;
+        m.init(mrec, mate_avail);
+        r2.init(rec, unit_bytes);
+        bool r2_live = r2.next();
+        while (m.next()) {
+            if (m.gn == 15 || m.rn == 15 || m.gn == m.rn) continue;
+            if (nasc && has_aligned_pos(rd.cig, rd.n_cigar, rd_pos, m.cr)) continue;   // bam.py:339
+            while (r2_live && r2.cr < m.cr) r2_live = r2.next();
+            if (r2_live && r2.cr == m.cr && r2.gn != 15 && r2.rn != 15) continue;      // consumed by the read's walk
+            slow_call<EMIT>(p, o, rd.ref_id, m.cr, m.gn, m.rn, m.q, out_rec, out_read, read_idx);
+        }
+        bad |= m.bad;
+    }
+    if (bad) {
+        o.status |= DYN_ST_BAD_RECORD;
+        if (!EMIT) { o.content[0] = o.content[1] = o.content[2] = o.content[3] = 0; o.w0 = o.w1 = o.w2 = 0; o.n_conv = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lane-balanced event resolution (fast path, shared-memory records)
+// ---------------------------------------------------------------------------------------------------
+struct TileSmem {
+    uint8_t *stage;
+    unsigned long long *slot;   // [kEvSlots][kThreads]
+    int *acc;                   // [7][kThreads]: a c g t w0 w1 w2
+    uint32_t *recoff;           // [kThreads] byte offset of the record inside `stage`
+    uint8_t *list;              // [kWarps][32 * kEvSlots]: lane | slot << 5
+};
+
+__device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const TallyParams &p, int o_tid, int s) {
+    uint32_t status = 0;
+    unsigned long long *slot = sm.slot + s * kThreads + o_tid;
+    const unsigned long long pl = *slot;
+    const uint8_t *rec = sm.stage + sm.recoff[o_tid];
+    const uint4 h = *reinterpret_cast<const uint4 *>(rec);
+    const int pos = (int)h.x;
+    const uint32_t l_seq = h.z & 0xffff, n_cigar = h.z >> 16;
+    const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
+    const uint32_t *seqw = cig + n_cigar;
+    const uint8_t *seqb = reinterpret_cast<const uint8_t *>(seqw);
+    int *acc = sm.acc + o_tid;
+    if (pl & kEvRange) {
+        // clipped / inserted query range: count_query took those bases for reference bases
+        const int qs = (int)(pl & 0xffff), len = (int)((pl >> 20) & 0xffff);
+        int da = 0, dc = 0, dg = 0, dt = 0;
+        count_range(seqw, qs, qs + len, da, dc, dg, dt);
+        if (da) atomicSub(acc + 0 * kThreads, da);
+        if (dc) atomicSub(acc + 1 * kThreads, dc);
+        if (dg) atomicSub(acc + 2 * kThreads, dg);
+        if (dt) atomicSub(acc + 3 * kThreads, dt);
+        *slot = 0;
+        return 0;
+    }
+    const int aoff = (int)(pl & 0xffff);
+    const uint32_t gn = (uint32_t)(pl >> 16) & 0xf;
+    // aligned (M/=/X) offset -> query / reference position through the CIGAR
+    int qpos = -1, rpos = 0;
+    {
+        int q = 0, r = pos, done = 0;
+        for (uint32_t ci = 0; ci < n_cigar; ++ci) {
+            const uint32_t c = cig[ci];
+            const int op = (int)(c & 0xf), len = (int)(c >> 4);
+            if (op == 0 || op == 7 || op == 8) {
+                if (aoff < done + len) { qpos = q + (aoff - done); rpos = r + (aoff - done); break; }
+                done += len; q += len; r += len;
+            } else if (op == 1 || op == 4) q += len;
+            else if (op == 2 || op == 3) r += len;
         }
     }
+    if (qpos < 0 || qpos >= (int)l_seq) { *slot = 0; return DYN_ST_BAD_RECORD; }
+    const uint32_t rn = (seqb[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
+    // count_query took the read base for the reference base: put the reference base in instead
+    const int gi = base_idx(gn), ri = base_idx(rn);
+    if (gi != ri) {
+        if (gi >= 0) atomicAdd(acc + gi * kThreads, 1);
+        if (ri >= 0) atomicSub(acc + ri * kThreads, 1);
+    }
+    if (gn == 15 || rn == 15 || gn == rn) { *slot = 0; return 0; }   // bam.py:389-390, 405
+    const uint8_t *qual = seqb + pad4(((size_t)l_seq + 1) >> 1);
+    const uint32_t q = qual[qpos];
+    *slot = (unsigned long long)(uint32_t)rpos | ((unsigned long long)((gn << 4) | rn) << 32) | ((unsigned long long)q << 40);
+    if ((int)q <= p.quality) return 0;                                // conversion.py:424 (strict)
+    if (gi < 0 || ri < 0) return DYN_ST_NON_ACGT_CONV;
+    const int idx = conv_idx(gi, ri);
+    if (p.n_snps > 0 &&
+        snp_lookup(p.snps, p.n_snps, ((unsigned long long)idx << 56) | ((unsigned long long)h.y << 32) | (uint32_t)rpos))
+        return 0;
+    const uint32_t sh = (idx & 3) << 3;
+    uint32_t *w = reinterpret_cast<uint32_t *>(acc + (4 + (idx >> 2)) * kThreads);
+    const uint32_t old = atomicAdd(w, 1u << sh);
+    if (((old >> sh) & 0xff) == 0xff) { atomicSub(w, 1u << sh); status |= DYN_ST_COUNTER_OVERFLOW; }
+    return status;
 }
 
-__global__ void __launch_bounds__(kThreads, 4) tally_kernel(const TallyParams p) {
+__global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(const TallyParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *stage = smem;                                                        // [stage_bytes]
-    uint32_t *ev = reinterpret_cast<uint32_t *>(smem + p.stage_bytes);            // [kEvSlots][kThreads]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ev + kEvSlots * kThreads);       // 8 B
-    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(bar + 2);                  // [kThreads/32 + 2]
-    uint32_t *s_sub = warp_sums + kThreads / 32 + 2;                              // sub-tile end broadcast
+    TileSmem sm;
+    sm.stage = smem;                                                                   // [stage_bytes]
+    sm.slot = reinterpret_cast<unsigned long long *>(smem + p.stage_bytes);            // 8 * kEvSlots * kThreads
+    sm.acc = reinterpret_cast<int *>(sm.slot + kEvSlots * kThreads);                   // 4 * 7 * kThreads
+    sm.recoff = reinterpret_cast<uint32_t *>(sm.acc + 7 * kThreads);                   // 4 * kThreads
+    sm.list = reinterpret_cast<uint8_t *>(sm.recoff + kThreads);                       // kThreads * kEvSlots
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm.list + kThreads * kEvSlots);       // 16 B
+    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(bar + 2);                       // [kWarps + 4]
+    uint32_t *s_sub = warp_sums + kWarps + 4;                                          // sub-tile broadcast
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
+    uint8_t *wlist = sm.list + wid * 32 * kEvSlots;
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -258,120 +473,164 @@ __global__ void __launch_bounds__(kThreads, 4) tally_kernel(const TallyParams p)
             if (tid == 0 && bytes > 0) {
                 fence_proxy_async();
                 mbar_expect_tx(bar, bytes);
-                tma_bulk_g2s(stage, p.records + ((unsigned long long)off0 << 4), bytes, bar);
+                tma_bulk_g2s(sm.stage, p.records + ((unsigned long long)off0 << 4), bytes, bar);
             }
             const long long r = r0 + tid;
-            const bool active = r < r1 && !oversized;
-            uint32_t my_off = 0, my_end = 0;
-            if (r < r1) { my_off = __ldg(p.rec_off + r); my_end = __ldg(p.rec_off + r + 1); }
+            const bool inrange = r < r1;
+            uint32_t my_off = off0, my_end = off0;
+            if (inrange) { my_off = __ldg(p.rec_off + r); my_end = __ldg(p.rec_off + r + 1); }
+            const size_t unit_bytes = (size_t)(my_end - my_off) << 4;
             if (bytes > 0) {
                 mbar_wait(bar, parity);
                 parity ^= 1;
             }
 
             // ---- header
-            Acc cn = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            RecView v;
-            v.pos = 0; v.l_seq = 0; v.n_cigar = 0; v.md_len = 0; v.ref_id = 0;
-            const uint8_t *rec = stage + ((size_t)(my_off - off0) << 4);
-            bool good = active;
-            if (active) {
-                const uint4 h = *reinterpret_cast<const uint4 *>(rec);
-                v.pos = (int)h.x; v.ref_id = h.y;
-                v.l_seq = h.z & 0xffff; v.n_cigar = h.z >> 16; v.md_len = h.w & 0xffff;
-                const size_t need = 16 + 4 * (size_t)v.n_cigar + (((((size_t)v.l_seq + 1) >> 1) + 3) & ~(size_t)3) +
-                                    v.l_seq + v.md_len;
-                if (need > ((size_t)(my_end - my_off) << 4)) {   // truncated / corrupt record
-                    good = false; v.l_seq = v.n_cigar = v.md_len = 0;
+            // a record larger than the staging buffer is walked straight from global memory
+            const uint8_t *rec = sm.stage + ((size_t)(my_off - off0) << 4);
+            const uint8_t *slow_rec = oversized ? p.records + ((size_t)my_off << 4) : rec;
+            int ca = 0, cc = 0, cg = 0, ct = 0;
+            uint32_t status = 0;
+            int pos = 0, l_seq = 0, n_cigar = 0, md_len = 0;
+            bool good = inrange, slow = false;
+            if (inrange) {
+                if (oversized || unit_bytes < 16) slow = true;
+                else {
+                    const uint4 h = *reinterpret_cast<const uint4 *>(rec);
+                    if ((h.w >> 16) & DYN_REC_HAS_MATE) slow = true;
+                    else {
+                        pos = (int)h.x;
+                        l_seq = h.z & 0xffff; n_cigar = h.z >> 16; md_len = h.w & 0xffff;
+                        if (record_need(l_seq, n_cigar, md_len) > unit_bytes) {   // truncated / corrupt record
+                            good = false; l_seq = n_cigar = md_len = 0;
+                        }
+                    }
                 }
             }
-            v.cig = reinterpret_cast<const uint32_t *>(rec + 16);
-            v.seqw = v.cig + v.n_cigar;
-            v.seqb = reinterpret_cast<const uint8_t *>(v.seqw);
-            v.qual = v.seqb + ((((v.l_seq + 1) >> 1) + 3) & ~3);
-            v.md = v.qual + v.l_seq;
-            if (r < r1 && !good) cn.status |= DYN_ST_BAD_RECORD;
+            const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
+            const uint32_t *seqw = cig + n_cigar;
+            const uint8_t *md = reinterpret_cast<const uint8_t *>(seqw) + pad4(((size_t)l_seq + 1) >> 1) + l_seq;
+            sm.recoff[tid] = (uint32_t)(my_off - off0) << 4;
+            unsigned long long *myslot = sm.slot + tid;
+            int n_ev = 0;
 
+#ifdef DYN_TALLY_DEBUG_SKIP
+            if (DYN_TALLY_DEBUG_SKIP >= 2) { l_seq = 0; n_cigar = 0; }
+            md_len = 0;
+#endif
             // ---- 1. whole-query base content
-            count_query(v.seqw, v.l_seq, cn);
+            count_query(seqw, l_seq, ca, cc, cg, ct);
 
-            // ---- 2. CIGAR pre-scan
+            // ---- 2. CIGAR pre-scan: totals; clipped / inserted query ranges become events
             int m_total = 0, d_total = 0;
             {
                 int q = 0;
-                for (int ci = 0; ci < v.n_cigar; ++ci) {
-                    const uint32_t c = v.cig[ci];
+                for (int ci = 0; ci < n_cigar; ++ci) {
+                    const uint32_t c = cig[ci];
                     const int op = c & 0xf, len = (int)(c >> 4);
                     if (op == 0 || op == 7 || op == 8) { m_total += len; q += len; }
                     else if (op == 1 || op == 4) {
-                        if (q + len <= v.l_seq && len > 0) uncount_range(v.seqw, q, q + len, cn);
+                        if (len > 0 && q + len <= l_seq) {
+                            if (n_ev < kEvSlots)
+                                myslot[n_ev * kThreads] = kEvRange | (unsigned long long)q | ((unsigned long long)len << 20);
+                            ++n_ev;
+                        }
                         q += len;
                     } else if (op == 2) d_total += len;
                 }
-                if (q != v.l_seq) { cn.status |= DYN_ST_BAD_RECORD; good = false; }
+                if (q != l_seq) good = false;
             }
 
-            // ---- 3. MD scan: locate events (warp-uniform trip count)
-            int n_ev = 0;
+            // ---- 3. MD scan: locate mismatch events (warp-uniform trip count)
             {
-                const int md_len = good ? v.md_len : 0;
-                const int max_len = __reduce_max_sync(0xffffffffu, md_len);
+                const int my_len = good ? md_len : 0;
+                const int max_len = __reduce_max_sync(0xffffffffu, my_len);
                 int val = 0, aoff = 0, n_delb = 0;
                 bool in_del = false;
                 for (int j = 0; j < max_len; ++j) {
-                    if (j < md_len) {
-                        const uint32_t c = v.md[j];
+                    if (j < my_len) {
+                        const uint32_t c = md[j];
                         const uint32_t d = c - '0';
                         if (d <= 9u) { val = val * 10 + (int)d; in_del = false; }
                         else if (c == '^') { aoff += val; val = 0; in_del = true; }
                         else {
                             const uint32_t code = letter_code(c);
                             if (in_del) {   // deleted reference base: counts toward content (bam.py:359-360)
-                                cn.a += (code == 1); cn.c += (code == 2); cn.g += (code == 4); cn.t += (code == 8);
+                                ca += (code == 1); cc += (code == 2); cg += (code == 4); ct += (code == 8);
                                 ++n_delb;
                             } else {
                                 aoff += val; val = 0;
-                                if (n_ev < kEvSlots) ev[n_ev * kThreads + tid] = (uint32_t)aoff | (code << 16);
+                                if (n_ev < kEvSlots) myslot[n_ev * kThreads] = (unsigned long long)((uint32_t)aoff | (code << 16));
                                 ++n_ev; ++aoff;
                             }
                         }
                     }
                 }
-                if (good && (aoff + val != m_total || n_delb != d_total)) { cn.status |= DYN_ST_BAD_RECORD; n_ev = 0; }
+                if (good && (aoff + val != m_total || n_delb != d_total || m_total > 0xffff)) good = false;
             }
+            if (inrange && !slow && !good) status |= DYN_ST_BAD_RECORD;
+            if (good && n_ev > kEvSlots) slow = true;
 
-            // ---- 4. resolve events
+            // ---- 4. compact the warp's events, resolve them lane-balanced
+            const int n_slot = (good && !slow) ? n_ev : 0;
+            sm.acc[0 * kThreads + tid] = ca; sm.acc[1 * kThreads + tid] = cc;
+            sm.acc[2 * kThreads + tid] = cg; sm.acc[3 * kThreads + tid] = ct;
+            sm.acc[4 * kThreads + tid] = 0; sm.acc[5 * kThreads + tid] = 0; sm.acc[6 * kThreads + tid] = 0;
             {
-                const int n_slot = min(n_ev, kEvSlots);
-                const int max_ev = __reduce_max_sync(0xffffffffu, n_slot);
-                uint32_t dummy = 0;
-                for (int e = 0; e < max_ev; ++e) {
-                    if (e < n_slot) {
-                        const uint32_t w = ev[e * kThreads + tid];
-                        do_event<false>(v, p, (int)(w & 0xffff), w >> 16, cn, nullptr, nullptr, 0, dummy);
+                int incl = n_slot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const int n_events = __shfl_sync(0xffffffffu, incl, 31);
+                const int first = incl - n_slot;
+                const int max_slot = __reduce_max_sync(0xffffffffu, n_slot);
+                for (int s = 0; s < max_slot; ++s)
+                    if (s < n_slot) wlist[first + s] = (uint8_t)(lane | (s << 5));
+                __syncwarp();
+                for (int e0 = 0; e0 < n_events; e0 += 32) {
+                    const int e = e0 + lane;
+                    if (e < n_events) {
+                        const uint32_t le = wlist[e];
+                        status |= resolve_event(sm, p, (wid << 5) + (int)(le & 31), (int)(le >> 5));
                     }
                 }
-                if (n_ev > kEvSlots) overflow_events<false>(v, p, cn, nullptr, nullptr, 0, dummy);
+                __syncwarp();
             }
 
-            if (r < r1) {
-                uint32_t a = (uint32_t)max(cn.a, 0), c = (uint32_t)max(cn.c, 0), g = (uint32_t)max(cn.g, 0),
-                         t = (uint32_t)max(cn.t, 0);
+            // ---- 5. gather the read's results
+            uint32_t w0 = 0, w1 = 0, w2 = 0, n_conv = 0;
+            if (n_slot > 0) {
+                ca = sm.acc[0 * kThreads + tid]; cc = sm.acc[1 * kThreads + tid];
+                cg = sm.acc[2 * kThreads + tid]; ct = sm.acc[3 * kThreads + tid];
+                w0 = (uint32_t)sm.acc[4 * kThreads + tid]; w1 = (uint32_t)sm.acc[5 * kThreads + tid];
+                w2 = (uint32_t)sm.acc[6 * kThreads + tid];
+                for (int s = 0; s < n_slot; ++s) n_conv += myslot[s * kThreads] != 0ull;
+            }
+            if (inrange && slow) {
+                SlowOut so;
+                slow_unit<false>(slow_rec, unit_bytes, p, (uint32_t)r, so, nullptr, nullptr);
+                ca = so.content[0]; cc = so.content[1]; cg = so.content[2]; ct = so.content[3];
+                w0 = so.w0; w1 = so.w1; w2 = so.w2; n_conv = so.n_conv; status |= so.status;
+            }
+            if (inrange) {
+                uint32_t a = (uint32_t)max(ca, 0), c = (uint32_t)max(cc, 0), g = (uint32_t)max(cg, 0), t = (uint32_t)max(ct, 0);
                 if ((a | c | g | t) > 255u) {
-                    cn.status |= DYN_ST_COUNTER_OVERFLOW;
+                    status |= DYN_ST_COUNTER_OVERFLOW;
                     a = min(a, 255u); c = min(c, 255u); g = min(g, 255u); t = min(t, 255u);
                 }
-                if (!good) { a = c = g = t = 0; cn.w0 = cn.w1 = cn.w2 = 0; cn.n_conv = 0; }
+                if (!good && !slow) { a = c = g = t = 0; w0 = w1 = w2 = 0; n_conv = 0; }
                 uint4 o;
-                o.x = cn.w0; o.y = cn.w1; o.z = cn.w2;
+                o.x = w0; o.y = w1; o.z = w2;
                 o.w = a | (c << 8) | (g << 16) | (t << 24);
                 reinterpret_cast<uint4 *>(p.counts)[r] = o;
-                status_acc |= cn.status;
             }
+            status_acc |= status;
 
             if (emit) {
                 // block exclusive scan of n_conv -> one global atomic per (sub-)tile
-                const uint32_t mine_n = (r < r1) ? cn.n_conv : 0u;
+                const uint32_t mine_n = inrange ? n_conv : 0u;
                 uint32_t incl = mine_n;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -382,14 +641,14 @@ __global__ void __launch_bounds__(kThreads, 4) tally_kernel(const TallyParams p)
                 __syncthreads();
                 if (tid == 0) {
                     uint32_t run = 0;
-                    for (int w = 0; w < kThreads / 32; ++w) { const uint32_t t = warp_sums[w]; warp_sums[w] = run; run += t; }
+                    for (int w = 0; w < kWarps; ++w) { const uint32_t t = warp_sums[w]; warp_sums[w] = run; run += t; }
                     const unsigned long long base = run ? atomicAdd(p.conv_total, (unsigned long long)run) : 0ull;
-                    reinterpret_cast<unsigned long long *>(warp_sums + kThreads / 32)[0] = base;
+                    reinterpret_cast<unsigned long long *>(warp_sums + kWarps)[0] = base;
                 }
                 __syncthreads();
-                const unsigned long long base = reinterpret_cast<unsigned long long *>(warp_sums + kThreads / 32)[0];
+                const unsigned long long base = reinterpret_cast<unsigned long long *>(warp_sums + kWarps)[0];
                 const unsigned long long mine = base + warp_sums[wid] + (incl - mine_n);
-                if (r < r1) {
+                if (inrange) {
                     uint32_t n = mine_n;
                     if (n > 0xffffu) { n = 0xffffu; status_acc |= DYN_ST_COUNTER_OVERFLOW; }
                     const bool fits = mine + mine_n <= (unsigned long long)p.conv_cap;
@@ -397,24 +656,28 @@ __global__ void __launch_bounds__(kThreads, 4) tally_kernel(const TallyParams p)
                     p.conv_n[r] = fits ? (uint16_t)n : (uint16_t)0;
                     if (mine_n > 0 && !fits) status_acc |= DYN_ST_CONV_CAPACITY;
                     if (mine_n > 0 && fits) {
-                        uint32_t emitted = 0;
-                        const int n_slot = min(n_ev, kEvSlots);
-                        for (int e = 0; e < n_slot; ++e) {
-                            const uint32_t w = ev[e * kThreads + tid];
-                            do_event<true>(v, p, (int)(w & 0xffff), w >> 16, cn, p.conv_rec + mine, p.conv_read + mine,
-                                           (uint32_t)r, emitted);
+                        if (slow) {
+                            SlowOut so;
+                            slow_unit<true>(slow_rec, unit_bytes, p, (uint32_t)r, so, p.conv_rec + mine, p.conv_read + mine);
+                        } else {
+                            uint32_t k = 0;
+                            for (int s = 0; s < n_slot; ++s) {
+                                const unsigned long long cr = myslot[s * kThreads];
+                                if (cr != 0ull) { p.conv_rec[mine + k] = cr; p.conv_read[mine + k] = (uint32_t)r; ++k; }
+                            }
                         }
-                        if (n_ev > kEvSlots)
-                            overflow_events<true>(v, p, cn, p.conv_rec + mine, p.conv_read + mine, (uint32_t)r, emitted);
                     }
                 }
             }
-            __syncthreads();   // everyone is done with `stage` / `ev` before the next bulk copy lands
+            __syncthreads();   // everyone is done with `stage` / slots before the next bulk copy lands
             r0 = r1;
         }
     }
     if (status_acc) atomicOr(p.status, status_acc);
 }
+
+constexpr size_t kFixedSmem = sizeof(unsigned long long) * kEvSlots * kThreads + sizeof(int) * 7 * kThreads +
+                              sizeof(uint32_t) * kThreads + kThreads * kEvSlots + 16 + sizeof(uint32_t) * (kWarps + 4 + 4);
 
 }  // namespace
 
@@ -432,7 +695,6 @@ extern "C" int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint
     if (flags & DYN_TALLY_EMIT_CONV)
         DYN_ARG(d_conv_off && d_conv_n && d_conv_rec && d_conv_read && d_conv_total, "null conversion buffer");
     DYN_ARG(n_snps == 0 || d_snps, "null snp table");
-    DYN_ARG(!(flags & DYN_TALLY_NASC), "paired records / --nasc are handled by dyn_tally_pairs");
 
     TallyParams p;
     p.records = static_cast<const uint8_t *>(d_records);
@@ -450,18 +712,23 @@ extern "C" int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint
     p.conv_cap = conv_capacity;
     p.conv_total = reinterpret_cast<unsigned long long *>(d_conv_total);
     p.status = d_status;
-    // 4 CTAs per SM share 227 KB: 46 KB staging + 8 KB event slots + bookkeeping each
-    p.stage_bytes = 46 * 1024;
+    // staging buffer: one tile of kThreads records.  The caller may pass the mean record size (in 16-byte
+    // units) in flags bits 16..31 (DYN_TALLY_REC16_HINT); default fits 91-nt reads (~12 units).
+    uint32_t hint16 = flags >> 16;
+    if (hint16 == 0) hint16 = 12;
+    size_t stage = ((size_t)kThreads * hint16 * 16 * 17 / 16 + 1023) & ~(size_t)1023;   // + 6 % slack
+    const size_t max_stage = ctx->smem_optin - kFixedSmem - 1024;
+    if (stage > max_stage) stage = max_stage & ~(size_t)1023;
+    if (stage < 8192) stage = 8192;
+    p.stage_bytes = (uint32_t)stage;
     p.n_tiles = (n_reads + kThreads - 1) / kThreads;
-    const size_t smem = p.stage_bytes + sizeof(uint32_t) * kEvSlots * kThreads + 16 +
-                        sizeof(uint32_t) * (kThreads / 32 + 2 + 4) + 16;
+    const size_t smem = stage + kFixedSmem;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        DYN_CUDA(cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    long long grid = (long long)ctx->sm_count * 4;
+    DYN_CUDA(cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tally_kernel, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
     tally_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     DYN_CUDA(cudaGetLastError());

@@ -110,6 +110,8 @@ def tally_reads(ctx: Context, records: torch.Tensor, rec_off: torch.Tensor, out:
     n = rec_off.numel() - 1
     out.scalars.zero_()
     flags = (TALLY_NASC if nasc else 0) | (TALLY_EMIT_CONV if emit_conv else 0)
+    if n > 0:   # DYN_TALLY_REC16_HINT: mean unit size in 16-byte units (sizes the kernel's staging buffer)
+        flags |= min(0xffff, -(-(records.numel() // 16) // n)) << 16
     check(
         ctx.lib.dyn_tally_reads(
             ctx.handle, ptr(records), ptr(rec_off), n, ptr(snps), 0 if snps is None else snps.numel(), int(quality),

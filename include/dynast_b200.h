@@ -44,7 +44,7 @@ extern "C" {
  *     zero padding to a multiple of 16 bytes
  * If hdr.flag has DYN_REC_HAS_MATE, a second record (the first-seen mate of a read pair, same layout)
  * follows inside the same [rec_off[i], rec_off[i+1]) range; the pair is one counting unit
- * (bam.py:307-352).
+ * (bam.py:307-352) and dyn_tally_reads applies the overlap rules of bam.py:332-346, 393-419.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t pos;      /* 0-based leftmost reference position (BAM pos) */
@@ -71,6 +71,9 @@ typedef struct {
 /* tally flags */
 #define DYN_TALLY_NASC 0x1u        /* --nasc: drop mate conversions inside the pair overlap (bam.py:339,396) */
 #define DYN_TALLY_EMIT_CONV 0x2u   /* also emit the per-mismatch records (conversions.csv rows) */
+/* optional tuning hint in flags bits 16..31: mean size of a counting unit in 16-byte units (sizes the
+ * shared-memory staging buffer; 0 = assume ~91-nt single-end reads). Results never depend on it. */
+#define DYN_TALLY_REC16_HINT(units16) ((uint32_t)(units16) << 16)
 
 /* status bits accumulated in *d_status by the tally (0 == clean) */
 #define DYN_ST_COUNTER_OVERFLOW 0x1u /* a counter exceeded 255: the reference raises when re-reading uint8 */

@@ -42,6 +42,52 @@ def test_fixture_bam_single_end(gpu_ctx, oracle_lib, align, kw):
     assert hit == 250
 
 
+@pytest.mark.parametrize('align,kw,nasc', [
+    ('smartseq_align', dict(umi_tag=None, barcode_tag='RG', velocity=False), False),
+    ('nasc_align', dict(umi_tag=None, barcode_tag='RG', velocity=False), True),
+    ('nasc_align', dict(umi_tag=None, barcode_tag='RG', velocity=False), False),
+])
+def test_fixture_bam_paired(gpu_ctx, oracle_lib, align, kw, nasc):
+    """Paired units (first-seen mate packed behind the read): overlap / mate-call rules of bam.py:307-352, 393-419."""
+    from oracle import pack
+    from dynast_b200 import device, records as rec
+    blob, off, meta, refs = pack.units_from_bam(ref_path(align, 'Aligned.sortedByCoord.out.bam'), rec.pack_one,
+                                                rec.pack_units, **kw)
+    assert len(meta) > 100
+    orc = pack.run_tally(blob, off, quality=27, nasc=nasc)
+    gpu = device.tally_reads_host(blob, off, quality=27, nasc=nasc)
+    assert orc['total'] > 0
+    _compare(gpu, orc)
+
+
+def test_event_overflow_and_long_reads(gpu_ctx, oracle_lib):
+    """Reads with more mismatches than event slots, reads whose counters pass 255, and one record larger
+    than the staging buffer all take the sequential walker and must still equal the oracle."""
+    from oracle import pack
+    from dynast_b200 import device, records as rec, synth
+    d = synth.make_reads(600, seed=21, p_e=0.04)           # ~11 mismatches per read
+    orc = pack.run_tally(d['blob'], d['rec_off'], quality=27)
+    gpu = device.tally_reads_host(d['blob'], d['rec_off'], quality=27)
+    assert (orc['conv_n'] > 8).sum() > 100
+    _compare(gpu, orc)
+    d = synth.make_reads(300, seed=22, read_len=300, p_e=0.002)   # A/C/G/T content can exceed 255 -> status bit
+    orc = pack.run_tally(d['blob'], d['rec_off'], quality=27)
+    gpu = device.tally_reads_host(d['blob'], d['rec_off'], quality=27)
+    _compare(gpu, orc)
+    # 400 short reads and one 40 kb record in the middle of a tile
+    small = synth.make_reads(400, seed=23)
+    big = synth.make_reads(1, seed=24, read_len=40000, p_e=0.001)
+    units = []
+    for src, lo, hi in ((small, 0, 200), (big, 0, 1), (small, 200, 400)):
+        for i in range(lo, hi):
+            a, b = int(src['rec_off'][i]) * 16, int(src['rec_off'][i + 1]) * 16
+            units.append([bytes(src['blob'][a:b])])
+    blob, off = rec.pack_units(units)
+    orc = pack.run_tally(blob, off, quality=27)
+    gpu = device.tally_reads_host(blob, off, quality=27)
+    _compare(gpu, orc)
+
+
 @pytest.mark.parametrize('n_reads,seed', [(1, 3), (31, 4), (257, 5), (20000, 6)])
 def test_synthetic_vs_oracle(gpu_ctx, oracle_lib, n_reads, seed):
     from oracle import pack
