@@ -26,6 +26,18 @@ PROTOTYPES = {
         (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'dyn_em_pc': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     'dyn_em_pc_host': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+    'dyn_count_records': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
+    'dyn_complement_counts': (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    'dyn_barcode_first_pos': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    'dyn_dedup_umi': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _u32,
+                             _i32, _vp, _i32, _vp, _vp, _vp]),
+    'dyn_group_sums': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp]),
+    'dyn_rates_pe': (_i32, [_vp, _vp, _i64, _u32, _vp, _vp, _vp]),
+    'dyn_alpha': (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'dyn_aggregate_kn': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _u32, _u32, _u32, _i32, _i32, _i32, _vp, _vp, _vp,
+                                _vp, _vp]),
+    'dyn_kn_csr': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'dyn_pi_fit': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
     'dyn_synth_fill': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

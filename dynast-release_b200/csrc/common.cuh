@@ -32,14 +32,30 @@ struct dyn_ctx {
     cudaStream_t copy_stream[2];
     cudaEvent_t ev[4];
     // lazily grown device scratch (never shrinks); used by host-buffer entry points and sort temp
-    void *scratch[8];
-    size_t scratch_bytes[8];
+    void *scratch[16];
+    size_t scratch_bytes[16];
     // lazily built device tables
     double *em_coef;        // binomial coefficient table (wrapped-int64 semantics), [em_coef_K][em_coef_N]
     int em_coef_K, em_coef_N;
 };
 
 int dyn_ctx_scratch(dyn_ctx *ctx, int slot, size_t bytes, void **out);
+
+// Scratch slots (device-pointer entry points reuse them in stream order; one stream per context at a time):
+//   0 EM scalars, 1-7 host-buffer tally / EM staging, 8 dedup, 9 aggregation, 10 pi, 11 coverage, 12 consensus
+// Bump allocator over one scratch slot: run the same carve() twice, first with base == nullptr to size it.
+struct Arena {
+    uint8_t *base;
+    size_t used;
+    explicit Arena(void *b = nullptr) : base(static_cast<uint8_t *>(b)), used(0) {}
+    template <typename T>
+    T *take(size_t n) {
+        used = (used + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + used) : nullptr;
+        used += sizeof(T) * n;
+        return p;
+    }
+};
 
 // ---- small device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -1,0 +1,296 @@
+// Strand complement and UMI deduplication.
+//
+// Replaces dynast/preprocessing/conversion.py:99-125 (complement_counts), :203-243 (deduplicate_counts)
+// and the ordering logic of the count_conversions driver (:529-606), which in the reference are pandas
+// sorts over per-split CSV files in a process pool.
+//
+// What the reference computes, restated as keys:
+//   * frame order F = (gene strand '-' last, reads without any mismatch last, BAM order)
+//       conversion.py:533-541 -- parts with conversions, then count_no_conversions, then complement_counts
+//   * split-file order = (barcode in first-appearance order of F, F)          conversion.py:543-579
+//   * per split: STABLE ascending sort by ([has_conversions,] transcriptome, score, conversion_sum) on the
+//     complemented counts, drop_duplicates((barcode, umi, GX), keep='last')   conversion.py:225-243
+//     -> winner of a UMI group = max priority, ties -> last in split-file order; survivors keep sorted order
+//   * per split: forward-strand rows, then reverse-strand rows                conversion.py:602-606
+// On the device that is four stable LSD radix sorts (cub::DeviceRadixSort, keys restricted to the bits in
+// use) and one stream compaction; the result is the list of surviving read indices in output order.
+// HBM-bound: ~20 B/read algorithmic (16 B key + priority in, 4 B index out); the sorts move more.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// complement_counts on one 16-byte counter row: the 12 conversion columns reversed, the 4 base columns
+// reversed (conversion.py:122-123: CONVERSION_COLUMNS[::-1] + BASE_COLUMNS[::-1]).
+__device__ __forceinline__ uint4 complement_row(uint4 v) {
+    uint4 o;
+    o.x = bswap32(v.z); o.y = bswap32(v.y); o.z = bswap32(v.x); o.w = bswap32(v.w);
+    return o;
+}
+
+__global__ void complement_kernel(uint4 *counts, const uint8_t *strand, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || !strand[i]) return;
+    counts[i] = complement_row(counts[i]);
+}
+
+__global__ void first_pos_kernel(const uint32_t *barcode, const uint8_t *strand, const uint16_t *conv_n, long long n,
+                                 long long n_barcodes, unsigned long long *first_pos, uint32_t *n_reads) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = barcode[i];
+    if (b >= (unsigned long long)n_barcodes) return;
+    const unsigned long long pos = ((unsigned long long)(strand[i] != 0) << 33) |
+                                   ((unsigned long long)(conv_n[i] == 0) << 32) | (unsigned long long)i;
+    atomicMin(first_pos + b, pos);
+    atomicAdd(n_reads + b, 1u);
+}
+
+struct DedupIn {
+    const uint4 *counts;
+    const uint8_t *strand, *transcriptome;
+    const uint16_t *score, *conv_n;
+    const uint32_t *barcode, *ord_of_barcode, *split_of_barcode;
+    long long n;
+    uint32_t conv_mask;
+    int use_conversions;
+};
+
+__global__ void order_key_kernel(DedupIn in, uint32_t *key, uint32_t *val) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const uint32_t ord = in.ord_of_barcode ? in.ord_of_barcode[in.barcode[i]] : 0u;
+    key[i] = (ord << 2) | ((uint32_t)(in.strand[i] != 0) << 1) | (uint32_t)(in.conv_n[i] == 0);
+    val[i] = (uint32_t)i;
+}
+
+// priority of read r: [has_conversions][transcriptome][score:16][conversion_sum:12], on complemented counts
+__global__ void prio_key_kernel(DedupIn in, const uint32_t *order, uint32_t *key) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const uint32_t r = order[i];
+    uint4 c = in.counts[r];
+    if (in.strand[r]) c = complement_row(c);
+    const uint32_t w[3] = {c.x, c.y, c.z};
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j)
+        if ((in.conv_mask >> j) & 1u) sum += (w[j >> 2] >> ((j & 3) << 3)) & 0xffu;
+    const uint32_t has = (in.use_conversions && sum > 0) ? 1u : 0u;
+    key[i] = (has << 29) | ((uint32_t)(in.transcriptome[r] != 0) << 28) | ((uint32_t)in.score[r] << 12) | (sum & 0xfffu);
+}
+
+__global__ void gather_u64_kernel(const unsigned long long *src, const uint32_t *idx, unsigned long long *dst, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src ? src[idx[i]] : 0ull;
+}
+
+// the last element of every run of equal (hi, lo) keys wins its UMI group
+__global__ void winner_kernel(const unsigned long long *hi, const unsigned long long *lo, const uint32_t *idx,
+                              uint8_t *win, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool last = (i + 1 == n) || lo[i] != lo[i + 1] || (hi && hi[i] != hi[i + 1]);
+    if (last) win[idx[i]] = 1;
+}
+
+__global__ void flag_kernel(const uint8_t *win, const uint32_t *order, uint8_t *flag, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = win[order[i]];
+}
+
+__global__ void final_key_kernel(DedupIn in, const uint32_t *winners, const long long *n_out, unsigned long long pad,
+                                 const unsigned long long *extra, int extra_bits, unsigned long long *key) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    if (i >= *n_out) { key[i] = pad; return; }
+    const uint32_t r = winners[i];
+    const unsigned long long split = in.split_of_barcode ? in.split_of_barcode[in.barcode[r]] : 0u;
+    key[i] = ((((split << 1) | (unsigned long long)(in.strand[r] != 0))) << extra_bits) | (extra ? extra[r] : 0ull);
+}
+
+__global__ void copy_u32_kernel(const uint32_t *src, uint32_t *dst, const long long *n_valid, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n && i < *n_valid) dst[i] = src[i];
+}
+
+inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+inline int bits_for(uint64_t max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b)) ++b;
+    return b;
+}
+
+}  // namespace
+
+extern "C" int dyn_complement_counts(dyn_ctx_t *ctx, uint8_t *d_counts, const uint8_t *d_strand, int64_t n_reads,
+                                     void *stream) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n_reads >= 0, "negative n_reads");
+    if (n_reads == 0) return DYN_OK;
+    DYN_ARG(d_counts && d_strand, "null buffer");
+    DYN_ARG((reinterpret_cast<uintptr_t>(d_counts) & 15) == 0, "counts must be 16-byte aligned");
+    complement_kernel<<<grid_for(n_reads), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<uint4 *>(d_counts), d_strand, n_reads);
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}
+
+extern "C" int dyn_barcode_first_pos(dyn_ctx_t *ctx, const uint32_t *d_barcode, const uint8_t *d_strand,
+                                     const uint16_t *d_conv_n, int64_t n_reads, int64_t n_barcodes,
+                                     uint64_t *d_first_pos, uint32_t *d_n_reads, void *stream_) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n_reads >= 0 && n_barcodes >= 0, "negative size");
+    if (n_barcodes == 0) return DYN_OK;
+    DYN_ARG(d_first_pos && d_n_reads, "null output");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DYN_CUDA(cudaMemsetAsync(d_first_pos, 0xff, sizeof(uint64_t) * n_barcodes, stream));
+    DYN_CUDA(cudaMemsetAsync(d_n_reads, 0, sizeof(uint32_t) * n_barcodes, stream));
+    if (n_reads == 0) return DYN_OK;
+    DYN_ARG(d_barcode && d_strand && d_conv_n, "null buffer");
+    first_pos_kernel<<<grid_for(n_reads), kBlock, 0, stream>>>(d_barcode, d_strand, d_conv_n, n_reads, n_barcodes,
+                                                               reinterpret_cast<unsigned long long *>(d_first_pos),
+                                                               d_n_reads);
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}
+
+extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uint64_t *d_key_lo, int key_hi_bits,
+                             int key_lo_bits, const uint8_t *d_counts, const uint8_t *d_strand,
+                             const uint8_t *d_transcriptome, const uint16_t *d_score, const uint16_t *d_conv_n,
+                             const uint32_t *d_barcode, const uint32_t *d_ord_of_barcode,
+                             const uint32_t *d_split_of_barcode, int64_t n_barcodes, int64_t n_splits,
+                             int64_t n_reads, uint32_t conv_mask, int use_conversions,
+                             const uint64_t *d_final_extra, int final_extra_bits, uint32_t *d_out_idx,
+                             int64_t *d_n_out, void *stream_) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n_reads >= 0 && n_reads < 0xffffffffLL, "n_reads out of range");
+    DYN_ARG(d_n_out != nullptr, "null n_out");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DYN_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(int64_t), stream));
+    if (n_reads == 0) return DYN_OK;
+    DYN_ARG(d_key_lo && d_counts && d_strand && d_transcriptome && d_score && d_conv_n && d_out_idx, "null buffer");
+    DYN_ARG((d_ord_of_barcode == nullptr && d_split_of_barcode == nullptr) || d_barcode, "barcode ids needed");
+    DYN_ARG(n_barcodes <= (1LL << 29), "too many barcodes");
+    if (key_lo_bits <= 0 || key_lo_bits > 64) key_lo_bits = 64;
+    if (key_hi_bits < 0 || key_hi_bits > 64) key_hi_bits = 64;
+    const bool has_hi = d_key_hi != nullptr && key_hi_bits > 0;
+    const size_t n = (size_t)n_reads;
+
+    size_t tmp_bytes = 0, t = 0;
+    {
+        cub::DoubleBuffer<uint32_t> k32(nullptr, nullptr), v32(nullptr, nullptr);
+        cub::DoubleBuffer<unsigned long long> k64(nullptr, nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, t, k32, v32, n_reads, 0, 32, stream);
+        tmp_bytes = t;
+        cub::DeviceRadixSort::SortPairs(nullptr, t, k64, v32, n_reads, 0, 64, stream);
+        if (t > tmp_bytes) tmp_bytes = t;
+        cub::DeviceSelect::Flagged(nullptr, t, (uint32_t *)nullptr, (uint8_t *)nullptr, (uint32_t *)nullptr,
+                                   (long long *)nullptr, n_reads, stream);
+        if (t > tmp_bytes) tmp_bytes = t;
+    }
+    uint32_t *k32a, *k32b, *v32a, *v32b, *order;
+    unsigned long long *k64a, *k64b, *hi_sorted;
+    uint8_t *win, *flag;
+    void *tmp;
+    Arena ar;
+    for (int pass = 0; pass < 2; ++pass) {
+        k32a = ar.take<uint32_t>(n); k32b = ar.take<uint32_t>(n);
+        v32a = ar.take<uint32_t>(n); v32b = ar.take<uint32_t>(n);
+        order = ar.take<uint32_t>(n);
+        k64a = ar.take<unsigned long long>(n); k64b = ar.take<unsigned long long>(n);
+        hi_sorted = ar.take<unsigned long long>(has_hi ? n : 1);
+        win = ar.take<uint8_t>(n); flag = ar.take<uint8_t>(n);
+        tmp = ar.take<uint8_t>(tmp_bytes);
+        if (pass == 0) {
+            void *base = nullptr;
+            int rc = dyn_ctx_scratch(ctx, 8, ar.used + 256, &base);
+            if (rc) return rc;
+            ar = Arena(base);
+        }
+    }
+
+    DedupIn in;
+    in.counts = reinterpret_cast<const uint4 *>(d_counts);
+    in.strand = d_strand; in.transcriptome = d_transcriptome; in.score = d_score; in.conv_n = d_conv_n;
+    in.barcode = d_barcode; in.ord_of_barcode = d_ord_of_barcode; in.split_of_barcode = d_split_of_barcode;
+    in.n = n_reads; in.conv_mask = conv_mask & 0xfffu; in.use_conversions = use_conversions;
+    const unsigned g = grid_for(n_reads);
+
+    // 1. split-file order: stable sort of BAM order by (barcode order, strand, no-mismatch)
+    order_key_kernel<<<g, kBlock, 0, stream>>>(in, k32a, v32a);
+    {
+        cub::DoubleBuffer<uint32_t> k(k32a, k32b), v(v32a, v32b);
+        const int bits = (d_ord_of_barcode ? bits_for((uint64_t)(n_barcodes > 0 ? n_barcodes - 1 : 0)) : 0) + 2;
+        t = tmp_bytes;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, bits, stream));
+        if (v.Current() != v32a) DYN_CUDA(cudaMemcpyAsync(v32a, v.Current(), 4 * n, cudaMemcpyDeviceToDevice, stream));
+    }
+    // 2. dedup sort: stable by priority (30 bits) -> `order` = read indices, ascending (priority, split-file order)
+    prio_key_kernel<<<g, kBlock, 0, stream>>>(in, v32a, k32a);
+    {
+        cub::DoubleBuffer<uint32_t> k(k32a, k32b), v(v32a, v32b);
+        t = tmp_bytes;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, 30, stream));
+        DYN_CUDA(cudaMemcpyAsync(order, v.Current(), 4 * n, cudaMemcpyDeviceToDevice, stream));
+    }
+    // 3. group by (barcode, umi, gene) key, stable: the last element of a run is the group's winner
+    DYN_CUDA(cudaMemcpyAsync(v32a, order, 4 * n, cudaMemcpyDeviceToDevice, stream));
+    gather_u64_kernel<<<g, kBlock, 0, stream>>>(reinterpret_cast<const unsigned long long *>(d_key_lo), v32a, k64a, n_reads);
+    uint32_t *grouped_idx;
+    unsigned long long *lo_sorted;
+    {
+        cub::DoubleBuffer<unsigned long long> k(k64a, k64b);
+        cub::DoubleBuffer<uint32_t> v(v32a, v32b);
+        t = tmp_bytes;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, key_lo_bits, stream));
+        if (has_hi) {
+            uint32_t *cur = v.Current();
+            unsigned long long *other = k.Alternate();
+            gather_u64_kernel<<<g, kBlock, 0, stream>>>(reinterpret_cast<const unsigned long long *>(d_key_hi), cur, other, n_reads);
+            cub::DoubleBuffer<unsigned long long> kh(other, k.Current());
+            t = tmp_bytes;
+            DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, kh, v, n_reads, 0, key_hi_bits, stream));
+            DYN_CUDA(cudaMemcpyAsync(hi_sorted, kh.Current(), 8 * n, cudaMemcpyDeviceToDevice, stream));
+            grouped_idx = v.Current();
+            lo_sorted = (kh.Current() == k64a) ? k64b : k64a;
+            gather_u64_kernel<<<g, kBlock, 0, stream>>>(reinterpret_cast<const unsigned long long *>(d_key_lo), grouped_idx, lo_sorted, n_reads);
+        } else {
+            grouped_idx = v.Current();
+            lo_sorted = k.Current();
+        }
+    }
+    DYN_CUDA(cudaMemsetAsync(win, 0, n, stream));
+    winner_kernel<<<g, kBlock, 0, stream>>>(has_hi ? hi_sorted : nullptr, lo_sorted, grouped_idx, win, n_reads);
+    // 4. survivors in dedup-sorted order
+    flag_kernel<<<g, kBlock, 0, stream>>>(win, order, flag, n_reads);
+    uint32_t *winners = (grouped_idx == v32a) ? v32b : v32a;
+    t = tmp_bytes;
+    DYN_CUDA(cub::DeviceSelect::Flagged(tmp, t, order, flag, winners, reinterpret_cast<long long *>(d_n_out), n_reads, stream));
+    // 5. per split: forward-strand genes first, then reverse (stable); padding keys sort to the end
+    // (an optional per-read extra key orders rows inside a (split, strand) block: the no-UMI path sorts by
+    // (barcode, GX), conversion.py:193-196)
+    if (!d_final_extra) final_extra_bits = 0;
+    if (n_splits < 1 || !d_split_of_barcode) n_splits = 1;
+    const int top_bits = bits_for((uint64_t)(2 * n_splits));
+    DYN_ARG(final_extra_bits >= 0 && top_bits + final_extra_bits <= 64, "final key does not fit 64 bits");
+    const unsigned long long pad = (top_bits + final_extra_bits == 64) ? ~0ull : ((unsigned long long)(2 * n_splits) << final_extra_bits);
+    final_key_kernel<<<g, kBlock, 0, stream>>>(in, winners, reinterpret_cast<const long long *>(d_n_out), pad,
+                                               reinterpret_cast<const unsigned long long *>(d_final_extra), final_extra_bits, k64a);
+    {
+        uint32_t *valt = (winners == v32a) ? v32b : v32a;
+        cub::DoubleBuffer<unsigned long long> k(k64a, k64b);
+        cub::DoubleBuffer<uint32_t> v(winners, valt);
+        t = tmp_bytes;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, top_bits + final_extra_bits, stream));
+        copy_u32_kernel<<<g, kBlock, 0, stream>>>(v.Current(), d_out_idx, reinterpret_cast<const long long *>(d_n_out), n_reads);
+    }
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}

@@ -133,3 +133,194 @@ def em_pc(ctx: Context, k: torch.Tensor, n: torch.Tensor, count: torch.Tensor, o
                           ptr(status), ptr(iters), _stream())
     )
     return p_c, status, iters
+
+
+# --------------------------------------------------------------------------------------------------
+# count -> estimate stages after the tally (all asynchronous on the current torch stream)
+# --------------------------------------------------------------------------------------------------
+CONVERSION_COLUMNS = ['AC', 'AG', 'AT', 'CA', 'CG', 'CT', 'GA', 'GC', 'GT', 'TA', 'TC', 'TG']
+BASE_COLUMNS = ['A', 'C', 'G', 'T']
+
+
+def conv_mask(conversions) -> int:
+    """12-bit column mask of an iterable of conversions ('TC', ...); None -> all columns."""
+    if conversions is None:
+        return 0xfff
+    m = 0
+    for c in conversions:
+        m |= 1 << CONVERSION_COLUMNS.index(c)
+    return m
+
+
+def base_mask(conversions) -> int:
+    m = 0
+    for c in conversions:
+        m |= 1 << BASE_COLUMNS.index(c[0])
+    return m
+
+
+def _bits(max_value: int) -> int:
+    return max(1, int(max_value).bit_length())
+
+
+def count_records(ctx: Context, conv_rec, conv_read, conv_contig, counts, quality=27, snps=None):
+    """dyn_count_records: adds the quality/SNP-filtered mismatch records to counts[:, :12] in place.
+    Returns the status tensor (int32 scalar on the device)."""
+    status = torch.zeros(1, dtype=torch.int32, device=counts.device)
+    check(
+        ctx.lib.dyn_count_records(ctx.handle, ptr(conv_rec), ptr(conv_read), ptr(conv_contig), conv_rec.numel(),
+                                  counts.shape[0], ptr(snps), 0 if snps is None else snps.numel(), int(quality),
+                                  ptr(counts), ptr(status), _stream())
+    )
+    return status
+
+
+def complement_counts(ctx: Context, counts: torch.Tensor, strand: torch.Tensor):
+    """dyn_complement_counts, in place."""
+    check(ctx.lib.dyn_complement_counts(ctx.handle, ptr(counts), ptr(strand), counts.shape[0], _stream()))
+    return counts
+
+
+def barcode_first_pos(ctx: Context, barcode, strand, conv_n, n_barcodes: int):
+    dev = barcode.device
+    first = torch.empty(n_barcodes, dtype=torch.int64, device=dev)
+    n_reads = torch.empty(n_barcodes, dtype=torch.int32, device=dev)
+    check(ctx.lib.dyn_barcode_first_pos(ctx.handle, ptr(barcode), ptr(strand), ptr(conv_n), barcode.numel(), n_barcodes,
+                                        ptr(first), ptr(n_reads), _stream()))
+    return first, n_reads
+
+
+def split_plan(first_pos: np.ndarray, n_reads: np.ndarray, threshold: int = 50000):
+    """Barcode order and split assignment of conversion.py:543-579 (sequential packing; host side, O(barcodes)).
+    Returns (ord_of_barcode, split_of_barcode, n_splits); barcodes without reads get the last rank."""
+    B = len(first_pos)
+    present = n_reads > 0
+    order = np.argsort(np.where(present, first_pos.view(np.uint64), np.uint64(2**63)), kind='stable')
+    split_of = np.zeros(B, dtype=np.uint32)
+    n_splits = 0
+    cur = -1
+    cur_size = 0
+    for b in order:
+        if not present[b]:
+            continue
+        if n_reads[b] > threshold:
+            split_of[b] = n_splits
+            n_splits += 1
+        elif cur < 0:
+            cur = n_splits
+            n_splits += 1
+            split_of[b] = cur
+        else:
+            split_of[b] = cur
+            cur_size += int(n_reads[b])
+            if cur_size > threshold:
+                cur = -1
+                cur_size = 0
+    ord_of = np.empty(B, dtype=np.uint32)
+    # split-file order: by split, then first appearance
+    keys = np.lexsort((np.argsort(order), split_of)) if B else np.zeros(0, dtype=np.int64)
+    ord_of[keys] = np.arange(B, dtype=np.uint32)
+    return ord_of, split_of, max(n_splits, 1)
+
+
+def dedup(ctx: Context, key_lo, counts, strand, transcriptome, score, conv_n, barcode, n_barcodes, conversions=None,
+          use_conversions=True, key_hi=None, key_lo_bits=64, key_hi_bits=0, final_extra=None, final_extra_bits=0,
+          split_threshold=50000):
+    """a5 + a6 on device tensors. Returns the surviving read indices (int32 tensor) in output row order."""
+    n = counts.shape[0]
+    dev = counts.device
+    first, n_reads = barcode_first_pos(ctx, barcode, strand, conv_n, n_barcodes)
+    ord_of, split_of, n_splits = split_plan(first.cpu().numpy(), n_reads.cpu().numpy(), split_threshold)
+    ord_of_d = torch.from_numpy(ord_of.view(np.int32)).to(dev)
+    split_of_d = torch.from_numpy(split_of.view(np.int32)).to(dev)
+    out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    use = 1 if (use_conversions and conversions is not None) else 0
+    check(
+        ctx.lib.dyn_dedup_umi(ctx.handle, ptr(key_hi), ptr(key_lo), int(key_hi_bits), int(key_lo_bits), ptr(counts),
+                              ptr(strand), ptr(transcriptome), ptr(score), ptr(conv_n), ptr(barcode), ptr(ord_of_d),
+                              ptr(split_of_d), n_barcodes, n_splits, n, conv_mask(conversions), use, ptr(final_extra),
+                              int(final_extra_bits), ptr(out), ptr(n_out), _stream())
+    )
+    return out[:int(n_out.item())]
+
+
+def group_sums(ctx: Context, counts, strand, group, n_groups: int, sel=None, conversions=None):
+    """dyn_group_sums -> (sums [G,16] int64, n_reads [G] int64, n_with [G] int64)."""
+    dev = counts.device
+    sums = torch.empty((n_groups, 16), dtype=torch.int64, device=dev)
+    n_reads = torch.empty(n_groups, dtype=torch.int64, device=dev)
+    n_with = torch.empty(n_groups, dtype=torch.int64, device=dev)
+    n_sel = counts.shape[0] if sel is None else sel.numel()
+    check(ctx.lib.dyn_group_sums(ctx.handle, ptr(counts), ptr(strand), ptr(group), ptr(sel), n_sel, n_groups,
+                                 conv_mask(conversions), ptr(sums), ptr(n_reads), ptr(n_with), _stream()))
+    return sums, n_reads, n_with
+
+
+def rates_pe(ctx: Context, sums, pe_conversions=None):
+    """dyn_rates_pe -> (rates [G,12] float64, p_e [G] float64)."""
+    G = sums.shape[0]
+    rates = torch.empty((G, 12), dtype=torch.float64, device=sums.device)
+    p_e = torch.empty(G, dtype=torch.float64, device=sums.device)
+    mask = 0 if pe_conversions is None else conv_mask(pe_conversions)
+    check(ctx.lib.dyn_rates_pe(ctx.handle, ptr(sums), G, mask, ptr(rates), ptr(p_e), _stream()))
+    return rates, p_e
+
+
+def alpha(ctx: Context, n_reads, n_with, pi_c):
+    out = torch.empty(n_reads.numel(), dtype=torch.float64, device=n_reads.device)
+    check(ctx.lib.dyn_alpha(ctx.handle, ptr(n_reads), ptr(n_with), ptr(pi_c), n_reads.numel(), ptr(out), _stream()))
+    return out
+
+
+def aggregate_kn(ctx: Context, counts, strand, group, gene, n_groups: int, n_genes: int, conversions, sel=None,
+                 exclude=None, first_appearance=True):
+    """dyn_aggregate_kn -> (group, gene, k, n, count, first) int64 tensors, one row per distinct key."""
+    dev = counts.device
+    n_sel = counts.shape[0] if sel is None else sel.numel()
+    gene_bits = _bits(max(n_genes - 1, 0)) if gene is not None else 0
+    group_bits = _bits(max(n_groups - 1, 0))
+    keys = torch.empty(max(n_sel, 1), dtype=torch.int64, device=dev)
+    cnt = torch.empty(max(n_sel, 1), dtype=torch.int32, device=dev)
+    first = torch.empty(max(n_sel, 1), dtype=torch.int32, device=dev)
+    n_rows = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(
+        ctx.lib.dyn_aggregate_kn(ctx.handle, ptr(counts), ptr(strand), ptr(group), ptr(gene), ptr(sel), n_sel,
+                                 conv_mask(conversions), base_mask(conversions),
+                                 0 if not exclude else conv_mask(exclude), group_bits, gene_bits,
+                                 1 if first_appearance else 0, ptr(keys), ptr(cnt), ptr(first), ptr(n_rows), _stream())
+    )
+    m = int(n_rows.item())
+    k64 = keys[:m]
+    return dict(
+        group=(k64 >> (22 + gene_bits)), gene=((k64 >> 22) & ((1 << gene_bits) - 1)) if gene_bits else torch.zeros_like(k64),
+        k=(k64 >> 10) & 0xfff, n=k64 & 0x3ff, count=cnt[:m].to(torch.int64), first=first[:m].to(torch.int64),
+        keys=k64, count32=cnt[:m], n_rows=n_rows,
+    )
+
+
+def kn_csr(ctx: Context, keys, count32, n_rows, n_groups: int):
+    """dyn_kn_csr on key-sorted rows without gene bits -> (k, n, count, off, total)."""
+    dev = keys.device
+    m = keys.numel()
+    k = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+    n = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+    c = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    off = torch.empty(n_groups + 1, dtype=torch.int64, device=dev)
+    total = torch.empty(max(n_groups, 1), dtype=torch.int64, device=dev)
+    check(ctx.lib.dyn_kn_csr(ctx.handle, ptr(keys), ptr(count32), ptr(n_rows), m, n_groups, ptr(k), ptr(n), ptr(c),
+                             ptr(off), ptr(total), _stream()))
+    return k[:m], n[:m], c[:m], off, total[:n_groups]
+
+
+def pi_fit(ctx: Context, k, n, count, off, p_e, p_c, max_cells=None):
+    """dyn_pi_fit -> (alpha_beta_pi [G,3] float64, status [G] int32)."""
+    G = off.numel() - 1
+    dev = off.device
+    out = torch.empty((G, 3), dtype=torch.float64, device=dev)
+    status = torch.empty(G, dtype=torch.int32, device=dev)
+    if max_cells is None:
+        max_cells = int((off[1:] - off[:-1]).max().item()) if G else 1
+    check(ctx.lib.dyn_pi_fit(ctx.handle, ptr(k), ptr(n), ptr(count), ptr(off), G, int(max_cells), ptr(p_e), ptr(p_c),
+                             ptr(out), ptr(status), _stream()))
+    return out, status

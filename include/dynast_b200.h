@@ -151,6 +151,104 @@ int dyn_em_pc_host(dyn_ctx_t *ctx, const int32_t *h_k, const int32_t *h_n, const
                    int32_t *h_em_status, int32_t *h_iters);
 
 /* ------------------------------------------------------------------------------------------------
+ * a3, file-based entry: conversion counters from mismatch records (the rows of conversions.csv), for
+ * callers of count_conversions that hold the reference's CSV interchange rather than packed BAM records.
+ * Replaces conversion.count_conversions_part's per-line loop (conversion.py:417-426).  d_counts [n_reads][16]
+ * must hold zeros in columns 0..11 and the A/C/G/T content in 12..15; record layout = DYN_CONV_* above;
+ * d_conv_contig = contig id of each record for the SNP key (may be NULL when n_snps == 0).
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_count_records(dyn_ctx_t *ctx, const uint64_t *d_conv_rec, const uint32_t *d_conv_read,
+                      const uint32_t *d_conv_contig, int64_t n_records, int64_t n_reads, const uint64_t *d_snps,
+                      int64_t n_snps, int quality, uint8_t *d_counts, uint32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a4: strand complement (conversion.complement_counts, conversion.py:99-125), in place on the 16-byte
+ * counter rows: for reads whose gene lies on '-' (d_strand[i] != 0) the 12 conversion columns and the
+ * 4 base columns are reversed (AC<->TG, AG<->TC, ..., A<->T, C<->G).  An involution.  The row ORDER
+ * change of the reference (forward rows first) is applied by dyn_dedup_umi, not here.
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_complement_counts(dyn_ctx_t *ctx, uint8_t *d_counts, const uint8_t *d_strand, int64_t n_reads, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a6 helper: per barcode, the smallest frame position of its reads and its read count.  Frame position
+ * of read i = (strand << 33) | ((conv_n == 0) << 32) | i  -- the row order of the combined, complemented
+ * counts frame (conversion.py:533-541).  The host turns this into the barcode order / split assignment of
+ * conversion.py:543-579 (a sequential packing over <= n_barcodes entries).
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_barcode_first_pos(dyn_ctx_t *ctx, const uint32_t *d_barcode, const uint8_t *d_strand, const uint16_t *d_conv_n,
+                          int64_t n_reads, int64_t n_barcodes, uint64_t *d_first_pos, uint32_t *d_n_reads, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a5 + a6: UMI deduplication and output ordering.
+ * Replaces conversion.deduplicate_counts (conversion.py:203-243) as driven by count_conversions
+ * (conversion.py:541-606).  Group key of read i = (d_key_hi[i], d_key_lo[i]) = interned (barcode, umi, GX)
+ * (d_key_hi may be NULL; *_bits = number of significant low bits).  Priority, on COMPLEMENTED counters:
+ * ([has_conversions,] transcriptome, score, conversion_sum) with conversion_sum over the columns of
+ * conv_mask (bit j = column j of DYN_N_COUNTERS order); use_conversions adds has_conversions.
+ *   d_counts            original-orientation rows (complemented on the fly with d_strand)
+ *   d_conv_n            number of mismatch records of the read (0 -> the read sits in the second block)
+ *   d_ord_of_barcode    [n_barcodes] rank of the barcode in split-file order; d_split_of_barcode its split
+ *                       (both NULL: one split, barcodes unordered -- only valid for a single barcode)
+ *   d_final_extra       optional per-read key (final_extra_bits wide) ordering rows inside a (split, strand)
+ *                       block before the priority order: the no-UMI path (conversion.drop_multimappers,
+ *                       conversion.py:148-200) groups by read id, use_conversions = 0, and sorts survivors
+ *                       by (barcode, GX) -- pass the rank of that pair here; NULL for the UMI path
+ *   d_out_idx [n_reads] surviving read indices in counts_{convs}.csv row order; *d_n_out their number
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uint64_t *d_key_lo, int key_hi_bits, int key_lo_bits,
+                  const uint8_t *d_counts, const uint8_t *d_strand, const uint8_t *d_transcriptome,
+                  const uint16_t *d_score, const uint16_t *d_conv_n, const uint32_t *d_barcode,
+                  const uint32_t *d_ord_of_barcode, const uint32_t *d_split_of_barcode, int64_t n_barcodes,
+                  int64_t n_splits, int64_t n_reads, uint32_t conv_mask, int use_conversions,
+                  const uint64_t *d_final_extra, int final_extra_bits, uint32_t *d_out_idx, int64_t *d_n_out,
+                  void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a9 / a11 / a16: per-group reductions over selected reads (d_sel: read indices, NULL = all reads).
+ * dyn_group_sums: 16-column sums (aggregation.py:74-79, p_e.py:72-76), number of reads and number of
+ * reads with any conversion of conv_mask (alpha.py:72-75) per group.  d_strand != NULL complements.
+ * dyn_rates_pe: rates[g][j] = sum_j / sum_base(j) (aggregation.py:82-85) and p_e[g] = NaN-skipping mean of
+ * the rates selected by pe_mask (p_e.py:82-93); sums are truncated to uint32 as the reference does.
+ * dyn_alpha: alpha[g] = (n_with / n_reads) / pi_c[g], NaN where pi_c <= 0 or missing (alpha.py:76-84).
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_group_sums(dyn_ctx_t *ctx, const uint8_t *d_counts, const uint8_t *d_strand, const uint32_t *d_group,
+                   const uint32_t *d_sel, int64_t n_sel, int64_t n_groups, uint32_t conv_mask, uint64_t *d_sums,
+                   uint64_t *d_n_reads, uint64_t *d_n_with, void *stream);
+int dyn_rates_pe(dyn_ctx_t *ctx, const uint64_t *d_sums, int64_t n_groups, uint32_t pe_mask, double *d_rates,
+                 double *d_p_e, void *stream);
+int dyn_alpha(dyn_ctx_t *ctx, const uint64_t *d_n_reads, const uint64_t *d_n_with, const double *d_pi_c,
+              int64_t n_groups, double *d_alpha, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a10: (group, gene, k, n) read counts (aggregation.aggregate_counts, aggregation.py:92-119).
+ * k = sum of the conv_mask columns, n = sum of the base_mask columns (bit j = base column 12 + j); reads
+ * with a non-zero exclude_mask column are skipped (estimate.py:248-255).  Row key =
+ * ((group << gene_bits | gene) << 22) | (k << 10) | n.  Rows come out in first-appearance order
+ * (groupby(sort=False)) or, with first_appearance_order == 0, sorted by key.  d_first = position (in the
+ * selection) of the first read of the row.  Outputs need room for n_sel rows.
+ * dyn_kn_csr turns key-sorted rows with gene_bits == 0 into the EM / pi input: triplets (k, n, count),
+ * offsets d_off[n_groups + 1] and per-group read totals.
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_aggregate_kn(dyn_ctx_t *ctx, const uint8_t *d_counts, const uint8_t *d_strand, const uint32_t *d_group,
+                     const uint32_t *d_gene, const uint32_t *d_sel, int64_t n_sel, uint32_t conv_mask,
+                     uint32_t base_mask, uint32_t exclude_mask, int group_bits, int gene_bits,
+                     int first_appearance_order, uint64_t *d_keys, uint32_t *d_count, uint32_t *d_first,
+                     int64_t *d_n_rows, void *stream);
+int dyn_kn_csr(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count, const int64_t *d_n_rows,
+               int64_t max_rows, int64_t n_groups, int32_t *d_k, int32_t *d_n, int64_t *d_cnt, int64_t *d_off,
+               uint64_t *d_total, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a15: batched labeled-fraction fit -- posterior means of (alpha, beta, pi_g) of dynast/models/pi.stan
+ * (pi.stan:4-34) for every group, replacing pi.fit_stan_mcmc (pi.py:118-187).  Group g owns triplets
+ * [d_off[g], d_off[g+1]) of (k, n, count) and its own p_e / p_c.  Deterministic quadrature, see csrc/pi.cu.
+ * d_status: 0 ok, 1 empty group, 2 degenerate (p outside (0,1) / zero evidence), 3 more than max_cells.
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_pi_fit(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n, const int64_t *d_count, const int64_t *d_off,
+               int64_t n_groups, int64_t max_cells, const double *d_p_e, const double *d_p_c, double *d_alpha_beta_pi,
+               int32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic input generator (bench / test utility; not on the timed path). Generates packed records
  * for the BASELINE configs directly in HBM; every decision is a pure function of (seed, read index).
  * Model: SURVEY.md section 8d (C2) after dynast/benchmarking/simulation.py:22-79.

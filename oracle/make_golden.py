@@ -146,12 +146,149 @@ def em_golden():
     print('em_golden: ok', sts.count(0), 'p_c<=p_e', sts.count(1), 'zerodiv', sts.count(2))
 
 
+def _write_gz(path, text):
+    with open(path, 'wb') as raw:
+        with gzip.GzipFile(fileobj=raw, mode='wb', mtime=0) as fo:
+            fo.write(text.encode())
+
+
+def synth_counts_case(name, seed, n_reads, umi=True, dup_read_ids=False, with_snps=False, conversions=frozenset({'TC'}),
+                      use_conversions=True, threshold=60):
+    """Synthetic conversions.csv / alignments.csv / conversions.idx -> the REFERENCE's count_conversions, rates,
+    aggregates, p_e and alpha on them (tie-heavy UMI groups, +/- genes, several splits)."""
+    import pickle
+    import tempfile
+    import pandas as pd
+    import dynast.config as config
+    import dynast.preprocessing.conversion as conv
+    import dynast.preprocessing.aggregation as agg
+    import dynast.estimation.p_e as p_e
+    import dynast.estimation.alpha as alpha
+    rng = np.random.default_rng(seed)
+    out_dir = os.path.join(GOLD, 'synth_counts', name)
+    os.makedirs(out_dir, exist_ok=True)
+    genes = {f'G{i:02d}': {'strand': '+' if i % 3 else '-', 'chromosome': f'chr{i % 4}'} for i in range(9)}
+    gene_names = list(genes)
+    bc_w = np.array([40, 25, 10, 8, 5, 4, 3, 2, 1.5, 1, 0.3, 0.2])
+    bcs = [''.join(rng.choice(list('ACGT'), 8)) for _ in bc_w]
+    ali_lines, conv_lines, index = [], [], []
+    ali_pos = len('read_id,index,barcode,umi,GX,A,C,G,T,velocity,transcriptome,score\n')
+    conv_pos = len('read_id,index,contig,genome_i,conversion,quality\n')
+    letters = 'ACGT'
+    prev_id = None
+    for i in range(n_reads):
+        rid = f'read{i:06d}'
+        if dup_read_ids and prev_id is not None and rng.random() < 0.03:
+            rid = prev_id
+        prev_id = rid
+        bc = bcs[rng.choice(len(bcs), p=bc_w / bc_w.sum())]
+        um = ''.join(rng.choice(list('ACGT'), 2)) if umi else 'NA'   # 16 UMIs -> many duplicates
+        gx = gene_names[int(rng.integers(0, len(gene_names)))]
+        content = rng.integers(8, 30, 4)
+        vel = ['spliced', 'unspliced', 'ambiguous'][int(rng.integers(0, 3))]
+        tr = bool(rng.random() < 0.6)
+        score = int(rng.integers(55, 60))
+        m = int(rng.poisson(0.9))
+        if m:
+            start = conv_pos
+            for _ in range(m):
+                a = int(rng.integers(0, 4))
+                b = (a + int(rng.integers(1, 4))) % 4
+                if rng.random() < 0.5:
+                    a, b = (3, 1) if genes[gx]['strand'] == '+' else (0, 2)
+                line = f'{rid},1,{genes[gx]["chromosome"]},{int(rng.integers(0, 400))},{letters[a]}{letters[b]},{int(rng.integers(20, 41))}\n'
+                conv_lines.append(line)
+                conv_pos += len(line)
+            index.append((start, m, ali_pos))
+        line = f'{rid},1,{bc},{um},{gx},{content[0]},{content[1]},{content[2]},{content[3]},{vel},{tr},{score}\n'
+        ali_lines.append(line)
+        ali_pos += len(line)
+    ali_text = 'read_id,index,barcode,umi,GX,A,C,G,T,velocity,transcriptome,score\n' + ''.join(ali_lines)
+    conv_text = 'read_id,index,contig,genome_i,conversion,quality\n' + ''.join(conv_lines)
+    snps = None
+    if with_snps:
+        snps = {}
+        for line in conv_lines[::7]:
+            f = line.strip().split(',')
+            snps.setdefault(f[4], {}).setdefault(f[2], set()).add(int(f[3]))
+    tmp = tempfile.mkdtemp()
+    ap, cp, ip, op = (os.path.join(tmp, x) for x in ('alignments.csv', 'conversions.csv', 'conversions.idx', 'counts.csv'))
+    open(ap, 'w').write(ali_text)
+    open(cp, 'w').write(conv_text)
+    with gzip.open(ip, 'wb') as f:
+        pickle.dump(index, f)
+    old = config.COUNTS_SPLIT_THRESHOLD
+    config.COUNTS_SPLIT_THRESHOLD = threshold
+    try:
+        conv.count_conversions(cp, ap, ip, op, genes, snps=snps, quality=27, conversions=conversions,
+                               dedup_use_conversions=use_conversions, n_threads=2, temp_dir=tmp)
+    finally:
+        config.COUNTS_SPLIT_THRESHOLD = old
+    counts_text = open(op).read()
+    _write_gz(os.path.join(out_dir, 'alignments.csv.gz'), ali_text)
+    _write_gz(os.path.join(out_dir, 'conversions.csv.gz'), conv_text)
+    _write_gz(os.path.join(out_dir, 'counts.csv.gz'), counts_text)
+    meta = dict(index=index, genes=genes, snps={c: {k: sorted(v) for k, v in d.items()} for c, d in (snps or {}).items()},
+                conversions=sorted(conversions) if conversions is not None else None, use_conversions=use_conversions,
+                threshold=threshold)
+    with open(os.path.join(out_dir, 'meta.json'), 'w') as f:
+        json.dump(meta, f)
+    # downstream stages of the reference on its own counts
+    df = conv.complement_counts(conv.read_counts(op), genes)
+    convs = conversions if conversions is not None else frozenset({'TC'})
+    agg.calculate_mutation_rates(df, os.path.join(tmp, 'rates.csv'), group_by='barcode')
+    agg.aggregate_counts(df, os.path.join(tmp, 'A.csv'), conversions=convs)
+    p_e.estimate_p_e(df, os.path.join(tmp, 'p_e.csv'), conversions=frozenset({convs}), group_by=['barcode'])
+    pi_c = {bc: 0.1 + 0.05 * i for i, bc in enumerate(sorted(set(df['barcode'])))}
+    pi_c[sorted(pi_c)[0]] = 0.0
+    alpha.estimate_alpha(df, pi_c, os.path.join(tmp, 'alpha.csv'), convs, group_by=['barcode'], pi_c_group_by=['barcode'])
+    for f in ('rates.csv', 'A.csv', 'p_e.csv', 'alpha.csv'):
+        _write_gz(os.path.join(out_dir, f + '.gz'), open(os.path.join(tmp, f)).read())
+    with open(os.path.join(out_dir, 'pi_c.json'), 'w') as f:
+        json.dump(pi_c, f)
+    print('synth_counts', name, len(counts_text.splitlines()) - 1, 'rows')
+
+
+def synth_counts():
+    synth_counts_case('umi_tc', 31, 2500, with_snps=True)
+    synth_counts_case('umi_exon', 32, 2500, use_conversions=False)
+    synth_counts_case('umi_dual', 33, 2000, conversions=frozenset({'TC', 'AG'}))
+    synth_counts_case('umi_noconv', 34, 1500, conversions=None)
+    synth_counts_case('noumi', 35, 1500, umi=False, conversions=None)
+    synth_counts_case('noumi_dups', 36, 1500, umi=False, dup_read_ids=True)
+
+
+def pi_golden():
+    """Posterior means of pi.stan by QUADPACK (oracle/pi_oracle.py) on seeded histograms of several shapes."""
+    from oracle import pi_oracle
+    rng = np.random.default_rng(515)
+    cases = []
+    for reads, pi, pc, pe in [(16, 0.3, 0.05, 1e-3), (40, 0.0, 0.04, 5e-4), (60, 1.0, 0.06, 2e-3), (300, 0.2, 0.03, 1e-3),
+                              (300, 0.85, 0.08, 2e-4), (2500, 0.5, 0.05, 1e-3), (2500, 0.02, 0.05, 1.5e-3), (20000, 0.3, 0.02, 2e-3)]:
+        n = np.clip(rng.poisson(23, reads), 1, 150)
+        lab = rng.random(reads) < pi
+        k = rng.binomial(n, np.where(lab, pc, pe))
+        key, cnt = np.unique(k.astype(np.int64) * 1024 + n, return_counts=True)
+        cases.append((key // 1024, key % 1024, cnt, pe * rng.uniform(0.8, 1.2), pc * rng.uniform(0.8, 1.2)))
+    ks, ns, cs, off, pes, pcs, out = [], [], [], [0], [], [], []
+    for k, n, c, pe, pc in cases:
+        out.append(pi_oracle.posterior_means(k, n, c, pe, pc))
+        ks.append(k); ns.append(n); cs.append(c); off.append(off[-1] + len(k)); pes.append(pe); pcs.append(pc)
+        print('pi_golden', len(out), out[-1])
+    np.savez_compressed(os.path.join(GOLD, 'pi_golden.npz'), k=np.concatenate(ks).astype(np.int32),
+                        n=np.concatenate(ns).astype(np.int32), count=np.concatenate(cs).astype(np.int64),
+                        off=np.asarray(off, dtype=np.int64), p_e=np.asarray(pes), p_c=np.asarray(pcs),
+                        alpha_beta_pi=np.asarray(out))
+
+
 def main():
     refstub.install()
     os.makedirs(GOLD, exist_ok=True)
     copy_fixtures()
     gene_strands()
     em_golden()
+    synth_counts()
+    pi_golden()
 
 
 if __name__ == '__main__':

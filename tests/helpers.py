@@ -75,3 +75,46 @@ def oracle_em_batch(lib, k, n, count, off, p_e, nasc=False):
     lib.dyn_oracle_em_batch(k.ctypes.data, n.ctypes.data, count.ctypes.data, off.ctypes.data, B, p_e.ctypes.data,
                             1 if nasc else 0, p_c.ctypes.data, status.ctypes.data)
     return p_c, status
+
+
+def materialize(tmp_path, *parts, name=None):
+    """Write a (possibly gzip-stored) golden file to tmp_path uncompressed; returns the path."""
+    src = os.path.join(GOLDEN, *parts)
+    dst = os.path.join(str(tmp_path), name or parts[-1].replace('.gz', ''))
+    if os.path.exists(src + '.gz'):
+        src += '.gz'
+    if src.endswith('.gz'):
+        with gzip.open(src, 'rb') as f, open(dst, 'wb') as out:
+            out.write(f.read())
+    else:
+        with open(src, 'rb') as f, open(dst, 'wb') as out:
+            out.write(f.read())
+    return dst
+
+
+def golden_text(*parts) -> str:
+    p = os.path.join(GOLDEN, *parts)
+    if os.path.exists(p + '.gz'):
+        p += '.gz'
+    if p.endswith('.gz'):
+        with gzip.open(p, 'rt') as f:
+            return f.read()
+    with open(p) as f:
+        return f.read()
+
+
+def synth_case_meta(name):
+    import pickle
+    with open(os.path.join(GOLDEN, 'synth_counts', name, 'meta.json')) as f:
+        meta = json.load(f)
+    meta['index'] = [tuple(x) for x in meta['index']]
+    meta['snps'] = {c: {k: set(v) for k, v in d.items()} for c, d in meta['snps'].items()} or None
+    return meta
+
+
+def write_index(tmp_path, index, name='conversions.idx'):
+    import pickle
+    p = os.path.join(str(tmp_path), name)
+    with gzip.open(p, 'wb') as f:
+        pickle.dump(list(index), f)
+    return p

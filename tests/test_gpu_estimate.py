@@ -1,0 +1,112 @@
+"""GPU: the estimate stage operators (p_e, p_c, alpha, pi) against the reference's fixtures and its own outputs
+on synthetic inputs. Mirrors tests/estimation/test_p_e.py:20-61, test_p_c.py:28-65, test_alpha.py:17-30."""
+import io
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from helpers import GOLDEN, gene_infos, golden_text, materialize, ref_text, synth_case_meta
+
+pytestmark = pytest.mark.gpu
+
+
+def test_estimate_p_e_fixture(gpu_ctx, tmp_path):
+    from dynast_b200.estimation import p_e
+    from dynast_b200.preprocessing import conversion
+    counts = materialize(tmp_path, 'ref', 'SRR11683995_count', 'counts_TC.csv')
+    df = conversion.complement_counts(conversion.read_counts(counts), gene_infos())
+    path = p_e.estimate_p_e(df, str(tmp_path / 'p_e.csv'), conversions=frozenset({frozenset({'TC'})}), group_by=['barcode'])
+    got = p_e.read_p_e(path, group_by=['barcode'])
+    want = pd.read_csv(io.StringIO(ref_text('SRR11683995_estimate', 'p_e.csv')), dtype={'barcode': 'category'})
+    assert len(got) == len(want)
+    for barcode, value in zip(want['barcode'], want['p_e']):
+        assert got[barcode] == value or (np.isnan(value) and np.isnan(got[barcode]))
+
+
+def test_estimate_p_e_control_fixture(gpu_ctx, tmp_path):
+    from dynast_b200.estimation import p_e
+    from dynast_b200.preprocessing import conversion
+    counts = materialize(tmp_path, 'ref', 'SRR11683995_count_control', 'counts_TC.csv')
+    df = conversion.complement_counts(conversion.read_counts(counts), gene_infos())
+    path = p_e.estimate_p_e_control(df, str(tmp_path / 'p_e.csv'), conversions=frozenset({'TC'}))
+    assert p_e.read_p_e(path) == float(ref_text('SRR11683995_estimate_control', 'p_e.csv'))
+
+
+@pytest.mark.parametrize('name', ['umi_tc', 'umi_dual', 'noumi'])
+def test_p_e_alpha_synthetic_bytes(gpu_ctx, tmp_path, name):
+    from dynast_b200.estimation import alpha, p_e
+    from dynast_b200.preprocessing import conversion
+    meta = synth_case_meta(name)
+    counts = materialize(tmp_path, 'synth_counts', name, 'counts.csv')
+    df = conversion.complement_counts(conversion.read_counts(counts), meta['genes'])
+    convs = frozenset(meta['conversions']) if meta['conversions'] is not None else frozenset({'TC'})
+    path = p_e.estimate_p_e(df, str(tmp_path / 'p_e.csv'), conversions=frozenset({convs}), group_by=['barcode'])
+    assert open(path).read() == golden_text('synth_counts', name, 'p_e.csv')
+    with open(os.path.join(GOLDEN, 'synth_counts', name, 'pi_c.json')) as f:
+        pi_c = json.load(f)
+    path = alpha.estimate_alpha(df, pi_c, str(tmp_path / 'alpha.csv'), convs, group_by=['barcode'], pi_c_group_by=['barcode'])
+    assert open(path).read() == golden_text('synth_counts', name, 'alpha.csv')
+
+
+def test_estimate_alpha_fixture_bytes(gpu_ctx, tmp_path):
+    from dynast_b200.estimation import alpha, pi
+    from dynast_b200.preprocessing import conversion
+    counts = materialize(tmp_path, 'ref', 'SRR11683995_count', 'counts_TC.csv')
+    df = conversion.complement_counts(conversion.read_counts(counts), gene_infos())
+    pi_path = materialize(tmp_path, 'ref', 'SRR11683995_estimate_alpha', 'pi_total_TC.csv')
+    _, _, pi_c = pi.read_pi(pi_path, group_by=['barcode'])
+    path = alpha.estimate_alpha(df, pi_c, str(tmp_path / 'alpha.csv'), frozenset(['TC']), group_by=['barcode'],
+                                pi_c_group_by=['barcode'])
+    assert open(path).read() == ref_text('SRR11683995_estimate_alpha', 'alpha_total_TC.csv')
+
+
+@pytest.mark.parametrize('est_dir,agg,nasc', [
+    ('SRR11683995_estimate', 'A_total_TC.csv', False),
+    ('nasc_estimate', 'A_transcriptome_TC.csv', True),
+])
+def test_estimate_p_c_fixture(gpu_ctx, tmp_path, est_dir, agg, nasc):
+    """Reference tolerance: rtol 1e-5 (test_p_c.py:45); north star: 1e-6. The committed CSV itself is 1.0e-6 away
+    from what the reference computes with today's numba, hence 2.5e-6 here; bit-exact
+    agreement with the reference run in this container is asserted in test_gpu_em.py."""
+    from dynast_b200.estimation import p_c, p_e
+    from dynast_b200.preprocessing import aggregation
+    df = aggregation.read_aggregates(materialize(tmp_path, 'ref', est_dir, agg))
+    pe = p_e.read_p_e(materialize(tmp_path, 'ref', est_dir, 'p_e.csv'), group_by=['barcode'])
+    path = p_c.estimate_p_c(df, pe, str(tmp_path / 'p_c.csv'), group_by=['barcode'], threshold=0, n_threads=2, nasc=nasc)
+    want = pd.read_csv(io.StringIO(ref_text(est_dir, 'p_c_TC.csv')))
+    got = pd.read_csv(path)
+    assert list(got['barcode']) == list(want['barcode'])
+    np.testing.assert_allclose(got['p_c'].values, want['p_c'].values, rtol=2.5e-6)
+
+
+def test_estimate_pi_against_quadpack(gpu_ctx, tmp_path):
+    """Posterior means of pi.stan against an independent QUADPACK / Gauss-Legendre integration (golden values
+    produced by oracle/pi_oracle.py); parity with the reference's MCMC is unpinned (its tests mock Stan)."""
+    from dynast_b200.estimation import pi
+    g = np.load(os.path.join(GOLDEN, 'pi_golden.npz'))
+    vals, status = pi.fit_batch(g['k'], g['n'], g['count'], g['off'], g['p_e'], g['p_c'])
+    assert (status == 0).all()
+    np.testing.assert_allclose(vals, g['alpha_beta_pi'], rtol=1e-6)
+
+
+def test_estimate_pi_fixture_monte_carlo(gpu_ctx, tmp_path):
+    """The fixture pi_*.csv are unseeded NUTS posterior means (1000 draws): agreement is statistical."""
+    from dynast_b200.estimation import p_c, p_e, pi
+    from dynast_b200.preprocessing import aggregation
+    est = 'SRR11683995_estimate_alpha'
+    df = aggregation.read_aggregates(materialize(tmp_path, 'ref', est, 'A_total_TC.csv'))
+    pe = p_e.read_p_e(materialize(tmp_path, 'ref', est, 'p_e.csv'), group_by=['barcode'])
+    pc = p_c.read_p_c(materialize(tmp_path, 'ref', est, 'p_c_TC.csv'), group_by=['barcode'])
+    want = pd.read_csv(io.StringIO(ref_text(est, 'pi_total_TC.csv')))
+    df = df.drop(columns='GX').groupby(['barcode', 'conversion', 'base'], sort=False, observed=True).sum().reset_index()
+    path = pi.estimate_pi(df, pe, pc, str(tmp_path / 'pi.csv'), group_by=['barcode'], p_group_by=['barcode'], threshold=16)
+    got = pd.read_csv(path)
+    assert list(got.columns) == ['barcode', 'alpha', 'beta', 'pi']
+    m = got.merge(want, on='barcode', suffixes=('', '_ref'))
+    assert len(m) == len(want) == len(got)
+    assert np.abs(m['pi'] - m['pi_ref']).max() < 0.03
+    assert np.abs(m['pi'] - m['pi_ref']).mean() < 0.006
+    assert np.abs(np.log(m['alpha'] / m['alpha_ref'])).mean() < 0.1
