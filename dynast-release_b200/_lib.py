@@ -115,3 +115,20 @@ def ptr(arr):
     if hasattr(arr, 'data_ptr'):
         return C.c_void_p(arr.data_ptr())
     return C.c_void_p(arr.ctypes.data)
+
+
+def current_device_index() -> int:
+    """Index of the current CUDA device (the operators run on torch's current device)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise DynastB200Error('no CUDA device: dynast_b200 has no CPU fallback')
+    return torch.cuda.current_device()
+
+
+def current_context() -> Context:
+    return Context.get(current_device_index())
+
+
+def current_torch_device():
+    import torch
+    return torch.device('cuda', current_device_index())

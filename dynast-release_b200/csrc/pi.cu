@@ -96,22 +96,31 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
         const int cells = (int)(t1 - t0);
         const double p_e = p.p_e[g], p_c = p.p_c[g];
         double *out = p.out + g * 3;
-        if (cells <= 0 || cells > p.max_cells || !(p_e > 0.0) || !(p_c > 0.0) || !(p_e < 1.0) || !(p_c < 1.0)) {
+        // pi.stan:9-10: p_c, p_e in [0, 1]; binomial_lpmf(k | n, 0) is 0 for k == 0 and -inf otherwise
+        if (cells <= 0 || cells > p.max_cells || !(p_e >= 0.0) || !(p_c >= 0.0) || !(p_e <= 1.0) || !(p_c <= 1.0)) {
             if (tid == 0) { out[0] = out[1] = out[2] = nan(""); p.status[g] = cells <= 0 ? 1 : (cells > p.max_cells ? 3 : 2); }
             continue;
         }
         const double lpc = log(p_c), lqc = log1p(-p_c), lpe = log(p_e), lqe = log1p(-p_e);
-        double total = 0.0;
+        double total = 0.0, impossible = 0.0;
         for (int i = tid; i < cells; i += kPiThreads) {
             const double k = (double)p.k[t0 + i], n = (double)p.n[t0 + i];
-            const double la = k * lpc + (n - k) * lqc, lb = k * lpe + (n - k) * lqe;
+            // x * log(y) with 0 * log(0) = 0
+            const double la = (k > 0.0 ? k * lpc : 0.0) + (n - k > 0.0 ? (n - k) * lqc : 0.0);
+            const double lb = (k > 0.0 ? k * lpe : 0.0) + (n - k > 0.0 ? (n - k) * lqe : 0.0);
             const double m = fmax(la, lb);
             const long long c = p.count[t0 + i];
             const bool ok = c > 0 && n > 0.0 && k <= n;      // pi.py:223: base > 0 and count > 0
-            ca[i] = exp(la - m); cb[i] = exp(lb - m); cc[i] = ok ? (double)c : 0.0;
+            if (ok && !(m > -INFINITY)) impossible += 1.0;   // the cell has probability zero under both rates
+            ca[i] = (m > -INFINITY) ? exp(la - m) : 1.0; cb[i] = (m > -INFINITY) ? exp(lb - m) : 1.0; cc[i] = ok ? (double)c : 0.0;
             total += cc[i];
         }
         total = block_sum(total, red);
+        impossible = block_sum(impossible, red);
+        if (impossible > 0.0) {   // Stan cannot initialise: the reference drops the group (pi.py:298-304)
+            if (tid == 0) { out[0] = out[1] = out[2] = nan(""); p.status[g] = 2; }
+            continue;
+        }
         if (!(total > 0.0)) {
             if (tid == 0) { out[0] = out[1] = out[2] = nan(""); p.status[g] = 1; }
             continue;
@@ -281,7 +290,7 @@ static int pi_tables(dyn_ctx *ctx, cudaStream_t stream, const double **gl_x, con
             }
         // tanh-sinh on (0, 1): s = 1 / (1 + exp(-2u)), u = (pi/2) sinh t, t = (j - J) h
         const int J = (kNJ - 1) / 2;
-        const double T = 6.2, hstep = T / J;
+        const double T = 6.0, hstep = T / J;   // smallest node ~1e-275: pi^(alpha-1) stays finite for alpha >= e^-3
         double *s = h.data() + 2 * kNA + kNA * kNA, *c = s + kNJ, *ww = c + kNJ;
         for (int j = 0; j < kNJ; ++j) {
             const double t = (j - J) * hstep, u = 0.5 * M_PI * sinh(t);

@@ -6,7 +6,7 @@ import pandas as pd
 import torch
 
 from .. import pipeline
-from .._lib import Context
+from .. import _lib
 from ..preprocessing.aggregation import group_sums
 from ._groups import group_codes, lookup
 
@@ -38,7 +38,7 @@ def estimate_alpha(
     keep = ~np.isnan(pic_rows)
     df = df[keep]
     pic_rows = pic_rows[keep]
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     if group_by is None:
         if not isinstance(pi_c, float):
             raise Exception('`pi_c` and `p_c` must be a float when `group_by` is not provided')

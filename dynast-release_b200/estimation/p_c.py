@@ -6,6 +6,8 @@ import numpy as np
 import pandas as pd
 import torch
 
+from .. import _lib
+
 from .. import device
 from ._groups import csr_from_rows, group_codes, lookup
 
@@ -38,7 +40,7 @@ def estimate_p_c(
     totals = np.where(off[1:] > off[:-1], totals, 0)
     pe = lookup(p_e, keys, 1)
     if group_by is None:
-        p_c, status, _ = device.em_pc_host(k, n, c, off, pe, nasc=nasc, device=torch.cuda.current_device())
+        p_c, status, _ = device.em_pc_host(k, n, c, off, pe, nasc=nasc, device=_lib.current_device_index())
         if status[0] == 1:
             raise ValueError('p_c <= p_e')
         if status[0] != 0:
@@ -57,7 +59,7 @@ def estimate_p_c(
     np.cumsum(lens, out=sub_off[1:])
     take = np.concatenate([np.arange(off[g], off[g + 1]) for g in sel]) if len(sel) else np.zeros(0, dtype=np.int64)
     p_c, status, _ = device.em_pc_host(k[take], n[take], c[take], sub_off, pe[sel], nasc=nasc,
-                                       device=torch.cuda.current_device())
+                                       device=_lib.current_device_index())
     p_cs = {keys[g]: float(p_c[i]) for i, g in enumerate(sel) if status[i] == 0}
     with open(p_c_path, 'w') as f:
         f.write(f'{",".join(group_by)},p_c\n')

@@ -5,7 +5,7 @@ import pandas as pd
 import torch
 
 from .. import pipeline
-from .._lib import Context
+from .. import _lib
 from ..preprocessing.aggregation import group_sums
 from ..preprocessing.conversion import BASE_COLUMNS, CONVERSION_COLUMNS
 
@@ -54,7 +54,7 @@ def estimate_p_e(df_counts: pd.DataFrame, p_e_path: str,
     columns = [c for c in CONVERSION_COLUMNS if c[0] not in bases]
     if bases == BASE_COLUMNS:
         columns = [c for c in CONVERSION_COLUMNS if c not in flattened]
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     keys, sums, _, _ = group_sums(df_counts, group_by)
     _, p_e = pipeline.rates_pe(ctx, sums, pe_conversions=columns)
     p_e = p_e.cpu().numpy()

@@ -10,7 +10,7 @@ import pandas as pd
 import torch
 
 from .. import pipeline
-from .._lib import Context
+from .. import _lib
 from ._groups import csr_from_rows, group_codes, lookup
 
 
@@ -50,8 +50,8 @@ def guess_beta_parameters(guess: float, strength: int = 5) -> Tuple[float, float
 
 def fit_batch(k, n, count, off, p_e, p_c):
     """Posterior means (alpha, beta, pi) for CSR groups on the current device. Returns (values [G,3], status [G])."""
-    dev = torch.device('cuda', torch.cuda.current_device())
-    ctx = Context.get(torch.cuda.current_device())
+    dev = _lib.current_torch_device()
+    ctx = _lib.current_context()
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     out, status = pipeline.pi_fit(ctx, t(k.astype(np.int32)), t(n.astype(np.int32)), t(count.astype(np.int64)),
                                   t(off.astype(np.int64)), t(np.asarray(p_e, dtype=np.float64)),

@@ -223,16 +223,28 @@ def split_plan(first_pos: np.ndarray, n_reads: np.ndarray, threshold: int = 5000
     return ord_of, split_of, max(n_splits, 1)
 
 
-def dedup(ctx: Context, key_lo, counts, strand, transcriptome, score, conv_n, barcode, n_barcodes, conversions=None,
-          use_conversions=True, key_hi=None, key_lo_bits=64, key_hi_bits=0, final_extra=None, final_extra_bits=0,
-          split_threshold=50000):
-    """a5 + a6 on device tensors. Returns the surviving read indices (int32 tensor) in output row order."""
-    n = counts.shape[0]
-    dev = counts.device
+def plan_splits(ctx: Context, barcode, strand, conv_n, n_barcodes: int, split_threshold=50000):
+    """Barcode order / split assignment (conversion.py:543-579) of a counts frame on the device.
+    Returns (ord_of_barcode, split_of_barcode, n_splits) with the two tables on the device."""
     first, n_reads = barcode_first_pos(ctx, barcode, strand, conv_n, n_barcodes)
     ord_of, split_of, n_splits = split_plan(first.cpu().numpy(), n_reads.cpu().numpy(), split_threshold)
-    ord_of_d = torch.from_numpy(ord_of.view(np.int32)).to(dev)
-    split_of_d = torch.from_numpy(split_of.view(np.int32)).to(dev)
+    dev = barcode.device
+    return (torch.from_numpy(ord_of.view(np.int32)).to(dev), torch.from_numpy(split_of.view(np.int32)).to(dev), n_splits)
+
+
+def dedup(ctx: Context, key_lo, counts, strand, transcriptome, score, conv_n, barcode, n_barcodes, conversions=None,
+          use_conversions=True, key_hi=None, key_lo_bits=64, key_hi_bits=0, final_extra=None, final_extra_bits=0,
+          split_threshold=50000, plan=None):
+    """a5 + a6 on device tensors. Returns the surviving read indices (int32 tensor) in output row order.
+    `plan` = plan_splits(...) of the frame the splits were cut from (defaults to this frame)."""
+    n = counts.shape[0]
+    dev = counts.device
+    if barcode is None:   # one split, input order is the tie-break (conversion.deduplicate_counts on a frame)
+        ord_of_d = split_of_d = None
+        n_splits, n_barcodes = 1, 0
+    else:
+        ord_of_d, split_of_d, n_splits = plan if plan is not None else plan_splits(ctx, barcode, strand, conv_n, n_barcodes,
+                                                                                   split_threshold)
     out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     n_out = torch.zeros(1, dtype=torch.int64, device=dev)
     use = 1 if (use_conversions and conversions is not None) else 0

@@ -7,7 +7,7 @@ import pandas as pd
 import torch
 
 from .. import pipeline
-from .._lib import Context
+from .. import _lib
 from .conversion import BASE_COLUMNS, COLUMNS, CONVERSION_COLUMNS, _counts_to_device, _device
 
 
@@ -49,7 +49,7 @@ def _group_ids(df: pd.DataFrame, group_by):
 
 def group_sums(df_counts: pd.DataFrame, group_by, conversions=None):
     """Device reduction shared by rates / p_e / alpha: returns (keys frame, sums [G,16], n_reads, n_with)."""
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     ids, keys = _group_ids(df_counts, group_by)
     G = 1 if keys is None else len(keys)
     counts = _counts_to_device(df_counts)
@@ -60,7 +60,7 @@ def group_sums(df_counts: pd.DataFrame, group_by, conversions=None):
 
 def calculate_mutation_rates(df_counts: pd.DataFrame, rates_path: str, group_by: Optional[List[str]] = None) -> str:
     """aggregation.calculate_mutation_rates (aggregation.py:61-89); df_counts is the complemented frame."""
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     keys, sums, _, _ = group_sums(df_counts, group_by)
     rates, _ = pipeline.rates_pe(ctx, sums)
     df_rates = pd.DataFrame(rates.cpu().numpy(), columns=CONVERSION_COLUMNS)
@@ -73,7 +73,7 @@ def calculate_mutation_rates(df_counts: pd.DataFrame, rates_path: str, group_by:
 def aggregate_counts(df_counts: pd.DataFrame, aggregates_path: str, conversions: FrozenSet[str] = frozenset({'TC'})) -> str:
     """aggregation.aggregate_counts (aggregation.py:92-119): rows (barcode, GX, conversion=k, base=n, count) in
     first-appearance order."""
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     bc, bc_names = pd.factorize(df_counts['barcode'].astype(object), sort=False)
     gx, gx_names = pd.factorize(df_counts['GX'].astype(object), sort=False)
     counts = _counts_to_device(df_counts)

@@ -13,7 +13,7 @@ import pandas as pd
 import torch
 
 from .. import pipeline, records
-from .._lib import Context
+from .. import _lib
 
 CONVERSION_COLUMNS = records.CONVERSION_COLUMNS
 BASE_COLUMNS = records.BASE_COLUMNS
@@ -24,10 +24,12 @@ _COMP = {'A': 'T', 'C': 'G', 'G': 'C', 'T': 'A'}
 CONVERSION_COMPLEMENT = {c: _COMP[c[0]] + _COMP[c[1]] for c in CONVERSION_COLUMNS}
 CSV_COLUMNS = ['read_id', 'barcode', 'umi', 'GX'] + COLUMNS + ['velocity', 'transcriptome', 'score']
 COUNTS_SPLIT_THRESHOLD = 50000   # dynast/config.py:51
+_PANDAS_NA_STRINGS = ['-1.#IND', '1.#QNAN', '1.#IND', '-1.#QNAN', '#N/A N/A', '#N/A', 'N/A', 'n/a', 'NA', '<NA>', '#NA', 'NULL',
+                      'null', 'NaN', '-NaN', 'nan', '-nan', 'None', '']
 
 
 def _device():
-    return torch.device('cuda', torch.cuda.current_device())
+    return _lib.current_torch_device()
 
 
 def read_counts(counts_path: str, *args, **kwargs) -> pd.DataFrame:
@@ -71,7 +73,7 @@ def complement_counts(df_counts: pd.DataFrame, gene_infos: dict) -> pd.DataFrame
     the device; rows come back forward-strand first, then reverse (original index kept)."""
     other = [c for c in df_counts.columns if c not in COLUMNS]
     strand = _strand_array(df_counts['GX'], gene_infos)
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     counts = _counts_to_device(df_counts)
     pipeline.complement_counts(ctx, counts, torch.from_numpy(strand).to(counts.device))
     out = df_counts[other].copy()
@@ -116,16 +118,17 @@ def _group_key(parts):
 
 
 def _dedup_frame(df: pd.DataFrame, strand: np.ndarray, conv_n: np.ndarray, conversions, use_conversions: bool, umi: bool,
-                 counts_complemented: bool, split_threshold: int):
-    """Runs dyn_dedup_umi for a counts frame. Returns surviving row positions in output order."""
-    ctx = Context.get(torch.cuda.current_device())
+                 counts_complemented: bool, split_threshold: int, barcode_ids=None, plan=None):
+    """Runs dyn_dedup_umi for a counts frame. Returns surviving row positions in output order.
+    barcode_ids = (ids, n) and plan = pipeline.plan_splits(...) when the splits were cut from a larger frame."""
+    ctx = _lib.current_context()
     dev = _device()
     n = len(df)
     counts = _counts_to_device(df)
     strand_d = torch.from_numpy(np.ascontiguousarray(strand, dtype=np.uint8)).to(dev)
     if counts_complemented:   # the kernel wants original orientation and complements on the fly
         pipeline.complement_counts(ctx, counts, strand_d)
-    bc, n_bc = _intern(df['barcode'])
+    bc, n_bc = barcode_ids if barcode_ids is not None else _intern(df['barcode'])
     score = df['score'].to_numpy(dtype=np.int64)
     if n and (score.min() < 0 or score.max() > 65535):
         raise ValueError('alignment score outside uint16 range (the reference reads it as uint16)')
@@ -150,7 +153,7 @@ def _dedup_frame(df: pd.DataFrame, strand: np.ndarray, conv_n: np.ndarray, conve
         to(score.astype(np.uint16), np.int16), to(conv_n.astype(np.uint16), np.int16), to(bc, np.int32), n_bc,
         conversions=conversions, use_conversions=use_conversions, key_hi=None if hi is None else to(hi, np.int64),
         key_lo_bits=lo_bits, key_hi_bits=hi_bits, final_extra=None if extra is None else to(extra, np.int64),
-        final_extra_bits=extra_bits, split_threshold=split_threshold)
+        final_extra_bits=extra_bits, split_threshold=split_threshold, plan=plan)
     return out.cpu().numpy().astype(np.int64)
 
 
@@ -165,29 +168,22 @@ def deduplicate_counts(df_counts: pd.DataFrame, conversions: Optional[FrozenSet[
 
 
 def _dedup_frame_plain(df, conversions, use_conversions):
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     dev = _device()
     n = len(df)
     counts = _counts_to_device(df)
-    zeros8 = torch.zeros(n, dtype=torch.uint8, device=dev)
     bc, n_bc = _intern(df['barcode'])
     um, n_um = _intern(df['umi'])
     gx, n_gx = _intern(df['GX'])
     hi, lo, hi_bits, lo_bits = _group_key([(bc, n_bc), (um, n_um), (gx, n_gx)])
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(dev)
-    out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
-    from .._lib import check, ptr
-    import ctypes as C
-    use = 1 if (use_conversions and conversions is not None) else 0
-    score = t(df['score'].to_numpy(dtype=np.int64).astype(np.uint16), np.int16)
-    tr = t(df['transcriptome'].to_numpy(dtype=bool).astype(np.uint8), np.uint8)
-    ones16 = torch.ones(n, dtype=torch.int16, device=dev)
-    check(ctx.lib.dyn_dedup_umi(ctx.handle, ptr(None if hi is None else t(hi, np.int64)), ptr(t(lo, np.int64)), hi_bits,
-                                lo_bits, ptr(counts), ptr(zeros8), ptr(tr), ptr(score), ptr(ones16), None, None, None, 0, 1,
-                                n, pipeline.conv_mask(conversions), use, None, 0, ptr(out), ptr(n_out),
-                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    return out[:int(n_out.item())].cpu().numpy().astype(np.int64)
+    out = pipeline.dedup(
+        ctx, t(lo, np.int64), counts, torch.zeros(n, dtype=torch.uint8, device=dev),
+        t(df['transcriptome'].to_numpy(dtype=bool).astype(np.uint8), np.uint8),
+        t(df['score'].to_numpy(dtype=np.int64).astype(np.uint16), np.int16), torch.ones(n, dtype=torch.int16, device=dev),
+        None, 0, conversions=conversions, use_conversions=use_conversions, key_hi=None if hi is None else t(hi, np.int64),
+        key_lo_bits=lo_bits, key_hi_bits=hi_bits)
+    return out.cpu().numpy().astype(np.int64)
 
 
 def drop_multimappers(df_counts: pd.DataFrame, conversions: Optional[FrozenSet[str]] = None) -> pd.DataFrame:
@@ -263,7 +259,7 @@ def count_conversions(
 
     # mismatch records of the indexed reads
     dev = _device()
-    ctx = Context.get(torch.cuda.current_device())
+    ctx = _lib.current_context()
     conv = pd.read_csv(conversions_path, dtype={'read_id': 'string', 'contig': object, 'conversion': object}, na_filter=False)
     conv_starts = _line_starts(conversions_path)[1:len(conv) + 1]
     first_line = np.searchsorted(conv_starts, idx[:, 0])
@@ -308,13 +304,24 @@ def count_conversions(
     frame[COLUMNS] = counts_d.cpu().numpy()
 
     umi = bool((frame['umi'] != 'NA').all())
+    strand = _strand_array(frame['GX'], gene_infos)
+    # splits are cut from the whole frame (conversion.py:543-579), before any per-split rule drops rows
+    bc, n_bc = _intern(frame['barcode'])
+    tdev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(dev)
+    plan = pipeline.plan_splits(ctx, tdev(bc, np.int32), tdev(strand, np.uint8), tdev(conv_n.astype(np.uint16), np.int16),
+                                n_bc, COUNTS_SPLIT_THRESHOLD) if len(frame) else None
     if not umi:   # conversion.py:542 -> drop_multimappers path
         frame['_row'] = np.arange(len(frame))
         frame = _multimapper_rules(frame)
-        conv_n = conv_n[frame['_row'].to_numpy()]
+        rows = frame['_row'].to_numpy()
+        conv_n, strand, bc = conv_n[rows], strand[rows], bc[rows]
         frame = frame.drop(columns='_row').reset_index(drop=True)
-    strand = _strand_array(frame['GX'], gene_infos)
     keep = _dedup_frame(frame, strand, conv_n, conversions, dedup_use_conversions, umi, counts_complemented=False,
-                        split_threshold=COUNTS_SPLIT_THRESHOLD)
-    frame.iloc[keep][CSV_COLUMNS[1:]].to_csv(counts_path, header=True, index=False)
+                        split_threshold=COUNTS_SPLIT_THRESHOLD, barcode_ids=(bc, n_bc), plan=plan)
+    out = frame.iloc[keep][CSV_COLUMNS[1:]].copy()
+    # The reference re-reads every split with pandas' default NA parsing before the final write
+    # (conversion.py:604-605), so strings such as the 'NA' umi placeholder come out as empty cells.
+    for col in ('barcode', 'umi', 'GX', 'velocity'):
+        out[col] = out[col].where(~out[col].isin(_PANDAS_NA_STRINGS), '')
+    out.to_csv(counts_path, header=True, index=False)
     return counts_path

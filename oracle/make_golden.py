@@ -178,10 +178,10 @@ def synth_counts_case(name, seed, n_reads, umi=True, dup_read_ids=False, with_sn
     prev_id = None
     for i in range(n_reads):
         rid = f'read{i:06d}'
-        if dup_read_ids and prev_id is not None and rng.random() < 0.03:
-            rid = prev_id
-        prev_id = rid
         bc = bcs[rng.choice(len(bcs), p=bc_w / bc_w.sum())]
+        if dup_read_ids and prev_id is not None and rng.random() < 0.03:
+            rid, bc = prev_id, prev_bc   # a multimapping read keeps its barcode
+        prev_id, prev_bc = rid, bc
         um = ''.join(rng.choice(list('ACGT'), 2)) if umi else 'NA'   # 16 UMIs -> many duplicates
         gx = gene_names[int(rng.integers(0, len(gene_names)))]
         content = rng.integers(8, 30, 4)

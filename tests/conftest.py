@@ -33,3 +33,22 @@ def gpu_ctx():
     assert torch.cuda.is_available(), 'gpu-marked test run without a CUDA device'
     from dynast_b200._lib import Context
     return Context.get(0)
+
+
+@pytest.fixture
+def fake_gpu(monkeypatch, oracle_lib):
+    """Host-logic tests: numpy stand-ins for the device stages (tests/fake_device.py). CPU only."""
+    import fake_device
+    fake_device.install(monkeypatch)
+    return True
+
+
+@pytest.fixture(params=['cpu-host-logic', pytest.param('gpu', marks=pytest.mark.gpu)])
+def backend(request):
+    """Operator tests run twice: against the real kernels (-m gpu) and, for the host logic alone, against the
+    numpy stand-ins (-m 'not gpu')."""
+    if request.param == 'gpu':
+        request.getfixturevalue('gpu_ctx')
+    else:
+        request.getfixturevalue('fake_gpu')
+    return request.param
