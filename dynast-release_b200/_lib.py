@@ -38,6 +38,7 @@ PROTOTYPES = {
                                 _vp, _vp]),
     'dyn_kn_csr': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_pi_fit': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'dyn_consensus': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
     'dyn_synth_fill': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -1,0 +1,364 @@
+// UMI consensus calling.
+//
+// Replaces dynast/preprocessing/consensus.py:57-200 (call_consensus_from_reads: a Python loop over
+// get_aligned_pairs of every read plus a Python loop over every reference position of the group's span,
+// run in worker processes fed with SAM strings).
+//
+// On the device this is the sort / segmented-reduce the north star names:
+//   1. expand   one thread per member read walks CIGAR + MD (walker.cuh) and emits one tuple per aligned
+//               or deleted reference base: key = (group << 32 | reference position), value = (Phred, read
+//               base, reference base, deletion flag).  Bases the reference skips (reference N, read N,
+//               consensus.py:79-91) emit a sentinel key.  Per group min start / max end by atomics.
+//   2. sort     cub::DeviceRadixSort on the 64-bit keys (stable: within a position tuples stay in the
+//               group's read order, so "first seen reference base" is the first tuple of a run).
+//   3. reduce   one thread per run of equal keys: the four quality sums, the consensus call with the tie
+//               rules of consensus.py:137-146, quality clipped to 42 -> one 32-bit cell per covered position.
+//   4. assemble one thread per group walks its cells: run-length CIGAR (gaps become N ops), MD and NM exactly
+//               as consensus.py:116-176 builds them, 4-bit sequence and qualities -> one packed record
+//               (the same layout the tally reads, so `dynast count` can run on the result without a BAM
+//               round trip).  Sizes first, exclusive scan, then the write pass.
+// HBM-bound on the sort: 12 B per base tuple, moved ~2 x 8 radix passes; algorithmic bytes = the group's
+// packed records in + one record out.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "walker.cuh"
+
+namespace {
+
+constexpr int kBlock = 128;
+inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+constexpr unsigned long long kInvalid = ~0ull;
+
+// tuple value: [0..7] Phred, [8..11] read base (BAM nibble), [12..15] reference base, [16] deletion
+__device__ __forceinline__ uint32_t pack_val(uint32_t q, uint32_t rn, uint32_t gn, uint32_t del) {
+    return (q & 0xff) | (rn << 8) | (gn << 12) | (del << 16);
+}
+
+__device__ __forceinline__ long long group_of(const long long *group_off, long long n_groups, long long item) {
+    long long lo = 0, hi = n_groups;   // last g with group_off[g] <= item
+    while (lo + 1 < hi) { const long long mid = (lo + hi) >> 1; if (group_off[mid] <= item) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void size_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
+                            long long n_items, unsigned long long *tuple_cnt, uint32_t *g_left, uint32_t *g_right, int32_t *g_ref,
+                            int32_t *status) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
+    const uint4 h = *reinterpret_cast<const uint4 *>(rec);
+    const uint32_t n_cigar = h.z >> 16;
+    const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
+    uint32_t n_ref = 0, span = 0;
+    for (uint32_t c = 0; c < n_cigar; ++c) {
+        const uint32_t op = cig[c] & 0xf, len = cig[c] >> 4;
+        if (op == 0 || op == 2 || op == 7 || op == 8) { n_ref += len; span += len; }
+        else if (op == 3) span += len;
+    }
+    tuple_cnt[i] = n_ref;
+    const long long g = group_of(group_off, n_groups, i);
+    atomicMin(g_left + g, h.x);
+    atomicMax(g_right + g, h.x + span);
+    const int old = atomicCAS(g_ref + g, -1, (int)h.y);
+    if (old != -1 && old != (int)h.y) status[g] = 4;   // reads on several contigs: the reference raises (consensus.py:57-58)
+}
+
+__global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
+                              long long n_items, const unsigned long long *tuple_off, unsigned long long *key, uint32_t *val,
+                              int32_t *status) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
+    const long long g = group_of(group_off, n_groups, i);
+    unsigned long long o = tuple_off[i];
+    const unsigned long long end = tuple_off[i + 1];
+    Walker w;
+    w.init(rec, (size_t)1 << 40);   // sizes were validated by the packer / the tally
+    int kind;
+    while (o < end && (kind = w.next_event()) != 0) {
+        const uint32_t gn = w.gn;
+        unsigned long long k = kInvalid;
+        uint32_t v = 0;
+        const int gi = base_idx(gn);
+        if (kind == 2) {
+            if (gi >= 0) { k = ((unsigned long long)g << 32) | (uint32_t)w.cr; v = pack_val(0, 0, gn, 1); }
+        } else if (gi >= 0 && base_idx(w.rn) >= 0) {
+            k = ((unsigned long long)g << 32) | (uint32_t)w.cr; v = pack_val(w.q, w.rn, gn, 0);
+        }
+        key[o] = k; val[o] = v; ++o;
+    }
+    if (w.bad) status[g] = 2;
+    for (; o < end; ++o) { key[o] = kInvalid; val[o] = 0; }
+}
+
+__global__ void head_kernel(const unsigned long long *key, long long n, uint32_t *flag) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (key[i] != kInvalid && (i == 0 || key[i] != key[i - 1])) ? 1u : 0u;
+}
+
+// cell: [0..1] consensus base, [2..3] reference base, [4] deletion, [8..15] quality
+__global__ void reduce_kernel(const unsigned long long *key, const uint32_t *val, const uint32_t *flag, const uint32_t *idx,
+                              long long n, int quality, unsigned long long *cell_key, uint32_t *cell) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const unsigned long long k = key[i];
+    uint32_t s[4] = {0, 0, 0, 0};
+    const int ref = base_idx((val[i] >> 12) & 0xf);    // first seen (consensus.py:84-90)
+    for (long long j = i; j < n && key[j] == k; ++j) {
+        const uint32_t v = val[j];
+        if (!((v >> 16) & 1u)) s[base_idx((v >> 8) & 0xf)] += v & 0xffu;
+    }
+    uint32_t out;
+    const uint32_t base_q = max(max(s[0], s[1]), max(s[2], s[3]));
+    if (base_q == 0) out = ((uint32_t)ref << 2) | (1u << 4);     // no support: deletion (consensus.py:113-123)
+    else {
+        int base;
+        if ((int)base_q < quality) base = ref;
+        else if (s[ref] == base_q) base = ref;                   // ties: reference if present
+        else base = s[0] == base_q ? 0 : (s[1] == base_q ? 1 : (s[2] == base_q ? 2 : 3));
+        out = (uint32_t)base | ((uint32_t)ref << 2) | (min(base_q, 42u) << 8);
+    }
+    cell_key[idx[i]] = k;
+    cell[idx[i]] = out;
+}
+
+struct GroupOut { uint32_t n_cigar, l_seq, md_len, nm; };
+
+__device__ __forceinline__ int num_digits(uint32_t v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
+__device__ __forceinline__ uint8_t *put_num(uint8_t *p, uint32_t v) {
+    const int d = num_digits(v);
+    for (int i = d - 1; i >= 0; --i) { p[i] = (uint8_t)('0' + v % 10); v /= 10; }
+    return p + d;
+}
+
+// One thread per group. WRITE=false: sizes only (stored in `sizes`); WRITE=true: the record at out + 16 * out_off[g].
+template <bool WRITE>
+__global__ void assemble_kernel(const unsigned long long *cell_key, const uint32_t *cell, const long long *n_cells_p,
+                                long long n_groups, const uint32_t *g_left, const uint32_t *g_right, const int32_t *g_ref,
+                                GroupOut *sizes, uint32_t *out_cap16, const uint32_t *out_off, uint8_t *out,
+                                long long out_capacity16, uint32_t *out_nm, int32_t *status) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const long long n_cells = *n_cells_p;
+    long long lo = 0, hi = n_cells;      // first cell of group g
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)(cell_key[mid] >> 32) < g) lo = mid + 1; else hi = mid; }
+    const long long c0 = lo;
+    const uint32_t left = g_left[g], right = g_right[g];
+    const bool empty = left == 0xffffffffu;      // group without reads
+    uint32_t *cig = nullptr;
+    uint8_t *seq = nullptr, *qual = nullptr, *md = nullptr;
+    GroupOut sz = {0, 0, 0, 0};
+    bool fits = true;
+    if (WRITE) {
+        sz = sizes[g];
+        if ((long long)out_off[g + 1] > out_capacity16 || status[g] == 3) fits = false;
+        uint8_t *rec = out + ((size_t)out_off[g] << 4);
+        if (fits) {
+            uint32_t *h = reinterpret_cast<uint32_t *>(rec);
+            h[0] = empty ? 0u : left;
+            h[1] = (uint32_t)g_ref[g];
+            h[2] = sz.l_seq | (sz.n_cigar << 16);
+            h[3] = sz.md_len;      // flag 0: the caller sets strand / tags
+            cig = reinterpret_cast<uint32_t *>(rec + 16);
+            seq = rec + 16 + 4 * (size_t)sz.n_cigar;
+            const size_t seq_bytes = pad4(((size_t)sz.l_seq + 1) >> 1);
+            for (size_t b = 0; b < seq_bytes; ++b) seq[b] = 0;
+            qual = seq + seq_bytes;
+            md = qual + sz.l_seq;
+            const size_t used = 16 + 4 * (size_t)sz.n_cigar + seq_bytes + sz.l_seq + sz.md_len;
+            for (size_t b = used; b < (((size_t)out_off[g + 1] - out_off[g]) << 4); ++b) rec[b] = 0;
+            out_nm[g] = sz.nm;
+        }
+    }
+    uint32_t n_cigar = 0, l_seq = 0, md_len = 0, nm = 0;
+    uint32_t run_op = 0xffu, run_n = 0;     // ops: 0 M, 2 D, 3 N (BAM codes)
+    uint32_t md_n = 0;
+    bool md_zero = true, md_del = false;
+    uint8_t *mdp = md;
+    auto cigar_push = [&](uint32_t op, uint32_t n) {
+        if (n == 0) return;
+        if (op == run_op) { run_n += n; return; }
+        if (run_op != 0xffu) { if (WRITE && fits) cig[n_cigar] = (run_n << 4) | run_op; ++n_cigar; }
+        run_op = op; run_n = n;
+    };
+    auto md_number = [&]() {
+        if (md_n > 0 || md_zero) {
+            if (WRITE && fits) mdp = put_num(mdp, md_n);
+            md_len += num_digits(md_n);
+            md_n = 0;
+        }
+    };
+    uint32_t prev = left;    // next expected reference position
+    if (!empty) {
+        for (long long c = c0; c < n_cells && (long long)(cell_key[c] >> 32) == g; ++c) {
+            const uint32_t pos = (uint32_t)cell_key[c], v = cell[c];
+            cigar_push(3, pos - prev);                 // positions nobody observed (consensus.py:109-111)
+            prev = pos + 1;
+            const uint32_t ref = (v >> 2) & 3u;
+            if ((v >> 4) & 1u) {
+                cigar_push(2, 1);
+                md_number();
+                if (!md_del) { if (WRITE && fits) *mdp++ = '^'; ++md_len; }
+                if (WRITE && fits) *mdp++ = (uint8_t)"ACGT"[ref];
+                ++md_len;
+                md_del = true;
+            } else {
+                cigar_push(0, 1);
+                md_del = false;
+                const uint32_t base = v & 3u;
+                if (base == ref) { ++md_n; md_zero = false; }
+                else {
+                    md_number();
+                    if (WRITE && fits) *mdp++ = (uint8_t)"ACGT"[ref];
+                    ++md_len;
+                    md_zero = true;
+                    ++nm;
+                }
+                if (WRITE && fits) {
+                    seq[l_seq >> 1] |= (uint8_t)((1u << base) << ((l_seq & 1) ? 0 : 4));
+                    qual[l_seq] = (uint8_t)((v >> 8) & 0xff);
+                }
+                ++l_seq;
+            }
+        }
+        cigar_push(3, right - prev);
+    }
+    // MD always ends with a number (consensus.py:175); the last CIGAR run is flushed (:176)
+    if (WRITE && fits) mdp = put_num(mdp, md_n);
+    md_len += num_digits(md_n);
+    if (run_op != 0xffu) { if (WRITE && fits) cig[n_cigar] = (run_n << 4) | run_op; ++n_cigar; }
+    if (!WRITE) {
+        GroupOut o = {n_cigar, l_seq, md_len, nm};
+        sizes[g] = o;
+        const size_t bytes = 16 + 4 * (size_t)n_cigar + pad4(((size_t)l_seq + 1) >> 1) + l_seq + md_len;
+        out_cap16[g] = (uint32_t)((bytes + 15) >> 4);
+        if (n_cigar > 0xffffu || l_seq > 0xffffu || md_len > 0xffffu) status[g] = 3;   // does not fit a BAM record
+    } else if (!fits && status[g] == 0) status[g] = 5;   // output capacity exceeded
+}
+
+__global__ void init_groups_kernel(uint32_t *g_left, uint32_t *g_right, int32_t *g_ref, int32_t *status, long long n) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    g_left[g] = 0xffffffffu; g_right[g] = 0u; g_ref[g] = -1; status[g] = 0;
+}
+
+}  // namespace
+
+extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_item_rec16, const int64_t *d_group_off,
+                             int64_t n_groups, int64_t n_items, int quality, void *d_out_records,
+                             int64_t out_capacity_bytes, uint32_t *d_out_off, uint32_t *d_out_nm, int32_t *d_out_status,
+                             void *stream_) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n_groups >= 0 && n_items >= 0 && n_groups < 0xffffffffLL, "size out of range");
+    if (n_groups == 0) return DYN_OK;
+    DYN_ARG(d_group_off && d_out_off && d_out_nm && d_out_status, "null buffer");
+    DYN_ARG(n_items == 0 || (d_records && d_item_rec16), "null records");
+    DYN_ARG(out_capacity_bytes == 0 || d_out_records, "null output");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long *group_off = reinterpret_cast<const long long *>(d_group_off);
+    const uint8_t *records = static_cast<const uint8_t *>(d_records);
+
+    // ---- per-item tuple counts, per-group span (scratch slot 12, part 1)
+    size_t scan_tmp = 0, t = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr, n_items + 1, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t, (uint32_t *)nullptr, (uint32_t *)nullptr, n_groups + 1, stream);
+    if (t > scan_tmp) scan_tmp = t;
+    uint32_t *g_left, *g_right, *out_cap16;
+    int32_t *g_ref;
+    unsigned long long *tuple_cnt, *tuple_off;
+    GroupOut *sizes;
+    long long *n_cells;
+    void *tmp0;
+    Arena a0;
+    for (int pass = 0; pass < 2; ++pass) {
+        tuple_cnt = a0.take<unsigned long long>(n_items + 1);
+        tuple_off = a0.take<unsigned long long>(n_items + 1);
+        g_left = a0.take<uint32_t>(n_groups); g_right = a0.take<uint32_t>(n_groups); g_ref = a0.take<int32_t>(n_groups);
+        out_cap16 = a0.take<uint32_t>(n_groups + 1);
+        sizes = a0.take<GroupOut>(n_groups);
+        n_cells = a0.take<long long>(2);
+        tmp0 = a0.take<uint8_t>(scan_tmp);
+        if (pass == 0) {
+            void *base = nullptr;
+            int rc = dyn_ctx_scratch(ctx, 12, a0.used + 256, &base);
+            if (rc) return rc;
+            a0 = Arena(base);
+        }
+    }
+    init_groups_kernel<<<grid_for(n_groups), kBlock, 0, stream>>>(g_left, g_right, g_ref, d_out_status, n_groups);
+    DYN_CUDA(cudaMemsetAsync(tuple_cnt, 0, sizeof(unsigned long long) * (n_items + 1), stream));
+    DYN_CUDA(cudaMemsetAsync(n_cells, 0, 16, stream));
+    unsigned long long n_tuples = 0;
+    if (n_items > 0) {
+        size_kernel<<<grid_for(n_items), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_cnt,
+                                                              g_left, g_right, g_ref, d_out_status);
+        t = scan_tmp;
+        DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, tuple_cnt, tuple_off, n_items + 1, stream));
+        DYN_CUDA(cudaMemcpyAsync(&n_tuples, tuple_off + n_items, 8, cudaMemcpyDeviceToHost, stream));
+        DYN_CUDA(cudaStreamSynchronize(stream));      // the tuple arrays are sized from this total
+    }
+    DYN_ARG(n_tuples < 0x7fffffffull, "more than 2^31 base tuples in one call: split the groups into batches");
+
+    // ---- expand, sort, reduce (scratch slot 13)
+    unsigned long long *cell_key = nullptr;
+    uint32_t *cell = nullptr;
+    if (n_tuples > 0) {
+        const size_t n = (size_t)n_tuples;
+        size_t sort_tmp = 0;
+        {
+            cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+            cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+            cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, k, v, (long long)n, 0, 64, stream);
+            cub::DeviceScan::ExclusiveSum(nullptr, t, (uint32_t *)nullptr, (uint32_t *)nullptr, (long long)n, stream);
+            if (t > sort_tmp) sort_tmp = t;
+        }
+        unsigned long long *ka, *kb;
+        uint32_t *va, *vb, *flag, *idx;
+        void *tmp1;
+        Arena a1;
+        for (int pass = 0; pass < 2; ++pass) {
+            ka = a1.take<unsigned long long>(n); kb = a1.take<unsigned long long>(n);
+            va = a1.take<uint32_t>(n); vb = a1.take<uint32_t>(n);
+            flag = a1.take<uint32_t>(n + 1); idx = a1.take<uint32_t>(n + 1);
+            tmp1 = a1.take<uint8_t>(sort_tmp);
+            if (pass == 0) {
+                void *base = nullptr;
+                int rc = dyn_ctx_scratch(ctx, 13, a1.used + 256, &base);
+                if (rc) return rc;
+                a1 = Arena(base);
+            }
+        }
+        expand_kernel<<<grid_for(n_items), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_off, ka,
+                                                                va, d_out_status);
+        cub::DoubleBuffer<unsigned long long> k(ka, kb);
+        cub::DoubleBuffer<uint32_t> v(va, vb);
+        t = sort_tmp;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp1, t, k, v, (long long)n, 0, 64, stream));
+        DYN_CUDA(cudaMemsetAsync(flag + n, 0, 4, stream));
+        head_kernel<<<grid_for((long long)n), kBlock, 0, stream>>>(k.Current(), (long long)n, flag);
+        t = sort_tmp;
+        DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp1, t, flag, idx, (long long)n + 1, stream));
+        // cells overwrite the alternate buffers (n_cells <= n)
+        cell_key = k.Alternate();
+        cell = v.Alternate();
+        reduce_kernel<<<grid_for((long long)n), kBlock, 0, stream>>>(k.Current(), v.Current(), flag, idx, (long long)n, quality,
+                                                                     cell_key, cell);
+        // n_cells = idx[n] (uint32) -> int64 slot
+        DYN_CUDA(cudaMemcpyAsync(n_cells, idx + n, 4, cudaMemcpyDeviceToDevice, stream));
+    }
+
+    // ---- assemble: sizes, offsets, records
+    assemble_kernel<false><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, n_groups, g_left, g_right, g_ref, sizes,
+                                                                     out_cap16, nullptr, nullptr, 0, d_out_nm, d_out_status);
+    DYN_CUDA(cudaMemsetAsync(out_cap16 + n_groups, 0, 4, stream));
+    t = scan_tmp;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, out_cap16, d_out_off, n_groups + 1, stream));
+    assemble_kernel<true><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, n_groups, g_left, g_right, g_ref, sizes,
+                                                                    out_cap16, d_out_off, static_cast<uint8_t *>(d_out_records),
+                                                                    out_capacity_bytes >> 4, d_out_nm, d_out_status);
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}

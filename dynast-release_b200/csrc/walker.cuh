@@ -1,0 +1,143 @@
+// Sequential CIGAR/MD walker over one packed read record (include/dynast_b200.h), shared by the tally's
+// slow path (paired units, event overflow, oversized records) and the consensus expansion.
+// Restates pysam's get_aligned_pairs(with_seq=True) as used by dynast/preprocessing/bam.py:386-411 and
+// consensus.py:73-97: M/=/X pairs with the reference base taken from MD, deleted reference bases from
+// the ^XYZ runs, N skips advancing the reference only, I/S advancing the query only.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+// BAM 4-bit code of an upper/lower-case IUPAC letter, indexed by (letter & 31), 4 bits per entry:
+//   @ A B C D E F G H I J K L M N O | P Q R S T U V W X Y Z
+//   0 1 14 2 13 0 0 4 11 0 0 12 0 3 15 0 | 0 0 5 6 8 0 7 9 0 10 0 ...
+__device__ __forceinline__ uint32_t letter_code(uint32_t ch) {
+    const unsigned long long lo = (0ull) | (1ull << 4) | (14ull << 8) | (2ull << 12) | (13ull << 16) | (0ull << 20) |
+                                  (0ull << 24) | (4ull << 28) | (11ull << 32) | (0ull << 36) | (0ull << 40) |
+                                  (12ull << 44) | (0ull << 48) | (3ull << 52) | (15ull << 56) | (0ull << 60);
+    const unsigned long long hi = (0ull) | (0ull << 4) | (5ull << 8) | (6ull << 12) | (8ull << 16) | (0ull << 20) |
+                                  (7ull << 24) | (9ull << 28) | (0ull << 32) | (10ull << 36);
+    const uint32_t i = ch & 31;
+    const unsigned long long t = (i & 16) ? hi : lo;
+    return (uint32_t)(t >> ((i & 15) << 2)) & 0xf;
+}
+
+// one-hot BAM base code -> 0..3 (A C G T), anything else -> -1
+__device__ __forceinline__ int base_idx(uint32_t code) { return __popc(code) == 1 ? __ffs((int)code) - 1 : -1; }
+
+__device__ __forceinline__ size_t pad4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+__device__ __forceinline__ size_t record_need(uint32_t l_seq, uint32_t n_cigar, uint32_t md_len) {
+    return 16 + 4 * (size_t)n_cigar + pad4(((size_t)l_seq + 1) >> 1) + l_seq + md_len;
+}
+
+struct Walker {
+    const uint32_t *cig;
+    const uint8_t *seq, *qual, *md;
+    int n_cigar, l_seq, md_len, ref_id;
+    int ci, op_left, qpos, rpos, mdp, run;
+    int del[4];
+    int del_left;      // deleted reference bases still to be reported (next_event only)
+    bool bad;
+    // current aligned pair
+    int cq, cr;
+    uint32_t gn, rn, q;
+
+    // returns padded record size, 0 if the record does not fit `avail`
+    __device__ size_t init(const uint8_t *rec, size_t avail) {
+        bad = false;
+        ci = op_left = qpos = mdp = run = 0;
+        del_left = 0;
+        del[0] = del[1] = del[2] = del[3] = 0;
+        n_cigar = l_seq = md_len = 0;
+        rpos = 0; ref_id = 0;
+        cig = nullptr; seq = qual = md = nullptr;
+        if (avail < 16) { bad = true; return 0; }
+        const uint4 h = *reinterpret_cast<const uint4 *>(rec);
+        const uint32_t ls = h.z & 0xffff, nc = h.z >> 16, ml = h.w & 0xffff;
+        const size_t need = record_need(ls, nc, ml);
+        if (need > avail) { bad = true; return 0; }
+        rpos = (int)h.x; ref_id = (int)h.y;
+        l_seq = (int)ls; n_cigar = (int)nc; md_len = (int)ml;
+        cig = reinterpret_cast<const uint32_t *>(rec + 16);
+        seq = rec + 16 + 4 * (size_t)nc;
+        qual = seq + pad4(((size_t)ls + 1) >> 1);
+        md = qual + ls;
+        return (need + 15) & ~(size_t)15;
+    }
+    __device__ bool md_digit() const { return mdp < md_len && (uint32_t)(md[mdp] - '0') <= 9u; }
+    __device__ void md_number() {
+        while (run == 0 && md_digit())
+            while (md_digit()) run = run * 10 + (int)(md[mdp++] - '0');
+    }
+    // advance to the next aligned (M/=/X) pair
+    __device__ bool next() {
+        for (;;) {
+            if (bad) return false;
+            if (op_left == 0) {
+                if (ci >= n_cigar) return false;
+                const uint32_t c = cig[ci++];
+                const int op = (int)(c & 0xf), len = (int)(c >> 4);
+                if (op == 0 || op == 7 || op == 8) { op_left = len; continue; }
+                if (op == 2) {
+                    md_number();
+                    if (run != 0 || mdp >= md_len || md[mdp] != '^') { bad = true; return false; }
+                    ++mdp;
+                    for (int j = 0; j < len; ++j) {
+                        if (mdp >= md_len) { bad = true; return false; }
+                        const int b = base_idx(letter_code(md[mdp++]));
+                        if (b >= 0) ++del[b];
+                    }
+                    rpos += len;
+                } else if (op == 3) rpos += len;
+                else if (op == 1 || op == 4) { qpos += len; if (qpos > l_seq) { bad = true; return false; } }
+                continue;
+            }
+            if (qpos >= l_seq) { bad = true; return false; }
+            md_number();
+            rn = (seq[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
+            if (run > 0) { gn = rn; --run; }
+            else {
+                if (mdp >= md_len || md[mdp] == '^') { bad = true; return false; }
+                gn = letter_code(md[mdp++]);
+            }
+            cq = qpos; cr = rpos; q = qual[qpos];
+            ++qpos; ++rpos; --op_left;
+            return true;
+        }
+    }
+
+    // Like next(), but deleted reference bases are reported too (consensus.py:73-97 walks
+    // get_aligned_pairs(matches_only=False)): returns 0 at the end, 1 for an aligned pair (cq, cr, gn, rn, q),
+    // 2 for a deleted reference base (cr, gn).
+    __device__ int next_event() {
+        for (;;) {
+            if (bad) return 0;
+            if (del_left > 0) {
+                if (mdp >= md_len) { bad = true; return 0; }
+                gn = letter_code(md[mdp++]);
+                cr = rpos++;
+                --del_left;
+                return 2;
+            }
+            if (op_left == 0) {
+                if (ci >= n_cigar) return 0;
+                const uint32_t c = cig[ci++];
+                const int op = (int)(c & 0xf), len = (int)(c >> 4);
+                if (op == 0 || op == 7 || op == 8) op_left = len;
+                else if (op == 2) {
+                    md_number();
+                    if (run != 0 || mdp >= md_len || md[mdp] != '^') { bad = true; return 0; }
+                    ++mdp;
+                    del_left = len;
+                } else if (op == 3) rpos += len;
+                else if (op == 1 || op == 4) { qpos += len; if (qpos > l_seq) { bad = true; return 0; } }
+                continue;
+            }
+            return next() ? 1 : 0;
+        }
+    }
+};
+
+
+}  // namespace

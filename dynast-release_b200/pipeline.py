@@ -336,3 +336,19 @@ def pi_fit(ctx: Context, k, n, count, off, p_e, p_c, max_cells=None):
     check(ctx.lib.dyn_pi_fit(ctx.handle, ptr(k), ptr(n), ptr(count), ptr(off), G, int(max_cells), ptr(p_e), ptr(p_c),
                              ptr(out), ptr(status), _stream()))
     return out, status
+
+
+def consensus(ctx: Context, records: torch.Tensor, item_rec16: torch.Tensor, group_off: torch.Tensor, quality: int = 27,
+              out_capacity_bytes: Optional[int] = None):
+    """dyn_consensus -> dict(records uint8 tensor, off int32 [G+1] (16-byte units), nm int32 [G], status int32 [G])."""
+    G = group_off.numel() - 1
+    dev = records.device
+    if out_capacity_bytes is None:   # a consensus record is never larger than its members together (+ header slack)
+        out_capacity_bytes = int(records.numel()) + 64 * G + 1024
+    out = torch.empty(out_capacity_bytes, dtype=torch.uint8, device=dev)
+    off = torch.zeros(G + 1, dtype=torch.int32, device=dev)
+    nm = torch.zeros(max(G, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(max(G, 1), dtype=torch.int32, device=dev)
+    check(ctx.lib.dyn_consensus(ctx.handle, ptr(records), ptr(item_rec16), ptr(group_off), G, item_rec16.numel(), int(quality),
+                                ptr(out), out_capacity_bytes, ptr(off), ptr(nm), ptr(status), _stream()))
+    return dict(records=out, off=off, nm=nm[:G], status=status[:G])

@@ -249,6 +249,21 @@ int dyn_pi_fit(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n, const int
                int32_t *d_status, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * a8: UMI consensus.  Replaces consensus.call_consensus_from_reads (dynast/preprocessing/consensus.py:57-200)
+ * for every (gene, barcode, UMI) group at once.  Group g consists of the member records
+ * d_item_rec16[d_group_off[g] .. d_group_off[g+1]) (offsets into d_records in 16-byte units; the two mates of
+ * a pair are two items); the grouping itself (consensus.py:338-430) is done by the caller.
+ * Output: one packed record per group (same layout as the input records: pos = leftmost start, CIGAR with
+ * M / D / N runs, 4-bit consensus sequence, qualities clipped to 42, MD text; flag 0) at
+ * d_out_records + 16 * d_out_off[g]; NM in d_out_nm[g].  d_out_status[g]: 0 ok, 2 malformed member record,
+ * 3 does not fit a BAM record, 4 members on several contigs (the reference raises), 5 output capacity.
+ * The call synchronises the stream once (it sizes its tuple buffers from a device total).
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_item_rec16, const int64_t *d_group_off,
+                  int64_t n_groups, int64_t n_items, int quality, void *d_out_records, int64_t out_capacity_bytes,
+                  uint32_t *d_out_off, uint32_t *d_out_nm, int32_t *d_out_status, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic input generator (bench / test utility; not on the timed path). Generates packed records
  * for the BASELINE configs directly in HBM; every decision is a pure function of (seed, read index).
  * Model: SURVEY.md section 8d (C2) after dynast/benchmarking/simulation.py:22-79.
