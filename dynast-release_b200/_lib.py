@@ -39,6 +39,14 @@ PROTOTYPES = {
     'dyn_kn_csr': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_pi_fit': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'dyn_consensus': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'dyn_coverage': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'dyn_unique_counts': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'dyn_bam_pack': (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
+    'dyn_bam_result_free': (None, [_vp]),
+    'dyn_bam_n_units': (_i64, [_vp]),
+    'dyn_bam_n_records_seen': (_i64, [_vp]),
+    'dyn_bam_n_refs': (_i64, [_vp]),
+    'dyn_bam_field': (_vp, [_vp, _i32, C.POINTER(_i64)]),
     'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
     'dyn_synth_fill': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

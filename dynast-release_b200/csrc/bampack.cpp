@@ -1,0 +1,358 @@
+// Host BAM ingest: BGZF inflate + record packing (SURVEY.md section 8 row a1/a2 host side, f1).
+//
+// Replaces what the reference gets from pysam/htslib in dynast/preprocessing/bam.py:253-312 (iterate a
+// coordinate-sorted BAM, apply the read filter, pair mates) and writes the packed records of
+// include/dynast_b200.h that the tally / coverage / consensus kernels read, plus the per-unit metadata the
+// CSV outputs need (read name, HI, AS, barcode / UMI / gene strings).
+//   * BGZF blocks are independent gzip members: their boundaries are found from the BSIZE extra field and
+//     they are inflated in parallel (std::thread + zlib raw inflate) into one contiguous buffer;
+//   * records are then parsed in file order; the read filter is bam.py:173-174, 242-248, 286-292
+//     (secondary / unmapped / duplicate dropped, supplementary kept, required tags, barcode '-'); the first
+//     seen mate of a pair is parked under (read name, HI) and packed behind its mate (bam.py:307-312); the
+//     pending table is reset at every contig change, as parse_read_contig runs once per contig.
+// Integer / byte work on the host; no GPU involvement. Output buffers are page-locked when a CUDA context is
+// available so that dyn_tally_reads_host can stream them with cudaMemcpyAsync.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dynast_b200.h"
+
+void dyn_set_error(const char *fmt, ...);
+
+namespace {
+
+struct Block { size_t in_off, in_len, out_off, out_len; };
+
+struct Pool {              // string pool with offsets
+    std::vector<char> data;
+    std::vector<uint32_t> off;   // n + 1
+    Pool() { off.push_back(0); }
+    void add(const char *s, size_t n) { data.insert(data.end(), s, s + n); off.push_back((uint32_t)data.size()); }
+};
+
+struct Aux {               // the tags of one record that the path needs
+    const char *md = nullptr; size_t md_len = 0;
+    const char *bc = nullptr; size_t bc_len = 0;
+    const char *umi = nullptr; size_t umi_len = 0;
+    const char *gx = nullptr; size_t gx_len = 0;
+    bool has_hi = false, has_as = false, has_bc = false, has_umi = false, has_gx = false, has_md = false;
+    int64_t hi = 0, as = 0;
+};
+
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+bool parse_aux(const uint8_t *p, const uint8_t *end, const char *bc_tag, const char *umi_tag, const char *gx_tag, Aux &a) {
+    while (p + 3 <= end) {
+        const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
+        p += 3;
+        int64_t ival = 0;
+        bool is_int = false;
+        const uint8_t *sval = nullptr;
+        size_t slen = 0;
+        switch (ty) {
+            case 'A': if (p + 1 > end) return false; sval = p; slen = 1; p += 1; break;
+            case 'c': if (p + 1 > end) return false; ival = (int8_t)p[0]; is_int = true; p += 1; break;
+            case 'C': if (p + 1 > end) return false; ival = p[0]; is_int = true; p += 1; break;
+            case 's': if (p + 2 > end) return false; ival = (int16_t)rd16(p); is_int = true; p += 2; break;
+            case 'S': if (p + 2 > end) return false; ival = rd16(p); is_int = true; p += 2; break;
+            case 'i': if (p + 4 > end) return false; ival = (int32_t)rd32(p); is_int = true; p += 4; break;
+            case 'I': if (p + 4 > end) return false; ival = rd32(p); is_int = true; p += 4; break;
+            case 'f': if (p + 4 > end) return false; p += 4; break;
+            case 'Z': case 'H': {
+                const uint8_t *q = (const uint8_t *)memchr(p, 0, (size_t)(end - p));
+                if (!q) return false;
+                sval = p; slen = (size_t)(q - p); p = q + 1;
+                break;
+            }
+            case 'B': {
+                if (p + 5 > end) return false;
+                const char sub = (char)p[0];
+                const uint32_t cnt = rd32(p + 1);
+                const size_t w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                p += 5 + (size_t)cnt * w;
+                if (p > end) return false;
+                break;
+            }
+            default: return false;
+        }
+        auto is = [&](const char *tag) { return tag && tag[0] == t0 && tag[1] == t1; };
+        if (t0 == 'M' && t1 == 'D' && sval) { a.md = (const char *)sval; a.md_len = slen; a.has_md = true; }
+        if (t0 == 'H' && t1 == 'I' && is_int) { a.hi = ival; a.has_hi = true; }
+        if (t0 == 'A' && t1 == 'S' && is_int) { a.as = ival; a.has_as = true; }
+        if (is(bc_tag) && sval) { a.bc = (const char *)sval; a.bc_len = slen; a.has_bc = true; }
+        if (is(umi_tag) && sval) { a.umi = (const char *)sval; a.umi_len = slen; a.has_umi = true; }
+        if (is(gx_tag) && sval) { a.gx = (const char *)sval; a.gx_len = slen; a.has_gx = true; }
+    }
+    return true;
+}
+
+struct Pending { size_t rec_pos; };   // offset of the parked mate's BAM record in the inflated stream
+
+}  // namespace
+
+struct dyn_bam_result {
+    uint8_t *blob = nullptr;        // packed records (page-locked if possible)
+    size_t blob_bytes = 0;
+    bool blob_pinned = false;
+    std::vector<uint32_t> rec_off;  // n_units + 1 (16-byte units)
+    std::vector<int32_t> ref_id, pos, hi, score;
+    std::vector<uint16_t> flag;
+    std::vector<uint8_t> gx_assigned, paired;
+    Pool name, barcode, umi, gene;
+    std::string header_text;
+    Pool ref_name;
+    std::vector<int32_t> ref_len;
+    int64_t n_records_seen = 0;
+};
+
+namespace {
+
+// packed size of one BAM record
+inline size_t packed_bytes(uint32_t l_seq, uint32_t n_cigar, size_t md_len) {
+    const size_t b = 16 + 4 * (size_t)n_cigar + ((((size_t)l_seq + 1) / 2 + 3) & ~(size_t)3) + l_seq + md_len;
+    return (b + 15) & ~(size_t)15;
+}
+
+// rec points at the BAM alignment record body (after block_size)
+size_t pack_record(const uint8_t *rec, const Aux &a, uint16_t extra_flag, std::vector<uint8_t> &out) {
+    const int32_t ref_id = (int32_t)rd32(rec), pos = (int32_t)rd32(rec + 4);
+    const uint32_t l_read_name = rec[8];
+    const uint32_t n_cigar = rd16(rec + 12);
+    const uint16_t flag = rd16(rec + 14);
+    const uint32_t l_seq = rd32(rec + 16);
+    const uint8_t *cigar = rec + 32 + l_read_name;
+    const uint8_t *seq = cigar + 4 * (size_t)n_cigar;
+    const uint8_t *qual = seq + (l_seq + 1) / 2;
+    const size_t bytes = packed_bytes(l_seq, n_cigar, a.md_len);
+    const size_t o = out.size();
+    out.resize(o + bytes, 0);
+    uint8_t *p = out.data() + o;
+    memcpy(p, &pos, 4); memcpy(p + 4, &ref_id, 4);
+    const uint16_t ls = (uint16_t)l_seq, nc = (uint16_t)n_cigar, ml = (uint16_t)a.md_len, fl = (uint16_t)((flag & 0x0fff) | extra_flag);
+    memcpy(p + 8, &ls, 2); memcpy(p + 10, &nc, 2); memcpy(p + 12, &ml, 2); memcpy(p + 14, &fl, 2);
+    memcpy(p + 16, cigar, 4 * (size_t)n_cigar);
+    uint8_t *ps = p + 16 + 4 * (size_t)n_cigar;
+    memcpy(ps, seq, (l_seq + 1) / 2);
+    if (l_seq & 1) ps[l_seq / 2] &= 0xf0;     // the spec leaves the low nibble of the last byte undefined
+    uint8_t *pq = ps + ((((size_t)l_seq + 1) / 2 + 3) & ~(size_t)3);
+    memcpy(pq, qual, l_seq);
+    memcpy(pq + l_seq, a.md, a.md_len);
+    return bytes;
+}
+
+}  // namespace
+
+extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const char *umi_tag, const char *gene_tag,
+                            int require_gene, int n_threads, dyn_bam_result_t **out_result) {
+    if (!path || !out_result) { dyn_set_error("dyn_bam_pack: null argument"); return DYN_ERR_ARG; }
+    if (barcode_tag && !barcode_tag[0]) barcode_tag = nullptr;
+    if (umi_tag && !umi_tag[0]) umi_tag = nullptr;
+    if (gene_tag && !gene_tag[0]) gene_tag = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) { dyn_set_error("dyn_bam_pack: cannot open %s", path); return DYN_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    const long fsz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> raw((size_t)std::max(fsz, 0L));
+    if (fsz > 0 && fread(raw.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); dyn_set_error("dyn_bam_pack: short read on %s", path); return DYN_ERR_IO; }
+    fclose(f);
+
+    // ---- BGZF block table
+    std::vector<Block> blocks;
+    size_t ip = 0, total_out = 0;
+    while (ip + 18 <= raw.size()) {
+        const uint8_t *h = raw.data() + ip;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { dyn_set_error("dyn_bam_pack: %s is not BGZF", path); return DYN_ERR_FORMAT; }
+        const uint32_t xlen = rd16(h + 10);
+        uint32_t bsize = 0;
+        bool found = false;
+        for (size_t x = 12; x + 4 <= 12 + xlen && ip + x + 4 <= raw.size();) {
+            const uint32_t slen = rd16(h + x + 2);
+            if (h[x] == 'B' && h[x + 1] == 'C' && slen == 2) { bsize = rd16(h + x + 4); found = true; }
+            x += 4 + slen;
+        }
+        if (!found || ip + bsize + 1 > raw.size()) { dyn_set_error("dyn_bam_pack: corrupt BGZF block in %s", path); return DYN_ERR_FORMAT; }
+        const size_t blen = (size_t)bsize + 1;
+        const uint32_t isize = rd32(h + blen - 4);
+        Block b;
+        b.in_off = ip + 12 + xlen; b.in_len = blen - 12 - xlen - 8; b.out_off = total_out; b.out_len = isize;
+        blocks.push_back(b);
+        total_out += isize;
+        ip += blen;
+    }
+    std::vector<uint8_t> data(total_out);
+    {
+        std::atomic<size_t> next(0);
+        std::atomic<int> failed(0);
+        auto work = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= blocks.size()) return;
+                const Block &b = blocks[i];
+                if (b.out_len == 0) continue;
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
+                zs.next_in = raw.data() + b.in_off; zs.avail_in = (uInt)b.in_len;
+                zs.next_out = data.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
+                const int rc = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (rc != Z_STREAM_END || zs.avail_out != 0) { failed = 1; return; }
+            }
+        };
+        const int nt = std::max(1, std::min(n_threads, 64));
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work);
+        for (auto &t : th) t.join();
+        if (failed) { dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return DYN_ERR_FORMAT; }
+    }
+    std::vector<uint8_t>().swap(raw);
+
+    // ---- header
+    dyn_bam_result *res = new dyn_bam_result();
+    const uint8_t *d = data.data();
+    const size_t n = data.size();
+    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete res; dyn_set_error("dyn_bam_pack: bad BAM magic in %s", path); return DYN_ERR_FORMAT; }
+    size_t p = 4;
+    const uint32_t l_text = rd32(d + p); p += 4;
+    if (p + l_text + 4 > n) { delete res; dyn_set_error("dyn_bam_pack: truncated header"); return DYN_ERR_FORMAT; }
+    res->header_text.assign((const char *)d + p, l_text); p += l_text;
+    const uint32_t n_ref = rd32(d + p); p += 4;
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        if (p + 4 > n) { delete res; dyn_set_error("dyn_bam_pack: truncated reference list"); return DYN_ERR_FORMAT; }
+        const uint32_t l_name = rd32(d + p); p += 4;
+        if (p + l_name + 4 > n) { delete res; dyn_set_error("dyn_bam_pack: truncated reference list"); return DYN_ERR_FORMAT; }
+        res->ref_name.add((const char *)d + p, l_name ? l_name - 1 : 0); p += l_name;
+        res->ref_len.push_back((int32_t)rd32(d + p)); p += 4;
+    }
+
+    // ---- records
+    std::vector<uint8_t> blob;
+    blob.reserve(n / 2);
+    res->rec_off.push_back(0);
+    std::unordered_map<std::string, Pending> pending;
+    int32_t cur_ref = -2;
+    std::string key;
+    while (p + 4 <= n) {
+        const uint32_t block_size = rd32(d + p);
+        const uint8_t *rec = d + p + 4;
+        if (p + 4 + block_size > n || block_size < 32) { delete res; dyn_set_error("dyn_bam_pack: truncated record"); return DYN_ERR_FORMAT; }
+        const size_t rec_pos = p + 4;
+        p += 4 + block_size;
+        ++res->n_records_seen;
+        const int32_t ref_id = (int32_t)rd32(rec);
+        const uint32_t l_read_name = rec[8], n_cigar = rd16(rec + 12), l_seq = rd32(rec + 16);
+        const uint16_t flag = rd16(rec + 14);
+        if (ref_id != cur_ref) { pending.clear(); cur_ref = ref_id; }      // parse_read_contig runs per contig
+        if (ref_id < 0) continue;                                           // bam.fetch(contig) never yields these
+        if (flag & (0x100 | 0x4 | 0x400)) continue;                         // bam.py:173: secondary, unmapped, duplicate
+        const size_t fixed = 32 + l_read_name + 4 * (size_t)n_cigar + (l_seq + 1) / 2 + l_seq;
+        if (fixed > block_size) { delete res; dyn_set_error("dyn_bam_pack: corrupt record"); return DYN_ERR_FORMAT; }
+        Aux a;
+        if (!parse_aux(rec + fixed, rec + block_size, barcode_tag, umi_tag, gene_tag, a)) { delete res; dyn_set_error("dyn_bam_pack: corrupt aux data"); return DYN_ERR_FORMAT; }
+        if ((barcode_tag && !a.has_bc) || (umi_tag && !a.has_umi) || (require_gene && gene_tag && !a.has_gx)) continue;   // bam.py:174, 242-248
+        if (barcode_tag && a.bc_len == 1 && a.bc[0] == '-') continue;       // bam.py:290
+        if (!a.has_hi || !a.has_as) { delete res; dyn_set_error("dyn_bam_pack: alignment without HI / AS tag (KeyError in the reference, bam.py:295-296)"); return DYN_ERR_FORMAT; }
+        if (!a.has_md) { delete res; dyn_set_error("dyn_bam_pack: alignment without MD tag (count.py:119-124)"); return DYN_ERR_FORMAT; }
+        if (l_seq > 0xffff || n_cigar > 0xffff || a.md_len > 0xffff) { delete res; dyn_set_error("dyn_bam_pack: record too long for the packed layout"); return DYN_ERR_FORMAT; }
+        const char *name = (const char *)rec + 32;
+        const size_t name_len = l_read_name ? l_read_name - 1 : 0;
+        const uint8_t *mate_rec = nullptr;
+        Aux ma;
+        if (flag & 0x1) {                                                   // bam.py:307-312
+            key.assign(name, name_len);
+            key.push_back('\0');
+            key.append(std::to_string(a.hi));
+            auto it = pending.find(key);
+            if (it == pending.end()) { pending.emplace(key, Pending{rec_pos}); continue; }
+            mate_rec = d + it->second.rec_pos;
+            pending.erase(it);
+            const uint32_t m_name = mate_rec[8], m_cig = rd16(mate_rec + 12), m_seq = rd32(mate_rec + 16);
+            const uint32_t m_size = rd32(mate_rec - 4);
+            parse_aux(mate_rec + 32 + m_name + 4 * (size_t)m_cig + (m_seq + 1) / 2 + m_seq, mate_rec + m_size, barcode_tag, umi_tag, gene_tag, ma);
+            if (!ma.has_md) { delete res; dyn_set_error("dyn_bam_pack: alignment without MD tag (count.py:119-124)"); return DYN_ERR_FORMAT; }
+        }
+        pack_record(rec, a, mate_rec ? DYN_REC_HAS_MATE : 0, blob);
+        if (mate_rec) pack_record(mate_rec, ma, 0, blob);
+        res->rec_off.push_back((uint32_t)(blob.size() >> 4));
+        res->ref_id.push_back(ref_id);
+        res->pos.push_back((int32_t)rd32(rec + 4));
+        res->flag.push_back(flag);
+        res->hi.push_back((int32_t)a.hi);
+        res->score.push_back((int32_t)a.as);
+        res->gx_assigned.push_back(a.has_gx ? 1 : 0);
+        res->paired.push_back(mate_rec ? 1 : 0);
+        res->name.add(name, name_len);
+        res->barcode.add(a.has_bc ? a.bc : "NA", a.has_bc ? a.bc_len : 2);
+        res->umi.add(a.has_umi ? a.umi : "NA", a.has_umi ? a.umi_len : 2);
+        res->gene.add(a.has_gx ? a.gx : "", a.has_gx ? a.gx_len : 0);
+        if ((blob.size() >> 4) > 0xfffffff0ull) { delete res; dyn_set_error("dyn_bam_pack: more than 64 GiB of packed records: split the BAM by read range"); return DYN_ERR_NOMEM; }
+    }
+    res->blob_bytes = blob.size();
+    const size_t alloc = std::max<size_t>(blob.size(), 16);
+    if (cudaHostAlloc((void **)&res->blob, alloc, cudaHostAllocPortable) == cudaSuccess) res->blob_pinned = true;
+    else {
+        cudaGetLastError();
+        if (posix_memalign((void **)&res->blob, 256, alloc) != 0) { delete res; dyn_set_error("dyn_bam_pack: out of memory"); return DYN_ERR_NOMEM; }
+    }
+    if (!blob.empty()) memcpy(res->blob, blob.data(), blob.size());
+    *out_result = res;
+    return DYN_OK;
+}
+
+extern "C" void dyn_bam_result_free(dyn_bam_result_t *r) {
+    if (!r) return;
+    if (r->blob) { if (r->blob_pinned) cudaFreeHost(r->blob); else free(r->blob); }
+    delete r;
+}
+
+extern "C" int64_t dyn_bam_n_units(const dyn_bam_result_t *r) { return r ? (int64_t)r->ref_id.size() : 0; }
+extern "C" int64_t dyn_bam_n_records_seen(const dyn_bam_result_t *r) { return r ? r->n_records_seen : 0; }
+extern "C" int64_t dyn_bam_n_refs(const dyn_bam_result_t *r) { return r ? (int64_t)r->ref_len.size() : 0; }
+
+// field: 0 blob (uint8), 1 rec_off (uint32, n+1), 2 ref_id (int32), 3 pos (int32), 4 flag (uint16), 5 HI (int32),
+// 6 AS (int32), 7 gx_assigned (uint8), 8 paired (uint8), 9 ref_len (int32), 10 header text (char)
+// string pools (chars / uint32 offsets n+1): 20/21 read name, 22/23 barcode, 24/25 umi, 26/27 gene, 28/29 reference names
+extern "C" const void *dyn_bam_field(const dyn_bam_result_t *r, int field, int64_t *n_bytes) {
+    if (!r) return nullptr;
+    const void *p = nullptr;
+    size_t nb = 0;
+    auto vec = [&](const auto &v) { p = v.data(); nb = v.size() * sizeof(v[0]); };
+    switch (field) {
+        case 0: p = r->blob; nb = r->blob_bytes; break;
+        case 1: vec(r->rec_off); break;
+        case 2: vec(r->ref_id); break;
+        case 3: vec(r->pos); break;
+        case 4: vec(r->flag); break;
+        case 5: vec(r->hi); break;
+        case 6: vec(r->score); break;
+        case 7: vec(r->gx_assigned); break;
+        case 8: vec(r->paired); break;
+        case 9: vec(r->ref_len); break;
+        case 10: p = r->header_text.data(); nb = r->header_text.size(); break;
+        case 20: vec(r->name.data); break;
+        case 21: vec(r->name.off); break;
+        case 22: vec(r->barcode.data); break;
+        case 23: vec(r->barcode.off); break;
+        case 24: vec(r->umi.data); break;
+        case 25: vec(r->umi.off); break;
+        case 26: vec(r->gene.data); break;
+        case 27: vec(r->gene.off); break;
+        case 28: vec(r->ref_name.data); break;
+        case 29: vec(r->ref_name.off); break;
+        default: return nullptr;
+    }
+    if (n_bytes) *n_bytes = (int64_t)nb;
+    return p;
+}

@@ -167,15 +167,14 @@ def deduplicate_counts(df_counts: pd.DataFrame, conversions: Optional[FrozenSet[
     return df_counts.iloc[keep].reset_index(drop=True)
 
 
-def _dedup_frame_plain(df, conversions, use_conversions):
+def _dedup_rows(df, key_cols, conversions=None, use_conversions=False, with_counts=False):
+    """One-split dedup of a frame on the device: priority ([has_conversions,] transcriptome, score,
+    conversion_sum), ties -> last row; returns surviving row positions in ascending priority order."""
     ctx = _lib.current_context()
     dev = _device()
     n = len(df)
-    counts = _counts_to_device(df)
-    bc, n_bc = _intern(df['barcode'])
-    um, n_um = _intern(df['umi'])
-    gx, n_gx = _intern(df['GX'])
-    hi, lo, hi_bits, lo_bits = _group_key([(bc, n_bc), (um, n_um), (gx, n_gx)])
+    counts = _counts_to_device(df) if with_counts else torch.zeros((n, 16), dtype=torch.uint8, device=dev)
+    hi, lo, hi_bits, lo_bits = _group_key([_intern(df[c]) for c in key_cols])
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(dev)
     out = pipeline.dedup(
         ctx, t(lo, np.int64), counts, torch.zeros(n, dtype=torch.uint8, device=dev),
@@ -184,6 +183,10 @@ def _dedup_frame_plain(df, conversions, use_conversions):
         None, 0, conversions=conversions, use_conversions=use_conversions, key_hi=None if hi is None else t(hi, np.int64),
         key_lo_bits=lo_bits, key_hi_bits=hi_bits)
     return out.cpu().numpy().astype(np.int64)
+
+
+def _dedup_frame_plain(df, conversions, use_conversions):
+    return _dedup_rows(df, ['barcode', 'umi', 'GX'], conversions, use_conversions, with_counts=True)
 
 
 def drop_multimappers(df_counts: pd.DataFrame, conversions: Optional[FrozenSet[str]] = None) -> pd.DataFrame:

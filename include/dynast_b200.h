@@ -264,6 +264,41 @@ int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_item_
                   uint32_t *d_out_off, uint32_t *d_out_nm, int32_t *d_out_status, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * a7: coverage of positions of interest and grouped key counts.
+ * dyn_coverage replaces coverage.calculate_coverage_contig (dynast/preprocessing/coverage.py:101-149):
+ * d_cov[i] = number of selected counting units (d_selected[u] != 0, NULL = all) whose aligned (M/=/X)
+ * positions include position-of-interest i; d_poi = sorted unique keys (ref_id << 32 | position); a pair
+ * counts the union of its mates' positions once (coverage.py:136-142).  d_first[i] = smallest
+ * (unit << 32 | position) that touched entry i (all ones if untouched): coverage.csv lists positions in that
+ * order (coverage.py:144-149).
+ * dyn_unique_counts: distinct 64-bit keys of an array (key ~0 = skip) with their multiplicity and first
+ * occurrence, sorted by key -- the counting dictionaries of snp.extract_conversions_part (snp.py:108-133).
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_coverage(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_rec_off, int64_t n_units,
+                 const uint8_t *d_selected, const uint64_t *d_poi, int64_t n_poi, uint32_t *d_cov, uint64_t *d_first,
+                 void *stream);
+int dyn_unique_counts(dyn_ctx_t *ctx, const uint64_t *d_keys, int64_t n_keys, uint64_t *d_out_keys, uint32_t *d_out_count,
+                      uint32_t *d_out_first, int64_t *d_n_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host BAM ingest (what the reference gets from pysam, bam.py:253-312): BGZF inflate on n_threads host
+ * threads, read filter (bam.py:173-174, 242-248, 286-292), mate pairing (bam.py:307-312), packing into the
+ * record layout above (page-locked memory when available).  The BAM must be coordinate sorted.  tags may be
+ * NULL / ""; require_gene = the reference's `not velocity`.  Per-unit metadata is read with dyn_bam_field:
+ *   0 blob u8 | 1 rec_off u32[n+1] | 2 ref_id i32 | 3 pos i32 | 4 flag u16 | 5 HI i32 | 6 AS i32 |
+ *   7 gx_assigned u8 | 8 paired u8 | 9 ref_len i32 | 10 header text |
+ *   string pools (chars, u32 offsets[n+1]): 20/21 read name, 22/23 barcode, 24/25 umi, 26/27 gene, 28/29 ref names
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dyn_bam_result dyn_bam_result_t;
+int dyn_bam_pack(const char *path, const char *barcode_tag, const char *umi_tag, const char *gene_tag, int require_gene,
+                 int n_threads, dyn_bam_result_t **out_result);
+void dyn_bam_result_free(dyn_bam_result_t *result);
+int64_t dyn_bam_n_units(const dyn_bam_result_t *result);
+int64_t dyn_bam_n_records_seen(const dyn_bam_result_t *result);
+int64_t dyn_bam_n_refs(const dyn_bam_result_t *result);
+const void *dyn_bam_field(const dyn_bam_result_t *result, int field, int64_t *n_bytes);
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic input generator (bench / test utility; not on the timed path). Generates packed records
  * for the BASELINE configs directly in HBM; every decision is a pure function of (seed, read index).
  * Model: SURVEY.md section 8d (C2) after dynast/benchmarking/simulation.py:22-79.
