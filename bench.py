@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-em', action='store_true')
+    ap.add_argument('--skip-pipeline', action='store_true')
     ap.add_argument('--no-emit', action='store_true', help='diagnostic: counters only, no mismatch records')
     return ap.parse_args()
 
@@ -337,19 +338,70 @@ def main():
                'timing': 'host perf_counter around the blocking C-ABI call, device synchronised on both sides'}
         del h_rec, h_counts, h_conv_rec, h_conv_read
 
+    # ---------------------------------------------------------------- whole device path on the same batch (untimed stages)
+    pipe = None
+    if not args.skip_pipeline:
+        timings = {}
+        reps = 2
+        pipeline.count_to_estimate(ctx, batch.records, batch.rec_off, batch.barcode - rank * args.barcodes, batch.umi, batch.gene,
+                                   batch.score, batch.strand, args.barcodes, batch.n_genes, out)        # warm-up
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(reps):
+            res = pipeline.count_to_estimate(ctx, batch.records, batch.rec_off, batch.barcode - rank * args.barcodes, batch.umi,
+                                             batch.gene, batch.score, batch.strand, args.barcodes, batch.n_genes, out,
+                                             timings=timings)
+        p1.record(stream)
+        barrier()
+        pipe_ms = p0.elapsed_time(p1) / reps
+        if dist is not None:
+            t = torch.tensor([pipe_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pipe_ms = float(t.item())
+        pipe = {'metric': 'reads/s, tally -> UMI dedup -> p_e -> (k,n) histograms -> EM -> pi/alpha, device resident',
+                'value': world * n_reads / (pipe_ms * 1e-3), 'unit': UNIT, 'ms': pipe_ms,
+                'stage_ms': {k: v / reps for k, v in timings.items()},
+                'reads_after_dedup': int(res['selected'].numel()),
+                'barcodes_with_p_c': int((res['em_status'] == 0).sum().item()),
+                'note': 'includes the host round trips of the dedup split plan and the EM / pi shape discovery'}
+        del res
+
     # ---------------------------------------------------------------- p_c EM (C4), barcodes split over ranks
     em = None
     if not args.skip_em:
+        from dynast_b200 import distributed
         nb = args.em_barcodes // world
+        n_global = nb * world
         k, n, c, off, pe = build_em_batch_gpu(nb, 2004 + rank, device)
+        # rank-local histogram rows with global barcode ids; the EM of barcode b runs on rank b % world after
+        # an all-gather of the rows (NCCL over NVLink) -- the one exchange of the path
+        local_b = torch.repeat_interleave(torch.arange(nb, device=device), off[1:] - off[:-1])
+        rows = torch.stack([local_b * world + rank, k.long(), n.long(), c], dim=1).contiguous()
+        if dist is not None:
+            pe_all = torch.empty(n_global, dtype=torch.float64, device=device)
+            dist.all_gather_into_tensor(pe_all, pe.contiguous())
+            pe_global = pe_all.view(world, nb).t().reshape(-1).contiguous()      # barcode id = local * world + rank
+        else:
+            pe_global = pe
+        iters_box = {}
+
+        def em_fn(k_, n_, c_, off_, pe_):
+            p_c_, st_, it_ = pipeline.em_pc(ctx, k_, n_, c_, off_, pe_.contiguous())
+            iters_box['iters'] = it_
+            return p_c_, st_
+
+        def em_step():
+            return distributed.distributed_p_c(rows, pe_global, n_global, em_fn)
+
         for _ in range(2):
-            p_c, st_em, iters = pipeline.em_pc(ctx, k, n, c, off, pe)
+            p_c, st_em = em_step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
         e0.record(stream)
         for _ in range(reps):
-            p_c, st_em, iters = pipeline.em_pc(ctx, k, n, c, off, pe)
+            p_c, st_em = em_step()
         e1.record(stream)
         barrier()
         em_ms = e0.elapsed_time(e1) / reps
@@ -357,10 +409,12 @@ def main():
             t = torch.tensor([em_ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             em_ms = float(t.item())
-        em = {'metric': 'barcodes/s p_c EM', 'value': world * nb / (em_ms * 1e-3), 'unit': 'barcodes/s',
-              'barcodes': world * nb, 'ms': em_ms, 'ok_fraction': float((st_em == 0).float().mean().item()),
+        iters = iters_box['iters']
+        em = {'metric': 'barcodes/s p_c EM', 'value': n_global / (em_ms * 1e-3), 'unit': 'barcodes/s',
+              'barcodes': n_global, 'ms': em_ms, 'ok_fraction': float((st_em == 0).float().mean().item()),
               'mean_iters': float(iters.float().mean().item()), 'workload': 'C4: k<=30, n<=150, 1% adversarial full shape',
-              'dtype': 'f64 E step / f32 M step (as the reference)'}
+              'dtype': 'f64 E step / f32 M step (as the reference)',
+              'exchange': 'none (1 GPU)' if dist is None else 'all-gather of (barcode,k,n,count) rows + all-gather of p_c inside the timed region'}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, N = 1)
     cpu_baseline = None
@@ -393,7 +447,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config, 'gpu_launches': args.steps,
-            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'em': em, 'clocks': clocks,
+            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'em': em, 'pipeline': pipe, 'clocks': clocks,
             'conversions_per_read': n_conv / n_reads,
         }
         print(json.dumps(line))

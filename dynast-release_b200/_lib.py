@@ -29,6 +29,7 @@ PROTOTYPES = {
     'dyn_count_records': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     'dyn_complement_counts': (_i32, [_vp, _vp, _vp, _i64, _vp]),
     'dyn_barcode_first_pos': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    'dyn_split_plan': (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'dyn_dedup_umi': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _u32,
                              _i32, _vp, _i32, _vp, _vp, _vp]),
     'dyn_group_sums': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp]),

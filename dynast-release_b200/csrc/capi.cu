@@ -242,3 +242,51 @@ extern "C" int dyn_em_pc_host(dyn_ctx_t *ctx, const int32_t *h_k, const int32_t 
     DYN_CUDA(cudaStreamSynchronize(st));
     return DYN_OK;
 }
+
+// --------------------------------------------------------------------------------------------------
+// Host side of a6: barcode order and split assignment (conversion.py:543-579) from the per-barcode first
+// frame position / read count that dyn_barcode_first_pos produced.  Sequential by nature (a split closes when
+// its running size passes the threshold), O(B log B) on the host for B barcodes.
+// --------------------------------------------------------------------------------------------------
+#include <numeric>
+#include <vector>
+
+extern "C" int dyn_split_plan(const uint64_t *h_first_pos, const uint32_t *h_n_reads, int64_t n_barcodes, int64_t threshold,
+                              uint32_t *h_ord_of_barcode, uint32_t *h_split_of_barcode, int64_t *h_n_splits) {
+    DYN_ARG(n_barcodes >= 0, "negative n_barcodes");
+    DYN_ARG(h_n_splits != nullptr, "null n_splits");
+    *h_n_splits = 1;
+    if (n_barcodes == 0) return DYN_OK;
+    DYN_ARG(h_first_pos && h_n_reads && h_ord_of_barcode && h_split_of_barcode, "null buffer");
+    std::vector<int64_t> order((size_t)n_barcodes);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        const uint64_t fa = h_n_reads[a] ? h_first_pos[a] : ~0ull, fb = h_n_reads[b] ? h_first_pos[b] : ~0ull;
+        return fa < fb;
+    });
+    int64_t n_splits = 0, cur = -1, cur_size = 0;
+    for (int64_t i = 0; i < n_barcodes; ++i) {
+        const int64_t b = order[i];
+        h_split_of_barcode[b] = 0;
+        if (!h_n_reads[b]) continue;
+        if ((int64_t)h_n_reads[b] > threshold) h_split_of_barcode[b] = (uint32_t)n_splits++;        // its own split
+        else if (cur < 0) { cur = n_splits++; h_split_of_barcode[b] = (uint32_t)cur; }             // opens a residual split
+        else {
+            h_split_of_barcode[b] = (uint32_t)cur;
+            cur_size += h_n_reads[b];
+            if (cur_size > threshold) { cur = -1; cur_size = 0; }
+        }
+    }
+    // split-file order: by split, then first appearance
+    std::vector<int64_t> rank_of((size_t)n_barcodes);
+    for (int64_t i = 0; i < n_barcodes; ++i) rank_of[order[i]] = i;
+    std::vector<int64_t> by_split((size_t)n_barcodes);
+    std::iota(by_split.begin(), by_split.end(), 0);
+    std::stable_sort(by_split.begin(), by_split.end(), [&](int64_t a, int64_t b) {
+        if (h_split_of_barcode[a] != h_split_of_barcode[b]) return h_split_of_barcode[a] < h_split_of_barcode[b];
+        return rank_of[a] < rank_of[b];
+    });
+    for (int64_t i = 0; i < n_barcodes; ++i) h_ord_of_barcode[by_split[i]] = (uint32_t)i;
+    *h_n_splits = n_splits > 0 ? n_splits : 1;
+    return DYN_OK;
+}

@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing of the count -> estimate path: one process per GPU, torch.distributed.
+
+The path shards without a data-path collective up to the per-barcode histograms: every rank tallies (and, for UMI
+data whose barcodes are rank-local, deduplicates) its own read range.  The one exchange the north star names is
+the all-gather of per-barcode (k, n) histograms before the EM: a barcode's reads may sit in several read ranges,
+and the EM needs the barcode's whole histogram.  After the gather the EM is partitioned by barcode
+(owner = barcode mod world) and the 8-byte results are gathered back.  Works with NCCL (device tensors) and
+with gloo (CPU tensors; used by the CPU tests for the exchange logic)."""
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def all_gather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather of a [m, c] int64 tensor whose m differs per rank (padded to the largest m, then trimmed)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return rows
+    m = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    sizes = [torch.zeros_like(m) for _ in range(world)]
+    dist.all_gather(sizes, m, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    padded = torch.zeros((cap, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    padded[:rows.shape[0]] = rows
+    out = torch.empty((world * cap, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * cap:r * cap + sizes[r]] for r in range(world)], dim=0)
+
+
+def owned_csr(rows: torch.Tensor, n_barcodes: int, rank: int, world: int):
+    """rows = [barcode, k, n, count] (any order, duplicates allowed) -> the CSR triplets of the barcodes this rank
+    owns (barcode % world == rank), barcodes ascending.  Returns (barcode ids, k int32, n int32, count int64, off int64)."""
+    mine = rows[rows[:, 0] % world == rank] if world > 1 else rows
+    order = torch.argsort(mine[:, 0], stable=True)
+    mine = mine[order]
+    owned = torch.arange(rank, n_barcodes, world, dtype=torch.int64, device=rows.device)
+    local = torch.div(mine[:, 0] - rank, world, rounding_mode='floor')
+    off = torch.zeros(owned.numel() + 1, dtype=torch.int64, device=rows.device)
+    if mine.shape[0]:
+        off[1:] = torch.cumsum(torch.bincount(local, minlength=owned.numel()), 0)
+    return owned, mine[:, 1].to(torch.int32).contiguous(), mine[:, 2].to(torch.int32).contiguous(), mine[:, 3].contiguous(), off
+
+
+def distributed_p_c(rows: torch.Tensor, p_e: torch.Tensor, n_barcodes: int,
+                    em: Callable[[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
+                    group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """p_c of every barcode from rank-local histogram rows.
+    rows: [m, 4] int64 (global barcode id, k, n, read count) of this rank's read range; p_e: [n_barcodes] float64
+    (identical on every rank); em(k, n, count, off, p_e_owned) -> (p_c, status) for CSR groups -- the EM kernel
+    (pipeline.em_pc) on a GPU.  Returns (p_c [n_barcodes] float64, status [n_barcodes] int32) on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    all_rows = all_gather_rows(rows, group) if world > 1 else rows
+    owned, k, n, c, off = owned_csr(all_rows, n_barcodes, rank, world)
+    p_c_own, st_own = em(k, n, c, off, p_e[owned])
+    if world == 1:
+        return p_c_own, st_own
+    per = (n_barcodes + world - 1) // world
+    pad_pc = torch.full((per,), float('nan'), dtype=torch.float64, device=rows.device)
+    pad_st = torch.full((per,), -1, dtype=torch.int32, device=rows.device)
+    pad_pc[:owned.numel()] = p_c_own
+    pad_st[:owned.numel()] = st_own
+    g_pc = torch.empty(world * per, dtype=torch.float64, device=rows.device)
+    g_st = torch.empty(world * per, dtype=torch.int32, device=rows.device)
+    dist.all_gather_into_tensor(g_pc, pad_pc, group=group)
+    dist.all_gather_into_tensor(g_st, pad_st, group=group)
+    # rank r's slot j holds barcode r + j * world
+    p_c = g_pc.view(world, per).t().reshape(-1)[:n_barcodes].contiguous()
+    status = g_st.view(world, per).t().reshape(-1)[:n_barcodes].contiguous()
+    return p_c, status
+
+
+def read_range(n_reads: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous read range of a rank (read-range sharding of a coordinate-sorted BAM)."""
+    per = (n_reads + world - 1) // world
+    return min(rank * per, n_reads), min((rank + 1) * per, n_reads)

@@ -178,6 +178,11 @@ int dyn_complement_counts(dyn_ctx_t *ctx, uint8_t *d_counts, const uint8_t *d_st
 int dyn_barcode_first_pos(dyn_ctx_t *ctx, const uint32_t *d_barcode, const uint8_t *d_strand, const uint16_t *d_conv_n,
                           int64_t n_reads, int64_t n_barcodes, uint64_t *d_first_pos, uint32_t *d_n_reads, void *stream);
 
+/* Host half of the same step: HOST arrays in, HOST arrays out; h_ord_of_barcode = rank of the barcode in
+ * split-file order, h_split_of_barcode = index of its split file, *h_n_splits = number of splits. */
+int dyn_split_plan(const uint64_t *h_first_pos, const uint32_t *h_n_reads, int64_t n_barcodes, int64_t threshold,
+                   uint32_t *h_ord_of_barcode, uint32_t *h_split_of_barcode, int64_t *h_n_splits);
+
 /* ------------------------------------------------------------------------------------------------
  * a5 + a6: UMI deduplication and output ordering.
  * Replaces conversion.deduplicate_counts (conversion.py:203-243) as driven by count_conversions

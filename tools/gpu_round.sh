@@ -6,7 +6,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$tag.log 2>&1; echo "pyt
 tail -5 gpurun_out/pytest_$tag.log
 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
 cat gpurun_out/bench_$tag.json
-B="python bench.py --reads 4000000 --steps 2 --warmup 1 --skip-e2e --skip-cpu --em-barcodes 2000"
+B="python bench.py --reads 4000000 --steps 2 --warmup 1 --skip-e2e --skip-cpu --skip-pipeline --em-barcodes 2000"
 $B > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $B > gpurun_out/ncu_l_$tag.log 2>&1
 $B > gpurun_out/plain2_$tag.log 2>&1 &&
