@@ -281,6 +281,45 @@ def pi_golden():
                         alpha_beta_pi=np.asarray(out))
 
 
+def adata_golden():
+    """Layers of the reference's utils.results_to_adata (anndata replaced by a capturing stand-in) for the
+    synthetic counts of synth_counts/umi_dual, with pi and with alpha estimates."""
+    import io
+    import dynast.utils as du
+    import dynast.preprocessing.conversion as conv
+
+    class Capture:
+        def __init__(self, X=None, obs=None, var=None, layers=None):
+            self.X, self.obs, self.var, self.layers = X, obs, var, layers
+
+    du.anndata.AnnData = Capture
+    name = 'umi_dual'
+    with open(os.path.join(GOLD, 'synth_counts', name, 'meta.json')) as f:
+        meta = json.load(f)
+    with gzip.open(os.path.join(GOLD, 'synth_counts', name, 'counts.csv.gz'), 'rt') as f:
+        df = conv.complement_counts(conv.read_counts(io.StringIO(f.read())), meta['genes'])
+    conversions = frozenset({frozenset({'TC'}), frozenset({'AG'})})
+    rng = np.random.default_rng(77)
+    pairs = sorted(set(zip(df['barcode'], df['GX'])))
+    pis = {key: {('TC',): {p: float(rng.random()) for p in pairs[::2]}, ('AG',): {p: float(rng.random()) for p in pairs[1::3]}}
+           for key in ('transcriptome', 'total', 'spliced', 'unspliced')}
+    barcodes = sorted(set(df['barcode']))
+    alphas = {key: {('TC',): {b: float(rng.uniform(0.2, 1.3)) for b in barcodes[::2]}} for key in ('transcriptome', 'total', 'spliced')}
+    out = {}
+    for tag, kw in (('plain', {}), ('pi', dict(pis=pis)), ('alpha', dict(alphas=alphas))):
+        ad = du.results_to_adata(df, conversions, gene_infos=None, **kw)
+        out[f'{tag}/X'] = ad.X.toarray()
+        for k, v in ad.layers.items():
+            out[f'{tag}/layer/{k}'] = v.toarray()
+        for c in ad.obs.columns:
+            out[f'{tag}/obs/{c}'] = ad.obs[c].to_numpy(dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, 'adata_golden.npz'), **out)
+    with open(os.path.join(GOLD, 'adata_golden_inputs.json'), 'w') as f:
+        json.dump(dict(pis={k: {'_'.join(c): {'|'.join(p): v for p, v in d.items()} for c, d in byc.items()} for k, byc in pis.items()},
+                       alphas={k: {'_'.join(c): d for c, d in byc.items()} for k, byc in alphas.items()}), f)
+    print('adata_golden', len(out), 'arrays')
+
+
 def main():
     refstub.install()
     os.makedirs(GOLD, exist_ok=True)
@@ -289,6 +328,7 @@ def main():
     em_golden()
     synth_counts()
     pi_golden()
+    adata_golden()
 
 
 if __name__ == '__main__':

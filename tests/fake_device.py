@@ -199,3 +199,14 @@ def install(monkeypatch):
         return p_c, status, np.zeros(len(p_e), dtype=np.int32)
 
     monkeypatch.setattr(device, 'em_pc_host', em_pc_host)
+    from dynast_b200.preprocessing import snp
+    monkeypatch.setattr(snp, 'unique_counts', unique_counts_host)
+
+
+def unique_counts_host(keys):
+    """numpy stand-in for dyn_unique_counts (preprocessing.snp.unique_counts)."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    valid = keys != np.uint64(0xffffffffffffffff)
+    uk, first, cnt = np.unique(keys[valid], return_index=True, return_counts=True)
+    pos = np.flatnonzero(valid)[first] if len(uk) else np.zeros(0, dtype=np.int64)
+    return uk, cnt.astype(np.uint32), pos.astype(np.uint32)
