@@ -10,7 +10,7 @@
 //   * one thread per counting unit ("warp per read batch": a warp owns 32 consecutive reads); a tile is
 //     kThreads consecutive packed records = ONE contiguous byte range of the record blob, fetched by one
 //     TMA 1-D bulk copy (cp.async.bulk -> UBLKCP) into shared memory and awaited on an mbarrier.
-//     CTAs are small (128 threads, ~40 KB) so five or six share an SM: while one waits for its tile
+//     CTAs are small (64 threads, ~20 KB) so eight to ten share an SM: while one waits for its tile
 //     the others walk theirs (multi-buffering across CTAs, no intra-CTA pipeline state);
 //   * the walk keeps the lanes of a warp converged (v1, a per-read CIGAR/MD state machine, ran with
 //     5.7 of 32 lanes active; v3, per-lane event loops, spent 45 % of its instructions at 3 lanes):
@@ -36,13 +36,13 @@
 namespace {
 
 #ifndef DYN_TALLY_THREADS
-#define DYN_TALLY_THREADS 128
+#define DYN_TALLY_THREADS 64
 #endif
 #ifndef DYN_TALLY_SLOTS
 #define DYN_TALLY_SLOTS 8
 #endif
 #ifndef DYN_TALLY_MIN_CTAS
-#define DYN_TALLY_MIN_CTAS 5
+#define DYN_TALLY_MIN_CTAS 8
 #endif
 constexpr int kThreads = DYN_TALLY_THREADS;
 constexpr int kWarps = kThreads / 32;
@@ -344,14 +344,28 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
     const bool emit = (p.flags & DYN_TALLY_EMIT_CONV) != 0;
     const uint32_t cap16 = p.stage_bytes >> 4;
 
+    // Offsets of the NEXT tile are fetched while the current one is being walked: the dependent chain
+    // rec_off -> TMA issue -> mbarrier wait was 14 % of the stall samples (profiles/r1_tally_v4_ncu_summary.txt).
+    uint32_t pf_off0 = 0, pf_off_end = 0, pf_my_off = 0, pf_my_end = 0;
+    auto prefetch_offsets = [&](long long tile) {
+        if (tile >= p.n_tiles) return;
+        const long long n0 = tile * kThreads, n1 = min(p.n_reads, n0 + (long long)kThreads);
+        pf_off0 = __ldg(p.rec_off + n0);
+        pf_off_end = __ldg(p.rec_off + n1);
+        const long long r = n0 + tid;
+        if (r < n1) { pf_my_off = __ldg(p.rec_off + r); pf_my_end = __ldg(p.rec_off + r + 1); }
+    };
+    prefetch_offsets(blockIdx.x);
+
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long t0 = tile * kThreads;
         const long long t1 = min(p.n_reads, t0 + (long long)kThreads);
-        const uint32_t off_end = __ldg(p.rec_off + t1);
+        const uint32_t off_end = pf_off_end, tile_off0 = pf_off0, tile_my_off = pf_my_off, tile_my_end = pf_my_end;
         long long r0 = t0;
         while (r0 < t1) {
             // ---- sub-tile [r0, r1): as many reads as fit the staging buffer (normally the whole tile)
-            const uint32_t off0 = __ldg(p.rec_off + r0);
+            const bool first_sub = r0 == t0;
+            const uint32_t off0 = first_sub ? tile_off0 : __ldg(p.rec_off + r0);
             long long r1 = t1;
             bool oversized = false;
             if (off_end - off0 > cap16) {                // uniform across the CTA
@@ -368,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                 __syncthreads();
                 if (cnt == 0) { oversized = true; r1 = r0 + 1; } else r1 = r0 + cnt;
             }
-            const uint32_t off1 = __ldg(p.rec_off + r1);
+            const uint32_t off1 = (r1 == t1) ? off_end : __ldg(p.rec_off + r1);
             const uint32_t bytes = oversized ? 0u : (off1 - off0) << 4;
             if (tid == 0 && bytes > 0) {
                 fence_proxy_async();
@@ -378,7 +392,11 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             const long long r = r0 + tid;
             const bool inrange = r < r1;
             uint32_t my_off = off0, my_end = off0;
-            if (inrange) { my_off = __ldg(p.rec_off + r); my_end = __ldg(p.rec_off + r + 1); }
+            if (inrange) {
+                if (first_sub) { my_off = tile_my_off; my_end = tile_my_end; }
+                else { my_off = __ldg(p.rec_off + r); my_end = __ldg(p.rec_off + r + 1); }
+            }
+            if (first_sub) prefetch_offsets(tile + gridDim.x);
             const size_t unit_bytes = (size_t)(my_end - my_off) << 4;
             if (bytes > 0) {
                 mbar_wait(bar, parity);

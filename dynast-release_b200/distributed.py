@@ -76,3 +76,27 @@ def read_range(n_reads: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous read range of a rank (read-range sharding of a coordinate-sorted BAM)."""
     per = (n_reads + world - 1) // world
     return min(rank * per, n_reads), min((rank + 1) * per, n_reads)
+
+
+def exchange_by_owner(owner: torch.Tensor, *columns: torch.Tensor, group=None):
+    """All-to-all of per-read rows to the rank that owns them (UMI groups may straddle read ranges, so
+    before dedup every rank sends its fixed-size per-read records -- group key, 16 counters, priority fields -- to
+    owner = barcode mod world).  `owner` [n] holds the destination rank of every local row; each column is a
+    tensor with leading dimension n.  Returns the received columns, grouped by source rank in rank order (rows
+    of one source keep their order, so a stable concatenation of read ranges is preserved)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [c for c in columns]
+    order = torch.argsort(owner, stable=True)
+    send_counts = torch.bincount(owner, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    send_split = [int(x) for x in send_counts.tolist()]
+    recv_split = [int(x) for x in recv_counts.tolist()]
+    out = []
+    for c in columns:
+        src = c[order].contiguous()
+        dst = torch.empty((sum(recv_split),) + tuple(c.shape[1:]), dtype=c.dtype, device=c.device)
+        dist.all_to_all_single(dst, src, output_split_sizes=recv_split, input_split_sizes=send_split, group=group)
+        out.append(dst)
+    return out

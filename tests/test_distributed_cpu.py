@@ -44,6 +44,21 @@ def _worker(rank, world, port, n_barcodes, out_dir):
     p_c, status = distributed.distributed_p_c(rows, p_e, n_barcodes, _oracle_em)
     np.save(os.path.join(out_dir, f'pc{rank}.npy'), p_c.numpy())
     np.save(os.path.join(out_dir, f'st{rank}.npy'), status.numpy())
+    # per-read exchange to the barcode owner (all-to-all): every row must land on rank barcode % world, rows of
+    # one source rank in their original order, sources in rank order
+    g = torch.Generator().manual_seed(7 + rank)
+    bc = torch.randint(0, n_barcodes, (300 + 50 * rank,), generator=g)
+    payload = torch.stack([bc, torch.arange(len(bc)) + 1000 * rank], dim=1)
+    counts = torch.randint(0, 255, (len(bc), 16), generator=g).to(torch.uint8)
+    got_payload, got_counts = distributed.exchange_by_owner(bc % world, payload, counts)
+    assert (got_payload[:, 0] % world == rank).all()
+    assert got_counts.shape == (got_payload.shape[0], 16)
+    src = got_payload[:, 1] // 1000
+    assert (src[1:] >= src[:-1]).all()
+    for r in range(world):
+        idx = got_payload[src == r, 1]
+        assert (idx[1:] > idx[:-1]).all()
+    np.save(os.path.join(out_dir, f'xchg{rank}.npy'), got_payload.numpy())
     lo, hi = distributed.read_range(1001, rank, world)
     assert (lo, hi) == ((0, 501) if rank == 0 else (501, 1001))
     dist.destroy_process_group()
@@ -57,6 +72,8 @@ def test_histogram_exchange_world2(tmp_path, oracle_lib):
     sts = [np.load(tmp_path / f'st{r}.npy') for r in range(world)]
     assert np.array_equal(sts[0], sts[1])
     assert np.array_equal(pcs[0], pcs[1], equal_nan=True)
+    got = np.concatenate([np.load(tmp_path / f'xchg{r}.npy') for r in range(world)])
+    assert len(got) == sum(300 + 50 * r for r in range(world)) and len(np.unique(got[:, 1])) == len(got)
     # single-process answer over the union of the rows
     sys.path.insert(0, ROOT)
     from dynast_b200 import distributed
