@@ -39,7 +39,7 @@ PROTOTYPES = {
                                 _vp, _vp]),
     'dyn_kn_csr': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_pi_fit': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
-    'dyn_consensus': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'dyn_consensus': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'dyn_coverage': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     'dyn_unique_counts': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     'dyn_bam_pack': (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),

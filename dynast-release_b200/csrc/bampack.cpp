@@ -118,14 +118,46 @@ struct dyn_bam_result {
 
 namespace {
 
-// packed size of one BAM record
-inline size_t packed_bytes(uint32_t l_seq, uint32_t n_cigar, size_t md_len) {
-    const size_t b = 16 + 4 * (size_t)n_cigar + ((((size_t)l_seq + 1) / 2 + 3) & ~(size_t)3) + l_seq + md_len;
-    return (b + 15) & ~(size_t)15;
+// BAM 4-bit code of an MD letter
+inline uint32_t letter_code(char ch) {
+    static const char codes[] = "=ACMGRSVTWYHKDBN";
+    if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
+    for (uint32_t i = 0; i < 16; ++i)
+        if (codes[i] == ch) return i;
+    return 0;
+}
+
+// MD text -> tokens (include/dynast_b200.h); returns false when the tag disagrees with the CIGAR
+bool tokenize_md(const char *md, size_t md_len, const uint8_t *cigar, uint32_t n_cigar, std::vector<uint32_t> &toks) {
+    toks.clear();
+    uint64_t aoff = 0, val = 0, n_del = 0;
+    bool in_del = false, ok = true;
+    for (size_t i = 0; i < md_len; ++i) {
+        const char ch = md[i];
+        if (ch >= '0' && ch <= '9') { val = val * 10 + (uint64_t)(ch - '0'); in_del = false; }
+        else if (ch == '^') { aoff += val; val = 0; in_del = true; }
+        else if (in_del) { toks.push_back((uint32_t)std::min<uint64_t>(aoff, 0xffff) | (letter_code(ch) << 16) | (1u << 20)); ++n_del; }
+        else {
+            aoff += val; val = 0;
+            if (aoff > 0xffff) ok = false;
+            toks.push_back((uint32_t)(aoff & 0xffff) | (letter_code(ch) << 16));
+            ++aoff;
+        }
+    }
+    aoff += val;
+    uint64_t m_total = 0, d_total = 0;
+    for (uint32_t c = 0; c < n_cigar; ++c) {
+        const uint32_t w = rd32(cigar + 4 * (size_t)c), op = w & 0xf, len = w >> 4;
+        if (op == 0 || op == 7 || op == 8) m_total += len;
+        else if (op == 2) d_total += len;
+    }
+    if (aoff != m_total || n_del != d_total) ok = false;
+    if (toks.size() > 0xffff) { toks.clear(); ok = false; }
+    return ok;
 }
 
 // rec points at the BAM alignment record body (after block_size)
-size_t pack_record(const uint8_t *rec, const Aux &a, uint16_t extra_flag, std::vector<uint8_t> &out) {
+size_t pack_record(const uint8_t *rec, const Aux &a, uint16_t extra_flag, std::vector<uint32_t> &toks, std::vector<uint8_t> &out) {
     const int32_t ref_id = (int32_t)rd32(rec), pos = (int32_t)rd32(rec + 4);
     const uint32_t l_read_name = rec[8];
     const uint32_t n_cigar = rd16(rec + 12);
@@ -134,20 +166,24 @@ size_t pack_record(const uint8_t *rec, const Aux &a, uint16_t extra_flag, std::v
     const uint8_t *cigar = rec + 32 + l_read_name;
     const uint8_t *seq = cigar + 4 * (size_t)n_cigar;
     const uint8_t *qual = seq + (l_seq + 1) / 2;
-    const size_t bytes = packed_bytes(l_seq, n_cigar, a.md_len);
+    const bool ok = tokenize_md(a.md, a.md_len, cigar, n_cigar, toks);
+    const size_t raw = 16 + 4 * (size_t)n_cigar + 4 * toks.size() + ((((size_t)l_seq + 1) / 2 + 3) & ~(size_t)3) + l_seq;
+    const size_t bytes = (raw + 15) & ~(size_t)15;
     const size_t o = out.size();
     out.resize(o + bytes, 0);
     uint8_t *p = out.data() + o;
     memcpy(p, &pos, 4); memcpy(p + 4, &ref_id, 4);
-    const uint16_t ls = (uint16_t)l_seq, nc = (uint16_t)n_cigar, ml = (uint16_t)a.md_len, fl = (uint16_t)((flag & 0x0fff) | extra_flag);
-    memcpy(p + 8, &ls, 2); memcpy(p + 10, &nc, 2); memcpy(p + 12, &ml, 2); memcpy(p + 14, &fl, 2);
+    const uint16_t ls = (uint16_t)l_seq, nc = (uint16_t)n_cigar, nt = (uint16_t)toks.size();
+    const uint16_t fl = (uint16_t)((flag & 0x0fff) | extra_flag | (ok ? 0 : DYN_REC_BAD_MD));
+    memcpy(p + 8, &ls, 2); memcpy(p + 10, &nc, 2); memcpy(p + 12, &nt, 2); memcpy(p + 14, &fl, 2);
     memcpy(p + 16, cigar, 4 * (size_t)n_cigar);
-    uint8_t *ps = p + 16 + 4 * (size_t)n_cigar;
+    uint8_t *pt = p + 16 + 4 * (size_t)n_cigar;
+    if (!toks.empty()) memcpy(pt, toks.data(), 4 * toks.size());
+    uint8_t *ps = pt + 4 * toks.size();
     memcpy(ps, seq, (l_seq + 1) / 2);
     if (l_seq & 1) ps[l_seq / 2] &= 0xf0;     // the spec leaves the low nibble of the last byte undefined
     uint8_t *pq = ps + ((((size_t)l_seq + 1) / 2 + 3) & ~(size_t)3);
     memcpy(pq, qual, l_seq);
-    memcpy(pq + l_seq, a.md, a.md_len);
     return bytes;
 }
 
@@ -244,6 +280,7 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
     std::unordered_map<std::string, Pending> pending;
     int32_t cur_ref = -2;
     std::string key;
+    std::vector<uint32_t> toks;
     while (p + 4 <= n) {
         const uint32_t block_size = rd32(d + p);
         const uint8_t *rec = d + p + 4;
@@ -265,7 +302,7 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
         if (barcode_tag && a.bc_len == 1 && a.bc[0] == '-') continue;       // bam.py:290
         if (!a.has_hi || !a.has_as) { delete res; dyn_set_error("dyn_bam_pack: alignment without HI / AS tag (KeyError in the reference, bam.py:295-296)"); return DYN_ERR_FORMAT; }
         if (!a.has_md) { delete res; dyn_set_error("dyn_bam_pack: alignment without MD tag (count.py:119-124)"); return DYN_ERR_FORMAT; }
-        if (l_seq > 0xffff || n_cigar > 0xffff || a.md_len > 0xffff) { delete res; dyn_set_error("dyn_bam_pack: record too long for the packed layout"); return DYN_ERR_FORMAT; }
+        if (l_seq > 0xffff || n_cigar > 0xffff) { delete res; dyn_set_error("dyn_bam_pack: record too long for the packed layout"); return DYN_ERR_FORMAT; }
         const char *name = (const char *)rec + 32;
         const size_t name_len = l_read_name ? l_read_name - 1 : 0;
         const uint8_t *mate_rec = nullptr;
@@ -283,8 +320,8 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
             parse_aux(mate_rec + 32 + m_name + 4 * (size_t)m_cig + (m_seq + 1) / 2 + m_seq, mate_rec + m_size, barcode_tag, umi_tag, gene_tag, ma);
             if (!ma.has_md) { delete res; dyn_set_error("dyn_bam_pack: alignment without MD tag (count.py:119-124)"); return DYN_ERR_FORMAT; }
         }
-        pack_record(rec, a, mate_rec ? DYN_REC_HAS_MATE : 0, blob);
-        if (mate_rec) pack_record(mate_rec, ma, 0, blob);
+        pack_record(rec, a, mate_rec ? DYN_REC_HAS_MATE : 0, toks, blob);
+        if (mate_rec) pack_record(mate_rec, ma, 0, toks, blob);
         res->rec_off.push_back((uint32_t)(blob.size() >> 4));
         res->ref_id.push_back(ref_id);
         res->pos.push_back((int32_t)rd32(rec + 4));

@@ -15,8 +15,9 @@
 //               rules of consensus.py:137-146, quality clipped to 42 -> one 32-bit cell per covered position.
 //   4. assemble one thread per group walks its cells: run-length CIGAR (gaps become N ops), MD and NM exactly
 //               as consensus.py:116-176 builds them, 4-bit sequence and qualities -> one packed record
-//               (the same layout the tally reads, so `dynast count` can run on the result without a BAM
-//               round trip).  Sizes first, exclusive scan, then the write pass.
+//               (the same layout the tally reads -- MD as tokens -- so `dynast count` can run on the result
+//               without a BAM round trip) plus the MD text for the BAM writer.  Sizes first, exclusive scans,
+//               then the write pass.
 // HBM-bound on the sort: 12 B per base tuple, moved ~2 x 8 radix passes; algorithmic bytes = the group's
 // packed records in + one record out.
 #include <cub/cub.cuh>
@@ -125,7 +126,7 @@ __global__ void reduce_kernel(const unsigned long long *key, const uint32_t *val
     cell[idx[i]] = out;
 }
 
-struct GroupOut { uint32_t n_cigar, l_seq, md_len, nm; };
+struct GroupOut { uint32_t n_cigar, l_seq, md_len, nm, n_tok; };
 
 __device__ __forceinline__ int num_digits(uint32_t v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
 __device__ __forceinline__ uint8_t *put_num(uint8_t *p, uint32_t v) {
@@ -138,8 +139,9 @@ __device__ __forceinline__ uint8_t *put_num(uint8_t *p, uint32_t v) {
 template <bool WRITE>
 __global__ void assemble_kernel(const unsigned long long *cell_key, const uint32_t *cell, const long long *n_cells_p,
                                 long long n_groups, const uint32_t *g_left, const uint32_t *g_right, const int32_t *g_ref,
-                                GroupOut *sizes, uint32_t *out_cap16, const uint32_t *out_off, uint8_t *out,
-                                long long out_capacity16, uint32_t *out_nm, int32_t *status) {
+                                GroupOut *sizes, uint32_t *out_cap16, uint32_t *md_cap, const uint32_t *out_off, uint8_t *out,
+                                long long out_capacity16, const uint32_t *md_off, uint8_t *out_md, long long md_capacity,
+                                uint32_t *out_nm, int32_t *status) {
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     const long long n_cells = *n_cells_p;
@@ -148,32 +150,33 @@ __global__ void assemble_kernel(const unsigned long long *cell_key, const uint32
     const long long c0 = lo;
     const uint32_t left = g_left[g], right = g_right[g];
     const bool empty = left == 0xffffffffu;      // group without reads
-    uint32_t *cig = nullptr;
+    uint32_t *cig = nullptr, *tokp = nullptr;
     uint8_t *seq = nullptr, *qual = nullptr, *md = nullptr;
-    GroupOut sz = {0, 0, 0, 0};
+    GroupOut sz = {0, 0, 0, 0, 0};
     bool fits = true;
     if (WRITE) {
         sz = sizes[g];
-        if ((long long)out_off[g + 1] > out_capacity16 || status[g] == 3) fits = false;
+        if ((long long)out_off[g + 1] > out_capacity16 || (long long)md_off[g + 1] > md_capacity || status[g] == 3) fits = false;
         uint8_t *rec = out + ((size_t)out_off[g] << 4);
         if (fits) {
             uint32_t *h = reinterpret_cast<uint32_t *>(rec);
             h[0] = empty ? 0u : left;
             h[1] = (uint32_t)g_ref[g];
             h[2] = sz.l_seq | (sz.n_cigar << 16);
-            h[3] = sz.md_len;      // flag 0: the caller sets strand / tags
+            h[3] = sz.n_tok;       // flag 0: the caller sets strand / tags
             cig = reinterpret_cast<uint32_t *>(rec + 16);
-            seq = rec + 16 + 4 * (size_t)sz.n_cigar;
+            tokp = cig + sz.n_cigar;
+            seq = reinterpret_cast<uint8_t *>(tokp + sz.n_tok);
             const size_t seq_bytes = pad4(((size_t)sz.l_seq + 1) >> 1);
             for (size_t b = 0; b < seq_bytes; ++b) seq[b] = 0;
             qual = seq + seq_bytes;
-            md = qual + sz.l_seq;
-            const size_t used = 16 + 4 * (size_t)sz.n_cigar + seq_bytes + sz.l_seq + sz.md_len;
+            md = out_md + md_off[g];
+            const size_t used = 16 + 4 * (size_t)sz.n_cigar + 4 * (size_t)sz.n_tok + seq_bytes + sz.l_seq;
             for (size_t b = used; b < (((size_t)out_off[g + 1] - out_off[g]) << 4); ++b) rec[b] = 0;
             out_nm[g] = sz.nm;
         }
     }
-    uint32_t n_cigar = 0, l_seq = 0, md_len = 0, nm = 0;
+    uint32_t n_cigar = 0, l_seq = 0, md_len = 0, nm = 0, n_tok = 0;
     uint32_t run_op = 0xffu, run_n = 0;     // ops: 0 M, 2 D, 3 N (BAM codes)
     uint32_t md_n = 0;
     bool md_zero = true, md_del = false;
@@ -202,8 +205,8 @@ __global__ void assemble_kernel(const unsigned long long *cell_key, const uint32
                 cigar_push(2, 1);
                 md_number();
                 if (!md_del) { if (WRITE && fits) *mdp++ = '^'; ++md_len; }
-                if (WRITE && fits) *mdp++ = (uint8_t)"ACGT"[ref];
-                ++md_len;
+                if (WRITE && fits) { *mdp++ = (uint8_t)"ACGT"[ref]; tokp[n_tok] = min(l_seq, 0xffffu) | ((1u << ref) << 16) | (1u << 20); }
+                ++md_len; ++n_tok;
                 md_del = true;
             } else {
                 cigar_push(0, 1);
@@ -212,8 +215,8 @@ __global__ void assemble_kernel(const unsigned long long *cell_key, const uint32
                 if (base == ref) { ++md_n; md_zero = false; }
                 else {
                     md_number();
-                    if (WRITE && fits) *mdp++ = (uint8_t)"ACGT"[ref];
-                    ++md_len;
+                    if (WRITE && fits) { *mdp++ = (uint8_t)"ACGT"[ref]; tokp[n_tok] = (l_seq & 0xffffu) | ((1u << ref) << 16); }
+                    ++md_len; ++n_tok;
                     md_zero = true;
                     ++nm;
                 }
@@ -231,11 +234,12 @@ __global__ void assemble_kernel(const unsigned long long *cell_key, const uint32
     md_len += num_digits(md_n);
     if (run_op != 0xffu) { if (WRITE && fits) cig[n_cigar] = (run_n << 4) | run_op; ++n_cigar; }
     if (!WRITE) {
-        GroupOut o = {n_cigar, l_seq, md_len, nm};
+        GroupOut o = {n_cigar, l_seq, md_len, nm, n_tok};
         sizes[g] = o;
-        const size_t bytes = 16 + 4 * (size_t)n_cigar + pad4(((size_t)l_seq + 1) >> 1) + l_seq + md_len;
+        const size_t bytes = 16 + 4 * (size_t)n_cigar + 4 * (size_t)n_tok + pad4(((size_t)l_seq + 1) >> 1) + l_seq;
         out_cap16[g] = (uint32_t)((bytes + 15) >> 4);
-        if (n_cigar > 0xffffu || l_seq > 0xffffu || md_len > 0xffffu) status[g] = 3;   // does not fit a BAM record
+        md_cap[g] = md_len;
+        if (n_cigar > 0xffffu || l_seq > 0xffffu || n_tok > 0xffffu) status[g] = 3;   // does not fit a BAM record
     } else if (!fits && status[g] == 0) status[g] = 5;   // output capacity exceeded
 }
 
@@ -249,12 +253,13 @@ __global__ void init_groups_kernel(uint32_t *g_left, uint32_t *g_right, int32_t 
 
 extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_item_rec16, const int64_t *d_group_off,
                              int64_t n_groups, int64_t n_items, int quality, void *d_out_records,
-                             int64_t out_capacity_bytes, uint32_t *d_out_off, uint32_t *d_out_nm, int32_t *d_out_status,
-                             void *stream_) {
+                             int64_t out_capacity_bytes, uint32_t *d_out_off, void *d_out_md, int64_t md_capacity_bytes,
+                             uint32_t *d_out_md_off, uint32_t *d_out_nm, int32_t *d_out_status, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
     DYN_ARG(n_groups >= 0 && n_items >= 0 && n_groups < 0xffffffffLL, "size out of range");
     if (n_groups == 0) return DYN_OK;
-    DYN_ARG(d_group_off && d_out_off && d_out_nm && d_out_status, "null buffer");
+    DYN_ARG(d_group_off && d_out_off && d_out_md_off && d_out_nm && d_out_status, "null buffer");
+    DYN_ARG(md_capacity_bytes == 0 || d_out_md, "null MD output");
     DYN_ARG(n_items == 0 || (d_records && d_item_rec16), "null records");
     DYN_ARG(out_capacity_bytes == 0 || d_out_records, "null output");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -266,7 +271,7 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr, n_items + 1, stream);
     cub::DeviceScan::ExclusiveSum(nullptr, t, (uint32_t *)nullptr, (uint32_t *)nullptr, n_groups + 1, stream);
     if (t > scan_tmp) scan_tmp = t;
-    uint32_t *g_left, *g_right, *out_cap16;
+    uint32_t *g_left, *g_right, *out_cap16, *md_cap;
     int32_t *g_ref;
     unsigned long long *tuple_cnt, *tuple_off;
     GroupOut *sizes;
@@ -278,6 +283,7 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
         tuple_off = a0.take<unsigned long long>(n_items + 1);
         g_left = a0.take<uint32_t>(n_groups); g_right = a0.take<uint32_t>(n_groups); g_ref = a0.take<int32_t>(n_groups);
         out_cap16 = a0.take<uint32_t>(n_groups + 1);
+        md_cap = a0.take<uint32_t>(n_groups + 1);
         sizes = a0.take<GroupOut>(n_groups);
         n_cells = a0.take<long long>(2);
         tmp0 = a0.take<uint8_t>(scan_tmp);
@@ -352,13 +358,19 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
 
     // ---- assemble: sizes, offsets, records
     assemble_kernel<false><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, n_groups, g_left, g_right, g_ref, sizes,
-                                                                     out_cap16, nullptr, nullptr, 0, d_out_nm, d_out_status);
+                                                                     out_cap16, md_cap, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                                                                     d_out_nm, d_out_status);
     DYN_CUDA(cudaMemsetAsync(out_cap16 + n_groups, 0, 4, stream));
+    DYN_CUDA(cudaMemsetAsync(md_cap + n_groups, 0, 4, stream));
     t = scan_tmp;
     DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, out_cap16, d_out_off, n_groups + 1, stream));
+    t = scan_tmp;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, md_cap, d_out_md_off, n_groups + 1, stream));
     assemble_kernel<true><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, n_groups, g_left, g_right, g_ref, sizes,
-                                                                    out_cap16, d_out_off, static_cast<uint8_t *>(d_out_records),
-                                                                    out_capacity_bytes >> 4, d_out_nm, d_out_status);
+                                                                    out_cap16, md_cap, d_out_off, static_cast<uint8_t *>(d_out_records),
+                                                                    out_capacity_bytes >> 4, d_out_md_off,
+                                                                    static_cast<uint8_t *>(d_out_md), md_capacity_bytes, d_out_nm,
+                                                                    d_out_status);
     DYN_CUDA(cudaGetLastError());
     return DYN_OK;
 }

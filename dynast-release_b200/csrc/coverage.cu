@@ -43,14 +43,14 @@ __global__ void coverage_kernel(const uint8_t *records, const uint32_t *rec_off,
     if (u >= n_units || (selected && !selected[u])) return;
     const uint8_t *rec = records + ((size_t)rec_off[u] << 4);
     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
-    const uint32_t n_cigar = h.z >> 16, l_seq = h.z & 0xffff, md_len = h.w & 0xffff;
+    const uint32_t n_cigar = h.z >> 16, l_seq = h.z & 0xffff, n_tok = h.w & 0xffff;
     const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
     const bool has_mate = ((h.w >> 16) & DYN_REC_HAS_MATE) != 0;
     const unsigned long long contig = (unsigned long long)h.y << 32;
     for (int which = 0; which < (has_mate ? 2 : 1); ++which) {
         const uint8_t *r2 = rec;
         if (which == 1) {
-            const size_t b = 16 + 4 * (size_t)n_cigar + (((((size_t)l_seq + 1) >> 1) + 3) & ~(size_t)3) + l_seq + md_len;
+            const size_t b = 16 + 4 * (size_t)n_cigar + 4 * (size_t)n_tok + (((((size_t)l_seq + 1) >> 1) + 3) & ~(size_t)3) + l_seq;
             r2 = rec + ((b + 15) & ~(size_t)15);
         }
         const uint4 h2 = *reinterpret_cast<const uint4 *>(r2);

@@ -53,15 +53,7 @@ __device__ int cdf_search(const float *cdf, int n, float u) {
 }
 
 constexpr int kMaxLen = 304;      // read_len limit of the generator
-constexpr int kMaxMd = 448;
-
-__device__ int put_num(uint8_t *md, int p, int v) {
-    char tmp[8];
-    int n = 0;
-    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) md[p++] = (uint8_t)tmp[--n];
-    return p;
-}
+constexpr int kMaxTok = 320;
 
 struct Keys {
     uint32_t barcode, gene;
@@ -102,9 +94,9 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
     }
     uint8_t seq[(kMaxLen + 1) / 2 + 4];
     uint8_t qual[kMaxLen];
-    uint8_t md[kMaxMd];
+    uint32_t tok[kMaxTok];
     for (int i = 0; i < (L + 1) / 2 + 4; ++i) seq[i] = 0;
-    int qp = 0, mdp = 0, run = 0, nm = 0;
+    int qp = 0, n_tok = 0, aligned = 0, nm = 0;
     const int conv_from = rev_gene ? 0 : 3, conv_to = rev_gene ? 2 : 1;
     const float pc = (float)P.p_c, pe3 = (float)(3.0 * P.p_e), fn = (float)P.frac_n;
     const uint8_t code[4] = {1, 2, 4, 8};
@@ -126,20 +118,16 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
                 const bool is_n = u3 < fn;
                 const uint8_t nib = is_n ? 15 : code[b];
                 seq[qp >> 1] |= nib << ((qp & 1) ? 0 : 4);
-                if (!is_n && b == gb) ++run;
-                else {
-                    mdp = put_num(md, mdp, run);
-                    md[mdp++] = (uint8_t)"ACGT"[gb];
-                    run = 0;
+                if (is_n || b != gb) {
+                    if (n_tok < kMaxTok) tok[n_tok++] = (uint32_t)aligned | ((uint32_t)code[gb] << 16);
                     ++nm;
                 }
+                ++aligned;
                 ++qp;
             }
         } else if (op == 2) {
-            mdp = put_num(md, mdp, run);
-            run = 0;
-            md[mdp++] = '^';
-            for (int j = 0; j < len; ++j) md[mdp++] = (uint8_t)"ACGT"[g.next() & 3];
+            for (int j = 0; j < len; ++j)
+                if (n_tok < kMaxTok) tok[n_tok++] = (uint32_t)aligned | ((uint32_t)code[g.next() & 3] << 16) | (1u << 20);
         } else if (op == 1 || op == 4) {
             for (int j = 0; j < len; ++j) {
                 const unsigned long long r = g.next();
@@ -149,9 +137,8 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
             }
         }
     }
-    mdp = put_num(md, mdp, run);
     const int seq_bytes = (((L + 1) >> 1) + 3) & ~3;
-    const size_t raw = 16 + 4 * (size_t)n_cig + seq_bytes + L + mdp;
+    const size_t raw = 16 + 4 * (size_t)n_cig + 4 * (size_t)n_tok + seq_bytes + L;
     const size_t bytes = (raw + 15) & ~(size_t)15;
     if (keys) {
         keys->barcode = (uint32_t)bc; keys->gene = (uint32_t)gene; keys->umi = umi;
@@ -161,18 +148,18 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
         dyn_read_hdr_t h;
         h.pos = (int32_t)(((unsigned long long)idx * (unsigned long long)P.pos_span) / 0x100000000ull);
         h.ref_id = P.gene_contig[gene];
-        h.l_seq = (uint16_t)L; h.n_cigar = (uint16_t)n_cig; h.md_len = (uint16_t)mdp;
+        h.l_seq = (uint16_t)L; h.n_cigar = (uint16_t)n_cig; h.n_tok = (uint16_t)n_tok;
         h.flag = (g.next() & 1) ? 16 : 0;
         *reinterpret_cast<uint4 *>(out) = *reinterpret_cast<uint4 *>(&h);
         uint8_t *p = out + 16;
         for (int i = 0; i < n_cig; ++i) reinterpret_cast<uint32_t *>(p)[i] = cig[i];
         p += 4 * n_cig;
+        for (int i = 0; i < n_tok; ++i) reinterpret_cast<uint32_t *>(p)[i] = tok[i];
+        p += 4 * n_tok;
         for (int i = 0; i < seq_bytes; ++i) p[i] = seq[i];
         p += seq_bytes;
         for (int i = 0; i < L; ++i) p[i] = qual[i];
         p += L;
-        for (int i = 0; i < mdp; ++i) p[i] = md[i];
-        p += mdp;
         for (size_t i = raw; i < bytes; ++i) *p++ = 0;
     }
     return bytes;

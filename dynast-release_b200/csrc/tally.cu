@@ -16,9 +16,10 @@
 //     5.7 of 32 lanes active; v3, per-lane event loops, spent 45 % of its instructions at 3 lanes):
 //       1. base content of the WHOLE query in a fixed-trip loop, 8 bases per 32-bit word with nibble
 //          one-hot bit planes (no popc, no masks);
-//       2. CIGAR pre-scan and a one-byte-per-iteration MD scan with warp-uniform trip counts that only
-//          LOCATE work: each mismatch (aligned offset, reference base) and each clipped / inserted query
-//          range becomes an event in the read's slot list; deleted reference bases are added on the spot;
+//       2. CIGAR pre-scan and a loop over the record's MD tokens (the packer tokenises the MD text; v4 spent
+//          10 of its 57 warp-instructions per read scanning it byte by byte) with warp-uniform trip counts
+//          that only LOCATE work: each mismatch (aligned offset, reference base) and each clipped / inserted
+//          query range becomes an event in the read's slot list; deleted reference bases are added on the spot;
 //       3. the warp's events are compacted (warp scan) and resolved LANE-BALANCED -- lane i takes event
 //          i, whoever's read it belongs to: offset -> query/reference position through the CIGAR, read
 //          base, Phred, quality / SNP filter; results flow back to the owner through shared-memory
@@ -263,7 +264,7 @@ __device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const Tall
     const int pos = (int)h.x;
     const uint32_t l_seq = h.z & 0xffff, n_cigar = h.z >> 16;
     const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
-    const uint32_t *seqw = cig + n_cigar;
+    const uint32_t *seqw = cig + n_cigar + (h.w & 0xffff);      // MD tokens sit between the CIGAR and the sequence
     const uint8_t *seqb = reinterpret_cast<const uint8_t *>(seqw);
     int *acc = sm.acc + o_tid;
     if (pl & kEvRange) {
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             const uint8_t *slow_rec = oversized ? p.records + ((size_t)my_off << 4) : rec;
             int ca = 0, cc = 0, cg = 0, ct = 0;
             uint32_t status = 0;
-            int pos = 0, l_seq = 0, n_cigar = 0, md_len = 0;
+            int l_seq = 0, n_cigar = 0, n_tok = 0;
             bool good = inrange, slow = false;
             if (inrange) {
                 if (oversized || unit_bytes < 16) slow = true;
@@ -417,24 +418,24 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
                     if ((h.w >> 16) & DYN_REC_HAS_MATE) slow = true;
                     else {
-                        pos = (int)h.x;
-                        l_seq = h.z & 0xffff; n_cigar = h.z >> 16; md_len = h.w & 0xffff;
-                        if (record_need(l_seq, n_cigar, md_len) > unit_bytes) {   // truncated / corrupt record
-                            good = false; l_seq = n_cigar = md_len = 0;
+                        l_seq = h.z & 0xffff; n_cigar = h.z >> 16; n_tok = h.w & 0xffff;
+                        // truncated / corrupt record, or an MD tag that disagrees with the CIGAR
+                        if (record_need(l_seq, n_cigar, n_tok) > unit_bytes || ((h.w >> 16) & DYN_REC_BAD_MD)) {
+                            good = false; l_seq = n_cigar = n_tok = 0;
                         }
                     }
                 }
             }
             const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
-            const uint32_t *seqw = cig + n_cigar;
-            const uint8_t *md = reinterpret_cast<const uint8_t *>(seqw) + pad4(((size_t)l_seq + 1) >> 1) + l_seq;
+            const uint32_t *tok = cig + n_cigar;
+            const uint32_t *seqw = tok + n_tok;
             sm.recoff[tid] = (uint32_t)(my_off - off0) << 4;
             unsigned long long *myslot = sm.slot + tid;
             int n_ev = 0;
 
 #ifdef DYN_TALLY_DEBUG_SKIP
             if (DYN_TALLY_DEBUG_SKIP >= 2) { l_seq = 0; n_cigar = 0; }
-            md_len = 0;
+            n_tok = 0;
 #endif
             // ---- 1. whole-query base content
             count_query(seqw, l_seq, ca, cc, cg, ct);
@@ -459,32 +460,29 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                 if (q != l_seq) good = false;
             }
 
-            // ---- 3. MD scan: locate mismatch events (warp-uniform trip count)
+            // ---- 3. MD tokens: mismatches become events, deleted reference bases count toward the content
+            //         right away (bam.py:359-360); warp-uniform trip count
             {
-                const int my_len = good ? md_len : 0;
-                const int max_len = __reduce_max_sync(0xffffffffu, my_len);
-                int val = 0, aoff = 0, n_delb = 0;
-                bool in_del = false;
-                for (int j = 0; j < max_len; ++j) {
-                    if (j < my_len) {
-                        const uint32_t c = md[j];
-                        const uint32_t d = c - '0';
-                        if (d <= 9u) { val = val * 10 + (int)d; in_del = false; }
-                        else if (c == '^') { aoff += val; val = 0; in_del = true; }
-                        else {
-                            const uint32_t code = letter_code(c);
-                            if (in_del) {   // deleted reference base: counts toward content (bam.py:359-360)
-                                ca += (code == 1); cc += (code == 2); cg += (code == 4); ct += (code == 8);
-                                ++n_delb;
-                            } else {
-                                aoff += val; val = 0;
-                                if (n_ev < kEvSlots) myslot[n_ev * kThreads] = (unsigned long long)((uint32_t)aoff | (code << 16));
-                                ++n_ev; ++aoff;
-                            }
+                const int my_tok = good ? n_tok : 0;
+                const int max_tok = __reduce_max_sync(0xffffffffu, my_tok);
+                int n_delb = 0, last = -1;
+                for (int j = 0; j < max_tok; ++j) {
+                    if (j < my_tok) {
+                        const uint32_t tk = tok[j];
+                        const uint32_t code = DYN_TOK_BASE(tk);
+                        if (DYN_TOK_IS_DEL(tk)) {
+                            ca += (code == 1); cc += (code == 2); cg += (code == 4); ct += (code == 8);
+                            ++n_delb;
+                        } else {
+                            const int aoff = (int)DYN_TOK_AOFF(tk);
+                            if (aoff <= last || aoff >= m_total) good = false;   // tokens must ascend inside the aligned span
+                            last = aoff;
+                            if (n_ev < kEvSlots) myslot[n_ev * kThreads] = (unsigned long long)((uint32_t)aoff | (code << 16));
+                            ++n_ev;
                         }
                     }
                 }
-                if (good && (aoff + val != m_total || n_delb != d_total || m_total > 0xffff)) good = false;
+                if (n_delb != d_total) good = false;
             }
             if (inrange && !slow && !good) status |= DYN_ST_BAD_RECORD;
             if (good && n_ev > kEvSlots) slow = true;

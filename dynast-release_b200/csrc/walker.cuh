@@ -1,8 +1,8 @@
 // Sequential CIGAR/MD walker over one packed read record (include/dynast_b200.h), shared by the tally's
 // slow path (paired units, event overflow, oversized records) and the consensus expansion.
 // Restates pysam's get_aligned_pairs(with_seq=True) as used by dynast/preprocessing/bam.py:386-411 and
-// consensus.py:73-97: M/=/X pairs with the reference base taken from MD, deleted reference bases from
-// the ^XYZ runs, N skips advancing the reference only, I/S advancing the query only.
+// consensus.py:73-97: M/=/X pairs with the reference base taken from the record's MD tokens, deleted reference
+// bases from the deleted-base tokens, N skips advancing the reference only, I/S advancing the query only.
 #pragma once
 #include "common.cuh"
 
@@ -27,15 +27,15 @@ __device__ __forceinline__ int base_idx(uint32_t code) { return __popc(code) == 
 
 __device__ __forceinline__ size_t pad4(size_t x) { return (x + 3) & ~(size_t)3; }
 
-__device__ __forceinline__ size_t record_need(uint32_t l_seq, uint32_t n_cigar, uint32_t md_len) {
-    return 16 + 4 * (size_t)n_cigar + pad4(((size_t)l_seq + 1) >> 1) + l_seq + md_len;
+__device__ __forceinline__ size_t record_need(uint32_t l_seq, uint32_t n_cigar, uint32_t n_tok) {
+    return 16 + 4 * (size_t)n_cigar + 4 * (size_t)n_tok + pad4(((size_t)l_seq + 1) >> 1) + l_seq;
 }
 
 struct Walker {
-    const uint32_t *cig;
-    const uint8_t *seq, *qual, *md;
-    int n_cigar, l_seq, md_len, ref_id;
-    int ci, op_left, qpos, rpos, mdp, run;
+    const uint32_t *cig, *tok;
+    const uint8_t *seq, *qual;
+    int n_cigar, l_seq, n_tok, ref_id;
+    int ci, op_left, qpos, rpos, ti, aligned;
     int del[4];
     int del_left;      // deleted reference bases still to be reported (next_event only)
     bool bad;
@@ -46,46 +46,46 @@ struct Walker {
     // returns padded record size, 0 if the record does not fit `avail`
     __device__ size_t init(const uint8_t *rec, size_t avail) {
         bad = false;
-        ci = op_left = qpos = mdp = run = 0;
+        ci = op_left = qpos = ti = aligned = 0;
         del_left = 0;
         del[0] = del[1] = del[2] = del[3] = 0;
-        n_cigar = l_seq = md_len = 0;
+        n_cigar = l_seq = n_tok = 0;
         rpos = 0; ref_id = 0;
-        cig = nullptr; seq = qual = md = nullptr;
+        cig = tok = nullptr; seq = qual = nullptr;
         if (avail < 16) { bad = true; return 0; }
         const uint4 h = *reinterpret_cast<const uint4 *>(rec);
-        const uint32_t ls = h.z & 0xffff, nc = h.z >> 16, ml = h.w & 0xffff;
-        const size_t need = record_need(ls, nc, ml);
+        const uint32_t ls = h.z & 0xffff, nc = h.z >> 16, nt = h.w & 0xffff;
+        const size_t need = record_need(ls, nc, nt);
         if (need > avail) { bad = true; return 0; }
+        if ((h.w >> 16) & DYN_REC_BAD_MD) bad = true;     // MD disagrees with the CIGAR (pysam raises)
         rpos = (int)h.x; ref_id = (int)h.y;
-        l_seq = (int)ls; n_cigar = (int)nc; md_len = (int)ml;
+        l_seq = (int)ls; n_cigar = (int)nc; n_tok = (int)nt;
         cig = reinterpret_cast<const uint32_t *>(rec + 16);
-        seq = rec + 16 + 4 * (size_t)nc;
+        tok = cig + nc;
+        seq = reinterpret_cast<const uint8_t *>(tok + nt);
         qual = seq + pad4(((size_t)ls + 1) >> 1);
-        md = qual + ls;
         return (need + 15) & ~(size_t)15;
     }
-    __device__ bool md_digit() const { return mdp < md_len && (uint32_t)(md[mdp] - '0') <= 9u; }
-    __device__ void md_number() {
-        while (run == 0 && md_digit())
-            while (md_digit()) run = run * 10 + (int)(md[mdp++] - '0');
+    // one deleted-base token; false if the next token is not one
+    __device__ bool take_del(uint32_t &code) {
+        if (ti >= n_tok || !DYN_TOK_IS_DEL(tok[ti])) { bad = true; return false; }
+        code = DYN_TOK_BASE(tok[ti++]);
+        return true;
     }
     // advance to the next aligned (M/=/X) pair
     __device__ bool next() {
         for (;;) {
             if (bad) return false;
             if (op_left == 0) {
-                if (ci >= n_cigar) return false;
+                if (ci >= n_cigar) { if (ti != n_tok) bad = true; return false; }
                 const uint32_t c = cig[ci++];
                 const int op = (int)(c & 0xf), len = (int)(c >> 4);
                 if (op == 0 || op == 7 || op == 8) { op_left = len; continue; }
                 if (op == 2) {
-                    md_number();
-                    if (run != 0 || mdp >= md_len || md[mdp] != '^') { bad = true; return false; }
-                    ++mdp;
                     for (int j = 0; j < len; ++j) {
-                        if (mdp >= md_len) { bad = true; return false; }
-                        const int b = base_idx(letter_code(md[mdp++]));
+                        uint32_t code;
+                        if (!take_del(code)) return false;
+                        const int b = base_idx(code);
                         if (b >= 0) ++del[b];
                     }
                     rpos += len;
@@ -94,15 +94,11 @@ struct Walker {
                 continue;
             }
             if (qpos >= l_seq) { bad = true; return false; }
-            md_number();
             rn = (seq[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
-            if (run > 0) { gn = rn; --run; }
-            else {
-                if (mdp >= md_len || md[mdp] == '^') { bad = true; return false; }
-                gn = letter_code(md[mdp++]);
-            }
+            gn = rn;
+            if (ti < n_tok && !DYN_TOK_IS_DEL(tok[ti]) && (int)DYN_TOK_AOFF(tok[ti]) == aligned) gn = DYN_TOK_BASE(tok[ti++]);
             cq = qpos; cr = rpos; q = qual[qpos];
-            ++qpos; ++rpos; --op_left;
+            ++qpos; ++rpos; ++aligned; --op_left;
             return true;
         }
     }
@@ -114,23 +110,20 @@ struct Walker {
         for (;;) {
             if (bad) return 0;
             if (del_left > 0) {
-                if (mdp >= md_len) { bad = true; return 0; }
-                gn = letter_code(md[mdp++]);
+                uint32_t code;
+                if (!take_del(code)) return 0;
+                gn = code;
                 cr = rpos++;
                 --del_left;
                 return 2;
             }
             if (op_left == 0) {
-                if (ci >= n_cigar) return 0;
+                if (ci >= n_cigar) { if (ti != n_tok) bad = true; return 0; }
                 const uint32_t c = cig[ci++];
                 const int op = (int)(c & 0xf), len = (int)(c >> 4);
                 if (op == 0 || op == 7 || op == 8) op_left = len;
-                else if (op == 2) {
-                    md_number();
-                    if (run != 0 || mdp >= md_len || md[mdp] != '^') { bad = true; return 0; }
-                    ++mdp;
-                    del_left = len;
-                } else if (op == 3) rpos += len;
+                else if (op == 2) del_left = len;
+                else if (op == 3) rpos += len;
                 else if (op == 1 || op == 4) { qpos += len; if (qpos > l_seq) { bad = true; return 0; } }
                 continue;
             }
@@ -138,6 +131,5 @@ struct Walker {
         }
     }
 };
-
 
 }  // namespace

@@ -17,8 +17,8 @@ def mate_offsets(blob: np.ndarray, rec_off: np.ndarray) -> np.ndarray:
     """16-byte offset of the second record of every unit (equal to the next unit's offset when there is none)."""
     o = rec_off[:-1].astype(np.int64) * 16
     u16 = lambda at: blob[o + at].astype(np.int64) | (blob[o + at + 1].astype(np.int64) << 8)
-    l_seq, n_cigar, md_len = u16(8), u16(10), u16(12)
-    size = 16 + 4 * n_cigar + ((((l_seq + 1) // 2) + 3) & ~3) + l_seq + md_len
+    l_seq, n_cigar, n_tok = u16(8), u16(10), u16(12)
+    size = 16 + 4 * n_cigar + 4 * n_tok + ((((l_seq + 1) // 2) + 3) & ~3) + l_seq
     return ((o + ((size + 15) & ~15)) // 16).astype(np.int64)
 
 
@@ -74,7 +74,8 @@ def call_consensus_groups(
     gene_strand = np.array([gene_infos[g]['strand'] for g in g_gene], dtype=object) if n_groups else np.zeros(0, dtype=object)
     reverse = (gene_strand == '-') if strand != 'reverse' else (gene_strand == '+')
     return dict(
-        records=out['records'].cpu().numpy(), off=out['off'].cpu().numpy().view(np.uint32), nm=out['nm'].cpu().numpy(),
+        records=out['records'].cpu().numpy(), off=out['off'].cpu().numpy().view(np.uint32), md=out['md'].cpu().numpy(),
+        md_off=out['md_off'].cpu().numpy().view(np.uint32), nm=out['nm'].cpu().numpy(),
         status=out['status'].cpu().numpy(), gene=g_gene, barcode=np.asarray([u[1] for u in uniq], dtype=object)[multi],
         umi=np.asarray([u[2] for u in uniq], dtype=object)[multi], n_reads=members[multi],
         AS=np.bincount(ugid, weights=score[units], minlength=n_groups).astype(np.int64), reverse=reverse,

@@ -15,20 +15,91 @@ BASE_COLUMNS = ['A', 'C', 'G', 'T']
 COLUMNS = CONVERSION_COLUMNS + BASE_COLUMNS
 
 
+BAD_MD = 0x4000
+
+
+def tokenize_md(md: str, cigar: Sequence[Tuple[int, int]]):
+    """MD tag text -> (tokens, consistent): one uint32 per MD letter, in MD order -- aligned (M/=/X) offset in
+    bits 0..15, reference base (BAM 4-bit code) in bits 16..19, bit 20 for a deleted base (^XYZ run).
+    `consistent` is False when the tag disagrees with the CIGAR (matched + mismatched bases != M/=/X length or
+    deleted letters != D length); pysam raises on such records."""
+    toks = []
+    aoff = 0
+    val = 0
+    in_del = False
+    n_del = 0
+    ok = True
+    for ch in md:
+        if ch.isdigit():
+            val = val * 10 + int(ch)
+            in_del = False
+        elif ch == '^':
+            aoff += val
+            val = 0
+            in_del = True
+        else:
+            code = _CODE.get(ch, 0)
+            if in_del:
+                toks.append((min(aoff, 0xffff)) | (code << 16) | (1 << 20))
+                n_del += 1
+            else:
+                aoff += val
+                val = 0
+                if aoff > 0xffff:
+                    ok = False
+                toks.append((aoff & 0xffff) | (code << 16))
+                aoff += 1
+    aoff += val
+    m_total = sum(n for op, n in cigar if op in (0, 7, 8))
+    d_total = sum(n for op, n in cigar if op == 2)
+    if aoff != m_total or n_del != d_total:
+        ok = False
+    return toks, ok
+
+
 def pack_one(pos: int, ref_id: int, flag: int, cigar: Sequence[Tuple[int, int]], seq: str, qual: Sequence[int],
              md: str) -> bytes:
-    """One record: 16-byte header + cigar + 4-bit seq (padded to 4) + qual + MD, padded to 16 bytes."""
+    """One record: 16-byte header + cigar + MD tokens + 4-bit seq (padded to 4) + qual, padded to 16 bytes."""
     l_seq = len(seq)
-    hdr = np.zeros(1, dtype=[('pos', '<i4'), ('ref', '<i4'), ('l', '<u2'), ('nc', '<u2'), ('ml', '<u2'), ('fl', '<u2')])
-    mdb = md.encode()
-    hdr['pos'], hdr['ref'], hdr['l'], hdr['nc'], hdr['ml'], hdr['fl'] = pos, ref_id, l_seq, len(cigar), len(mdb), flag
+    toks, ok = tokenize_md(md, cigar)
+    if len(toks) > 0xffff:
+        toks, ok = [], False
+    hdr = np.zeros(1, dtype=[('pos', '<i4'), ('ref', '<i4'), ('l', '<u2'), ('nc', '<u2'), ('nt', '<u2'), ('fl', '<u2')])
+    hdr['pos'], hdr['ref'], hdr['l'], hdr['nc'], hdr['nt'] = pos, ref_id, l_seq, len(cigar), len(toks)
+    hdr['fl'] = flag | (0 if ok else BAD_MD)
     cig = np.array([(n << 4) | op for op, n in cigar], dtype='<u4').tobytes()
+    tok = np.array(toks, dtype='<u4').tobytes()
     nb = (l_seq + 1) // 2
     sb = bytearray((nb + 3) & ~3)
     for i, c in enumerate(seq):
         sb[i >> 1] |= _CODE[c] << (4 if (i & 1) == 0 else 0)
-    body = hdr.tobytes() + cig + bytes(sb) + np.asarray(qual, dtype=np.uint8).tobytes() + mdb
+    body = hdr.tobytes() + cig + tok + bytes(sb) + np.asarray(qual, dtype=np.uint8).tobytes()
     return body + b'\0' * (-len(body) % 16)
+
+
+def md_from_tokens(tokens: Sequence[int], cigar: Sequence[Tuple[int, int]]) -> str:
+    """Canonical MD text of a tokenised record (the inverse of tokenize_md for well-formed tags)."""
+    out = []
+    run_start = 0
+    i = 0
+    m_total = sum(n for op, n in cigar if op in (0, 7, 8))
+    prev_del = False
+    for t in tokens:
+        aoff, code, is_del = t & 0xffff, (t >> 16) & 15, (t >> 20) & 1
+        if is_del:
+            if not prev_del:
+                out.append(str(aoff - run_start))
+                out.append('^')
+                run_start = aoff
+            out.append(SEQ_CODES[code])
+            prev_del = True
+        else:
+            out.append(str(aoff - run_start))
+            out.append(SEQ_CODES[code])
+            run_start = aoff + 1
+            prev_del = False
+    out.append(str(m_total - run_start))
+    return ''.join(out)
 
 
 def pack_units(units: Iterable[List[bytes]]) -> Tuple[np.ndarray, np.ndarray]:

@@ -37,11 +37,17 @@ extern "C" {
  * Read i occupies bytes [16*rec_off[i], 16*rec_off[i+1]) of the record blob:
  *     dyn_read_hdr_t hdr;                      16 bytes
  *     uint32_t cigar[n_cigar];                 BAM encoding: len << 4 | op   (MIDNSHP=X -> 0..8)
+ *     uint32_t tok[n_tok];                     the MD tag, tokenised by the packer (text -> binary, nothing
+ *                                              resolved): one token per MD letter, in MD order --
+ *                                              bits 0..15 aligned (M/=/X) offset at which it occurs,
+ *                                              bits 16..19 reference base (BAM 4-bit code), bit 20 set for a
+ *                                              deleted reference base (a letter of a ^XYZ run)
  *     uint8_t  seq[(l_seq + 1) / 2];           BAM 4-bit codes "=ACMGRSVTWYHKDBN", high nibble first;
  *                                              zero-padded to a multiple of 4 bytes
  *     uint8_t  qual[l_seq];                    Phred
- *     uint8_t  md[md_len];                     MD tag text, no terminator
  *     zero padding to a multiple of 16 bytes
+ * The packer checks the MD tag against the CIGAR (matched + mismatched bases == M/=/X length, deleted
+ * letters == D length) and sets DYN_REC_BAD_MD otherwise (pysam raises on such a record).
  * If hdr.flag has DYN_REC_HAS_MATE, a second record (the first-seen mate of a read pair, same layout)
  * follows inside the same [rec_off[i], rec_off[i+1]) range; the pair is one counting unit
  * (bam.py:307-352) and dyn_tally_reads applies the overlap rules of bam.py:332-346, 393-419.
@@ -51,11 +57,15 @@ typedef struct {
     int32_t ref_id;   /* contig index in the BAM header */
     uint16_t l_seq;   /* query length including soft clips */
     uint16_t n_cigar;
-    uint16_t md_len;
+    uint16_t n_tok;   /* number of MD tokens */
     uint16_t flag;    /* BAM flag bits 0..11 | DYN_REC_* */
 } dyn_read_hdr_t;
 
 #define DYN_REC_HAS_MATE 0x8000u
+#define DYN_REC_BAD_MD 0x4000u
+#define DYN_TOK_AOFF(tok) ((uint32_t)(tok) & 0xffffu)
+#define DYN_TOK_BASE(tok) (((uint32_t)(tok) >> 16) & 0xfu)
+#define DYN_TOK_IS_DEL(tok) (((uint32_t)(tok) >> 20) & 1u)
 
 /* Conversion record codes: (ref nibble << 4) | read nibble, both BAM 4-bit codes (A=1,C=2,G=4,T=8).
  * One 64-bit record per mismatch: bits 0..31 genome_i (0-based), 32..39 code, 40..47 Phred,
@@ -259,14 +269,16 @@ int dyn_pi_fit(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n, const int
  * d_item_rec16[d_group_off[g] .. d_group_off[g+1]) (offsets into d_records in 16-byte units; the two mates of
  * a pair are two items); the grouping itself (consensus.py:338-430) is done by the caller.
  * Output: one packed record per group (same layout as the input records: pos = leftmost start, CIGAR with
- * M / D / N runs, 4-bit consensus sequence, qualities clipped to 42, MD text; flag 0) at
- * d_out_records + 16 * d_out_off[g]; NM in d_out_nm[g].  d_out_status[g]: 0 ok, 2 malformed member record,
+ * M / D / N runs, MD tokens, 4-bit consensus sequence, qualities clipped to 42; flag 0) at
+ * d_out_records + 16 * d_out_off[g]; the MD tag TEXT exactly as consensus.py:124-161, 175 builds it at
+ * d_out_md + d_out_md_off[g] (bytes, no terminator); NM in d_out_nm[g].  d_out_status[g]: 0 ok, 2 malformed member record,
  * 3 does not fit a BAM record, 4 members on several contigs (the reference raises), 5 output capacity.
  * The call synchronises the stream once (it sizes its tuple buffers from a device total).
  * ------------------------------------------------------------------------------------------------ */
 int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_item_rec16, const int64_t *d_group_off,
                   int64_t n_groups, int64_t n_items, int quality, void *d_out_records, int64_t out_capacity_bytes,
-                  uint32_t *d_out_off, uint32_t *d_out_nm, int32_t *d_out_status, void *stream);
+                  uint32_t *d_out_off, void *d_out_md, int64_t md_capacity_bytes, uint32_t *d_out_md_off,
+                  uint32_t *d_out_nm, int32_t *d_out_status, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a7: coverage of positions of interest and grouped key counts.

@@ -18,10 +18,11 @@
 typedef struct {
     int32_t pos;
     int32_t ref_id;
-    uint16_t l_seq, n_cigar, md_len, flag;
+    uint16_t l_seq, n_cigar, n_tok, flag;
 } hdr_t;
 
 #define HAS_MATE 0x8000u
+#define BAD_MD 0x4000u
 #define ST_OVERFLOW 0x1u
 #define ST_BAD 0x2u
 #define ST_NON_ACGT 0x4u
@@ -51,19 +52,23 @@ typedef struct {
 } resolved_t;
 
 static size_t record_bytes(const hdr_t *h) {
-    size_t b = 16 + 4 * (size_t)h->n_cigar + ((((size_t)h->l_seq + 1) / 2 + 3) & ~(size_t)3) + h->l_seq + h->md_len;
+    size_t b = 16 + 4 * (size_t)h->n_cigar + 4 * (size_t)h->n_tok + ((((size_t)h->l_seq + 1) / 2 + 3) & ~(size_t)3) + h->l_seq;
     return (b + 15) & ~(size_t)15;
 }
 
+/* Aligned pairs of one record.  The MD tag arrives tokenised by the packer (include/dynast_b200.h): one token
+ * per MD letter in MD order -- aligned offset, reference base, deleted-base flag.  An aligned base whose
+ * running aligned offset equals the next mismatch token's offset takes that token's reference base, every
+ * other aligned base matches; a D op consumes one deleted-base token per base. */
 static void resolve(const uint8_t *rec, resolved_t *r) {
     memcpy(&r->h, rec, 16);
     const hdr_t *h = &r->h;
     const uint32_t *cig = (const uint32_t *)(rec + 16);
-    const uint8_t *seq = rec + 16 + 4 * (size_t)h->n_cigar;
+    const uint32_t *tok = cig + h->n_cigar;
+    const uint8_t *seq = (const uint8_t *)(tok + h->n_tok);
     const uint8_t *qual = seq + ((((size_t)h->l_seq + 1) / 2 + 3) & ~(size_t)3);
-    const uint8_t *md = qual + h->l_seq;
     r->bytes = record_bytes(h);
-    size_t cap = (size_t)h->l_seq + 1, dcap = (size_t)h->md_len + 1;
+    size_t cap = (size_t)h->l_seq + 1, dcap = (size_t)h->n_tok + 1;
     r->qpos = (int *)malloc(sizeof(int) * cap);
     r->rpos = (int *)malloc(sizeof(int) * cap);
     r->refn = (uint8_t *)malloc(cap);
@@ -71,36 +76,28 @@ static void resolve(const uint8_t *rec, resolved_t *r) {
     r->q = (uint8_t *)malloc(cap);
     r->deln = (uint8_t *)malloc(dcap);
     r->n_pairs = r->n_del = 0;
-    r->bad = 0;
-    int qp = 0, rp = h->pos, mdp = 0, run = 0;
+    r->bad = (h->flag & BAD_MD) != 0;
+    int qp = 0, rp = h->pos, ti = 0, aligned = 0;
     for (int ci = 0; ci < h->n_cigar && !r->bad; ci++) {
         int op = cig[ci] & 0xf, len = (int)(cig[ci] >> 4);
         if (op == 0 || op == 7 || op == 8) {
             for (int j = 0; j < len; j++) {
                 if (qp >= h->l_seq) { r->bad = 1; break; }
-                while (run == 0 && mdp < h->md_len && md[mdp] >= '0' && md[mdp] <= '9') {
-                    while (mdp < h->md_len && md[mdp] >= '0' && md[mdp] <= '9') run = run * 10 + (md[mdp++] - '0');
-                    if (run == 0) continue;
-                }
                 int rn = (seq[qp >> 1] >> ((qp & 1) ? 0 : 4)) & 0xf;
-                int gn;
-                if (run > 0) { gn = rn; run--; }
-                else {
-                    if (mdp >= h->md_len || md[mdp] == '^') { r->bad = 1; break; }
-                    gn = letter_code(md[mdp++]);
+                int gn = rn;
+                if (ti < h->n_tok && !((tok[ti] >> 20) & 1) && (int)(tok[ti] & 0xffff) == aligned) {
+                    gn = (int)((tok[ti] >> 16) & 0xf);
+                    ti++;
                 }
                 int i = r->n_pairs++;
                 r->qpos[i] = qp; r->rpos[i] = rp; r->refn[i] = (uint8_t)gn; r->readn[i] = (uint8_t)rn; r->q[i] = qual[qp];
-                qp++; rp++;
+                qp++; rp++; aligned++;
             }
         } else if (op == 2) {
-            while (run == 0 && mdp < h->md_len && md[mdp] >= '0' && md[mdp] <= '9')
-                while (mdp < h->md_len && md[mdp] >= '0' && md[mdp] <= '9') run = run * 10 + (md[mdp++] - '0');
-            if (run != 0 || mdp >= h->md_len || md[mdp] != '^') { r->bad = 1; break; }
-            mdp++;
             for (int j = 0; j < len; j++) {
-                if (mdp >= h->md_len) { r->bad = 1; break; }
-                r->deln[r->n_del++] = (uint8_t)letter_code(md[mdp++]);
+                if (ti >= h->n_tok || !((tok[ti] >> 20) & 1)) { r->bad = 1; break; }
+                r->deln[r->n_del++] = (uint8_t)((tok[ti] >> 16) & 0xf);
+                ti++;
             }
             rp += len;
         } else if (op == 3) {
@@ -110,6 +107,7 @@ static void resolve(const uint8_t *rec, resolved_t *r) {
             if (qp > h->l_seq) r->bad = 1;
         }
     }
+    if (!r->bad && ti != h->n_tok) r->bad = 1;
 }
 
 static void resolved_free(resolved_t *r) {

@@ -109,16 +109,21 @@ def decode(out, g):
     o = int(out['off'][g]) * 16
     b = out['records'][o:int(out['off'][g + 1]) * 16].tobytes()
     pos, ref_id = np.frombuffer(b[:8], '<i4')
-    l_seq, n_cigar, md_len, flag = np.frombuffer(b[8:16], '<u2')
+    l_seq, n_cigar, n_tok, flag = (int(x) for x in np.frombuffer(b[8:16], '<u2'))
     cig = np.frombuffer(b[16:16 + 4 * n_cigar], '<u4')
-    p = 16 + 4 * n_cigar
-    nb = ((int(l_seq) + 1) // 2 + 3) & ~3
+    tok = np.frombuffer(b[16 + 4 * n_cigar:16 + 4 * n_cigar + 4 * n_tok], '<u4')
+    p = 16 + 4 * n_cigar + 4 * n_tok
+    nb = ((l_seq + 1) // 2 + 3) & ~3
     seqb = b[p:p + nb]
     seq = ''.join(rec.SEQ_CODES[(seqb[i >> 1] >> (4 if i % 2 == 0 else 0)) & 15] for i in range(l_seq))
     qual = list(b[p + nb:p + nb + l_seq])
-    md = b[p + nb + l_seq:p + nb + l_seq + md_len].decode()
-    return dict(start=int(pos), ref_id=int(ref_id), seq=seq, qual=qual, md=md, flag=int(flag),
-                cigar=[('MIDNSHP=X'[int(c) & 15], int(c) >> 4) for c in cig], nm=int(out['nm'][g]))
+    md = out['md'][int(out['md_off'][g]):int(out['md_off'][g + 1])].tobytes().decode()
+    cigar = [('MIDNSHP=X'[int(c) & 15], int(c) >> 4) for c in cig]
+    # the record's MD tokens say the same as its MD text (same letters at the same aligned offsets)
+    letters = [rec.SEQ_CODES[(int(t) >> 16) & 15] for t in tok]
+    assert letters == [c for c in md if c.isalpha()]
+    assert all(0 <= (int(t) & 0xffff) <= l_seq for t in tok)
+    return dict(start=int(pos), ref_id=int(ref_id), seq=seq, qual=qual, md=md, flag=int(flag), cigar=cigar, nm=int(out['nm'][g]))
 
 
 def check_groups(groups, quality=27):

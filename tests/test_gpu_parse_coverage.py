@@ -113,7 +113,7 @@ def test_consensus_groups_from_bam(gpu_ctx, tmp_path):
     multi = {k: v for k, v in groups.items() if len(v) >= 2}
     assert len(res['gene']) == len(multi) > 0
     assert (res['status'] == 0).all()
-    out = dict(records=res['records'], off=res['off'], nm=res['nm'])
+    out = dict(records=res['records'], off=res['off'], nm=res['nm'], md=res['md'], md_off=res['md_off'])
     for g in range(len(res['gene'])):
         members = multi[(res['gene'][g], res['barcode'][g], res['umi'][g])]
         want = call_consensus(members, quality=27)
