@@ -337,3 +337,72 @@ def consensus(ctx: Context, records: torch.Tensor, item_rec16: torch.Tensor, gro
                                 ptr(out), out_capacity_bytes, ptr(off), ptr(md), out_capacity_bytes, ptr(md_off), ptr(nm),
                                 ptr(status), _stream()))
     return dict(records=out, off=off, md=md, md_off=md_off, nm=nm[:G], status=status[:G])
+
+
+# --------------------------------------------------------------------------------------------------
+# The whole device-resident hot path for one read range: tally -> dedup -> p_e -> (k, n) histograms -> EM -> pi
+# --------------------------------------------------------------------------------------------------
+def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score, strand, n_barcodes: int, n_genes: int,
+                      out: TallyBuffers, conversions=('TC',), quality: int = 27, umi_bits: int = 24,
+                      cell_threshold: int = 1000, with_pi: bool = True, timings: Optional[dict] = None):
+    """Runs every stage of the path on device tensors (the packed records of one GPU's read range plus the
+    interned barcode / umi / gene ids of its reads).  Mirrors count() then estimate(method='alpha') of the
+    reference: count_conversions (count.py:306) -> estimate_p_e (estimate.py:197-234) -> aggregate_counts
+    (:243-255) -> estimate_p_c (:259-275) -> estimate_pi per barcode + estimate_alpha (:328-395).
+    Returns a dict of device tensors.  `timings`, if given, receives per-stage milliseconds (CUDA events)."""
+    dev = records.device
+    stream = torch.cuda.current_stream()
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            marks.append((name, e))
+
+    mark('start')
+    tally_reads(ctx, records, rec_off, out, quality=quality, emit_conv=True)
+    mark('tally')
+    gene_bits = _bits(max(n_genes - 1, 0))
+    bc_bits = _bits(max(n_barcodes - 1, 0))
+    key = (barcode.to(torch.int64) << (umi_bits + gene_bits)) | ((umi & ((1 << umi_bits) - 1)) << gene_bits) | gene.to(torch.int64)
+    n = barcode.numel()
+    transcriptome = torch.ones(n, dtype=torch.uint8, device=dev)
+    sel = dedup(ctx, key, out.counts, strand, transcriptome, score.to(torch.int16), out.conv_n, barcode, n_barcodes,
+                conversions=conversions, use_conversions=True, key_lo_bits=bc_bits + umi_bits + gene_bits)
+    mark('dedup')
+    pe_cols = [c for c in CONVERSION_COLUMNS if c[0] not in {x[0] for x in conversions}]
+    sums, n_reads, n_with = group_sums(ctx, out.counts, strand, barcode, n_barcodes, sel=sel, conversions=conversions)
+    rates, p_e = rates_pe(ctx, sums, pe_conversions=pe_cols)
+    mark('p_e')
+    rows = aggregate_kn(ctx, out.counts, strand, barcode, None, n_barcodes, 0, conversions, sel=sel, first_appearance=False)
+    k, nn, c, off, total = kn_csr(ctx, rows['keys'], rows['count32'], rows['n_rows'], n_barcodes)
+    mark('aggregate')
+    # estimate_p_c skips barcodes below the read threshold (p_c.py:215-217): give them an empty histogram
+    lens = off[1:] - off[:-1]
+    keep = total >= cell_threshold
+    off_kept = torch.zeros_like(off)
+    off_kept[1:] = torch.cumsum(torch.where(keep, lens, torch.zeros_like(lens)), 0)
+    row_keep = torch.repeat_interleave(keep, lens)
+    p_c, em_status, iters = em_pc(ctx, k[row_keep].contiguous(), nn[row_keep].contiguous(), c[row_keep].contiguous(), off_kept, p_e)
+    em_status = torch.where(keep, em_status, torch.full_like(em_status, -1))
+    mark('em')
+    res = dict(selected=sel, sums=sums, rates=rates, p_e=p_e, p_c=p_c, em_status=em_status, em_iters=iters, n_reads=n_reads,
+               n_with=n_with, hist=(k, nn, c, off))
+    if with_pi:
+        ok = em_status == 0
+        pc_safe = torch.where(ok, p_c, torch.full_like(p_c, 0.5))
+        pe_safe = torch.where(torch.isnan(p_e), torch.zeros_like(p_e), p_e)
+        off_pi = torch.zeros_like(off)
+        off_pi[1:] = torch.cumsum(torch.where(ok, lens, torch.zeros_like(lens)), 0)
+        row_ok = torch.repeat_interleave(ok, lens)
+        abp, pi_status = pi_fit(ctx, k[row_ok].contiguous(), nn[row_ok].contiguous(), c[row_ok].contiguous(), off_pi, pe_safe, pc_safe,
+                                max_cells=int(lens.max().item()) if lens.numel() else 1)
+        pi_c = torch.where(ok & (pi_status == 0), abp[:, 2], torch.full_like(p_c, float('nan')))
+        res.update(pi=abp, pi_status=pi_status, alpha=alpha(ctx, n_reads, n_with, pi_c))
+        mark('pi')
+    if timings is not None:
+        stream.synchronize()
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
+    return res
