@@ -351,10 +351,12 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
     auto prefetch_offsets = [&](long long tile) {
         if (tile >= p.n_tiles) return;
         const long long n0 = tile * kThreads, n1 = min(p.n_reads, n0 + (long long)kThreads);
-        pf_off0 = __ldg(p.rec_off + n0);
-        pf_off_end = __ldg(p.rec_off + n1);
-        const long long r = n0 + tid;
-        if (r < n1) { pf_my_off = __ldg(p.rec_off + r); pf_my_end = __ldg(p.rec_off + r + 1); }
+        // volatile asm: keep the loads HERE (the compiler otherwise sinks them to their first use, one tile later)
+        const long long r = min(n0 + tid, n1 - 1);
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(pf_off0) : "l"(p.rec_off + n0));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(pf_off_end) : "l"(p.rec_off + n1));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(pf_my_off) : "l"(p.rec_off + r));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(pf_my_end) : "l"(p.rec_off + r + 1));
     };
     prefetch_offsets(blockIdx.x);
 
