@@ -15,7 +15,7 @@
 //   * E step: unmasked cells never change, so columns are independent and run one per thread; each
 //     column's sums run in the reference's kp order;
 //   * M step: the two sequential float32 sums (row-major; cells that are zero for good are skipped,
-//     x + 0 == x exactly) run as two interleaved dependency chains on one lane.
+//     x + 0 == x exactly) run as two dependency chains on two lanes of one warp, over a packed (k, n) list.
 // The kernel is latency-bound on those serial chains, not HBM- or FP64-throughput-bound; parallelism
 // comes from many barcodes resident per SM.
 #include "common.cuh"
@@ -38,6 +38,7 @@ struct EmParams {
     const double *coef;   // [coef_K][coef_N]
     int coef_K, coef_N;
     int max_cells;        // dense capacity (cells) of the shared-memory layout
+    int cls_lo, cls_hi;   // this launch handles barcodes with cls_lo < K * N <= cls_hi (size classes, see dyn_em_pc)
     int max_K, max_N;     // pow-table capacities
     unsigned long long *work_counter;
 };
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
         __syncthreads();
         K = sh.K; N = sh.N;
         const int KN = K * N;
+        if (KN <= p.cls_lo || KN > p.cls_hi) continue;      // another launch's size class
         if (K == 0 || N == 0) {
             if (tid == 0) { p.p_c[b] = 0.0; p.status[b] = DYN_EM_PC_LE_PE; if (p.iters) p.iters[b] = 0; }
             continue;
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
         if (tid == 0) {
             int na = 0;
             for (int i = 0; i < KN; ++i)
-                if (cnt[i] != 0 || mask[i]) cnt[na++] = (uint32_t)i;   // in place: na <= i, cnt[i] already consumed
+                if (cnt[i] != 0 || mask[i]) cnt[na++] = ((uint32_t)(i / N) << 16) | (uint32_t)(i % N);   // in place: na <= i, cnt[i] already consumed
             sh.nact = na;
             int nc = 0;
             for (int n = 0; n < N; ++n)
@@ -276,39 +278,67 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                 }
             }
             __syncthreads();
-            // ---- M step
-            if (!NASC) {
-                // numba: (new_values * arange).sum() == float32 products, float32 sequential sum
-                if (tid == 0) {
+            // ---- M step: two sequential sums in the reference's cell order (row-major; cells that are zero for
+            //      good are skipped, x + 0 == x exactly).  The sums must stay sequential (float32, p_c.py:162-165:
+            //      reordering moves p_c by ~1e-6), but the loads and products need not: warp 0 takes 32 active cells
+            //      at a time, every lane loads and multiplies one cell, then the 32 products are folded into the
+            //      running sums in order through shuffles -- the dependency chain is one add per cell.
+            if (tid < 32) {
+                if (!NASC) {
+                    // numba: (new_values * arange).sum() == float32 products, float32 sequential sum
                     float sk = 0.0f, sn = 0.0f;
-                    for (int i = 0; i < nact; ++i) {
-                        const uint32_t cell = act[i];
-                        const float x = v[cell];
-                        sk = __fadd_rn(sk, __fmul_rn(x, (float)(cell / N)));
-                        sn = __fadd_rn(sn, __fmul_rn(x, (float)(cell % N)));
+                    for (int base = 0; base < nact; base += 32) {
+                        const int i = base + tid;
+                        float pk = 0.0f, pn = 0.0f;
+                        if (i < nact) {
+                            const uint32_t a = act[i];
+                            const uint32_t kk = a >> 16, nn = a & 0xffffu;
+                            const float x = v[kk * N + nn];
+                            pk = __fmul_rn(x, (float)kk);
+                            pn = __fmul_rn(x, (float)nn);
+                        }
+                        const int cnt32 = min(32, nact - base);
+#pragma unroll 8
+                        for (int j = 0; j < cnt32; ++j) {
+                            sk = __fadd_rn(sk, __shfl_sync(0xffffffffu, pk, j));
+                            sn = __fadd_rn(sn, __shfl_sync(0xffffffffu, pn, j));
+                        }
                     }
-                    const double prev = sh.p_c;
-                    const double nw = sn > 0.0f ? (double)__fdiv_rn(sk, sn) : prev;
-                    sh.prev = prev;
-                    sh.p_c = nw;
-                    if (prev == nw) sh.done = 1;
-                }
-            } else {
-                if (tid == 0) {
+                    if (tid == 0) {
+                        const double prev = sh.p_c;
+                        const double nw = sn > 0.0f ? (double)__fdiv_rn(sk, sn) : prev;
+                        sh.prev = prev;
+                        sh.p_c = nw;
+                        if (prev == nw) sh.done = 1;
+                    }
+                } else {
                     double sk = 0.0, sn = 0.0;
-                    for (int i = 0; i < nact; ++i) {
-                        const uint32_t cell = act[i];
-                        const double x = (double)v[cell];
-                        sk = __dadd_rn(sk, __dmul_rn((double)(cell / N), x));
-                        sn = __dadd_rn(sn, __dmul_rn((double)(cell % N), x));
+                    for (int base = 0; base < nact; base += 32) {
+                        const int i = base + tid;
+                        double pk = 0.0, pn = 0.0;
+                        if (i < nact) {
+                            const uint32_t a = act[i];
+                            const uint32_t kk = a >> 16, nn = a & 0xffffu;
+                            const double x = (double)v[kk * N + nn];
+                            pk = __dmul_rn((double)kk, x);
+                            pn = __dmul_rn((double)nn, x);
+                        }
+                        const int cnt32 = min(32, nact - base);
+#pragma unroll 8
+                        for (int j = 0; j < cnt32; ++j) {
+                            sk = __dadd_rn(sk, __shfl_sync(0xffffffffu, pk, j));
+                            sn = __dadd_rn(sn, __shfl_sync(0xffffffffu, pn, j));
+                        }
                     }
-                    const double prev = sh.p_c;
-                    const double nw = sn > 0.0 ? __ddiv_rn(sk, sn) : 0.0;
-                    sh.prev = prev;
-                    sh.p_c = nw;
-                    if (prev == nw) sh.done = 1;
-                    else if (nw < prev) sh.bis_r = prev;
-                    else sh.bis_l = prev;
+                    if (tid == 0) {
+                        const double prev = sh.p_c;
+                        const double nw = sn > 0.0 ? __ddiv_rn(sk, sn) : 0.0;
+                        sh.prev = prev;
+                        sh.p_c = nw;
+                        if (prev == nw) sh.done = 1;
+                        else if (nw < prev) sh.bis_r = prev;
+                        else sh.bis_l = prev;
+                    }
                 }
             }
             __syncthreads();
@@ -362,8 +392,7 @@ extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n,
 
     // shrink the dense capacity until the layout fits; barcodes beyond it report DYN_EM_UNSUPPORTED
     while (em_smem_bytes((int)max_cells, max_K, max_N) > ctx->smem_optin - 1024 && max_cells > 64) max_cells /= 2;
-    const size_t smem = em_smem_bytes((int)max_cells, max_K, max_N);
-    if (smem > ctx->smem_optin - 1024) {
+    if (em_smem_bytes((int)max_cells, max_K, max_N) > ctx->smem_optin - 1024) {
         dyn_set_error("dyn_em_pc: histogram shape %d x %d does not fit shared memory", max_K, max_N);
         return DYN_ERR_ARG;
     }
@@ -387,17 +416,30 @@ extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n,
     p.n_barcodes = n_barcodes;
     p.p_e = d_p_e; p.p_c = d_p_c; p.status = d_em_status; p.iters = d_iters;
     p.coef = ctx->em_coef; p.coef_K = ctx->em_coef_K; p.coef_N = ctx->em_coef_N;
-    p.max_cells = (int)max_cells; p.max_K = max_K; p.max_N = max_N;
-    p.work_counter = d_work;
+    p.max_K = max_K; p.max_N = max_N;
 
+    // The kernel is latency-bound per barcode (a few dependent fp64 / fp32 chains per iteration), so throughput
+    // comes from resident barcodes per SM, and those are limited by the dense shared-memory layout.  One rare
+    // large histogram (k = 30, n = 150 -> 4 681 cells, 45 KB) would size every CTA: barcodes are therefore run in
+    // two size classes, <= kSmallCells cells with a small layout (many CTAs per SM) and the rest with the full one.
+    const int kSmallCells = 1024;
+    const int n_classes = max_cells > kSmallCells ? 2 : 1;
     auto kern = nasc ? em_kernel<true> : em_kernel<false>;
-    DYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEmThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)ctx->sm_count * per_sm;
-    if (grid > n_barcodes) grid = n_barcodes;
-    kern<<<(unsigned)grid, kEmThreads, smem, stream>>>(p);
-    DYN_CUDA(cudaGetLastError());
+    for (int c = 0; c < n_classes; ++c) {
+        const int cap = (n_classes == 2 && c == 0) ? kSmallCells : (int)max_cells;
+        p.max_cells = cap;
+        p.cls_lo = (n_classes == 2 && c == 1) ? kSmallCells : -1;
+        p.cls_hi = (n_classes == 2 && c == 0) ? kSmallCells : 0x7fffffff;
+        p.work_counter = d_work + c;
+        const size_t smem = em_smem_bytes(cap, max_K, max_N);
+        DYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEmThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)ctx->sm_count * per_sm;
+        if (grid > n_barcodes) grid = n_barcodes;
+        kern<<<(unsigned)grid, kEmThreads, smem, stream>>>(p);
+        DYN_CUDA(cudaGetLastError());
+    }
     return DYN_OK;
 }
