@@ -295,9 +295,16 @@ def main():
     alg_bytes = alg_in + alg_out
     peak, peak_src = peaks()
     achieved = alg_bytes / (np.mean(kernel_ms) * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r1_tally_traffic.json')
+    if os.path.exists(tp):      # DRAM bytes per read from the committed ncu --set full capture, scaled to this launch
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj['bytes_per_read'] * n_reads, tj['source']
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'kernel': 'tally_kernel', 'peak_source': peak_src,
-                'algorithmic_bytes_per_read': alg_bytes / n_reads}
+                'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu DRAM bytes per read x reads in the launch)',
+                'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel': 'tally_kernel',
+                'peak_source': peak_src, 'algorithmic_bytes_per_read': alg_bytes / n_reads}
 
     # ---------------------------------------------------------------- e2e through the host-buffer C-ABI
     e2e = None

@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
     uint32_t *cnt = reinterpret_cast<uint32_t *>(v + p.max_cells);          // [max_cells]; later: active list
     double *powp = reinterpret_cast<double *>(cnt + p.max_cells);           // [max_K]
     double *powq = powp + p.max_K;                                          // [max_K + max_N]
-    int *cols = reinterpret_cast<int *>(powq + p.max_K + p.max_N);          // [max_N] columns with masked cells
+    double *den_n = powq + p.max_K + p.max_N;                               // [max_N] E-step denominators
+    int *cols = reinterpret_cast<int *>(den_n + p.max_N);                   // [max_N] columns with masked cells
     uint8_t *mask = reinterpret_cast<uint8_t *>(cols + p.max_N);            // [max_cells]
     __shared__ EmShared sh;
     __shared__ unsigned long long s_work;
@@ -241,27 +242,40 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                 if (!ok) sh.fail = DYN_EM_ZERODIV;
             }
             __syncthreads();
-            // ---- E step: one thread per column that owns masked cells
-            for (int ci = tid; ci < ncols; ci += kEmThreads) {
-                const int n = cols[ci];
-                const double *cf = p.coef + n;
-                if (!NASC) {
+            // ---- E step.  Unmasked cells never change, so (non-NASC) every masked cell can be updated
+            //      independently: first one thread per column for the denominators, then one thread per masked
+            //      cell for its numerator -- a column full of masked cells (k up to 30 at n = 150) no longer
+            //      serialises on one thread.  Each sum runs in the reference's kp order.
+            if (!NASC) {
+                for (int ci = tid; ci < ncols; ci += kEmThreads) {
+                    const int n = cols[ci];
+                    const double *cf = p.coef + n;
                     double den = 0.0;
                     for (int kp = 0; kp < K; ++kp)
                         if (!mask[kp * N + n])
                             den = __dadd_rn(den, __dmul_rn(__dmul_rn(cf[kp * p.coef_N], powp[kp]), powq[n - kp + K - 1]));
-                    if (den > 0.0) {
-                        for (int k = 0; k < K; ++k) {
-                            if (!mask[k * N + n]) continue;
-                            const double pk = __dmul_rn(__dmul_rn(cf[k * p.coef_N], powp[k]), powq[n - k + K - 1]);
-                            double num = 0.0;
-                            for (int kp = 0; kp < K; ++kp)
-                                if (!mask[kp * N + n]) num = __dadd_rn(num, __dmul_rn(pk, (double)v[kp * N + n]));
-                            v[k * N + n] = __double2float_rn(__ddiv_rn(num, den));
-                        }
-                    }
-                } else {
-                    // Gauss-Seidel within the column, sums over kp IN the mask (p_c.py:80-88, as written)
+                    den_n[n] = den;
+                }
+                __syncthreads();
+                for (int i = tid; i < nact; i += kEmThreads) {
+                    const uint32_t a = act[i];
+                    const int k = (int)(a >> 16), n = (int)(a & 0xffffu);
+                    if (!mask[k * N + n]) continue;
+                    const double den = den_n[n];
+                    if (!(den > 0.0)) continue;
+                    const double pk = __dmul_rn(__dmul_rn(p.coef[k * p.coef_N + n], powp[k]), powq[n - k + K - 1]);
+                    double num = 0.0;
+                    for (int kp = 0; kp < K; ++kp)
+                        if (!mask[kp * N + n]) num = __dadd_rn(num, __dmul_rn(pk, (double)v[kp * N + n]));
+                    v[k * N + n] = __double2float_rn(__ddiv_rn(num, den));
+                }
+            }
+            for (int ci = tid; NASC && ci < ncols; ci += kEmThreads) {
+                const int n = cols[ci];
+                const double *cf = p.coef + n;
+                {
+                    // Gauss-Seidel within the column, sums over kp IN the mask (p_c.py:80-88, as written):
+                    // a masked cell reads cells updated earlier in the same sweep, so the column stays serial
                     double den = 0.0;
                     for (int kp = 0; kp < K; ++kp)
                         if (mask[kp * N + n])
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
 static size_t em_smem_bytes(int max_cells, int max_K, int max_N) {
     size_t s = 0;
     s += sizeof(float) * max_cells + sizeof(uint32_t) * max_cells;   // v, cnt/active list
-    s += sizeof(double) * (max_K + max_K + max_N);
+    s += sizeof(double) * (max_K + max_K + max_N + max_N);
     s += sizeof(int) * max_N;
     s += max_cells;
     return (s + 15) & ~(size_t)15;
