@@ -384,7 +384,7 @@ extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n,
     DYN_ARG(ctx != nullptr, "null context");
     DYN_ARG(n_barcodes >= 0, "negative n_barcodes");
     if (n_barcodes == 0) return DYN_OK;
-    DYN_ARG(d_k && d_n && d_count && d_off && d_p_e && d_p_c && d_em_status, "null buffer");
+    DYN_ARG(d_off && d_p_e && d_p_c && d_em_status, "null buffer");   // triplet pointers may be NULL when every barcode is empty
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
     // shape discovery (one small kernel + a 12-byte read back: the only synchronisation of this call)

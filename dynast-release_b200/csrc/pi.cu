@@ -312,7 +312,7 @@ extern "C" int dyn_pi_fit(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n
     DYN_ARG(ctx != nullptr, "null context");
     DYN_ARG(n_groups >= 0, "negative n_groups");
     if (n_groups == 0) return DYN_OK;
-    DYN_ARG(d_k && d_n && d_count && d_off && d_p_e && d_p_c && d_alpha_beta_pi && d_status, "null buffer");
+    DYN_ARG(d_off && d_p_e && d_p_c && d_alpha_beta_pi && d_status, "null buffer");   // triplets may be NULL when all groups are empty
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PiParams p;
     int rc = pi_tables(ctx, stream, &p.gl_x, &p.gl_w, &p.log_beta_fn, &p.ts_s, &p.ts_c, &p.ts_w);
