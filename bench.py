@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-em', action='store_true')
     ap.add_argument('--skip-pipeline', action='store_true')
+    ap.add_argument('--skip-consensus', action='store_true')
+    ap.add_argument('--consensus-reads', type=int, default=20_000_000, help='C3-like reads per GPU for the consensus stage')
     ap.add_argument('--no-emit', action='store_true', help='diagnostic: counters only, no mismatch records')
     return ap.parse_args()
 
@@ -374,6 +376,40 @@ def main():
                 'note': 'includes the host round trips of the dedup split plan and the EM / pi shape discovery'}
         del res
 
+    # ---------------------------------------------------------------- UMI consensus (C3-like: 3.5 reads per UMI group)
+    cons = None
+    if not args.skip_consensus:
+        nc = args.consensus_reads
+        cb = pipeline.SynthBatch(nc, seed=2003 + rank, n_barcodes=2 * args.barcodes, reads_per_umi=3.5, device=local_rank, clustered=True)
+        key = (cb.barcode.to(torch.int64) << 39) | ((cb.umi & 0xffffff) << 15) | cb.gene.to(torch.int64)
+
+        def group_items():   # consensus.py:338-430: group by (gene, barcode, UMI); here a device sort of the interned key
+            skey, order = torch.sort(key, stable=True)
+            uk, counts = torch.unique_consecutive(skey, return_counts=True)
+            multi = counts >= 2
+            keep = torch.repeat_interleave(multi, counts)
+            goff = torch.zeros(int(multi.sum().item()) + 1, dtype=torch.int64, device=device)
+            goff[1:] = torch.cumsum(counts[multi], 0)
+            return (cb.rec_off[order[keep]]).contiguous(), goff
+
+        items, goff = group_items()
+        pipeline.consensus(ctx, cb.records, items, goff, quality=27)
+        barrier()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record(stream)
+        items, goff = group_items()
+        c1.record(stream)
+        cres = pipeline.consensus(ctx, cb.records, items, goff, quality=27)
+        c2.record(stream)
+        barrier()
+        ok = bool((cres['status'] == 0).all().item())
+        cons = {'metric': 'member reads/s, UMI consensus (expand, radix sort, per-position reduce, assemble)',
+                'value': world * int(items.numel()) / (c1.elapsed_time(c2) * 1e-3), 'unit': UNIT, 'ms_consensus': c1.elapsed_time(c2),
+                'ms_grouping': c0.elapsed_time(c1), 'reads': nc, 'member_reads': int(items.numel()), 'groups': int(goff.numel() - 1),
+                'all_status_ok': ok, 'workload': 'C3-like: 91-nt reads, 3.5 reads per (barcode, UMI, gene) group, starts within 300 nt'}
+        del cb, cres, items, goff, key
+        torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- p_c EM (C4), barcodes split over ranks
     em = None
     if not args.skip_em:
@@ -454,7 +490,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config, 'gpu_launches': args.steps,
-            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'em': em, 'pipeline': pipe, 'clocks': clocks,
+            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'em': em, 'pipeline': pipe, 'consensus': cons, 'clocks': clocks,
             'conversions_per_read': n_conv / n_reads,
         }
         print(json.dumps(line))

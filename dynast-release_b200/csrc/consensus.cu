@@ -30,7 +30,7 @@ namespace {
 constexpr int kBlock = 128;
 inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
-constexpr unsigned long long kInvalid = ~0ull;
+// sentinel of skipped bases: group field = n_groups (one past the last group), set per launch
 
 // tuple value: [0..7] Phred, [8..11] read base (BAM nibble), [12..15] reference base, [16] deletion
 __device__ __forceinline__ uint32_t pack_val(uint32_t q, uint32_t rn, uint32_t gn, uint32_t del) {
@@ -69,6 +69,7 @@ __global__ void size_kernel(const uint8_t *records, const uint32_t *item_rec16, 
 __global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
                               long long n_items, const unsigned long long *tuple_off, unsigned long long *key, uint32_t *val,
                               int32_t *status) {
+    const unsigned long long kInvalid = ((unsigned long long)n_groups << 32) | 0xffffffffull;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
@@ -94,10 +95,10 @@ __global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16
     for (; o < end; ++o) { key[o] = kInvalid; val[o] = 0; }
 }
 
-__global__ void head_kernel(const unsigned long long *key, long long n, uint32_t *flag) {
+__global__ void head_kernel(const unsigned long long *key, long long n, long long n_groups, uint32_t *flag) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    flag[i] = (key[i] != kInvalid && (i == 0 || key[i] != key[i - 1])) ? 1u : 0u;
+    flag[i] = ((long long)(key[i] >> 32) < n_groups && (i == 0 || key[i] != key[i - 1])) ? 1u : 0u;
 }
 
 // cell: [0..1] consensus base, [2..3] reference base, [4] deletion, [8..15] quality
@@ -342,9 +343,12 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
         cub::DoubleBuffer<unsigned long long> k(ka, kb);
         cub::DoubleBuffer<uint32_t> v(va, vb);
         t = sort_tmp;
-        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp1, t, k, v, (long long)n, 0, 64, stream));
+        // bits in use: 32 position bits + the group id; the sentinel key is (n_groups << 32 | ~0), one past the last group
+        int key_bits = 33;
+        while (key_bits < 64 && ((unsigned long long)n_groups >> (key_bits - 32))) ++key_bits;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp1, t, k, v, (long long)n, 0, key_bits, stream));
         DYN_CUDA(cudaMemsetAsync(flag + n, 0, 4, stream));
-        head_kernel<<<grid_for((long long)n), kBlock, 0, stream>>>(k.Current(), (long long)n, flag);
+        head_kernel<<<grid_for((long long)n), kBlock, 0, stream>>>(k.Current(), (long long)n, n_groups, flag);
         t = sort_tmp;
         DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp1, t, flag, idx, (long long)n + 1, stream));
         // cells overwrite the alternate buffers (n_cells <= n)

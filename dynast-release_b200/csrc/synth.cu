@@ -146,7 +146,10 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
     }
     if (out) {
         dyn_read_hdr_t h;
-        h.pos = (int32_t)(((unsigned long long)idx * (unsigned long long)P.pos_span) / 0x100000000ull);
+        // pos_span > 0: reads laid out in index order over the span (a coordinate-sorted BAM);
+        // pos_span < 0: the reads of a UMI group start within 300 nt of the group's anchor (config C3: consensus input)
+        if (P.pos_span > 0) h.pos = (int32_t)(((unsigned long long)idx * (unsigned long long)P.pos_span) / 0x100000000ull);
+        else h.pos = (int32_t)(mix64(grp ^ 0x5bd1e995ull) % (unsigned long long)(-P.pos_span)) + (int32_t)(g.next() % 300);
         h.ref_id = P.gene_contig[gene];
         h.l_seq = (uint16_t)L; h.n_cigar = (uint16_t)n_cig; h.n_tok = (uint16_t)n_tok;
         h.flag = (g.next() & 1) ? 16 : 0;
@@ -196,7 +199,7 @@ static int make_params(const dyn_synth_params_t *sp, SynthParams *P) {
     P->umi_len = sp->umi_len; P->n_groups = sp->n_groups; P->p_c = sp->p_c; P->p_e = sp->p_e; P->frac_n = sp->frac_n;
     P->bc_cdf = sp->d_bc_cdf; P->gene_cdf = sp->d_gene_cdf; P->gene_pi = sp->d_gene_pi;
     P->gene_strand = sp->d_gene_strand; P->gene_contig = sp->d_gene_contig;
-    P->pos_span = sp->pos_span > 0 ? sp->pos_span : (1ll << 27);
+    P->pos_span = sp->pos_span != 0 ? sp->pos_span : (1ll << 27);
     return DYN_OK;
 }
 

@@ -23,7 +23,7 @@ class SynthBatch:
     def __init__(self, n_reads: int, seed: int = 2001, read_len: int = 91, n_barcodes: int = 10000,
                  n_genes: int = 20000, n_contigs: int = 25, p_c: float = 0.05, p_e: float = 5e-4,
                  frac_n: float = 0.001, umi_len: int = 12, reads_per_umi: float = 2.0, device: int = 0,
-                 barcode_base: int = 0, with_keys: bool = True):
+                 barcode_base: int = 0, with_keys: bool = True, clustered: bool = False):
         self.ctx = Context.get(device)
         dev = torch.device('cuda', device)
         rng = np.random.default_rng(seed)
@@ -41,7 +41,7 @@ class SynthBatch:
         sp = SynthParams()
         sp.seed, sp.read_len, sp.n_barcodes, sp.n_genes, sp.umi_len = seed, read_len, n_barcodes, n_genes, umi_len
         sp.n_groups = max(1, int(n_reads / reads_per_umi))
-        sp.pos_span = 1 << 27
+        sp.pos_span = -(1 << 27) if clustered else 1 << 27
         sp.p_c, sp.p_e, sp.frac_n = p_c, p_e, frac_n
         sp.d_bc_cdf = self.tables['bc_cdf'].data_ptr()
         sp.d_gene_cdf = self.tables['gene_cdf'].data_ptr()

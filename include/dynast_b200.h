@@ -327,7 +327,8 @@ typedef struct {
     int32_t n_genes;
     int32_t umi_len;        /* nt, 2 bits each in the u64 UMI key */
     int64_t n_groups;       /* number of (barcode, gene, UMI) groups reads are drawn from */
-    int64_t pos_span;       /* reference span over which reads are laid out in order (0: 2^27) */
+    int64_t pos_span;       /* > 0: reference span over which reads are laid out in index order (0: 2^27);
+                             * < 0: reads of a UMI group start within 300 nt of an anchor in [0, -pos_span) */
     double p_c, p_e, frac_n;
     const float *d_bc_cdf;        /* [n_barcodes] cumulative sampling weights */
     const float *d_gene_cdf;      /* [n_genes] */
