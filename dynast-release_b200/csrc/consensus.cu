@@ -5,8 +5,8 @@
 // run in worker processes fed with SAM strings).
 //
 // On the device this is the sort / segmented-reduce the north star names:
-//   1. expand   one thread per member read walks CIGAR + MD (walker.cuh) and emits one tuple per aligned
-//               or deleted reference base: key = (group << 32 | reference position), value = (Phred, read
+//   1. expand   one warp per member read (lanes over the aligned offsets and the deleted-base tokens, coalesced
+//               writes) emits one tuple per aligned or deleted reference base: key = (group << 32 | reference position), value = (Phred, read
 //               base, reference base, deletion flag).  Bases the reference skips (reference N, read N,
 //               consensus.py:79-91) emit a sentinel key.  Per group min start / max end by atomics.
 //   2. sort     cub::DeviceRadixSort on the 64-bit keys (stable: within a position tuples stay in the
@@ -66,33 +66,100 @@ __global__ void size_kernel(const uint8_t *records, const uint32_t *item_rec16, 
     if (old != -1 && old != (int)h.y) status[g] = 4;   // reads on several contigs: the reference raises (consensus.py:57-58)
 }
 
+// One WARP per member read: lane l takes aligned offsets l, l + 32, ... (query / reference position through the
+// CIGAR, reference base = read base unless an MD mismatch token sits at that offset) and the read's deleted-base
+// tokens, so the 12-byte tuples of a read are written by consecutive lanes into consecutive slots
+// (slot = aligned offset for M/=/X bases, m_total + d for the d-th deleted base).
 __global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
                               long long n_items, const unsigned long long *tuple_off, unsigned long long *key, uint32_t *val,
                               int32_t *status) {
     const unsigned long long kInvalid = ((unsigned long long)n_groups << 32) | 0xffffffffull;
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= n_items) return;
     const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
-    const long long g = group_of(group_off, n_groups, i);
-    unsigned long long o = tuple_off[i];
-    const unsigned long long end = tuple_off[i + 1];
-    Walker w;
-    w.init(rec, (size_t)1 << 40);   // sizes were validated by the packer / the tally
-    int kind;
-    while (o < end && (kind = w.next_event()) != 0) {
-        const uint32_t gn = w.gn;
+    const unsigned long long g = (unsigned long long)group_of(group_off, n_groups, i);
+    const unsigned long long o0 = tuple_off[i], end = tuple_off[i + 1];
+    const uint4 h = *reinterpret_cast<const uint4 *>(rec);
+    const int pos = (int)h.x;
+    const uint32_t l_seq = h.z & 0xffff, n_cigar = h.z >> 16, n_tok = h.w & 0xffff;
+    const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
+    const uint32_t *tok = cig + n_cigar;
+    const uint8_t *seq = reinterpret_cast<const uint8_t *>(tok + n_tok);
+    const uint8_t *qual = seq + pad4(((size_t)l_seq + 1) >> 1);
+    uint32_t m_total = 0, d_total = 0;
+    for (uint32_t c = 0; c < n_cigar; ++c) {
+        const uint32_t op = cig[c] & 0xf, len = cig[c] >> 4;
+        if (op == 0 || op == 7 || op == 8) m_total += len;
+        else if (op == 2) d_total += len;
+    }
+    bool bad = ((h.w >> 16) & DYN_REC_BAD_MD) != 0 || (unsigned long long)(m_total + d_total) != end - o0;
+    if (bad) {
+        for (unsigned long long o = o0 + lane; o < end; o += 32) { key[o] = kInvalid; val[o] = 0; }
+        if (lane == 0) status[g] = 2;
+        return;
+    }
+    // aligned bases
+    for (uint32_t a = lane; a < m_total; a += 32) {
+        int q = 0, r = pos, done = 0, qpos = -1, rpos = 0;
+        for (uint32_t c = 0; c < n_cigar; ++c) {
+            const uint32_t w = cig[c];
+            const int op = (int)(w & 0xf), len = (int)(w >> 4);
+            if (op == 0 || op == 7 || op == 8) {
+                if ((int)a < done + len) { qpos = q + ((int)a - done); rpos = r + ((int)a - done); break; }
+                done += len; q += len; r += len;
+            } else if (op == 1 || op == 4) q += len;
+            else if (op == 2 || op == 3) r += len;
+        }
         unsigned long long k = kInvalid;
         uint32_t v = 0;
-        const int gi = base_idx(gn);
-        if (kind == 2) {
-            if (gi >= 0) { k = ((unsigned long long)g << 32) | (uint32_t)w.cr; v = pack_val(0, 0, gn, 1); }
-        } else if (gi >= 0 && base_idx(w.rn) >= 0) {
-            k = ((unsigned long long)g << 32) | (uint32_t)w.cr; v = pack_val(w.q, w.rn, gn, 0);
-        }
-        key[o] = k; val[o] = v; ++o;
+        if (qpos >= 0 && qpos < (int)l_seq) {
+            const uint32_t rn = (seq[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
+            uint32_t gn = rn;
+            for (uint32_t t = 0; t < n_tok; ++t) {
+                const uint32_t tk = tok[t];
+                if (!DYN_TOK_IS_DEL(tk) && DYN_TOK_AOFF(tk) == a) gn = DYN_TOK_BASE(tk);
+            }
+            if (base_idx(gn) >= 0 && base_idx(rn) >= 0) {      // reference N and read N are skipped (consensus.py:79-91)
+                k = (g << 32) | (uint32_t)rpos;
+                v = pack_val(qual[qpos], rn, gn, 0);
+            }
+        } else bad = true;
+        key[o0 + a] = k; val[o0 + a] = v;
     }
-    if (w.bad) status[g] = 2;
-    for (; o < end; ++o) { key[o] = kInvalid; val[o] = 0; }
+    // deleted reference bases: the d-th deleted-base token belongs to the d-th base of the CIGAR's D ops
+    uint32_t carry = 0;
+    for (uint32_t t0 = 0; t0 < n_tok; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const uint32_t tk = t < n_tok ? tok[t] : 0u;
+        const bool is_del = t < n_tok && DYN_TOK_IS_DEL(tk);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, is_del);
+        if (is_del) {
+            uint32_t d = carry + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+            unsigned long long k = kInvalid;
+            uint32_t v = 0;
+            if (d < d_total) {
+                int r = pos;
+                uint32_t left = d;
+                int rpos = -1;
+                for (uint32_t c = 0; c < n_cigar; ++c) {
+                    const uint32_t w = cig[c];
+                    const int op = (int)(w & 0xf), len = (int)(w >> 4);
+                    if (op == 2) { if (left < (uint32_t)len) { rpos = r + (int)left; break; } left -= (uint32_t)len; r += len; }
+                    else if (op == 0 || op == 3 || op == 7 || op == 8) r += len;
+                }
+                const uint32_t gn = DYN_TOK_BASE(tk);
+                if (rpos >= 0 && base_idx(gn) >= 0) { k = (g << 32) | (uint32_t)rpos; v = pack_val(0, 0, gn, 1); }
+                key[o0 + m_total + d] = k; val[o0 + m_total + d] = v;
+            } else bad = true;
+        }
+        carry += (uint32_t)__popc(ballot);
+    }
+    if (carry != d_total) {     // fewer deleted-base tokens than the CIGAR deletes: the unwritten slots must not be read
+        for (uint32_t d = carry + lane; d < d_total; d += 32) { key[o0 + m_total + d] = kInvalid; val[o0 + m_total + d] = 0; }
+        bad = true;
+    }
+    if (bad) status[g] = 2;
 }
 
 __global__ void head_kernel(const unsigned long long *key, long long n, long long n_groups, uint32_t *flag) {
@@ -338,8 +405,8 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
                 a1 = Arena(base);
             }
         }
-        expand_kernel<<<grid_for(n_items), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_off, ka,
-                                                                va, d_out_status);
+        expand_kernel<<<grid_for(n_items * 32), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_off, ka,
+                                                                     va, d_out_status);
         cub::DoubleBuffer<unsigned long long> k(ka, kb);
         cub::DoubleBuffer<uint32_t> v(va, vb);
         t = sort_tmp;
