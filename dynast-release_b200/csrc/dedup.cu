@@ -12,8 +12,9 @@
 //     complemented counts, drop_duplicates((barcode, umi, GX), keep='last')   conversion.py:225-243
 //     -> winner of a UMI group = max priority, ties -> last in split-file order; survivors keep sorted order
 //   * per split: forward-strand rows, then reverse-strand rows                conversion.py:602-606
-// On the device that is four stable LSD radix sorts (cub::DeviceRadixSort, keys restricted to the bits in
-// use) and one stream compaction; the result is the list of surviving read indices in output order.
+// On the device that is three stable LSD radix sorts (cub::DeviceRadixSort, keys restricted to the bits in
+// use: [priority | barcode order | strand | no-mismatch], the group key, [split | strand | extra]) and one
+// stream compaction; the result is the list of surviving read indices in output order.
 // HBM-bound: ~20 B/read algorithmic (16 B key + priority in, 4 B index out); the sorts move more.
 #include <cub/cub.cuh>
 
@@ -61,28 +62,24 @@ struct DedupIn {
     int use_conversions;
 };
 
-__global__ void order_key_kernel(DedupIn in, uint32_t *key, uint32_t *val) {
+// dedup sort key of read i in ONE word: [priority:30][barcode order][strand][no-mismatch]; a stable sort of the
+// reads (in BAM order) by it == split-file order refined by the stable priority sort of conversion.py:238
+__global__ void sort_key_kernel(DedupIn in, int low_bits, unsigned long long *key, uint32_t *val) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= in.n) return;
-    const uint32_t ord = in.ord_of_barcode ? in.ord_of_barcode[in.barcode[i]] : 0u;
-    key[i] = (ord << 2) | ((uint32_t)(in.strand[i] != 0) << 1) | (uint32_t)(in.conv_n[i] == 0);
-    val[i] = (uint32_t)i;
-}
-
-// priority of read r: [has_conversions][transcriptome][score:16][conversion_sum:12], on complemented counts
-__global__ void prio_key_kernel(DedupIn in, const uint32_t *order, uint32_t *key) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= in.n) return;
-    const uint32_t r = order[i];
-    uint4 c = in.counts[r];
-    if (in.strand[r]) c = complement_row(c);
+    uint4 c = in.counts[i];
+    if (in.strand[i]) c = complement_row(c);
     const uint32_t w[3] = {c.x, c.y, c.z};
     uint32_t sum = 0;
 #pragma unroll
     for (int j = 0; j < 12; ++j)
         if ((in.conv_mask >> j) & 1u) sum += (w[j >> 2] >> ((j & 3) << 3)) & 0xffu;
-    const uint32_t has = (in.use_conversions && sum > 0) ? 1u : 0u;
-    key[i] = (has << 29) | ((uint32_t)(in.transcriptome[r] != 0) << 28) | ((uint32_t)in.score[r] << 12) | (sum & 0xfffu);
+    const unsigned long long has = (in.use_conversions && sum > 0) ? 1u : 0u;
+    const unsigned long long prio = (has << 29) | ((unsigned long long)(in.transcriptome[i] != 0) << 28) |
+                                    ((unsigned long long)in.score[i] << 12) | (sum & 0xfffu);
+    const unsigned long long ord = in.ord_of_barcode ? in.ord_of_barcode[in.barcode[i]] : 0u;
+    key[i] = (prio << low_bits) | (ord << 2) | ((unsigned long long)(in.strand[i] != 0) << 1) | (unsigned long long)(in.conv_n[i] == 0);
+    val[i] = (uint32_t)i;
 }
 
 __global__ void gather_u64_kernel(const unsigned long long *src, const uint32_t *idx, unsigned long long *dst, long long n) {
@@ -195,13 +192,12 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
                                    (long long *)nullptr, n_reads, stream);
         if (t > tmp_bytes) tmp_bytes = t;
     }
-    uint32_t *k32a, *k32b, *v32a, *v32b, *order;
+    uint32_t *v32a, *v32b, *order;
     unsigned long long *k64a, *k64b, *hi_sorted;
     uint8_t *win, *flag;
     void *tmp;
     Arena ar;
     for (int pass = 0; pass < 2; ++pass) {
-        k32a = ar.take<uint32_t>(n); k32b = ar.take<uint32_t>(n);
         v32a = ar.take<uint32_t>(n); v32b = ar.take<uint32_t>(n);
         order = ar.take<uint32_t>(n);
         k64a = ar.take<unsigned long long>(n); k64b = ar.take<unsigned long long>(n);
@@ -223,21 +219,15 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
     in.n = n_reads; in.conv_mask = conv_mask & 0xfffu; in.use_conversions = use_conversions;
     const unsigned g = grid_for(n_reads);
 
-    // 1. split-file order: stable sort of BAM order by (barcode order, strand, no-mismatch)
-    order_key_kernel<<<g, kBlock, 0, stream>>>(in, k32a, v32a);
+    // 1 + 2. dedup sort: one stable sort of the reads (BAM order) by [priority | barcode order | strand | no-mismatch]
+    //        -> `order` = read indices, ascending (priority, split-file order)
     {
-        cub::DoubleBuffer<uint32_t> k(k32a, k32b), v(v32a, v32b);
-        const int bits = (d_ord_of_barcode ? bits_for((uint64_t)(n_barcodes > 0 ? n_barcodes - 1 : 0)) : 0) + 2;
+        const int low_bits = (d_ord_of_barcode ? bits_for((uint64_t)(n_barcodes > 0 ? n_barcodes - 1 : 0)) : 0) + 2;
+        sort_key_kernel<<<g, kBlock, 0, stream>>>(in, low_bits, k64a, v32a);
+        cub::DoubleBuffer<unsigned long long> k(k64a, k64b);
+        cub::DoubleBuffer<uint32_t> v(v32a, v32b);
         t = tmp_bytes;
-        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, bits, stream));
-        if (v.Current() != v32a) DYN_CUDA(cudaMemcpyAsync(v32a, v.Current(), 4 * n, cudaMemcpyDeviceToDevice, stream));
-    }
-    // 2. dedup sort: stable by priority (30 bits) -> `order` = read indices, ascending (priority, split-file order)
-    prio_key_kernel<<<g, kBlock, 0, stream>>>(in, v32a, k32a);
-    {
-        cub::DoubleBuffer<uint32_t> k(k32a, k32b), v(v32a, v32b);
-        t = tmp_bytes;
-        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, 30, stream));
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, low_bits + 30, stream));
         DYN_CUDA(cudaMemcpyAsync(order, v.Current(), 4 * n, cudaMemcpyDeviceToDevice, stream));
     }
     // 3. group by (barcode, umi, gene) key, stable: the last element of a run is the group's winner
