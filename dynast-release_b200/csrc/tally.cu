@@ -29,10 +29,14 @@
 //   * mismatch records are placed with one global atomic per CTA tile (block scan of per-read counts)
 //     and copied out of the slots -- the MD string is parsed once;
 //   * paired units (bam.py:307-352, 393-419), reads with more events than slots and records larger
-//     than the staging buffer take a sequential per-thread walker (slow_unit) -- same results, no
-//     attempt at convergence; the single-end fast path is what the bench times.
+//     than the staging buffer are parked on a list and taken by a second kernel with a sequential
+//     per-thread walker (tally_slow_kernel / slow_unit) -- same results, no attempt at convergence.  Keeping
+//     the walker out of the tile kernel takes it from 128 to ~90 registers (11 CTAs per SM instead of 8);
+//     the single-end fast path is what the bench times.
 #include "common.cuh"
 #include "walker.cuh"
+
+#include <algorithm>
 
 namespace {
 
@@ -43,7 +47,10 @@ namespace {
 #define DYN_TALLY_SLOTS 8
 #endif
 #ifndef DYN_TALLY_MIN_CTAS
-#define DYN_TALLY_MIN_CTAS 8
+#define DYN_TALLY_MIN_CTAS 12
+#endif
+#ifndef DYN_TALLY_SLACK
+#define DYN_TALLY_SLACK 256          // staging bytes beyond kThreads mean-sized records
 #endif
 constexpr int kThreads = DYN_TALLY_THREADS;
 constexpr int kWarps = kThreads / 32;
@@ -68,6 +75,8 @@ struct TallyParams {
     uint32_t *status;
     uint32_t stage_bytes;
     long long n_tiles;
+    uint32_t *slow_list;     // read indices left to tally_slow_kernel (paired units, event overflow, oversized records)
+    uint32_t *n_slow;
 };
 
 __device__ __forceinline__ bool snp_lookup(const unsigned long long *snps, long long n, unsigned long long key) {
@@ -80,47 +89,59 @@ __device__ __forceinline__ bool snp_lookup(const unsigned long long *snps, long 
     return lo < n && __ldg(snps + lo) == key;
 }
 
-__device__ __forceinline__ uint32_t fold_nibbles(uint32_t acc) {
-    acc = (acc & 0x0f0f0f0fu) + ((acc >> 4) & 0x0f0f0f0fu);
-    return (acc * 0x01010101u) >> 24;
-}
-
 // column of conversion ref -> read in conversion.py:44-57 (alphabetical AC AG AT CA ...)
 __device__ __forceinline__ int conv_idx(int r, int d) { return r * 3 + (d > r ? d - 1 : d); }
 
-// A/C/G/T over the whole query: fixed-trip, no masks (the packer zero-pads, code 0 is not a base).
+// Base counting by byte permute: PRMT's selector nibbles ARE the 4-bit base codes.  Selector value v picks table
+// byte v & 7 and, when bit 3 is set, replicates that byte's sign bit instead (PTX prmt.b32, generic mode), so with
+//   table AC: byte 1 = 0x01 (A = 1), byte 2 = 0x10 (C = 2), rest 0      -> every other code, 9..15 included, gives 0
+//   table GT: byte 4 = 0x01 (G = 4), byte 0 = 0x80 (T = 8 -> 0xff, '=' = 0 -> 0x80; & 0x11 leaves T = 0x11, '=' = 0)
+// four bases are classified per instruction, exactly, for all 16 codes; per byte lane the low nibble counts A
+// (resp. G + T) and the high nibble C (resp. T).  Nibble fields hold 15: fold after at most 7 words (14 adds).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+constexpr uint32_t kLutAC = 0x00100100u, kLutT = 0x00000080u, kLutG = 0x00000001u;
+
+__device__ __forceinline__ void fold_fields(uint32_t acc_ac, uint32_t acc_gt, int &ca, int &cc, int &cg, int &ct) {
+    const uint32_t a = ((acc_ac & 0x0f0f0f0fu) * 0x01010101u) >> 24, c = (((acc_ac >> 4) & 0x0f0f0f0fu) * 0x01010101u) >> 24;
+    const uint32_t gt = ((acc_gt & 0x0f0f0f0fu) * 0x01010101u) >> 24, t = (((acc_gt >> 4) & 0x0f0f0f0fu) * 0x01010101u) >> 24;
+    ca += (int)a; cc += (int)c; cg += (int)(gt - t); ct += (int)t;
+}
+
+// A/C/G/T over the whole query: no masks (the packer zero-pads, code 0 is not a base).
 __device__ __forceinline__ void count_query(const uint32_t *seqw, int l_seq, int &ca, int &cc, int &cg, int &ct) {
     const int n_words = (l_seq + 7) >> 3;
-    for (int w0 = 0; w0 < n_words; w0 += 15) {
-        uint32_t aa = 0, ac = 0, ag = 0, at = 0;
-        const int w1 = min(n_words, w0 + 15);
-#pragma unroll 4
+    for (int w0 = 0; w0 < n_words; w0 += 7) {
+        uint32_t acc_ac = 0, acc_gt = 0;
+        const int w1 = min(n_words, w0 + 7);
+#pragma unroll 7
         for (int w = w0; w < w1; ++w) {
-            const uint32_t x = seqw[w];
-            const uint32_t b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u,
-                           b3 = (x >> 3) & 0x11111111u;
-            const uint32_t s = b0 + b1 + b2 + b3;
-            const uint32_t onehot = s & ~(s >> 1) & ~(s >> 2);
-            aa += b0 & onehot; ac += b1 & onehot; ag += b2 & onehot; at += b3 & onehot;
+            const uint32_t x = seqw[w], xh = x >> 16;
+            acc_ac += prmt(kLutAC, 0u, x) + prmt(kLutAC, 0u, xh);
+            acc_gt += (prmt(kLutT, kLutG, x) & 0x11111111u) + (prmt(kLutT, kLutG, xh) & 0x11111111u);
         }
-        ca += (int)fold_nibbles(aa); cc += (int)fold_nibbles(ac);
-        cg += (int)fold_nibbles(ag); ct += (int)fold_nibbles(at);
+        fold_fields(acc_ac, acc_gt, ca, cc, cg, ct);
     }
 }
 
 // A/C/G/T of query range [a, b) (soft clips, insertions).
 __device__ __forceinline__ void count_range(const uint32_t *seqw, int a, int b, int &ca, int &cc, int &cg, int &ct) {
-    for (int w = a >> 3; w <= (b - 1) >> 3; ++w) {
-        uint32_t x = seqw[w];
-        x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);   // base i at bits 4*(i&7)
-        const int lo = max(a - (w << 3), 0), hi = min(b - (w << 3), 8);
-        const uint32_t mask = (hi == 8 ? 0xffffffffu : ((1u << (4 * hi)) - 1u)) & ~((1u << (4 * lo)) - 1u);
-        const uint32_t b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u,
-                       b3 = (x >> 3) & 0x11111111u;
-        const uint32_t s = b0 + b1 + b2 + b3;
-        const uint32_t onehot = s & ~(s >> 1) & ~(s >> 2) & mask;
-        ca += __popc(b0 & onehot); cc += __popc(b1 & onehot);
-        cg += __popc(b2 & onehot); ct += __popc(b3 & onehot);
+    for (int w0 = a >> 3; w0 <= (b - 1) >> 3; w0 += 7) {
+        uint32_t acc_ac = 0, acc_gt = 0;
+        const int w1 = min(((b - 1) >> 3) + 1, w0 + 7);
+        for (int w = w0; w < w1; ++w) {
+            // base i of the word sits at bits 4 * (i ^ 1): build the mask for bases [lo, hi) and swap its nibbles
+            const int lo = max(a - (w << 3), 0), hi = min(b - (w << 3), 8);
+            uint32_t mask = (hi == 8 ? 0xffffffffu : ((1u << (4 * hi)) - 1u)) & ~((1u << (4 * lo)) - 1u);
+            mask = ((mask & 0x0f0f0f0fu) << 4) | ((mask >> 4) & 0x0f0f0f0fu);
+            const uint32_t x = seqw[w] & mask, xh = x >> 16;
+            acc_ac += prmt(kLutAC, 0u, x) + prmt(kLutAC, 0u, xh);
+            acc_gt += (prmt(kLutT, kLutG, x) & 0x11111111u) + (prmt(kLutT, kLutG, xh) & 0x11111111u);
+        }
+        fold_fields(acc_ac, acc_gt, ca, cc, cg, ct);
     }
 }
 
@@ -253,10 +274,27 @@ struct TileSmem {
     int *acc;                   // [7][kThreads]: a c g t w0 w1 w2
     uint32_t *recoff;           // [kThreads] byte offset of the record inside `stage`
     uint8_t *list;              // [kWarps][32 * kEvSlots]: lane | slot << 5
+    uint32_t *wmask;            // [kWarps][kEvSlots + 1] ballot of "event e left a mismatch record", per chunk of 32 events
+    uint32_t *wpre;             // [kWarps][kEvSlots + 1] records in the chunks before
 };
 
-__device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const TallyParams &p, int o_tid, int s) {
+// one read's 16 output bytes (conversion.py:46-57 column order), saturating at 255
+__device__ __forceinline__ void store_counts(const TallyParams &p, long long r, int ca, int cc, int cg, int ct, uint32_t w0,
+                                             uint32_t w1, uint32_t w2, uint32_t &status) {
+    uint32_t a = (uint32_t)max(ca, 0), c = (uint32_t)max(cc, 0), g = (uint32_t)max(cg, 0), t = (uint32_t)max(ct, 0);
+    if ((a | c | g | t) > 255u) {
+        status |= DYN_ST_COUNTER_OVERFLOW;
+        a = min(a, 255u); c = min(c, 255u); g = min(g, 255u); t = min(t, 255u);
+    }
+    uint4 o;
+    o.x = w0; o.y = w1; o.z = w2;
+    o.w = a | (c << 8) | (g << 16) | (t << 24);
+    reinterpret_cast<uint4 *>(p.counts)[r] = o;
+}
+
+__device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const TallyParams &p, int o_tid, int s, bool &is_rec) {
     uint32_t status = 0;
+    is_rec = false;
     unsigned long long *slot = sm.slot + s * kThreads + o_tid;
     const unsigned long long pl = *slot;
     const uint8_t *rec = sm.stage + sm.recoff[o_tid];
@@ -307,6 +345,7 @@ __device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const Tall
     const uint8_t *qual = seqb + pad4(((size_t)l_seq + 1) >> 1);
     const uint32_t q = qual[qpos];
     *slot = (unsigned long long)(uint32_t)rpos | ((unsigned long long)((gn << 4) | rn) << 32) | ((unsigned long long)q << 40);
+    is_rec = true;
     if ((int)q <= p.quality) return 0;                                // conversion.py:424 (strict)
     if (gi < 0 || ri < 0) return DYN_ST_NON_ACGT_CONV;
     const int idx = conv_idx(gi, ri);
@@ -331,10 +370,13 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm.list + kThreads * kEvSlots);       // 16 B
     uint32_t *warp_sums = reinterpret_cast<uint32_t *>(bar + 2);                       // [kWarps + 4]
     uint32_t *s_sub = warp_sums + kWarps + 4;                                          // sub-tile broadcast
+    sm.wmask = s_sub + 4;                                                              // [kWarps][kEvSlots + 1]
+    sm.wpre = sm.wmask + kWarps * (kEvSlots + 1);                                      // [kWarps][kEvSlots + 1]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
     uint8_t *wlist = sm.list + wid * 32 * kEvSlots;
+    uint32_t *wmask = sm.wmask + wid * (kEvSlots + 1), *wpre = sm.wpre + wid * (kEvSlots + 1);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -409,7 +451,6 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             // ---- header
             // a record larger than the staging buffer is walked straight from global memory
             const uint8_t *rec = sm.stage + ((size_t)(my_off - off0) << 4);
-            const uint8_t *slow_rec = oversized ? p.records + ((size_t)my_off << 4) : rec;
             int ca = 0, cc = 0, cg = 0, ct = 0;
             uint32_t status = 0;
             int l_seq = 0, n_cigar = 0, n_tok = 0;
@@ -461,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                 }
                 if (q != l_seq) good = false;
             }
+            const int n_rng = n_ev;     // slots [0, n_rng) hold query ranges, the rest mismatches
 
             // ---- 3. MD tokens: mismatches become events, deleted reference bases count toward the content
             //         right away (bam.py:359-360); warp-uniform trip count
@@ -489,73 +531,80 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             if (inrange && !slow && !good) status |= DYN_ST_BAD_RECORD;
             if (good && n_ev > kEvSlots) slow = true;
 
-            // ---- 4. compact the warp's events, resolve them lane-balanced
+            // ---- 4. compact the warp's events, resolve them lane-balanced.  Every chunk of 32 events leaves a
+            //         ballot of "this event is a mismatch record": per-read record counts and output positions
+            //         are popcounts over those ballots (no per-read loops over the slots).
             const int n_slot = (good && !slow) ? n_ev : 0;
             sm.acc[0 * kThreads + tid] = ca; sm.acc[1 * kThreads + tid] = cc;
             sm.acc[2 * kThreads + tid] = cg; sm.acc[3 * kThreads + tid] = ct;
             sm.acc[4 * kThreads + tid] = 0; sm.acc[5 * kThreads + tid] = 0; sm.acc[6 * kThreads + tid] = 0;
-            {
-                int incl = n_slot;
+            // the warp's list holds all query ranges first, then the mismatches (lanes of a chunk take the same
+            // path); one scan carries both counts: ranges in the low half, mismatches in the high half
+            const int n_rs = n_slot ? n_rng : 0;
+            uint32_t incl = (uint32_t)n_rs | ((uint32_t)(n_slot - n_rs) << 16);
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                const int n_events = __shfl_sync(0xffffffffu, incl, 31);
-                const int first = incl - n_slot;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int n_ranges = (int)(tot & 0xffffu), n_events = n_ranges + (int)(tot >> 16);
+            const int first_rng = (int)(incl & 0xffffu) - n_rs;
+            const int first = n_ranges + (int)(incl >> 16) - (n_slot - n_rs);     // first mismatch event of this read
+            uint32_t warp_recs = 0;
+            {
                 const int max_slot = __reduce_max_sync(0xffffffffu, n_slot);
                 for (int s = 0; s < max_slot; ++s)
-                    if (s < n_slot) wlist[first + s] = (uint8_t)(lane | (s << 5));
+                    if (s < n_slot) wlist[s < n_rs ? first_rng + s : first + (s - n_rs)] = (uint8_t)(lane | (s << 5));
                 __syncwarp();
-                for (int e0 = 0; e0 < n_events; e0 += 32) {
+                int c = 0;
+                for (int e0 = 0; e0 < n_events; e0 += 32, ++c) {
                     const int e = e0 + lane;
+                    bool is_rec = false;
                     if (e < n_events) {
                         const uint32_t le = wlist[e];
-                        status |= resolve_event(sm, p, (wid << 5) + (int)(le & 31), (int)(le >> 5));
+                        status |= resolve_event(sm, p, (wid << 5) + (int)(le & 31), (int)(le >> 5), is_rec);
                     }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, is_rec);
+                    if (lane == 0) { wmask[c] = mask; wpre[c] = warp_recs; }
+                    warp_recs += __popc(mask);
                 }
+                if (lane == 0) { wmask[c] = 0u; wpre[c] = warp_recs; }
                 __syncwarp();
             }
+            // records among the warp's events [0, x)
+            auto recs_before = [&](int x) { return wpre[x >> 5] + (uint32_t)__popc(wmask[x >> 5] & ((1u << (x & 31)) - 1u)); };
 
             // ---- 5. gather the read's results
-            uint32_t w0 = 0, w1 = 0, w2 = 0, n_conv = 0;
+            uint32_t w0 = 0, w1 = 0, w2 = 0;
             if (n_slot > 0) {
                 ca = sm.acc[0 * kThreads + tid]; cc = sm.acc[1 * kThreads + tid];
                 cg = sm.acc[2 * kThreads + tid]; ct = sm.acc[3 * kThreads + tid];
                 w0 = (uint32_t)sm.acc[4 * kThreads + tid]; w1 = (uint32_t)sm.acc[5 * kThreads + tid];
                 w2 = (uint32_t)sm.acc[6 * kThreads + tid];
-                for (int s = 0; s < n_slot; ++s) n_conv += myslot[s * kThreads] != 0ull;
             }
-            if (inrange && slow) {
-                SlowOut so;
-                slow_unit<false>(slow_rec, unit_bytes, p, (uint32_t)r, so, nullptr, nullptr);
-                ca = so.content[0]; cc = so.content[1]; cg = so.content[2]; ct = so.content[3];
-                w0 = so.w0; w1 = so.w1; w2 = so.w2; n_conv = so.n_conv; status |= so.status;
-            }
-            if (inrange) {
-                uint32_t a = (uint32_t)max(ca, 0), c = (uint32_t)max(cc, 0), g = (uint32_t)max(cg, 0), t = (uint32_t)max(ct, 0);
-                if ((a | c | g | t) > 255u) {
-                    status |= DYN_ST_COUNTER_OVERFLOW;
-                    a = min(a, 255u); c = min(c, 255u); g = min(g, 255u); t = min(t, 255u);
+            const uint32_t pre0 = recs_before(first);
+            const uint32_t n_conv = recs_before(first + (n_slot - n_rs)) - pre0;
+            {
+                // units for tally_slow_kernel: it writes every output of theirs
+                const bool park = inrange && slow;
+                const uint32_t pm = __ballot_sync(0xffffffffu, park);
+                if (pm) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(p.n_slow, (uint32_t)__popc(pm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (park) p.slow_list[base + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)r;
                 }
-                if (!good && !slow) { a = c = g = t = 0; w0 = w1 = w2 = 0; n_conv = 0; }
-                uint4 o;
-                o.x = w0; o.y = w1; o.z = w2;
-                o.w = a | (c << 8) | (g << 16) | (t << 24);
-                reinterpret_cast<uint4 *>(p.counts)[r] = o;
+            }
+            if (inrange && !slow) {
+                if (!good) { ca = cc = cg = ct = 0; w0 = w1 = w2 = 0; }
+                store_counts(p, r, ca, cc, cg, ct, w0, w1, w2, status);
             }
             status_acc |= status;
 
             if (emit) {
-                // block exclusive scan of n_conv -> one global atomic per (sub-)tile
-                const uint32_t mine_n = inrange ? n_conv : 0u;
-                uint32_t incl = mine_n;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                if (lane == 31) warp_sums[wid] = incl;
+                // one global atomic per (sub-)tile; the warps' totals are already known
+                if (lane == 0) warp_sums[wid] = warp_recs;
                 __syncthreads();
                 if (tid == 0) {
                     uint32_t run = 0;
@@ -564,25 +613,31 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     reinterpret_cast<unsigned long long *>(warp_sums + kWarps)[0] = base;
                 }
                 __syncthreads();
-                const unsigned long long base = reinterpret_cast<unsigned long long *>(warp_sums + kWarps)[0];
-                const unsigned long long mine = base + warp_sums[wid] + (incl - mine_n);
-                if (inrange) {
-                    uint32_t n = mine_n;
+                const unsigned long long wbase = reinterpret_cast<unsigned long long *>(warp_sums + kWarps)[0] + warp_sums[wid];
+                bool fits = true;
+                if (inrange && !slow) {
+                    const unsigned long long mine = wbase + pre0;
+                    uint32_t n = n_conv;
                     if (n > 0xffffu) { n = 0xffffu; status_acc |= DYN_ST_COUNTER_OVERFLOW; }
-                    const bool fits = mine + mine_n <= (unsigned long long)p.conv_cap;
+                    fits = mine + n_conv <= (unsigned long long)p.conv_cap;
                     p.conv_off[r] = (uint32_t)mine;
                     p.conv_n[r] = fits ? (uint16_t)n : (uint16_t)0;
-                    if (mine_n > 0 && !fits) status_acc |= DYN_ST_CONV_CAPACITY;
-                    if (mine_n > 0 && fits) {
-                        if (slow) {
-                            SlowOut so;
-                            slow_unit<true>(slow_rec, unit_bytes, p, (uint32_t)r, so, p.conv_rec + mine, p.conv_read + mine);
-                        } else {
-                            uint32_t k = 0;
-                            for (int s = 0; s < n_slot; ++s) {
-                                const unsigned long long cr = myslot[s * kThreads];
-                                if (cr != 0ull) { p.conv_rec[mine + k] = cr; p.conv_read[mine + k] = (uint32_t)r; ++k; }
-                            }
+                    if (n_conv > 0 && !fits) status_acc |= DYN_ST_CONV_CAPACITY;
+                }
+                // a tile either fits the conversion buffer or (at most one tile per call) straddles its end
+                const bool all_fit = __all_sync(0xffffffffu, fits);
+                if (!all_fit) sm.acc[tid] = fits ? 1 : 0;
+                __syncwarp();
+                for (int e0 = 0; e0 < n_events; e0 += 32) {
+                    const int e = e0 + lane;
+                    if (e < n_events) {
+                        const uint32_t le = wlist[e];
+                        const int o_tid = (wid << 5) + (int)(le & 31);
+                        const unsigned long long cr = sm.slot[(le >> 5) * kThreads + o_tid];
+                        if (cr != 0ull && (all_fit || sm.acc[o_tid])) {
+                            const unsigned long long at = wbase + recs_before(e);
+                            p.conv_rec[at] = cr;
+                            p.conv_read[at] = (uint32_t)(r0 + o_tid);
                         }
                     }
                 }
@@ -594,8 +649,39 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
     if (status_acc) atomicOr(p.status, status_acc);
 }
 
+// Units the tile kernel parked: one thread per unit, straight from global memory (two walks when mismatch
+// records are wanted: count, reserve the output range with one atomic, write).
+__global__ void __launch_bounds__(128) tally_slow_kernel(const TallyParams p) {
+    const uint32_t n = *p.n_slow;
+    const bool emit = (p.flags & DYN_TALLY_EMIT_CONV) != 0;
+    uint32_t status = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t r = p.slow_list[i];
+        const uint32_t off = __ldg(p.rec_off + r), end = __ldg(p.rec_off + r + 1);
+        const uint8_t *rec = p.records + ((size_t)off << 4);
+        const size_t unit_bytes = (size_t)(end - off) << 4;
+        SlowOut so;
+        slow_unit<false>(rec, unit_bytes, p, r, so, nullptr, nullptr);
+        status |= so.status;
+        store_counts(p, r, so.content[0], so.content[1], so.content[2], so.content[3], so.w0, so.w1, so.w2, status);
+        if (emit) {
+            const uint32_t n_conv = so.n_conv;
+            const unsigned long long mine = n_conv ? atomicAdd(p.conv_total, (unsigned long long)n_conv) : 0ull;
+            uint32_t nn = n_conv;
+            if (nn > 0xffffu) { nn = 0xffffu; status |= DYN_ST_COUNTER_OVERFLOW; }
+            const bool fits = mine + n_conv <= (unsigned long long)p.conv_cap;
+            p.conv_off[r] = (uint32_t)mine;
+            p.conv_n[r] = fits ? (uint16_t)nn : (uint16_t)0;
+            if (n_conv > 0 && !fits) status |= DYN_ST_CONV_CAPACITY;
+            if (n_conv > 0 && fits) slow_unit<true>(rec, unit_bytes, p, r, so, p.conv_rec + mine, p.conv_read + mine);
+        }
+    }
+    if (status) atomicOr(p.status, status);
+}
+
 constexpr size_t kFixedSmem = sizeof(unsigned long long) * kEvSlots * kThreads + sizeof(int) * 7 * kThreads +
-                              sizeof(uint32_t) * kThreads + kThreads * kEvSlots + 16 + sizeof(uint32_t) * (kWarps + 4 + 4);
+                              sizeof(uint32_t) * kThreads + kThreads * kEvSlots + 16 + sizeof(uint32_t) * (kWarps + 4 + 4) +
+                              sizeof(uint32_t) * 2 * kWarps * (kEvSlots + 1);
 
 }  // namespace
 
@@ -634,13 +720,21 @@ extern "C" int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint
     // units) in flags bits 16..31 (DYN_TALLY_REC16_HINT); default fits 91-nt reads (~12 units).
     uint32_t hint16 = flags >> 16;
     if (hint16 == 0) hint16 = 12;
-    size_t stage = ((size_t)kThreads * hint16 * 16 * 17 / 16 + 1023) & ~(size_t)1023;   // + 6 % slack
+    size_t stage = ((size_t)kThreads * hint16 * 16 + DYN_TALLY_SLACK + 255) & ~(size_t)255;
     const size_t max_stage = ctx->smem_optin - kFixedSmem - 1024;
     if (stage > max_stage) stage = max_stage & ~(size_t)1023;
     if (stage < 8192) stage = 8192;
     p.stage_bytes = (uint32_t)stage;
     p.n_tiles = (n_reads + kThreads - 1) / kThreads;
     const size_t smem = stage + kFixedSmem;
+    // parked units: one list per stream in use (the host-buffer entry point runs two)
+    void *park = nullptr;
+    const int park_slot = (stream == static_cast<void *>(ctx->copy_stream[1])) ? 15 : 14;
+    int rc = dyn_ctx_scratch(ctx, park_slot, 256 + sizeof(uint32_t) * (size_t)n_reads, &park);
+    if (rc) return rc;
+    p.n_slow = static_cast<uint32_t *>(park);
+    p.slow_list = p.n_slow + 64;
+    DYN_CUDA(cudaMemsetAsync(p.n_slow, 0, sizeof(uint32_t), static_cast<cudaStream_t>(stream)));
 
     DYN_CUDA(cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -649,6 +743,9 @@ extern "C" int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
     tally_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    DYN_CUDA(cudaGetLastError());
+    long long slow_grid = std::min<long long>((long long)ctx->sm_count * 8, (n_reads + 127) / 128);
+    tally_slow_kernel<<<(unsigned)slow_grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     DYN_CUDA(cudaGetLastError());
     return DYN_OK;
 }
