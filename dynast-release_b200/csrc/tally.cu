@@ -14,24 +14,29 @@
 //     the others walk theirs (multi-buffering across CTAs, no intra-CTA pipeline state);
 //   * the walk keeps the lanes of a warp converged (v1, a per-read CIGAR/MD state machine, ran with
 //     5.7 of 32 lanes active; v3, per-lane event loops, spent 45 % of its instructions at 3 lanes):
-//       1. base content of the WHOLE query in a fixed-trip loop, 8 bases per 32-bit word with nibble
-//          one-hot bit planes (no popc, no masks);
-//       2. CIGAR pre-scan and a loop over the record's MD tokens (the packer tokenises the MD text; v4 spent
-//          10 of its 57 warp-instructions per read scanning it byte by byte) with warp-uniform trip counts
-//          that only LOCATE work: each mismatch (aligned offset, reference base) and each clipped / inserted
-//          query range becomes an event in the read's slot list; deleted reference bases are added on the spot;
-//       3. the warp's events are compacted (warp scan) and resolved LANE-BALANCED -- lane i takes event
-//          i, whoever's read it belongs to: offset -> query/reference position through the CIGAR, read
-//          base, Phred, quality / SNP filter; results flow back to the owner through shared-memory
-//          atomics on that read's private accumulators, the finished 64-bit mismatch record replaces
-//          the event in its slot;
+//       1. CIGAR pre-scan: aligned / deleted totals, the soft clips at either end, number of interior
+//          query ranges (insertions);
+//       2. base content of the query between the end clips, 4 bases per byte-permute instruction
+//          (the 4-bit base codes are the PRMT selectors, see count_query);
+//       3. the number of mismatch events is known before the MD tokens are read (tokens - deleted
+//          bases), so ONE packed warp scan places every read's events in the warp's shared list --
+//          ranges first, then mismatches; the token loop (the packer tokenises the MD text; v4 spent
+//          10 of its 57 warp-instructions per read scanning it byte by byte) has a warp-uniform trip
+//          count and only LOCATES work: (aligned offset, reference base) goes straight into the list,
+//          deleted reference bases are added to the content on the spot;
+//       4. the list is resolved LANE-BALANCED -- lane i takes event i, whoever's read it belongs to:
+//          offset -> query/reference position through the CIGAR, read base, Phred, quality / SNP
+//          filter; results flow back to the owner through shared-memory atomics on that read's private
+//          accumulators, the finished 64-bit mismatch record replaces the event in the list; a ballot
+//          per chunk of 32 events records which entries are records, and per-read record counts and
+//          output positions are popcounts over those ballots;
 //   * counters leave as one 128-bit store per read (consecutive threads -> consecutive 16 B: coalesced);
-//   * mismatch records are placed with one global atomic per CTA tile (block scan of per-read counts)
-//     and copied out of the slots -- the MD string is parsed once;
-//   * paired units (bam.py:307-352, 393-419), reads with more events than slots and records larger
+//   * mismatch records are placed with one global atomic per warp and copied out of the list
+//     lane-balanced (consecutive lanes -> consecutive records);
+//   * paired units (bam.py:307-352, 393-419), warps whose events overflow the list and records larger
 //     than the staging buffer are parked on a list and taken by a second kernel with a sequential
 //     per-thread walker (tally_slow_kernel / slow_unit) -- same results, no attempt at convergence.  Keeping
-//     the walker out of the tile kernel takes it from 128 to ~90 registers (11 CTAs per SM instead of 8);
+//     the walker out of the tile kernel takes it from 128 to ~70 registers (11-12 CTAs per SM instead of 8);
 //     the single-end fast path is what the bench times.
 #include "common.cuh"
 #include "walker.cuh"
@@ -54,7 +59,7 @@ namespace {
 #endif
 constexpr int kThreads = DYN_TALLY_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kEvSlots = DYN_TALLY_SLOTS;   // events kept per read in shared memory; more -> sequential walker
+constexpr int kEvSlots = DYN_TALLY_SLOTS;   // event list entries per read (a warp of 32 reads shares 32 x this many)
 constexpr unsigned long long kEvRange = 1ull << 63;
 
 struct TallyParams {
@@ -111,20 +116,37 @@ __device__ __forceinline__ void fold_fields(uint32_t acc_ac, uint32_t acc_gt, in
     ca += (int)a; cc += (int)c; cg += (int)(gt - t); ct += (int)t;
 }
 
-// A/C/G/T over the whole query: no masks (the packer zero-pads, code 0 is not a base).
-__device__ __forceinline__ void count_query(const uint32_t *seqw, int l_seq, int &ca, int &cc, int &cg, int &ct) {
-    const int n_words = (l_seq + 7) >> 3;
-    for (int w0 = 0; w0 < n_words; w0 += 7) {
-        uint32_t acc_ac = 0, acc_gt = 0;
-        const int w1 = min(n_words, w0 + 7);
-#pragma unroll 7
-        for (int w = w0; w < w1; ++w) {
-            const uint32_t x = seqw[w], xh = x >> 16;
+// nibble mask of bases [lo, hi) of a sequence word (0 <= lo < hi <= 8); base i sits at bits 4 * (i ^ 1)
+__device__ __forceinline__ uint32_t word_mask(int lo, int hi) {
+    const uint32_t m = (0xffffffffu >> (32 - 4 * hi)) & ~((1u << (4 * lo)) - 1u);
+    return ((m & 0x0f0f0f0fu) << 4) | ((m >> 4) & 0x0f0f0f0fu);
+}
+
+// A/C/G/T over query bases [qa, qb) -- the whole query minus leading / trailing soft clips.  Words are taken in
+// fully unrolled rounds of 6 with predicated loads (a word past the end reads as 0 = no base); the first word
+// is masked at a fixed slot, the last word is peeled.
+__device__ __forceinline__ void count_query(const uint32_t *seqw, int qa, int qb, int &ca, int &cc, int &cg, int &ct) {
+    if (qb <= qa) return;
+    const int wa = qa >> 3, we = (qb - 1) >> 3;
+    const uint32_t mask_lo = word_mask(qa & 7, 8), mask_hi = word_mask(0, ((qb - 1) & 7) + 1);
+    uint32_t acc_ac, acc_gt;
+    {
+        const uint32_t x = seqw[we] & mask_hi & (wa == we ? mask_lo : 0xffffffffu), xh = x >> 16;
+        acc_ac = prmt(kLutAC, 0u, x) + prmt(kLutAC, 0u, xh);
+        acc_gt = (prmt(kLutT, kLutG, x) & 0x11111111u) + (prmt(kLutT, kLutG, xh) & 0x11111111u);
+    }
+    for (int w0 = wa; w0 < we; w0 += 6) {
+        if (w0 != wa) { fold_fields(acc_ac, acc_gt, ca, cc, cg, ct); acc_ac = acc_gt = 0; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            uint32_t x = (w0 + k < we) ? seqw[w0 + k] : 0u;
+            if (k == 0 && w0 == wa) x &= mask_lo;
+            const uint32_t xh = x >> 16;
             acc_ac += prmt(kLutAC, 0u, x) + prmt(kLutAC, 0u, xh);
             acc_gt += (prmt(kLutT, kLutG, x) & 0x11111111u) + (prmt(kLutT, kLutG, xh) & 0x11111111u);
         }
-        fold_fields(acc_ac, acc_gt, ca, cc, cg, ct);
     }
+    fold_fields(acc_ac, acc_gt, ca, cc, cg, ct);
 }
 
 // A/C/G/T of query range [a, b) (soft clips, insertions).
@@ -268,12 +290,20 @@ __device__ __noinline__ void slow_unit(const uint8_t *rec, size_t unit_bytes, co
 // ---------------------------------------------------------------------------------------------------
 // Lane-balanced event resolution (fast path, shared-memory records)
 // ---------------------------------------------------------------------------------------------------
+// A warp's events live in ONE list of 64-bit entries (kWarpEvents per warp): first every query range (insertions,
+// interior clips), then every mismatch, each group in read order.  An entry starts as the event
+//   mismatch: aligned offset [0,16) | reference base code [16,20) | owner lane [24,29)
+//   range:    kEvRange | query start [0,16) | owner lane [24,29) | length [32,48)
+//   kEvNull:  nothing to do (the read turned out to be malformed)
+// and is overwritten by its result: the finished mismatch record, or 0.
+constexpr int kWarpEvents = 32 * kEvSlots;
+constexpr unsigned long long kEvNull = 1ull << 62;
+
 struct TileSmem {
     uint8_t *stage;
-    unsigned long long *slot;   // [kEvSlots][kThreads]
+    unsigned long long *list;   // [kWarps][kWarpEvents]
     int *acc;                   // [7][kThreads]: a c g t w0 w1 w2
     uint32_t *recoff;           // [kThreads] byte offset of the record inside `stage`
-    uint8_t *list;              // [kWarps][32 * kEvSlots]: lane | slot << 5
     uint32_t *wmask;            // [kWarps][kEvSlots + 1] ballot of "event e left a mismatch record", per chunk of 32 events
     uint32_t *wpre;             // [kWarps][kEvSlots + 1] records in the chunks before
 };
@@ -292,11 +322,10 @@ __device__ __forceinline__ void store_counts(const TallyParams &p, long long r, 
     reinterpret_cast<uint4 *>(p.counts)[r] = o;
 }
 
-__device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const TallyParams &p, int o_tid, int s, bool &is_rec) {
-    uint32_t status = 0;
-    is_rec = false;
-    unsigned long long *slot = sm.slot + s * kThreads + o_tid;
-    const unsigned long long pl = *slot;
+// Resolves one event of the read owned by thread o_tid; returns the mismatch record it leaves (0: none).
+__device__ __forceinline__ unsigned long long resolve_event(const TileSmem &sm, const TallyParams &p, int o_tid,
+                                                            unsigned long long pl, uint32_t &status) {
+    if (pl & kEvNull) return 0ull;
     const uint8_t *rec = sm.stage + sm.recoff[o_tid];
     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
     const int pos = (int)h.x;
@@ -306,16 +335,15 @@ __device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const Tall
     const uint8_t *seqb = reinterpret_cast<const uint8_t *>(seqw);
     int *acc = sm.acc + o_tid;
     if (pl & kEvRange) {
-        // clipped / inserted query range: count_query took those bases for reference bases
-        const int qs = (int)(pl & 0xffff), len = (int)((pl >> 20) & 0xffff);
+        // inserted / interior clipped query range: count_query took those bases for reference bases
+        const int qs = (int)(pl & 0xffff), len = (int)((pl >> 32) & 0xffff);
         int da = 0, dc = 0, dg = 0, dt = 0;
         count_range(seqw, qs, qs + len, da, dc, dg, dt);
         if (da) atomicSub(acc + 0 * kThreads, da);
         if (dc) atomicSub(acc + 1 * kThreads, dc);
         if (dg) atomicSub(acc + 2 * kThreads, dg);
         if (dt) atomicSub(acc + 3 * kThreads, dt);
-        *slot = 0;
-        return 0;
+        return 0ull;
     }
     const int aoff = (int)(pl & 0xffff);
     const uint32_t gn = (uint32_t)(pl >> 16) & 0xf;
@@ -333,7 +361,7 @@ __device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const Tall
             else if (op == 2 || op == 3) r += len;
         }
     }
-    if (qpos < 0 || qpos >= (int)l_seq) { *slot = 0; return DYN_ST_BAD_RECORD; }
+    if (qpos < 0 || qpos >= (int)l_seq) { status |= DYN_ST_BAD_RECORD; return 0ull; }
     const uint32_t rn = (seqb[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
     // count_query took the read base for the reference base: put the reference base in instead
     const int gi = base_idx(gn), ri = base_idx(rn);
@@ -341,41 +369,39 @@ __device__ __forceinline__ uint32_t resolve_event(const TileSmem &sm, const Tall
         if (gi >= 0) atomicAdd(acc + gi * kThreads, 1);
         if (ri >= 0) atomicSub(acc + ri * kThreads, 1);
     }
-    if (gn == 15 || rn == 15 || gn == rn) { *slot = 0; return 0; }   // bam.py:389-390, 405
+    if (gn == 15 || rn == 15 || gn == rn) return 0ull;   // bam.py:389-390, 405
     const uint8_t *qual = seqb + pad4(((size_t)l_seq + 1) >> 1);
     const uint32_t q = qual[qpos];
-    *slot = (unsigned long long)(uint32_t)rpos | ((unsigned long long)((gn << 4) | rn) << 32) | ((unsigned long long)q << 40);
-    is_rec = true;
-    if ((int)q <= p.quality) return 0;                                // conversion.py:424 (strict)
-    if (gi < 0 || ri < 0) return DYN_ST_NON_ACGT_CONV;
+    const unsigned long long out =
+        (unsigned long long)(uint32_t)rpos | ((unsigned long long)((gn << 4) | rn) << 32) | ((unsigned long long)q << 40);
+    if ((int)q <= p.quality) return out;                                // conversion.py:424 (strict)
+    if (gi < 0 || ri < 0) { status |= DYN_ST_NON_ACGT_CONV; return out; }
     const int idx = conv_idx(gi, ri);
     if (p.n_snps > 0 &&
         snp_lookup(p.snps, p.n_snps, ((unsigned long long)idx << 56) | ((unsigned long long)h.y << 32) | (uint32_t)rpos))
-        return 0;
+        return out;
     const uint32_t sh = (idx & 3) << 3;
     uint32_t *w = reinterpret_cast<uint32_t *>(acc + (4 + (idx >> 2)) * kThreads);
     const uint32_t old = atomicAdd(w, 1u << sh);
     if (((old >> sh) & 0xff) == 0xff) { atomicSub(w, 1u << sh); status |= DYN_ST_COUNTER_OVERFLOW; }
-    return status;
+    return out;
 }
 
 __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(const TallyParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     TileSmem sm;
     sm.stage = smem;                                                                   // [stage_bytes]
-    sm.slot = reinterpret_cast<unsigned long long *>(smem + p.stage_bytes);            // 8 * kEvSlots * kThreads
-    sm.acc = reinterpret_cast<int *>(sm.slot + kEvSlots * kThreads);                   // 4 * 7 * kThreads
+    sm.list = reinterpret_cast<unsigned long long *>(smem + p.stage_bytes);            // 8 * kWarps * kWarpEvents
+    sm.acc = reinterpret_cast<int *>(sm.list + kWarps * kWarpEvents);                  // 4 * 7 * kThreads
     sm.recoff = reinterpret_cast<uint32_t *>(sm.acc + 7 * kThreads);                   // 4 * kThreads
-    sm.list = reinterpret_cast<uint8_t *>(sm.recoff + kThreads);                       // kThreads * kEvSlots
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm.list + kThreads * kEvSlots);       // 16 B
-    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(bar + 2);                       // [kWarps + 4]
-    uint32_t *s_sub = warp_sums + kWarps + 4;                                          // sub-tile broadcast
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm.recoff + kThreads);                // 16 B
+    uint32_t *s_sub = reinterpret_cast<uint32_t *>(bar + 2);                           // sub-tile broadcast
     sm.wmask = s_sub + 4;                                                              // [kWarps][kEvSlots + 1]
     sm.wpre = sm.wmask + kWarps * (kEvSlots + 1);                                      // [kWarps][kEvSlots + 1]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
-    uint8_t *wlist = sm.list + wid * 32 * kEvSlots;
+    unsigned long long *wlist = sm.list + wid * kWarpEvents;
     uint32_t *wmask = sm.wmask + wid * (kEvSlots + 1), *wpre = sm.wpre + wid * (kEvSlots + 1);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -449,13 +475,13 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             }
 
             // ---- header
-            // a record larger than the staging buffer is walked straight from global memory
             const uint8_t *rec = sm.stage + ((size_t)(my_off - off0) << 4);
             int ca = 0, cc = 0, cg = 0, ct = 0;
             uint32_t status = 0;
             int l_seq = 0, n_cigar = 0, n_tok = 0;
             bool good = inrange, slow = false;
             if (inrange) {
+                // a record larger than the staging buffer is never staged
                 if (oversized || unit_bytes < 16) slow = true;
                 else {
                     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
@@ -469,22 +495,18 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     }
                 }
             }
+            if (slow) good = false;
             const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
             const uint32_t *tok = cig + n_cigar;
             const uint32_t *seqw = tok + n_tok;
             sm.recoff[tid] = (uint32_t)(my_off - off0) << 4;
-            unsigned long long *myslot = sm.slot + tid;
-            int n_ev = 0;
 
 #ifdef DYN_TALLY_DEBUG_SKIP
             if (DYN_TALLY_DEBUG_SKIP >= 2) { l_seq = 0; n_cigar = 0; }
             n_tok = 0;
 #endif
-            // ---- 1. whole-query base content
-            count_query(seqw, l_seq, ca, cc, cg, ct);
-
-            // ---- 2. CIGAR pre-scan: totals; clipped / inserted query ranges become events
-            int m_total = 0, d_total = 0;
+            // ---- 1. CIGAR pre-scan: totals, the soft clips at either end, number of interior query ranges
+            int m_total = 0, d_total = 0, n_rng = 0, lead = 0, trail = 0;
             {
                 int q = 0;
                 for (int ci = 0; ci < n_cigar; ++ci) {
@@ -492,24 +514,68 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     const int op = c & 0xf, len = (int)(c >> 4);
                     if (op == 0 || op == 7 || op == 8) { m_total += len; q += len; }
                     else if (op == 1 || op == 4) {
-                        if (len > 0 && q + len <= l_seq) {
-                            if (n_ev < kEvSlots)
-                                myslot[n_ev * kThreads] = kEvRange | (unsigned long long)q | ((unsigned long long)len << 20);
-                            ++n_ev;
-                        }
+                        if (op == 4 && ci == 0) lead = len;
+                        else if (op == 4 && ci == n_cigar - 1) trail = len;
+                        else if (len > 0 && q + len <= l_seq) ++n_rng;
                         q += len;
                     } else if (op == 2) d_total += len;
                 }
                 if (q != l_seq) good = false;
             }
-            const int n_rng = n_ev;     // slots [0, n_rng) hold query ranges, the rest mismatches
 
-            // ---- 3. MD tokens: mismatches become events, deleted reference bases count toward the content
-            //         right away (bam.py:359-360); warp-uniform trip count
+            // ---- 2. base content of the query between the end clips
             {
-                const int my_tok = good ? n_tok : 0;
+                const int qa = min(lead, l_seq), qb = max(qa, l_seq - trail);
+                count_query(seqw, qa, qb, ca, cc, cg, ct);
+            }
+
+            // ---- 3. event counts are known before the MD tokens are read (every deleted reference base has a
+            //         token, every other token is a mismatch): one packed warp scan places every read's ranges
+            //         and mismatches in the warp's list
+            if (n_tok < d_total) good = false;
+            if (good && (n_tok - d_total > kWarpEvents || n_rng > kWarpEvents)) { slow = true; good = false; }
+            const int n_mm = good ? n_tok - d_total : 0;
+            const int n_rs = good ? n_rng : 0;
+            uint32_t incl = (uint32_t)n_rs | ((uint32_t)n_mm << 16);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int n_ranges = (int)(tot & 0xffffu);
+            int n_events = n_ranges + (int)(tot >> 16);
+            const int first_rng = (int)(incl & 0xffffu) - n_rs;
+            const int first = n_ranges + (int)(incl >> 16) - n_mm;          // first mismatch event of this read
+            if (n_events > kWarpEvents) {
+                // the warp's list is full: reads whose events do not fit go to the sequential kernel
+                if (good && (first_rng + n_rs > kWarpEvents || first + n_mm > kWarpEvents)) { slow = true; good = false; }
+                n_events = kWarpEvents;
+                for (int j = lane; j < kWarpEvents; j += 32) wlist[j] = kEvNull;
+                __syncwarp();
+            }
+            const bool listed = good;       // this read's events are in the list
+
+            // ---- 4. fill the list: interior ranges (rare), then the MD tokens with a warp-uniform trip count;
+            //         deleted reference bases count toward the content right away (bam.py:359-360)
+            if (listed && n_rs > 0) {
+                int q = 0, k = 0;
+                for (int ci = 0; ci < n_cigar; ++ci) {
+                    const uint32_t c = cig[ci];
+                    const int op = c & 0xf, len = (int)(c >> 4);
+                    if (op == 0 || op == 7 || op == 8) q += len;
+                    else if (op == 1 || op == 4) {
+                        if (!(op == 4 && (ci == 0 || ci == n_cigar - 1)) && len > 0 && q + len <= l_seq)
+                            wlist[first_rng + k++] = kEvRange | (unsigned long long)q | ((unsigned long long)lane << 24) |
+                                                     ((unsigned long long)len << 32);
+                        q += len;
+                    }
+                }
+            }
+            {
+                const int my_tok = listed ? n_tok : 0;
                 const int max_tok = __reduce_max_sync(0xffffffffu, my_tok);
-                int n_delb = 0, last = -1;
+                int n_delb = 0, last = -1, k = 0;
                 for (int j = 0; j < max_tok; ++j) {
                     if (j < my_tok) {
                         const uint32_t tk = tok[j];
@@ -521,51 +587,38 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                             const int aoff = (int)DYN_TOK_AOFF(tk);
                             if (aoff <= last || aoff >= m_total) good = false;   // tokens must ascend inside the aligned span
                             last = aoff;
-                            if (n_ev < kEvSlots) myslot[n_ev * kThreads] = (unsigned long long)((uint32_t)aoff | (code << 16));
-                            ++n_ev;
+                            if (k < n_mm) wlist[first + k] = (unsigned long long)((uint32_t)aoff | (code << 16) | ((uint32_t)lane << 24));
+                            ++k;
                         }
                     }
                 }
-                if (n_delb != d_total) good = false;
+                if (listed && (n_delb != d_total || k != n_mm)) good = false;
+                if (listed && !good)        // malformed after all: take its events back
+                    for (int j = 0; j < n_rs + n_mm; ++j) wlist[j < n_rs ? first_rng + j : first + (j - n_rs)] = kEvNull;
             }
             if (inrange && !slow && !good) status |= DYN_ST_BAD_RECORD;
-            if (good && n_ev > kEvSlots) slow = true;
 
-            // ---- 4. compact the warp's events, resolve them lane-balanced.  Every chunk of 32 events leaves a
-            //         ballot of "this event is a mismatch record": per-read record counts and output positions
-            //         are popcounts over those ballots (no per-read loops over the slots).
-            const int n_slot = (good && !slow) ? n_ev : 0;
+            // ---- 5. resolve the events lane-balanced (lane i takes event i, whoever's read it belongs to).  Every
+            //         chunk of 32 events leaves a ballot of "this event is a mismatch record": per-read record
+            //         counts and output positions are popcounts over those ballots.
             sm.acc[0 * kThreads + tid] = ca; sm.acc[1 * kThreads + tid] = cc;
             sm.acc[2 * kThreads + tid] = cg; sm.acc[3 * kThreads + tid] = ct;
             sm.acc[4 * kThreads + tid] = 0; sm.acc[5 * kThreads + tid] = 0; sm.acc[6 * kThreads + tid] = 0;
-            // the warp's list holds all query ranges first, then the mismatches (lanes of a chunk take the same
-            // path); one scan carries both counts: ranges in the low half, mismatches in the high half
-            const int n_rs = n_slot ? n_rng : 0;
-            uint32_t incl = (uint32_t)n_rs | ((uint32_t)(n_slot - n_rs) << 16);
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-            const int n_ranges = (int)(tot & 0xffffu), n_events = n_ranges + (int)(tot >> 16);
-            const int first_rng = (int)(incl & 0xffffu) - n_rs;
-            const int first = n_ranges + (int)(incl >> 16) - (n_slot - n_rs);     // first mismatch event of this read
+            __syncwarp();
             uint32_t warp_recs = 0;
             {
-                const int max_slot = __reduce_max_sync(0xffffffffu, n_slot);
-                for (int s = 0; s < max_slot; ++s)
-                    if (s < n_slot) wlist[s < n_rs ? first_rng + s : first + (s - n_rs)] = (uint8_t)(lane | (s << 5));
-                __syncwarp();
                 int c = 0;
                 for (int e0 = 0; e0 < n_events; e0 += 32, ++c) {
                     const int e = e0 + lane;
-                    bool is_rec = false;
+                    unsigned long long out = 0ull;
                     if (e < n_events) {
-                        const uint32_t le = wlist[e];
-                        status |= resolve_event(sm, p, (wid << 5) + (int)(le & 31), (int)(le >> 5), is_rec);
+                        const unsigned long long pl = wlist[e];
+                        const uint32_t owner = (uint32_t)(pl >> 24) & 31u;
+                        out = resolve_event(sm, p, (wid << 5) + (int)owner, pl, status);
+                        if (out) out |= (unsigned long long)owner << 48;      // kept for the copy-out below
+                        wlist[e] = out;
                     }
-                    const uint32_t mask = __ballot_sync(0xffffffffu, is_rec);
+                    const uint32_t mask = __ballot_sync(0xffffffffu, out != 0ull);
                     if (lane == 0) { wmask[c] = mask; wpre[c] = warp_recs; }
                     warp_recs += __popc(mask);
                 }
@@ -575,16 +628,16 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             // records among the warp's events [0, x)
             auto recs_before = [&](int x) { return wpre[x >> 5] + (uint32_t)__popc(wmask[x >> 5] & ((1u << (x & 31)) - 1u)); };
 
-            // ---- 5. gather the read's results
-            uint32_t w0 = 0, w1 = 0, w2 = 0;
-            if (n_slot > 0) {
+            // ---- 6. gather the read's results
+            uint32_t w0 = 0, w1 = 0, w2 = 0, pre0 = 0, n_conv = 0;
+            if (good) {
                 ca = sm.acc[0 * kThreads + tid]; cc = sm.acc[1 * kThreads + tid];
                 cg = sm.acc[2 * kThreads + tid]; ct = sm.acc[3 * kThreads + tid];
                 w0 = (uint32_t)sm.acc[4 * kThreads + tid]; w1 = (uint32_t)sm.acc[5 * kThreads + tid];
                 w2 = (uint32_t)sm.acc[6 * kThreads + tid];
-            }
-            const uint32_t pre0 = recs_before(first);
-            const uint32_t n_conv = recs_before(first + (n_slot - n_rs)) - pre0;
+                pre0 = recs_before(first);
+                n_conv = recs_before(first + n_mm) - pre0;
+            } else { ca = cc = cg = ct = 0; }
             {
                 // units for tally_slow_kernel: it writes every output of theirs
                 const bool park = inrange && slow;
@@ -596,24 +649,14 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     if (park) p.slow_list[base + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)r;
                 }
             }
-            if (inrange && !slow) {
-                if (!good) { ca = cc = cg = ct = 0; w0 = w1 = w2 = 0; }
-                store_counts(p, r, ca, cc, cg, ct, w0, w1, w2, status);
-            }
+            if (inrange && !slow) store_counts(p, r, ca, cc, cg, ct, w0, w1, w2, status);
             status_acc |= status;
 
             if (emit) {
-                // one global atomic per (sub-)tile; the warps' totals are already known
-                if (lane == 0) warp_sums[wid] = warp_recs;
-                __syncthreads();
-                if (tid == 0) {
-                    uint32_t run = 0;
-                    for (int w = 0; w < kWarps; ++w) { const uint32_t t = warp_sums[w]; warp_sums[w] = run; run += t; }
-                    const unsigned long long base = run ? atomicAdd(p.conv_total, (unsigned long long)run) : 0ull;
-                    reinterpret_cast<unsigned long long *>(warp_sums + kWarps)[0] = base;
-                }
-                __syncthreads();
-                const unsigned long long wbase = reinterpret_cast<unsigned long long *>(warp_sums + kWarps)[0] + warp_sums[wid];
+                // one global atomic per warp reserves the output range of its 32 reads
+                unsigned long long wbase = 0ull;
+                if (lane == 0 && warp_recs) wbase = atomicAdd(p.conv_total, (unsigned long long)warp_recs);
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 bool fits = true;
                 if (inrange && !slow) {
                     const unsigned long long mine = wbase + pre0;
@@ -624,25 +667,24 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     p.conv_n[r] = fits ? (uint16_t)n : (uint16_t)0;
                     if (n_conv > 0 && !fits) status_acc |= DYN_ST_CONV_CAPACITY;
                 }
-                // a tile either fits the conversion buffer or (at most one tile per call) straddles its end
+                // a warp either fits the conversion buffer or (rarely) straddles its end
                 const bool all_fit = __all_sync(0xffffffffu, fits);
                 if (!all_fit) sm.acc[tid] = fits ? 1 : 0;
                 __syncwarp();
-                for (int e0 = 0; e0 < n_events; e0 += 32) {
+                for (int e0 = n_ranges & ~31; e0 < n_events; e0 += 32) {
                     const int e = e0 + lane;
-                    if (e < n_events) {
-                        const uint32_t le = wlist[e];
-                        const int o_tid = (wid << 5) + (int)(le & 31);
-                        const unsigned long long cr = sm.slot[(le >> 5) * kThreads + o_tid];
-                        if (cr != 0ull && (all_fit || sm.acc[o_tid])) {
+                    if (e < n_events && ((wmask[e >> 5] >> (e & 31)) & 1u)) {
+                        const unsigned long long cr = wlist[e];
+                        const int o_tid = (wid << 5) + (int)((cr >> 48) & 31);
+                        if (all_fit || sm.acc[o_tid]) {
                             const unsigned long long at = wbase + recs_before(e);
-                            p.conv_rec[at] = cr;
+                            p.conv_rec[at] = cr & 0xffffffffffffull;
                             p.conv_read[at] = (uint32_t)(r0 + o_tid);
                         }
                     }
                 }
             }
-            __syncthreads();   // everyone is done with `stage` / slots before the next bulk copy lands
+            __syncthreads();   // everyone is done with `stage` / the lists before the next bulk copy lands
             r0 = r1;
         }
     }
@@ -679,8 +721,8 @@ __global__ void __launch_bounds__(128) tally_slow_kernel(const TallyParams p) {
     if (status) atomicOr(p.status, status);
 }
 
-constexpr size_t kFixedSmem = sizeof(unsigned long long) * kEvSlots * kThreads + sizeof(int) * 7 * kThreads +
-                              sizeof(uint32_t) * kThreads + kThreads * kEvSlots + 16 + sizeof(uint32_t) * (kWarps + 4 + 4) +
+constexpr size_t kFixedSmem = sizeof(unsigned long long) * kWarps * kWarpEvents + sizeof(int) * 7 * kThreads +
+                              sizeof(uint32_t) * kThreads + 16 + sizeof(uint32_t) * 4 +
                               sizeof(uint32_t) * 2 * kWarps * (kEvSlots + 1);
 
 }  // namespace

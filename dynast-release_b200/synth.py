@@ -12,6 +12,41 @@ from . import records
 BASES = np.array(list('ACGT'))
 
 
+def _complex_cigar(rng, L):
+    """Hard clips, soft clips at either end, several M/=/X pieces separated by I, D and N -- including an insertion
+    right after the leading clip and right before the trailing one."""
+    while True:
+        lead = int(rng.integers(1, 15)) if rng.random() < 0.4 else 0
+        trail = int(rng.integers(1, 15)) if rng.random() < 0.4 else 0
+        n_seg = int(rng.integers(1, 5))
+        gaps = [int(rng.choice([1, 1, 2, 3])) for _ in range(n_seg - 1)]
+        gap_len = [int(rng.integers(1, 5)) if g != 3 else int(rng.integers(20, 3000)) for g in gaps]
+        edge_ins = [int(rng.integers(1, 4)) if rng.random() < 0.15 else 0 for _ in range(2)]
+        body = L - lead - trail - sum(n for g, n in zip(gaps, gap_len) if g == 1) - sum(edge_ins)
+        if body >= n_seg:
+            break
+    cuts = np.sort(rng.choice(np.arange(1, body), n_seg - 1, replace=False)) if n_seg > 1 else np.array([], dtype=int)
+    pieces = np.diff(np.concatenate([[0], cuts, [body]])).astype(int)
+    cigar = []
+    if rng.random() < 0.2:
+        cigar.append((5, int(rng.integers(1, 10))))
+    if lead:
+        cigar.append((4, lead))
+    if edge_ins[0]:
+        cigar.append((1, edge_ins[0]))
+    for j, m in enumerate(pieces):
+        cigar.append((int(rng.choice([0, 0, 0, 7, 8])), int(m)))
+        if j < n_seg - 1:
+            cigar.append((gaps[j], gap_len[j]))
+    if edge_ins[1]:
+        cigar.append((1, edge_ins[1]))
+    if trail:
+        cigar.append((4, trail))
+    if rng.random() < 0.2:
+        cigar.append((5, int(rng.integers(1, 10))))
+    return cigar
+
+
 def make_reads(
     n_reads: int,
     seed: int = 2001,
@@ -24,6 +59,7 @@ def make_reads(
     frac_n: float = 0.001,
     umi_len: int = 12,
     reads_per_umi: float = 2.0,
+    complex_cigars: bool = False,
 ):
     """Returns dict(blob, rec_off, barcode_id, umi, gene_id, score, strand_gene, truth...) with one
     single-end read per counting unit.  CIGAR mix: 70 % LM, 18 % aMbNcM, 8 % sS(L-s)M, 2 % one 1-3 nt D,
@@ -31,6 +67,7 @@ def make_reads(
     base is substituted to each specific other base w.p. p_e; Phred 90 % in 36..40, 10 % in 2..27."""
     rng = np.random.default_rng(seed)
     units = []
+    raw = []
     L = read_len
     gene_strand = rng.integers(0, 2, n_genes)
     gene_contig = rng.integers(0, n_contigs, n_genes)
@@ -53,7 +90,9 @@ def make_reads(
     kind = rng.choice(5, n_reads, p=[0.70, 0.18, 0.08, 0.02, 0.02])
     for i in range(n_reads):
         k = kind[i]
-        if k == 0:
+        if complex_cigars:
+            cigar = _complex_cigar(rng, L)
+        elif k == 0:
             cigar = [(0, L)]
         elif k == 1:
             a = int(rng.integers(10, L - 10))
@@ -68,7 +107,7 @@ def make_reads(
             a = int(rng.integers(10, L - 10))
             ins = int(rng.integers(1, 4))
             cigar = [(0, a), (1, ins), (0, L - a - ins)]
-        n_ref = sum(n for op, n in cigar if op in (0, 2))
+        n_ref = sum(n for op, n in cigar if op in (0, 2, 7, 8))
         ref = rng.integers(0, 4, n_ref)
         qual = np.where(rng.random(L) < 0.9, rng.integers(36, 41, L), rng.integers(2, 28, L))
         seq = []
@@ -79,7 +118,7 @@ def make_reads(
         strand_rev = gene_strand[gene_id[i]] == 1
         conv_from, conv_to = (0, 2) if strand_rev else (3, 1)   # A>G on reverse-strand genes, T>C on forward
         for op, n in cigar:
-            if op == 0:
+            if op in (0, 7, 8):
                 for _ in range(n):
                     g = int(ref[ri])
                     ri += 1
@@ -115,6 +154,7 @@ def make_reads(
         flag = 16 if rng.random() < 0.5 else 0
         score[i] = L - 2 * nm
         units.append([records.pack_one(int(pos[i]), int(gene_contig[gene_id[i]]), flag, cigar, ''.join(seq), qual, ''.join(md))])
+        raw.append((int(pos[i]), cigar, ''.join(seq), [int(x) for x in qual], ''.join(md)))
     blob, rec_off = records.pack_units(units)
     return dict(
         blob=blob,
@@ -125,4 +165,5 @@ def make_reads(
         score=score,
         gene_strand=gene_strand.astype(np.uint8),
         labelled=labelled,
+        raw=raw,
     )

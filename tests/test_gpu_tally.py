@@ -99,6 +99,19 @@ def test_synthetic_vs_oracle(gpu_ctx, oracle_lib, n_reads, seed):
         _compare(gpu, orc)
 
 
+@pytest.mark.parametrize('read_len,p_e,seed', [(91, 5e-4, 31), (150, 0.01, 32), (40, 0.03, 33), (17, 0.05, 34)])
+def test_complex_cigars(gpu_ctx, oracle_lib, read_len, p_e, seed):
+    """Hard / soft clips at both ends, =/X pieces, several insertions, deletions and junctions per read, insertions
+    next to the clips; N calls inside clipped and inserted stretches."""
+    from oracle import pack
+    from dynast_b200 import device, synth
+    d = synth.make_reads(3000, seed=seed, read_len=read_len, p_e=p_e, frac_n=0.01, complex_cigars=True)
+    orc = pack.run_tally(d['blob'], d['rec_off'], quality=20)
+    gpu = device.tally_reads_host(d['blob'], d['rec_off'], quality=20)
+    assert orc['status'] == 0 and orc['total'] > 0
+    _compare(gpu, orc)
+
+
 def test_snp_filter(gpu_ctx, oracle_lib):
     from oracle import pack
     from dynast_b200 import device, records as rec, synth

@@ -66,3 +66,62 @@ def test_tally_oracle_matches_fixture_rows(oracle_lib, align, count, kw, nasc):
         assert (row['barcode'], row['umi'], int(row['score']), row['transcriptome']) == (
             m['barcode'], m['umi'], m['score'], str(m['gx_assigned']))
     assert n_cmp == len(ali)
+
+
+def _plain_tally(pos, cigar, seq, qual, md, quality):
+    """The reference's per-read rules (bam.py:357-411, conversion.py:417-426) written out on (CIGAR, MD, SEQ)
+    text, independent of the packed format and of the C walker."""
+    import re
+    aligned, q, r = [], 0, pos
+    for op, n in cigar:
+        if op in (0, 7, 8):
+            aligned += [(q + i, r + i) for i in range(n)]
+            q += n
+            r += n
+        elif op in (1, 4):
+            q += n
+        elif op in (2, 3):
+            r += n
+    ref_bases, deleted, ai = [], [], 0
+    for num, dele, mm in re.findall(r'(\d+)|(\^[A-Z]+)|([A-Z])', md):
+        if num:
+            for _ in range(int(num)):
+                ref_bases.append(seq[aligned[ai][0]])
+                ai += 1
+        elif dele:
+            deleted += list(dele[1:])
+        else:
+            ref_bases.append(mm)
+            ai += 1
+    assert ai == len(aligned)
+    content = [sum(1 for b in ref_bases + deleted if b == c) for c in 'ACGT']
+    names = [a + b for a in 'ACGT' for b in 'ACGT' if a != b]
+    counts = [0] * 12
+    recs = []
+    for (qp, rp), g in zip(aligned, ref_bases):
+        b = seq[qp]
+        if g == 'N' or b == 'N' or g == b:
+            continue
+        recs.append((rp, g + b, qual[qp]))
+        if qual[qp] > quality:
+            counts[names.index(g + b)] += 1
+    return counts + content, recs
+
+
+@pytest.mark.parametrize('read_len,p_e,seed', [(91, 5e-4, 31), (40, 0.03, 33), (17, 0.05, 34)])
+def test_tally_oracle_complex_cigars(oracle_lib, read_len, p_e, seed):
+    """C oracle == the rules above on reads with clips at both ends, =/X pieces, several I / D / N per read."""
+    from oracle import pack
+    from dynast_b200 import records as rec, synth
+    d = synth.make_reads(400, seed=seed, read_len=read_len, p_e=p_e, frac_n=0.01, complex_cigars=True)
+    out = pack.run_tally(d['blob'], d['rec_off'], quality=20)
+    assert out['status'] == 0
+    pos, refl, readl, q = rec.decode_conv(out['conv_rec'])
+    n_ops = set()
+    for i, (p0, cigar, seq, qual, md) in enumerate(d['raw']):
+        want, recs = _plain_tally(p0, cigar, seq, qual, md, 20)
+        assert want == [int(x) for x in out['counts'][i]], (cigar, md)
+        o, n = int(out['conv_off'][i]), int(out['conv_n'][i])
+        assert [(int(pos[j]), refl[j] + readl[j], int(q[j])) for j in range(o, o + n)] == recs
+        n_ops.update(op for op, _ in cigar)
+    assert n_ops == {0, 1, 2, 3, 4, 5, 7, 8}
