@@ -108,7 +108,13 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-constexpr uint32_t kLutAC = 0x00100100u, kLutT = 0x00000080u, kLutG = 0x00000001u;
+constexpr uint32_t kLutG = 0x00000001u;
+// The two tables that go in PRMT's register operand are read from shared memory once per thread: given the
+// constants, ptxas keeps them in uniform registers and copies them to a fresh register in front of EVERY PRMT
+// (one extra instruction per four bases).
+struct BaseLut {
+    uint32_t ac, t;
+};
 
 __device__ __forceinline__ void fold_fields(uint32_t acc_ac, uint32_t acc_gt, int &ca, int &cc, int &cg, int &ct) {
     const uint32_t a = ((acc_ac & 0x0f0f0f0fu) * 0x01010101u) >> 24, c = (((acc_ac >> 4) & 0x0f0f0f0fu) * 0x01010101u) >> 24;
@@ -125,15 +131,16 @@ __device__ __forceinline__ uint32_t word_mask(int lo, int hi) {
 // A/C/G/T over query bases [qa, qb) -- the whole query minus leading / trailing soft clips.  Words are taken in
 // fully unrolled rounds of 6 with predicated loads (a word past the end reads as 0 = no base); the first word
 // is masked at a fixed slot, the last word is peeled.
-__device__ __forceinline__ void count_query(const uint32_t *seqw, int qa, int qb, int &ca, int &cc, int &cg, int &ct) {
+__device__ __forceinline__ void count_query(const BaseLut &lut, const uint32_t *seqw, int qa, int qb, int &ca, int &cc, int &cg,
+                                            int &ct) {
     if (qb <= qa) return;
     const int wa = qa >> 3, we = (qb - 1) >> 3;
     const uint32_t mask_lo = word_mask(qa & 7, 8), mask_hi = word_mask(0, ((qb - 1) & 7) + 1);
     uint32_t acc_ac, acc_gt;
     {
         const uint32_t x = seqw[we] & mask_hi & (wa == we ? mask_lo : 0xffffffffu), xh = x >> 16;
-        acc_ac = prmt(kLutAC, 0u, x) + prmt(kLutAC, 0u, xh);
-        acc_gt = (prmt(kLutT, kLutG, x) & 0x11111111u) + (prmt(kLutT, kLutG, xh) & 0x11111111u);
+        acc_ac = prmt(lut.ac, 0u, x) + prmt(lut.ac, 0u, xh);
+        acc_gt = (prmt(lut.t, kLutG, x) & 0x11111111u) + (prmt(lut.t, kLutG, xh) & 0x11111111u);
     }
     for (int w0 = wa; w0 < we; w0 += 6) {
         if (w0 != wa) { fold_fields(acc_ac, acc_gt, ca, cc, cg, ct); acc_ac = acc_gt = 0; }
@@ -142,15 +149,16 @@ __device__ __forceinline__ void count_query(const uint32_t *seqw, int qa, int qb
             uint32_t x = (w0 + k < we) ? seqw[w0 + k] : 0u;
             if (k == 0 && w0 == wa) x &= mask_lo;
             const uint32_t xh = x >> 16;
-            acc_ac += prmt(kLutAC, 0u, x) + prmt(kLutAC, 0u, xh);
-            acc_gt += (prmt(kLutT, kLutG, x) & 0x11111111u) + (prmt(kLutT, kLutG, xh) & 0x11111111u);
+            acc_ac += prmt(lut.ac, 0u, x) + prmt(lut.ac, 0u, xh);
+            acc_gt += (prmt(lut.t, kLutG, x) & 0x11111111u) + (prmt(lut.t, kLutG, xh) & 0x11111111u);
         }
     }
     fold_fields(acc_ac, acc_gt, ca, cc, cg, ct);
 }
 
 // A/C/G/T of query range [a, b) (soft clips, insertions).
-__device__ __forceinline__ void count_range(const uint32_t *seqw, int a, int b, int &ca, int &cc, int &cg, int &ct) {
+__device__ __forceinline__ void count_range(const BaseLut &lut, const uint32_t *seqw, int a, int b, int &ca, int &cc, int &cg,
+                                            int &ct) {
     for (int w0 = a >> 3; w0 <= (b - 1) >> 3; w0 += 7) {
         uint32_t acc_ac = 0, acc_gt = 0;
         const int w1 = min(((b - 1) >> 3) + 1, w0 + 7);
@@ -160,8 +168,8 @@ __device__ __forceinline__ void count_range(const uint32_t *seqw, int a, int b, 
             uint32_t mask = (hi == 8 ? 0xffffffffu : ((1u << (4 * hi)) - 1u)) & ~((1u << (4 * lo)) - 1u);
             mask = ((mask & 0x0f0f0f0fu) << 4) | ((mask >> 4) & 0x0f0f0f0fu);
             const uint32_t x = seqw[w] & mask, xh = x >> 16;
-            acc_ac += prmt(kLutAC, 0u, x) + prmt(kLutAC, 0u, xh);
-            acc_gt += (prmt(kLutT, kLutG, x) & 0x11111111u) + (prmt(kLutT, kLutG, xh) & 0x11111111u);
+            acc_ac += prmt(lut.ac, 0u, x) + prmt(lut.ac, 0u, xh);
+            acc_gt += (prmt(lut.t, kLutG, x) & 0x11111111u) + (prmt(lut.t, kLutG, xh) & 0x11111111u);
         }
         fold_fields(acc_ac, acc_gt, ca, cc, cg, ct);
     }
@@ -323,8 +331,8 @@ __device__ __forceinline__ void store_counts(const TallyParams &p, long long r, 
 }
 
 // Resolves one event of the read owned by thread o_tid; returns the mismatch record it leaves (0: none).
-__device__ __forceinline__ unsigned long long resolve_event(const TileSmem &sm, const TallyParams &p, int o_tid,
-                                                            unsigned long long pl, uint32_t &status) {
+__device__ __forceinline__ unsigned long long resolve_event(const TileSmem &sm, const TallyParams &p, const BaseLut &lut,
+                                                            int o_tid, unsigned long long pl, uint32_t &status) {
     if (pl & kEvNull) return 0ull;
     const uint8_t *rec = sm.stage + sm.recoff[o_tid];
     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
@@ -338,7 +346,7 @@ __device__ __forceinline__ unsigned long long resolve_event(const TileSmem &sm, 
         // inserted / interior clipped query range: count_query took those bases for reference bases
         const int qs = (int)(pl & 0xffff), len = (int)((pl >> 32) & 0xffff);
         int da = 0, dc = 0, dg = 0, dt = 0;
-        count_range(seqw, qs, qs + len, da, dc, dg, dt);
+        count_range(lut, seqw, qs, qs + len, da, dc, dg, dt);
         if (da) atomicSub(acc + 0 * kThreads, da);
         if (dc) atomicSub(acc + 1 * kThreads, dc);
         if (dg) atomicSub(acc + 2 * kThreads, dg);
@@ -406,8 +414,13 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_sub[2] = 0x00100100u;     // BaseLut: A -> 0x01, C -> 0x10
+        s_sub[3] = 0x00000080u;     //          T -> 0xff (sign of 0x80 replicated), '=' -> 0x80
     }
     __syncthreads();
+    BaseLut lut;
+    lut.ac = reinterpret_cast<volatile uint32_t *>(s_sub)[2];
+    lut.t = reinterpret_cast<volatile uint32_t *>(s_sub)[3];
     uint32_t parity = 0;
     uint32_t status_acc = 0;
     const bool emit = (p.flags & DYN_TALLY_EMIT_CONV) != 0;
@@ -427,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(pf_my_end) : "l"(p.rec_off + r + 1));
     };
     prefetch_offsets(blockIdx.x);
+    bool pre_issued = false;     // the bulk copy of this tile was started during the previous tile's copy-out
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long t0 = tile * kThreads;
@@ -455,11 +469,12 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             }
             const uint32_t off1 = (r1 == t1) ? off_end : __ldg(p.rec_off + r1);
             const uint32_t bytes = oversized ? 0u : (off1 - off0) << 4;
-            if (tid == 0 && bytes > 0) {
+            if (tid == 0 && bytes > 0 && !pre_issued) {
                 fence_proxy_async();
                 mbar_expect_tx(bar, bytes);
                 tma_bulk_g2s(sm.stage, p.records + ((unsigned long long)off0 << 4), bytes, bar);
             }
+            pre_issued = false;
             const long long r = r0 + tid;
             const bool inrange = r < r1;
             uint32_t my_off = off0, my_end = off0;
@@ -526,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
             // ---- 2. base content of the query between the end clips
             {
                 const int qa = min(lead, l_seq), qb = max(qa, l_seq - trail);
-                count_query(seqw, qa, qb, ca, cc, cg, ct);
+                count_query(lut, seqw, qa, qb, ca, cc, cg, ct);
             }
 
             // ---- 3. event counts are known before the MD tokens are read (every deleted reference base has a
@@ -614,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     if (e < n_events) {
                         const unsigned long long pl = wlist[e];
                         const uint32_t owner = (uint32_t)(pl >> 24) & 31u;
-                        out = resolve_event(sm, p, (wid << 5) + (int)owner, pl, status);
+                        out = resolve_event(sm, p, lut, (wid << 5) + (int)owner, pl, status);
                         if (out) out |= (unsigned long long)owner << 48;      // kept for the copy-out below
                         wlist[e] = out;
                     }
@@ -649,13 +664,26 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     if (park) p.slow_list[base + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)r;
                 }
             }
+            // ---- 7. the records are dead from here on (the copy-out below reads the list only): start the next
+            //         tile's bulk copy now, so that it lands while this tile's output range is reserved and written
+            __syncthreads();
+            if (r1 == t1 && tile + gridDim.x < p.n_tiles && pf_off_end > pf_off0 && pf_off_end - pf_off0 <= cap16) {
+                if (tid == 0) {
+                    const uint32_t nbytes = (pf_off_end - pf_off0) << 4;
+                    fence_proxy_async();
+                    mbar_expect_tx(bar, nbytes);
+                    tma_bulk_g2s(sm.stage, p.records + ((unsigned long long)pf_off0 << 4), nbytes, bar);
+                }
+                pre_issued = true;
+            }
+            // one global atomic per warp reserves the output range of its 32 reads; its latency hides behind the
+            // counter stores
+            unsigned long long wbase = 0ull;
+            if (emit && lane == 0 && warp_recs) wbase = atomicAdd(p.conv_total, (unsigned long long)warp_recs);
             if (inrange && !slow) store_counts(p, r, ca, cc, cg, ct, w0, w1, w2, status);
             status_acc |= status;
 
             if (emit) {
-                // one global atomic per warp reserves the output range of its 32 reads
-                unsigned long long wbase = 0ull;
-                if (lane == 0 && warp_recs) wbase = atomicAdd(p.conv_total, (unsigned long long)warp_recs);
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 bool fits = true;
                 if (inrange && !slow) {
@@ -684,7 +712,6 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     }
                 }
             }
-            __syncthreads();   // everyone is done with `stage` / the lists before the next bulk copy lands
             r0 = r1;
         }
     }
