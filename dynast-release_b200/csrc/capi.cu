@@ -41,6 +41,7 @@ extern "C" int dyn_ctx_create(int device, dyn_ctx_t **out) {
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     for (int i = 0; i < 2; ++i) DYN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) DYN_CUDA(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    DYN_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_small), 256, cudaHostAllocDefault));
     *out = ctx;
     return DYN_OK;
 }
@@ -52,6 +53,7 @@ extern "C" int dyn_ctx_destroy(dyn_ctx_t *ctx) {
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->em_coef) cudaFree(ctx->em_coef);
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(ctx->copy_stream[i]);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
     return DYN_OK;
@@ -128,8 +130,11 @@ extern "C" int dyn_tally_reads_host(dyn_ctx_t *ctx, const void *h_records, const
     struct Slot {
         int64_t r0, nr;
         uint32_t *d_conv_off; uint16_t *d_conv_n; uint64_t *d_conv_rec; uint32_t *d_conv_read; uint64_t *d_conv_total;
-        uint64_t chunk_total;   // pinned-less 8-byte landing zone (small synchronous-ish copy)
+        uint64_t *chunk_total;  // page-locked landing zone: a copy into pageable memory would block the host until
+                                // the chunk is done and serialise the two streams
     } slot[2];
+    slot[0].chunk_total = ctx->h_small;
+    slot[1].chunk_total = ctx->h_small + 8;
     uint64_t total_conv = 0;
 
     // Software pipeline: step c enqueues chunk c (H2D, kernel, fixed-size D2H) on stream c&1, then
@@ -170,7 +175,7 @@ extern "C" int dyn_tally_reads_host(dyn_ctx_t *ctx, const void *h_records, const
             if (rc) return rc;
             DYN_CUDA(cudaMemcpyAsync(h_counts + (size_t)r0 * 16, d_counts, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
             if (emit) {
-                DYN_CUDA(cudaMemcpyAsync(&sl.chunk_total, sl.d_conv_total, 8, cudaMemcpyDeviceToHost, st));
+                DYN_CUDA(cudaMemcpyAsync(sl.chunk_total, sl.d_conv_total, 8, cudaMemcpyDeviceToHost, st));
                 DYN_CUDA(cudaMemcpyAsync(h_conv_off + r0, sl.d_conv_off, sizeof(uint32_t) * nr, cudaMemcpyDeviceToHost, st));
                 DYN_CUDA(cudaMemcpyAsync(h_conv_n + r0, sl.d_conv_n, sizeof(uint16_t) * nr, cudaMemcpyDeviceToHost, st));
             }
@@ -181,7 +186,7 @@ extern "C" int dyn_tally_reads_host(dyn_ctx_t *ctx, const void *h_records, const
             Slot &sl = slot[s];
             DYN_CUDA(cudaStreamSynchronize(st));
             if (emit) {
-                uint64_t chunk_total = sl.chunk_total;
+                uint64_t chunk_total = *sl.chunk_total;
                 if (chunk_total > max_conv) chunk_total = max_conv;   // status carries DYN_ST_CONV_CAPACITY
                 if (total_conv + chunk_total > (uint64_t)conv_capacity) {
                     dyn_set_error("dyn_tally_reads_host: conversion capacity %lld exceeded", (long long)conv_capacity);

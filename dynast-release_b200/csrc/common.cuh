@@ -31,6 +31,7 @@ struct dyn_ctx {
     size_t smem_optin;      // max dynamic shared memory per block
     cudaStream_t copy_stream[2];
     cudaEvent_t ev[4];
+    uint64_t *h_small;      // 256 page-locked bytes: landing zone for small asynchronous device -> host copies
     // lazily grown device scratch (never shrinks); used by host-buffer entry points and sort temp
     void *scratch[16];
     size_t scratch_bytes[16];
