@@ -352,15 +352,25 @@ def main():
     if not args.skip_pipeline:
         timings = {}
         reps = 2
-        pipeline.count_to_estimate(ctx, batch.records, batch.rec_off, batch.barcode - rank * args.barcodes, batch.umi, batch.gene,
-                                   batch.score, batch.strand, args.barcodes, batch.n_genes, out)        # warm-up
+        # N > 1: read-range sharding means a barcode's reads sit on every rank.  Give every (barcode, UMI) group a
+        # global barcode id whose owner (id % world) is spread over the ranks, and let the path do its per-read
+        # all-to-all to the owner before dedup; every rank ends up with ~n_reads reads of args.barcodes barcodes.
+        xchg = world > 1
+        p_bc = batch.barcode - rank * args.barcodes
+        if xchg:
+            p_bc = (p_bc.to(torch.int64) * world + batch.umi % world).to(torch.int32)
+        p_nb = args.barcodes * world
+
+        def run_path(t=None):
+            return pipeline.count_to_estimate(ctx, batch.records, batch.rec_off, p_bc, batch.umi, batch.gene, batch.score,
+                                              batch.strand, p_nb, batch.n_genes, out, timings=t, exchange=xchg)
+
+        run_path()        # warm-up
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(stream)
         for _ in range(reps):
-            res = pipeline.count_to_estimate(ctx, batch.records, batch.rec_off, batch.barcode - rank * args.barcodes, batch.umi,
-                                             batch.gene, batch.score, batch.strand, args.barcodes, batch.n_genes, out,
-                                             timings=timings)
+            res = run_path(timings)
         p1.record(stream)
         barrier()
         pipe_ms = p0.elapsed_time(p1) / reps
@@ -373,6 +383,7 @@ def main():
                 'stage_ms': {k: v / reps for k, v in timings.items()},
                 'reads_after_dedup': int(res['selected'].numel()),
                 'barcodes_with_p_c': int((res['em_status'] == 0).sum().item()),
+                'exchange': ('all-to-all of 40-byte per-read rows to rank barcode % world before dedup (NCCL)' if xchg else None),
                 'note': 'includes the host round trips of the dedup split plan and the EM / pi shape discovery'}
         del res
 
@@ -489,7 +500,7 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config, 'gpu_launches': args.steps,
+            'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config, 'gpu_launches': 2 * args.steps,
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'em': em, 'pipeline': pipe, 'consensus': cons, 'clocks': clocks,
             'conversions_per_read': n_conv / n_reads,
         }

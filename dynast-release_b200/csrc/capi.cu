@@ -49,7 +49,7 @@ extern "C" int dyn_ctx_create(int device, dyn_ctx_t **out) {
 extern "C" int dyn_ctx_destroy(dyn_ctx_t *ctx) {
     if (!ctx) return DYN_OK;
     cudaSetDevice(ctx->device);
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < kScratchSlots; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->em_coef) cudaFree(ctx->em_coef);
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(ctx->copy_stream[i]);
@@ -62,7 +62,7 @@ extern "C" int dyn_ctx_destroy(dyn_ctx_t *ctx) {
 extern "C" int dyn_ctx_sm_count(dyn_ctx_t *ctx) { return ctx ? ctx->sm_count : 0; }
 
 int dyn_ctx_scratch(dyn_ctx *ctx, int slot, size_t bytes, void **out) {
-    if (slot < 0 || slot >= 16) { dyn_set_error("bad scratch slot"); return DYN_ERR_ARG; }
+    if (slot < 0 || slot >= kScratchSlots) { dyn_set_error("bad scratch slot"); return DYN_ERR_ARG; }
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) DYN_CUDA(cudaFree(ctx->scratch[slot]));
         ctx->scratch[slot] = nullptr;

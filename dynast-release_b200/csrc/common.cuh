@@ -25,6 +25,8 @@ void dyn_set_error(const char *fmt, ...);
         }                                  \
     } while (0)
 
+constexpr int kScratchSlots = 24;
+
 struct dyn_ctx {
     int device;
     int sm_count;
@@ -33,8 +35,8 @@ struct dyn_ctx {
     cudaEvent_t ev[4];
     uint64_t *h_small;      // 256 page-locked bytes: landing zone for small asynchronous device -> host copies
     // lazily grown device scratch (never shrinks); used by host-buffer entry points and sort temp
-    void *scratch[16];
-    size_t scratch_bytes[16];
+    void *scratch[kScratchSlots];
+    size_t scratch_bytes[kScratchSlots];
     // lazily built device tables
     double *em_coef;        // binomial coefficient table (wrapped-int64 semantics), [em_coef_K][em_coef_N]
     int em_coef_K, em_coef_N;
@@ -43,7 +45,8 @@ struct dyn_ctx {
 int dyn_ctx_scratch(dyn_ctx *ctx, int slot, size_t bytes, void **out);
 
 // Scratch slots (device-pointer entry points reuse them in stream order; one stream per context at a time):
-//   0 EM scalars, 1-7 host-buffer tally / EM staging, 8 dedup, 9 aggregation, 10 pi, 11 coverage, 12 consensus
+//   0 EM scalars, 1-7 host-buffer tally / EM staging, 8 dedup, 9 aggregation, 10 pi, 11 coverage, 12-13 consensus,
+//   14-15 tally parked units (one per copy stream), 16 per-read exchange
 // Bump allocator over one scratch slot: run the same carve() twice, first with base == nullptr to size it.
 struct Arena {
     uint8_t *base;

@@ -1,0 +1,162 @@
+// Per-read exchange to the barcode owner ("the one exchange"): UMI groups
+// (barcode, umi, gene) may straddle the read ranges the GPUs tally, so before deduplication every rank sends
+// the fixed-size per-read row -- 16 counters, group key, priority fields -- to rank barcode mod world.  The
+// reference has no counterpart (one process reads the whole conversions.csv, conversion.py:529-606); these
+// kernels are the device side of dynast_b200.distributed.exchange_reads:
+//   dyn_owner_partition  stable partition of the local reads by owner (one radix pass over log2(world) bits)
+//                        + per-owner counts = the all-to-all split sizes
+//   dyn_pack_reads       gathers the struct-of-arrays columns of the partitioned reads into 40-byte rows, so the
+//                        exchange is ONE all-to-all of one buffer
+//   dyn_unpack_reads     rows -> columns on the receiving side
+// HBM-bound streaming passes: 38 B of columns in, 40 B out per read (and back).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int kBlock = 256;
+inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+__global__ void owner_kernel(const uint32_t *barcode, long long n, uint32_t world, uint8_t *owner, uint32_t *iota,
+                             unsigned long long *counts) {
+    __shared__ unsigned int local[DYN_MAX_WORLD];
+    for (int i = threadIdx.x; i < DYN_MAX_WORLD; i += blockDim.x) local[i] = 0;
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t o = barcode[i] % world;
+        owner[i] = (uint8_t)o;
+        iota[i] = (uint32_t)i;
+        atomicAdd(&local[o], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)world; i += blockDim.x)
+        if (local[i]) atomicAdd(&counts[i], (unsigned long long)local[i]);
+}
+
+struct alignas(8) ReadRow {     // 40 bytes
+    uint32_t counts[4];
+    unsigned long long umi;
+    uint32_t barcode, gene;
+    int16_t score;
+    uint16_t conv_n;
+    uint8_t strand, transcriptome, pad[2];
+};
+static_assert(sizeof(ReadRow) == DYN_READ_ROW_BYTES, "row layout");
+
+__global__ void pack_kernel(const uint32_t *perm, long long n, const uint4 *counts, const uint32_t *barcode,
+                            const unsigned long long *umi, const uint32_t *gene, const int16_t *score, const uint16_t *conv_n,
+                            const uint8_t *strand, const uint8_t *transcriptome, ReadRow *rows) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long s = perm ? (long long)perm[i] : i;
+    ReadRow r;
+    const uint4 cv = counts[s];
+    r.counts[0] = cv.x; r.counts[1] = cv.y; r.counts[2] = cv.z; r.counts[3] = cv.w;
+    r.umi = umi[s];
+    r.barcode = barcode[s];
+    r.gene = gene[s];
+    r.score = score[s];
+    r.conv_n = conv_n[s];
+    r.strand = strand[s];
+    r.transcriptome = transcriptome ? transcriptome[s] : (uint8_t)1;
+    r.pad[0] = r.pad[1] = 0;
+    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(&r);
+    unsigned long long *o = reinterpret_cast<unsigned long long *>(rows + i);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) o[k] = w[k];
+}
+
+__global__ void unpack_kernel(const ReadRow *rows, long long n, uint4 *counts, uint32_t *barcode, unsigned long long *umi,
+                              uint32_t *gene, int16_t *score, uint16_t *conv_n, uint8_t *strand, uint8_t *transcriptome) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ReadRow r;
+    const unsigned long long *s = reinterpret_cast<const unsigned long long *>(rows + i);
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(&r);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = s[k];
+    counts[i] = make_uint4(r.counts[0], r.counts[1], r.counts[2], r.counts[3]);
+    umi[i] = r.umi;
+    barcode[i] = r.barcode;
+    gene[i] = r.gene;
+    score[i] = r.score;
+    conv_n[i] = r.conv_n;
+    strand[i] = r.strand;
+    transcriptome[i] = r.transcriptome;
+}
+
+}  // namespace
+
+extern "C" int dyn_owner_partition(dyn_ctx_t *ctx, const uint32_t *d_barcode, int64_t n, int world, uint32_t *d_perm,
+                                   uint64_t *d_owner_counts, void *stream) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n >= 0 && n <= 0xffffffffll, "bad n");
+    DYN_ARG(world >= 1 && world <= DYN_MAX_WORLD, "world out of range");
+    DYN_ARG(d_owner_counts != nullptr, "null counts");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DYN_CUDA(cudaMemsetAsync(d_owner_counts, 0, sizeof(uint64_t) * world, st));
+    if (n == 0) return DYN_OK;
+    DYN_ARG(d_barcode && d_perm, "null buffer");
+    int bits = 0;
+    while ((1 << bits) < world) ++bits;
+    size_t temp = 0;
+    DYN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint8_t *)nullptr, (uint8_t *)nullptr,
+                                             (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, bits > 0 ? bits : 1, st));
+    Arena sizing;
+    for (int pass = 0; pass < 2; ++pass) {
+        void *base = nullptr;
+        if (pass == 1) {
+            int rc = dyn_ctx_scratch(ctx, 16, sizing.used + 256, &base);
+            if (rc) return rc;
+        }
+        Arena a(base);
+        uint8_t *owner = a.take<uint8_t>((size_t)n), *owner_sorted = a.take<uint8_t>((size_t)n);
+        uint32_t *iota = a.take<uint32_t>((size_t)n);
+        uint8_t *tmp = a.take<uint8_t>(temp);
+        if (pass == 0) { sizing = a; continue; }
+        const unsigned grid = std::min<unsigned>(grid_for(n), (unsigned)ctx->sm_count * 8);
+        owner_kernel<<<grid, kBlock, 0, st>>>(d_barcode, n, (uint32_t)world, owner, iota,
+                                              reinterpret_cast<unsigned long long *>(d_owner_counts));
+        DYN_CUDA(cudaGetLastError());
+        if (world == 1) {
+            DYN_CUDA(cudaMemcpyAsync(d_perm, iota, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+        } else {
+            DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, temp, owner, owner_sorted, iota, d_perm, (int)n, 0, bits, st));
+        }
+    }
+    return DYN_OK;
+}
+
+extern "C" int dyn_pack_reads(dyn_ctx_t *ctx, const uint32_t *d_perm, int64_t n, const uint8_t *d_counts,
+                              const uint32_t *d_barcode, const uint64_t *d_umi, const uint32_t *d_gene, const int16_t *d_score,
+                              const uint16_t *d_conv_n, const uint8_t *d_strand, const uint8_t *d_transcriptome, void *d_rows,
+                              void *stream) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n >= 0, "negative n");
+    if (n == 0) return DYN_OK;
+    DYN_ARG(d_counts && d_barcode && d_umi && d_gene && d_score && d_conv_n && d_strand && d_rows, "null buffer");
+    DYN_ARG((reinterpret_cast<uintptr_t>(d_counts) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_rows) & 7) == 0, "alignment");
+    pack_kernel<<<grid_for(n), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_perm, n, reinterpret_cast<const uint4 *>(d_counts), d_barcode, reinterpret_cast<const unsigned long long *>(d_umi),
+        d_gene, d_score, d_conv_n, d_strand, d_transcriptome, static_cast<ReadRow *>(d_rows));
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}
+
+extern "C" int dyn_unpack_reads(dyn_ctx_t *ctx, const void *d_rows, int64_t n, uint8_t *d_counts, uint32_t *d_barcode,
+                                uint64_t *d_umi, uint32_t *d_gene, int16_t *d_score, uint16_t *d_conv_n, uint8_t *d_strand,
+                                uint8_t *d_transcriptome, void *stream) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n >= 0, "negative n");
+    if (n == 0) return DYN_OK;
+    DYN_ARG(d_rows && d_counts && d_barcode && d_umi && d_gene && d_score && d_conv_n && d_strand && d_transcriptome, "null buffer");
+    DYN_ARG((reinterpret_cast<uintptr_t>(d_counts) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_rows) & 7) == 0, "alignment");
+    unpack_kernel<<<grid_for(n), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const ReadRow *>(d_rows), n, reinterpret_cast<uint4 *>(d_counts), d_barcode,
+        reinterpret_cast<unsigned long long *>(d_umi), d_gene, d_score, d_conv_n, d_strand, d_transcriptome);
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}

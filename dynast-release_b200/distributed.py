@@ -100,3 +100,24 @@ def exchange_by_owner(owner: torch.Tensor, *columns: torch.Tensor, group=None):
         dist.all_to_all_single(dst, src, output_split_sizes=recv_split, input_split_sizes=send_split, group=group)
         out.append(dst)
     return out
+
+
+def exchange_reads(ctx, barcode, umi, gene, score16, conv_n, strand, counts, world: int, transcriptome=None, group=None):
+    """The per-read exchange before UMI dedup on device tensors, as ONE all-to-all: the local reads
+    are partitioned by owner = barcode % world (dyn_owner_partition), their columns gathered into 40-byte rows
+    (dyn_pack_reads), the rows exchanged (all_to_all_single over NCCL / NVLink), and unpacked on the receiving side
+    (dyn_unpack_reads).  Rows of one source rank keep their order and sources arrive in rank order, so contiguous
+    ascending read ranges stay in global read order -- what the "last row wins" tie rule of dedup needs.
+    Returns the dict of received columns (see pipeline.unpack_reads)."""
+    from . import pipeline
+    perm, owner_counts = pipeline.owner_partition(ctx, barcode, world)
+    rows = pipeline.pack_reads(ctx, perm, counts, barcode, umi, gene, score16, conv_n, strand, transcriptome)
+    if world == 1:
+        return pipeline.unpack_reads(ctx, rows)
+    recv_counts = torch.empty_like(owner_counts)
+    dist.all_to_all_single(recv_counts, owner_counts, group=group)
+    send_split = [int(x) for x in owner_counts.tolist()]
+    recv_split = [int(x) for x in recv_counts.tolist()]
+    got = torch.empty((sum(recv_split), rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    dist.all_to_all_single(got, rows, output_split_sizes=recv_split, input_split_sizes=send_split, group=group)
+    return pipeline.unpack_reads(ctx, got)

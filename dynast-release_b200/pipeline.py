@@ -306,6 +306,44 @@ def kn_csr(ctx: Context, keys, count32, n_rows, n_groups: int):
     return k[:m], n[:m], c[:m], off, total[:n_groups]
 
 
+READ_ROW_BYTES = 40
+
+
+def owner_partition(ctx: Context, barcode: torch.Tensor, world: int):
+    """dyn_owner_partition -> (perm int32 [n] (bit pattern uint32): local reads grouped by barcode % world, stable;
+    counts int64 [world])."""
+    n = barcode.numel()
+    perm = torch.empty(max(n, 1), dtype=torch.int32, device=barcode.device)
+    counts = torch.empty(world, dtype=torch.int64, device=barcode.device)
+    check(ctx.lib.dyn_owner_partition(ctx.handle, ptr(barcode), n, int(world), ptr(perm), ptr(counts), _stream()))
+    return perm[:n], counts
+
+
+def pack_reads(ctx: Context, perm, counts, barcode, umi, gene, score16, conv_n, strand, transcriptome=None):
+    """dyn_pack_reads -> uint8 [n, 40]: one row per read in `perm` order (perm None: as is)."""
+    n = barcode.numel()
+    rows = torch.empty((n, READ_ROW_BYTES), dtype=torch.uint8, device=barcode.device)
+    check(ctx.lib.dyn_pack_reads(ctx.handle, ptr(perm), n, ptr(counts), ptr(barcode), ptr(umi), ptr(gene), ptr(score16),
+                                 ptr(conv_n), ptr(strand), ptr(transcriptome), ptr(rows), _stream()))
+    return rows
+
+
+def unpack_reads(ctx: Context, rows: torch.Tensor):
+    """dyn_unpack_reads -> dict(counts uint8 [n,16], barcode int32, umi int64, gene int32, score int16, conv_n int16
+    (bit pattern uint16), strand uint8, transcriptome uint8)."""
+    n = rows.shape[0]
+    dev = rows.device
+    m = max(n, 1)
+    out = dict(counts=torch.empty((m, 16), dtype=torch.uint8, device=dev), barcode=torch.empty(m, dtype=torch.int32, device=dev),
+               umi=torch.empty(m, dtype=torch.int64, device=dev), gene=torch.empty(m, dtype=torch.int32, device=dev),
+               score=torch.empty(m, dtype=torch.int16, device=dev), conv_n=torch.empty(m, dtype=torch.int16, device=dev),
+               strand=torch.empty(m, dtype=torch.uint8, device=dev), transcriptome=torch.empty(m, dtype=torch.uint8, device=dev))
+    check(ctx.lib.dyn_unpack_reads(ctx.handle, ptr(rows), n, ptr(out['counts']), ptr(out['barcode']), ptr(out['umi']),
+                                   ptr(out['gene']), ptr(out['score']), ptr(out['conv_n']), ptr(out['strand']),
+                                   ptr(out['transcriptome']), _stream()))
+    return {k: v[:n] for k, v in out.items()}
+
+
 def pi_fit(ctx: Context, k, n, count, off, p_e, p_c, max_cells=None):
     """dyn_pi_fit -> (alpha_beta_pi [G,3] float64, status [G] int32)."""
     G = off.numel() - 1
@@ -344,12 +382,16 @@ def consensus(ctx: Context, records: torch.Tensor, item_rec16: torch.Tensor, gro
 # --------------------------------------------------------------------------------------------------
 def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score, strand, n_barcodes: int, n_genes: int,
                       out: TallyBuffers, conversions=('TC',), quality: int = 27, umi_bits: int = 24,
-                      cell_threshold: int = 1000, with_pi: bool = True, timings: Optional[dict] = None):
+                      cell_threshold: int = 1000, with_pi: bool = True, timings: Optional[dict] = None, group=None,
+                      exchange: bool = False):
     """Runs every stage of the path on device tensors (the packed records of one GPU's read range plus the
     interned barcode / umi / gene ids of its reads).  Mirrors count() then estimate(method='alpha') of the
     reference: count_conversions (count.py:306) -> estimate_p_e (estimate.py:197-234) -> aggregate_counts
     (:243-255) -> estimate_p_c (:259-275) -> estimate_pi per barcode + estimate_alpha (:328-395).
-    Returns a dict of device tensors.  `timings`, if given, receives per-stage milliseconds (CUDA events)."""
+    Returns a dict of device tensors.  `timings`, if given, receives per-stage milliseconds (CUDA events).
+    exchange=True (multi-GPU, read-range sharding): `barcode` holds GLOBAL barcode ids and n_barcodes the global
+    count; after the tally every read's row goes to rank barcode % world (distributed.exchange_reads) and the rest
+    of the path runs on the barcodes this rank owns (local id = global id // world)."""
     dev = records.device
     stream = torch.cuda.current_stream()
     marks = []
@@ -363,19 +405,33 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
     mark('start')
     tally_reads(ctx, records, rec_off, out, quality=quality, emit_conv=True)
     mark('tally')
+    counts, conv_n = out.counts, out.conv_n
+    score16 = score.to(torch.int16)
+    transcriptome = None
+    if exchange:
+        from . import distributed
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        got = distributed.exchange_reads(ctx, barcode, umi, gene, score16, conv_n, strand, counts, world, group=group)
+        counts, conv_n, score16, strand, umi, gene = got['counts'], got['conv_n'], got['score'], got['strand'], got['umi'], got['gene']
+        transcriptome = got['transcriptome']
+        barcode = torch.div(got['barcode'], world, rounding_mode='floor').to(torch.int32)
+        n_barcodes = (n_barcodes + world - 1) // world
+        mark('exchange')
     gene_bits = _bits(max(n_genes - 1, 0))
     bc_bits = _bits(max(n_barcodes - 1, 0))
     key = (barcode.to(torch.int64) << (umi_bits + gene_bits)) | ((umi & ((1 << umi_bits) - 1)) << gene_bits) | gene.to(torch.int64)
     n = barcode.numel()
-    transcriptome = torch.ones(n, dtype=torch.uint8, device=dev)
-    sel = dedup(ctx, key, out.counts, strand, transcriptome, score.to(torch.int16), out.conv_n, barcode, n_barcodes,
+    if transcriptome is None:
+        transcriptome = torch.ones(n, dtype=torch.uint8, device=dev)
+    sel = dedup(ctx, key, counts, strand, transcriptome, score16, conv_n, barcode, n_barcodes,
                 conversions=conversions, use_conversions=True, key_lo_bits=bc_bits + umi_bits + gene_bits)
     mark('dedup')
     pe_cols = [c for c in CONVERSION_COLUMNS if c[0] not in {x[0] for x in conversions}]
-    sums, n_reads, n_with = group_sums(ctx, out.counts, strand, barcode, n_barcodes, sel=sel, conversions=conversions)
+    sums, n_reads, n_with = group_sums(ctx, counts, strand, barcode, n_barcodes, sel=sel, conversions=conversions)
     rates, p_e = rates_pe(ctx, sums, pe_conversions=pe_cols)
     mark('p_e')
-    rows = aggregate_kn(ctx, out.counts, strand, barcode, None, n_barcodes, 0, conversions, sel=sel, first_appearance=False)
+    rows = aggregate_kn(ctx, counts, strand, barcode, None, n_barcodes, 0, conversions, sel=sel, first_appearance=False)
     k, nn, c, off, total = kn_csr(ctx, rows['keys'], rows['count32'], rows['n_rows'], n_barcodes)
     mark('aggregate')
     # estimate_p_c skips barcodes below the read threshold (p_c.py:215-217): give them an empty histogram
@@ -388,7 +444,7 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
     em_status = torch.where(keep, em_status, torch.full_like(em_status, -1))
     mark('em')
     res = dict(selected=sel, sums=sums, rates=rates, p_e=p_e, p_c=p_c, em_status=em_status, em_iters=iters, n_reads=n_reads,
-               n_with=n_with, hist=(k, nn, c, off))
+               n_with=n_with, hist=(k, nn, c, off), n_local_reads=n)
     if with_pi:
         ok = em_status == 0
         pc_safe = torch.where(ok, p_c, torch.full_like(p_c, 0.5))

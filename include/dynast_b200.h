@@ -298,6 +298,28 @@ int dyn_unique_counts(dyn_ctx_t *ctx, const uint64_t *d_keys, int64_t n_keys, ui
                       uint32_t *d_out_first, int64_t *d_n_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Per-read exchange to the barcode owner (multi-GPU).  The reference runs one process over the whole
+ * conversions.csv (conversion.py:529-606); with read-range sharding a UMI group can straddle ranks, so before
+ * dyn_dedup_umi every rank sends its reads' fixed-size rows to rank barcode % world.
+ *   dyn_owner_partition: d_perm = the local read indices grouped by owner (stable), d_owner_counts[world] = reads
+ *                        per owner (the all-to-all split sizes)
+ *   dyn_pack_reads:      row i = the columns of read d_perm[i] (d_perm NULL: read i), DYN_READ_ROW_BYTES each:
+ *                        counts[16] | umi u64 | barcode u32 | gene u32 | score i16 | conv_n u16 | strand u8 |
+ *                        transcriptome u8 | 2 pad
+ *   dyn_unpack_reads:    the inverse on the receiving side
+ * ------------------------------------------------------------------------------------------------ */
+#define DYN_MAX_WORLD 64
+#define DYN_READ_ROW_BYTES 40
+int dyn_owner_partition(dyn_ctx_t *ctx, const uint32_t *d_barcode, int64_t n, int world, uint32_t *d_perm,
+                        uint64_t *d_owner_counts, void *stream);
+int dyn_pack_reads(dyn_ctx_t *ctx, const uint32_t *d_perm, int64_t n, const uint8_t *d_counts, const uint32_t *d_barcode,
+                   const uint64_t *d_umi, const uint32_t *d_gene, const int16_t *d_score, const uint16_t *d_conv_n,
+                   const uint8_t *d_strand, const uint8_t *d_transcriptome, void *d_rows, void *stream);
+int dyn_unpack_reads(dyn_ctx_t *ctx, const void *d_rows, int64_t n, uint8_t *d_counts, uint32_t *d_barcode, uint64_t *d_umi,
+                     uint32_t *d_gene, int16_t *d_score, uint16_t *d_conv_n, uint8_t *d_strand, uint8_t *d_transcriptome,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host BAM ingest (what the reference gets from pysam, bam.py:253-312): BGZF inflate on n_threads host
  * threads, read filter (bam.py:173-174, 242-248, 286-292), mate pairing (bam.py:307-312), packing into the
  * record layout above (page-locked memory when available).  The BAM must be coordinate sorted.  tags may be

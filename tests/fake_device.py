@@ -178,6 +178,37 @@ def aggregate_kn(ctx, counts, strand, group, gene, n_groups, n_genes, conversion
                 count=t([rows[x][0] for x in keys]), first=t([rows[x][1] for x in keys]))
 
 
+_ROW = np.dtype([('counts', 'u1', 16), ('umi', '<i8'), ('barcode', '<i4'), ('gene', '<i4'), ('score', '<i2'), ('conv_n', '<i2'),
+                 ('strand', 'u1'), ('transcriptome', 'u1'), ('pad', 'u1', 2)])
+assert _ROW.itemsize == 40
+
+
+def owner_partition(ctx, barcode, world):
+    """numpy stand-in for dyn_owner_partition."""
+    owner = _np(barcode).astype(np.int64) % world
+    perm = np.argsort(owner, kind='stable').astype(np.int32)
+    return torch.from_numpy(perm), torch.from_numpy(np.bincount(owner, minlength=world).astype(np.int64))
+
+
+def pack_reads(ctx, perm, counts, barcode, umi, gene, score16, conv_n, strand, transcriptome=None):
+    """numpy stand-in for dyn_pack_reads (same 40-byte row layout)."""
+    n = barcode.numel()
+    idx = _np(perm).astype(np.int64) if perm is not None else np.arange(n)
+    rows = np.zeros(n, dtype=_ROW)
+    rows['counts'] = _np(counts)[idx]
+    rows['umi'], rows['barcode'], rows['gene'] = _np(umi)[idx], _np(barcode)[idx], _np(gene)[idx]
+    rows['score'], rows['conv_n'], rows['strand'] = _np(score16)[idx], _np(conv_n)[idx], _np(strand)[idx]
+    rows['transcriptome'] = _np(transcriptome)[idx] if transcriptome is not None else 1
+    return torch.from_numpy(rows.view(np.uint8).reshape(n, 40))
+
+
+def unpack_reads(ctx, rows):
+    """numpy stand-in for dyn_unpack_reads."""
+    r = np.ascontiguousarray(_np(rows)).reshape(-1).view(_ROW)
+    return {k: torch.from_numpy(np.ascontiguousarray(r[k])) for k in ('counts', 'barcode', 'umi', 'gene', 'score', 'conv_n', 'strand',
+                                                                      'transcriptome')}
+
+
 def install(monkeypatch):
     """Route the operator layer to the numpy stand-ins (torch CPU tensors)."""
     from dynast_b200 import _lib, device, pipeline
@@ -191,7 +222,8 @@ def install(monkeypatch):
     monkeypatch.setattr(_lib, 'current_context', lambda: _Ctx())
     monkeypatch.setattr(_lib, 'current_torch_device', lambda: torch.device('cpu'))
     monkeypatch.setattr(_lib, 'current_device_index', lambda: 0)
-    for name in ('count_records', 'complement_counts', 'plan_splits', 'dedup', 'group_sums', 'rates_pe', 'alpha', 'aggregate_kn'):
+    for name in ('count_records', 'complement_counts', 'plan_splits', 'dedup', 'group_sums', 'rates_pe', 'alpha', 'aggregate_kn',
+                 'owner_partition', 'pack_reads', 'unpack_reads'):
         monkeypatch.setattr(pipeline, name, globals()[name])
 
     def em_pc_host(k, n, count, off, p_e, nasc=False, device=0):

@@ -59,6 +59,26 @@ def _worker(rank, world, port, n_barcodes, out_dir):
         idx = got_payload[src == r, 1]
         assert (idx[1:] > idx[:-1]).all()
     np.save(os.path.join(out_dir, f'xchg{rank}.npy'), got_payload.numpy())
+    # the packed form of the same exchange (distributed.exchange_reads; numpy stand-ins for the three kernels)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import fake_device
+    from dynast_b200 import pipeline
+    for name in ('owner_partition', 'pack_reads', 'unpack_reads'):
+        setattr(pipeline, name, getattr(fake_device, name))
+    m = len(bc)
+    cols = dict(barcode=bc.to(torch.int32), umi=torch.arange(m, dtype=torch.int64) + 10**9 * rank,
+                gene=torch.randint(0, 500, (m,), generator=g).to(torch.int32),
+                score=torch.randint(-50, 90, (m,), generator=g).to(torch.int16),
+                conv_n=torch.randint(0, 9, (m,), generator=g).to(torch.int16),
+                strand=torch.randint(0, 2, (m,), generator=g).to(torch.uint8))
+    got = distributed.exchange_reads(None, cols['barcode'], cols['umi'], cols['gene'], cols['score'], cols['conv_n'],
+                                     cols['strand'], counts, world)
+    assert (got['barcode'] % world == rank).all() and (got['transcriptome'] == 1).all()
+    assert torch.equal(got['counts'], got_counts) and torch.equal(got['barcode'].to(torch.int64), got_payload[:, 0])
+    mine = got['umi'] // 10**9 == rank          # rows that stayed: columns still belong together
+    keep = cols['barcode'] % world == rank
+    for name in ('gene', 'score', 'conv_n', 'strand'):
+        assert torch.equal(got[name][mine], cols[name][keep])
     lo, hi = distributed.read_range(1001, rank, world)
     assert (lo, hi) == ((0, 501) if rank == 0 else (501, 1001))
     dist.destroy_process_group()

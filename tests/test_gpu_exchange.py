@@ -1,0 +1,102 @@
+"""GPU: the per-read exchange before UMI dedup.  Kernels against numpy on one GPU; the whole
+multi-GPU path (read-range sharding -> tally -> all-to-all to the barcode owner -> dedup -> ... -> EM) against the
+single-GPU path on the same reads when two GPUs are present."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('n,world', [(0, 2), (1, 1), (1000, 3), (300000, 8), (70001, 64)])
+def test_partition_pack_unpack(gpu_ctx, n, world):
+    import fake_device
+    from dynast_b200 import pipeline
+    from dynast_b200.pipeline import Context
+    ctx = Context.get(0)
+    g = torch.Generator().manual_seed(n + world)
+    cols = dict(barcode=torch.randint(0, 5000, (n,), generator=g).to(torch.int32),
+                umi=torch.randint(0, 1 << 40, (n,), generator=g),
+                gene=torch.randint(0, 30000, (n,), generator=g).to(torch.int32),
+                score=torch.randint(-300, 300, (n,), generator=g).to(torch.int16),
+                conv_n=torch.randint(0, 40000, (n,), generator=g).to(torch.int16),
+                strand=torch.randint(0, 2, (n,), generator=g).to(torch.uint8),
+                transcriptome=torch.randint(0, 2, (n,), generator=g).to(torch.uint8),
+                counts=torch.randint(0, 256, (n, 16), generator=g).to(torch.uint8))
+    d = {k: v.cuda() for k, v in cols.items()}
+    perm, cnt = pipeline.owner_partition(ctx, d['barcode'], world)
+    want_perm, want_cnt = fake_device.owner_partition(None, cols['barcode'], world)
+    assert torch.equal(cnt.cpu(), want_cnt)
+    assert torch.equal(perm.cpu(), want_perm)
+    rows = pipeline.pack_reads(ctx, perm, d['counts'], d['barcode'], d['umi'], d['gene'], d['score'], d['conv_n'], d['strand'],
+                               d['transcriptome'])
+    want_rows = fake_device.pack_reads(None, want_perm, cols['counts'], cols['barcode'], cols['umi'], cols['gene'], cols['score'],
+                                       cols['conv_n'], cols['strand'], cols['transcriptome'])
+    assert torch.equal(rows.cpu(), want_rows)
+    back = pipeline.unpack_reads(ctx, rows)
+    for k, v in back.items():
+        assert torch.equal(v.cpu(), cols[k][want_perm.long()]), k
+    # perm None = identity, transcriptome None = all ones
+    rows = pipeline.pack_reads(ctx, None, d['counts'], d['barcode'], d['umi'], d['gene'], d['score'], d['conv_n'], d['strand'])
+    back = pipeline.unpack_reads(ctx, rows)
+    assert torch.equal(back['umi'].cpu(), cols['umi']) and bool((back['transcriptome'] == 1).all())
+
+
+def _run(rank, world, port, n_reads, n_barcodes, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import conftest  # noqa: F401  (package alias)
+    import torch.distributed as dist
+    from dynast_b200 import distributed, pipeline
+    torch.cuda.set_device(rank)
+    if world > 1:
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    ctx = pipeline.Context.get(rank)
+    b = pipeline.SynthBatch(n_reads, seed=77, n_barcodes=n_barcodes, n_genes=300, device=rank, reads_per_umi=3.0)
+    lo, hi = distributed.read_range(n_reads, rank, world)
+    off = b.rec_off[lo:hi + 1].to(torch.int64) & 0xffffffff
+    rec = b.records[int(off[0]) * 16:int(off[-1]) * 16]
+    rec_off = (off - off[0]).to(torch.int32)
+    out = pipeline.TallyBuffers(hi - lo, 4 * (hi - lo) + 1024, device=rank)
+    res = pipeline.count_to_estimate(ctx, rec, rec_off, b.barcode[lo:hi], b.umi[lo:hi], b.gene[lo:hi], b.score[lo:hi],
+                                     b.strand[lo:hi], n_barcodes, b.n_genes, out, cell_threshold=50, with_pi=False,
+                                     exchange=world > 1)
+    k, n, c, off_h = res['hist']
+    np.savez(os.path.join(out_dir, f'r{world}_{rank}.npz'), p_e=res['p_e'].cpu().numpy(), p_c=res['p_c'].cpu().numpy(),
+             st=res['em_status'].cpu().numpy(), n_reads=res['n_reads'].cpu().numpy(), k=k.cpu().numpy(), n=n.cpu().numpy(),
+             c=c.cpu().numpy(), off=off_h.cpu().numpy(), n_sel=int(res['selected'].numel()), n_local=int(res['n_local_reads']))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_gpu_path_equals_one_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    n_reads, n_barcodes = 400000, 101
+    port = 29600 + (os.getpid() % 2000)
+    mp.spawn(_run, args=(1, port, n_reads, n_barcodes, str(tmp_path)), nprocs=1, join=True)
+    mp.spawn(_run, args=(2, port + 1, n_reads, n_barcodes, str(tmp_path)), nprocs=2, join=True)
+    one = np.load(tmp_path / 'r1_0.npz')
+    two = [np.load(tmp_path / f'r2_{r}.npz') for r in range(2)]
+    assert sum(int(t['n_local']) for t in two) == n_reads
+    assert sum(int(t['n_sel']) for t in two) == int(one['n_sel'])
+    checked = 0
+    for b in range(n_barcodes):
+        t, j = two[b % 2], b // 2
+        assert one['n_reads'][b] == t['n_reads'][j]
+        assert one['p_e'][b] == t['p_e'][j] or (np.isnan(one['p_e'][b]) and np.isnan(t['p_e'][j]))
+        a0, a1 = one['off'][b], one['off'][b + 1]
+        b0, b1 = t['off'][j], t['off'][j + 1]
+        assert np.array_equal(one['k'][a0:a1], t['k'][b0:b1]) and np.array_equal(one['n'][a0:a1], t['n'][b0:b1])
+        assert np.array_equal(one['c'][a0:a1], t['c'][b0:b1])
+        assert one['st'][b] == t['st'][j]
+        if one['st'][b] == 0:
+            assert one['p_c'][b] == t['p_c'][j]
+            checked += 1
+    assert checked > 20
