@@ -20,9 +20,10 @@
 // comes from many barcodes resident per SM.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 
-constexpr int kEmThreads = 64;
 constexpr int kMaxFactorialK = 66;   // k! == 0 (mod 2^64) for k >= 66 -> ZeroDivisionError in the reference
 
 struct EmParams {
@@ -56,7 +57,11 @@ __global__ void em_coef_kernel(double *coef, int K, int N) {
 }
 
 // per-barcode shape discovery: K = max k + 1, N = max n + 1; also global maxima
-__global__ void em_shape_kernel(const int32_t *k, const int32_t *n, const long long *off, long long B, int *maxima) {
+constexpr int kEmClasses = 3;
+__device__ __host__ inline int em_class_of(long long cells, int c0, int c1) { return cells <= c0 ? 0 : (cells <= c1 ? 1 : 2); }
+
+__global__ void em_shape_kernel(const int32_t *k, const int32_t *n, const long long *off, long long B, int *maxima, int c0,
+                                int c1) {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int K = 0, N = 0;
     if (b < B) {
@@ -68,6 +73,11 @@ __global__ void em_shape_kernel(const int32_t *k, const int32_t *n, const long l
     // warp reduce then atomics
     long long cells = (long long)K * N;
     int c = cells > 0x7fffffffLL ? 0x7fffffff : (int)cells;
+    if (b < B && K > 0) {       // per size class (few barcodes share a value: contention is not an issue next to the EM)
+        const int cls = em_class_of(cells, c0, c1);
+        atomicMax(maxima + 4 + 2 * cls, K);
+        atomicMax(maxima + 5 + 2 * cls, N);
+    }
     for (int d = 16; d; d >>= 1) {
         K = max(K, __shfl_xor_sync(0xffffffffu, K, d));
         N = max(N, __shfl_xor_sync(0xffffffffu, N, d));
@@ -104,8 +114,15 @@ struct EmShared {
     int done;
 };
 
-template <bool NASC>
-__global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
+// barrier of the CTA: a one-warp CTA (the small size class) never touches the hardware barrier
+template <int THREADS>
+__device__ __forceinline__ void cta_sync() {
+    if (THREADS == 32) __syncwarp(); else __syncthreads();
+}
+
+template <bool NASC, int THREADS>
+__global__ void __launch_bounds__(THREADS) em_kernel(const EmParams p) {
+    constexpr int kEmThreads = THREADS;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     // layout (capacities from p.max_cells / p.max_K / p.max_N)
     float *v = reinterpret_cast<float *>(smem_raw);                         // [max_cells]
@@ -116,14 +133,15 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
     int *cols = reinterpret_cast<int *>(den_n + p.max_N);                   // [max_N] columns with masked cells
     uint8_t *mask = reinterpret_cast<uint8_t *>(cols + p.max_N);            // [max_cells]
     __shared__ EmShared sh;
+    __shared__ __align__(16) double2 s_prod[32];     // M-step staging: one chunk of 32 (k, n) product pairs
     __shared__ unsigned long long s_work;
     __shared__ int s_scan[kEmThreads / 32];
 
     const int tid = threadIdx.x;
     for (;;) {
-        __syncthreads();
+        cta_sync<THREADS>();
         if (tid == 0) s_work = atomicAdd(p.work_counter, 1ull);
-        __syncthreads();
+        cta_sync<THREADS>();
         const long long b = (long long)s_work;
         if (b >= p.n_barcodes) break;
 
@@ -140,15 +158,15 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
             N = max(N, __shfl_xor_sync(0xffffffffu, N, d));
         }
         if ((tid & 31) == 0) { s_scan[tid >> 5] = K; }
-        __syncthreads();
+        cta_sync<THREADS>();
         if (tid == 0) {
             int kk = 0;
             for (int w = 0; w < kEmThreads / 32; ++w) kk = max(kk, s_scan[w]);
             sh.K = kk;
         }
-        __syncthreads();
+        cta_sync<THREADS>();
         if ((tid & 31) == 0) { s_scan[tid >> 5] = N; }
-        __syncthreads();
+        cta_sync<THREADS>();
         if (tid == 0) {
             int nn = 0;
             for (int w = 0; w < kEmThreads / 32; ++w) nn = max(nn, s_scan[w]);
@@ -156,7 +174,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
             sh.fail = 0;
             sh.done = 0;
         }
-        __syncthreads();
+        cta_sync<THREADS>();
         K = sh.K; N = sh.N;
         const int KN = K * N;
         if (KN <= p.cls_lo || KN > p.cls_hi) continue;      // another launch's size class
@@ -174,7 +192,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
         }
         // ---- dense histogram (duplicates summed, p_c.py:219)
         for (int i = tid; i < KN; i += kEmThreads) { cnt[i] = 0; mask[i] = 0; }
-        __syncthreads();
+        cta_sync<THREADS>();
         for (long long i = t0 + tid; i < t1; i += kEmThreads) {
             const long long c = p.count[i];
             if (c < 0 || c > 0x7fffffffLL) sh.fail = DYN_EM_UNSUPPORTED;
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
             for (int i = tid; i < K + N - 1; i += kEmThreads) powq[i] = ipow(q, i - (K - 1), ok);
             if (!ok) sh.fail = DYN_EM_ZERODIV;
         }
-        __syncthreads();
+        cta_sync<THREADS>();
         // ---- mask (p_c.py:138-143 / 64-68): one thread per column, suffix sums from the top row down
         for (int n = tid; n < N; n += kEmThreads) {
             long long s = 0;
@@ -205,9 +223,9 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
             }
             cols[n] = any ? 1 : 0;
         }
-        __syncthreads();
+        cta_sync<THREADS>();
         for (int i = tid; i < KN; i += kEmThreads) v[i] = (float)cnt[i];   // p_c.py:148
-        __syncthreads();
+        cta_sync<THREADS>();
         // ---- active list: row-major indices of cells that can ever be non-zero (non-zero or masked);
         //      compacted list of columns owning masked cells.  Both by thread 0..: sizes are tiny.
         if (tid == 0) {
@@ -224,7 +242,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
             sh.bis_r = 1.0;
             sh.bis_l = 0.0;
         }
-        __syncthreads();
+        cta_sync<THREADS>();
         const int nact = sh.nact, ncols = sh.ncols;
         const uint32_t *act = cnt;   // reused as the active list
 
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                 for (int i = tid; i < K + N - 1; i += kEmThreads) powq[i] = ipow(q, i - (K - 1), ok);
                 if (!ok) sh.fail = DYN_EM_ZERODIV;
             }
-            __syncthreads();
+            cta_sync<THREADS>();
             // ---- E step.  Unmasked cells never change, so (non-NASC) every masked cell can be updated
             //      independently: first one thread per column for the denominators, then one thread per masked
             //      cell for its numerator -- a column full of masked cells (k up to 30 at n = 150) no longer
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                             den = __dadd_rn(den, __dmul_rn(__dmul_rn(cf[kp * p.coef_N], powp[kp]), powq[n - kp + K - 1]));
                     den_n[n] = den;
                 }
-                __syncthreads();
+                cta_sync<THREADS>();
                 for (int i = tid; i < nact; i += kEmThreads) {
                     const uint32_t a = act[i];
                     const int k = (int)(a >> 16), n = (int)(a & 0xffffu);
@@ -291,16 +309,17 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                     }
                 }
             }
-            __syncthreads();
+            cta_sync<THREADS>();
             // ---- M step: two sequential sums in the reference's cell order (row-major; cells that are zero for
             //      good are skipped, x + 0 == x exactly).  The sums must stay sequential (float32, p_c.py:162-165:
             //      reordering moves p_c by ~1e-6), but the loads and products need not: warp 0 takes 32 active cells
             //      at a time, every lane loads and multiplies one cell, then the 32 products are folded into the
-            //      running sums in order through shuffles -- the dependency chain is one add per cell.
+            //      running sums in order out of a 32-entry shared-memory buffer -- the dependency chain is one add per cell.
             if (tid < 32) {
                 if (!NASC) {
                     // numba: (new_values * arange).sum() == float32 products, float32 sequential sum
                     float sk = 0.0f, sn = 0.0f;
+                    float2 *prod = reinterpret_cast<float2 *>(s_prod);
                     for (int base = 0; base < nact; base += 32) {
                         const int i = base + tid;
                         float pk = 0.0f, pn = 0.0f;
@@ -311,12 +330,20 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                             pk = __fmul_rn(x, (float)kk);
                             pn = __fmul_rn(x, (float)nn);
                         }
-                        const int cnt32 = min(32, nact - base);
-#pragma unroll 8
-                        for (int j = 0; j < cnt32; ++j) {
-                            sk = __fadd_rn(sk, __shfl_sync(0xffffffffu, pk, j));
-                            sn = __fadd_rn(sn, __shfl_sync(0xffffffffu, pn, j));
+                        // the 32 product pairs go through shared memory: one broadcast 128-bit load feeds four
+                        // adds of the two chains (a shuffle per add before).  Entries past the end are +0: x + 0 == x.
+                        prod[tid] = make_float2(pk, pn);
+                        __syncwarp();
+                        const int groups = (min(32, nact - base) + 7) >> 3;
+                        for (int g = 0; g < groups; ++g) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 q = reinterpret_cast<const float4 *>(prod)[g * 4 + j];
+                                sk = __fadd_rn(sk, q.x); sn = __fadd_rn(sn, q.y);
+                                sk = __fadd_rn(sk, q.z); sn = __fadd_rn(sn, q.w);
+                            }
                         }
+                        __syncwarp();
                     }
                     if (tid == 0) {
                         const double prev = sh.p_c;
@@ -327,6 +354,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                     }
                 } else {
                     double sk = 0.0, sn = 0.0;
+                    double2 *prod = s_prod;
                     for (int base = 0; base < nact; base += 32) {
                         const int i = base + tid;
                         double pk = 0.0, pn = 0.0;
@@ -337,12 +365,16 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                             pk = __dmul_rn((double)kk, x);
                             pn = __dmul_rn((double)nn, x);
                         }
+                        prod[tid] = make_double2(pk, pn);
+                        __syncwarp();
                         const int cnt32 = min(32, nact - base);
 #pragma unroll 8
                         for (int j = 0; j < cnt32; ++j) {
-                            sk = __dadd_rn(sk, __shfl_sync(0xffffffffu, pk, j));
-                            sn = __dadd_rn(sn, __shfl_sync(0xffffffffu, pn, j));
+                            const double2 q = prod[j];
+                            sk = __dadd_rn(sk, q.x);
+                            sn = __dadd_rn(sn, q.y);
                         }
+                        __syncwarp();
                     }
                     if (tid == 0) {
                         const double prev = sh.p_c;
@@ -355,7 +387,7 @@ __global__ void __launch_bounds__(kEmThreads) em_kernel(const EmParams p) {
                     }
                 }
             }
-            __syncthreads();
+            cta_sync<THREADS>();
         }
         if (tid == 0) {
             int st = sh.fail;
@@ -387,17 +419,19 @@ extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n,
     DYN_ARG(d_off && d_p_e && d_p_c && d_em_status, "null buffer");   // triplet pointers may be NULL when every barcode is empty
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-    // shape discovery (one small kernel + a 12-byte read back: the only synchronisation of this call)
+    // shape discovery (one small kernel + a 40-byte read back: the only synchronisation of this call).
+    // Size classes by dense cells K * N: <= kCells0 (one warp per barcode), <= kCells1 (two warps), rest (eight warps).
+    const int kCells0 = 512, kCells1 = 2048;
     void *scr = nullptr;
-    int rc = dyn_ctx_scratch(ctx, 0, 64, &scr);
+    int rc = dyn_ctx_scratch(ctx, 0, 128, &scr);
     if (rc) return rc;
     int *d_max = static_cast<int *>(scr);
-    unsigned long long *d_work = reinterpret_cast<unsigned long long *>(d_max + 4);
-    DYN_CUDA(cudaMemsetAsync(scr, 0, 64, stream));
+    unsigned long long *d_work = reinterpret_cast<unsigned long long *>(d_max + 16);
+    DYN_CUDA(cudaMemsetAsync(scr, 0, 128, stream));
     em_shape_kernel<<<(unsigned)((n_barcodes + 127) / 128), 128, 0, stream>>>(
-        d_k, d_n, reinterpret_cast<const long long *>(d_off), n_barcodes, d_max);
+        d_k, d_n, reinterpret_cast<const long long *>(d_off), n_barcodes, d_max, kCells0, kCells1);
     DYN_CUDA(cudaGetLastError());
-    int h_max[3];
+    int h_max[10];
     DYN_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaStreamSynchronize(stream));
     int max_K = h_max[0] < 1 ? 1 : h_max[0], max_N = h_max[1] < 1 ? 1 : h_max[1];
@@ -430,29 +464,39 @@ extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n,
     p.n_barcodes = n_barcodes;
     p.p_e = d_p_e; p.p_c = d_p_c; p.status = d_em_status; p.iters = d_iters;
     p.coef = ctx->em_coef; p.coef_K = ctx->em_coef_K; p.coef_N = ctx->em_coef_N;
-    p.max_K = max_K; p.max_N = max_N;
 
     // The kernel is latency-bound per barcode (a few dependent fp64 / fp32 chains per iteration), so throughput
     // comes from resident barcodes per SM, and those are limited by the dense shared-memory layout.  One rare
     // large histogram (k = 30, n = 150 -> 4 681 cells, 45 KB) would size every CTA: barcodes are therefore run in
-    // two size classes, <= kSmallCells cells with a small layout (many CTAs per SM) and the rest with the full one.
-    const int kSmallCells = 1024;
-    const int n_classes = max_cells > kSmallCells ? 2 : 1;
-    auto kern = nasc ? em_kernel<true> : em_kernel<false>;
-    for (int c = 0; c < n_classes; ++c) {
-        const int cap = (n_classes == 2 && c == 0) ? kSmallCells : (int)max_cells;
-        p.max_cells = cap;
-        p.cls_lo = (n_classes == 2 && c == 1) ? kSmallCells : -1;
-        p.cls_hi = (n_classes == 2 && c == 0) ? kSmallCells : 0x7fffffff;
+    // three size classes, each with a layout (cells, pow-table lengths) sized by its own largest member:
+    //   <= 512 cells   one warp per barcode -- no CTA barrier at all, up to 32 barcodes per SM;
+    //   <= 2048 cells  two warps;
+    //   larger         eight warps: the E step is the long part there.
+    // Every launch walks all barcodes (an atomic counter hands them out) and skips the other classes.
+    for (int c = 0; c < kEmClasses; ++c) {
+        int cls_K = h_max[4 + 2 * c], cls_N = h_max[5 + 2 * c];
+        if (cls_K < 1) continue;                                   // nobody in this class
+        if (cls_K > kMaxFactorialK) cls_K = kMaxFactorialK;
+        long long cap = c == 0 ? kCells0 : (c == 1 ? kCells1 : max_cells);
+        cap = std::min<long long>(cap, std::min<long long>(max_cells, (long long)cls_K * cls_N));
+        p.max_cells = (int)cap;
+        p.max_K = cls_K; p.max_N = cls_N;
+        p.cls_lo = c == 0 ? -1 : (c == 1 ? kCells0 : kCells1);
+        p.cls_hi = c == 0 ? kCells0 : (c == 1 ? kCells1 : 0x7fffffff);
         p.work_counter = d_work + c;
-        const size_t smem = em_smem_bytes(cap, max_K, max_N);
+        const size_t smem = em_smem_bytes((int)cap, cls_K, cls_N);
+        const int threads = c == 0 ? 32 : (c == 1 ? 64 : 256);
+        void (*kern)(const EmParams) =
+            c == 0 ? (nasc ? em_kernel<true, 32> : em_kernel<false, 32>)
+                   : (c == 1 ? (nasc ? em_kernel<true, 64> : em_kernel<false, 64>)
+                             : (nasc ? em_kernel<true, 256> : em_kernel<false, 256>));
         DYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEmThreads, smem));
+        DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         if (per_sm < 1) per_sm = 1;
         long long grid = (long long)ctx->sm_count * per_sm;
         if (grid > n_barcodes) grid = n_barcodes;
-        kern<<<(unsigned)grid, kEmThreads, smem, stream>>>(p);
+        kern<<<(unsigned)grid, threads, smem, stream>>>(p);
         DYN_CUDA(cudaGetLastError());
     }
     return DYN_OK;
