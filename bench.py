@@ -446,6 +446,8 @@ def main():
             return p_c_, st_
 
         def em_step():
+            if dist is None:      # one GPU: the CSR histograms go straight to the kernel, there is nothing to exchange
+                return em_fn(k, n, c, off, pe)
             return distributed.distributed_p_c(rows, pe_global, n_global, em_fn)
 
         for _ in range(2):
