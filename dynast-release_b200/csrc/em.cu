@@ -493,7 +493,8 @@ extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n,
     // class is issue-bound, 36.4 ms against 35.3 ms back to back for the C4 sweep.)
     for (int c = kEmClasses - 1; c >= 0; --c) {
         int cls_K = h_max[4 + 2 * c], cls_N = h_max[5 + 2 * c];
-        if (cls_K < 1) continue;                                   // nobody in this class
+        if (cls_K < 1 && c > 0) continue;                          // nobody in this class
+        if (cls_K < 1) cls_K = cls_N = 1;                          // class 0 also reports the barcodes without reads
         if (cls_K > kMaxFactorialK) cls_K = kMaxFactorialK;
         long long cap = c == 0 ? kCells0 : (c == 1 ? kCells1 : max_cells);
         cap = std::min<long long>(cap, std::min<long long>(max_cells, (long long)cls_K * cls_N));
