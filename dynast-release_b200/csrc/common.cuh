@@ -46,7 +46,7 @@ int dyn_ctx_scratch(dyn_ctx *ctx, int slot, size_t bytes, void **out);
 
 // Scratch slots (device-pointer entry points reuse them in stream order; one stream per context at a time):
 //   0 EM scalars, 1-7 host-buffer tally / EM staging, 8 dedup, 9 aggregation, 10 pi, 11 coverage, 12-13 consensus,
-//   14-15 tally parked units (one per copy stream), 16 per-read exchange
+//   14-15 tally parked units (one per copy stream), 16 per-read exchange, 17 consensus sorted path
 // Bump allocator over one scratch slot: run the same carve() twice, first with base == nullptr to size it.
 struct Arena {
     uint8_t *base;

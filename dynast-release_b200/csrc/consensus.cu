@@ -4,7 +4,9 @@
 // get_aligned_pairs of every read plus a Python loop over every reference position of the group's span,
 // run in worker processes fed with SAM strings).
 //
-// On the device this is the sort / segmented-reduce the north star names:
+// Groups of at most 256 reads that touch at most 32 blocks of 32 reference positions take the DIRECT path: one
+// warp per group accumulates those blocks in shared memory and emits the cells (direct_kernel) -- no tuples, no
+// sort.  The rest (very deep or very scattered groups) is the sort / segmented-reduce the north star names:
 //   1. expand   one warp per member read (lanes over the aligned offsets and the deleted-base tokens, coalesced
 //               writes) emits one tuple per aligned or deleted reference base: key = (group << 32 | reference position), value = (Phred, read
 //               base, reference base, deletion flag).  Bases the reference skips (reference N, read N,
@@ -23,6 +25,8 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+
+#include <algorithm>
 #include "walker.cuh"
 
 namespace {
@@ -45,7 +49,7 @@ __device__ __forceinline__ long long group_of(const long long *group_off, long l
 
 __global__ void size_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
                             long long n_items, unsigned long long *tuple_cnt, uint32_t *g_left, uint32_t *g_right, int32_t *g_ref,
-                            int32_t *status) {
+                            uint32_t *g_nref, int32_t *status) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
@@ -62,6 +66,7 @@ __global__ void size_kernel(const uint8_t *records, const uint32_t *item_rec16, 
     const long long g = group_of(group_off, n_groups, i);
     atomicMin(g_left + g, h.x);
     atomicMax(g_right + g, h.x + span);
+    atomicAdd(g_nref + g, min(n_ref, 0xffffu));
     const int old = atomicCAS(g_ref + g, -1, (int)h.y);
     if (old != -1 && old != (int)h.y) status[g] = 4;   // reads on several contigs: the reference raises (consensus.py:57-58)
 }
@@ -71,14 +76,15 @@ __global__ void size_kernel(const uint8_t *records, const uint32_t *item_rec16, 
 // tokens, so the 12-byte tuples of a read are written by consecutive lanes into consecutive slots
 // (slot = aligned offset for M/=/X bases, m_total + d for the d-th deleted base).
 __global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
-                              long long n_items, const unsigned long long *tuple_off, unsigned long long *key, uint32_t *val,
-                              int32_t *status) {
+                              long long n_items, const unsigned long long *tuple_off, const unsigned long long *win,
+                              unsigned long long *key, uint32_t *val, int32_t *status) {
     const unsigned long long kInvalid = ((unsigned long long)n_groups << 32) | 0xffffffffull;
     const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n_items) return;
     const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
     const unsigned long long g = (unsigned long long)group_of(group_off, n_groups, i);
+    if (win[g] != 0ull) return;        // direct_kernel's group
     const unsigned long long o0 = tuple_off[i], end = tuple_off[i + 1];
     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
     const int pos = (int)h.x;
@@ -162,6 +168,205 @@ __global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16
     if (bad) status[g] = 2;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Direct path: groups of at most 256 reads (16-bit quality sums cannot overflow) whose reads touch at most
+// kSlots blocks of kBlk reference positions never become tuples.  One WARP per group keeps those blocks in shared
+// memory -- four quality sums and (covered, first-seen reference base) per position; a block is found through a
+// 32-entry hash of its block number, so spliced reads cost a few more blocks, not the whole intron --, walks the
+// member reads in group order exactly as expand_kernel does (lanes over aligned offsets and deleted-base tokens)
+// and then emits the covered positions' cells block by block in ascending order.  A group that touches more
+// blocks gives up (win[g] = 0) and takes the tuple sort below with the very deep groups.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBlk = 32, kSlots = 32, kWin = kBlk * kSlots;
+constexpr int kDirectWarps = 4;
+constexpr int kNoBlock = -1;
+
+// win[g] = cell slots reserved for group g on the direct path (0: not eligible)
+__global__ void classify_groups_kernel(const uint32_t *g_left, const uint32_t *g_nref, const long long *group_off,
+                                       long long n_groups, unsigned long long *win) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g > n_groups) return;
+    unsigned long long w = 0;
+    if (g < n_groups && g_left[g] != 0xffffffffu && group_off[g + 1] - group_off[g] <= 256) w = min(g_nref[g], (uint32_t)kWin);
+    win[g] = w;        // win[n_groups] = 0: the exclusive scan's total lands there
+}
+
+__global__ void drop_direct_items_kernel(const long long *group_off, long long n_groups, long long n_items,
+                                         const unsigned long long *win, unsigned long long *tuple_cnt) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    if (win[group_of(group_off, n_groups, i)] != 0ull) tuple_cnt[i] = 0ull;
+}
+
+__device__ __forceinline__ uint32_t call_cell(const uint32_t s[4], int ref, int quality) {
+    const uint32_t base_q = max(max(s[0], s[1]), max(s[2], s[3]));
+    if (base_q == 0) return ((uint32_t)ref << 2) | (1u << 4);     // no support: deletion (consensus.py:113-123)
+    int base;
+    if ((int)base_q < quality) base = ref;
+    else if (s[ref] == base_q) base = ref;                         // ties: reference if present
+    else base = s[0] == base_q ? 0 : (s[1] == base_q ? 1 : (s[2] == base_q ? 2 : 3));
+    return (uint32_t)base | ((uint32_t)ref << 2) | (min(base_q, 42u) << 8);
+}
+
+// slot of reference block `blk` in the warp's table (claimed on first use); -1 when the table is full
+__device__ __forceinline__ int block_slot(int *blk_id, int blk) {
+    const uint32_t h = ((uint32_t)blk * 0x9E3779B1u) >> 27;
+    for (int probe = 0; probe < kSlots; ++probe) {
+        const int s = (int)((h + probe) & (kSlots - 1));
+        const int cur = blk_id[s];
+        if (cur == blk) return s;
+        if (cur == kNoBlock) {
+            const int old = atomicCAS(blk_id + s, kNoBlock, blk);
+            if (old == kNoBlock || old == blk) return s;
+        }
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t *records, const uint32_t *item_rec16,
+                                                                  const long long *group_off, long long n_groups,
+                                                                  unsigned long long *win, const unsigned long long *cell_start,
+                                                                  int quality, unsigned long long *cell_key, uint32_t *cell,
+                                                                  uint32_t *cell_cnt, int32_t *status) {
+    __shared__ __align__(8) uint16_t s_qs[kDirectWarps][kWin][4];
+    __shared__ uint8_t s_meta[kDirectWarps][kWin];      // bit 2 covered, bits 0..1 first-seen reference base
+    __shared__ int s_blk[kDirectWarps][kSlots];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint16_t(*qs)[4] = s_qs[wid];
+    uint8_t *meta = s_meta[wid];
+    int *blk_id = s_blk[wid];
+    for (int w = lane; w < kWin; w += 32) { *reinterpret_cast<uint2 *>(qs[w]) = make_uint2(0u, 0u); meta[w] = 0; }
+    blk_id[lane] = kNoBlock;
+    __syncwarp();
+    const long long n_warps = (long long)gridDim.x * kDirectWarps;
+    for (long long g = blockIdx.x * (long long)kDirectWarps + wid; g < n_groups; g += n_warps) {
+        if (win[g] == 0ull) continue;
+        bool bad = false, full = false;
+        for (long long i = group_off[g]; i < group_off[g + 1] && !full; ++i) {
+            const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
+            const uint4 h = *reinterpret_cast<const uint4 *>(rec);
+            const int pos = (int)h.x;
+            const uint32_t l_seq = h.z & 0xffff, n_cigar = h.z >> 16, n_tok = h.w & 0xffff;
+            const uint32_t *cig = reinterpret_cast<const uint32_t *>(rec + 16);
+            const uint32_t *tok = cig + n_cigar;
+            const uint8_t *seq = reinterpret_cast<const uint8_t *>(tok + n_tok);
+            const uint8_t *qual = seq + pad4(((size_t)l_seq + 1) >> 1);
+            if ((h.w >> 16) & DYN_REC_BAD_MD) { bad = true; continue; }
+            uint32_t m_total = 0, d_total = 0;
+            for (uint32_t c = 0; c < n_cigar; ++c) {
+                const uint32_t op = cig[c] & 0xf, len = cig[c] >> 4;
+                if (op == 0 || op == 7 || op == 8) m_total += len;
+                else if (op == 2) d_total += len;
+            }
+            // aligned bases
+            for (uint32_t a = lane; a < m_total; a += 32) {
+                int q = 0, r = pos, done = 0, qpos = -1, rpos = 0;
+                for (uint32_t c = 0; c < n_cigar; ++c) {
+                    const uint32_t w = cig[c];
+                    const int op = (int)(w & 0xf), len = (int)(w >> 4);
+                    if (op == 0 || op == 7 || op == 8) {
+                        if ((int)a < done + len) { qpos = q + ((int)a - done); rpos = r + ((int)a - done); break; }
+                        done += len; q += len; r += len;
+                    } else if (op == 1 || op == 4) q += len;
+                    else if (op == 2 || op == 3) r += len;
+                }
+                if (qpos >= 0 && qpos < (int)l_seq) {
+                    const uint32_t rn = (seq[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
+                    uint32_t gn = rn;
+                    for (uint32_t t = 0; t < n_tok; ++t) {
+                        const uint32_t tk = tok[t];
+                        if (!DYN_TOK_IS_DEL(tk) && DYN_TOK_AOFF(tk) == a) gn = DYN_TOK_BASE(tk);
+                    }
+                    const int gi = base_idx(gn), ri = base_idx(rn);
+                    if (gi >= 0 && ri >= 0) {      // reference N and read N are skipped (consensus.py:79-91)
+                        const int sl = block_slot(blk_id, rpos >> 5);
+                        if (sl < 0) full = true;
+                        else {
+                            const int w = sl * kBlk + (rpos & (kBlk - 1));
+                            if (!(meta[w] & 4)) meta[w] = (uint8_t)(4 | gi);
+                            qs[w][ri] = (uint16_t)(qs[w][ri] + qual[qpos]);
+                        }
+                    }
+                } else bad = true;
+            }
+            // deleted reference bases: the d-th deleted-base token belongs to the d-th base of the CIGAR's D ops
+            uint32_t carry = 0;
+            for (uint32_t t0 = 0; t0 < n_tok; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                const uint32_t tk = t < n_tok ? tok[t] : 0u;
+                const bool is_del = t < n_tok && DYN_TOK_IS_DEL(tk);
+                const uint32_t ballot = __ballot_sync(0xffffffffu, is_del);
+                if (is_del) {
+                    const uint32_t d = carry + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+                    if (d < d_total) {
+                        int r = pos, rpos = -1;
+                        uint32_t rest = d;
+                        for (uint32_t c = 0; c < n_cigar; ++c) {
+                            const uint32_t w = cig[c];
+                            const int op = (int)(w & 0xf), len = (int)(w >> 4);
+                            if (op == 2) { if (rest < (uint32_t)len) { rpos = r + (int)rest; break; } rest -= (uint32_t)len; r += len; }
+                            else if (op == 0 || op == 3 || op == 7 || op == 8) r += len;
+                        }
+                        const int gi = base_idx(DYN_TOK_BASE(tk));
+                        if (rpos >= 0 && gi >= 0) {
+                            const int sl = block_slot(blk_id, rpos >> 5);
+                            if (sl < 0) full = true;
+                            else {
+                                const int w = sl * kBlk + (rpos & (kBlk - 1));
+                                if (!(meta[w] & 4)) meta[w] = (uint8_t)(4 | gi);
+                            }
+                        }
+                    } else bad = true;
+                }
+                carry += (uint32_t)__popc(ballot);
+            }
+            if (carry != d_total) bad = true;
+            full = __any_sync(0xffffffffu, full);
+            __syncwarp();       // the next read of the group touches the same positions
+        }
+        // blocks in ascending order: rank of every slot's block number among the used ones
+        const int my_blk = blk_id[lane];
+        int rank = 0;
+        for (int j = 0; j < kSlots; ++j) {
+            const int o = __shfl_sync(0xffffffffu, my_blk, j);
+            rank += (o != kNoBlock && my_blk != kNoBlock && o < my_blk) ? 1 : 0;
+        }
+        const uint32_t used = __ballot_sync(0xffffffffu, my_blk != kNoBlock);
+        const int n_blk = __popc(used);
+        const unsigned long long base = cell_start[g];
+        const unsigned long long cap = win[g];
+        uint32_t run = 0;
+        for (int r = 0; r < n_blk; ++r) {
+            const int sl = __ffs((int)__ballot_sync(0xffffffffu, my_blk != kNoBlock && rank == r)) - 1;   // the slot ranked r
+            const int blk = __shfl_sync(0xffffffffu, my_blk, sl);
+            const int w = sl * kBlk + lane;
+            const uint32_t m = meta[w];
+            const bool covered = !full && (m & 4);
+            const uint32_t ballot = __ballot_sync(0xffffffffu, covered);
+            if (covered) {
+                const uint32_t s[4] = {qs[w][0], qs[w][1], qs[w][2], qs[w][3]};
+                const unsigned long long k = run + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+                if (k < cap) {
+                    cell_key[base + k] = ((unsigned long long)g << 32) | (uint32_t)(blk * kBlk + lane);
+                    cell[base + k] = call_cell(s, (int)(m & 3), quality);
+                }
+            }
+            run += (uint32_t)__popc(ballot);
+            // leave the block clean for the next group
+            *reinterpret_cast<uint2 *>(qs[w]) = make_uint2(0u, 0u);
+            meta[w] = 0;
+        }
+        __syncwarp();
+        blk_id[lane] = kNoBlock;
+        __syncwarp();
+        if (lane == 0) {
+            if (full) win[g] = 0ull;          // too many blocks: the sorted path takes the group
+            else cell_cnt[g] = run;
+        }
+        if (!full && __any_sync(0xffffffffu, bad) && lane == 0) status[g] = 2;
+    }
+}
+
 __global__ void head_kernel(const unsigned long long *key, long long n, long long n_groups, uint32_t *flag) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -205,17 +410,26 @@ __device__ __forceinline__ uint8_t *put_num(uint8_t *p, uint32_t v) {
 
 // One thread per group. WRITE=false: sizes only (stored in `sizes`); WRITE=true: the record at out + 16 * out_off[g].
 template <bool WRITE>
-__global__ void assemble_kernel(const unsigned long long *cell_key, const uint32_t *cell, const long long *n_cells_p,
-                                long long n_groups, const uint32_t *g_left, const uint32_t *g_right, const int32_t *g_ref,
+__global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint32_t *cell_s, const long long *n_cells_p,
+                                const unsigned long long *cell_key_d, const uint32_t *cell_d, const unsigned long long *win,
+                                const unsigned long long *cell_start, const uint32_t *cell_cnt, long long n_groups,
+                                const uint32_t *g_left, const uint32_t *g_right, const int32_t *g_ref,
                                 GroupOut *sizes, uint32_t *out_cap16, uint32_t *md_cap, const uint32_t *out_off, uint8_t *out,
                                 long long out_capacity16, const uint32_t *md_off, uint8_t *out_md, long long md_capacity,
                                 uint32_t *out_nm, int32_t *status) {
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
-    const long long n_cells = *n_cells_p;
-    long long lo = 0, hi = n_cells;      // first cell of group g
-    while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)(cell_key[mid] >> 32) < g) lo = mid + 1; else hi = mid; }
-    const long long c0 = lo;
+    // cells of the group: direct_kernel's groups know their range; the sorted path's cells are ordered by (group, position)
+    long long c0, c1;
+    const unsigned long long *cell_key = cell_key_s;
+    const uint32_t *cell = cell_s;
+    if (win[g] != 0ull) { cell_key = cell_key_d; cell = cell_d; c0 = (long long)cell_start[g]; c1 = c0 + cell_cnt[g]; }
+    else {
+        long long lo = 0, hi = *n_cells_p;
+        c1 = hi;
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)(cell_key[mid] >> 32) < g) lo = mid + 1; else hi = mid; }
+        c0 = lo;
+    }
     const uint32_t left = g_left[g], right = g_right[g];
     const bool empty = left == 0xffffffffu;      // group without reads
     uint32_t *cig = nullptr, *tokp = nullptr;
@@ -264,7 +478,7 @@ __global__ void assemble_kernel(const unsigned long long *cell_key, const uint32
     };
     uint32_t prev = left;    // next expected reference position
     if (!empty) {
-        for (long long c = c0; c < n_cells && (long long)(cell_key[c] >> 32) == g; ++c) {
+        for (long long c = c0; c < c1 && (long long)(cell_key[c] >> 32) == g; ++c) {
             const uint32_t pos = (uint32_t)cell_key[c], v = cell[c];
             cigar_push(3, pos - prev);                 // positions nobody observed (consensus.py:109-111)
             prev = pos + 1;
@@ -334,14 +548,16 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     const long long *group_off = reinterpret_cast<const long long *>(d_group_off);
     const uint8_t *records = static_cast<const uint8_t *>(d_records);
 
-    // ---- per-item tuple counts, per-group span (scratch slot 12, part 1)
+    // ---- per-item tuple counts, per-group span and path (scratch slot 12)
     size_t scan_tmp = 0, t = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr, n_items + 1, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t, (unsigned long long *)nullptr, (unsigned long long *)nullptr, n_groups + 1, stream);
+    if (t > scan_tmp) scan_tmp = t;
     cub::DeviceScan::ExclusiveSum(nullptr, t, (uint32_t *)nullptr, (uint32_t *)nullptr, n_groups + 1, stream);
     if (t > scan_tmp) scan_tmp = t;
-    uint32_t *g_left, *g_right, *out_cap16, *md_cap;
+    uint32_t *g_left, *g_right, *g_nref, *out_cap16, *md_cap, *cell_cnt;
     int32_t *g_ref;
-    unsigned long long *tuple_cnt, *tuple_off;
+    unsigned long long *tuple_cnt, *tuple_off, *win, *cell_start;
     GroupOut *sizes;
     long long *n_cells;
     void *tmp0;
@@ -349,7 +565,11 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     for (int pass = 0; pass < 2; ++pass) {
         tuple_cnt = a0.take<unsigned long long>(n_items + 1);
         tuple_off = a0.take<unsigned long long>(n_items + 1);
+        win = a0.take<unsigned long long>(n_groups + 1);
+        cell_start = a0.take<unsigned long long>(n_groups + 1);
+        cell_cnt = a0.take<uint32_t>(n_groups);
         g_left = a0.take<uint32_t>(n_groups); g_right = a0.take<uint32_t>(n_groups); g_ref = a0.take<int32_t>(n_groups);
+        g_nref = a0.take<uint32_t>(n_groups);
         out_cap16 = a0.take<uint32_t>(n_groups + 1);
         md_cap = a0.take<uint32_t>(n_groups + 1);
         sizes = a0.take<GroupOut>(n_groups);
@@ -365,20 +585,51 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     init_groups_kernel<<<grid_for(n_groups), kBlock, 0, stream>>>(g_left, g_right, g_ref, d_out_status, n_groups);
     DYN_CUDA(cudaMemsetAsync(tuple_cnt, 0, sizeof(unsigned long long) * (n_items + 1), stream));
     DYN_CUDA(cudaMemsetAsync(n_cells, 0, 16, stream));
-    unsigned long long n_tuples = 0;
-    if (n_items > 0) {
+    DYN_CUDA(cudaMemsetAsync(cell_cnt, 0, sizeof(uint32_t) * n_groups, stream));
+    DYN_CUDA(cudaMemsetAsync(g_nref, 0, sizeof(uint32_t) * n_groups, stream));
+    if (n_items > 0)
         size_kernel<<<grid_for(n_items), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_cnt,
-                                                              g_left, g_right, g_ref, d_out_status);
+                                                              g_left, g_right, g_ref, g_nref, d_out_status);
+
+    // ---- direct path (scratch slot 13): cell slots per eligible group, then one warp per group
+    classify_groups_kernel<<<grid_for(n_groups + 1), kBlock, 0, stream>>>(g_left, g_nref, group_off, n_groups, win);
+    t = scan_tmp;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, win, cell_start, n_groups + 1, stream));
+    unsigned long long n_direct = 0, n_tuples = 0;
+    DYN_CUDA(cudaMemcpyAsync(&n_direct, cell_start + n_groups, 8, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaStreamSynchronize(stream));      // the direct path's cell arrays are sized from this total
+    unsigned long long *cell_key_d = nullptr, *cell_key = nullptr;
+    uint32_t *cell_d = nullptr, *cell = nullptr;
+    if (n_direct > 0) {
+        Arena a1;
+        for (int pass = 0; pass < 2; ++pass) {
+            cell_key_d = a1.take<unsigned long long>((size_t)n_direct);
+            cell_d = a1.take<uint32_t>((size_t)n_direct);
+            if (pass == 0) {
+                void *base = nullptr;
+                int rc = dyn_ctx_scratch(ctx, 13, a1.used + 256, &base);
+                if (rc) return rc;
+                a1 = Arena(base);
+            }
+        }
+        int per_sm = 0;
+        DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, direct_kernel, 32 * kDirectWarps, 0));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = std::min<long long>((long long)ctx->sm_count * per_sm, (n_groups + kDirectWarps - 1) / kDirectWarps);
+        direct_kernel<<<(unsigned)grid, 32 * kDirectWarps, 0, stream>>>(records, d_item_rec16, group_off, n_groups, win, cell_start,
+                                                                        quality, cell_key_d, cell_d, cell_cnt, d_out_status);
+        DYN_CUDA(cudaGetLastError());
+    }
+
+    // ---- sorted path for what is left: expand, sort, reduce (scratch slot 17)
+    if (n_items > 0) {
+        drop_direct_items_kernel<<<grid_for(n_items), kBlock, 0, stream>>>(group_off, n_groups, n_items, win, tuple_cnt);
         t = scan_tmp;
         DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, tuple_cnt, tuple_off, n_items + 1, stream));
         DYN_CUDA(cudaMemcpyAsync(&n_tuples, tuple_off + n_items, 8, cudaMemcpyDeviceToHost, stream));
         DYN_CUDA(cudaStreamSynchronize(stream));      // the tuple arrays are sized from this total
     }
-    DYN_ARG(n_tuples < 0x7fffffffull, "more than 2^31 base tuples in one call: split the groups into batches");
-
-    // ---- expand, sort, reduce (scratch slot 13)
-    unsigned long long *cell_key = nullptr;
-    uint32_t *cell = nullptr;
+    DYN_ARG(n_tuples < 0x7fffffffull, "more than 2^31 base tuples outside the direct path in one call: split the groups into batches");
     if (n_tuples > 0) {
         const size_t n = (size_t)n_tuples;
         size_t sort_tmp = 0;
@@ -400,13 +651,13 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
             tmp1 = a1.take<uint8_t>(sort_tmp);
             if (pass == 0) {
                 void *base = nullptr;
-                int rc = dyn_ctx_scratch(ctx, 13, a1.used + 256, &base);
+                int rc = dyn_ctx_scratch(ctx, 17, a1.used + 256, &base);
                 if (rc) return rc;
                 a1 = Arena(base);
             }
         }
-        expand_kernel<<<grid_for(n_items * 32), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_off, ka,
-                                                                     va, d_out_status);
+        expand_kernel<<<grid_for(n_items * 32), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_off,
+                                                                     win, ka, va, d_out_status);
         cub::DoubleBuffer<unsigned long long> k(ka, kb);
         cub::DoubleBuffer<uint32_t> v(va, vb);
         t = sort_tmp;
@@ -428,7 +679,8 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     }
 
     // ---- assemble: sizes, offsets, records
-    assemble_kernel<false><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, n_groups, g_left, g_right, g_ref, sizes,
+    assemble_kernel<false><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, cell_key_d, cell_d, win, cell_start,
+                                                                     cell_cnt, n_groups, g_left, g_right, g_ref, sizes,
                                                                      out_cap16, md_cap, nullptr, nullptr, 0, nullptr, nullptr, 0,
                                                                      d_out_nm, d_out_status);
     DYN_CUDA(cudaMemsetAsync(out_cap16 + n_groups, 0, 4, stream));
@@ -437,7 +689,8 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, out_cap16, d_out_off, n_groups + 1, stream));
     t = scan_tmp;
     DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, md_cap, d_out_md_off, n_groups + 1, stream));
-    assemble_kernel<true><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, n_groups, g_left, g_right, g_ref, sizes,
+    assemble_kernel<true><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, cell_key_d, cell_d, win, cell_start,
+                                                                    cell_cnt, n_groups, g_left, g_right, g_ref, sizes,
                                                                     out_cap16, md_cap, d_out_off, static_cast<uint8_t *>(d_out_records),
                                                                     out_capacity_bytes >> 4, d_out_md_off,
                                                                     static_cast<uint8_t *>(d_out_md), md_capacity_bytes, d_out_nm,

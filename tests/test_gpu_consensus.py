@@ -166,3 +166,23 @@ def test_large_group_and_singleton(gpu_ctx):
         r.reference_id = 0
     groups.append(big)
     check_groups(groups)
+
+
+def test_deep_groups_both_paths(gpu_ctx):
+    """256 reads within one window stay on the direct path (16-bit quality sums: 256 * 93 fits), 257 take the sorted
+    path; both must equal the oracle."""
+    from oracle.consensus_oracle import make_read
+    rng = np.random.default_rng(12)
+    genome = [LETTERS[i] for i in rng.integers(0, 4, 400)]
+    groups = []
+    for depth in (256, 257, 300):
+        reads = []
+        for r in range(depth):
+            pos = int(rng.integers(0, 40))
+            L = int(rng.integers(30, 90))
+            cigar = [('M', L)] if r % 5 else [('M', 10), ('D', 2), ('M', L - 10)]
+            seq, qual, md = simulate_read(rng, genome, pos, cigar, p_mis=0.2, low_q=0.05)
+            qual = [93 if q > 30 else q for q in qual]
+            reads.append(make_read(f'd{depth}r{r}', pos, cigar, seq, qual, md, ref_id=1))
+        groups.append(reads)
+    check_groups(groups)
