@@ -82,10 +82,11 @@ __global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16
     const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n_items) return;
+    const unsigned long long o0 = tuple_off[i], end = tuple_off[i + 1];
+    if (end == o0) return;             // a read of direct_kernel's groups (or one without reference bases)
     const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
     const unsigned long long g = (unsigned long long)group_of(group_off, n_groups, i);
-    if (win[g] != 0ull) return;        // direct_kernel's group
-    const unsigned long long o0 = tuple_off[i], end = tuple_off[i + 1];
+    if (win[g] != 0ull) return;
     const uint4 h = *reinterpret_cast<const uint4 *>(rec);
     const int pos = (int)h.x;
     const uint32_t l_seq = h.z & 0xffff, n_cigar = h.z >> 16, n_tok = h.w & 0xffff;
@@ -450,11 +451,11 @@ __global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint
             tokp = cig + sz.n_cigar;
             seq = reinterpret_cast<uint8_t *>(tokp + sz.n_tok);
             const size_t seq_bytes = pad4(((size_t)sz.l_seq + 1) >> 1);
-            for (size_t b = 0; b < seq_bytes; ++b) seq[b] = 0;
             qual = seq + seq_bytes;
             md = out_md + md_off[g];
-            const size_t used = 16 + 4 * (size_t)sz.n_cigar + 4 * (size_t)sz.n_tok + seq_bytes + sz.l_seq;
-            for (size_t b = used; b < (((size_t)out_off[g + 1] - out_off[g]) << 4); ++b) rec[b] = 0;
+            // sequence and qualities are written a 32-bit word at a time below; zero what follows the last quality word
+            const size_t used4 = 16 + 4 * (size_t)sz.n_cigar + 4 * (size_t)sz.n_tok + seq_bytes + pad4(sz.l_seq);
+            for (size_t b = used4; b < (((size_t)out_off[g + 1] - out_off[g]) << 4); b += 4) *reinterpret_cast<uint32_t *>(rec + b) = 0u;
             out_nm[g] = sz.nm;
         }
     }
@@ -476,6 +477,7 @@ __global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint
             md_n = 0;
         }
     };
+    uint32_t seq_acc = 0, qual_acc = 0;
     uint32_t prev = left;    // next expected reference position
     if (!empty) {
         for (long long c = c0; c < c1 && (long long)(cell_key[c] >> 32) == g; ++c) {
@@ -503,13 +505,20 @@ __global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint
                     ++nm;
                 }
                 if (WRITE && fits) {
-                    seq[l_seq >> 1] |= (uint8_t)((1u << base) << ((l_seq & 1) ? 0 : 4));
-                    qual[l_seq] = (uint8_t)((v >> 8) & 0xff);
+                    // base i of a word sits at byte (i >> 1) & 3, high nibble when i is even
+                    seq_acc |= (1u << base) << (8 * ((l_seq >> 1) & 3) + ((l_seq & 1) ? 0 : 4));
+                    qual_acc |= ((v >> 8) & 0xffu) << (8 * (l_seq & 3));
+                    if ((l_seq & 7) == 7) { reinterpret_cast<uint32_t *>(seq)[l_seq >> 3] = seq_acc; seq_acc = 0; }
+                    if ((l_seq & 3) == 3) { reinterpret_cast<uint32_t *>(qual)[l_seq >> 2] = qual_acc; qual_acc = 0; }
                 }
                 ++l_seq;
             }
         }
         cigar_push(3, right - prev);
+    }
+    if (WRITE && fits) {     // the partial last words (zero padded)
+        if (l_seq & 7) reinterpret_cast<uint32_t *>(seq)[l_seq >> 3] = seq_acc;
+        if (l_seq & 3) reinterpret_cast<uint32_t *>(qual)[l_seq >> 2] = qual_acc;
     }
     // MD always ends with a number (consensus.py:175); the last CIGAR run is flushed (:176)
     if (WRITE && fits) mdp = put_num(mdp, md_n);
