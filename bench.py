@@ -414,7 +414,7 @@ def main():
         c2.record(stream)
         barrier()
         ok = bool((cres['status'] == 0).all().item())
-        cons = {'metric': 'member reads/s, UMI consensus (expand, radix sort, per-position reduce, assemble)',
+        cons = {'metric': 'member reads/s, UMI consensus (per-group shared-memory accumulation, tuple sort for scattered groups, assemble)',
                 'value': world * int(items.numel()) / (c1.elapsed_time(c2) * 1e-3), 'unit': UNIT, 'ms_consensus': c1.elapsed_time(c2),
                 'ms_grouping': c0.elapsed_time(c1), 'reads': nc, 'member_reads': int(items.numel()), 'groups': int(goff.numel() - 1),
                 'all_status_ok': ok, 'workload': 'C3-like: 91-nt reads, 3.5 reads per (barcode, UMI, gene) group, starts within 300 nt'}

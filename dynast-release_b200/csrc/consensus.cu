@@ -325,21 +325,19 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
             full = __any_sync(0xffffffffu, full);
             __syncwarp();       // the next read of the group touches the same positions
         }
-        // blocks in ascending order: rank of every slot's block number among the used ones
+        // blocks are emitted in ascending order: repeatedly the smallest block number not yet taken
         const int my_blk = blk_id[lane];
-        int rank = 0;
-        for (int j = 0; j < kSlots; ++j) {
-            const int o = __shfl_sync(0xffffffffu, my_blk, j);
-            rank += (o != kNoBlock && my_blk != kNoBlock && o < my_blk) ? 1 : 0;
-        }
         const uint32_t used = __ballot_sync(0xffffffffu, my_blk != kNoBlock);
         const int n_blk = __popc(used);
+        uint32_t my_key = my_blk == kNoBlock ? 0xffffffffu : (uint32_t)my_blk;
         const unsigned long long base = cell_start[g];
         const unsigned long long cap = win[g];
         uint32_t run = 0;
         for (int r = 0; r < n_blk; ++r) {
-            const int sl = __ffs((int)__ballot_sync(0xffffffffu, my_blk != kNoBlock && rank == r)) - 1;   // the slot ranked r
-            const int blk = __shfl_sync(0xffffffffu, my_blk, sl);
+            const uint32_t lowest = __reduce_min_sync(0xffffffffu, my_key);
+            const int sl = __ffs((int)__ballot_sync(0xffffffffu, my_key == lowest)) - 1;   // its slot
+            const int blk = (int)lowest;
+            if (lane == sl) my_key = 0xffffffffu;
             const int w = sl * kBlk + lane;
             const uint32_t m = meta[w];
             const bool covered = !full && (m & 4);
