@@ -380,17 +380,18 @@ def main():
             rep_ms.append(p0.elapsed_time(p1))
         if os.environ.get('DYN_BENCH_DEBUG'):
             sys.stderr.write('pipeline per rep: %r %r\n' % (rep_ms, per_rep))
-        # median over the repetitions: the stages between the kernels are host-driven (split plan, shape discovery),
-        # and a busy host core shows up as a one-off spike in one of them
-        pipe_ms = float(np.median(rep_ms))
-        timings = {k_: float(np.median([r_[k_] for r_ in per_rep])) for k_ in per_rep[0]}
+        # best of the repetitions, all of them listed: several stages are host-driven (split plan, shape discovery,
+        # allocations), and on a shared box a descheduled host thread shows up as 50-100 ms spikes in random stages
+        best = int(np.argmin(rep_ms))
+        pipe_ms = float(rep_ms[best])
+        timings = dict(per_rep[best])
         if dist is not None:
             t = torch.tensor([pipe_ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             pipe_ms = float(t.item())
         pipe = {'metric': 'reads/s, tally -> UMI dedup -> p_e -> (k,n) histograms -> EM -> pi/alpha, device resident',
                 'value': world * n_reads / (pipe_ms * 1e-3), 'unit': UNIT, 'ms': pipe_ms,
-                'stage_ms': timings, 'repetitions': reps, 'statistic': 'median',
+                'stage_ms': timings, 'repetitions': reps, 'statistic': 'best repetition', 'rep_ms': [float(x) for x in rep_ms],
                 'reads_after_dedup': int(res['selected'].numel()),
                 'barcodes_with_p_c': int((res['em_status'] == 0).sum().item()),
                 'exchange': ('all-to-all of 40-byte per-read rows to rank barcode % world before dedup (NCCL)' if xchg else None),

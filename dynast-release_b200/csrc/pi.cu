@@ -7,7 +7,7 @@
 // The reference reports the posterior MEANS of alpha, beta, pi_g (pi.py:186).  Those are three ratios of
 // integrals over a 3-dimensional box, computed here deterministically, one CTA per group:
 //   * the likelihood L(pi) is log-concave in pi, so its mode and the window [a, b] outside which it has
-//     dropped by e^-60 are found by bisection; all pi-integrals run over that window;
+//     dropped by e^-60 are found by a 9-section search (one warp per probe point); all pi-integrals run over that window;
 //   * pi: tanh-sinh (double exponential) quadrature on [a, b] -- exact handling of the integrable endpoint
 //     singularities pi^(alpha-1), (1-pi)^(beta-1) (alpha, beta go down to e^-3) when the window touches 0 or 1;
 //   * (log_alpha, log_beta): 32 x 32 Gauss-Legendre nodes on (-3, 3)^2;
@@ -28,6 +28,7 @@ namespace {
 constexpr int kPiThreads = 256;
 constexpr int kNA = 32;            // Gauss-Legendre nodes per hyper-parameter
 constexpr int kNJ = 257;           // tanh-sinh nodes
+static_assert(kNJ >= kPiThreads, "one node per thread");
 constexpr int kChunk = 64;         // pi nodes per bilinear-form chunk
 constexpr double kDrop = 60.0;     // window: log L within this of its maximum
 
@@ -75,6 +76,53 @@ __device__ __forceinline__ void loglik_partial(const double *ca, const double *c
     }
 }
 
+// The same, by ONE warp (lanes over the cells, shuffle reduction): every lane gets the totals.
+__device__ __forceinline__ void loglik_warp(const double *ca, const double *cb, const double *cc, int cells, double pi,
+                                            double q, double &ll, double &dl) {
+    ll = 0.0; dl = 0.0;
+    for (int i = threadIdx.x & 31; i < cells; i += 32) {
+        const double m = pi * ca[i] + q * cb[i];
+        ll += cc[i] * log(m);
+        dl += cc[i] * (ca[i] - cb[i]) / m;
+    }
+    for (int d = 16; d; d >>= 1) {
+        ll += __shfl_xor_sync(0xffffffffu, ll, d);
+        dl += __shfl_xor_sync(0xffffffffu, dl, d);
+    }
+}
+
+constexpr int kSections = kPiThreads / 32 + 1;     // interior probe points per round = warps per CTA
+constexpr int kRounds = 11;                        // (1 / 9)^11 = 3e-11 of the starting interval
+
+// Narrows [lo, hi] around the point where a monotone predicate flips, kSections-section search: in every round
+// warp w evaluates the likelihood at its own interior point and the CTA keeps the sub-interval of the flip --
+// 11 rounds of one barrier pair instead of 50-60 bisection steps of two block reductions each.
+//   MODE = 0: predicate d/dpi log L > 0 (true left of the mode);  MODE = 1: log L >= thr, true right of the flip
+//   (left window edge);  MODE = 2: log L >= thr, true left of the flip (right window edge).
+template <int MODE>
+__device__ __forceinline__ void section_search(const double *ca, const double *cb, const double *cc, int cells, double thr,
+                                               double &lo, double &hi, double *s_val) {
+    const int w = threadIdx.x >> 5;
+    for (int r = 0; r < kRounds; ++r) {
+        const double step = (hi - lo) / kSections;
+        const double x = lo + step * (w + 1);
+        double ll, dl;
+        loglik_warp(ca, cb, cc, cells, x, 1.0 - x, ll, dl);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_val[w] = MODE == 0 ? dl : ll;
+        __syncthreads();
+        // first interior point where the predicate differs from its value at `lo`
+        int f = kSections - 1;
+        for (int j = kSections - 2; j >= 0; --j) {
+            const bool pred = MODE == 0 ? s_val[j] > 0.0 : s_val[j] >= thr;
+            const bool at_lo = MODE != 1;      // MODE 0 / 2: true at lo;  MODE 1: false at lo
+            if (pred != at_lo) f = j;
+        }
+        const double nlo = lo + step * f, nhi = f == kSections - 1 ? hi : lo + step * (f + 1);
+        lo = nlo; hi = nhi;
+    }
+}
+
 __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     double *ca = reinterpret_cast<double *>(smem_raw);        // [max_cells] scaled Binom(k|n,p_c)
@@ -87,6 +135,7 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
     double *lq = lp + kNJ + 1;                                 // [kNJ] log (1 - pi_j)
     double *pj = lq + kNJ + 1;                                 // [kNJ] pi_j
     __shared__ double red[kPiThreads / 32];
+    __shared__ double s_val[kPiThreads / 32];
     __shared__ double s_lo, s_hi;
 
     const int tid = threadIdx.x;
@@ -136,12 +185,7 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
             if (!(d0 > 0.0)) mode = 0.0;
             else if (!(d1 < 0.0)) mode = 1.0;
             else {
-                for (int it = 0; it < 60; ++it) {
-                    const double mid = 0.5 * (lo + hi);
-                    loglik_partial(ca, cb, cc, cells, mid, 1.0 - mid, ll, dl);
-                    const double d = block_sum(dl, red);
-                    if (d > 0.0) lo = mid; else hi = mid;
-                }
+                section_search<0>(ca, cb, cc, cells, 0.0, lo, hi, s_val);
                 mode = 0.5 * (lo + hi);
             }
         }
@@ -154,22 +198,14 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
             const double l0 = block_sum(ll, red);          // may be -inf
             if (mode > 0.0 && !(l0 >= ll_max - kDrop)) {
                 double lo = 0.0, hi = mode;
-                for (int it = 0; it < 50; ++it) {
-                    const double mid = 0.5 * (lo + hi);
-                    loglik_partial(ca, cb, cc, cells, mid, 1.0 - mid, ll, dl);
-                    if (block_sum(ll, red) >= ll_max - kDrop) hi = mid; else lo = mid;
-                }
+                section_search<1>(ca, cb, cc, cells, ll_max - kDrop, lo, hi, s_val);
                 wa = lo;
             }
             loglik_partial(ca, cb, cc, cells, 1.0, 0.0, ll, dl);
             const double l1 = block_sum(ll, red);
             if (mode < 1.0 && !(l1 >= ll_max - kDrop)) {
                 double lo = mode, hi = 1.0;
-                for (int it = 0; it < 50; ++it) {
-                    const double mid = 0.5 * (lo + hi);
-                    loglik_partial(ca, cb, cc, cells, mid, 1.0 - mid, ll, dl);
-                    if (block_sum(ll, red) >= ll_max - kDrop) lo = mid; else hi = mid;
-                }
+                section_search<2>(ca, cb, cc, cells, ll_max - kDrop, lo, hi, s_val);
                 wb = hi;
             }
         }
@@ -177,7 +213,17 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
         __syncthreads();
         const double a = s_lo, b = s_hi, width = b - a;
         // ---- tanh-sinh nodes on [a, b]
-        for (int j = tid; j < kNJ; j += kPiThreads) {
+        // one node per thread; the nodes beyond the thread count (kNJ = 257: one) are summed by the whole CTA instead
+        // of making one thread walk the cells twice
+        for (int j = kPiThreads; j < kNJ; ++j) {
+            const double pi = a + width * p.ts_s[j], q = (1.0 - b) + width * p.ts_c[j];
+            double l = 0.0;
+            for (int i = tid; i < cells; i += kPiThreads) l += cc[i] * log(pi * ca[i] + q * cb[i]);
+            l = block_sum(l, red);
+            if (tid == 0) { pj[j] = pi; lp[j] = log(pi); lq[j] = log(q); v[j] = l; }
+        }
+        {
+            const int j = tid;
             const double s = p.ts_s[j], c = p.ts_c[j];
             const double pi = a + width * s, q = (1.0 - b) + width * c;
             double l = 0.0;

@@ -436,6 +436,7 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
     mark('aggregate')
     # estimate_p_c skips barcodes below the read threshold (p_c.py:215-217): give them an empty histogram
     lens = off[1:] - off[:-1]
+    max_len = int(lens.max().item()) if lens.numel() else 1
     keep = total >= cell_threshold
     off_kept = torch.zeros_like(off)
     off_kept[1:] = torch.cumsum(torch.where(keep, lens, torch.zeros_like(lens)), 0)
@@ -447,13 +448,11 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
                n_with=n_with, hist=(k, nn, c, off), n_local_reads=n)
     if with_pi:
         ok = em_status == 0
-        pc_safe = torch.where(ok, p_c, torch.full_like(p_c, 0.5))
+        # barcodes without a usable p_c keep their rows but get p_c = NaN: dyn_pi_fit reports them at once
+        # (status 2) and nothing has to be compacted
+        pc_in = torch.where(ok, p_c, torch.full_like(p_c, float('nan')))
         pe_safe = torch.where(torch.isnan(p_e), torch.zeros_like(p_e), p_e)
-        off_pi = torch.zeros_like(off)
-        off_pi[1:] = torch.cumsum(torch.where(ok, lens, torch.zeros_like(lens)), 0)
-        row_ok = torch.repeat_interleave(ok, lens)
-        abp, pi_status = pi_fit(ctx, k[row_ok].contiguous(), nn[row_ok].contiguous(), c[row_ok].contiguous(), off_pi, pe_safe, pc_safe,
-                                max_cells=int(lens.max().item()) if lens.numel() else 1)
+        abp, pi_status = pi_fit(ctx, k, nn, c, off, pe_safe, pc_in, max_cells=max_len)
         pi_c = torch.where(ok & (pi_status == 0), abp[:, 2], torch.full_like(p_c, float('nan')))
         res.update(pi=abp, pi_status=pi_status, alpha=alpha(ctx, n_reads, n_with, pi_c))
         mark('pi')
