@@ -76,27 +76,27 @@ __device__ __forceinline__ void loglik_partial(const double *ca, const double *c
     }
 }
 
-// The same, by ONE warp (lanes over the cells, shuffle reduction): every lane gets the totals.
-__device__ __forceinline__ void loglik_warp(const double *ca, const double *cb, const double *cc, int cells, double pi,
-                                            double q, double &ll, double &dl) {
-    ll = 0.0; dl = 0.0;
+// By ONE warp (lanes over the cells, shuffle reduction), every lane gets the total: d/dpi log L (DERIV, no
+// logarithm needed) or log L (no division needed).
+template <bool DERIV>
+__device__ __forceinline__ double loglik_warp(const double *ca, const double *cb, const double *cc, int cells, double pi,
+                                              double q) {
+    double acc = 0.0;
     for (int i = threadIdx.x & 31; i < cells; i += 32) {
         const double m = pi * ca[i] + q * cb[i];
-        ll += cc[i] * log(m);
-        dl += cc[i] * (ca[i] - cb[i]) / m;
+        acc += DERIV ? cc[i] * (ca[i] - cb[i]) / m : cc[i] * log(m);
     }
-    for (int d = 16; d; d >>= 1) {
-        ll += __shfl_xor_sync(0xffffffffu, ll, d);
-        dl += __shfl_xor_sync(0xffffffffu, dl, d);
-    }
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    return acc;
 }
 
 constexpr int kSections = kPiThreads / 32 + 1;     // interior probe points per round = warps per CTA
-constexpr int kRounds = 11;                        // (1 / 9)^11 = 3e-11 of the starting interval
+constexpr int kRounds = 8;                         // (1 / 9)^8 = 2e-8 of the starting interval: the window edges sit where
+                                                   // the integrand is e^-60 of its maximum, the mode only fixes that level
 
 // Narrows [lo, hi] around the point where a monotone predicate flips, kSections-section search: in every round
 // warp w evaluates the likelihood at its own interior point and the CTA keeps the sub-interval of the flip --
-// 11 rounds of one barrier pair instead of 50-60 bisection steps of two block reductions each.
+// 8 rounds of one barrier pair instead of 50-60 bisection steps of two block reductions each.
 //   MODE = 0: predicate d/dpi log L > 0 (true left of the mode);  MODE = 1: log L >= thr, true right of the flip
 //   (left window edge);  MODE = 2: log L >= thr, true left of the flip (right window edge).
 template <int MODE>
@@ -106,10 +106,9 @@ __device__ __forceinline__ void section_search(const double *ca, const double *c
     for (int r = 0; r < kRounds; ++r) {
         const double step = (hi - lo) / kSections;
         const double x = lo + step * (w + 1);
-        double ll, dl;
-        loglik_warp(ca, cb, cc, cells, x, 1.0 - x, ll, dl);
+        const double val = loglik_warp<MODE == 0>(ca, cb, cc, cells, x, 1.0 - x);
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_val[w] = MODE == 0 ? dl : ll;
+        if ((threadIdx.x & 31) == 0) s_val[w] = val;
         __syncthreads();
         // first interior point where the predicate differs from its value at `lo`
         int f = kSections - 1;
@@ -128,8 +127,8 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
     double *ca = reinterpret_cast<double *>(smem_raw);        // [max_cells] scaled Binom(k|n,p_c)
     double *cb = ca + p.max_cells;                             // [max_cells] scaled Binom(k|n,p_e)
     double *cc = cb + p.max_cells;                             // [max_cells] read counts
-    double *tA = cc + p.max_cells;                             // [kNA][kChunk]
-    double *tB = tA + kNA * kChunk;                            // [kNA][kChunk]
+    double *tA = cc + p.max_cells;                             // [kChunk][kNA]
+    double *tB = tA + kNA * kChunk;                            // [kChunk][kNA]
     double *v = tB + kNA * kChunk;                             // [kNJ] w_j * L_j
     double *lp = v + kNJ + 1;                                  // [kNJ] log pi_j
     double *lq = lp + kNJ + 1;                                 // [kNJ] log (1 - pi_j)
@@ -245,8 +244,9 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
         for (int j0 = 0; j0 < kNJ; j0 += kChunk) {
             const int nj = min(kChunk, kNJ - j0);
             __syncthreads();
+            // tables are [node][hyper-parameter]: the 8 x 4 (resp. 4) values a warp reads per node are contiguous
             for (int e = tid; e < kNA * kChunk; e += kPiThreads) {
-                const int r = e / kChunk, jj = e % kChunk;
+                const int r = e % kNA, jj = e / kNA;
                 if (jj < nj) {
                     const double ex = exp(p.gl_x[r]) - 1.0;     // alpha_r - 1 == beta_r - 1 (same nodes)
                     tA[e] = exp(ex * lp[j0 + jj]) * v[j0 + jj];
@@ -254,14 +254,15 @@ __global__ void __launch_bounds__(kPiThreads) pi_kernel(const PiParams p) {
                 } else { tA[e] = 0.0; tB[e] = 0.0; }
             }
             __syncthreads();
-            const double *ra = tA + ai * kChunk;
             for (int jj = 0; jj < nj; ++jj) {
-                const double x = ra[jj], xp = x * pj[j0 + jj];
+                const double x = tA[jj * kNA + ai], xp = x * pj[j0 + jj];
+                const double2 y01 = *reinterpret_cast<const double2 *>(tB + jj * kNA + b0);
+                const double2 y23 = *reinterpret_cast<const double2 *>(tB + jj * kNA + b0 + 2);
+                const double y[4] = {y01.x, y01.y, y23.x, y23.y};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const double y = tB[(b0 + u) * kChunk + jj];
-                    m0[u] = fma(x, y, m0[u]);
-                    m1[u] = fma(xp, y, m1[u]);
+                    m0[u] = fma(x, y[u], m0[u]);
+                    m1[u] = fma(xp, y[u], m1[u]);
                 }
             }
         }
@@ -364,8 +365,9 @@ extern "C" int dyn_pi_fit(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n
     int rc = pi_tables(ctx, stream, &p.gl_x, &p.gl_w, &p.log_beta_fn, &p.ts_s, &p.ts_c, &p.ts_w);
     if (rc) return rc;
     if (max_cells < 1) max_cells = 1;
+    max_cells = (max_cells + 1) & ~(int64_t)1;      // even: the tables behind the three cell arrays stay 16-byte aligned
     const size_t fixed = sizeof(double) * (2 * kNA * kChunk + 4 * (kNJ + 1));
-    const size_t cap = (ctx->smem_optin - 2048 - fixed) / (3 * sizeof(double));
+    const size_t cap = ((ctx->smem_optin - 2048 - fixed) / (3 * sizeof(double))) & ~(size_t)1;
     if ((size_t)max_cells > cap) max_cells = (int64_t)cap;   // larger groups report status 3
     p.k = d_k; p.n = d_n;
     p.count = reinterpret_cast<const long long *>(d_count);
