@@ -34,27 +34,74 @@ __device__ __forceinline__ uint32_t col(const uint4 &c, int j) {
     return (w >> ((j & 3) << 3)) & 0xffu;
 }
 
-// ---- a9: 16-column sums per group. Consecutive surviving reads mostly differ in group, so the adds go
-// straight to L2 atomics; zero columns (most conversion columns) are skipped.
-__global__ void group_sums_kernel(const uint4 *counts, const uint8_t *strand, const uint32_t *group, const uint32_t *sel,
-                                  long long n_sel, long long n_groups, unsigned long long *sums,
-                                  unsigned long long *n_reads, unsigned long long *n_with, uint32_t conv_mask) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n_sel) return;
-    const long long r = sel ? (long long)sel[i] : i;
-    const uint32_t g = group ? group[r] : 0u;
-    if ((long long)g >= n_groups) return;
-    const uint4 c = load_row(counts, strand, r);
-    unsigned long long *row = sums + (size_t)g * 16;
-    uint32_t k = 0;
+// ---- a9: 16-column sums per group.  Surviving reads come in split-file order: a stretch of a few thousand rows
+// holds a few dozen barcodes.  Every CTA therefore sums its stretch into a small shared-memory table (open
+// addressing on the group id, 32-bit shared atomics) and flushes the occupied slots with one 64-bit L2 atomic per
+// non-zero counter; a row whose group finds no slot goes straight to L2.
+constexpr int kSumSlots = 128;          // table slots per CTA
+constexpr int kSumRowsPerThread = 8;    // rows per thread: kBlock * 8 = 2 048 rows per CTA
+
+__global__ void __launch_bounds__(kBlock) group_sums_kernel(const uint4 *counts, const uint8_t *strand, const uint32_t *group,
+                                                            const uint32_t *sel, long long n_sel, long long n_groups,
+                                                            unsigned long long *sums, unsigned long long *n_reads,
+                                                            unsigned long long *n_with, uint32_t conv_mask) {
+    __shared__ uint32_t s_key[kSumSlots];
+    __shared__ uint32_t s_val[kSumSlots][18];       // 16 columns, reads, reads with a conversion
+    for (int i = threadIdx.x; i < kSumSlots; i += kBlock) s_key[i] = 0xffffffffu;
+    for (int i = threadIdx.x; i < kSumSlots * 18; i += kBlock) (&s_val[0][0])[i] = 0u;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kBlock * kSumRowsPerThread;
+    for (int it = 0; it < kSumRowsPerThread; ++it) {
+        const long long i = base + (long long)it * kBlock + threadIdx.x;
+        if (i >= n_sel) break;
+        const long long r = sel ? (long long)sel[i] : i;
+        const uint32_t g = group ? group[r] : 0u;
+        if ((long long)g >= n_groups) continue;
+        const uint4 c = load_row(counts, strand, r);
+        uint32_t k = 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint32_t v = col(c, j);
-        if (v) atomicAdd(row + j, (unsigned long long)v);
-        if (j < 12 && ((conv_mask >> j) & 1u)) k += v;
+        for (int j = 0; j < 12; ++j)
+            if ((conv_mask >> j) & 1u) k += col(c, j);
+        // slot of the group (claimed on first use)
+        int slot = -1;
+        uint32_t h = (g * 0x9E3779B1u) >> 25;
+        for (int probe = 0; probe < 8; ++probe) {
+            const int sidx = (int)((h + probe) & (kSumSlots - 1));
+            const uint32_t cur = s_key[sidx];
+            if (cur == g) { slot = sidx; break; }
+            if (cur == 0xffffffffu) {
+                const uint32_t old = atomicCAS(&s_key[sidx], 0xffffffffu, g);
+                if (old == 0xffffffffu || old == g) { slot = sidx; break; }
+            }
+        }
+        if (slot >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t v = col(c, j);
+                if (v) atomicAdd(&s_val[slot][j], v);
+            }
+            atomicAdd(&s_val[slot][16], 1u);
+            if (k > 0) atomicAdd(&s_val[slot][17], 1u);
+        } else {
+            unsigned long long *row = sums + (size_t)g * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t v = col(c, j);
+                if (v) atomicAdd(row + j, (unsigned long long)v);
+            }
+            if (n_reads) atomicAdd(n_reads + g, 1ull);
+            if (n_with && k > 0) atomicAdd(n_with + g, 1ull);
+        }
     }
-    if (n_reads) atomicAdd(n_reads + g, 1ull);
-    if (n_with && k > 0) atomicAdd(n_with + g, 1ull);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kSumSlots * 18; e += kBlock) {
+        const int slot = e / 18, j = e % 18;
+        const uint32_t g = s_key[slot], v = s_val[slot][j];
+        if (g == 0xffffffffu || v == 0u) continue;
+        if (j < 16) atomicAdd(sums + (size_t)g * 16 + j, (unsigned long long)v);
+        else if (j == 16) { if (n_reads) atomicAdd(n_reads + g, (unsigned long long)v); }
+        else if (n_with) atomicAdd(n_with + g, (unsigned long long)v);
+    }
 }
 
 // ---- a9 / a11: rates and p_e from the sums (uint32 wrap as in `.astype(np.uint32)`, aggregation.py:76)
@@ -193,7 +240,7 @@ extern "C" int dyn_group_sums(dyn_ctx_t *ctx, const uint8_t *d_counts, const uin
     if (d_n_with) DYN_CUDA(cudaMemsetAsync(d_n_with, 0, sizeof(uint64_t) * n_groups, stream));
     if (n_sel == 0) return DYN_OK;
     DYN_ARG(d_counts != nullptr, "null counts");
-    group_sums_kernel<<<grid_for(n_sel), kBlock, 0, stream>>>(
+    group_sums_kernel<<<(unsigned)((n_sel + kBlock * kSumRowsPerThread - 1) / (kBlock * kSumRowsPerThread)), kBlock, 0, stream>>>(
         reinterpret_cast<const uint4 *>(d_counts), d_strand, d_group, d_sel, n_sel, n_groups,
         reinterpret_cast<unsigned long long *>(d_sums), reinterpret_cast<unsigned long long *>(d_n_reads),
         reinterpret_cast<unsigned long long *>(d_n_with), conv_mask & 0xfffu);
