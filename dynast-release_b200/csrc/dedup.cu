@@ -20,6 +20,8 @@
 
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int kBlock = 256;
@@ -40,16 +42,30 @@ __global__ void complement_kernel(uint4 *counts, const uint8_t *strand, long lon
     counts[i] = complement_row(counts[i]);
 }
 
+// first read of every barcode (in the order of the reference's split plan) and reads per barcode.  First
+// occurrences sit at the very beginning of the array, so the 64-bit atomicMin is almost always skipped by a plain
+// load; the counters are privatised per CTA in shared memory when the barcode table fits (HIST).
+template <bool HIST>
 __global__ void first_pos_kernel(const uint32_t *barcode, const uint8_t *strand, const uint16_t *conv_n, long long n,
                                  long long n_barcodes, unsigned long long *first_pos, uint32_t *n_reads) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t b = barcode[i];
-    if (b >= (unsigned long long)n_barcodes) return;
-    const unsigned long long pos = ((unsigned long long)(strand[i] != 0) << 33) |
-                                   ((unsigned long long)(conv_n[i] == 0) << 32) | (unsigned long long)i;
-    atomicMin(first_pos + b, pos);
-    atomicAdd(n_reads + b, 1u);
+    extern __shared__ uint32_t s_hist[];
+    if (HIST) {
+        for (long long b = threadIdx.x; b < n_barcodes; b += blockDim.x) s_hist[b] = 0u;
+        __syncthreads();
+    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t b = barcode[i];
+        if (b >= (unsigned long long)n_barcodes) continue;
+        const unsigned long long pos = ((unsigned long long)(strand[i] != 0) << 33) |
+                                       ((unsigned long long)(conv_n[i] == 0) << 32) | (unsigned long long)i;
+        if (pos < *reinterpret_cast<volatile unsigned long long *>(first_pos + b)) atomicMin(first_pos + b, pos);
+        if (HIST) atomicAdd(&s_hist[b], 1u); else atomicAdd(n_reads + b, 1u);
+    }
+    if (HIST) {
+        __syncthreads();
+        for (long long b = threadIdx.x; b < n_barcodes; b += blockDim.x)
+            if (s_hist[b]) atomicAdd(n_reads + b, s_hist[b]);
+    }
 }
 
 struct DedupIn {
@@ -151,9 +167,18 @@ extern "C" int dyn_barcode_first_pos(dyn_ctx_t *ctx, const uint32_t *d_barcode, 
     DYN_CUDA(cudaMemsetAsync(d_n_reads, 0, sizeof(uint32_t) * n_barcodes, stream));
     if (n_reads == 0) return DYN_OK;
     DYN_ARG(d_barcode && d_strand && d_conv_n, "null buffer");
-    first_pos_kernel<<<grid_for(n_reads), kBlock, 0, stream>>>(d_barcode, d_strand, d_conv_n, n_reads, n_barcodes,
-                                                               reinterpret_cast<unsigned long long *>(d_first_pos),
-                                                               d_n_reads);
+    const size_t hist_bytes = sizeof(uint32_t) * (size_t)n_barcodes;
+    if (hist_bytes <= 64 * 1024) {
+        DYN_CUDA(cudaFuncSetAttribute(first_pos_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+        const unsigned grid = (unsigned)std::min<long long>((long long)ctx->sm_count * 3, (n_reads + kBlock - 1) / kBlock);
+        first_pos_kernel<true><<<grid, kBlock, hist_bytes, stream>>>(d_barcode, d_strand, d_conv_n, n_reads, n_barcodes,
+                                                                    reinterpret_cast<unsigned long long *>(d_first_pos),
+                                                                    d_n_reads);
+    } else {
+        first_pos_kernel<false><<<grid_for(n_reads), kBlock, 0, stream>>>(d_barcode, d_strand, d_conv_n, n_reads, n_barcodes,
+                                                                         reinterpret_cast<unsigned long long *>(d_first_pos),
+                                                                         d_n_reads);
+    }
     DYN_CUDA(cudaGetLastError());
     return DYN_OK;
 }
