@@ -143,3 +143,46 @@ def test_no_emit_and_empty(gpu_ctx, oracle_lib):
     assert (gpu['counts'] == orc['counts']).all()
     empty = device.tally_reads_host(np.zeros(0, np.uint8), np.zeros(1, np.uint32))
     assert empty['counts'].shape == (0, 16) and empty['total'] == 0
+
+
+@pytest.mark.parametrize('paired', [False, True])
+def test_conversion_capacity(gpu_ctx, oracle_lib, paired):
+    """A mismatch-record buffer that is too small: DYN_ST_CONV_CAPACITY is raised, counters are unaffected, a read
+    either has all of its records (inside the buffer) or reports none -- on the tile kernel and on the sequential
+    kernel (paired units)."""
+    import torch
+    from oracle import pack
+    from dynast_b200 import pipeline, records as rec, synth
+    if paired:
+        blob, off, meta, refs = pack.units_from_bam(ref_path('smartseq_align', 'Aligned.sortedByCoord.out.bam'), rec.pack_one,
+                                                    rec.pack_units, umi_tag=None, barcode_tag='RG', velocity=False)
+    else:
+        d = synth.make_reads(5000, seed=41, p_e=0.01)
+        blob, off = d['blob'], d['rec_off']
+    orc = pack.run_tally(blob, off, quality=27)
+    n = len(off) - 1
+    cap = orc['total'] // 2
+    assert cap > 10
+    ctx = pipeline.Context.get(0)
+    out = pipeline.TallyBuffers(n, cap, device=0)
+    pipeline.tally_reads(ctx, torch.from_numpy(np.ascontiguousarray(blob)).cuda(), torch.from_numpy(off.view(np.int32)).cuda(), out,
+                         quality=27)
+    torch.cuda.synchronize()
+    status = int(out.scalars[1].item()) & 0xffffffff
+    assert status & 0x8 and int(out.scalars[0].item()) == orc['total']
+    assert (out.counts.cpu().numpy() == orc['counts']).all()
+    conv_n = out.conv_n.cpu().numpy().view(np.uint16)
+    conv_off = out.conv_off.cpu().numpy().view(np.uint32)
+    conv_rec = out.conv_rec.cpu().numpy().view(np.uint64)
+    conv_read = out.conv_read.cpu().numpy().view(np.uint32)
+    kept = dropped = 0
+    for i in range(n):
+        want = orc['conv_rec'][orc['conv_off'][i]:orc['conv_off'][i] + orc['conv_n'][i]]
+        if conv_n[i]:
+            assert conv_off[i] + conv_n[i] <= cap
+            assert (conv_rec[conv_off[i]:conv_off[i] + conv_n[i]] == want).all()
+            assert (conv_read[conv_off[i]:conv_off[i] + conv_n[i]] == i).all()
+            kept += 1
+        elif len(want):
+            dropped += 1
+    assert kept > 0 and dropped > 0
