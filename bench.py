@@ -441,12 +441,16 @@ def main():
         k, n, c, off, pe = build_em_batch_gpu(nb, 2004 + rank, device)
         # rank-local histogram rows with global barcode ids; the EM of barcode b runs on rank b % world after
         # an all-gather of the rows (NCCL over NVLink) -- the one exchange of the path
+        # global barcode id = local * world + (local + rank) % world: a rank's barcodes are owned by all ranks in turn, so
+        # (world - 1) / world of its histogram rows really cross NVLink, as they do when every rank tallies a read range
         local_b = torch.repeat_interleave(torch.arange(nb, device=device), off[1:] - off[:-1])
-        rows = torch.stack([local_b * world + rank, k.long(), n.long(), c], dim=1).contiguous()
+        rows = torch.stack([local_b * world + (local_b + rank) % world, k.long(), n.long(), c], dim=1).to(torch.int32).contiguous()
         if dist is not None:
             pe_all = torch.empty(n_global, dtype=torch.float64, device=device)
             dist.all_gather_into_tensor(pe_all, pe.contiguous())
-            pe_global = pe_all.view(world, nb).t().reshape(-1).contiguous()      # barcode id = local * world + rank
+            gid = torch.arange(n_global, device=device)
+            loc = gid // world
+            pe_global = pe_all.view(world, nb)[(gid % world - loc) % world, loc].contiguous()
         else:
             pe_global = pe
         iters_box = {}
@@ -481,7 +485,7 @@ def main():
               'barcodes': n_global, 'ms': em_ms, 'ok_fraction': float((st_em == 0).float().mean().item()),
               'mean_iters': float(iters.float().mean().item()), 'workload': 'C4: k<=30, n<=150, 1% adversarial full shape',
               'dtype': 'f64 E step / f32 M step (as the reference)',
-              'exchange': 'none (1 GPU)' if dist is None else 'all-gather of (barcode,k,n,count) rows + all-gather of p_c inside the timed region'}
+              'exchange': 'none (1 GPU)' if dist is None else 'all-to-all of (barcode,k,n,count) rows to the barcode owner + all-gather of p_c inside the timed region'}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, N = 1)
     cpu_baseline = None

@@ -1,10 +1,11 @@
 """Multi-GPU plumbing of the count -> estimate path: one process per GPU, torch.distributed.
 
 The path shards without a data-path collective up to the per-barcode histograms: every rank tallies (and, for UMI
-data whose barcodes are rank-local, deduplicates) its own read range.  The one exchange the north star names is
-the all-gather of per-barcode (k, n) histograms before the EM: a barcode's reads may sit in several read ranges,
-and the EM needs the barcode's whole histogram.  After the gather the EM is partitioned by barcode
-(owner = barcode mod world) and the 8-byte results are gathered back.  Works with NCCL (device tensors) and
+data whose barcodes are rank-local, deduplicates) its own read range.  The exchange the north star names is that of
+the per-barcode (k, n) histograms before the EM: a barcode's reads may sit in several read ranges, and the EM needs
+the barcode's whole histogram.  The EM is partitioned by barcode (owner = barcode mod world): every rank sends its
+sparse histogram rows to their owners (all-to-all; the all-gather form moves world times more) and the 8-byte
+results are gathered back.  Works with NCCL (device tensors) and
 with gloo (CPU tensors; used by the CPU tests for the exchange logic)."""
 from typing import Callable, Optional, Tuple
 
@@ -36,24 +37,27 @@ def owned_csr(rows: torch.Tensor, n_barcodes: int, rank: int, world: int):
     order = torch.argsort(mine[:, 0], stable=True)
     mine = mine[order]
     owned = torch.arange(rank, n_barcodes, world, dtype=torch.int64, device=rows.device)
-    local = torch.div(mine[:, 0] - rank, world, rounding_mode='floor')
+    local = torch.div(mine[:, 0] - rank, world, rounding_mode='floor').to(torch.int64)
     off = torch.zeros(owned.numel() + 1, dtype=torch.int64, device=rows.device)
     if mine.shape[0]:
         off[1:] = torch.cumsum(torch.bincount(local, minlength=owned.numel()), 0)
-    return owned, mine[:, 1].to(torch.int32).contiguous(), mine[:, 2].to(torch.int32).contiguous(), mine[:, 3].contiguous(), off
+    return (owned, mine[:, 1].to(torch.int32).contiguous(), mine[:, 2].to(torch.int32).contiguous(),
+            mine[:, 3].to(torch.int64).contiguous(), off)
 
 
 def distributed_p_c(rows: torch.Tensor, p_e: torch.Tensor, n_barcodes: int,
                     em: Callable[[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
                     group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """p_c of every barcode from rank-local histogram rows.
-    rows: [m, 4] int64 (global barcode id, k, n, read count) of this rank's read range; p_e: [n_barcodes] float64
+    rows: [m, 4] int64 or int32 (global barcode id, k, n, read count) of this rank's read range; p_e: [n_barcodes] float64
     (identical on every rank); em(k, n, count, off, p_e_owned) -> (p_c, status) for CSR groups -- the EM kernel
     (pipeline.em_pc) on a GPU.  Returns (p_c [n_barcodes] float64, status [n_barcodes] int32) on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    all_rows = all_gather_rows(rows, group) if world > 1 else rows
-    owned, k, n, c, off = owned_csr(all_rows, n_barcodes, rank, world)
+    # every rank needs only the rows of the barcodes it owns: an all-to-all by owner moves 1/world of what the
+    # all-gather of the histograms would (all_gather_rows stays available for callers that want every row everywhere)
+    mine = exchange_by_owner(rows[:, 0] % world, rows, group=group)[0] if world > 1 else rows
+    owned, k, n, c, off = owned_csr(mine, n_barcodes, rank, world)
     p_c_own, st_own = em(k, n, c, off, p_e[owned])
     if world == 1:
         return p_c_own, st_own
