@@ -188,7 +188,8 @@ __global__ void classify_groups_kernel(const uint32_t *g_left, const uint32_t *g
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g > n_groups) return;
     unsigned long long w = 0;
-    if (g < n_groups && g_left[g] != 0xffffffffu && group_off[g + 1] - group_off[g] <= 256) w = min(g_nref[g], (uint32_t)kWin);
+    if (g < n_groups && g_left[g] != 0xffffffffu && group_off[g + 1] - group_off[g] <= 256)
+        w = (min(g_nref[g], (uint32_t)kWin) + 3u) & ~3u;      // multiple of 4: a group's cells start 16-byte aligned
     win[g] = w;        // win[n_groups] = 0: the exclusive scan's total lands there
 }
 
@@ -226,8 +227,8 @@ __device__ __forceinline__ int block_slot(int *blk_id, int blk) {
 
 __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t *records, const uint32_t *item_rec16,
                                                                   const long long *group_off, long long n_groups,
-                                                                  unsigned long long *win, const unsigned long long *cell_start,
-                                                                  int quality, unsigned long long *cell_key, uint32_t *cell,
+                                                                  const uint32_t *g_left, unsigned long long *win,
+                                                                  const unsigned long long *cell_start, int quality, uint32_t *cell,
                                                                   uint32_t *cell_cnt, int32_t *status) {
     __shared__ __align__(8) uint16_t s_qs[kDirectWarps][kWin][4];
     __shared__ uint8_t s_meta[kDirectWarps][kWin];      // bit 2 covered, bits 0..1 first-seen reference base
@@ -330,9 +331,14 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
         const uint32_t used = __ballot_sync(0xffffffffu, my_blk != kNoBlock);
         const int n_blk = __popc(used);
         uint32_t my_key = my_blk == kNoBlock ? 0xffffffffu : (uint32_t)my_blk;
+        // A direct cell carries, in its upper half, the number of reference positions skipped since the previous
+        // cell (the first one: since the group's leftmost start) -- no 8-byte key per cell; a gap that does not fit
+        // 16 bits sends the group to the sorted path.
         const unsigned long long base = cell_start[g];
         const unsigned long long cap = win[g];
         uint32_t run = 0;
+        uint32_t next_pos = g_left[g];          // position right after the previous cell
+        bool wide = false;
         for (int r = 0; r < n_blk; ++r) {
             const uint32_t lowest = __reduce_min_sync(0xffffffffu, my_key);
             const int sl = __ffs((int)__ballot_sync(0xffffffffu, my_key == lowest)) - 1;   // its slot
@@ -344,17 +350,20 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
             const uint32_t ballot = __ballot_sync(0xffffffffu, covered);
             if (covered) {
                 const uint32_t s[4] = {qs[w][0], qs[w][1], qs[w][2], qs[w][3]};
-                const unsigned long long k = run + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
-                if (k < cap) {
-                    cell_key[base + k] = ((unsigned long long)g << 32) | (uint32_t)(blk * kBlk + lane);
-                    cell[base + k] = call_cell(s, (int)(m & 3), quality);
-                }
+                const uint32_t below = ballot & ((1u << lane) - 1u);
+                const unsigned long long k = run + (uint32_t)__popc(below);
+                const uint32_t pos = (uint32_t)(blk * kBlk + lane);
+                const uint32_t gap = below ? (uint32_t)(lane - (31 - __clz((int)below)) - 1) : pos - next_pos;
+                if (gap > 0xffffu) wide = true;
+                if (k < cap) cell[base + k] = call_cell(s, (int)(m & 3), quality) | (gap << 16);
             }
+            if (ballot) next_pos = (uint32_t)(blk * kBlk) + (uint32_t)(31 - __clz((int)ballot)) + 1u;
             run += (uint32_t)__popc(ballot);
             // leave the block clean for the next group
             *reinterpret_cast<uint2 *>(qs[w]) = make_uint2(0u, 0u);
             meta[w] = 0;
         }
+        full = full || __any_sync(0xffffffffu, wide);
         __syncwarp();
         blk_id[lane] = kNoBlock;
         __syncwarp();
@@ -410,7 +419,7 @@ __device__ __forceinline__ uint8_t *put_num(uint8_t *p, uint32_t v) {
 // One thread per group. WRITE=false: sizes only (stored in `sizes`); WRITE=true: the record at out + 16 * out_off[g].
 template <bool WRITE>
 __global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint32_t *cell_s, const long long *n_cells_p,
-                                const unsigned long long *cell_key_d, const uint32_t *cell_d, const unsigned long long *win,
+                                const uint32_t *cell_d, const unsigned long long *win,
                                 const unsigned long long *cell_start, const uint32_t *cell_cnt, long long n_groups,
                                 const uint32_t *g_left, const uint32_t *g_right, const int32_t *g_ref,
                                 GroupOut *sizes, uint32_t *out_cap16, uint32_t *md_cap, const uint32_t *out_off, uint8_t *out,
@@ -419,14 +428,15 @@ __global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     // cells of the group: direct_kernel's groups know their range; the sorted path's cells are ordered by (group, position)
+    // cells of the group: direct_kernel's groups know their range (gap-encoded positions, see there); the sorted path's
+    // cells are ordered by (group, position)
+    const bool direct = win[g] != 0ull;
     long long c0, c1;
-    const unsigned long long *cell_key = cell_key_s;
-    const uint32_t *cell = cell_s;
-    if (win[g] != 0ull) { cell_key = cell_key_d; cell = cell_d; c0 = (long long)cell_start[g]; c1 = c0 + cell_cnt[g]; }
+    if (direct) { c0 = (long long)cell_start[g]; c1 = c0 + cell_cnt[g]; }
     else {
         long long lo = 0, hi = *n_cells_p;
         c1 = hi;
-        while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)(cell_key[mid] >> 32) < g) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)(cell_key_s[mid] >> 32) < g) lo = mid + 1; else hi = mid; }
         c0 = lo;
     }
     const uint32_t left = g_left[g], right = g_right[g];
@@ -478,8 +488,7 @@ __global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint
     uint32_t seq_acc = 0, qual_acc = 0;
     uint32_t prev = left;    // next expected reference position
     if (!empty) {
-        for (long long c = c0; c < c1 && (long long)(cell_key[c] >> 32) == g; ++c) {
-            const uint32_t pos = (uint32_t)cell_key[c], v = cell[c];
+        auto cell_step = [&](uint32_t pos, uint32_t v) {
             cigar_push(3, pos - prev);                 // positions nobody observed (consensus.py:109-111)
             prev = pos + 1;
             const uint32_t ref = (v >> 2) & 3u;
@@ -511,6 +520,18 @@ __global__ void assemble_kernel(const unsigned long long *cell_key_s, const uint
                 }
                 ++l_seq;
             }
+        };
+        if (direct) {
+            // four 4-byte cells per 16-byte load (the group's range starts 16-byte aligned)
+            for (long long c = c0; c < c1; c += 4) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(cell_d + c);
+                const uint32_t vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c + u < c1) cell_step(prev + (vv[u] >> 16), vv[u]);
+            }
+        } else {
+            for (long long c = c0; c < c1 && (long long)(cell_key_s[c] >> 32) == g; ++c) cell_step((uint32_t)cell_key_s[c], cell_s[c]);
         }
         cigar_push(3, right - prev);
     }
@@ -605,13 +626,12 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     unsigned long long n_direct = 0, n_tuples = 0;
     DYN_CUDA(cudaMemcpyAsync(&n_direct, cell_start + n_groups, 8, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaStreamSynchronize(stream));      // the direct path's cell arrays are sized from this total
-    unsigned long long *cell_key_d = nullptr, *cell_key = nullptr;
+    unsigned long long *cell_key = nullptr;
     uint32_t *cell_d = nullptr, *cell = nullptr;
     if (n_direct > 0) {
         Arena a1;
         for (int pass = 0; pass < 2; ++pass) {
-            cell_key_d = a1.take<unsigned long long>((size_t)n_direct);
-            cell_d = a1.take<uint32_t>((size_t)n_direct);
+            cell_d = a1.take<uint32_t>((size_t)n_direct + 4);
             if (pass == 0) {
                 void *base = nullptr;
                 int rc = dyn_ctx_scratch(ctx, 13, a1.used + 256, &base);
@@ -623,8 +643,8 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
         DYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, direct_kernel, 32 * kDirectWarps, 0));
         if (per_sm < 1) per_sm = 1;
         long long grid = std::min<long long>((long long)ctx->sm_count * per_sm, (n_groups + kDirectWarps - 1) / kDirectWarps);
-        direct_kernel<<<(unsigned)grid, 32 * kDirectWarps, 0, stream>>>(records, d_item_rec16, group_off, n_groups, win, cell_start,
-                                                                        quality, cell_key_d, cell_d, cell_cnt, d_out_status);
+        direct_kernel<<<(unsigned)grid, 32 * kDirectWarps, 0, stream>>>(records, d_item_rec16, group_off, n_groups, g_left, win,
+                                                                        cell_start, quality, cell_d, cell_cnt, d_out_status);
         DYN_CUDA(cudaGetLastError());
     }
 
@@ -686,7 +706,7 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     }
 
     // ---- assemble: sizes, offsets, records
-    assemble_kernel<false><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, cell_key_d, cell_d, win, cell_start,
+    assemble_kernel<false><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, cell_d, win, cell_start,
                                                                      cell_cnt, n_groups, g_left, g_right, g_ref, sizes,
                                                                      out_cap16, md_cap, nullptr, nullptr, 0, nullptr, nullptr, 0,
                                                                      d_out_nm, d_out_status);
@@ -696,7 +716,7 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
     DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, out_cap16, d_out_off, n_groups + 1, stream));
     t = scan_tmp;
     DYN_CUDA(cub::DeviceScan::ExclusiveSum(tmp0, t, md_cap, d_out_md_off, n_groups + 1, stream));
-    assemble_kernel<true><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, cell_key_d, cell_d, win, cell_start,
+    assemble_kernel<true><<<grid_for(n_groups), kBlock, 0, stream>>>(cell_key, cell, n_cells, cell_d, win, cell_start,
                                                                     cell_cnt, n_groups, g_left, g_right, g_ref, sizes,
                                                                     out_cap16, md_cap, d_out_off, static_cast<uint8_t *>(d_out_records),
                                                                     out_capacity_bytes >> 4, d_out_md_off,

@@ -186,3 +186,21 @@ def test_deep_groups_both_paths(gpu_ctx):
             reads.append(make_read(f'd{depth}r{r}', pos, cigar, seq, qual, md, ref_id=1))
         groups.append(reads)
     check_groups(groups)
+
+
+def test_long_introns(gpu_ctx):
+    """Gaps between covered positions: up to 65 535 skipped positions ride in the direct path's cells, longer ones send
+    the group to the sorted path."""
+    from oracle.consensus_oracle import make_read
+    rng = np.random.default_rng(13)
+    genome = [LETTERS[i] for i in rng.integers(0, 4, 200000)]
+    groups = []
+    for gap in (1000, 65535, 65536, 150000):
+        reads = []
+        for r in range(3):
+            pos = int(rng.integers(0, 30))
+            cigar = [('M', 40), ('N', gap - r), ('M', 35)]
+            seq, qual, md = simulate_read(rng, genome, pos, cigar)
+            reads.append(make_read(f'i{gap}r{r}', pos, cigar, seq, qual, md, ref_id=0))
+        groups.append(reads)
+    check_groups(groups)
