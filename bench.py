@@ -193,6 +193,26 @@ def cpu_em_baseline(k, n, c, off, pe, n_threads):
     return B / dt, np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
 
 
+def bind_near_gpu(index):
+    """Several ranks on one box: keep this process (and the page-locked buffers it allocates, first-touch placement)
+    on the CPUs NVML reports as local to its GPU, so that the host-buffer legs do not cross the socket interconnect.
+    Returns the number of CPUs bound to, or None when NVML gives no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [i for i in range(n_cpu) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     args = parse_args()
     import torch
@@ -204,6 +224,7 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device; dynast_b200 has no CPU fallback'
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else None
     dist = None
     if world > 1 and args.impl != 'reference':
         import torch.distributed as dist
@@ -218,7 +239,7 @@ def main():
         'workload': 'C2 synthetic scSLAM-seq-like 10x BAM records: 50M reads x 91 nt, 10k barcodes, TC, per GPU',
         'reads_per_gpu': n_reads, 'barcodes_per_gpu': args.barcodes, 'read_len': 91, 'quality': 27,
         'l2_policy': 'inputs (~8.8 GB packed records per step) are far larger than the 126 MB L2',
-        'parallelism': f'read-range x{world}',
+        'parallelism': f'read-range x{world}', 'cpus_bound_near_gpu': numa,
     }
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
