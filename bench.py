@@ -399,6 +399,11 @@ def main():
             barrier()
             per_rep.append(t_rep)
             rep_ms.append(p0.elapsed_time(p1))
+            if os.environ.get('DYN_BENCH_DEBUG'):
+                st = torch.cuda.memory_stats()
+                sys.stderr.write('alloc stats: device_alloc %d device_free %d retries %d reserved %.1f GB active %.1f GB\n' % (
+                    st.get('num_device_alloc', -1), st.get('num_device_free', -1), st.get('num_alloc_retries', -1),
+                    st.get('reserved_bytes.all.current', 0) / 1e9, st.get('active_bytes.all.current', 0) / 1e9))
         if os.environ.get('DYN_BENCH_DEBUG'):
             sys.stderr.write('pipeline per rep: %r %r\n' % (rep_ms, per_rep))
         # best of the repetitions, all of them listed: several stages are host-driven (split plan, shape discovery,
@@ -465,7 +470,8 @@ def main():
         # global barcode id = local * world + (local + rank) % world: a rank's barcodes are owned by all ranks in turn, so
         # (world - 1) / world of its histogram rows really cross NVLink, as they do when every rank tallies a read range
         local_b = torch.repeat_interleave(torch.arange(nb, device=device), off[1:] - off[:-1])
-        rows = torch.stack([local_b * world + (local_b + rank) % world, k.long(), n.long(), c], dim=1).to(torch.int32).contiguous()
+        em_keys = (((local_b * world + (local_b + rank) % world) << 22) | (k.long() << 10) | n.long()).contiguous()
+        em_cnt32 = c.to(torch.int32).contiguous()
         if dist is not None:
             pe_all = torch.empty(n_global, dtype=torch.float64, device=device)
             dist.all_gather_into_tensor(pe_all, pe.contiguous())
@@ -484,7 +490,7 @@ def main():
         def em_step():
             if dist is None:      # one GPU: the CSR histograms go straight to the kernel, there is nothing to exchange
                 return em_fn(k, n, c, off, pe)
-            return distributed.distributed_p_c(rows, pe_global, n_global, em_fn)
+            return distributed.distributed_p_c_keys(ctx, em_keys, em_cnt32, pe_global, n_global, em_fn)
 
         for _ in range(2):
             p_c, st_em = em_step()
@@ -506,7 +512,7 @@ def main():
               'barcodes': n_global, 'ms': em_ms, 'ok_fraction': float((st_em == 0).float().mean().item()),
               'mean_iters': float(iters.float().mean().item()), 'workload': 'C4: k<=30, n<=150, 1% adversarial full shape',
               'dtype': 'f64 E step / f32 M step (as the reference)',
-              'exchange': 'none (1 GPU)' if dist is None else 'all-to-all of (barcode,k,n,count) rows to the barcode owner + all-gather of p_c inside the timed region'}
+              'exchange': 'none (1 GPU)' if dist is None else 'all-to-all of (barcode,k,n) keys + counts to the barcode owner, device merge + CSR, all-gather of p_c: inside the timed region'}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, N = 1)
     cpu_baseline = None

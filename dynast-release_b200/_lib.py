@@ -45,6 +45,7 @@ PROTOTYPES = {
     'dyn_owner_partition': (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     'dyn_pack_reads': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_unpack_reads': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'dyn_merge_kn': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     'dyn_bam_pack': (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
     'dyn_bam_result_free': (None, [_vp]),
     'dyn_bam_n_units': (_i64, [_vp]),

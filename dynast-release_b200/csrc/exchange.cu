@@ -8,6 +8,9 @@
 //   dyn_pack_reads       gathers the struct-of-arrays columns of the partitioned reads into 40-byte rows, so the
 //                        exchange is ONE all-to-all of one buffer
 //   dyn_unpack_reads     rows -> columns on the receiving side
+//   dyn_merge_kn         the histogram exchange before the EM (no-UMI variant of SURVEY 8e): (group, k, n) rows with
+//                        read counts received from several ranks -> one sorted row per key with the counts summed,
+//                        group ids rewritten to the owner's local numbering (global id / world)
 // HBM-bound streaming passes: 38 B of columns in, 40 B out per read (and back).
 #include <cub/cub.cuh>
 
@@ -88,6 +91,13 @@ __global__ void unpack_kernel(const ReadRow *rows, long long n, uint4 *counts, u
     transcriptome[i] = r.transcriptome;
 }
 
+__global__ void localise_keys_kernel(const unsigned long long *in, long long n, uint32_t world, unsigned long long *out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = in[i];
+    out[i] = (((k >> 22) / world) << 22) | (k & 0x3fffffull);
+}
+
 }  // namespace
 
 extern "C" int dyn_owner_partition(dyn_ctx_t *ctx, const uint32_t *d_barcode, int64_t n, int world, uint32_t *d_perm,
@@ -158,5 +168,51 @@ extern "C" int dyn_unpack_reads(dyn_ctx_t *ctx, const void *d_rows, int64_t n, u
         static_cast<const ReadRow *>(d_rows), n, reinterpret_cast<uint4 *>(d_counts), d_barcode,
         reinterpret_cast<unsigned long long *>(d_umi), d_gene, d_score, d_conv_n, d_strand, d_transcriptome);
     DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}
+
+extern "C" int dyn_merge_kn(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count, int64_t n, int world, int group_bits,
+                            uint64_t *d_out_keys, uint32_t *d_out_count, int64_t *d_n_rows, void *stream) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n >= 0 && n < 0x7fffffffll, "bad n");
+    DYN_ARG(world >= 1 && world <= DYN_MAX_WORLD, "world out of range");
+    DYN_ARG(d_n_rows != nullptr, "null n_rows");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DYN_CUDA(cudaMemsetAsync(d_n_rows, 0, sizeof(int64_t), st));
+    if (n == 0) return DYN_OK;
+    DYN_ARG(d_keys && d_count && d_out_keys && d_out_count, "null buffer");
+    int end_bit = 22 + (group_bits > 0 && group_bits <= 42 ? group_bits : 42);
+    size_t t0 = 0, t1 = 0;
+    {
+        cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t0, k, v, (int)n, 0, end_bit, st));
+        DYN_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, t1, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                                (const uint32_t *)nullptr, (uint32_t *)nullptr, (long long *)nullptr, cub::Sum(),
+                                                (int)n, st));
+    }
+    const size_t temp = std::max(t0, t1);
+    Arena sizing;
+    for (int pass = 0; pass < 2; ++pass) {
+        void *base = nullptr;
+        if (pass == 1) {
+            int rc = dyn_ctx_scratch(ctx, 16, sizing.used + 256, &base);
+            if (rc) return rc;
+        }
+        Arena a(base);
+        unsigned long long *ka = a.take<unsigned long long>((size_t)n), *kb = a.take<unsigned long long>((size_t)n);
+        uint32_t *va = a.take<uint32_t>((size_t)n), *vb = a.take<uint32_t>((size_t)n);
+        uint8_t *tmp = a.take<uint8_t>(temp);
+        if (pass == 0) { sizing = a; continue; }
+        localise_keys_kernel<<<grid_for(n), kBlock, 0, st>>>(reinterpret_cast<const unsigned long long *>(d_keys), n, (uint32_t)world, ka);
+        DYN_CUDA(cudaMemcpyAsync(va, d_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+        cub::DoubleBuffer<unsigned long long> k(ka, kb);
+        cub::DoubleBuffer<uint32_t> v(va, vb);
+        size_t t = temp;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, (int)n, 0, end_bit, st));
+        t = temp;
+        DYN_CUDA(cub::DeviceReduce::ReduceByKey(tmp, t, k.Current(), reinterpret_cast<unsigned long long *>(d_out_keys), v.Current(),
+                                                d_out_count, reinterpret_cast<long long *>(d_n_rows), cub::Sum(), (int)n, st));
+    }
     return DYN_OK;
 }

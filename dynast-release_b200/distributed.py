@@ -125,3 +125,51 @@ def exchange_reads(ctx, barcode, umi, gene, score16, conv_n, strand, counts, wor
     got = torch.empty((sum(recv_split), rows.shape[1]), dtype=rows.dtype, device=rows.device)
     dist.all_to_all_single(got, rows, output_split_sizes=recv_split, input_split_sizes=send_split, group=group)
     return pipeline.unpack_reads(ctx, got)
+
+
+def exchange_kn_rows(ctx, keys, count32, n_barcodes: int, world: int, rank: int, group=None):
+    """The histogram exchange on device tensors (no per-read exchange ran: every rank holds partial histograms of
+    its read range).  keys: int64 (global barcode << 22 | k << 10 | n), count32: int32 reads per row.  Rows go to
+    rank barcode % world in ONE partition + two all-to-alls, and the owner merges what it received
+    (dyn_owner_partition, dyn_merge_kn, dyn_kn_csr).  Returns (owned barcode ids, k, n, count, off): the CSR
+    histograms of the barcodes this rank owns, local barcode j = global barcode rank + j * world."""
+    from . import pipeline
+    if world > 1:
+        perm, owner_counts = pipeline.owner_partition(ctx, (keys >> 22).to(torch.int32), world)
+        order = perm.to(torch.int64)
+        recv_counts = torch.empty_like(owner_counts)
+        dist.all_to_all_single(recv_counts, owner_counts, group=group)
+        send_split = [int(x) for x in owner_counts.tolist()]
+        recv_split = [int(x) for x in recv_counts.tolist()]
+        got_k = torch.empty(sum(recv_split), dtype=keys.dtype, device=keys.device)
+        got_c = torch.empty(sum(recv_split), dtype=count32.dtype, device=keys.device)
+        dist.all_to_all_single(got_k, keys[order].contiguous(), output_split_sizes=recv_split, input_split_sizes=send_split, group=group)
+        dist.all_to_all_single(got_c, count32[order].contiguous(), output_split_sizes=recv_split, input_split_sizes=send_split,
+                               group=group)
+        keys, count32 = got_k, got_c
+    owned = torch.arange(rank, n_barcodes, world, dtype=torch.int64, device=keys.device)
+    mk, mc, n_rows = pipeline.merge_kn(ctx, keys, count32, world)
+    k, n, c, off, _total = pipeline.kn_csr(ctx, mk, mc, n_rows, owned.numel())
+    m = int(off[-1].item())
+    return owned, k[:m], n[:m], c[:m], off
+
+
+def distributed_p_c_keys(ctx, keys, count32, p_e, n_barcodes: int, em, group=None):
+    """distributed_p_c for key-encoded rows, with the exchange and the CSR build on the device (exchange_kn_rows)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    owned, k, n, c, off = exchange_kn_rows(ctx, keys, count32, n_barcodes, world, rank, group=group)
+    p_c_own, st_own = em(k, n, c, off, p_e[owned])
+    if world == 1:
+        return p_c_own, st_own
+    per = (n_barcodes + world - 1) // world
+    pad_pc = torch.full((per,), float('nan'), dtype=torch.float64, device=keys.device)
+    pad_st = torch.full((per,), -1, dtype=torch.int32, device=keys.device)
+    pad_pc[:owned.numel()] = p_c_own
+    pad_st[:owned.numel()] = st_own
+    g_pc = torch.empty(world * per, dtype=torch.float64, device=keys.device)
+    g_st = torch.empty(world * per, dtype=torch.int32, device=keys.device)
+    dist.all_gather_into_tensor(g_pc, pad_pc, group=group)
+    dist.all_gather_into_tensor(g_st, pad_st, group=group)
+    return (g_pc.view(world, per).t().reshape(-1)[:n_barcodes].contiguous(),
+            g_st.view(world, per).t().reshape(-1)[:n_barcodes].contiguous())

@@ -344,6 +344,19 @@ def unpack_reads(ctx: Context, rows: torch.Tensor):
     return {k: v[:n] for k, v in out.items()}
 
 
+def merge_kn(ctx: Context, keys: torch.Tensor, count32: torch.Tensor, world: int = 1, group_bits: int = 0):
+    """dyn_merge_kn: weighted (group << 22 | k << 10 | n) rows, possibly repeated -> (keys int64 [m] sorted, count int32 [m],
+    n_rows int64 [1] device scalar); group ids are divided by `world`.  The outputs have room for every input row; the
+    first n_rows[0] are valid."""
+    m = keys.numel()
+    out_k = torch.empty(max(m, 1), dtype=torch.int64, device=keys.device)
+    out_c = torch.empty(max(m, 1), dtype=torch.int32, device=keys.device)
+    n_rows = torch.zeros(1, dtype=torch.int64, device=keys.device)
+    check(ctx.lib.dyn_merge_kn(ctx.handle, ptr(keys), ptr(count32), m, int(world), int(group_bits), ptr(out_k), ptr(out_c),
+                               ptr(n_rows), _stream()))
+    return out_k[:m], out_c[:m], n_rows
+
+
 def pi_fit(ctx: Context, k, n, count, off, p_e, p_c, max_cells=None):
     """dyn_pi_fit -> (alpha_beta_pi [G,3] float64, status [G] int32)."""
     G = off.numel() - 1

@@ -318,6 +318,14 @@ int dyn_pack_reads(dyn_ctx_t *ctx, const uint32_t *d_perm, int64_t n, const uint
 int dyn_unpack_reads(dyn_ctx_t *ctx, const void *d_rows, int64_t n, uint8_t *d_counts, uint32_t *d_barcode, uint64_t *d_umi,
                      uint32_t *d_gene, int16_t *d_score, uint16_t *d_conv_n, uint8_t *d_strand, uint8_t *d_transcriptome,
                      void *stream);
+/* The histogram exchange before the EM when no per-read exchange ran (no UMI stage): every rank holds
+ * partial (group, k, n) -> reads rows of its read range (dyn_aggregate_kn keys with gene_bits == 0: group << 22 |
+ * k << 10 | n) and sends them to rank group % world.  dyn_merge_kn turns what a rank received -- unsorted, the same
+ * key possibly from several ranks -- into dyn_kn_csr's input: group ids divided by world (the owner's local
+ * numbering), rows sorted by key, counts of equal keys summed (what csr_matrix does with duplicates, p_c.py:219).
+ * group_bits = bits of the largest LOCAL group id (0: all).  Outputs need room for n rows. */
+int dyn_merge_kn(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count, int64_t n, int world, int group_bits,
+                 uint64_t *d_out_keys, uint32_t *d_out_count, int64_t *d_n_rows, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host BAM ingest (what the reference gets from pysam, bam.py:253-312): BGZF inflate on n_threads host

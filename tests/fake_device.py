@@ -209,6 +209,30 @@ def unpack_reads(ctx, rows):
                                                                       'transcriptome')}
 
 
+def merge_kn(ctx, keys, count32, world=1, group_bits=0):
+    """numpy stand-in for dyn_merge_kn."""
+    k = _np(keys).astype(np.int64)
+    k = (((k >> 22) // world) << 22) | (k & 0x3fffff)
+    uk, inv = np.unique(k, return_inverse=True)
+    c = np.bincount(inv, weights=_np(count32).astype(np.float64), minlength=len(uk)).astype(np.int32)
+    out_k = np.zeros(len(k), np.int64); out_c = np.zeros(len(k), np.int32)
+    out_k[:len(uk)] = uk; out_c[:len(uk)] = c
+    return torch.from_numpy(out_k), torch.from_numpy(out_c), torch.tensor([len(uk)], dtype=torch.int64)
+
+
+def kn_csr(ctx, keys, count32, n_rows, n_groups):
+    """numpy stand-in for dyn_kn_csr."""
+    m = int(n_rows[0])
+    k = _np(keys)[:m].astype(np.int64)
+    g = k >> 22
+    off = np.zeros(n_groups + 1, np.int64)
+    off[1:] = np.cumsum(np.bincount(g, minlength=n_groups))
+    c = _np(count32)[:m].astype(np.int64)
+    total = np.bincount(g, weights=c.astype(np.float64), minlength=n_groups).astype(np.int64)
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a.astype(d)))
+    return t((k >> 10) & 0xfff, np.int32), t(k & 0x3ff, np.int32), t(c, np.int64), t(off, np.int64), t(total, np.int64)
+
+
 def install(monkeypatch):
     """Route the operator layer to the numpy stand-ins (torch CPU tensors)."""
     from dynast_b200 import _lib, device, pipeline
@@ -223,7 +247,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_lib, 'current_torch_device', lambda: torch.device('cpu'))
     monkeypatch.setattr(_lib, 'current_device_index', lambda: 0)
     for name in ('count_records', 'complement_counts', 'plan_splits', 'dedup', 'group_sums', 'rates_pe', 'alpha', 'aggregate_kn',
-                 'owner_partition', 'pack_reads', 'unpack_reads'):
+                 'owner_partition', 'pack_reads', 'unpack_reads', 'merge_kn', 'kn_csr'):
         monkeypatch.setattr(pipeline, name, globals()[name])
 
     def em_pc_host(k, n, count, off, p_e, nasc=False, device=0):

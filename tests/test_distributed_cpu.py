@@ -79,6 +79,13 @@ def _worker(rank, world, port, n_barcodes, out_dir):
     keep = cols['barcode'] % world == rank
     for name in ('gene', 'score', 'conv_n', 'strand'):
         assert torch.equal(got[name][mine], cols[name][keep])
+    # the key-encoded histogram exchange (distributed.distributed_p_c_keys) gives the same p_c as the row form
+    for name in ('merge_kn', 'kn_csr'):
+        setattr(pipeline, name, getattr(fake_device, name))
+    keys = (rows[:, 0] << 22) | (rows[:, 1] << 10) | rows[:, 2]
+    p_c2, status2 = distributed.distributed_p_c_keys(None, keys, rows[:, 3].to(torch.int32), p_e, n_barcodes, _oracle_em)
+    assert torch.equal(status2, status)
+    assert np.array_equal(p_c2.numpy(), p_c.numpy(), equal_nan=True)
     lo, hi = distributed.read_range(1001, rank, world)
     assert (lo, hi) == ((0, 501) if rank == 0 else (501, 1001))
     dist.destroy_process_group()

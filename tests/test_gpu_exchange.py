@@ -100,3 +100,27 @@ def test_two_gpu_path_equals_one_gpu(tmp_path):
             assert one['p_c'][b] == t['p_c'][j]
             checked += 1
     assert checked > 20
+
+
+@pytest.mark.parametrize('n,world', [(0, 1), (1, 1), (5000, 1), (200000, 4)])
+def test_merge_kn(gpu_ctx, n, world):
+    """dyn_merge_kn + dyn_kn_csr against numpy: repeated keys are summed, group ids become local, rows sorted."""
+    import fake_device
+    from dynast_b200 import pipeline
+    ctx = pipeline.Context.get(0)
+    g = torch.Generator().manual_seed(n + world)
+    n_groups = 300
+    grp = torch.randint(0, n_groups, (n,), generator=g) * world + (world - 1)     # this rank owns ids = world - 1 mod world
+    keys = (grp << 22) | (torch.randint(0, 6, (n,), generator=g) << 10) | torch.randint(0, 40, (n,), generator=g)
+    cnt = torch.randint(1, 1000, (n,), generator=g).to(torch.int32)
+    mk, mc, n_rows = pipeline.merge_kn(ctx, keys.cuda(), cnt.cuda(), world)
+    wk, wc, wn = fake_device.merge_kn(None, keys, cnt, world)
+    m = int(wn[0])
+    assert int(n_rows.item()) == m
+    assert torch.equal(mk.cpu()[:m], wk[:m]) and torch.equal(mc.cpu()[:m], wc[:m])
+    got = pipeline.kn_csr(ctx, mk, mc, n_rows, n_groups)
+    want = fake_device.kn_csr(None, wk, wc, wn, n_groups)
+    tot = int(want[3][-1])
+    for a, b in zip(got[:3], want[:3]):
+        assert torch.equal(a.cpu()[:tot], b[:tot])
+    assert torch.equal(got[3].cpu(), want[3]) and torch.equal(got[4].cpu(), want[4])
