@@ -32,6 +32,7 @@ PROTOTYPES = {
     'dyn_split_plan': (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'dyn_dedup_umi': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _u32,
                              _i32, _vp, _i32, _vp, _vp, _vp]),
+    'dyn_group_key': (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     'dyn_group_sums': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp]),
     'dyn_rates_pe': (_i32, [_vp, _vp, _i64, _u32, _vp, _vp, _vp]),
     'dyn_alpha': (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -68,6 +68,15 @@ __global__ void first_pos_kernel(const uint32_t *barcode, const uint8_t *strand,
     }
 }
 
+// (barcode, umi, gene) -> one 64-bit group key, barcode in the high bits (conversion.py:225 groups on the triple)
+__global__ void group_key_kernel(const uint32_t *barcode, const unsigned long long *umi, const uint32_t *gene, long long n,
+                                 int umi_bits, int gene_bits, unsigned long long *key) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long um = umi_bits >= 64 ? ~0ull : ((1ull << umi_bits) - 1ull);
+    key[i] = ((unsigned long long)barcode[i] << (umi_bits + gene_bits)) | ((umi[i] & um) << gene_bits) | (unsigned long long)gene[i];
+}
+
 struct DedupIn {
     const uint4 *counts;
     const uint8_t *strand, *transcriptome;
@@ -306,6 +315,20 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
         DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_reads, 0, top_bits + final_extra_bits, stream));
         copy_u32_kernel<<<g, kBlock, 0, stream>>>(v.Current(), d_out_idx, reinterpret_cast<const long long *>(d_n_out), n_reads);
     }
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}
+
+extern "C" int dyn_group_key(dyn_ctx_t *ctx, const uint32_t *d_barcode, const uint64_t *d_umi, const uint32_t *d_gene, int64_t n,
+                             int umi_bits, int gene_bits, uint64_t *d_key, void *stream) {
+    DYN_ARG(ctx != nullptr, "null context");
+    DYN_ARG(n >= 0, "negative n");
+    DYN_ARG(umi_bits >= 0 && gene_bits >= 0 && umi_bits + gene_bits < 64, "key fields do not fit 64 bits");
+    if (n == 0) return DYN_OK;
+    DYN_ARG(d_barcode && d_umi && d_gene && d_key, "null buffer");
+    group_key_kernel<<<grid_for(n), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_barcode, reinterpret_cast<const unsigned long long *>(d_umi), d_gene, n, umi_bits, gene_bits,
+        reinterpret_cast<unsigned long long *>(d_key));
     DYN_CUDA(cudaGetLastError());
     return DYN_OK;
 }

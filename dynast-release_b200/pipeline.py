@@ -433,8 +433,9 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
         mark('exchange')
     gene_bits = _bits(max(n_genes - 1, 0))
     bc_bits = _bits(max(n_barcodes - 1, 0))
-    key = (barcode.to(torch.int64) << (umi_bits + gene_bits)) | ((umi & ((1 << umi_bits) - 1)) << gene_bits) | gene.to(torch.int64)
     n = barcode.numel()
+    key = torch.empty(n, dtype=torch.int64, device=dev)
+    check(ctx.lib.dyn_group_key(ctx.handle, ptr(barcode), ptr(umi), ptr(gene), n, int(umi_bits), int(gene_bits), ptr(key), _stream()))
     if transcriptome is None:
         transcriptome = torch.ones(n, dtype=torch.uint8, device=dev)
     sel = dedup(ctx, key, counts, strand, transcriptome, score16, conv_n, barcode, n_barcodes,

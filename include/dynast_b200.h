@@ -218,6 +218,12 @@ int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uint64_t *d_ke
                   const uint64_t *d_final_extra, int final_extra_bits, uint32_t *d_out_idx, int64_t *d_n_out,
                   void *stream);
 
+/* The UMI-dedup group key of every read from its interned ids: barcode << (umi_bits + gene_bits) | (umi &
+ * mask(umi_bits)) << gene_bits | gene -- the (barcode, UMI, GX) triple conversion.py:225 groups on, as the single
+ * 64-bit d_key_lo dyn_dedup_umi takes (key_lo_bits = barcode bits + umi_bits + gene_bits). */
+int dyn_group_key(dyn_ctx_t *ctx, const uint32_t *d_barcode, const uint64_t *d_umi, const uint32_t *d_gene, int64_t n,
+                  int umi_bits, int gene_bits, uint64_t *d_key, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a9 / a11 / a16: per-group reductions over selected reads (d_sel: read indices, NULL = all reads).
  * dyn_group_sums: 16-column sums (aggregation.py:74-79, p_e.py:72-76), number of reads and number of

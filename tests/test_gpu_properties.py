@@ -151,3 +151,19 @@ def test_empty_inputs(gpu_ctx):
     assert pst.tolist() == [1, 1, 1] and bool(torch.isnan(abp).all())
     out = pipeline.consensus(gpu_ctx, torch.zeros(16, dtype=torch.uint8, device=dev), e32, torch.zeros(1, dtype=torch.int64, device=dev))
     assert out['off'].tolist() == [0]
+
+
+def test_group_key(gpu_ctx):
+    """dyn_group_key == the bit expression it replaces."""
+    from dynast_b200.pipeline import check, ptr, _stream
+    dev = torch.device('cuda', 0)
+    g = torch.Generator().manual_seed(5)
+    n = 100003
+    bc = torch.randint(0, 9000, (n,), generator=g).to(torch.int32).to(dev)
+    umi = torch.randint(0, 1 << 40, (n,), generator=g).to(dev)
+    gene = torch.randint(0, 30000, (n,), generator=g).to(torch.int32).to(dev)
+    for umi_bits, gene_bits in ((24, 15), (32, 16), (0, 15), (40, 0)):
+        key = torch.empty(n, dtype=torch.int64, device=dev)
+        check(gpu_ctx.lib.dyn_group_key(gpu_ctx.handle, ptr(bc), ptr(umi), ptr(gene), n, umi_bits, gene_bits, ptr(key), _stream()))
+        want = (bc.to(torch.int64) << (umi_bits + gene_bits)) | ((umi & ((1 << umi_bits) - 1)) << gene_bits) | gene.to(torch.int64)
+        assert torch.equal(key, want)
