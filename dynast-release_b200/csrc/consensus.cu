@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
             *reinterpret_cast<uint2 *>(qs[w]) = make_uint2(0u, 0u);
             meta[w] = 0;
         }
-        full = full || __any_sync(0xffffffffu, wide);
+        full = full || __any_sync(0xffffffffu, wide) || (unsigned long long)run > cap;   // (more cells than reserved: never
+                                                                                         // expected, the sorted path is safe)
         __syncwarp();
         blk_id[lane] = kNoBlock;
         __syncwarp();
