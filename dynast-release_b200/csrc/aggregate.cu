@@ -13,6 +13,8 @@
 
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int kBlock = 256;
@@ -316,8 +318,10 @@ extern "C" int dyn_aggregate_kn(dyn_ctx_t *ctx, const uint8_t *d_counts, const u
     cub::DoubleBuffer<unsigned long long> k(ka, kb);
     cub::DoubleBuffer<uint32_t> v(pa, pb);
     t = tmp_bytes;
-    // all 64 bits: the sentinel (~0) of excluded reads must sort last
-    DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_sel, 0, 64, stream));
+    // the bits in use plus one: valid keys have that extra bit clear, the sentinel (~0) of excluded reads has it set
+    // and sorts last; group_bits == 0 (unknown) sorts all 64 bits
+    const int end_bit = group_bits > 0 ? std::min(64, 22 + gene_bits + group_bits + 1) : 64;
+    DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_sel, 0, end_bit, stream));
     head_flag_kernel<<<g, kBlock, 0, stream>>>(k.Current(), flag, n_sel);
     iota_kernel<<<g, kBlock, 0, stream>>>(iota, n_sel);
     t = tmp_bytes;
@@ -337,7 +341,6 @@ extern "C" int dyn_aggregate_kn(dyn_ctx_t *ctx, const uint8_t *d_counts, const u
     gather_rows_kernel<<<g, kBlock, 0, stream>>>(k.Current(), v.Current(), heads, cnt, perm, n_rows,
                                                  reinterpret_cast<unsigned long long *>(d_keys), d_count, d_first);
     DYN_CUDA(cudaGetLastError());
-    (void)group_bits;
     return DYN_OK;
 }
 

@@ -247,6 +247,8 @@ int dyn_alpha(dyn_ctx_t *ctx, const uint64_t *d_n_reads, const uint64_t *d_n_wit
  * ((group << gene_bits | gene) << 22) | (k << 10) | n.  Rows come out in first-appearance order
  * (groupby(sort=False)) or, with first_appearance_order == 0, sorted by key.  d_first = position (in the
  * selection) of the first read of the row.  Outputs need room for n_sel rows.
+ * group_bits / gene_bits = bits of the largest group / gene id: the sort is restricted to them (group_bits == 0:
+ * unknown, all 64 bits are sorted; ids that do not fit the stated bits give wrong rows).
  * dyn_kn_csr turns key-sorted rows with gene_bits == 0 into the EM / pi input: triplets (k, n, count),
  * offsets d_off[n_groups + 1] and per-group read totals.
  * ------------------------------------------------------------------------------------------------ */
