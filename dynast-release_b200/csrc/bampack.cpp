@@ -20,6 +20,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -30,6 +32,18 @@
 void dyn_set_error(const char *fmt, ...);
 
 namespace {
+
+struct PhaseTimer {     // DYN_BAM_PACK_TIMING=1: phase times on stderr
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(getenv("DYN_BAM_PACK_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "dyn_bam_pack: %-10s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 struct Block { size_t in_off, in_len, out_off, out_len; };
 
@@ -195,6 +209,7 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
     if (barcode_tag && !barcode_tag[0]) barcode_tag = nullptr;
     if (umi_tag && !umi_tag[0]) umi_tag = nullptr;
     if (gene_tag && !gene_tag[0]) gene_tag = nullptr;
+    PhaseTimer timer;
     FILE *f = fopen(path, "rb");
     if (!f) { dyn_set_error("dyn_bam_pack: cannot open %s", path); return DYN_ERR_IO; }
     fseek(f, 0, SEEK_END);
@@ -204,6 +219,7 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
     if (fsz > 0 && fread(raw.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); dyn_set_error("dyn_bam_pack: short read on %s", path); return DYN_ERR_IO; }
     fclose(f);
 
+    timer.mark("read");
     // ---- BGZF block table
     std::vector<Block> blocks;
     size_t ip = 0, total_out = 0;
@@ -227,53 +243,229 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
         total_out += isize;
         ip += blen;
     }
-    std::vector<uint8_t> data(total_out);
-    {
-        std::atomic<size_t> next(0);
-        std::atomic<int> failed(0);
-        auto work = [&]() {
-            for (;;) {
-                const size_t i = next.fetch_add(1);
-                if (i >= blocks.size()) return;
-                const Block &b = blocks[i];
-                if (b.out_len == 0) continue;
+    // The inflated stream is NOT zero-initialised (first touch happens in the inflating threads), and the main thread
+    // walks the header and the chain of record sizes behind the inflating threads instead of after them: every step
+    // of that walk depends on the previous one (~100 ns of memory latency per record), so it is the one serial part.
+    std::unique_ptr<uint8_t[]> data_buf(new uint8_t[std::max<size_t>(total_out, 1)]);
+    uint8_t *const data = data_buf.get();
+    const uint8_t *d = data;
+    const size_t n = total_out;
+    std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[blocks.size() + 1]);
+    for (size_t i = 0; i <= blocks.size(); ++i) done[i].store(0, std::memory_order_relaxed);
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(0);
+    auto inflate_work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= blocks.size()) return;
+            const Block &b = blocks[i];
+            if (b.out_len != 0) {
                 z_stream zs;
                 memset(&zs, 0, sizeof(zs));
-                if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
+                if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; done[i].store(1, std::memory_order_release); return; }
                 zs.next_in = raw.data() + b.in_off; zs.avail_in = (uInt)b.in_len;
-                zs.next_out = data.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
+                zs.next_out = data + b.out_off; zs.avail_out = (uInt)b.out_len;
                 const int rc = inflate(&zs, Z_FINISH);
                 inflateEnd(&zs);
-                if (rc != Z_STREAM_END || zs.avail_out != 0) { failed = 1; return; }
+                if (rc != Z_STREAM_END || zs.avail_out != 0) failed = 1;
             }
-        };
-        const int nt = std::max(1, std::min(n_threads, 64));
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t) th.emplace_back(work);
-        for (auto &t : th) t.join();
-        if (failed) { dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return DYN_ERR_FORMAT; }
-    }
-    std::vector<uint8_t>().swap(raw);
+            done[i].store(1, std::memory_order_release);
+        }
+    };
+    const int nt_inflate = std::max(1, std::min(n_threads, 64));
+    std::vector<std::thread> inflaters;
+    for (int t = 0; t < nt_inflate; ++t) inflaters.emplace_back(inflate_work);
+    size_t ready_blocks = 0, ready_bytes = 0;
+    // blocks until the first `need` bytes of the stream are inflated (or everything is); false when inflate failed
+    auto wait_ready = [&](size_t need) -> bool {
+        need = std::min(need, total_out);
+        while (ready_bytes < need) {
+            bool advanced = false;
+            while (ready_blocks < blocks.size() && done[ready_blocks].load(std::memory_order_acquire)) {
+                ready_bytes = blocks[ready_blocks].out_off + blocks[ready_blocks].out_len;
+                ++ready_blocks;
+                advanced = true;
+            }
+            if (failed.load()) return false;
+            if (!advanced && ready_bytes < need) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        return !failed.load();
+    };
+    auto join_inflaters = [&]() { for (auto &t : inflaters) if (t.joinable()) t.join(); };
+    auto bail = [&](dyn_bam_result *r, int code) { join_inflaters(); delete r; return code; };
 
     // ---- header
     dyn_bam_result *res = new dyn_bam_result();
-    const uint8_t *d = data.data();
-    const size_t n = data.size();
-    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete res; dyn_set_error("dyn_bam_pack: bad BAM magic in %s", path); return DYN_ERR_FORMAT; }
+    if (!wait_ready(12)) { dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return bail(res, DYN_ERR_FORMAT); }
+    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { dyn_set_error("dyn_bam_pack: bad BAM magic in %s", path); return bail(res, DYN_ERR_FORMAT); }
     size_t p = 4;
     const uint32_t l_text = rd32(d + p); p += 4;
-    if (p + l_text + 4 > n) { delete res; dyn_set_error("dyn_bam_pack: truncated header"); return DYN_ERR_FORMAT; }
+    if (p + l_text + 4 > n) { dyn_set_error("dyn_bam_pack: truncated header"); return bail(res, DYN_ERR_FORMAT); }
+    if (!wait_ready(p + l_text + 4)) { dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return bail(res, DYN_ERR_FORMAT); }
     res->header_text.assign((const char *)d + p, l_text); p += l_text;
     const uint32_t n_ref = rd32(d + p); p += 4;
     for (uint32_t r = 0; r < n_ref; ++r) {
-        if (p + 4 > n) { delete res; dyn_set_error("dyn_bam_pack: truncated reference list"); return DYN_ERR_FORMAT; }
+        if (p + 4 > n) { dyn_set_error("dyn_bam_pack: truncated reference list"); return bail(res, DYN_ERR_FORMAT); }
+        if (!wait_ready(p + 4)) { dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return bail(res, DYN_ERR_FORMAT); }
         const uint32_t l_name = rd32(d + p); p += 4;
-        if (p + l_name + 4 > n) { delete res; dyn_set_error("dyn_bam_pack: truncated reference list"); return DYN_ERR_FORMAT; }
+        if (p + l_name + 4 > n) { dyn_set_error("dyn_bam_pack: truncated reference list"); return bail(res, DYN_ERR_FORMAT); }
+        if (!wait_ready(p + l_name + 4)) { dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return bail(res, DYN_ERR_FORMAT); }
         res->ref_name.add((const char *)d + p, l_name ? l_name - 1 : 0); p += l_name;
         res->ref_len.push_back((int32_t)rd32(d + p)); p += 4;
     }
 
-    // ---- records
+    // ---- records.  Files without paired records are filtered, tokenised and packed by all threads over ranges of record
+    //      indices and stitched together in order.  Paired files keep the sequential loop below: mate pairing
+    //      (bam.py:307-312) is a first-seen dictionary over the record order.
+    {
+        std::vector<size_t> rec_at;
+        rec_at.reserve(n / 300);
+        bool any_paired = false, chain_ok = true;
+        for (size_t q = p; q + 4 <= n;) {
+            if (!wait_ready(q + 4 + 16)) { chain_ok = false; break; }
+            const uint32_t block_size = rd32(d + q);
+            if (q + 4 + block_size > n || block_size < 32) { chain_ok = false; break; }
+            any_paired |= (rd16(d + q + 4 + 14) & 0x1) != 0;
+            rec_at.push_back(q);
+            q += 4 + (size_t)block_size;
+        }
+        join_inflaters();
+        std::vector<uint8_t>().swap(raw);
+        if (failed.load()) { delete res; dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return DYN_ERR_FORMAT; }
+        timer.mark("inflate+walk");
+        const int nt = std::max(1, std::min(n_threads, 64));
+        if (chain_ok && !any_paired && nt > 1 && rec_at.size() >= 4096) {
+            struct Part {
+                std::vector<uint8_t> blob;
+                std::vector<uint32_t> size16;
+                std::vector<int32_t> ref_id, pos, hi, score;
+                std::vector<uint16_t> flag;
+                std::vector<uint8_t> gx_assigned;
+                Pool name, barcode, umi, gene;
+                std::string error;
+                int err_code = 0;
+            };
+            const size_t n_rec = rec_at.size();
+            const size_t n_parts = (size_t)nt * 4;
+            std::vector<Part> parts(n_parts);
+            std::atomic<size_t> next_part(0);
+            auto fail = [](Part &pt, int code, const char *msg) { pt.err_code = code; pt.error = msg; };
+            auto work = [&]() {
+                std::vector<uint32_t> toks;
+                for (;;) {
+                    const size_t pi = next_part.fetch_add(1);
+                    if (pi >= n_parts) return;
+                    Part &pt = parts[pi];
+                    const size_t r0 = n_rec * pi / n_parts, r1 = n_rec * (pi + 1) / n_parts;
+                    pt.blob.reserve((r1 - r0) * 200);
+                    for (size_t ri = r0; ri < r1; ++ri) {
+                        const size_t q = rec_at[ri];
+                        const uint32_t block_size = rd32(d + q);
+                        const uint8_t *rec = d + q + 4;
+                        const int32_t ref_id = (int32_t)rd32(rec);
+                        const uint32_t l_read_name = rec[8], n_cigar = rd16(rec + 12), l_seq = rd32(rec + 16);
+                        const uint16_t flag = rd16(rec + 14);
+                        if (ref_id < 0) continue;
+                        if (flag & (0x100 | 0x4 | 0x400)) continue;
+                        const size_t fixed = 32 + l_read_name + 4 * (size_t)n_cigar + (l_seq + 1) / 2 + l_seq;
+                        if (fixed > block_size) { fail(pt, DYN_ERR_FORMAT, "dyn_bam_pack: corrupt record"); return; }
+                        Aux a;
+                        if (!parse_aux(rec + fixed, rec + block_size, barcode_tag, umi_tag, gene_tag, a)) { fail(pt, DYN_ERR_FORMAT, "dyn_bam_pack: corrupt aux data"); return; }
+                        if ((barcode_tag && !a.has_bc) || (umi_tag && !a.has_umi) || (require_gene && gene_tag && !a.has_gx)) continue;
+                        if (barcode_tag && a.bc_len == 1 && a.bc[0] == '-') continue;
+                        if (!a.has_hi || !a.has_as) { fail(pt, DYN_ERR_FORMAT, "dyn_bam_pack: alignment without HI / AS tag (KeyError in the reference, bam.py:295-296)"); return; }
+                        if (!a.has_md) { fail(pt, DYN_ERR_FORMAT, "dyn_bam_pack: alignment without MD tag (count.py:119-124)"); return; }
+                        if (l_seq > 0xffff || n_cigar > 0xffff) { fail(pt, DYN_ERR_FORMAT, "dyn_bam_pack: record too long for the packed layout"); return; }
+                        const size_t bytes = pack_record(rec, a, 0, toks, pt.blob);
+                        pt.size16.push_back((uint32_t)(bytes >> 4));
+                        pt.ref_id.push_back(ref_id);
+                        pt.pos.push_back((int32_t)rd32(rec + 4));
+                        pt.flag.push_back(flag);
+                        pt.hi.push_back((int32_t)a.hi);
+                        pt.score.push_back((int32_t)a.as);
+                        pt.gx_assigned.push_back(a.has_gx ? 1 : 0);
+                        pt.name.add((const char *)rec + 32, l_read_name ? l_read_name - 1 : 0);
+                        pt.barcode.add(a.has_bc ? a.bc : "NA", a.has_bc ? a.bc_len : 2);
+                        pt.umi.add(a.has_umi ? a.umi : "NA", a.has_umi ? a.umi_len : 2);
+                        pt.gene.add(a.has_gx ? a.gx : "", a.has_gx ? a.gx_len : 0);
+                    }
+                }
+            };
+            {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nt; ++t) th.emplace_back(work);
+                for (auto &t : th) t.join();
+            }
+            timer.mark("pack");
+            for (const Part &pt : parts)
+                if (pt.err_code) { delete res; dyn_set_error("%s", pt.error.c_str()); return pt.err_code; }
+            // stitch: unit counts and byte totals per part, then parallel copies
+            size_t units = 0, bytes = 0;
+            std::vector<size_t> unit0(n_parts), byte0(n_parts);
+            for (size_t i = 0; i < n_parts; ++i) { unit0[i] = units; byte0[i] = bytes; units += parts[i].size16.size(); bytes += parts[i].blob.size(); }
+            if ((bytes >> 4) > 0xfffffff0ull) { delete res; dyn_set_error("dyn_bam_pack: more than 64 GiB of packed records: split the BAM by read range"); return DYN_ERR_NOMEM; }
+            res->n_records_seen = (int64_t)n_rec;
+            res->blob_bytes = bytes;
+            const size_t alloc = std::max<size_t>(bytes, 16);
+            if (cudaHostAlloc((void **)&res->blob, alloc, cudaHostAllocPortable) == cudaSuccess) res->blob_pinned = true;
+            else {
+                cudaGetLastError();
+                if (posix_memalign((void **)&res->blob, 256, alloc) != 0) { delete res; dyn_set_error("dyn_bam_pack: out of memory"); return DYN_ERR_NOMEM; }
+            }
+            res->rec_off.assign(units + 1, 0);
+            res->ref_id.resize(units); res->pos.resize(units); res->hi.resize(units); res->score.resize(units);
+            res->flag.resize(units); res->gx_assigned.resize(units); res->paired.assign(units, 0);
+            Pool *dst_pool[4] = {&res->name, &res->barcode, &res->umi, &res->gene};
+            std::vector<size_t> pool0[4];
+            for (int k = 0; k < 4; ++k) {
+                pool0[k].resize(n_parts);
+                size_t tot = 0;
+                for (size_t i = 0; i < n_parts; ++i) {
+                    const Pool &sp = k == 0 ? parts[i].name : (k == 1 ? parts[i].barcode : (k == 2 ? parts[i].umi : parts[i].gene));
+                    pool0[k][i] = tot;
+                    tot += sp.data.size();
+                }
+                if (tot > 0xffffffffull) { delete res; dyn_set_error("dyn_bam_pack: string pool over 4 GiB: split the BAM by read range"); return DYN_ERR_NOMEM; }
+                dst_pool[k]->data.resize(tot);
+                dst_pool[k]->off.assign(units + 1, 0);
+                dst_pool[k]->off[units] = (uint32_t)tot;
+            }
+            std::atomic<size_t> next_copy(0);
+            auto copy = [&]() {
+                for (;;) {
+                    const size_t i = next_copy.fetch_add(1);
+                    if (i >= n_parts) return;
+                    const Part &pt = parts[i];
+                    const size_t u0 = unit0[i], nu = pt.size16.size();
+                    if (!pt.blob.empty()) memcpy(res->blob + byte0[i], pt.blob.data(), pt.blob.size());
+                    uint32_t o16 = (uint32_t)(byte0[i] >> 4);
+                    for (size_t j = 0; j < nu; ++j) { res->rec_off[u0 + j] = o16; o16 += pt.size16[j]; }
+                    if (nu) {
+                        memcpy(res->ref_id.data() + u0, pt.ref_id.data(), 4 * nu);
+                        memcpy(res->pos.data() + u0, pt.pos.data(), 4 * nu);
+                        memcpy(res->hi.data() + u0, pt.hi.data(), 4 * nu);
+                        memcpy(res->score.data() + u0, pt.score.data(), 4 * nu);
+                        memcpy(res->flag.data() + u0, pt.flag.data(), 2 * nu);
+                        memcpy(res->gx_assigned.data() + u0, pt.gx_assigned.data(), nu);
+                    }
+                    for (int k = 0; k < 4; ++k) {
+                        const Pool &sp = k == 0 ? pt.name : (k == 1 ? pt.barcode : (k == 2 ? pt.umi : pt.gene));
+                        if (!sp.data.empty()) memcpy(dst_pool[k]->data.data() + pool0[k][i], sp.data.data(), sp.data.size());
+                        for (size_t j = 0; j < nu; ++j) dst_pool[k]->off[u0 + j] = (uint32_t)(pool0[k][i] + sp.off[j]);
+                    }
+                }
+            };
+            {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nt; ++t) th.emplace_back(copy);
+                for (auto &t : th) t.join();
+            }
+            res->rec_off[units] = (uint32_t)(bytes >> 4);
+            timer.mark("stitch");
+            *out_result = res;
+            return DYN_OK;
+        }
+    }
     std::vector<uint8_t> blob;
     blob.reserve(n / 2);
     res->rec_off.push_back(0);
