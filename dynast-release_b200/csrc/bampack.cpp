@@ -252,6 +252,8 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
     const size_t n = total_out;
     std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[blocks.size() + 1]);
     for (size_t i = 0; i <= blocks.size(); ++i) done[i].store(0, std::memory_order_relaxed);
+    struct BlockRecs { std::vector<uint32_t> at; bool ok = false, paired = false; };
+    std::vector<BlockRecs> block_recs(blocks.size());
     std::atomic<size_t> next(0);
     std::atomic<int> failed(0);
     auto inflate_work = [&]() {
@@ -268,6 +270,23 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
                 const int rc = inflate(&zs, Z_FINISH);
                 inflateEnd(&zs);
                 if (rc != Z_STREAM_END || zs.avail_out != 0) failed = 1;
+            }
+            // htslib-style writers (STAR included) never split a record over BGZF blocks: walk the block's records
+            // right away, while it is hot in this core's cache, assuming it starts at a record boundary.  The
+            // assumption is checked by induction further down; a block that does not end on a record boundary
+            // sends the whole file to the sequential walk.
+            {
+                BlockRecs &br = block_recs[i];
+                const uint8_t *bp = data + b.out_off;
+                size_t q = 0;
+                while (q + 4 <= b.out_len) {
+                    const uint32_t bs = rd32(bp + q);
+                    if (bs < 32 || q + 4 + (size_t)bs > b.out_len) break;
+                    br.paired |= (rd16(bp + q + 4 + 14) & 0x1) != 0;
+                    br.at.push_back((uint32_t)q);
+                    q += 4 + (size_t)bs;
+                }
+                br.ok = q == b.out_len;
             }
             done[i].store(1, std::memory_order_release);
         }
@@ -321,7 +340,12 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
         std::vector<size_t> rec_at;
         rec_at.reserve(n / 300);
         bool any_paired = false, chain_ok = true;
-        for (size_t q = p; q + 4 <= n;) {
+        // (a) from the end of the header to the next block boundary, record by record
+        size_t b_next = 0;                              // first block that starts at or after p
+        while (b_next < blocks.size() && blocks[b_next].out_off < p) ++b_next;
+        const size_t stop = b_next < blocks.size() ? blocks[b_next].out_off : n;
+        size_t q = p;
+        while (q + 4 <= stop) {
             if (!wait_ready(q + 4 + 16)) { chain_ok = false; break; }
             const uint32_t block_size = rd32(d + q);
             if (q + 4 + block_size > n || block_size < 32) { chain_ok = false; break; }
@@ -329,6 +353,45 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
             rec_at.push_back(q);
             q += 4 + (size_t)block_size;
         }
+        // (b) if that landed exactly on the boundary and every later block ends on a record boundary as well, the
+        //     per-block walks of the inflating threads are the chain (induction over the blocks)
+        //     (the first few blocks decide which way to go: a writer that splits records keeps the sequential walk
+        //     running behind the inflating threads, as before)
+        bool try_blockwise = chain_ok && q == stop;
+        for (size_t i = b_next; try_blockwise && i < std::min(blocks.size(), b_next + 4); ++i) {
+            if (!wait_ready(blocks[i].out_off + blocks[i].out_len)) { chain_ok = false; break; }
+            try_blockwise = block_recs[i].ok;
+        }
+        if (chain_ok && !try_blockwise) {
+            while (q + 4 <= n) {
+                if (!wait_ready(q + 4 + 16)) { chain_ok = false; break; }
+                const uint32_t block_size = rd32(d + q);
+                if (q + 4 + block_size > n || block_size < 32) { chain_ok = false; break; }
+                any_paired |= (rd16(d + q + 4 + 14) & 0x1) != 0;
+                rec_at.push_back(q);
+                q += 4 + (size_t)block_size;
+            }
+        }
+        join_inflaters();
+        bool blockwise = try_blockwise && chain_ok && !failed.load();
+        for (size_t i = b_next; blockwise && i < blocks.size(); ++i) blockwise = block_recs[i].ok;
+        if (blockwise) {
+            for (size_t i = b_next; i < blocks.size(); ++i) {
+                any_paired |= block_recs[i].paired;
+                const size_t base = blocks[i].out_off;
+                for (const uint32_t o : block_recs[i].at) rec_at.push_back(base + o);
+            }
+        } else if (try_blockwise && chain_ok && !failed.load()) {
+            // (c) a later block does not end on a record boundary after all: the sequential walk over the rest
+            while (q + 4 <= n) {
+                const uint32_t block_size = rd32(d + q);
+                if (q + 4 + block_size > n || block_size < 32) { chain_ok = false; break; }
+                any_paired |= (rd16(d + q + 4 + 14) & 0x1) != 0;
+                rec_at.push_back(q);
+                q += 4 + (size_t)block_size;
+            }
+        }
+        std::vector<BlockRecs>().swap(block_recs);
         join_inflaters();
         std::vector<uint8_t>().swap(raw);
         if (failed.load()) { delete res; dyn_set_error("dyn_bam_pack: inflate failed in %s", path); return DYN_ERR_FORMAT; }

@@ -45,3 +45,33 @@ def test_bam_pack_errors(tmp_path):
     bad.write_bytes(b'not a bam file at all, just bytes')
     with pytest.raises(_lib.DynastB200Error):
         bamio.PackedBam(str(bad))
+
+
+@pytest.mark.parametrize('aligned', [True, False])
+def test_bam_pack_parallel_paths(tmp_path, aligned):
+    """Single-end files of >= 4 096 records take the parallel ingest (records packed by all threads, stitched in order;
+    the record chain from per-block walks when BGZF blocks end on record boundaries, else from the walk behind the
+    inflating threads): every field must equal the one-thread sequential result, and the oracle's packer."""
+    import os
+    import subprocess
+    import sys
+    import build
+    build.build_product()
+    from oracle import pack
+    from dynast_b200 import bamio, records as rec
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / 'big.bam')
+    subprocess.run([sys.executable, os.path.join(root, 'tools', 'make_bam.py'),
+                    ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'), out, '5'] + (['aligned'] if aligned else []),
+                   check=True, capture_output=True)
+    fields = ('rec_off', 'blob', 'read_id', 'hi', 'barcode', 'umi', 'gene', 'gx_assigned', 'score', 'ref_id', 'pos', 'flag', 'paired')
+    got = {}
+    for nt in (1, 4):
+        with bamio.PackedBam(out, barcode_tag='CB', umi_tag='UB', gene_tag='GX', require_gene=False, n_threads=nt) as pb:
+            assert pb.n_records_seen == 1780 * 5 and pb.n_units % 5 == 0 and pb.n_units > 1000
+            got[nt] = {f: np.array(getattr(pb, f)) for f in fields}
+    for f in fields:
+        assert np.array_equal(got[1][f], got[4][f]), f
+    blob, off, meta, refs = pack.units_from_bam(out, rec.pack_one, rec.pack_units, umi_tag='UB', barcode_tag='CB', velocity=True)
+    assert np.array_equal(got[4]['blob'], blob) and np.array_equal(got[4]['rec_off'], off)
+    assert list(got[4]['read_id']) == [m['read_id'] for m in meta] and len(meta) == len(off) - 1

@@ -1,7 +1,7 @@
 """Synthetic coordinate-sorted BAM for measuring the host ingest (dyn_bam_pack): the alignment records of a small BAM
 are repeated `copies` times each (in place, so the file stays sorted) and written as BGZF
 with zlib level 6, 64 KB of payload per block.
-    python tools/make_bam.py <in.bam> <out.bam> <copies>"""
+    python tools/make_bam.py <in.bam> <out.bam> <copies> [aligned]"""
 import struct
 import sys
 import zlib
@@ -27,17 +27,24 @@ def bgzf_blocks(data):
     return b''.join(out)
 
 
-def bgzf_write(f, payload, level=6):
-    for o in range(0, len(payload), 0xff00):
-        chunk = payload[o:o + 0xff00]
-        c = zlib.compressobj(level, zlib.DEFLATED, -15)
-        comp = c.compress(chunk) + c.flush()
-        f.write(b'\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00' + struct.pack('<H', len(comp) + 25) + comp +
-                struct.pack('<II', zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+def bgzf_block(f, chunk, level=6):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    comp = c.compress(chunk) + c.flush()
+    f.write(b'\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00' + struct.pack('<H', len(comp) + 25) + comp +
+            struct.pack('<II', zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+
+
+def bgzf_write(f, payload, rec_len=None):
+    """rec_len: all records of `payload` have this length -> blocks end on record boundaries, as htslib (and STAR)
+    write them; None: plain 0xff00-byte blocks."""
+    step = 0xff00 if not rec_len else max(rec_len, 0xff00 // rec_len * rec_len)
+    for o in range(0, len(payload), step):
+        bgzf_block(f, payload[o:o + step])
 
 
 def main():
     src, dst, copies = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    aligned = len(sys.argv) > 4 and sys.argv[4] == 'aligned'      # blocks end on record boundaries
     raw = bgzf_blocks(open(src, 'rb').read())
     assert raw[:4] == b'BAM\x01'
     l_text = struct.unpack_from('<i', raw, 4)[0]
@@ -71,8 +78,11 @@ def main():
                 # compressible instead of 8 000 identical records
                 block[:, q0:q0 + l_seq] = np.where(rng.random((copies, l_seq)) < 0.85, rng.integers(36, 41, (copies, l_seq)),
                                                    rng.integers(2, 36, (copies, l_seq)))
-                buf += block.tobytes()
                 n += copies
+                if aligned:
+                    bgzf_write(f, block.tobytes(), rec_len=len(r))
+                    continue
+                buf += block.tobytes()
                 if len(buf) > (64 << 20):
                     bgzf_write(f, bytes(buf))
                     buf = bytearray()
