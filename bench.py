@@ -334,14 +334,28 @@ def main():
     if not args.skip_e2e:
         import ctypes as C
         from dynast_b200._lib import check, ptr
-        h_rec = batch.records.cpu().pin_memory()
-        h_off = batch.rec_off.cpu().pin_memory()
-        h_counts = torch.empty((n_reads, 16), dtype=torch.uint8).pin_memory()
-        h_conv_off = torch.empty(n_reads, dtype=torch.int32).pin_memory()
-        h_conv_n = torch.empty(n_reads, dtype=torch.int16).pin_memory()
-        h_conv_rec = torch.empty(conv_cap, dtype=torch.int64).pin_memory()
-        h_conv_read = torch.empty(conv_cap, dtype=torch.int32).pin_memory()
+        # ~10.5 GB of page-locked host memory per rank; if any rank cannot get it (many ranks on a small host), every
+        # rank skips the leg together instead of one of them dying inside a collective
+        pinned_ok, pin_error = True, None
+        try:
+            h_rec = batch.records.cpu().pin_memory()
+            h_off = batch.rec_off.cpu().pin_memory()
+            h_counts = torch.empty((n_reads, 16), dtype=torch.uint8).pin_memory()
+            h_conv_off = torch.empty(n_reads, dtype=torch.int32).pin_memory()
+            h_conv_n = torch.empty(n_reads, dtype=torch.int16).pin_memory()
+            h_conv_rec = torch.empty(conv_cap, dtype=torch.int64).pin_memory()
+            h_conv_read = torch.empty(conv_cap, dtype=torch.int32).pin_memory()
+        except RuntimeError as exc:
+            pinned_ok, pin_error = False, str(exc).splitlines()[0][:200]
+        if dist is not None:
+            flag = torch.tensor([1 if pinned_ok else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            pinned_ok = bool(flag.item())
         tot, st = C.c_uint64(0), C.c_uint32(0)
+    if not args.skip_e2e and not pinned_ok:
+        e2e = {'value': None, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+               'skipped': 'page-locked host buffers could not be allocated on every rank: %s' % (pin_error or 'another rank failed')}
+    elif not args.skip_e2e:
 
         def e2e_step():
             check(ctx.lib.dyn_tally_reads_host(
