@@ -718,8 +718,124 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
     if (status_acc) atomicOr(p.status, status_acc);
 }
 
-// Units the tile kernel parked: one thread per unit, straight from global memory (two walks when mismatch
-// records are wanted: count, reserve the output range with one atomic, write).
+// One counting unit in ONE pass: the mate is walked once (content, overlap, its mismatch calls into a short list), the
+// read once (content, calls, the mate's calls looked up by reference position); every call is tallied and buffered, so
+// that the records can be written after one atomic has reserved their place.  Same rules as slow_unit (which stays as
+// the fallback when a unit has more mate calls or records than the buffers hold): bam.py:332-346, 389-419.
+constexpr int kMateCalls = 16, kRecBuf = 24;
+
+// "is reference position p an aligned position of the record" for a sequence of ascending p: a cursor over the
+// record's aligned blocks instead of a CIGAR scan per query
+struct AlignedCursor {
+    const uint32_t *cig;
+    int n_cigar, ci, lo, hi, r;        // current aligned block [lo, hi); r = reference position after the ops consumed
+    __device__ __forceinline__ void init(const uint32_t *c, int n, int pos) { cig = c; n_cigar = n; ci = 0; lo = hi = r = pos; }
+    __device__ __forceinline__ bool covers(int p) {
+        while (p >= hi && ci < n_cigar) {
+            const uint32_t c = cig[ci++];
+            const int op = (int)(c & 0xf), len = (int)(c >> 4);
+            if (op == 0 || op == 7 || op == 8) { lo = r; hi = r + len; r += len; }
+            else if (op == 2 || op == 3) r += len;
+        }
+        return p >= lo && p < hi;
+    }
+};
+
+__device__ __forceinline__ bool slow_unit_onepass(const uint8_t *rec, size_t unit_bytes, const TallyParams &p, SlowOut &o,
+                                                  unsigned long long *buf) {
+    o.content[0] = o.content[1] = o.content[2] = o.content[3] = 0;
+    o.w0 = o.w1 = o.w2 = 0; o.n_conv = 0; o.status = 0;
+    const bool nasc = (p.flags & DYN_TALLY_NASC) != 0;
+    Walker rd;
+    const size_t rd_bytes = rd.init(rec, unit_bytes);
+    if (rd.bad) { o.status |= DYN_ST_BAD_RECORD; return true; }
+    const bool has_mate = (reinterpret_cast<const uint16_t *>(rec)[7] & DYN_REC_HAS_MATE) != 0;
+    const int rd_pos = rd.rpos;
+    bool bad = false, overflow = false;
+    // A/C/G/T counters as four 16-bit fields of one register (l_seq <= 65535 per record; two records per unit are
+    // checked against overflow when unpacked)
+    unsigned long long content = 0ull, overlap = 0ull;
+    // the mate's mismatch calls in walk order = ascending reference position: position, (ref << 4 | read) codes, Phred
+    int m_pos[kMateCalls];
+    uint32_t m_val[kMateCalls];
+    int n_m = 0;
+    auto call = [&](int rpos, uint32_t gn, uint32_t rn, uint32_t q) {
+        if (o.n_conv < (uint32_t)kRecBuf)
+            buf[o.n_conv] = (unsigned long long)(uint32_t)rpos | ((unsigned long long)((gn << 4) | rn) << 32) | ((unsigned long long)q << 40);
+        else overflow = true;
+        ++o.n_conv;
+        if ((int)q <= p.quality) return;                // conversion.py:424 (strict)
+        const int r = base_idx(gn), d = base_idx(rn);
+        if (r < 0 || d < 0) { o.status |= DYN_ST_NON_ACGT_CONV; return; }
+        const int idx = conv_idx(r, d);
+        if (p.n_snps > 0 &&
+            snp_lookup(p.snps, p.n_snps, ((unsigned long long)idx << 56) | ((unsigned long long)(uint32_t)rd.ref_id << 32) | (uint32_t)rpos))
+            return;
+        bump_counter(o.w0, o.w1, o.w2, idx, o.status);
+    };
+    int mate_del[4] = {0, 0, 0, 0};
+    if (has_mate) {
+        Walker m;
+        m.init(rec + rd_bytes, unit_bytes - rd_bytes);
+        if (m.bad) { o.status |= DYN_ST_BAD_RECORD; return true; }
+        AlignedCursor cur;
+        cur.init(rd.cig, rd.n_cigar, rd_pos);
+        int prev_cr = -0x7fffffff;
+        while (m.next()) {
+            if (m.cr < prev_cr) { overflow = true; break; }          // never expected: positions ascend within a record
+            prev_cr = m.cr;
+            const int b = base_idx(m.gn);
+            if (b >= 0) content += 1ull << (16 * b);
+            if (m.gn == 15 || m.rn == 15) continue;
+            const bool in_read = cur.covers(m.cr);
+            if (b >= 0 && in_read) overlap += 1ull << (16 * b);
+            if (m.gn == m.rn) continue;
+            if (nasc && in_read) continue;                               // bam.py:339
+            if (n_m < kMateCalls) { m_pos[n_m] = m.cr; m_val[n_m] = (m.gn << 4) | m.rn | (m.q << 8); ++n_m; }
+            else overflow = true;
+        }
+        bad |= m.bad;
+        for (int b = 0; b < 4; ++b) mate_del[b] = m.del[b];
+        if (overflow) return false;
+    }
+    // content(mate) - overlap, floored at zero, before the read's own content is added (bam.py:332-346)
+    int cont[4];
+    for (int b = 0; b < 4; ++b)
+        cont[b] = max(0, (int)((content >> (16 * b)) & 0xffffu) + mate_del[b] - (int)((overlap >> (16 * b)) & 0xffffu));
+    content = 0ull;
+    // the read's walk; the mate's calls are met in ascending position, so one cursor over the list is enough
+    int e0 = 0;
+    int next_pos = n_m > 0 ? m_pos[0] : 0x7fffffff;
+    unsigned consumed = 0u;
+    while (rd.next()) {
+        const int b = base_idx(rd.gn);
+        if (b >= 0) content += 1ull << (16 * b);
+        if (rd.gn == 15 || rd.rn == 15) continue;              // bam.py:389-390
+        uint32_t rn = rd.rn, q = rd.q;
+        while (next_pos < rd.cr) { ++e0; next_pos = e0 < n_m ? m_pos[e0] : 0x7fffffff; }
+        if (next_pos == rd.cr) {
+            // the read holds a call at the mate's position: the entry is consumed; the mate wins only if strictly better
+            const uint32_t mv = m_val[e0], mq = (mv >> 8) & 0xffu;
+            if (!nasc && mq > q) { rn = mv & 0xfu; q = mq; }
+            consumed |= 1u << e0;
+        }
+        if (rd.gn != rn) call(rd.cr, rd.gn, rn, q);
+    }
+    bad |= rd.bad;
+    for (int b = 0; b < 4; ++b) o.content[b] = cont[b] + (int)((content >> (16 * b)) & 0xffffu) + rd.del[b];
+    // leftover mate calls, in the mate's walk order (bam.py:414-419)
+    for (int e = 0; e < n_m; ++e)
+        if (!((consumed >> e) & 1u)) call(m_pos[e], (m_val[e] >> 4) & 0xfu, m_val[e] & 0xfu, (m_val[e] >> 8) & 0xffu);
+    if (bad) {
+        o.status |= DYN_ST_BAD_RECORD;
+        o.content[0] = o.content[1] = o.content[2] = o.content[3] = 0; o.w0 = o.w1 = o.w2 = 0; o.n_conv = 0;
+        return true;
+    }
+    return !overflow;
+}
+
+// Units the tile kernel parked: one thread per unit, straight from global memory.  Normally one pass
+// (slow_unit_onepass); units that overflow its buffers take slow_unit twice: count, reserve the output range, write.
 __global__ void __launch_bounds__(128) tally_slow_kernel(const TallyParams p) {
     const uint32_t n = *p.n_slow;
     const bool emit = (p.flags & DYN_TALLY_EMIT_CONV) != 0;
@@ -730,7 +846,9 @@ __global__ void __launch_bounds__(128) tally_slow_kernel(const TallyParams p) {
         const uint8_t *rec = p.records + ((size_t)off << 4);
         const size_t unit_bytes = (size_t)(end - off) << 4;
         SlowOut so;
-        slow_unit<false>(rec, unit_bytes, p, r, so, nullptr, nullptr);
+        unsigned long long buf[kRecBuf];
+        const bool onepass = slow_unit_onepass(rec, unit_bytes, p, so, buf);
+        if (!onepass) slow_unit<false>(rec, unit_bytes, p, r, so, nullptr, nullptr);
         status |= so.status;
         store_counts(p, r, so.content[0], so.content[1], so.content[2], so.content[3], so.w0, so.w1, so.w2, status);
         if (emit) {
@@ -742,7 +860,11 @@ __global__ void __launch_bounds__(128) tally_slow_kernel(const TallyParams p) {
             p.conv_off[r] = (uint32_t)mine;
             p.conv_n[r] = fits ? (uint16_t)nn : (uint16_t)0;
             if (n_conv > 0 && !fits) status |= DYN_ST_CONV_CAPACITY;
-            if (n_conv > 0 && fits) slow_unit<true>(rec, unit_bytes, p, r, so, p.conv_rec + mine, p.conv_read + mine);
+            if (n_conv > 0 && fits) {
+                if (onepass) {
+                    for (uint32_t j = 0; j < n_conv; ++j) { p.conv_rec[mine + j] = buf[j]; p.conv_read[mine + j] = r; }
+                } else slow_unit<true>(rec, unit_bytes, p, r, so, p.conv_rec + mine, p.conv_read + mine);
+            }
         }
     }
     if (status) atomicOr(p.status, status);

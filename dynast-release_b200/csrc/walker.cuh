@@ -44,7 +44,7 @@ struct Walker {
     uint32_t gn, rn, q;
 
     // returns padded record size, 0 if the record does not fit `avail`
-    __device__ size_t init(const uint8_t *rec, size_t avail) {
+    __device__ __forceinline__ size_t init(const uint8_t *rec, size_t avail) {
         bad = false;
         ci = op_left = qpos = ti = aligned = 0;
         del_left = 0;
@@ -67,13 +67,13 @@ struct Walker {
         return (need + 15) & ~(size_t)15;
     }
     // one deleted-base token; false if the next token is not one
-    __device__ bool take_del(uint32_t &code) {
+    __device__ __forceinline__ bool take_del(uint32_t &code) {
         if (ti >= n_tok || !DYN_TOK_IS_DEL(tok[ti])) { bad = true; return false; }
         code = DYN_TOK_BASE(tok[ti++]);
         return true;
     }
     // advance to the next aligned (M/=/X) pair
-    __device__ bool next() {
+    __device__ __forceinline__ bool next() {
         for (;;) {
             if (bad) return false;
             if (op_left == 0) {
