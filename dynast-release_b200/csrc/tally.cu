@@ -836,7 +836,10 @@ __device__ __forceinline__ bool slow_unit_onepass(const uint8_t *rec, size_t uni
 
 // Units the tile kernel parked: one thread per unit, straight from global memory.  Normally one pass
 // (slow_unit_onepass); units that overflow its buffers take slow_unit twice: count, reserve the output range, write.
-__global__ void __launch_bounds__(128) tally_slow_kernel(const TallyParams p) {
+#ifndef DYN_SLOW_MIN_CTAS
+#define DYN_SLOW_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(128, DYN_SLOW_MIN_CTAS) tally_slow_kernel(const TallyParams p) {
     const uint32_t n = *p.n_slow;
     const bool emit = (p.flags & DYN_TALLY_EMIT_CONV) != 0;
     uint32_t status = 0;
@@ -935,7 +938,7 @@ extern "C" int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint
     if (grid > p.n_tiles) grid = p.n_tiles;
     tally_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     DYN_CUDA(cudaGetLastError());
-    long long slow_grid = std::min<long long>((long long)ctx->sm_count * 8, (n_reads + 127) / 128);
+    long long slow_grid = std::min<long long>((long long)ctx->sm_count * 2 * DYN_SLOW_MIN_CTAS, (n_reads + 127) / 128);
     tally_slow_kernel<<<(unsigned)slow_grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     DYN_CUDA(cudaGetLastError());
     return DYN_OK;

@@ -39,6 +39,10 @@ struct Walker {
     int del[4];
     int del_left;      // deleted reference bases still to be reported (next_event only)
     bool bad;
+    // the sequence / quality word and the MD token under the cursor are kept in registers: one load per 8 bases, per 4
+    // qualities and per token instead of three loads per base
+    uint32_t seq_w, qual_w, tok_w;
+    int seq_wi, qual_wi, tok_i;
     // current aligned pair
     int cq, cr;
     uint32_t gn, rn, q;
@@ -49,6 +53,7 @@ struct Walker {
         ci = op_left = qpos = ti = aligned = 0;
         del_left = 0;
         del[0] = del[1] = del[2] = del[3] = 0;
+        seq_w = qual_w = tok_w = 0; seq_wi = qual_wi = tok_i = -1;
         n_cigar = l_seq = n_tok = 0;
         rpos = 0; ref_id = 0;
         cig = tok = nullptr; seq = qual = nullptr;
@@ -94,10 +99,15 @@ struct Walker {
                 continue;
             }
             if (qpos >= l_seq) { bad = true; return false; }
-            rn = (seq[qpos >> 1] >> ((~qpos & 1) << 2)) & 0xf;
+            if ((qpos >> 3) != seq_wi) { seq_wi = qpos >> 3; seq_w = reinterpret_cast<const uint32_t *>(seq)[seq_wi]; }
+            rn = (seq_w >> ((((qpos >> 1) & 3) << 3) + ((~qpos & 1) << 2))) & 0xf;
             gn = rn;
-            if (ti < n_tok && !DYN_TOK_IS_DEL(tok[ti]) && (int)DYN_TOK_AOFF(tok[ti]) == aligned) gn = DYN_TOK_BASE(tok[ti++]);
-            cq = qpos; cr = rpos; q = qual[qpos];
+            if (ti < n_tok) {
+                if (tok_i != ti) { tok_i = ti; tok_w = tok[ti]; }
+                if (!DYN_TOK_IS_DEL(tok_w) && (int)DYN_TOK_AOFF(tok_w) == aligned) { gn = DYN_TOK_BASE(tok_w); ++ti; }
+            }
+            if ((qpos >> 2) != qual_wi) { qual_wi = qpos >> 2; qual_w = reinterpret_cast<const uint32_t *>(qual)[qual_wi]; }
+            cq = qpos; cr = rpos; q = (qual_w >> ((qpos & 3) << 3)) & 0xffu;
             ++qpos; ++rpos; ++aligned; --op_left;
             return true;
         }
