@@ -232,20 +232,38 @@ __global__ void __launch_bounds__(THREADS) em_kernel(const EmParams p) {
         for (int i = tid; i < KN; i += kEmThreads) v[i] = (float)cnt[i];   // p_c.py:148
         cta_sync<THREADS>();
         // ---- active list: row-major indices of cells that can ever be non-zero (non-zero or masked);
-        //      compacted list of columns owning masked cells.  Both by thread 0..: sizes are tiny.
-        if (tid == 0) {
+        //      compacted list of columns owning masked cells.  Warp 0 compacts 32 entries at a time by ballot, in
+        //      place: an entry lands at or before its own index, and a chunk is read completely before it is written.
+        if (tid < 32) {
             int na = 0;
-            for (int i = 0; i < KN; ++i)
-                if (cnt[i] != 0 || mask[i]) cnt[na++] = ((uint32_t)(i / N) << 16) | (uint32_t)(i % N);   // in place: na <= i, cnt[i] already consumed
-            sh.nact = na;
+            for (int i0 = 0; i0 < KN; i0 += 32) {
+                const int i = i0 + tid;
+                const bool keep = i < KN && (cnt[i] != 0 || mask[i]);
+                const uint32_t packed = ((uint32_t)(i / N) << 16) | (uint32_t)(i % N);
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) cnt[na + __popc(bal & ((1u << tid) - 1u))] = packed;
+                na += __popc(bal);
+                __syncwarp();
+            }
             int nc = 0;
-            for (int n = 0; n < N; ++n)
-                if (cols[n]) cols[nc++] = n;
-            sh.ncols = nc;
-            sh.p_c = NASC ? 0.5 : 0.1;
-            sh.prev = sh.p_c;
-            sh.bis_r = 1.0;
-            sh.bis_l = 0.0;
+            for (int n0 = 0; n0 < N; n0 += 32) {
+                const int n = n0 + tid;
+                const bool keep = n < N && cols[n] != 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) cols[nc + __popc(bal & ((1u << tid) - 1u))] = n;
+                nc += __popc(bal);
+                __syncwarp();
+            }
+            if (tid == 0) {
+                sh.nact = na;
+                sh.ncols = nc;
+                sh.p_c = NASC ? 0.5 : 0.1;
+                sh.prev = sh.p_c;
+                sh.bis_r = 1.0;
+                sh.bis_l = 0.0;
+            }
         }
         cta_sync<THREADS>();
         const int nact = sh.nact, ncols = sh.ncols;
