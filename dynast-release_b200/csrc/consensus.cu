@@ -75,13 +75,11 @@ __global__ void size_kernel(const uint8_t *records, const uint32_t *item_rec16, 
 // CIGAR, reference base = read base unless an MD mismatch token sits at that offset) and the read's deleted-base
 // tokens, so the 12-byte tuples of a read are written by consecutive lanes into consecutive slots
 // (slot = aligned offset for M/=/X bases, m_total + d for the d-th deleted base).
-__global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
-                              long long n_items, const unsigned long long *tuple_off, const unsigned long long *win,
-                              unsigned long long *key, uint32_t *val, int32_t *status) {
+__device__ __forceinline__ void expand_item(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off,
+                                            long long n_groups, long long i, int lane, const unsigned long long *tuple_off,
+                                            const unsigned long long *win, unsigned long long *key, uint32_t *val,
+                                            int32_t *status) {
     const unsigned long long kInvalid = ((unsigned long long)n_groups << 32) | 0xffffffffull;
-    const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= n_items) return;
     const unsigned long long o0 = tuple_off[i], end = tuple_off[i + 1];
     if (end == o0) return;             // a read of direct_kernel's groups (or one without reference bases)
     const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
@@ -167,6 +165,26 @@ __global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16
         bad = true;
     }
     if (bad) status[g] = 2;
+}
+
+// Most reads belong to direct_kernel's groups and have no tuples: every lane checks one read, and the warp then
+// expands the few that do, one after the other (launching a warp per read just to find that out cost 2.5 ms).
+__global__ void expand_kernel(const uint8_t *records, const uint32_t *item_rec16, const long long *group_off, long long n_groups,
+                              long long n_items, const unsigned long long *tuple_off, const unsigned long long *win,
+                              unsigned long long *key, uint32_t *val, int32_t *status) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp * 32; base < n_items; base += n_warps * 32) {
+        const long long mine = base + lane;
+        uint32_t todo = __ballot_sync(0xffffffffu, mine < n_items && tuple_off[mine + 1] != tuple_off[mine]);
+        while (todo) {
+            const int j = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            expand_item(records, item_rec16, group_off, n_groups, base + j, lane, tuple_off, win, key, val, status);
+            __syncwarp();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -684,8 +702,12 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
                 a1 = Arena(base);
             }
         }
-        expand_kernel<<<grid_for(n_items * 32), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups, n_items, tuple_off,
-                                                                     win, ka, va, d_out_status);
+        {
+            const long long warps_needed = (n_items + 31) / 32;
+            const long long grid = std::min<long long>((long long)ctx->sm_count * 16, (warps_needed * 32 + kBlock - 1) / kBlock);
+            expand_kernel<<<(unsigned)std::max<long long>(grid, 1), kBlock, 0, stream>>>(records, d_item_rec16, group_off, n_groups,
+                                                                                        n_items, tuple_off, win, ka, va, d_out_status);
+        }
         cub::DoubleBuffer<unsigned long long> k(ka, kb);
         cub::DoubleBuffer<uint32_t> v(va, vb);
         t = sort_tmp;
