@@ -33,8 +33,9 @@ def build_product(force=False, verbose=False):
     deps = srcs + glob.glob(os.path.join(PKG, 'csrc', '*.cuh')) + glob.glob(os.path.join(ROOT, 'include', '*.h'))
     if not force and not _newer(LIB, deps):
         return LIB
-    objs = []
-    for src in srcs:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(PKG, 'csrc', os.path.splitext(os.path.basename(src))[0] + '.o')
         if force or _newer(obj, [src] + [d for d in deps if d.endswith(('.cuh', '.h'))]):
             cmd = ['nvcc'] + NVCC_FLAGS + ['-c', src, '-o', obj]
@@ -43,7 +44,10 @@ def build_product(force=False, verbose=False):
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode:
                 raise RuntimeError(f'nvcc failed on {src}')
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, srcs))
     cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-lz', '-lpthread']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:

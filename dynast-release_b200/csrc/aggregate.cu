@@ -233,6 +233,7 @@ extern "C" int dyn_group_sums(dyn_ctx_t *ctx, const uint8_t *d_counts, const uin
                               const uint32_t *d_sel, int64_t n_sel, int64_t n_groups, uint32_t conv_mask,
                               uint64_t *d_sums, uint64_t *d_n_reads, uint64_t *d_n_with, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_sel >= 0 && n_groups >= 0, "negative size");
     if (n_groups == 0) return DYN_OK;
     DYN_ARG(d_sums != nullptr, "null output");
@@ -253,6 +254,7 @@ extern "C" int dyn_group_sums(dyn_ctx_t *ctx, const uint8_t *d_counts, const uin
 extern "C" int dyn_rates_pe(dyn_ctx_t *ctx, const uint64_t *d_sums, int64_t n_groups, uint32_t pe_mask, double *d_rates,
                             double *d_p_e, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     if (n_groups <= 0) return DYN_OK;
     DYN_ARG(d_sums != nullptr, "null sums");
     rates_kernel<<<grid_for(n_groups), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -267,6 +269,7 @@ extern "C" int dyn_aggregate_kn(dyn_ctx_t *ctx, const uint8_t *d_counts, const u
                                 int first_appearance_order, uint64_t *d_keys, uint32_t *d_count, uint32_t *d_first,
                                 int64_t *d_n_rows, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_sel >= 0 && n_sel < 0xffffffffLL, "n_sel out of range");
     DYN_ARG(d_n_rows != nullptr, "null n_rows");
     DYN_ARG(group_bits >= 0 && gene_bits >= 0 && group_bits + gene_bits <= 41, "group_bits + gene_bits must be <= 41");
@@ -348,6 +351,7 @@ extern "C" int dyn_kn_csr(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t
                           int64_t max_rows, int64_t n_groups, int32_t *d_k, int32_t *d_n, int64_t *d_cnt, int64_t *d_off,
                           uint64_t *d_total, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(max_rows >= 0 && n_groups >= 0, "negative size");
     DYN_ARG(d_n_rows && d_off && d_total, "null buffer");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -365,6 +369,7 @@ extern "C" int dyn_kn_csr(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t
 extern "C" int dyn_alpha(dyn_ctx_t *ctx, const uint64_t *d_n_reads, const uint64_t *d_n_with, const double *d_pi_c,
                          int64_t n_groups, double *d_alpha, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     if (n_groups <= 0) return DYN_OK;
     DYN_ARG(d_n_reads && d_n_with && d_pi_c && d_alpha, "null buffer");
     alpha_kernel<<<grid_for(n_groups), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(

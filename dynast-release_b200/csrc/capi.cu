@@ -34,13 +34,13 @@ extern "C" int dyn_ctx_create(int device, dyn_ctx_t **out) {
                       prop.minor);
         return DYN_ERR_ARG;
     }
-    dyn_ctx *ctx = new dyn_ctx();
-    memset(ctx, 0, sizeof(*ctx));
+    dyn_ctx *ctx = new dyn_ctx();     // value-initialised: every plain member is zero
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     for (int i = 0; i < 2; ++i) DYN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) DYN_CUDA(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    DYN_CUDA(cudaEventCreateWithFlags(&ctx->slot_ev, cudaEventDisableTiming));
     DYN_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_small), 256, cudaHostAllocDefault));
     *out = ctx;
     return DYN_OK;
@@ -55,6 +55,7 @@ extern "C" int dyn_ctx_destroy(dyn_ctx_t *ctx) {
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(ctx->copy_stream[i]);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->slot_ev) cudaEventDestroy(ctx->slot_ev);
     delete ctx;
     return DYN_OK;
 }
@@ -63,6 +64,20 @@ extern "C" int dyn_ctx_sm_count(dyn_ctx_t *ctx) { return ctx ? ctx->sm_count : 0
 
 int dyn_ctx_scratch(dyn_ctx *ctx, int slot, size_t bytes, void **out) {
     if (slot < 0 || slot >= kScratchSlots) { dyn_set_error("bad scratch slot"); return DYN_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    if (ctx->cur_managed) {
+        // the slot's previous user ran on another stream: order this call behind everything queued there
+        if (ctx->slot_used[slot] && ctx->slot_stream[slot] != ctx->cur_stream) {
+            if (cudaEventRecord(ctx->slot_ev, ctx->slot_stream[slot]) == cudaSuccess)
+                DYN_CUDA(cudaStreamWaitEvent(ctx->cur_stream, ctx->slot_ev, 0));
+            else {      // that stream no longer exists
+                cudaGetLastError();
+                DYN_CUDA(cudaDeviceSynchronize());
+            }
+        }
+        ctx->slot_stream[slot] = ctx->cur_stream;
+        ctx->slot_used[slot] = true;
+    }
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) DYN_CUDA(cudaFree(ctx->scratch[slot]));
         ctx->scratch[slot] = nullptr;
@@ -89,6 +104,7 @@ extern "C" int dyn_tally_reads_host(dyn_ctx_t *ctx, const void *h_records, const
                                     uint64_t *h_conv_rec, uint32_t *h_conv_read, int64_t conv_capacity,
                                     uint64_t *h_conv_total, uint32_t *h_status) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, nullptr, false);   // manages its own two streams and slots
     DYN_ARG(n_reads >= 0, "negative n_reads");
     DYN_ARG(h_status != nullptr, "null status");
     *h_status = 0;
@@ -213,6 +229,7 @@ extern "C" int dyn_em_pc_host(dyn_ctx_t *ctx, const int32_t *h_k, const int32_t 
                               const int64_t *h_off, int64_t B, const double *h_p_e, int nasc, double *h_p_c,
                               int32_t *h_em_status, int32_t *h_iters) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, nullptr, false);   // manages its own two streams and slots
     if (B <= 0) return DYN_OK;
     DYN_ARG(h_off && h_p_e && h_p_c && h_em_status, "null buffer");
     DYN_CUDA(cudaSetDevice(ctx->device));

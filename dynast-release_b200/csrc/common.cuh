@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/dynast_b200.h"
 
 void dyn_set_error(const char *fmt, ...);
@@ -40,6 +42,30 @@ struct dyn_ctx {
     // lazily built device tables
     double *em_coef;        // binomial coefficient table (wrapped-int64 semantics), [em_coef_K][em_coef_N]
     int em_coef_K, em_coef_N;
+    // One call at a time per context (the mutex is held for the whole of every entry point), and a scratch slot
+    // that changes streams is ordered by an event: the new stream waits for what the previous one queued.
+    std::recursive_mutex mu;
+    cudaStream_t cur_stream;
+    bool cur_managed;
+    cudaStream_t slot_stream[kScratchSlots];
+    bool slot_used[kScratchSlots];
+    cudaEvent_t slot_ev;
+};
+
+// Entered at the top of every C-ABI call that takes a context: serialises host threads on the context and tells
+// dyn_ctx_scratch which stream the call runs on (managed == false: the call orders its own streams).
+struct CtxEnter {
+    dyn_ctx *c;
+    cudaStream_t prev;
+    bool prev_managed;
+    CtxEnter(dyn_ctx *ctx, void *stream, bool managed = true) : c(ctx) {
+        c->mu.lock();
+        prev = c->cur_stream; prev_managed = c->cur_managed;
+        c->cur_stream = static_cast<cudaStream_t>(stream); c->cur_managed = managed;
+    }
+    ~CtxEnter() { c->cur_stream = prev; c->cur_managed = prev_managed; c->mu.unlock(); }
+    CtxEnter(const CtxEnter &) = delete;
+    CtxEnter &operator=(const CtxEnter &) = delete;
 };
 
 int dyn_ctx_scratch(dyn_ctx *ctx, int slot, size_t bytes, void **out);

@@ -104,6 +104,7 @@ __device__ __forceinline__ void expand_item(const uint8_t *records, const uint32
         if (lane == 0) status[g] = 2;
         return;
     }
+    bool iupac = false;      // a base other than A/C/G/T/N: BASE_IDX[...] raises KeyError in the reference (consensus.py:84-97)
     // aligned bases
     for (uint32_t a = lane; a < m_total; a += 32) {
         int q = 0, r = pos, done = 0, qpos = -1, rpos = 0;
@@ -125,6 +126,7 @@ __device__ __forceinline__ void expand_item(const uint8_t *records, const uint32
                 const uint32_t tk = tok[t];
                 if (!DYN_TOK_IS_DEL(tk) && DYN_TOK_AOFF(tk) == a) gn = DYN_TOK_BASE(tk);
             }
+            if (gn != 15 && rn != 15 && (base_idx(gn) < 0 || base_idx(rn) < 0)) iupac = true;
             if (base_idx(gn) >= 0 && base_idx(rn) >= 0) {      // reference N and read N are skipped (consensus.py:79-91)
                 k = (g << 32) | (uint32_t)rpos;
                 v = pack_val(qual[qpos], rn, gn, 0);
@@ -154,6 +156,7 @@ __device__ __forceinline__ void expand_item(const uint8_t *records, const uint32
                     else if (op == 0 || op == 3 || op == 7 || op == 8) r += len;
                 }
                 const uint32_t gn = DYN_TOK_BASE(tk);
+                if (gn != 15 && base_idx(gn) < 0) iupac = true;
                 if (rpos >= 0 && base_idx(gn) >= 0) { k = (g << 32) | (uint32_t)rpos; v = pack_val(0, 0, gn, 1); }
                 key[o0 + m_total + d] = k; val[o0 + m_total + d] = v;
             } else bad = true;
@@ -165,6 +168,7 @@ __device__ __forceinline__ void expand_item(const uint8_t *records, const uint32
         bad = true;
     }
     if (bad) status[g] = 2;
+    if (iupac) status[g] = 6;
 }
 
 // Most reads belong to direct_kernel's groups and have no tuples: every lane checks one read, and the warp then
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
     const long long n_warps = (long long)gridDim.x * kDirectWarps;
     for (long long g = blockIdx.x * (long long)kDirectWarps + wid; g < n_groups; g += n_warps) {
         if (win[g] == 0ull) continue;
-        bool bad = false, full = false;
+        bool bad = false, full = false, iupac = false;
         for (long long i = group_off[g]; i < group_off[g + 1] && !full; ++i) {
             const uint8_t *rec = records + ((size_t)item_rec16[i] << 4);
             const uint4 h = *reinterpret_cast<const uint4 *>(rec);
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
                         if (!DYN_TOK_IS_DEL(tk) && DYN_TOK_AOFF(tk) == a) gn = DYN_TOK_BASE(tk);
                     }
                     const int gi = base_idx(gn), ri = base_idx(rn);
+                    if (gn != 15 && rn != 15 && (gi < 0 || ri < 0)) iupac = true;   // BASE_IDX[...] KeyError (consensus.py:84-97)
                     if (gi >= 0 && ri >= 0) {      // reference N and read N are skipped (consensus.py:79-91)
                         const int sl = block_slot(blk_id, rpos >> 5);
                         if (sl < 0) full = true;
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
                             else if (op == 0 || op == 3 || op == 7 || op == 8) r += len;
                         }
                         const int gi = base_idx(DYN_TOK_BASE(tk));
+                        if (gi < 0 && DYN_TOK_BASE(tk) != 15) iupac = true;
                         if (rpos >= 0 && gi >= 0) {
                             const int sl = block_slot(blk_id, rpos >> 5);
                             if (sl < 0) full = true;
@@ -391,6 +397,7 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
             else cell_cnt[g] = run;
         }
         if (!full && __any_sync(0xffffffffu, bad) && lane == 0) status[g] = 2;
+        if (__any_sync(0xffffffffu, iupac) && lane == 0) status[g] = 6;
     }
 }
 
@@ -585,6 +592,7 @@ extern "C" int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32
                              int64_t out_capacity_bytes, uint32_t *d_out_off, void *d_out_md, int64_t md_capacity_bytes,
                              uint32_t *d_out_md_off, uint32_t *d_out_nm, int32_t *d_out_status, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_groups >= 0 && n_items >= 0 && n_groups < 0xffffffffLL, "size out of range");
     if (n_groups == 0) return DYN_OK;
     DYN_ARG(d_group_off && d_out_off && d_out_md_off && d_out_nm && d_out_status, "null buffer");

@@ -47,6 +47,7 @@ extern "C" int dyn_count_records(dyn_ctx_t *ctx, const uint64_t *d_conv_rec, con
                                  const uint32_t *d_conv_contig, int64_t n_records, int64_t n_reads, const uint64_t *d_snps,
                                  int64_t n_snps, int quality, uint8_t *d_counts, uint32_t *d_status, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     DYN_ARG(n_records >= 0 && n_reads >= 0, "negative size");
     if (n_records == 0) return DYN_OK;
     DYN_ARG(d_conv_rec && d_conv_read && d_counts && d_status, "null buffer");

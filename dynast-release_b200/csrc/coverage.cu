@@ -105,6 +105,7 @@ extern "C" int dyn_coverage(dyn_ctx_t *ctx, const void *d_records, const uint32_
                             const uint8_t *d_selected, const uint64_t *d_poi, int64_t n_poi, uint32_t *d_cov,
                             uint64_t *d_first, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_units >= 0 && n_poi >= 0, "negative size");
     if (n_poi == 0) return DYN_OK;
     DYN_ARG(d_poi && d_cov && d_first, "null buffer");
@@ -123,6 +124,7 @@ extern "C" int dyn_coverage(dyn_ctx_t *ctx, const void *d_records, const uint32_
 extern "C" int dyn_unique_counts(dyn_ctx_t *ctx, const uint64_t *d_keys, int64_t n_keys, uint64_t *d_out_keys,
                                  uint32_t *d_out_count, uint32_t *d_out_first, int64_t *d_n_out, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_keys >= 0 && n_keys < 0xffffffffLL, "n_keys out of range");
     DYN_ARG(d_n_out != nullptr, "null n_out");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

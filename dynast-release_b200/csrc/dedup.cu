@@ -154,6 +154,7 @@ inline int bits_for(uint64_t max_value) {
 extern "C" int dyn_complement_counts(dyn_ctx_t *ctx, uint8_t *d_counts, const uint8_t *d_strand, int64_t n_reads,
                                      void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     DYN_ARG(n_reads >= 0, "negative n_reads");
     if (n_reads == 0) return DYN_OK;
     DYN_ARG(d_counts && d_strand, "null buffer");
@@ -168,6 +169,7 @@ extern "C" int dyn_barcode_first_pos(dyn_ctx_t *ctx, const uint32_t *d_barcode, 
                                      const uint16_t *d_conv_n, int64_t n_reads, int64_t n_barcodes,
                                      uint64_t *d_first_pos, uint32_t *d_n_reads, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_reads >= 0 && n_barcodes >= 0, "negative size");
     if (n_barcodes == 0) return DYN_OK;
     DYN_ARG(d_first_pos && d_n_reads, "null output");
@@ -201,6 +203,7 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
                              const uint64_t *d_final_extra, int final_extra_bits, uint32_t *d_out_idx,
                              int64_t *d_n_out, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_reads >= 0 && n_reads < 0xffffffffLL, "n_reads out of range");
     DYN_ARG(d_n_out != nullptr, "null n_out");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -322,6 +325,7 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
 extern "C" int dyn_group_key(dyn_ctx_t *ctx, const uint32_t *d_barcode, const uint64_t *d_umi, const uint32_t *d_gene, int64_t n,
                              int umi_bits, int gene_bits, uint64_t *d_key, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     DYN_ARG(n >= 0, "negative n");
     DYN_ARG(umi_bits >= 0 && gene_bits >= 0 && umi_bits + gene_bits < 64, "key fields do not fit 64 bits");
     if (n == 0) return DYN_OK;

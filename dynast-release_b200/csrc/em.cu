@@ -448,6 +448,7 @@ extern "C" int dyn_em_pc(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n,
                          const int64_t *d_off, int64_t n_barcodes, const double *d_p_e, int nasc, double *d_p_c,
                          int32_t *d_em_status, int32_t *d_iters, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_barcodes >= 0, "negative n_barcodes");
     if (n_barcodes == 0) return DYN_OK;
     DYN_ARG(d_off && d_p_e && d_p_c && d_em_status, "null buffer");   // triplet pointers may be NULL when every barcode is empty

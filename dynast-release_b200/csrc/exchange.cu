@@ -103,7 +103,8 @@ __global__ void localise_keys_kernel(const unsigned long long *in, long long n, 
 extern "C" int dyn_owner_partition(dyn_ctx_t *ctx, const uint32_t *d_barcode, int64_t n, int world, uint32_t *d_perm,
                                    uint64_t *d_owner_counts, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
-    DYN_ARG(n >= 0 && n <= 0xffffffffll, "bad n");
+    CtxEnter enter_(ctx, stream);
+    DYN_ARG(n >= 0 && n <= 0x7fffffffll, "n outside [0, 2^31)");
     DYN_ARG(world >= 1 && world <= DYN_MAX_WORLD, "world out of range");
     DYN_ARG(d_owner_counts != nullptr, "null counts");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -145,6 +146,7 @@ extern "C" int dyn_pack_reads(dyn_ctx_t *ctx, const uint32_t *d_perm, int64_t n,
                               const uint16_t *d_conv_n, const uint8_t *d_strand, const uint8_t *d_transcriptome, void *d_rows,
                               void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     DYN_ARG(n >= 0, "negative n");
     if (n == 0) return DYN_OK;
     DYN_ARG(d_counts && d_barcode && d_umi && d_gene && d_score && d_conv_n && d_strand && d_rows, "null buffer");
@@ -160,6 +162,7 @@ extern "C" int dyn_unpack_reads(dyn_ctx_t *ctx, const void *d_rows, int64_t n, u
                                 uint64_t *d_umi, uint32_t *d_gene, int16_t *d_score, uint16_t *d_conv_n, uint8_t *d_strand,
                                 uint8_t *d_transcriptome, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     DYN_ARG(n >= 0, "negative n");
     if (n == 0) return DYN_OK;
     DYN_ARG(d_rows && d_counts && d_barcode && d_umi && d_gene && d_score && d_conv_n && d_strand && d_transcriptome, "null buffer");
@@ -174,6 +177,7 @@ extern "C" int dyn_unpack_reads(dyn_ctx_t *ctx, const void *d_rows, int64_t n, u
 extern "C" int dyn_merge_kn(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count, int64_t n, int world, int group_bits,
                             uint64_t *d_out_keys, uint32_t *d_out_count, int64_t *d_n_rows, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     DYN_ARG(n >= 0 && n < 0x7fffffffll, "bad n");
     DYN_ARG(world >= 1 && world <= DYN_MAX_WORLD, "world out of range");
     DYN_ARG(d_n_rows != nullptr, "null n_rows");

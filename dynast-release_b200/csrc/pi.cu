@@ -357,6 +357,7 @@ extern "C" int dyn_pi_fit(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n
                           const int64_t *d_off, int64_t n_groups, int64_t max_cells, const double *d_p_e,
                           const double *d_p_c, double *d_alpha_beta_pi, int32_t *d_status, void *stream_) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
     DYN_ARG(n_groups >= 0, "negative n_groups");
     if (n_groups == 0) return DYN_OK;
     DYN_ARG(d_off && d_p_e && d_p_c && d_alpha_beta_pi && d_status, "null buffer");   // triplets may be NULL when all groups are empty

@@ -207,6 +207,7 @@ static int make_params(const dyn_synth_params_t *sp, SynthParams *P) {
 extern "C" int dyn_synth_offsets(dyn_ctx_t *ctx, const dyn_synth_params_t *sp, int64_t n_reads, uint32_t *d_rec_off,
                                  void *stream_) {
     DYN_ARG(ctx && d_rec_off && n_reads > 0, "bad argument");
+    CtxEnter enter_(ctx, stream_);
     SynthParams P;
     int rc = make_params(sp, &P);
     if (rc) return rc;

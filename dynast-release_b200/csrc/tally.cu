@@ -885,6 +885,7 @@ extern "C" int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint
                                uint32_t *d_conv_read, int64_t conv_capacity, uint64_t *d_conv_total,
                                uint32_t *d_status, void *stream) {
     DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
     DYN_ARG(n_reads >= 0, "negative n_reads");
     if (n_reads == 0) return DYN_OK;
     DYN_ARG(d_records && d_rec_off && d_counts && d_status, "null buffer");

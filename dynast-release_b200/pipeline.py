@@ -442,6 +442,8 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
                 conversions=conversions, use_conversions=True, key_lo_bits=bc_bits + umi_bits + gene_bits)
     mark('dedup')
     pe_cols = [c for c in CONVERSION_COLUMNS if c[0] not in {x[0] for x in conversions}]
+    if not pe_cols:      # the labelled conversions start with all four bases (p_e.py:84-91): every non-induced column
+        pe_cols = [c for c in CONVERSION_COLUMNS if c not in set(conversions)]
     sums, n_reads, n_with = group_sums(ctx, counts, strand, barcode, n_barcodes, sel=sel, conversions=conversions)
     rates, p_e = rates_pe(ctx, sums, pe_conversions=pe_cols)
     mark('p_e')

@@ -53,6 +53,22 @@ def select_alignments(df_alignments: pd.DataFrame) -> Set[Tuple[str, int]]:
     return set(zip(sel['read_id'].astype(str), sel['index'].astype(int)))
 
 
+def _check_tally_status(status: int, counts: np.ndarray):
+    """DYN_ST_* bits of a quality-0 tally run -> the exception the reference would end in.  The kernel clamps the
+    A/C/G/T content at 255 and skips IUPAC mismatches; the reference writes the true values to the CSVs and fails
+    when they are re-read (uint8 columns, conversion.py:85-95; CONVERSION_IDX KeyError, conversion.py:421), so a
+    silently different file is never produced here."""
+    if status & 0x2:
+        raise ValueError('malformed alignment record (CIGAR / MD / sequence disagree)')
+    if status & 0x8:
+        raise ValueError('conversion-record capacity exceeded while parsing the BAM')
+    # 0x4 (IUPAC mismatch): the record IS emitted (resolve_event returns it before the counter lookup), so
+    # conversions.csv carries the row exactly as the reference writes it; count_conversions raises on it later
+    if status & 0x1 and len(counts) and (counts[:, 12:16] == 255).any():
+        raise ValueError('a read (or read pair) covers more than 255 reference bases of one kind: alignments.csv '
+                         'holds uint8 base contents (conversion.py:85-95)')
+
+
 def _lens(arr) -> np.ndarray:
     return np.char.str_len(np.asarray(arr, dtype=str)).astype(np.int64)
 
@@ -94,8 +110,7 @@ def parse_all_reads(
         n = pb.n_units
         out = device.tally_reads_host(pb.blob, pb.rec_off, quality=0, nasc=nasc, emit_conv=True,
                                       conv_capacity=max(16, int(pb.blob.size)), device=_lib.current_device_index())
-        if out['status'] & 0x2:
-            raise ValueError('malformed alignment record (CIGAR / MD / sequence disagree)')
+        _check_tally_status(out['status'], out['counts'])
         read_id, barcode, umi, gene = pb.read_id, pb.barcode, pb.umi, pb.gene
         hi, score, gx_assigned = pb.hi.copy(), pb.score.copy(), pb.gx_assigned.astype(bool)
         contig = pb.ref_name[pb.ref_id] if n else np.zeros(0, dtype=object)

@@ -96,7 +96,12 @@ typedef struct dyn_ctx dyn_ctx_t;
 const char *dyn_last_error(void);
 int dyn_version(void);
 
-/* One context per GPU (per process). Owns scratch buffers and an internal stream pool. */
+/* One context per GPU (per process). Owns scratch buffers and an internal stream pool.
+ * Threading / stream contract: a context runs ONE call at a time -- every entry point takes the context's lock for
+ * its whole duration, so concurrent host threads serialise -- and its scratch buffers follow stream order: when two
+ * consecutive calls that share a scratch buffer come on different streams, the later stream is made to wait
+ * (cudaStreamWaitEvent) for everything the earlier call queued.  Use one context per stream for calls that
+ * should overlap on the device. */
 int dyn_ctx_create(int device, dyn_ctx_t **ctx);
 int dyn_ctx_destroy(dyn_ctx_t *ctx);
 int dyn_ctx_sm_count(dyn_ctx_t *ctx);
@@ -280,7 +285,9 @@ int dyn_pi_fit(dyn_ctx_t *ctx, const int32_t *d_k, const int32_t *d_n, const int
  * M / D / N runs, MD tokens, 4-bit consensus sequence, qualities clipped to 42; flag 0) at
  * d_out_records + 16 * d_out_off[g]; the MD tag TEXT exactly as consensus.py:124-161, 175 builds it at
  * d_out_md + d_out_md_off[g] (bytes, no terminator); NM in d_out_nm[g].  d_out_status[g]: 0 ok, 2 malformed member record,
- * 3 does not fit a BAM record, 4 members on several contigs (the reference raises), 5 output capacity.
+ * 3 does not fit a BAM record, 4 members on several contigs (the reference raises), 5 output capacity,
+ * 6 a member holds a read or reference base other than A/C/G/T/N (the reference raises KeyError on BASE_IDX,
+ * consensus.py:84-97).
  * The call synchronises the stream once (it sizes its tuple buffers from a device total).
  * ------------------------------------------------------------------------------------------------ */
 int dyn_consensus(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_item_rec16, const int64_t *d_group_off,
@@ -316,7 +323,7 @@ int dyn_unique_counts(dyn_ctx_t *ctx, const uint64_t *d_keys, int64_t n_keys, ui
  *                        transcriptome u8 | 2 pad
  *   dyn_unpack_reads:    the inverse on the receiving side
  * ------------------------------------------------------------------------------------------------ */
-#define DYN_MAX_WORLD 64
+#define DYN_MAX_WORLD 64   /* dyn_owner_partition / dyn_merge_kn take at most 2^31 - 1 rows per call */
 #define DYN_READ_ROW_BYTES 40
 int dyn_owner_partition(dyn_ctx_t *ctx, const uint32_t *d_barcode, int64_t n, int world, uint32_t *d_perm,
                         uint64_t *d_owner_counts, void *stream);
