@@ -43,6 +43,7 @@ PROTOTYPES = {
     'dyn_consensus': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'dyn_coverage': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     'dyn_unique_counts': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'dyn_velocity': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     'dyn_owner_partition': (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     'dyn_pack_reads': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_unpack_reads': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -121,6 +122,13 @@ class SynthParams(C.Structure):
         ('p_e', C.c_double), ('frac_n', C.c_double), ('d_bc_cdf', C.c_void_p), ('d_gene_cdf', C.c_void_p),
         ('d_gene_pi', C.c_void_p), ('d_gene_strand', C.c_void_p), ('d_gene_contig', C.c_void_p),
     ]
+
+
+class Annotation(C.Structure):
+    """dyn_annotation_t"""
+    _fields_ = [('n_ref', C.c_int32), ('n_genes', C.c_int32)] + [(name, C.c_void_p) for name in (
+        'd_contig_off', 'd_gene_start', 'd_gene_end', 'd_gene_pmax', 'd_gene_strand', 'd_gene_tr_off', 'd_tr_exon_off',
+        'd_tr_intron_off', 'd_exon_start', 'd_exon_end', 'd_intron_start', 'd_intron_end')]
 
 
 def ptr(arr):

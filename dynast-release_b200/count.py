@@ -1,11 +1,9 @@
 """`dynast count` -- thin orchestrator with the stage order, options and output files of dynast/count.py:15-393
 (reference), calling the B200 operators of dynast_b200.preprocessing.
 
-Differences that are data-source, not semantics: gene annotation is passed as `gene_infos` (the dict
-`ngs_tools.gtf.genes_and_transcripts_from_gtf` builds -- {gene_id: {'strand', 'chromosome', 'gene_name', ...}};
-GTF parsing is out of scope) and the BAM must already be coordinate sorted (the reference sorts it with samtools
-when it is not).  `velocity=True` needs `velocity_assignments`.  The AnnData object is
-written only when `anndata` is importable; the layers are returned either way."""
+The GTF is parsed by dynast_b200.gtf (ngs_tools is not needed); the BAM must already be coordinate sorted (the
+reference sorts it with samtools when it is not).  The AnnData object is written only when `anndata` is
+importable; the layers are returned either way."""
 import datetime as dt
 import gzip
 import json
@@ -17,7 +15,7 @@ from typing import Dict, FrozenSet, List, Optional, Tuple
 
 import pandas as pd
 
-from . import constants, preprocessing, utils
+from . import constants, gtf, preprocessing, utils
 
 
 def _write_pickle(obj, path):
@@ -31,7 +29,7 @@ def _all_exists(*paths):
 
 def count(
     bam_path: str,
-    gene_infos: dict,
+    gtf_path,
     out_dir: str,
     strand: str = 'forward',
     umi_tag: Optional[str] = None,
@@ -53,9 +51,15 @@ def count(
     nasc: bool = False,
     overwrite: bool = False,
     velocity_assignments: Optional[Dict[Tuple[str, int], Tuple[str, str]]] = None,
-    consensus_bam: bool = False,
+    consensus_bam: Optional[bool] = None,
+    transcript_infos: Optional[dict] = None,
 ):
-    """count.count (count.py:15-393). Returns the results object (AnnData or utils.Results; None for --control)."""
+    """count.count (count.py:15-393). Returns the results object (AnnData or utils.Results; None for --control).
+
+    `gtf_path` is the annotation GTF, parsed by gtf.genes_and_transcripts_from_gtf as count.py:146-147 does with
+    ngs_tools; a ready-made `gene_infos` dictionary is accepted in its place (then `transcript_infos` carries the
+    exon / intron tables velocity assignment needs).  `consensus_bam` overrides the RN-tag detection of
+    count.py:295-304 (None: look at the BAM)."""
     t0 = time.time()
     start = dt.datetime.now()
     os.makedirs(out_dir, exist_ok=True)
@@ -68,14 +72,22 @@ def count(
     alignments_path = os.path.join(out_dir, constants.ALIGNMENTS_FILENAME)
     genes_path = os.path.join(out_dir, constants.GENES_FILENAME)
     bam_parsed = False
+    gene_infos = gtf_path if isinstance(gtf_path, dict) else None
     if not _all_exists(conversions_path, index_path, alignments_path, genes_path) or overwrite:
-        _write_pickle(gene_infos, genes_path)
+        if gene_infos is None:
+            gene_infos, transcript_infos = gtf.genes_and_transcripts_from_gtf(gtf_path, use_version=False)
+        # plain tuples for the segments: the pickle must load without this package (and without ngs_tools)
+        _write_pickle({g: {**info, 'segment': tuple(info['segment'])} if 'segment' in info else info
+                       for g, info in gene_infos.items()}, genes_path)
         preprocessing.parse_all_reads(
-            bam_path, conversions_path, alignments_path, index_path, gene_infos, None, strand=strand, umi_tag=umi_tag,
+            bam_path, conversions_path, alignments_path, index_path, gene_infos, transcript_infos, strand=strand, umi_tag=umi_tag,
             barcode_tag=barcode_tag, gene_tag=gene_tag, barcodes=barcodes, n_threads=n_threads, temp_dir=temp_dir, nasc=nasc,
             control=control, velocity=velocity, strict_exon_overlap=strict_exon_overlap,
             velocity_assignments=velocity_assignments)
         bam_parsed = True
+    elif gene_infos is None:
+        with gzip.open(genes_path, 'rb') as f:      # count.py:170-171
+            gene_infos = pickle.load(f)
 
     # ---- SNP detection (count.py:199-282)
     convs_path = os.path.join(out_dir, constants.CONVS_FILENAME)

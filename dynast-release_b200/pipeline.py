@@ -309,6 +309,29 @@ def kn_csr(ctx: Context, keys, count32, n_rows, n_groups: int):
 READ_ROW_BYTES = 40
 
 
+VELOCITY_NAMES = ('unassigned', 'spliced', 'unspliced', 'ambiguous')
+STRAND_MODES = {'forward': 0, 'reverse': 1, 'unstranded': 2}
+
+
+def velocity(ctx: Context, records: torch.Tensor, rec_off: torch.Tensor, tables, gx: Optional[torch.Tensor] = None,
+             strand: str = 'forward', strict_exon_overlap: bool = False):
+    """dyn_velocity: (gene row int32 [n], type uint8 [n] -- 0 dropped, 1 spliced, 2 unspliced, 3 ambiguous -- and the
+    status word) of every unit.  `tables` = gtf.AnnotationTables; gx = gene row per unit, -1 where the read carries
+    no gene tag."""
+    from ._lib import Annotation
+    n = rec_off.numel() - 1
+    dev = records.device
+    d = tables.to_device(dev)
+    ann = Annotation(n_ref=len(tables.contig_off) - 1, n_genes=tables.n_genes,
+                     **{'d_' + k: d[k].data_ptr() for k in tables.ARRAYS})
+    gene = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    kind = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(ctx.lib.dyn_velocity(ctx.handle, ptr(records), ptr(rec_off), n, ptr(gx), C.byref(ann), STRAND_MODES[strand],
+                               int(bool(strict_exon_overlap)), ptr(gene), ptr(kind), ptr(status), _stream()))
+    return gene[:n], kind[:n], status
+
+
 def owner_partition(ctx: Context, barcode: torch.Tensor, world: int):
     """dyn_owner_partition -> (perm int32 [n] (bit pattern uint32): local reads grouped by barcode % world, stable;
     counts int64 [world])."""

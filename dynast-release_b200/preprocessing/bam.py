@@ -9,7 +9,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from .. import _lib, bamio, device, pipeline, records
+from .. import _lib, bamio, device, gtf, pipeline, records
 
 CONVERSION_CSV_COLUMNS = ['read_id', 'index', 'contig', 'genome_i', 'conversion', 'quality']
 ALIGNMENT_COLUMNS = ['read_id', 'index', 'barcode', 'umi', 'GX', 'A', 'C', 'G', 'T', 'velocity', 'transcriptome', 'score']
@@ -69,6 +69,54 @@ def _check_tally_status(status: int, counts: np.ndarray):
                          'holds uint8 base contents (conversion.py:85-95)')
 
 
+_TABLES_CACHE = {}
+
+
+def annotation_tables(gene_infos: dict, transcript_infos: dict, ref_names) -> gtf.AnnotationTables:
+    """Device tables of an annotation (built once per (gene_infos, transcript_infos, contig list))."""
+    key = (id(gene_infos), id(transcript_infos), tuple(ref_names))
+    hit = _TABLES_CACHE.get(key)
+    if hit is None or hit[0] is not gene_infos:
+        _TABLES_CACHE.clear()
+        hit = _TABLES_CACHE[key] = (gene_infos, gtf.AnnotationTables(gene_infos, transcript_infos or {}, list(ref_names)))
+    return hit[1]
+
+
+def assign_velocity(blob: np.ndarray, rec_off: np.ndarray, gene: np.ndarray, tables: gtf.AnnotationTables,
+                    strand: str = 'forward', strict_exon_overlap: bool = False, chunk_bytes: int = 1 << 28):
+    """bam.assign_velocity_type (bam.py:177-228, 363-383) for every unit of a packed BAM: (gene ids, assignment
+    names, keep mask).  Records are streamed to the device in chunks; the work is dyn_velocity."""
+    ctx = _lib.current_context()
+    dev = _lib.current_torch_device()
+    n = len(rec_off) - 1
+    uniq, inv = np.unique(np.asarray(gene, dtype=object).astype(str), return_inverse=True) if n else (np.zeros(0, str), np.zeros(0, int))
+    rows = np.array([-1 if g == '' else tables.gene_index.get(g, -2) for g in uniq], dtype=np.int32)
+    gx = rows[inv] if n else np.zeros(0, dtype=np.int32)
+    out_gene = np.full(n, -1, dtype=np.int32)
+    out_type = np.zeros(n, dtype=np.uint8)
+    status = 0
+    off64 = rec_off.astype(np.int64)
+    u0 = 0
+    while u0 < n:
+        u1 = int(np.searchsorted(off64, off64[u0] + max(chunk_bytes // 16, 1), side='right')) - 1
+        u1 = min(max(u1, u0 + 1), n)
+        d_rec = torch.from_numpy(np.ascontiguousarray(blob[off64[u0] * 16:off64[u1] * 16])).to(dev)
+        d_off = torch.from_numpy((off64[u0:u1 + 1] - off64[u0]).astype(np.int32)).to(dev)
+        g, t, st = pipeline.velocity(ctx, d_rec, d_off, tables, gx=torch.from_numpy(gx[u0:u1]).to(dev), strand=strand,
+                                     strict_exon_overlap=strict_exon_overlap)
+        out_gene[u0:u1] = g.cpu().numpy()
+        out_type[u0:u1] = t.cpu().numpy()
+        status |= int(st.item())
+        u0 = u1
+    if status & 2:
+        bad = sorted({g for g, r in zip(uniq, rows) if r == -2})
+        raise KeyError(f'gene tag value not in the annotation of its contig: {bad[:5] if bad else "(contig mismatch)"}')
+    if status & 1:
+        raise ValueError('an alignment has more than 48 aligned blocks')
+    ids = np.asarray(tables.gene_ids + [''], dtype=object)
+    return ids[out_gene], np.asarray(pipeline.VELOCITY_NAMES, dtype=object)[out_type], out_type != 0
+
+
 def _lens(arr) -> np.ndarray:
     return np.char.str_len(np.asarray(arr, dtype=str)).astype(np.int64)
 
@@ -97,14 +145,13 @@ def parse_all_reads(
     """bam.parse_all_reads (bam.py:648-780): conversions.csv, alignments.csv and the conversions index of a
     coordinate-sorted BAM, byte for byte.
 
-    Velocity assignment (bam.py:177-228, 363-383) is SURVEY section 8 row f2 ("next"): with velocity=True the
-    (gene, assignment) of every read must be supplied through `velocity_assignments` ({(read_id, HI): (GX,
-    velocity)}; reads absent from it are dropped, as bam.py:382-383 does for unassigned reads).
-    `n_threads` drives the BGZF inflate; `temp_dir`, `strand`, `transcript_infos`, `control`,
-    `strict_exon_overlap` are accepted for signature compatibility."""
-    if velocity and velocity_assignments is None:
-        raise NotImplementedError('velocity assignment is not part of the B200 hot path yet: pass velocity=False '
-                                  '(dynast count --no-splicing) or supply velocity_assignments')
+    Velocity assignment (bam.py:177-228, 363-383) runs on the device (dyn_velocity) from `gene_infos` /
+    `transcript_infos` (gtf.genes_and_transcripts_from_gtf, or the dictionaries ngs_tools builds); reads it
+    leaves unassigned are dropped (bam.py:382-383).  `velocity_assignments` ({(read_id, HI): (GX, velocity)})
+    overrides the computation when given.  `n_threads` drives the BGZF inflate; `temp_dir` and `control` are
+    accepted for signature compatibility."""
+    if velocity and velocity_assignments is None and not gene_infos:
+        raise ValueError('velocity=True needs gene_infos and transcript_infos (gtf.genes_and_transcripts_from_gtf)')
     with bamio.PackedBam(bam_path, barcode_tag=barcode_tag, umi_tag=umi_tag, gene_tag=gene_tag, require_gene=not velocity,
                          n_threads=n_threads) as pb:
         n = pb.n_units
@@ -114,12 +161,20 @@ def parse_all_reads(
         read_id, barcode, umi, gene = pb.read_id, pb.barcode, pb.umi, pb.gene
         hi, score, gx_assigned = pb.hi.copy(), pb.score.copy(), pb.gx_assigned.astype(bool)
         contig = pb.ref_name[pb.ref_id] if n else np.zeros(0, dtype=object)
+        computed = None
+        if velocity and velocity_assignments is None:
+            tables = annotation_tables(gene_infos, transcript_infos, pb.ref_name)
+            computed = assign_velocity(pb.blob, pb.rec_off, gene, tables, strand=strand,
+                                       strict_exon_overlap=strict_exon_overlap)
     keep = np.ones(n, dtype=bool)
     if barcodes:
         keep &= np.isin(barcode, list(barcodes))
     assignment = np.full(n, 'unassigned', dtype=object)
     gx_out = gene.copy()
-    if velocity:
+    if computed is not None:
+        gx_out, assignment, assigned = computed
+        keep &= assigned
+    elif velocity:
         for i in range(n):
             hit = velocity_assignments.get((read_id[i], int(hi[i]))) if keep[i] else None
             if hit is None:

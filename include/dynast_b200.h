@@ -313,6 +313,41 @@ int dyn_unique_counts(dyn_ctx_t *ctx, const uint64_t *d_keys, int64_t n_keys, ui
                       uint32_t *d_out_first, int64_t *d_n_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * f2: velocity assignment.  Replaces bam.assign_velocity_type (dynast/preprocessing/bam.py:177-228, built on
+ * ngs_tools.gtf.SegmentCollection) and the read-strand rule of bam.py:363-380 for every counting unit at once.
+ * The annotation is the flat form of (gene_infos, transcript_infos) -- ngs_tools.gtf.genes_and_transcripts_from_gtf,
+ * count.py:146-147 -- with 0-based half-open coordinates: genes grouped by contig (BAM header order) and sorted by
+ * (start, end) inside a contig (bam.py:177-178), exons and introns of every transcript sorted and collapsed.
+ *   d_gx [n_units] i32    gene row of the unit's gene tag; -1 = no tag: the gene is searched among the genes of the
+ *                         unit's contig that contain the alignment and lie on the read's strand; any other
+ *                         negative value or a gene of another contig = the reference's KeyError (status bit 2).
+ *                         NULL = no unit carries a gene
+ *   strand_mode           0 forward, 1 reverse, 2 unstranded (--strand)
+ *   d_out_gene [n_units]  assigned gene row, -1 when the unit is dropped (bam.py:382-383)
+ *   d_out_type [n_units]  0 dropped, 1 spliced, 2 unspliced, 3 ambiguous
+ *   d_status              u32, OR-accumulated: 1 a unit has more aligned blocks than the kernel holds (48),
+ *                         2 gene tag unknown to the annotation of the unit's contig
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t n_ref, n_genes;
+    const int32_t *d_contig_off;      /* [n_ref + 1] genes of contig c: rows [d_contig_off[c], d_contig_off[c + 1]) */
+    const int32_t *d_gene_start, *d_gene_end;   /* [n_genes] */
+    const int32_t *d_gene_pmax;       /* [n_genes] running maximum of d_gene_end inside the contig */
+    const uint8_t *d_gene_strand;     /* [n_genes] 0 '+', 1 '-', 2 other */
+    const int32_t *d_gene_tr_off;     /* [n_genes + 1] transcripts of a gene */
+    const int32_t *d_tr_exon_off, *d_tr_intron_off;   /* [n_transcripts + 1] */
+    const int32_t *d_exon_start, *d_exon_end, *d_intron_start, *d_intron_end;
+} dyn_annotation_t;
+
+#define DYN_VELOCITY_NONE 0
+#define DYN_VELOCITY_SPLICED 1
+#define DYN_VELOCITY_UNSPLICED 2
+#define DYN_VELOCITY_AMBIGUOUS 3
+int dyn_velocity(dyn_ctx_t *ctx, const void *d_records, const uint32_t *d_rec_off, int64_t n_units, const int32_t *d_gx,
+                 const dyn_annotation_t *annotation, int strand_mode, int strict_exon_overlap, int32_t *d_out_gene,
+                 uint8_t *d_out_type, uint32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-read exchange to the barcode owner (multi-GPU).  The reference runs one process over the whole
  * conversions.csv (conversion.py:529-606); with read-range sharding a UMI group can straddle ranks, so before
  * dyn_dedup_umi every rank sends its reads' fixed-size rows to rank barcode % world.

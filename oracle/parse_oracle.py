@@ -38,8 +38,17 @@ def parse_contig(
     nasc: bool = False,
     velocity: bool = True,
     velocity_lookup: Optional[Dict[Tuple[str, int], Tuple[str, str]]] = None,
+    annotation=None,
+    strand: str = 'forward',
+    strict_exon_overlap: bool = False,
 ):
-    """Returns (conversion_lines, alignment_lines, index) for one contig; index offsets are local."""
+    """Returns (conversion_lines, alignment_lines, index) for one contig; index offsets are local.
+    `annotation` = (gene_infos of this contig, transcript_infos): velocity is computed by
+    oracle/velocity_oracle.py (bam.py:177-228, 363-383) instead of being looked up."""
+    if velocity and annotation is not None:
+        from . import velocity_oracle
+        v_genes, v_transcripts = annotation
+        v_order = velocity_oracle.gene_order(v_genes)
     required = []
     if not velocity:
         required.append(gene_tag)
@@ -101,7 +110,13 @@ def parse_contig(
         content.update(read.get_reference_sequence().upper())
 
         assignment = 'unassigned'
-        if velocity:
+        if velocity and annotation is not None:
+            gx, assignment = velocity_oracle.assign_velocity_type(
+                ref_positions, v_genes, v_transcripts, v_order, gx=gx,
+                strand=velocity_oracle.read_strand(read.flag, strand), strict_exon_overlap=strict_exon_overlap)
+            if not assignment or not gx:
+                continue
+        elif velocity:
             hit = (velocity_lookup or {}).get((read_id, hi))
             if hit is None:
                 continue
@@ -153,8 +168,15 @@ def parse_all_reads(
     nasc=False,
     velocity=True,
     velocity_lookup=None,
+    annotation=None,
+    strand='forward',
+    strict_exon_overlap=False,
 ):
     """Whole-BAM driver (bam.py:648-780 with n_threads=1). Writes both CSVs, returns the index list."""
+    genes_by_contig = None
+    if annotation is not None:
+        from . import velocity_oracle
+        genes_by_contig = velocity_oracle.by_contig(annotation[0])
     _, refs, reads = bamio.read_bam(bam_path)
     per_contig: Dict[int, List[bamio.Read]] = {}
     for r in reads:
@@ -176,6 +198,9 @@ def parse_all_reads(
                 nasc=nasc,
                 velocity=velocity,
                 velocity_lookup=velocity_lookup,
+                annotation=None if annotation is None else (genes_by_contig.get(refs[ref_id][0], {}), annotation[1]),
+                strand=strand,
+                strict_exon_overlap=strict_exon_overlap,
             )
             fc.write(''.join(conv))
             fa.write(''.join(ali))

@@ -46,11 +46,15 @@ def test_count_smartseq_no_splicing(gpu_ctx, tmp_path):
 def test_count_control_with_snp_detection(gpu_ctx, tmp_path):
     """UMI fixture, --control --snp-threshold 0.5: coverage.csv and snps.csv byte-equal, counts use the SNP mask."""
     from dynast_b200 import count
-    lookup = {(r['read_id'], int(r['index'])): (r['GX'], r['velocity']) for r in ref_rows('SRR11683995_count', 'alignments.csv')}
+    from velocity_cases import FIXTURE_GTF
     out = str(tmp_path / 'control')
-    res = count.count(ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'), gene_infos(), out, umi_tag='UB',
-                      barcode_tag='CB', control=True, snp_threshold=0.5, velocity=True, velocity_assignments=lookup)
+    # the default path: GTF in, velocity assigned on the device
+    res = count.count(ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'), FIXTURE_GTF, out, umi_tag='UB',
+                      barcode_tag='CB', control=True, snp_threshold=0.5)
     assert res is None
+    assert open(os.path.join(out, 'alignments.csv')).read() == ref_text('SRR11683995_count', 'alignments.csv')
+    with gzip.open(os.path.join(out, 'genes.pkl.gz'), 'rb') as f:
+        assert len(pickle.load(f)) == len(gene_infos())
     for name in ('coverage.csv', 'snps.csv', 'counts_TC.csv'):
         assert open(os.path.join(out, name)).read() == ref_text('SRR11683995_count_control', name), name
 

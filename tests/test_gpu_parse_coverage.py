@@ -19,14 +19,15 @@ pytestmark = pytest.mark.gpu
     ('nasc_align', 'nasc_count', dict(umi_tag=None, barcode_tag='RG', velocity=False), True),
 ])
 def test_parse_all_reads_bytes(gpu_ctx, tmp_path, align, count, kw, nasc):
+    from dynast_b200 import gtf
     from dynast_b200.preprocessing import bam
-    lookup = None
-    if kw['velocity']:   # velocity assignment is row f2 (next): injected from the fixture, as in the oracle test
-        lookup = {(r['read_id'], int(r['index'])): (r['GX'], r['velocity']) for r in ref_rows(count, 'alignments.csv')}
+    from velocity_cases import FIXTURE_GTF
+    genes, transcripts = gene_infos(), None
+    if kw['velocity']:   # velocity assignment on the device from the annotation oracle/make_velocity_gtf.py synthesised
+        genes, transcripts = gtf.genes_and_transcripts_from_gtf(FIXTURE_GTF)
     c, a, i = (str(tmp_path / x) for x in ('conversions.csv', 'alignments.csv', 'conversions.idx'))
-    got = bam.parse_all_reads(ref_path(align, 'Aligned.sortedByCoord.out.bam'), c, a, i, gene_infos(), None, strand='forward',
-                              gene_tag='GX', barcodes=None, n_threads=1, temp_dir=str(tmp_path), nasc=nasc,
-                              velocity_assignments=lookup, **kw)
+    got = bam.parse_all_reads(ref_path(align, 'Aligned.sortedByCoord.out.bam'), c, a, i, genes, transcripts, strand='forward',
+                              gene_tag='GX', barcodes=None, n_threads=1, temp_dir=str(tmp_path), nasc=nasc, **kw)
     assert got == (c, a, i)
     assert open(c).read() == ref_text(count, 'conversions.csv')
     assert open(a).read() == ref_text(count, 'alignments.csv')
@@ -34,11 +35,30 @@ def test_parse_all_reads_bytes(gpu_ctx, tmp_path, align, count, kw, nasc):
         assert pickle.load(f) == pickle.load(g)
 
 
-def test_parse_velocity_needs_assignments(gpu_ctx, tmp_path):
+def test_parse_velocity_injected_assignments(gpu_ctx, tmp_path):
+    """`velocity_assignments` overrides the device assignment (what round 1 tested); without an annotation and
+    without assignments the call refuses."""
     from dynast_b200.preprocessing import bam
-    with pytest.raises(NotImplementedError):
-        bam.parse_all_reads(ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'), 'c', 'a', 'i', {}, None,
-                            umi_tag='UB', barcode_tag='CB')
+    path = ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam')
+    with pytest.raises(ValueError):
+        bam.parse_all_reads(path, 'c', 'a', 'i', {}, None, umi_tag='UB', barcode_tag='CB')
+    lookup = {(r['read_id'], int(r['index'])): (r['GX'], r['velocity']) for r in ref_rows('SRR11683995_count', 'alignments.csv')}
+    c, a, i = (str(tmp_path / x) for x in ('conversions.csv', 'alignments.csv', 'conversions.idx'))
+    bam.parse_all_reads(path, c, a, i, gene_infos(), None, umi_tag='UB', barcode_tag='CB', velocity_assignments=lookup)
+    assert open(a).read() == ref_text('SRR11683995_count', 'alignments.csv')
+
+
+def test_parse_velocity_unknown_gene_tag_raises(gpu_ctx, tmp_path):
+    """A GX value absent from the annotation of the read's contig is a KeyError in the reference (bam.py:186, 203)."""
+    from dynast_b200 import gtf
+    from dynast_b200.preprocessing import bam
+    from velocity_cases import FIXTURE_GTF
+    genes, transcripts = gtf.genes_and_transcripts_from_gtf(FIXTURE_GTF)
+    tagged = next(r['GX'] for r in ref_rows('SRR11683995_count', 'alignments.csv') if r['transcriptome'] == 'True')
+    genes = {g: v for g, v in genes.items() if g != tagged}
+    with pytest.raises(KeyError):
+        bam.parse_all_reads(ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'), str(tmp_path / 'c'), str(tmp_path / 'a'),
+                            str(tmp_path / 'i'), genes, transcripts, umi_tag='UB', barcode_tag='CB')
 
 
 def _selected(tmp_path):
