@@ -54,6 +54,11 @@ PROTOTYPES = {
     'dyn_bam_n_records_seen': (_i64, [_vp]),
     'dyn_bam_n_refs': (_i64, [_vp]),
     'dyn_bam_field': (_vp, [_vp, _i32, C.POINTER(_i64)]),
+    'dyn_bam_stream_open': (_i32, [C.c_char_p, _vp, C.POINTER(_vp)]),
+    'dyn_bam_stream_next': (_i32, [_vp, C.POINTER(_vp)]),
+    'dyn_bam_stream_close': (None, [_vp]),
+    'dyn_bam_stream_n_refs': (_i64, [_vp]),
+    'dyn_bam_stream_field': (_vp, [_vp, _i32, C.POINTER(_i64)]),
     'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
     'dyn_synth_fill': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
@@ -122,6 +127,13 @@ class SynthParams(C.Structure):
         ('p_e', C.c_double), ('frac_n', C.c_double), ('d_bc_cdf', C.c_void_p), ('d_gene_cdf', C.c_void_p),
         ('d_gene_pi', C.c_void_p), ('d_gene_strand', C.c_void_p), ('d_gene_contig', C.c_void_p),
     ]
+
+
+class BamStreamOpts(C.Structure):
+    """dyn_bam_stream_opts_t"""
+    _fields_ = [('barcode_tag', C.c_char_p), ('umi_tag', C.c_char_p), ('gene_tag', C.c_char_p), ('require_gene', C.c_int32),
+                ('n_threads', C.c_int32), ('part', C.c_int32), ('n_parts', C.c_int32), ('chunk_bytes', C.c_int64),
+                ('lean', C.c_int32), ('keys', C.c_int32), ('gene_ids', C.POINTER(C.c_char_p)), ('n_gene_ids', C.c_int64)]
 
 
 class Annotation(C.Structure):

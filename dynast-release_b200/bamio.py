@@ -10,6 +10,7 @@ from . import _lib
 _FIELDS = {'blob': (0, np.uint8), 'rec_off': (1, np.uint32), 'ref_id': (2, np.int32), 'pos': (3, np.int32),
            'flag': (4, np.uint16), 'hi': (5, np.int32), 'score': (6, np.int32), 'gx_assigned': (7, np.uint8),
            'paired': (8, np.uint8), 'ref_len': (9, np.int32)}
+_FIELDS.update({'barcode_key': (11, np.uint64), 'umi_key': (12, np.uint64), 'gene_idx': (13, np.int32)})
 _POOLS = {'read_id': (20, 21), 'barcode': (22, 23), 'umi': (24, 25), 'gene': (26, 27), 'ref_name': (28, 29)}
 
 
@@ -24,10 +25,21 @@ class PackedBam:
         enc = lambda s: s.encode() if s else None
         _lib.check(self.lib.dyn_bam_pack(path.encode(), enc(barcode_tag), enc(umi_tag), enc(gene_tag), int(require_gene),
                                          int(n_threads), C.byref(h)))
+        self._adopt(h)
+
+    def _adopt(self, h):
         self.handle = h
         self.n_units = int(self.lib.dyn_bam_n_units(h))
         self.n_records_seen = int(self.lib.dyn_bam_n_records_seen(h))
         self._cache = {}
+
+    @classmethod
+    def from_handle(cls, lib, handle) -> 'PackedBam':
+        """A chunk handed out by dyn_bam_stream_next."""
+        self = cls.__new__(cls)
+        self.lib = lib
+        self._adopt(handle)
+        return self
 
     def _raw(self, field: int, dtype):
         nb = C.c_int64(0)
@@ -64,6 +76,84 @@ class PackedBam:
     def close(self):
         if self.handle:
             self.lib.dyn_bam_result_free(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def decode_key(key: int, suffix: bool = True) -> str:
+    """The string a 2-bit barcode / UMI key stands for (the inverse of the packer's encoding)."""
+    key = int(key)
+    if key == 0:
+        return 'NA'
+    well = (key >> 58) if suffix else 0
+    k = key & ((1 << 58) - 1) if suffix else key
+    out = []
+    while k > 1:
+        out.append('ACGT'[k & 3])
+        k >>= 2
+    return ''.join(reversed(out)) + (f'-{well - 1}' if well else '')
+
+
+class BamStream:
+    """dyn_bam_stream_*: block range `part` of `n_parts` of a coordinate-sorted BAM, chunk by chunk (each chunk a
+    PackedBam; close it when done -- its page-locked buffer is reused).  The next chunks are inflated and packed by
+    the library's threads while the caller works on the current one.  gene_ids: the gene tag becomes an index into
+    this list and barcode / UMI become 2-bit keys (fields barcode_key, umi_key, gene_idx) instead of strings."""
+
+    def __init__(self, path: str, barcode_tag: Optional[str] = None, umi_tag: Optional[str] = None,
+                 gene_tag: Optional[str] = 'GX', require_gene: bool = False, n_threads: int = 8, part: int = 0,
+                 n_parts: int = 1, chunk_bytes: int = 0, lean: bool = False, keys: bool = False,
+                 gene_ids: Optional[List[str]] = None):
+        self.lib = _lib.load()
+        enc = lambda s: s.encode() if s else None
+        self._gene_ids = None
+        o = _lib.BamStreamOpts(barcode_tag=enc(barcode_tag), umi_tag=enc(umi_tag), gene_tag=enc(gene_tag),
+                               require_gene=int(require_gene), n_threads=int(n_threads), part=int(part), n_parts=int(n_parts),
+                               chunk_bytes=int(chunk_bytes), lean=int(lean), keys=int(keys or gene_ids is not None))
+        if gene_ids is not None:
+            self._gene_ids = (C.c_char_p * len(gene_ids))(*[g.encode() for g in gene_ids])
+            o.gene_ids = C.cast(self._gene_ids, C.POINTER(C.c_char_p))
+            o.n_gene_ids = len(gene_ids)
+        h = C.c_void_p()
+        _lib.check(self.lib.dyn_bam_stream_open(path.encode(), C.byref(o), C.byref(h)))
+        self.handle = h
+
+    def _raw(self, field: int, dtype):
+        nb = C.c_int64(0)
+        p = self.lib.dyn_bam_stream_field(self.handle, field, C.byref(nb))
+        if not p or nb.value == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nb.value,)).view(dtype).copy()
+
+    @property
+    def ref_len(self) -> np.ndarray:
+        return self._raw(9, np.int32)
+
+    @property
+    def header_text(self) -> str:
+        return self._raw(10, np.uint8).tobytes().decode(errors='replace')
+
+    @property
+    def ref_name(self) -> np.ndarray:
+        data, off = self._raw(28, np.uint8).tobytes(), self._raw(29, np.uint32)
+        return np.array([data[off[i]:off[i + 1]].decode() for i in range(len(off) - 1)], dtype=object)
+
+    def __iter__(self):
+        while True:
+            h = C.c_void_p()
+            _lib.check(self.lib.dyn_bam_stream_next(self.handle, C.byref(h)))
+            if not h:
+                return
+            yield PackedBam.from_handle(self.lib, h)
+
+    def close(self):
+        if self.handle:
+            self.lib.dyn_bam_stream_close(self.handle)
             self.handle = None
 
     def __enter__(self):

@@ -57,13 +57,41 @@ def tokenize_md(md: str, cigar: Sequence[Tuple[int, int]]):
     return toks, ok
 
 
+LEAN = 0x2000
+
+
+def fold_token_quals(toks: List[int], cigar: Sequence[Tuple[int, int]], qual: Sequence[int]) -> List[int]:
+    """Lean layout: the Phred of the query base at every non-deleted token's aligned offset goes into bits 21..28."""
+    aligned_to_query = {}
+    done = q = 0
+    for op, n in cigar:
+        if op in (0, 7, 8):
+            for i in range(n):
+                aligned_to_query[done + i] = q + i
+            done += n
+            q += n
+        elif op in (1, 4):
+            q += n
+    out = []
+    for t in toks:
+        if not (t >> 20) & 1:
+            qpos = aligned_to_query.get(t & 0xffff)
+            t |= (int(qual[qpos]) if qpos is not None and qpos < len(qual) else 0) << 21
+        out.append(t)
+    return out
+
+
 def pack_one(pos: int, ref_id: int, flag: int, cigar: Sequence[Tuple[int, int]], seq: str, qual: Sequence[int],
-             md: str) -> bytes:
-    """One record: 16-byte header + cigar + MD tokens + 4-bit seq (padded to 4) + qual, padded to 16 bytes."""
+             md: str, lean: bool = False) -> bytes:
+    """One record: 16-byte header + cigar + MD tokens + 4-bit seq (padded to 4) + qual, padded to 16 bytes.
+    lean: the DYN_REC_LEAN layout (no qual stream, mismatch qualities inside the tokens; single-end units only)."""
     l_seq = len(seq)
     toks, ok = tokenize_md(md, cigar)
     if len(toks) > 0xffff:
         toks, ok = [], False
+    if lean:
+        toks = fold_token_quals(toks, cigar, qual)
+        flag |= LEAN
     hdr = np.zeros(1, dtype=[('pos', '<i4'), ('ref', '<i4'), ('l', '<u2'), ('nc', '<u2'), ('nt', '<u2'), ('fl', '<u2')])
     hdr['pos'], hdr['ref'], hdr['l'], hdr['nc'], hdr['nt'] = pos, ref_id, l_seq, len(cigar), len(toks)
     hdr['fl'] = flag | (0 if ok else BAD_MD)
@@ -73,7 +101,7 @@ def pack_one(pos: int, ref_id: int, flag: int, cigar: Sequence[Tuple[int, int]],
     sb = bytearray((nb + 3) & ~3)
     for i, c in enumerate(seq):
         sb[i >> 1] |= _CODE[c] << (4 if (i & 1) == 0 else 0)
-    body = hdr.tobytes() + cig + tok + bytes(sb) + np.asarray(qual, dtype=np.uint8).tobytes()
+    body = hdr.tobytes() + cig + tok + bytes(sb) + (b'' if lean else np.asarray(qual, dtype=np.uint8).tobytes())
     return body + b'\0' * (-len(body) % 16)
 
 

@@ -44,7 +44,7 @@ extern "C" {
  *                                              deleted reference base (a letter of a ^XYZ run)
  *     uint8_t  seq[(l_seq + 1) / 2];           BAM 4-bit codes "=ACMGRSVTWYHKDBN", high nibble first;
  *                                              zero-padded to a multiple of 4 bytes
- *     uint8_t  qual[l_seq];                    Phred
+ *     uint8_t  qual[l_seq];                    Phred (absent in a lean record, see DYN_REC_LEAN)
  *     zero padding to a multiple of 16 bytes
  * The packer checks the MD tag against the CIGAR (matched + mismatched bases == M/=/X length, deleted
  * letters == D length) and sets DYN_REC_BAD_MD otherwise (pysam raises on such a record).
@@ -63,9 +63,16 @@ typedef struct {
 
 #define DYN_REC_HAS_MATE 0x8000u
 #define DYN_REC_BAD_MD 0x4000u
+/* Lean record (single-end units only): the qual[] stream is left out and every non-deleted MD token carries, in
+ * bits 21..28, the Phred of the query base at its aligned offset -- the only qualities a single-end read's tally
+ * needs (bam.py:391-411, conversion.py:424).  Half the bytes per read.  Paired units keep the full layout (the mate
+ * rule of bam.py:395-403 compares qualities at positions where only one mate mismatches), and so does anything
+ * that goes to dyn_consensus (it sums every base's quality). */
+#define DYN_REC_LEAN 0x2000u
 #define DYN_TOK_AOFF(tok) ((uint32_t)(tok) & 0xffffu)
 #define DYN_TOK_BASE(tok) (((uint32_t)(tok) >> 16) & 0xfu)
 #define DYN_TOK_IS_DEL(tok) (((uint32_t)(tok) >> 20) & 1u)
+#define DYN_TOK_QUAL(tok) (((uint32_t)(tok) >> 21) & 0xffu)   /* lean records only */
 
 /* Conversion record codes: (ref nibble << 4) | read nibble, both BAM 4-bit codes (A=1,C=2,G=4,T=8).
  * One 64-bit record per mismatch: bits 0..31 genome_i (0-based), 32..39 code, 40..47 Phred,
@@ -394,6 +401,39 @@ int64_t dyn_bam_n_units(const dyn_bam_result_t *result);
 int64_t dyn_bam_n_records_seen(const dyn_bam_result_t *result);
 int64_t dyn_bam_n_refs(const dyn_bam_result_t *result);
 const void *dyn_bam_field(const dyn_bam_result_t *result, int field, int64_t *n_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Streaming, range-split ingest (replaces bam.split_bam + one pysam reader per split, bam.py:609-645, 708-726):
+ * reader `part` of `n_parts` takes a contiguous range of the file's BGZF blocks (cut by compressed bytes; it owns
+ * the records that START there) and returns it chunk by chunk; a producer thread inflates and packs the next chunks
+ * while the caller streams the current one to the GPU.  A chunk is a dyn_bam_result_t (dyn_bam_field; free it with
+ * dyn_bam_result_free -- its page-locked blob returns to the stream's pool).
+ *   lean   single-end units are packed in the DYN_REC_LEAN layout
+ *   keys   instead of the string pools (fields 20-27) a chunk carries numeric keys:
+ *            11 barcode u64  2-bit packed A/C/G/T under a sentinel bit, a "-<n>" suffix as n + 1 in bits 58..63;
+ *                            ~0 = not representable (other letters / longer than 28 nt), 0 = no barcode tag
+ *            12 umi u64      likewise (up to 31 nt, no suffix)
+ *            13 gene i32     index of the gene tag's value in gene_ids, -1 = no tag, -2 = not in gene_ids
+ * Paired BAMs keep the first-seen-mate table across chunks but must be read with n_parts == 1.
+ * dyn_bam_stream_next: *chunk == NULL with DYN_OK at the end of the range.
+ * dyn_bam_stream_field: 9 ref_len | 10 header text | 28/29 reference names (as dyn_bam_field).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dyn_bam_stream dyn_bam_stream_t;
+typedef struct {
+    const char *barcode_tag, *umi_tag, *gene_tag;   /* NULL / "" = none */
+    int32_t require_gene;                           /* the reference's `not velocity` */
+    int32_t n_threads;
+    int32_t part, n_parts;
+    int64_t chunk_bytes;                            /* inflated bytes per chunk; 0 = 256 MiB */
+    int32_t lean, keys;
+    const char *const *gene_ids;                    /* [n_gene_ids], used with keys */
+    int64_t n_gene_ids;
+} dyn_bam_stream_opts_t;
+int dyn_bam_stream_open(const char *path, const dyn_bam_stream_opts_t *opts, dyn_bam_stream_t **out_stream);
+int dyn_bam_stream_next(dyn_bam_stream_t *stream, dyn_bam_result_t **chunk);
+void dyn_bam_stream_close(dyn_bam_stream_t *stream);
+int64_t dyn_bam_stream_n_refs(const dyn_bam_stream_t *stream);
+const void *dyn_bam_stream_field(const dyn_bam_stream_t *stream, int field, int64_t *n_bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Synthetic input generator (bench / test utility; not on the timed path). Generates packed records

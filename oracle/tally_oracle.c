@@ -23,6 +23,7 @@ typedef struct {
 
 #define HAS_MATE 0x8000u
 #define BAD_MD 0x4000u
+#define LEAN 0x2000u   /* no qual[] stream: the Phred of a mismatching base rides in bits 21..28 of its MD token */
 #define ST_OVERFLOW 0x1u
 #define ST_BAD 0x2u
 #define ST_NON_ACGT 0x4u
@@ -52,7 +53,8 @@ typedef struct {
 } resolved_t;
 
 static size_t record_bytes(const hdr_t *h) {
-    size_t b = 16 + 4 * (size_t)h->n_cigar + 4 * (size_t)h->n_tok + ((((size_t)h->l_seq + 1) / 2 + 3) & ~(size_t)3) + h->l_seq;
+    size_t b = 16 + 4 * (size_t)h->n_cigar + 4 * (size_t)h->n_tok + ((((size_t)h->l_seq + 1) / 2 + 3) & ~(size_t)3) +
+               ((h->flag & LEAN) ? 0 : h->l_seq);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -85,12 +87,15 @@ static void resolve(const uint8_t *rec, resolved_t *r) {
                 if (qp >= h->l_seq) { r->bad = 1; break; }
                 int rn = (seq[qp >> 1] >> ((qp & 1) ? 0 : 4)) & 0xf;
                 int gn = rn;
+                /* lean records carry qualities at MD letters only -- the only ones a single-end read needs */
+                int q = (h->flag & LEAN) ? 0 : qual[qp];
                 if (ti < h->n_tok && !((tok[ti] >> 20) & 1) && (int)(tok[ti] & 0xffff) == aligned) {
                     gn = (int)((tok[ti] >> 16) & 0xf);
+                    if (h->flag & LEAN) q = (int)((tok[ti] >> 21) & 0xff);
                     ti++;
                 }
                 int i = r->n_pairs++;
-                r->qpos[i] = qp; r->rpos[i] = rp; r->refn[i] = (uint8_t)gn; r->readn[i] = (uint8_t)rn; r->q[i] = qual[qp];
+                r->qpos[i] = qp; r->rpos[i] = rp; r->refn[i] = (uint8_t)gn; r->readn[i] = (uint8_t)rn; r->q[i] = (uint8_t)q;
                 qp++; rp++; aligned++;
             }
         } else if (op == 2) {
@@ -143,6 +148,7 @@ int dyn_oracle_tally(const uint8_t *records, const uint32_t *rec_off, int64_t r_
         resolved_t rd, mt;
         resolve(rec, &rd);
         int has_mate = (rd.h.flag & HAS_MATE) != 0;
+        if (has_mate && (rd.h.flag & LEAN)) { rd.bad = 1; has_mate = 0; }   /* pairs need every quality */
         long content[4] = {0, 0, 0, 0};
         call_t *calls = NULL;
         int n_calls = 0;
