@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument('--skip-consensus', action='store_true')
     ap.add_argument('--consensus-reads', type=int, default=20_000_000, help='C3-like reads per GPU for the consensus stage')
     ap.add_argument('--no-emit', action='store_true', help='diagnostic: counters only, no mismatch records')
+    ap.add_argument('--full-records', action='store_true',
+                    help='records with their whole Phred stream (round-1 layout) instead of the lean single-end layout')
     return ap.parse_args()
 
 
@@ -238,14 +240,17 @@ def main():
     config = {
         'workload': 'C2 synthetic scSLAM-seq-like 10x BAM records: 50M reads x 91 nt, 10k barcodes, TC, per GPU',
         'reads_per_gpu': n_reads, 'barcodes_per_gpu': args.barcodes, 'read_len': 91, 'quality': 27,
-        'l2_policy': 'inputs (~8.8 GB packed records per step) are far larger than the 126 MB L2',
+        'record_layout': 'full (Phred stream kept)' if args.full_records else
+                         'lean (single-end: Phred only at mismatches, inside the MD tokens; include/dynast_b200.h DYN_REC_LEAN)',
+        'l2_policy': 'inputs (~%.1f GB packed records per step) are far larger than the 126 MB L2' % (8.8 if args.full_records else 4.2),
         'parallelism': f'read-range x{world}', 'cpus_bound_near_gpu': numa,
     }
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if args.impl == 'reference':
         sample = min(n_reads, args.cpu_sample_reads)
-        batch = pipeline.SynthBatch(sample, seed=2001, n_barcodes=args.barcodes, device=local_rank, with_keys=False)
+        batch = pipeline.SynthBatch(sample, seed=2001, n_barcodes=args.barcodes, device=local_rank, with_keys=False,
+                                    lean=not args.full_records)
         blob = batch.records.cpu().numpy()
         rec_off = batch.rec_off.cpu().numpy().view(np.uint32)
         del batch
@@ -271,7 +276,7 @@ def main():
 
     # ---------------------------------------------------------------- workload (setup, untimed)
     batch = pipeline.SynthBatch(n_reads, seed=2001 + rank, n_barcodes=args.barcodes, device=local_rank,
-                                barcode_base=rank * args.barcodes)
+                                barcode_base=rank * args.barcodes, lean=not args.full_records)
     conv_cap = int(n_reads * 1.5) + 1024
     out = pipeline.TallyBuffers(n_reads, conv_cap, device=local_rank)
     alg_in = batch.algorithmic_input_bytes()
@@ -319,7 +324,7 @@ def main():
     peak, peak_src = peaks()
     achieved = alg_bytes / (np.mean(kernel_ms) * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, 'profiles', 'r1_tally_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'r1_tally_traffic.json' if args.full_records else 'r2_tally_traffic.json')
     if os.path.exists(tp):      # DRAM bytes per read from the committed ncu --set full capture, scaled to this launch
         with open(tp) as f:
             tj = json.load(f)

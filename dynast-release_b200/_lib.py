@@ -125,7 +125,7 @@ class SynthParams(C.Structure):
         ('seed', C.c_uint64), ('read_len', C.c_int32), ('n_barcodes', C.c_int32), ('n_genes', C.c_int32),
         ('umi_len', C.c_int32), ('n_groups', C.c_int64), ('pos_span', C.c_int64), ('p_c', C.c_double),
         ('p_e', C.c_double), ('frac_n', C.c_double), ('d_bc_cdf', C.c_void_p), ('d_gene_cdf', C.c_void_p),
-        ('d_gene_pi', C.c_void_p), ('d_gene_strand', C.c_void_p), ('d_gene_contig', C.c_void_p),
+        ('d_gene_pi', C.c_void_p), ('d_gene_strand', C.c_void_p), ('d_gene_contig', C.c_void_p), ('lean', C.c_int32),
     ]
 
 

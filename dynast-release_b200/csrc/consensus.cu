@@ -98,7 +98,7 @@ __device__ __forceinline__ void expand_item(const uint8_t *records, const uint32
         if (op == 0 || op == 7 || op == 8) m_total += len;
         else if (op == 2) d_total += len;
     }
-    bool bad = ((h.w >> 16) & DYN_REC_BAD_MD) != 0 || (unsigned long long)(m_total + d_total) != end - o0;
+    bool bad = ((h.w >> 16) & (DYN_REC_BAD_MD | DYN_REC_LEAN)) != 0 || (unsigned long long)(m_total + d_total) != end - o0;
     if (bad) {
         for (unsigned long long o = o0 + lane; o < end; o += 32) { key[o] = kInvalid; val[o] = 0; }
         if (lane == 0) status[g] = 2;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(32 * kDirectWarps) direct_kernel(const uint8_t
             const uint32_t *tok = cig + n_cigar;
             const uint8_t *seq = reinterpret_cast<const uint8_t *>(tok + n_tok);
             const uint8_t *qual = seq + pad4(((size_t)l_seq + 1) >> 1);
-            if ((h.w >> 16) & DYN_REC_BAD_MD) { bad = true; continue; }
+            if ((h.w >> 16) & (DYN_REC_BAD_MD | DYN_REC_LEAN)) { bad = true; continue; }
             uint32_t m_total = 0, d_total = 0;
             for (uint32_t c = 0; c < n_cigar; ++c) {
                 const uint32_t op = cig[c] & 0xf, len = cig[c] >> 4;

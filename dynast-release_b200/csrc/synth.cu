@@ -25,6 +25,7 @@ struct SynthParams {
     const uint8_t *gene_strand;   // [n_genes] 0 '+', 1 '-'
     const int32_t *gene_contig;   // [n_genes]
     long long pos_span;
+    int lean;                 // DYN_REC_LEAN layout
 };
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -119,7 +120,8 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
                 const uint8_t nib = is_n ? 15 : code[b];
                 seq[qp >> 1] |= nib << ((qp & 1) ? 0 : 4);
                 if (is_n || b != gb) {
-                    if (n_tok < kMaxTok) tok[n_tok++] = (uint32_t)aligned | ((uint32_t)code[gb] << 16);
+                    if (n_tok < kMaxTok)
+                        tok[n_tok++] = (uint32_t)aligned | ((uint32_t)code[gb] << 16) | (P.lean ? (uint32_t)qual[qp] << 21 : 0u);
                     ++nm;
                 }
                 ++aligned;
@@ -138,7 +140,7 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
         }
     }
     const int seq_bytes = (((L + 1) >> 1) + 3) & ~3;
-    const size_t raw = 16 + 4 * (size_t)n_cig + 4 * (size_t)n_tok + seq_bytes + L;
+    const size_t raw = 16 + 4 * (size_t)n_cig + 4 * (size_t)n_tok + seq_bytes + (P.lean ? 0 : L);
     const size_t bytes = (raw + 15) & ~(size_t)15;
     if (keys) {
         keys->barcode = (uint32_t)bc; keys->gene = (uint32_t)gene; keys->umi = umi;
@@ -152,7 +154,7 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
         else h.pos = (int32_t)(mix64(grp ^ 0x5bd1e995ull) % (unsigned long long)(-P.pos_span)) + (int32_t)(g.next() % 300);
         h.ref_id = P.gene_contig[gene];
         h.l_seq = (uint16_t)L; h.n_cigar = (uint16_t)n_cig; h.n_tok = (uint16_t)n_tok;
-        h.flag = (g.next() & 1) ? 16 : 0;
+        h.flag = (uint16_t)(((g.next() & 1) ? 16 : 0) | (P.lean ? DYN_REC_LEAN : 0));
         *reinterpret_cast<uint4 *>(out) = *reinterpret_cast<uint4 *>(&h);
         uint8_t *p = out + 16;
         for (int i = 0; i < n_cig; ++i) reinterpret_cast<uint32_t *>(p)[i] = cig[i];
@@ -161,8 +163,10 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
         p += 4 * n_tok;
         for (int i = 0; i < seq_bytes; ++i) p[i] = seq[i];
         p += seq_bytes;
-        for (int i = 0; i < L; ++i) p[i] = qual[i];
-        p += L;
+        if (!P.lean) {
+            for (int i = 0; i < L; ++i) p[i] = qual[i];
+            p += L;
+        }
         for (size_t i = raw; i < bytes; ++i) *p++ = 0;
     }
     return bytes;
@@ -200,6 +204,7 @@ static int make_params(const dyn_synth_params_t *sp, SynthParams *P) {
     P->bc_cdf = sp->d_bc_cdf; P->gene_cdf = sp->d_gene_cdf; P->gene_pi = sp->d_gene_pi;
     P->gene_strand = sp->d_gene_strand; P->gene_contig = sp->d_gene_contig;
     P->pos_span = sp->pos_span != 0 ? sp->pos_span : (1ll << 27);
+    P->lean = sp->lean != 0;
     return DYN_OK;
 }
 

@@ -232,6 +232,7 @@ __device__ __noinline__ void slow_unit(const uint8_t *rec, size_t unit_bytes, co
     const size_t rd_bytes = rd.init(rec, unit_bytes);
     if (rd.bad) { o.status |= DYN_ST_BAD_RECORD; return; }
     const bool has_mate = (reinterpret_cast<const uint16_t *>(rec)[7] & DYN_REC_HAS_MATE) != 0;
+    if (has_mate && rd.lean) { o.status |= DYN_ST_BAD_RECORD; return; }      // the mate rule needs every quality
     const uint8_t *mrec = rec + rd_bytes;
     const size_t mate_avail = unit_bytes - rd_bytes;
     const int rd_pos = rd.rpos;
@@ -378,8 +379,8 @@ __device__ __forceinline__ unsigned long long resolve_event(const TileSmem &sm, 
         if (ri >= 0) atomicSub(acc + ri * kThreads, 1);
     }
     if (gn == 15 || rn == 15 || gn == rn) return 0ull;   // bam.py:389-390, 405
-    const uint8_t *qual = seqb + pad4(((size_t)l_seq + 1) >> 1);
-    const uint32_t q = qual[qpos];
+    // lean records carry the Phred of a mismatching base in its MD token (copied into bits 32..39 of the event)
+    const uint32_t q = ((h.w >> 16) & DYN_REC_LEAN) ? (uint32_t)(pl >> 32) & 0xffu : seqb[pad4(((size_t)l_seq + 1) >> 1) + qpos];
     const unsigned long long out =
         (unsigned long long)(uint32_t)rpos | ((unsigned long long)((gn << 4) | rn) << 32) | ((unsigned long long)q << 40);
     if ((int)q <= p.quality) return out;                                // conversion.py:424 (strict)
@@ -504,7 +505,8 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                     else {
                         l_seq = h.z & 0xffff; n_cigar = h.z >> 16; n_tok = h.w & 0xffff;
                         // truncated / corrupt record, or an MD tag that disagrees with the CIGAR
-                        if (record_need(l_seq, n_cigar, n_tok) > unit_bytes || ((h.w >> 16) & DYN_REC_BAD_MD)) {
+                        if (record_need(l_seq, n_cigar, n_tok, ((h.w >> 16) & DYN_REC_LEAN) != 0) > unit_bytes ||
+                            ((h.w >> 16) & DYN_REC_BAD_MD)) {
                             good = false; l_seq = n_cigar = n_tok = 0;
                         }
                     }
@@ -602,7 +604,9 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                             const int aoff = (int)DYN_TOK_AOFF(tk);
                             if (aoff <= last || aoff >= m_total) good = false;   // tokens must ascend inside the aligned span
                             last = aoff;
-                            if (k < n_mm) wlist[first + k] = (unsigned long long)((uint32_t)aoff | (code << 16) | ((uint32_t)lane << 24));
+                            if (k < n_mm)
+                                wlist[first + k] = (unsigned long long)((uint32_t)aoff | (code << 16) | ((uint32_t)lane << 24)) |
+                                                   ((unsigned long long)DYN_TOK_QUAL(tk) << 32);
                             ++k;
                         }
                     }
@@ -750,6 +754,7 @@ __device__ __forceinline__ bool slow_unit_onepass(const uint8_t *rec, size_t uni
     const size_t rd_bytes = rd.init(rec, unit_bytes);
     if (rd.bad) { o.status |= DYN_ST_BAD_RECORD; return true; }
     const bool has_mate = (reinterpret_cast<const uint16_t *>(rec)[7] & DYN_REC_HAS_MATE) != 0;
+    if (has_mate && rd.lean) { o.status |= DYN_ST_BAD_RECORD; return true; }      // the mate rule needs every quality
     const int rd_pos = rd.rpos;
     bool bad = false, overflow = false;
     // A/C/G/T counters as four 16-bit fields of one register (l_seq <= 65535 per record; two records per unit are

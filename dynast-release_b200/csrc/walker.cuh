@@ -27,8 +27,9 @@ __device__ __forceinline__ int base_idx(uint32_t code) { return __popc(code) == 
 
 __device__ __forceinline__ size_t pad4(size_t x) { return (x + 3) & ~(size_t)3; }
 
-__device__ __forceinline__ size_t record_need(uint32_t l_seq, uint32_t n_cigar, uint32_t n_tok) {
-    return 16 + 4 * (size_t)n_cigar + 4 * (size_t)n_tok + pad4(((size_t)l_seq + 1) >> 1) + l_seq;
+// bytes of a record before padding; a lean record (DYN_REC_LEAN) has no qual[] stream
+__device__ __forceinline__ size_t record_need(uint32_t l_seq, uint32_t n_cigar, uint32_t n_tok, bool lean = false) {
+    return 16 + 4 * (size_t)n_cigar + 4 * (size_t)n_tok + pad4(((size_t)l_seq + 1) >> 1) + (lean ? 0 : l_seq);
 }
 
 struct Walker {
@@ -38,7 +39,7 @@ struct Walker {
     int ci, op_left, qpos, rpos, ti, aligned;
     int del[4];
     int del_left;      // deleted reference bases still to be reported (next_event only)
-    bool bad;
+    bool bad, lean;
     // the sequence / quality word and the MD token under the cursor are kept in registers: one load per 8 bases, per 4
     // qualities and per token instead of three loads per base
     uint32_t seq_w, qual_w, tok_w;
@@ -49,7 +50,7 @@ struct Walker {
 
     // returns padded record size, 0 if the record does not fit `avail`
     __device__ __forceinline__ size_t init(const uint8_t *rec, size_t avail) {
-        bad = false;
+        bad = lean = false;
         ci = op_left = qpos = ti = aligned = 0;
         del_left = 0;
         del[0] = del[1] = del[2] = del[3] = 0;
@@ -60,7 +61,8 @@ struct Walker {
         if (avail < 16) { bad = true; return 0; }
         const uint4 h = *reinterpret_cast<const uint4 *>(rec);
         const uint32_t ls = h.z & 0xffff, nc = h.z >> 16, nt = h.w & 0xffff;
-        const size_t need = record_need(ls, nc, nt);
+        lean = ((h.w >> 16) & DYN_REC_LEAN) != 0;
+        const size_t need = record_need(ls, nc, nt, lean);
         if (need > avail) { bad = true; return 0; }
         if ((h.w >> 16) & DYN_REC_BAD_MD) bad = true;     // MD disagrees with the CIGAR (pysam raises)
         rpos = (int)h.x; ref_id = (int)h.y;
@@ -102,12 +104,17 @@ struct Walker {
             if ((qpos >> 3) != seq_wi) { seq_wi = qpos >> 3; seq_w = reinterpret_cast<const uint32_t *>(seq)[seq_wi]; }
             rn = (seq_w >> ((((qpos >> 1) & 3) << 3) + ((~qpos & 1) << 2))) & 0xf;
             gn = rn;
+            uint32_t tq = 0;         // lean records: the Phred rides in the MD token (mismatching bases only)
             if (ti < n_tok) {
                 if (tok_i != ti) { tok_i = ti; tok_w = tok[ti]; }
-                if (!DYN_TOK_IS_DEL(tok_w) && (int)DYN_TOK_AOFF(tok_w) == aligned) { gn = DYN_TOK_BASE(tok_w); ++ti; }
+                if (!DYN_TOK_IS_DEL(tok_w) && (int)DYN_TOK_AOFF(tok_w) == aligned) { gn = DYN_TOK_BASE(tok_w); tq = DYN_TOK_QUAL(tok_w); ++ti; }
             }
-            if ((qpos >> 2) != qual_wi) { qual_wi = qpos >> 2; qual_w = reinterpret_cast<const uint32_t *>(qual)[qual_wi]; }
-            cq = qpos; cr = rpos; q = (qual_w >> ((qpos & 3) << 3)) & 0xffu;
+            if (lean) q = tq;
+            else {
+                if ((qpos >> 2) != qual_wi) { qual_wi = qpos >> 2; qual_w = reinterpret_cast<const uint32_t *>(qual)[qual_wi]; }
+                q = (qual_w >> ((qpos & 3) << 3)) & 0xffu;
+            }
+            cq = qpos; cr = rpos;
             ++qpos; ++rpos; ++aligned; --op_left;
             return true;
         }

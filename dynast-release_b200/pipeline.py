@@ -23,7 +23,7 @@ class SynthBatch:
     def __init__(self, n_reads: int, seed: int = 2001, read_len: int = 91, n_barcodes: int = 10000,
                  n_genes: int = 20000, n_contigs: int = 25, p_c: float = 0.05, p_e: float = 5e-4,
                  frac_n: float = 0.001, umi_len: int = 12, reads_per_umi: float = 2.0, device: int = 0,
-                 barcode_base: int = 0, with_keys: bool = True, clustered: bool = False):
+                 barcode_base: int = 0, with_keys: bool = True, clustered: bool = False, lean: bool = False):
         self.ctx = Context.get(device)
         dev = torch.device('cuda', device)
         rng = np.random.default_rng(seed)
@@ -43,6 +43,8 @@ class SynthBatch:
         sp.n_groups = max(1, int(n_reads / reads_per_umi))
         sp.pos_span = -(1 << 27) if clustered else 1 << 27
         sp.p_c, sp.p_e, sp.frac_n = p_c, p_e, frac_n
+        sp.lean = int(lean)
+        self.lean = bool(lean)
         sp.d_bc_cdf = self.tables['bc_cdf'].data_ptr()
         sp.d_gene_cdf = self.tables['gene_cdf'].data_ptr()
         sp.d_gene_pi = self.tables['gene_pi'].data_ptr()
@@ -77,7 +79,8 @@ class SynthBatch:
             torch.cuda.current_stream().synchronize()
 
     def algorithmic_input_bytes(self) -> int:
-        """Unpadded record bytes (16 + 4 n_cigar + 4 n_tok + ceil(l/2) + l per read) + 4-byte offsets."""
+        """Unpadded record bytes (16 + 4 n_cigar + 4 n_tok + ceil(l/2) [+ l: Phred, absent from lean records] per
+        read) + 4-byte offsets."""
         off = (self.rec_off[:-1].to(torch.int64) & 0xffffffff) * 16
         total = 0
         step = 1 << 24
@@ -86,7 +89,7 @@ class SynthBatch:
             lo = self.records[o + 8].to(torch.int64) | (self.records[o + 9].to(torch.int64) << 8)
             nc = self.records[o + 10].to(torch.int64) | (self.records[o + 11].to(torch.int64) << 8)
             ml = self.records[o + 12].to(torch.int64) | (self.records[o + 13].to(torch.int64) << 8)
-            total += int((16 + 4 * nc + (lo + 1) // 2 + lo + 4 * ml).sum().item())
+            total += int((16 + 4 * nc + (lo + 1) // 2 + (0 if self.lean else lo) + 4 * ml).sum().item())
         return total + 4 * (self.n_reads + 1)
 
 

@@ -60,6 +60,7 @@ def make_reads(
     umi_len: int = 12,
     reads_per_umi: float = 2.0,
     complex_cigars: bool = False,
+    lean: bool = False,
 ):
     """Returns dict(blob, rec_off, barcode_id, umi, gene_id, score, strand_gene, truth...) with one
     single-end read per counting unit.  CIGAR mix: 70 % LM, 18 % aMbNcM, 8 % sS(L-s)M, 2 % one 1-3 nt D,
@@ -153,7 +154,7 @@ def make_reads(
         md.append(str(run))
         flag = 16 if rng.random() < 0.5 else 0
         score[i] = L - 2 * nm
-        units.append([records.pack_one(int(pos[i]), int(gene_contig[gene_id[i]]), flag, cigar, ''.join(seq), qual, ''.join(md))])
+        units.append([records.pack_one(int(pos[i]), int(gene_contig[gene_id[i]]), flag, cigar, ''.join(seq), qual, ''.join(md), lean=lean)])
         raw.append((int(pos[i]), cigar, ''.join(seq), [int(x) for x in qual], ''.join(md)))
     blob, rec_off = records.pack_units(units)
     return dict(

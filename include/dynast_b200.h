@@ -455,6 +455,7 @@ typedef struct {
     const float *d_gene_pi;       /* [n_genes] labelled fraction */
     const uint8_t *d_gene_strand; /* [n_genes] 0 '+', 1 '-' */
     const int32_t *d_gene_contig; /* [n_genes] */
+    int32_t lean;                 /* != 0: records in the DYN_REC_LEAN layout (same reads, same qualities at mismatches) */
 } dyn_synth_params_t;
 
 /* d_rec_off[0..n_reads] (16-byte units); the blob needs 16 * d_rec_off[n_reads] bytes. */

@@ -186,3 +186,53 @@ def test_conversion_capacity(gpu_ctx, oracle_lib, paired):
         elif len(want):
             dropped += 1
     assert kept > 0 and dropped > 0
+
+
+@pytest.mark.parametrize('kw', [
+    dict(n_reads=20000, seed=51),
+    dict(n_reads=3000, seed=52, read_len=150, p_e=0.01, frac_n=0.01, complex_cigars=True),
+    dict(n_reads=600, seed=53, p_e=0.04),                      # event overflow -> sequential kernel on lean records
+    dict(n_reads=300, seed=54, read_len=300, p_e=0.002),
+])
+def test_lean_records_give_the_results_of_full_records(gpu_ctx, oracle_lib, kw):
+    """DYN_REC_LEAN (no Phred stream, the mismatching bases' qualities inside the MD tokens): the kernel and the
+    oracle on lean records both equal the oracle on the full records -- counters, mismatch records, status."""
+    from oracle import pack
+    from dynast_b200 import device, synth
+    full = synth.make_reads(**kw)
+    lean = synth.make_reads(lean=True, **kw)
+    assert lean['blob'].size < 0.7 * full['blob'].size
+    for quality in (27, 0):
+        want = pack.run_tally(full['blob'], full['rec_off'], quality=quality)
+        _compare(pack.run_tally(lean['blob'], lean['rec_off'], quality=quality), want)
+        _compare(device.tally_reads_host(lean['blob'], lean['rec_off'], quality=quality), want)
+
+
+def test_lean_device_generator_matches_full(gpu_ctx, oracle_lib):
+    """csrc/synth.cu with lean = 1 writes the same reads in the lean layout: same tally, about half the bytes."""
+    import torch
+    from oracle import pack
+    from dynast_b200 import pipeline
+    ctx = pipeline.Context.get(0)
+    res = {}
+    for lean in (False, True):
+        b = pipeline.SynthBatch(50_000, seed=61, n_barcodes=50, n_genes=300, device=0, lean=lean)
+        out = pipeline.TallyBuffers(b.n_reads, b.n_reads * 2 + 1024, device=0)
+        pipeline.tally_reads(ctx, b.records, b.rec_off, out, quality=27)
+        torch.cuda.synchronize()
+        res[lean] = (out.counts.cpu().numpy(), int(out.scalars[0].item()), b.n_bytes,
+                     pack.run_tally(b.records.cpu().numpy(), b.rec_off.cpu().numpy().view(np.uint32), quality=27))
+        assert int(out.scalars[1].item()) == 0
+    assert (res[False][0] == res[True][0]).all() and res[False][1] == res[True][1]
+    assert (res[True][0] == res[True][3]['counts']).all() and (res[False][0] == res[False][3]['counts']).all()
+    assert res[True][2] < 0.55 * res[False][2]
+
+
+def test_lean_pair_is_rejected(gpu_ctx):
+    """A unit with a mate cannot be lean (the mate rule compares qualities the lean layout does not carry)."""
+    from dynast_b200 import device, records as rec
+    a = rec.pack_one(100, 0, 0x1 | 0x40, [(0, 20)], 'A' * 20, [30] * 20, '20', lean=True)
+    b = rec.pack_one(110, 0, 0x1 | 0x80, [(0, 20)], 'A' * 20, [30] * 20, '20')
+    blob, off = rec.pack_units([[a, b]])
+    out = device.tally_reads_host(blob, off)
+    assert out['status'] & 0x2
