@@ -59,6 +59,8 @@ PROTOTYPES = {
     'dyn_bam_stream_close': (None, [_vp]),
     'dyn_bam_stream_n_refs': (_i64, [_vp]),
     'dyn_bam_stream_field': (_vp, [_vp, _i32, C.POINTER(_i64)]),
+    'dyn_bam_write': (_i32, [C.c_char_p, C.c_char_p, _i32, C.POINTER(C.c_char_p), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _i32, _i32, _i32]),
     'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
     'dyn_synth_fill': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

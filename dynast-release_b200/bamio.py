@@ -161,3 +161,39 @@ class BamStream:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def write_bam(path: str, refs, blob: np.ndarray, rec_off: np.ndarray, order=None, names=None, aux=None, mapq=None, flag=None,
+              header_text: Optional[str] = None, level: int = 6, n_threads: int = 8, index: bool = True):
+    """dyn_bam_write: packed records (full layout, no mates) -> a BAM file (+ .bai).  refs: [(name, length)];
+    names: list of str or None ("r<i>"); aux: list of bytes (pre-encoded tags) or a (bytes, uint32 offsets) pair;
+    order: unit order in the file (coordinate order for a sorted BAM)."""
+    lib = _lib.load()
+    n = len(rec_off) - 1
+    if header_text is None:
+        header_text = '@HD\tVN:1.4\tSO:coordinate\n' + ''.join(f'@SQ\tSN:{r}\tLN:{l}\n' for r, l in refs)
+    ref_names = (C.c_char_p * max(len(refs), 1))(*[str(r).encode() for r, _ in refs])
+    ref_lens = np.asarray([l for _, l in refs], dtype=np.int32)
+
+    def pool(items):
+        if items is None:
+            return None, None
+        if isinstance(items, tuple):
+            return np.frombuffer(items[0], dtype=np.uint8), np.ascontiguousarray(items[1], dtype=np.uint32)
+        enc = [x.encode() if isinstance(x, str) else bytes(x) for x in items]
+        off = np.zeros(len(enc) + 1, dtype=np.uint32)
+        np.cumsum([len(x) for x in enc], out=off[1:])
+        return np.frombuffer(b''.join(enc) or b'\0', dtype=np.uint8), off
+
+    n_data, n_off = pool(names)
+    a_data, a_off = pool(aux)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.uint32)
+    order = None if order is None else np.ascontiguousarray(order, dtype=np.int64)
+    mapq = None if mapq is None else np.ascontiguousarray(mapq, dtype=np.uint8)
+    flag = None if flag is None else np.ascontiguousarray(flag, dtype=np.uint16)
+    p = _lib.ptr
+    _lib.check(lib.dyn_bam_write(path.encode(), header_text.encode(), len(refs), C.cast(ref_names, C.POINTER(C.c_char_p)),
+                                 p(ref_lens), p(blob), p(rec_off), n, p(order), p(n_data), p(n_off), p(a_data), p(a_off), p(mapq),
+                                 p(flag), int(level), int(n_threads), int(bool(index))))
+    return path

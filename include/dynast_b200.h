@@ -436,6 +436,22 @@ int64_t dyn_bam_stream_n_refs(const dyn_bam_stream_t *stream);
 const void *dyn_bam_stream_field(const dyn_bam_stream_t *stream, int field, int64_t *n_bytes);
 
 /* ------------------------------------------------------------------------------------------------
+ * BAM writer (what call_consensus gets from pysam + samtools sort / index, consensus.py:360-366, 476-494; also builds
+ * the synthetic BAMs of the ingest benchmarks).  Unit u -- one packed record in the FULL layout, no mate -- becomes one
+ * alignment record: name = h_names[h_name_off[u] .. h_name_off[u + 1]) ("r<u>" when h_names is NULL), MAPQ h_mapq[u]
+ * (255 when NULL), flag h_flag[u] (the record's own low 12 bits when NULL), the caller's pre-encoded aux bytes
+ * h_aux[h_aux_off[u] .. h_aux_off[u + 1]) followed by the MD tag rebuilt from the record's MD tokens.  Units are written
+ * in h_order (NULL: as they come) -- pass the coordinate order for a sorted file.  BGZF blocks end on record boundaries;
+ * level = zlib level; write_index != 0 also writes <path>.bai (binning + linear index, SAM specification section 5).
+ * Host call, all pointers are host pointers.
+ * ------------------------------------------------------------------------------------------------ */
+int dyn_bam_write(const char *path, const char *header_text, int32_t n_ref, const char *const *ref_names,
+                  const int32_t *ref_lens, const void *h_records, const uint32_t *h_rec_off, int64_t n_units,
+                  const int64_t *h_order, const char *h_names, const uint32_t *h_name_off, const uint8_t *h_aux,
+                  const uint32_t *h_aux_off, const uint8_t *h_mapq, const uint16_t *h_flag, int level, int n_threads,
+                  int write_index);
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic input generator (bench / test utility; not on the timed path). Generates packed records
  * for the BASELINE configs directly in HBM; every decision is a pure function of (seed, read index).
  * Model: SURVEY.md section 8d (C2) after dynast/benchmarking/simulation.py:22-79.
