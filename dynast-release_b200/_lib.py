@@ -59,6 +59,12 @@ PROTOTYPES = {
     'dyn_bam_stream_close': (None, [_vp]),
     'dyn_bam_stream_n_refs': (_i64, [_vp]),
     'dyn_bam_stream_field': (_vp, [_vp, _i32, C.POINTER(_i64)]),
+    'dyn_bam_dev_open': (_i32, [_vp, C.c_char_p, _vp, C.POINTER(_vp)]),
+    'dyn_bam_dev_next': (_i32, [_vp, _vp, _vp]),
+    'dyn_bam_dev_close': (None, [_vp]),
+    'dyn_bam_dev_n_refs': (_i64, [_vp]),
+    'dyn_bam_dev_field': (_vp, [_vp, _i32, C.POINTER(_i64)]),
+    'dyn_inflate_blocks': (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     'dyn_bam_write': (_i32, [C.c_char_p, C.c_char_p, _i32, C.POINTER(C.c_char_p), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _i32, _i32, _i32]),
     'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
@@ -136,6 +142,14 @@ class BamStreamOpts(C.Structure):
     _fields_ = [('barcode_tag', C.c_char_p), ('umi_tag', C.c_char_p), ('gene_tag', C.c_char_p), ('require_gene', C.c_int32),
                 ('n_threads', C.c_int32), ('part', C.c_int32), ('n_parts', C.c_int32), ('chunk_bytes', C.c_int64),
                 ('lean', C.c_int32), ('keys', C.c_int32), ('gene_ids', C.POINTER(C.c_char_p)), ('n_gene_ids', C.c_int64)]
+
+
+class BamDevChunk(C.Structure):
+    """dyn_bam_dev_chunk_t"""
+    _fields_ = [('n_units', C.c_int64), ('n_records_seen', C.c_int64), ('records_bytes', C.c_int64), ('compressed_bytes', C.c_int64),
+                ('inflated_bytes', C.c_int64), ('end', C.c_int32), ('reserved', C.c_int32)] + [(name, C.c_void_p) for name in (
+                    'd_records', 'd_rec_off', 'd_barcode_key', 'd_umi_key', 'd_gene_idx', 'd_score', 'd_ref_id', 'd_pos', 'd_hi',
+                    'd_flag', 'd_gx_assigned')]
 
 
 class Annotation(C.Structure):

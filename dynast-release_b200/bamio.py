@@ -197,3 +197,89 @@ def write_bam(path: str, refs, blob: np.ndarray, rec_off: np.ndarray, order=None
                                  p(ref_lens), p(blob), p(rec_off), n, p(order), p(n_data), p(n_off), p(a_data), p(a_off), p(mapq),
                                  p(flag), int(level), int(n_threads), int(bool(index))))
     return path
+
+
+class _DeviceArray:
+    """A library-owned device buffer seen through __cuda_array_interface__ (zero-copy torch.as_tensor)."""
+
+    def __init__(self, pointer: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (pointer, False), 'version': 2}
+
+
+class DeviceBamStream:
+    """dyn_bam_dev_*: the block range `part` of `n_parts` of a coordinate-sorted single-end BAM, inflated and packed on
+    the GPU (csrc/bamdevice.cu).  Iterating yields dicts of torch tensors that VIEW library memory -- records (uint8),
+    rec_off (int32 bit pattern of uint32, n + 1), barcode_key / umi_key (int64 bit patterns), gene_idx, score, ref_id,
+    pos, hi (int32), flag (int16 bit pattern), gx_assigned (uint8) -- valid until the second-next chunk is requested, plus
+    n_units / n_records_seen / compressed_bytes / inflated_bytes.  Raises DynastB200Error for files this path does not
+    take (paired records, records that straddle BGZF blocks): use BamStream for those."""
+
+    def __init__(self, ctx, path: str, barcode_tag: Optional[str] = None, umi_tag: Optional[str] = None,
+                 gene_tag: Optional[str] = 'GX', require_gene: bool = False, part: int = 0, n_parts: int = 1,
+                 chunk_bytes: int = 0, lean: bool = True, gene_ids: Optional[List[str]] = None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        enc = lambda s: s.encode() if s else None
+        o = _lib.BamStreamOpts(barcode_tag=enc(barcode_tag), umi_tag=enc(umi_tag), gene_tag=enc(gene_tag),
+                               require_gene=int(require_gene), n_threads=1, part=int(part), n_parts=int(n_parts),
+                               chunk_bytes=int(chunk_bytes), lean=int(lean), keys=1)
+        self._gene_ids = None
+        if gene_ids is not None:
+            self._gene_ids = (C.c_char_p * max(len(gene_ids), 1))(*[g.encode() for g in gene_ids])
+            o.gene_ids = C.cast(self._gene_ids, C.POINTER(C.c_char_p))
+            o.n_gene_ids = len(gene_ids)
+        h = C.c_void_p()
+        _lib.check(self.lib.dyn_bam_dev_open(ctx.handle, path.encode(), C.byref(o), C.byref(h)))
+        self.handle = h
+
+    def _raw(self, field: int, dtype):
+        nb = C.c_int64(0)
+        p = self.lib.dyn_bam_dev_field(self.handle, field, C.byref(nb))
+        if not p or nb.value == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nb.value,)).view(dtype).copy()
+
+    @property
+    def ref_len(self) -> np.ndarray:
+        return self._raw(9, np.int32)
+
+    @property
+    def ref_name(self) -> np.ndarray:
+        data, off = self._raw(28, np.uint8).tobytes(), self._raw(29, np.uint32)
+        return np.array([data[off[i]:off[i + 1]].decode() for i in range(len(off) - 1)], dtype=object)
+
+    def __iter__(self):
+        import torch
+        dev = torch.device('cuda', self.ctx.device)
+        while True:
+            ch = _lib.BamDevChunk()
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(self.lib.dyn_bam_dev_next(self.handle, C.byref(ch), stream))
+            if ch.end == 2:
+                return
+            n = int(ch.n_units)
+            view = lambda p, count, ts, dt: (torch.as_tensor(_DeviceArray(p, count, ts), device=dev) if count else torch.empty(0, dtype=dt, device=dev))
+            out = dict(n_units=n, n_records_seen=int(ch.n_records_seen), compressed_bytes=int(ch.compressed_bytes),
+                       inflated_bytes=int(ch.inflated_bytes))
+            if n:
+                out.update(
+                    records=view(ch.d_records, int(ch.records_bytes), '|u1', torch.uint8), rec_off=view(ch.d_rec_off, n + 1, '<i4', torch.int32),
+                    barcode_key=view(ch.d_barcode_key, n, '<i8', torch.int64), umi_key=view(ch.d_umi_key, n, '<i8', torch.int64),
+                    gene_idx=view(ch.d_gene_idx, n, '<i4', torch.int32), score=view(ch.d_score, n, '<i4', torch.int32),
+                    ref_id=view(ch.d_ref_id, n, '<i4', torch.int32), pos=view(ch.d_pos, n, '<i4', torch.int32),
+                    hi=view(ch.d_hi, n, '<i4', torch.int32), flag=view(ch.d_flag, n, '<i2', torch.int16),
+                    gx_assigned=view(ch.d_gx_assigned, n, '|u1', torch.uint8))
+            yield out
+            if ch.end:
+                return
+
+    def close(self):
+        if self.handle:
+            self.lib.dyn_bam_dev_close(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -1,0 +1,573 @@
+// Device BAM ingest: BGZF inflate and record packing ON THE GPU (the follow-up the
+// host ingest's ceiling calls for: zlib on the host cores tops out near 1.5e7 records/s per box, two orders of
+// magnitude below what the tally takes from HBM).
+//
+// Replaces, for coordinate-sorted single-end BAMs whose BGZF blocks end on record boundaries (what htslib, samtools
+// and STAR write), everything the reference gets from pysam / htslib between the file and the per-read loop of
+// dynast/preprocessing/bam.py:253-312:
+//   host    a reader thread copies the COMPRESSED bytes of the next run of BGZF blocks into page-locked staging
+//           memory and lists the blocks (BSIZE / ISIZE hops, no inflate); cudaMemcpyAsync moves them -- PCIe carries
+//           ~90 B per record instead of the ~280 B of the inflated stream;
+//   k1      inflate_kernel: ONE WARP PER BGZF BLOCK (inflate_core.cuh: lane 0 decodes Huffman symbols through
+//           shared-memory lookup tables, the warp writes literals lane-parallel and copies matches cooperatively);
+//   k2      index kernels: one thread per block walks its record chain (count, then positions after a scan);
+//   k3      parse_kernel: one thread per record -- read filter, aux-tag scan (MD / HI / AS / barcode / UMI / gene),
+//           2-bit barcode / UMI keys, FNV hash of the gene id, packed size;
+//   scan    unit index and record offset of every kept record (one cub::DeviceScan over count << 40 | size);
+//   k4      pack_kernel: one thread per kept record writes the packed record (header, CIGAR, MD tokens with the
+//           Phred folded in for the lean layout, 4-bit sequence) and the unit's keys; the gene id's hash is looked
+//           up in the sorted table of the caller's gene list.
+// The chunk that comes out is what dyn_bam_stream_next returns with keys = 1, but resident in HBM: the tally, the
+// velocity kernel and everything downstream read it where it lies.  Files this path does not take (paired records,
+// records straddling blocks) are reported with DYN_ERR_FORMAT; callers fall back to dyn_bam_stream_*.
+#include <cub/cub.cuh>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <memory>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "bamrec_core.cuh"
+#include "common.cuh"
+#include "inflate_core.cuh"
+
+namespace {
+
+constexpr int kInfWarps = 8;          // warps per CTA of the inflate kernel (one Tables set each)
+
+struct BlockDesc { uint32_t in_off, in_len, out_off, out_len; };
+
+__global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *in, uint8_t *out, const BlockDesc *blocks, int n_blocks,
+                                                                unsigned int *next_block, uint32_t *status) {
+    __shared__ inflate::Tables tables[kInfWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    inflate::Tables &t = tables[wid];
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = (int)atomicAdd(next_block, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_blocks) return;
+        const BlockDesc bd = blocks[b];
+        uint8_t *dst = out + bd.out_off;
+        inflate::State s;
+        inflate::state_init(s, in + bd.in_off, bd.in_len, bd.out_len);
+        if (bd.out_len == 0) s.phase = 3;
+        for (;;) {
+            int n = 0;
+            uint32_t bytes = 0;
+            if (lane == 0) {
+                if (s.err == inflate::OK && s.phase == 0) inflate::begin_block(s, t);
+                if (s.err == inflate::OK && s.phase == 1) n = inflate::decode_batch(s, t, &bytes);
+            }
+            __syncwarp();
+            n = __shfl_sync(0xffffffffu, n, 0);
+            const int err = __shfl_sync(0xffffffffu, s.err, 0);
+            const int phase = __shfl_sync(0xffffffffu, s.phase, 0);
+            const uint32_t out_pos = __shfl_sync(0xffffffffu, s.out_pos, 0);
+            if (n > 0) {
+                // ---- flush the queue: positions by a prefix sum over the symbol lengths
+                const uint32_t e = lane < n ? t.batch[lane] : 0u;
+                const bool is_match = lane < n && (e >> 31);
+                const uint32_t my_len = lane < n ? (is_match ? (e & 0x1ffu) : 1u) : 0u;
+                uint32_t incl = my_len;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const uint32_t my_pos = out_pos + incl - my_len;
+                if (lane < n && !is_match) dst[my_pos] = (uint8_t)e;
+                __syncwarp();
+                uint32_t mm = __ballot_sync(0xffffffffu, is_match);
+                while (mm) {
+                    const int i = __ffs((int)mm) - 1;
+                    mm &= mm - 1;
+                    const uint32_t ei = __shfl_sync(0xffffffffu, e, i), pi = __shfl_sync(0xffffffffu, my_pos, i);
+                    const uint32_t len = ei & 0x1ffu, dist = (ei >> 9) & 0xffffu;
+                    const uint8_t *src = dst + pi - dist;
+                    if (dist >= len) { for (uint32_t k = lane; k < len; k += 32) dst[pi + k] = src[k]; }
+                    else { for (uint32_t k = lane; k < len; k += 32) dst[pi + k] = src[k % dist]; }      // overlapping copy = a repeating pattern
+                    __syncwarp();
+                }
+            }
+            if (phase == 2 && err == inflate::OK) {
+                // stored block: a plain copy by the warp
+                const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)s.br.p, 0);
+                const uint32_t len = __shfl_sync(0xffffffffu, s.stored_left, 0);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)sp);
+                for (uint32_t k = lane; k < len; k += 32) dst[out_pos + k] = src[k];
+                __syncwarp();
+                if (lane == 0) { s.br.p += len; s.out_pos += len; s.stored_left = 0; s.phase = s.last ? 3 : 0; }
+            }
+            if (lane == 0) s.out_pos += bytes;
+            const int phase2 = __shfl_sync(0xffffffffu, s.phase, 0);
+            if (err != inflate::OK || phase2 == 3) break;
+        }
+        if (lane == 0) {
+            uint32_t st = (uint32_t)s.err;
+            if (st == 0 && s.out_pos != bd.out_len) st = inflate::ERR_OUTPUT;
+            if (st) atomicOr(status, 1u << st);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- record chain: one thread per block.  pass 0: count the records that start in the block and check that the
+// chain ends exactly at the block's end; pass 1: write their offsets.
+__global__ void index_kernel(const uint8_t *data, const BlockDesc *blocks, int n_blocks, uint32_t first_skip, uint32_t *n_rec,
+                             const uint32_t *rec_base, uint32_t *rec_at, uint32_t *status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const BlockDesc bd = blocks[b];
+    const uint8_t *p = data + bd.out_off;
+    uint32_t q = b == 0 ? first_skip : 0u, n = 0;
+    uint32_t *dst = rec_at ? rec_at + rec_base[b] : nullptr;
+    bool paired = false;
+    while (q + 4 <= bd.out_len) {
+        const uint32_t bs = bamrec::ld32(p + q);
+        if (bs < 32 || q + 4 + bs > bd.out_len) break;
+        paired |= (bamrec::ld16(p + q + 4 + 14) & 0x1) != 0;
+        if (dst) dst[n] = bd.out_off + q;
+        ++n;
+        q += 4 + bs;
+    }
+    if (!dst) {
+        n_rec[b] = n;
+        if (q != bd.out_len) atomicOr(status, 1u << 8);       // a record straddles BGZF blocks
+        if (paired) atomicOr(status, 1u << 9);                // paired records: mate pairing is the host path's
+    }
+}
+
+__global__ void parse_kernel(const uint8_t *data, const uint32_t *rec_at, uint32_t n_rec, bamrec::Tags tg, bamrec::Parsed *parsed,
+                             unsigned long long *scan_in, uint32_t *status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    bamrec::Parsed pr;
+    bamrec::parse_record(data, rec_at[i], tg, pr);
+    parsed[i] = pr;
+    scan_in[i] = pr.size16 ? ((1ull << 40) | pr.size16) : 0ull;
+    if (pr.error) atomicOr(status, 1u << (15 + pr.error));
+}
+
+struct UnitOut {
+    uint8_t *blob;
+    uint32_t *rec_off;
+    unsigned long long *bc_key, *umi_key;
+    int32_t *gene_idx, *score, *ref_id, *pos, *hi;
+    uint16_t *flag;
+    uint8_t *gx_assigned;
+};
+
+__global__ void pack_kernel(const uint8_t *data, const uint32_t *rec_at, uint32_t n_rec, const bamrec::Parsed *parsed,
+                            const unsigned long long *scan, int lean, const unsigned long long *gene_hash, const int32_t *gene_of_hash,
+                            int n_gene_hash, UnitOut o) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const bamrec::Parsed pr = parsed[i];
+    if (!pr.size16) return;
+    const unsigned long long sc = scan[i];
+    const uint32_t unit = (uint32_t)(sc >> 40);
+    const unsigned long long off16 = sc & ((1ull << 40) - 1);
+    bamrec::pack_record(data, rec_at[i], pr, lean, o.blob + (off16 << 4));
+    o.rec_off[unit] = (uint32_t)off16;
+    o.bc_key[unit] = pr.bc_key;
+    o.umi_key[unit] = pr.umi_key;
+    int32_t gi = -1;
+    if (pr.gx_assigned) {
+        gi = -2;
+        int lo = 0, hi = n_gene_hash;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (gene_hash[mid] < pr.gx_hash) lo = mid + 1; else hi = mid; }
+        if (lo < n_gene_hash && gene_hash[lo] == pr.gx_hash) gi = gene_of_hash[lo];
+    }
+    o.gene_idx[unit] = gi;
+    o.score[unit] = pr.score;
+    o.hi[unit] = pr.hi;
+    o.gx_assigned[unit] = pr.gx_assigned;
+    const uint8_t *rec = data + rec_at[i] + 4;
+    o.ref_id[unit] = (int32_t)bamrec::ld32(rec);
+    o.pos[unit] = (int32_t)bamrec::ld32(rec + 4);
+    o.flag[unit] = (uint16_t)bamrec::ld16(rec + 14);
+}
+
+struct DevBuf {         // grow-only device buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return DYN_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); dyn_set_error("dyn_bam_dev: device allocation of %zu bytes failed", want); return DYN_ERR_NOMEM; }
+        cap = want;
+        return DYN_OK;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+struct Staged {          // one run of BGZF blocks, compressed, in page-locked memory
+    uint8_t *bytes = nullptr;
+    size_t cap = 0, len = 0;
+    std::vector<BlockDesc> blocks;
+    size_t inflated = 0;
+    uint32_t first_skip = 0;
+    bool last = false;
+};
+
+}  // namespace
+
+struct dyn_bam_dev {
+    dyn_ctx *ctx = nullptr;
+    int fd = -1;
+    size_t file_len = 0;
+    // options
+    bamrec::Tags tags{};
+    int lean = 1;
+    size_t chunk_bytes = 256u << 20;
+    // header / file layout (host)
+    std::string header_text;
+    std::vector<char> ref_names;
+    std::vector<uint32_t> ref_name_off{0};
+    std::vector<int32_t> ref_len;
+    struct FileBlock { size_t start, in_off, in_len, out_len; };
+    std::vector<FileBlock> blocks;         // this part's blocks
+    size_t next_block = 0;
+    uint32_t first_skip = 0;
+    // gene table
+    DevBuf gene_hash, gene_of_hash;
+    int n_gene_hash = 0;
+    // reader thread
+    std::thread reader;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Staged *> ready, free_list;
+    bool finished = false, stop = false;
+    int err = 0;
+    std::string err_msg;
+    Staged staged[3];
+    // device buffers: shared intermediates + two sets of outputs
+    DevBuf d_comp, d_blocks, d_inflated, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
+    struct OutSet { DevBuf blob, rec_off, bc, umi, gene, score, ref_id, pos, hi, flag, gxa; } out[2];
+    int cur = 0;
+    uint32_t *h_small = nullptr;          // page-locked landing zone
+    cudaEvent_t ev_copy = nullptr;
+    int64_t records_seen = 0;
+
+    ~dyn_bam_dev() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        if (reader.joinable()) reader.join();
+        for (Staged &s : staged) if (s.bytes) cudaFreeHost(s.bytes);
+        if (h_small) cudaFreeHost(h_small);
+        if (ev_copy) cudaEventDestroy(ev_copy);
+        if (fd >= 0) close(fd);
+    }
+};
+
+namespace {
+
+bool pread_all(int fd, uint8_t *dst, size_t len, size_t off) {
+    size_t got = 0;
+    while (got < len) {
+        const ssize_t r = pread(fd, dst + got, len - got, (off_t)(off + got));
+        if (r <= 0) return false;
+        got += (size_t)r;
+    }
+    return true;
+}
+
+void read_ahead(dyn_bam_dev *d) {
+    for (;;) {
+        Staged *s = nullptr;
+        {
+            std::unique_lock<std::mutex> l(d->mu);
+            d->cv.wait(l, [&] { return d->stop || !d->free_list.empty(); });
+            if (d->stop) return;
+            if (d->next_block >= d->blocks.size()) { d->finished = true; d->cv.notify_all(); return; }
+            s = d->free_list.front();
+            d->free_list.pop_front();
+        }
+        size_t b1 = d->next_block, acc = 0;
+        while (b1 < d->blocks.size() && (b1 == d->next_block || acc + d->blocks[b1].out_len <= d->chunk_bytes)) acc += d->blocks[b1++].out_len;
+        const size_t f0 = d->blocks[d->next_block].start;
+        const size_t f1 = b1 < d->blocks.size() ? d->blocks[b1].start : d->blocks[b1 - 1].in_off + d->blocks[b1 - 1].in_len + 8;
+        s->len = f1 - f0;
+        bool ok = true;
+        if (s->cap < s->len) {
+            if (s->bytes) cudaFreeHost(s->bytes);
+            s->cap = s->len + s->len / 4 + (1 << 20);
+            if (cudaHostAlloc((void **)&s->bytes, s->cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); s->bytes = nullptr; s->cap = 0; ok = false; }
+        }
+        if (ok) {
+            // the file range is read by a few threads: one pread stream does not saturate a page cache / NVMe
+            const int nt = 4;
+            std::vector<std::thread> th;
+            std::vector<char> good(nt, 1);
+            for (int t = 0; t < nt; ++t)
+                th.emplace_back([&, t] {
+                    const size_t a = s->len * t / nt, b = s->len * (t + 1) / nt;
+                    good[t] = pread_all(d->fd, s->bytes + a, b - a, f0 + a) ? 1 : 0;
+                });
+            for (auto &t : th) t.join();
+            for (char g : good) ok &= g != 0;
+        }
+        s->blocks.clear();
+        s->inflated = 0;
+        for (size_t b = d->next_block; b < b1; ++b) {
+            const dyn_bam_dev::FileBlock &fb = d->blocks[b];
+            s->blocks.push_back(BlockDesc{(uint32_t)(fb.in_off - f0), (uint32_t)fb.in_len, (uint32_t)s->inflated, (uint32_t)fb.out_len});
+            s->inflated += fb.out_len;
+        }
+        s->first_skip = d->next_block == 0 ? d->first_skip : 0;
+        d->next_block = b1;
+        s->last = b1 >= d->blocks.size();
+        std::lock_guard<std::mutex> l(d->mu);
+        if (!ok) { d->err = DYN_ERR_IO; d->err_msg = "dyn_bam_dev: reading the BAM failed"; d->finished = true; d->cv.notify_all(); return; }
+        d->ready.push_back(s);
+        d->cv.notify_all();
+    }
+}
+
+}  // namespace
+
+// helpers of bamstream.cpp (block table, header, part boundaries) reused through the stream object
+extern "C" int dyn_bam_stream_layout(const char *path, int part, int n_parts, int64_t *n_blocks, const uint64_t **starts,
+                                     const uint64_t **in_offs, const uint64_t **in_lens, const uint64_t **out_lens, uint32_t *first_skip,
+                                     dyn_bam_stream_t **holder);
+
+extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_stream_opts_t *o, dyn_bam_dev_t **out) {
+    DYN_ARG(ctx != nullptr && path && o && out, "null argument");
+    CtxEnter enter_(ctx, nullptr, false);
+    DYN_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<dyn_bam_dev> d(new dyn_bam_dev());
+    d->ctx = ctx;
+    auto tag2 = [](const char *t) -> uint32_t { return (t && t[0] && t[1]) ? ((uint32_t)(uint8_t)t[0] | ((uint32_t)(uint8_t)t[1] << 8)) : 0u; };
+    d->tags.bc = tag2(o->barcode_tag); d->tags.umi = tag2(o->umi_tag); d->tags.gx = tag2(o->gene_tag);
+    d->tags.require_gene = o->require_gene != 0;
+    d->lean = o->lean != 0;
+    d->tags.lean = d->lean;
+    if (o->chunk_bytes > 0) d->chunk_bytes = (size_t)o->chunk_bytes;
+    // ---- file layout through the host stream reader's code (block table, header, part boundary guesser)
+    int64_t nb = 0;
+    const uint64_t *starts, *in_offs, *in_lens, *out_lens;
+    dyn_bam_stream_t *holder = nullptr;
+    int rc = dyn_bam_stream_layout(path, o->part, o->n_parts, &nb, &starts, &in_offs, &in_lens, &out_lens, &d->first_skip, &holder);
+    if (rc) return rc;
+    for (int64_t i = 0; i < nb; ++i) d->blocks.push_back({(size_t)starts[i], (size_t)in_offs[i], (size_t)in_lens[i], (size_t)out_lens[i]});
+    {
+        int64_t n = 0;
+        const char *t = static_cast<const char *>(dyn_bam_stream_field(holder, 10, &n));
+        d->header_text.assign(t ? t : "", (size_t)n);
+        const char *names = static_cast<const char *>(dyn_bam_stream_field(holder, 28, &n));
+        d->ref_names.assign(names, names + n);
+        const uint32_t *offs = static_cast<const uint32_t *>(dyn_bam_stream_field(holder, 29, &n));
+        d->ref_name_off.assign(offs, offs + n / 4);
+        const int32_t *lens = static_cast<const int32_t *>(dyn_bam_stream_field(holder, 9, &n));
+        d->ref_len.assign(lens, lens + n / 4);
+    }
+    dyn_bam_stream_close(holder);
+    // ---- gene table: FNV hashes of the ids, sorted; two ids with one hash cannot be told apart on the device
+    {
+        std::vector<std::pair<uint64_t, int32_t>> hs;
+        for (int64_t i = 0; i < o->n_gene_ids; ++i)
+            hs.emplace_back(bamrec::fnv1a(reinterpret_cast<const uint8_t *>(o->gene_ids[i]), (uint32_t)strlen(o->gene_ids[i])), (int32_t)i);
+        std::sort(hs.begin(), hs.end());
+        for (size_t i = 1; i < hs.size(); ++i)
+            if (hs[i].first == hs[i - 1].first) { dyn_set_error("dyn_bam_dev_open: two gene ids share a 64-bit hash"); return DYN_ERR_ARG; }
+        std::vector<uint64_t> h(hs.size());
+        std::vector<int32_t> g(hs.size());
+        for (size_t i = 0; i < hs.size(); ++i) { h[i] = hs[i].first; g[i] = hs[i].second; }
+        d->n_gene_hash = (int)hs.size();
+        if ((rc = d->gene_hash.ensure(8 * std::max<size_t>(hs.size(), 1)))) return rc;
+        if ((rc = d->gene_of_hash.ensure(4 * std::max<size_t>(hs.size(), 1)))) return rc;
+        if (!hs.empty()) {
+            DYN_CUDA(cudaMemcpy(d->gene_hash.p, h.data(), 8 * h.size(), cudaMemcpyHostToDevice));
+            DYN_CUDA(cudaMemcpy(d->gene_of_hash.p, g.data(), 4 * g.size(), cudaMemcpyHostToDevice));
+        }
+    }
+    d->fd = open(path, O_RDONLY);
+    if (d->fd < 0) { dyn_set_error("dyn_bam_dev_open: cannot open %s", path); return DYN_ERR_IO; }
+    DYN_CUDA(cudaHostAlloc((void **)&d->h_small, 256, cudaHostAllocDefault));
+    DYN_CUDA(cudaEventCreateWithFlags(&d->ev_copy, cudaEventDisableTiming));
+    if ((rc = d->d_small.ensure(256))) return rc;
+    for (Staged &s : d->staged) d->free_list.push_back(&s);
+    dyn_bam_dev *dp = d.release();
+    dp->reader = std::thread(read_ahead, dp);
+    *out = dp;
+    return DYN_OK;
+}
+
+extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, void *stream_) {
+    if (!d || !chunk) { dyn_set_error("dyn_bam_dev_next: null argument"); return DYN_ERR_ARG; }
+    memset(chunk, 0, sizeof(*chunk));
+    CtxEnter enter_(d->ctx, stream_, false);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DYN_CUDA(cudaSetDevice(d->ctx->device));
+    Staged *s = nullptr;
+    {
+        std::unique_lock<std::mutex> l(d->mu);
+        d->cv.wait(l, [&] { return !d->ready.empty() || d->finished; });
+        if (d->ready.empty()) {
+            if (d->err) { dyn_set_error("%s", d->err_msg.c_str()); return d->err; }
+            chunk->end = 2;         // past the end of the range
+            return DYN_OK;
+        }
+        s = d->ready.front();
+        d->ready.pop_front();
+    }
+    struct Release {        // the staging buffer goes back to the reader when this call is done with it
+        dyn_bam_dev *d; Staged *s;
+        ~Release() { std::lock_guard<std::mutex> l(d->mu); d->free_list.push_back(s); d->cv.notify_all(); }
+    } release{d, s};
+    const int nb = (int)s->blocks.size();
+    int rc;
+    if ((rc = d->d_comp.ensure(s->len + 16))) return rc;
+    if ((rc = d->d_blocks.ensure(sizeof(BlockDesc) * (size_t)nb))) return rc;
+    if ((rc = d->d_inflated.ensure(s->inflated + 16))) return rc;
+    if ((rc = d->d_nrec.ensure(4 * (size_t)(nb + 1)))) return rc;
+    if ((rc = d->d_recbase.ensure(4 * (size_t)(nb + 1)))) return rc;
+    uint32_t *d_small = d->d_small.as<uint32_t>();      // [0] inflate work counter, [1] status, [2..3] scan totals
+    DYN_CUDA(cudaMemsetAsync(d_small, 0, 64, stream));
+    DYN_CUDA(cudaMemcpyAsync(d->d_comp.p, s->bytes, s->len, cudaMemcpyHostToDevice, stream));
+    DYN_CUDA(cudaMemcpyAsync(d->d_blocks.p, s->blocks.data(), sizeof(BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, stream));
+    // ---- k1: inflate, one warp per block
+    {
+        const int ctas = std::min((nb + kInfWarps - 1) / kInfWarps, d->ctx->sm_count * 6);
+        inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(d->d_comp.as<uint8_t>(), d->d_inflated.as<uint8_t>(), d->d_blocks.as<BlockDesc>(), nb,
+                                                            d_small, d_small + 1);
+        DYN_CUDA(cudaGetLastError());
+    }
+    // ---- k2: records per block, their prefix sum, the total
+    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_blocks.as<BlockDesc>(), nb, s->first_skip,
+                                                       d->d_nrec.as<uint32_t>(), nullptr, nullptr, d_small + 1);
+    DYN_CUDA(cudaGetLastError());
+    DYN_CUDA(cudaMemsetAsync(d->d_nrec.as<uint32_t>() + nb, 0, 4, stream));
+    size_t tmp_bytes = 0;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d->d_nrec.as<uint32_t>(), d->d_recbase.as<uint32_t>(), nb + 1, stream));
+    if ((rc = d->d_tmp.ensure(tmp_bytes))) return rc;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(d->d_tmp.p, tmp_bytes, d->d_nrec.as<uint32_t>(), d->d_recbase.as<uint32_t>(), nb + 1, stream));
+    DYN_CUDA(cudaMemcpyAsync(d->h_small, d->d_recbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaMemcpyAsync(d->h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaStreamSynchronize(stream));
+    const uint32_t n_rec = d->h_small[0];
+    uint32_t status = d->h_small[1];
+    auto status_error = [&](uint32_t st) -> int {
+        if (st & 0xeu) { dyn_set_error("dyn_bam_dev: inflate failed (corrupt BGZF block, status 0x%x)", st); return DYN_ERR_FORMAT; }
+        if (st & (1u << 8)) { dyn_set_error("dyn_bam_dev: alignment records straddle BGZF blocks: use the host reader (dyn_bam_stream_*)"); return DYN_ERR_FORMAT; }
+        if (st & (1u << 9)) { dyn_set_error("dyn_bam_dev: paired records: use the host reader (dyn_bam_stream_*)"); return DYN_ERR_FORMAT; }
+        if (st & (1u << 16)) { dyn_set_error("dyn_bam_dev: corrupt record or aux data"); return DYN_ERR_FORMAT; }
+        if (st & (1u << 17)) { dyn_set_error("dyn_bam_dev: alignment without HI / AS tag (KeyError in the reference, bam.py:295-296)"); return DYN_ERR_FORMAT; }
+        if (st & (1u << 18)) { dyn_set_error("dyn_bam_dev: alignment without MD tag (count.py:119-124)"); return DYN_ERR_FORMAT; }
+        if (st & (1u << 19)) { dyn_set_error("dyn_bam_dev: record too long for the packed layout"); return DYN_ERR_FORMAT; }
+        return DYN_OK;
+    };
+    if ((rc = status_error(status))) return rc;
+    d->records_seen += n_rec;
+    chunk->n_records_seen = n_rec;
+    chunk->end = s->last ? 1 : 0;
+    dyn_bam_dev::OutSet &os = d->out[d->cur];
+    d->cur ^= 1;
+    if (n_rec == 0) return DYN_OK;
+    // ---- k2 (positions), k3 (parse), scan
+    if ((rc = d->d_recat.ensure(4 * (size_t)n_rec))) return rc;
+    if ((rc = d->d_parsed.ensure(sizeof(bamrec::Parsed) * (size_t)n_rec))) return rc;
+    if ((rc = d->d_scan_in.ensure(8 * (size_t)(n_rec + 1)))) return rc;
+    if ((rc = d->d_scan.ensure(8 * (size_t)(n_rec + 1)))) return rc;
+    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_blocks.as<BlockDesc>(), nb, s->first_skip,
+                                                       nullptr, d->d_recbase.as<uint32_t>(), d->d_recat.as<uint32_t>(), d_small + 1);
+    DYN_CUDA(cudaGetLastError());
+    parse_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_recat.as<uint32_t>(), n_rec, d->tags,
+                                                          d->d_parsed.as<bamrec::Parsed>(), d->d_scan_in.as<unsigned long long>(), d_small + 1);
+    DYN_CUDA(cudaGetLastError());
+    DYN_CUDA(cudaMemsetAsync(d->d_scan_in.as<unsigned long long>() + n_rec, 0, 8, stream));
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d->d_scan_in.as<unsigned long long>(), d->d_scan.as<unsigned long long>(), (int)(n_rec + 1), stream));
+    if ((rc = d->d_tmp.ensure(tmp_bytes))) return rc;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(d->d_tmp.p, tmp_bytes, d->d_scan_in.as<unsigned long long>(), d->d_scan.as<unsigned long long>(), (int)(n_rec + 1), stream));
+    DYN_CUDA(cudaMemcpyAsync(d->h_small + 2, d->d_scan.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaMemcpyAsync(d->h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaStreamSynchronize(stream));
+    status = d->h_small[1];
+    if ((rc = status_error(status))) return rc;
+    const unsigned long long tot = *reinterpret_cast<unsigned long long *>(d->h_small + 2);
+    const uint32_t n_units = (uint32_t)(tot >> 40);
+    const unsigned long long total16 = tot & ((1ull << 40) - 1);
+    if (total16 > 0xfffffff0ull) { dyn_set_error("dyn_bam_dev: chunk over 64 GiB of packed records"); return DYN_ERR_NOMEM; }
+    // ---- k4: pack
+    const size_t nu = std::max<uint32_t>(n_units, 1);
+    if ((rc = os.blob.ensure((size_t)total16 * 16 + 16)) || (rc = os.rec_off.ensure(4 * (nu + 1))) || (rc = os.bc.ensure(8 * nu)) ||
+        (rc = os.umi.ensure(8 * nu)) || (rc = os.gene.ensure(4 * nu)) || (rc = os.score.ensure(4 * nu)) || (rc = os.ref_id.ensure(4 * nu)) ||
+        (rc = os.pos.ensure(4 * nu)) || (rc = os.hi.ensure(4 * nu)) || (rc = os.flag.ensure(2 * nu)) || (rc = os.gxa.ensure(nu)))
+        return rc;
+    UnitOut uo;
+    uo.blob = os.blob.as<uint8_t>(); uo.rec_off = os.rec_off.as<uint32_t>();
+    uo.bc_key = os.bc.as<unsigned long long>(); uo.umi_key = os.umi.as<unsigned long long>();
+    uo.gene_idx = os.gene.as<int32_t>(); uo.score = os.score.as<int32_t>(); uo.ref_id = os.ref_id.as<int32_t>();
+    uo.pos = os.pos.as<int32_t>(); uo.hi = os.hi.as<int32_t>(); uo.flag = os.flag.as<uint16_t>(); uo.gx_assigned = os.gxa.as<uint8_t>();
+    if (n_units) {
+        pack_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_recat.as<uint32_t>(), n_rec, d->d_parsed.as<bamrec::Parsed>(),
+                                                             d->d_scan.as<unsigned long long>(), d->lean, d->gene_hash.as<unsigned long long>(),
+                                                             d->gene_of_hash.as<int32_t>(), d->n_gene_hash, uo);
+        DYN_CUDA(cudaGetLastError());
+    }
+    const uint32_t end16 = (uint32_t)total16;
+    DYN_CUDA(cudaMemcpyAsync(uo.rec_off + n_units, &end16, 4, cudaMemcpyHostToDevice, stream));
+    DYN_CUDA(cudaStreamSynchronize(stream));       // (&end16 is a stack variable; the staging buffer is released on return)
+    chunk->n_units = n_units;
+    chunk->records_bytes = (int64_t)total16 * 16;
+    chunk->d_records = uo.blob; chunk->d_rec_off = uo.rec_off;
+    chunk->d_barcode_key = reinterpret_cast<uint64_t *>(uo.bc_key); chunk->d_umi_key = reinterpret_cast<uint64_t *>(uo.umi_key);
+    chunk->d_gene_idx = uo.gene_idx; chunk->d_score = uo.score; chunk->d_ref_id = uo.ref_id; chunk->d_pos = uo.pos; chunk->d_hi = uo.hi;
+    chunk->d_flag = uo.flag; chunk->d_gx_assigned = uo.gx_assigned;
+    chunk->compressed_bytes = (int64_t)s->len;
+    chunk->inflated_bytes = (int64_t)s->inflated;
+    return DYN_OK;
+}
+
+extern "C" void dyn_bam_dev_close(dyn_bam_dev_t *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    delete d;
+}
+
+extern "C" int64_t dyn_bam_dev_n_refs(const dyn_bam_dev_t *d) { return d ? (int64_t)d->ref_len.size() : 0; }
+
+extern "C" const void *dyn_bam_dev_field(const dyn_bam_dev_t *d, int field, int64_t *n_bytes) {
+    if (!d) return nullptr;
+    const void *p = nullptr;
+    size_t nb = 0;
+    switch (field) {
+        case 9: p = d->ref_len.data(); nb = d->ref_len.size() * 4; break;
+        case 10: p = d->header_text.data(); nb = d->header_text.size(); break;
+        case 28: p = d->ref_names.data(); nb = d->ref_names.size(); break;
+        case 29: p = d->ref_name_off.data(); nb = d->ref_name_off.size() * 4; break;
+        default: return nullptr;
+    }
+    if (n_bytes) *n_bytes = (int64_t)nb;
+    return p;
+}
+
+// Test / tool entry: inflate BGZF-style raw deflate blocks that already sit in device memory (one warp per block).
+extern "C" int dyn_inflate_blocks(dyn_ctx_t *ctx, const void *d_in, void *d_out, const uint32_t *d_block_desc, int32_t n_blocks,
+                                  uint32_t *d_work, uint32_t *d_status, void *stream) {
+    DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream);
+    DYN_ARG(n_blocks >= 0, "negative n_blocks");
+    if (n_blocks == 0) return DYN_OK;
+    DYN_ARG(d_in && d_out && d_block_desc && d_work && d_status, "null buffer");
+    DYN_CUDA(cudaMemsetAsync(d_work, 0, 4, static_cast<cudaStream_t>(stream)));
+    const int ctas = std::min((n_blocks + kInfWarps - 1) / kInfWarps, ctx->sm_count * 6);
+    inflate_kernel<<<ctas, kInfWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t *>(d_in), static_cast<uint8_t *>(d_out),
+                                                                                    reinterpret_cast<const BlockDesc *>(d_block_desc), n_blocks, d_work, d_status);
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}

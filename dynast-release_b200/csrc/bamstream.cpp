@@ -153,6 +153,7 @@ struct dyn_bam_stream {
     std::string err_msg;
     std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
     int64_t records_seen = 0;
+    std::vector<uint64_t> lay_start, lay_in_off, lay_in_len, lay_out_len;      // dyn_bam_stream_layout
 
     ~dyn_bam_stream() {
         {
@@ -637,7 +638,7 @@ void produce(dyn_bam_stream *s) {
 
 }  // namespace
 
-extern "C" int dyn_bam_stream_open(const char *path, const dyn_bam_stream_opts_t *o, dyn_bam_stream_t **out) {
+static int stream_create(const char *path, const dyn_bam_stream_opts_t *o, bool start, dyn_bam_stream_t **out) {
     if (!path || !o || !out) { dyn_set_error("dyn_bam_stream_open: null argument"); return DYN_ERR_ARG; }
     if (o->n_parts < 1 || o->part < 0 || o->part >= o->n_parts) { dyn_set_error("dyn_bam_stream_open: part %d of %d", o->part, o->n_parts); return DYN_ERR_ARG; }
     std::unique_ptr<dyn_bam_stream> s(new dyn_bam_stream());
@@ -691,8 +692,40 @@ extern "C" int dyn_bam_stream_open(const char *path, const dyn_bam_stream_opts_t
         }
     }
     dyn_bam_stream *sp = s.release();
-    sp->producer = std::thread(produce, sp);
+    if (start) sp->producer = std::thread(produce, sp);
     *out = sp;
+    return DYN_OK;
+}
+
+extern "C" int dyn_bam_stream_open(const char *path, const dyn_bam_stream_opts_t *o, dyn_bam_stream_t **out) {
+    return stream_create(path, o, true, out);
+}
+
+// The block range of a part without reading it (the device ingest, bamdevice.cu, shares the block table, the header
+// parse and the part-boundary guesser): per block its file offset, the offset / length of its deflate payload and its
+// inflated size; *first_skip = bytes of the first block that precede the part's first record.  The arrays live in
+// *holder (close it with dyn_bam_stream_close).
+extern "C" int dyn_bam_stream_layout(const char *path, int part, int n_parts, int64_t *n_blocks, const uint64_t **starts,
+                                     const uint64_t **in_offs, const uint64_t **in_lens, const uint64_t **out_lens, uint32_t *first_skip,
+                                     dyn_bam_stream_t **holder) {
+    dyn_bam_stream_opts_t o;
+    memset(&o, 0, sizeof(o));
+    o.part = part; o.n_parts = n_parts; o.n_threads = 1;
+    dyn_bam_stream_t *s = nullptr;
+    const int rc = stream_create(path, &o, false, &s);
+    if (rc) return rc;
+    for (size_t b = s->next_block; b < s->end_block; ++b) {
+        const Block &bl = s->blocks[b];
+        // the block starts 12 + xlen bytes before its payload: recover it from the previous block's end
+        s->lay_in_off.push_back(bl.in_off);
+        s->lay_in_len.push_back(bl.in_len);
+        s->lay_out_len.push_back(bl.out_len);
+        s->lay_start.push_back(b == 0 ? 0 : s->blocks[b - 1].in_off + s->blocks[b - 1].in_len + 8);
+    }
+    *n_blocks = (int64_t)s->lay_start.size();
+    *starts = s->lay_start.data(); *in_offs = s->lay_in_off.data(); *in_lens = s->lay_in_len.data(); *out_lens = s->lay_out_len.data();
+    *first_skip = (uint32_t)s->first_skip;
+    *holder = s;
     return DYN_OK;
 }
 

@@ -436,6 +436,39 @@ int64_t dyn_bam_stream_n_refs(const dyn_bam_stream_t *stream);
 const void *dyn_bam_stream_field(const dyn_bam_stream_t *stream, int field, int64_t *n_bytes);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device ingest: the same block range, inflated and packed ON THE GPU (csrc/bamdevice.cu) -- one warp per BGZF block
+ * inflates it, one thread per alignment record filters / tokenises / packs it; only the compressed bytes cross PCIe.
+ * Takes coordinate-sorted single-end BAMs whose BGZF blocks end on record boundaries (htslib / samtools / STAR write
+ * them so); anything else is refused with DYN_ERR_FORMAT and belongs to dyn_bam_stream_*.  Options as for
+ * dyn_bam_stream_open (keys are always produced, n_threads is ignored, gene_ids gives the gene index).
+ * dyn_bam_dev_next fills *chunk with DEVICE pointers to one chunk's units -- packed records, offsets (n_units + 1),
+ * keys as in dyn_bam_stream chunks (fields 11-13), AS, reference id, position, HI, flag, gene-tag-present -- valid until
+ * the second-next call; chunk->end is 1 on the last chunk of the range and 2 (nothing else set) on calls past it.  The call runs on `stream` and
+ * synchronises it (chunk sizes come back from the device).
+ * dyn_inflate_blocks: the inflate kernel alone on raw deflate payloads in device memory; d_block_desc = n_blocks x
+ * {in_off, in_len, out_off, out_len} (u32), *d_status gets bit (1 << code) of inflate error codes 1 data, 2 input,
+ * 3 output size; d_work is a scratch u32.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dyn_bam_dev dyn_bam_dev_t;
+typedef struct {
+    int64_t n_units, n_records_seen, records_bytes, compressed_bytes, inflated_bytes;
+    int32_t end, reserved;
+    const void *d_records;
+    const uint32_t *d_rec_off;
+    const uint64_t *d_barcode_key, *d_umi_key;
+    const int32_t *d_gene_idx, *d_score, *d_ref_id, *d_pos, *d_hi;
+    const uint16_t *d_flag;
+    const uint8_t *d_gx_assigned;
+} dyn_bam_dev_chunk_t;
+int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_stream_opts_t *opts, dyn_bam_dev_t **out_dev);
+int dyn_bam_dev_next(dyn_bam_dev_t *dev, dyn_bam_dev_chunk_t *chunk, void *stream);
+void dyn_bam_dev_close(dyn_bam_dev_t *dev);
+int64_t dyn_bam_dev_n_refs(const dyn_bam_dev_t *dev);
+const void *dyn_bam_dev_field(const dyn_bam_dev_t *dev, int field, int64_t *n_bytes);
+int dyn_inflate_blocks(dyn_ctx_t *ctx, const void *d_in, void *d_out, const uint32_t *d_block_desc, int32_t n_blocks,
+                       uint32_t *d_work, uint32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * BAM writer (what call_consensus gets from pysam + samtools sort / index, consensus.py:360-366, 476-494; also builds
  * the synthetic BAMs of the ingest benchmarks).  Unit u -- one packed record in the FULL layout, no mate -- becomes one
  * alignment record: name = h_names[h_name_off[u] .. h_name_off[u + 1]) ("r<u>" when h_names is NULL), MAPQ h_mapq[u]
