@@ -422,7 +422,7 @@ def consensus(ctx: Context, records: torch.Tensor, item_rec16: torch.Tensor, gro
 def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score, strand, n_barcodes: int, n_genes: int,
                       out: TallyBuffers, conversions=('TC',), quality: int = 27, umi_bits: int = 24,
                       cell_threshold: int = 1000, with_pi: bool = True, timings: Optional[dict] = None, group=None,
-                      exchange: bool = False):
+                      exchange: bool = False, tallied=None, transcriptome=None):
     """Runs every stage of the path on device tensors (the packed records of one GPU's read range plus the
     interned barcode / umi / gene ids of its reads).  Mirrors count() then estimate(method='alpha') of the
     reference: count_conversions (count.py:306) -> estimate_p_e (estimate.py:197-234) -> aggregate_counts
@@ -430,8 +430,10 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
     Returns a dict of device tensors.  `timings`, if given, receives per-stage milliseconds (CUDA events).
     exchange=True (multi-GPU, read-range sharding): `barcode` holds GLOBAL barcode ids and n_barcodes the global
     count; after the tally every read's row goes to rank barcode % world (distributed.exchange_reads) and the rest
-    of the path runs on the barcodes this rank owns (local id = global id // world)."""
-    dev = records.device
+    of the path runs on the barcodes this rank owns (local id = global id // world).
+    tallied = (counts [n, 16] uint8, conv_n [n] int16): the tally already ran (tally_bam streams it chunk by chunk while
+    the BAM is being read) and records / rec_off / out are not used; transcriptome = the reads' gene-tag-present flag."""
+    dev = barcode.device
     stream = torch.cuda.current_stream()
     marks = []
 
@@ -442,16 +444,19 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
             marks.append((name, e))
 
     mark('start')
-    tally_reads(ctx, records, rec_off, out, quality=quality, emit_conv=True)
+    if tallied is None:
+        tally_reads(ctx, records, rec_off, out, quality=quality, emit_conv=True)
+        counts, conv_n = out.counts, out.conv_n
+    else:
+        counts, conv_n = tallied
     mark('tally')
-    counts, conv_n = out.counts, out.conv_n
     score16 = score.to(torch.int16)
-    transcriptome = None
     if exchange:
         from . import distributed
         import torch.distributed as dist
         world = dist.get_world_size(group)
-        got = distributed.exchange_reads(ctx, barcode, umi, gene, score16, conv_n, strand, counts, world, group=group)
+        got = distributed.exchange_reads(ctx, barcode, umi, gene, score16, conv_n, strand, counts, world, group=group,
+                                         transcriptome=transcriptome)
         counts, conv_n, score16, strand, umi, gene = got['counts'], got['conv_n'], got['score'], got['strand'], got['umi'], got['gene']
         transcriptome = got['transcriptome']
         barcode = torch.div(got['barcode'], world, rounding_mode='floor').to(torch.int32)
@@ -502,4 +507,147 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
         stream.synchronize()
         for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
             timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
+    return res
+
+
+# --------------------------------------------------------------------------------------------------
+# From a BAM file: streamed ingest (device or host) -> tally per chunk -> the path above
+# --------------------------------------------------------------------------------------------------
+def tally_bam(ctx: Context, path: str, gene_ids, barcode_tag: Optional[str] = 'CB', umi_tag: Optional[str] = 'UB',
+              gene_tag: str = 'GX', require_gene: bool = True, quality: int = 27, nasc: bool = False, part: int = 0,
+              n_parts: int = 1, chunk_bytes: int = 256 << 20, ingest: str = 'device', n_threads: int = 8, snps=None,
+              stats: Optional[dict] = None):
+    """Streams block range `part` of `n_parts` of a coordinate-sorted BAM through the tally: every chunk of the reader
+    (bamio.DeviceBamStream: inflate + pack on the GPU; bamio.BamStream: on the host cores, then cudaMemcpyAsync from
+    page-locked memory) is tallied as it arrives while the next one is being read.  ingest = 'device' | 'host' | 'auto'
+    (device, falling back to the host reader for files the device path refuses: paired records, records straddling
+    BGZF blocks).  Returns the per-read columns of the whole range on the device: counts [n, 16] uint8, conv_n int16,
+    barcode_key / umi_key int64 (2-bit packed), gene_idx int32 (index into gene_ids, -1 no tag, -2 unknown), score int32,
+    transcriptome uint8 (gene tag present), status (int, DYN_ST_* bits)."""
+    from . import bamio
+    dev = torch.device('cuda', ctx.device)
+    kw = dict(barcode_tag=barcode_tag, umi_tag=umi_tag, gene_tag=gene_tag, require_gene=require_gene, part=part, n_parts=n_parts,
+              chunk_bytes=chunk_bytes)
+    cols = {k: [] for k in ('counts', 'conv_n', 'barcode_key', 'umi_key', 'gene_idx', 'score', 'transcriptome')}
+    status = torch.zeros(1, dtype=torch.int64, device=dev)
+    seen = units = compressed = inflated = 0
+
+    def tally_chunk(records, rec_off, n):
+        out = TallyBuffers(n, 2 * n + 4096, device=ctx.device)
+        tally_reads(ctx, records, rec_off, out, quality=quality, nasc=nasc, emit_conv=True, snps=snps)
+        status.bitwise_or_(out.scalars[1:2])
+        cols['counts'].append(out.counts)
+        cols['conv_n'].append(out.conv_n)
+
+    def run_device():
+        nonlocal seen, units, compressed, inflated
+        with bamio.DeviceBamStream(ctx, path, lean=True, gene_ids=list(gene_ids), **kw) as st:
+            for ch in st:
+                seen += ch['n_records_seen']; compressed += ch['compressed_bytes']; inflated += ch['inflated_bytes']
+                n = ch['n_units']
+                if not n:
+                    continue
+                units += n
+                tally_chunk(ch['records'], ch['rec_off'], n)
+                # the chunk's buffers are reused two chunks later: keep copies of the (small) key columns
+                cols['barcode_key'].append(ch['barcode_key'].clone()); cols['umi_key'].append(ch['umi_key'].clone())
+                cols['gene_idx'].append(ch['gene_idx'].clone()); cols['score'].append(ch['score'].clone())
+                cols['transcriptome'].append(ch['gx_assigned'].clone())
+
+    def run_host():
+        nonlocal seen, units
+        pending = []        # (chunk, event): a chunk's page-locked buffers are released once its copies have run
+        with bamio.BamStream(path, keys=True, lean=True, gene_ids=list(gene_ids), n_threads=n_threads, **kw) as st:
+            for ch in st:
+                seen += ch.n_records_seen
+                n = ch.n_units
+                if n:
+                    units += n
+                    h2d = lambda a: torch.from_numpy(a).to(dev, non_blocking=True)
+                    records = h2d(ch.blob)
+                    rec_off = torch.from_numpy(ch.rec_off.view(np.int32)).to(dev)
+                    cols['barcode_key'].append(torch.from_numpy(ch.barcode_key.view(np.int64)).to(dev))
+                    cols['umi_key'].append(torch.from_numpy(ch.umi_key.view(np.int64)).to(dev))
+                    cols['gene_idx'].append(torch.from_numpy(ch.gene_idx).to(dev)); cols['score'].append(torch.from_numpy(ch.score).to(dev))
+                    cols['transcriptome'].append(torch.from_numpy(ch.gx_assigned).to(dev))
+                    tally_chunk(records, rec_off, n)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending.append((ch, ev))
+                while len(pending) > 2:
+                    old, oev = pending.pop(0)
+                    oev.synchronize()
+                    old.close()
+            for old, oev in pending:
+                oev.synchronize()
+                old.close()
+
+    if ingest in ('device', 'auto'):
+        try:
+            run_device()
+        except _lib.DynastB200Error as exc:
+            if ingest == 'device' or not any(w in str(exc) for w in ('straddle', 'paired')):
+                raise
+            for v in cols.values():
+                v.clear()
+            seen = units = compressed = inflated = 0
+            run_host()
+            ingest = 'host (the device path refused the file: %s)' % str(exc).split(': ', 2)[-1][:60]
+    else:
+        run_host()
+    empty = dict(counts=torch.empty((0, 16), dtype=torch.uint8, device=dev), conv_n=torch.empty(0, dtype=torch.int16, device=dev),
+                 barcode_key=torch.empty(0, dtype=torch.int64, device=dev), umi_key=torch.empty(0, dtype=torch.int64, device=dev),
+                 gene_idx=torch.empty(0, dtype=torch.int32, device=dev), score=torch.empty(0, dtype=torch.int32, device=dev),
+                 transcriptome=torch.empty(0, dtype=torch.uint8, device=dev))
+    res = {k: (torch.cat(v) if len(v) > 1 else (v[0] if v else empty[k])) for k, v in cols.items()}
+    res['status'] = int(status.item()) & 0xffffffff
+    if stats is not None:
+        stats.update(records_seen=seen, units=units, compressed_bytes=compressed, inflated_bytes=inflated, ingest=ingest)
+    return res
+
+
+def count_from_bam(ctx: Context, path: str, gene_ids, gene_strand, conversions=('TC',), group=None, timings: Optional[dict] = None,
+                   stats: Optional[dict] = None, cell_threshold: int = 1000, with_pi: bool = True, **bam_kw):
+    """`dynast count` + `dynast estimate` on the device from a BAM file: tally_bam over this rank's block range
+    (part = rank, n_parts = world when `group` is given), barcode / UMI keys -> dense ids, then count_to_estimate on the
+    tallied reads (with the per-read exchange to the barcode owner when several ranks share the file).
+    gene_strand: uint8 per gene of gene_ids (0 '+', 1 '-').  Returns count_to_estimate's dict plus `barcode_keys`
+    (the 2-bit key of every dense barcode id; bamio.decode_key turns it back into the string)."""
+    world, rank = 1, 0
+    if group is not None:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        bam_kw.update(part=rank, n_parts=world)
+    t = tally_bam(ctx, path, gene_ids, stats=stats, **bam_kw)
+    dev = t['counts'].device
+    if t['status'] & 0x2:
+        raise ValueError('malformed alignment record (CIGAR / MD / sequence disagree)')
+    if t['gene_idx'].numel() and int(t['gene_idx'].min().item()) < 0:
+        raise KeyError('a read carries no gene tag or one that is not in gene_ids (KeyError in complement_counts, conversion.py:116)')
+    bc_keys = torch.unique(t['barcode_key'])
+    if world > 1:       # one global, sorted barcode table: dense ids agree on every rank (owner = id % world)
+        import torch.distributed as dist
+        n_max = torch.tensor([bc_keys.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=group)
+        pad = torch.full((int(n_max.item()),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+        pad[:bc_keys.numel()] = bc_keys
+        every = torch.empty(world * pad.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, pad, group=group)
+        bc_keys = torch.unique(every)
+        bc_keys = bc_keys[bc_keys != torch.iinfo(torch.int64).max]
+    barcode = torch.searchsorted(bc_keys, t['barcode_key']).to(torch.int32)
+    n_barcodes = int(bc_keys.numel())
+    umi = t['umi_key']
+    umi_bits = max(1, int(umi.max().item()).bit_length()) if umi.numel() else 1
+    gene_bits, bc_bits = _bits(max(len(gene_ids) - 1, 0)), _bits(max(n_barcodes - 1, 0))
+    if umi_bits + gene_bits + bc_bits > 64:      # long UMIs: dense ids instead of the 2-bit value
+        u, inv = torch.unique(umi, return_inverse=True)
+        umi, umi_bits = inv.to(torch.int64), _bits(max(int(u.numel()) - 1, 0))
+    strand_table = torch.as_tensor(np.ascontiguousarray(gene_strand, dtype=np.uint8), device=dev)
+    strand = strand_table[t['gene_idx'].long()]
+    res = count_to_estimate(ctx, None, None, barcode, umi, t['gene_idx'], t['score'], strand, n_barcodes, len(gene_ids), None,
+                            conversions=conversions, umi_bits=umi_bits, cell_threshold=cell_threshold, with_pi=with_pi, timings=timings,
+                            group=group, exchange=world > 1, tallied=(t['counts'], t['conv_n']), transcriptome=t['transcriptome'])
+    res['barcode_keys'] = bc_keys
+    res['n_reads_tallied'] = int(barcode.numel())
     return res

@@ -168,3 +168,58 @@ def make_reads(
         labelled=labelled,
         raw=raw,
     )
+
+
+# ------------------------------------------------------------------------------------------------
+# Synthetic BAM files (bench / test utility): the device generator's reads written through dyn_bam_write
+# ------------------------------------------------------------------------------------------------
+def _digits(values: np.ndarray, width: int, base: int, alphabet: bytes) -> np.ndarray:
+    """[n, width] uint8 matrix of the base-`base` digits of `values`, most significant first, drawn from `alphabet`."""
+    v = values.astype(np.uint64)
+    out = np.empty((len(v), width), dtype=np.uint8)
+    table = np.frombuffer(alphabet, dtype=np.uint8)
+    for j in range(width - 1, -1, -1):
+        out[:, j] = table[(v % np.uint64(base)).astype(np.int64)]
+        v //= np.uint64(base)
+    return out
+
+
+def barcode_strings(ids: np.ndarray, width: int = 16) -> np.ndarray:
+    """[n, width] ACGT letters of barcode ids (a multiplicative hash spreads consecutive ids over the letters)."""
+    return _digits((ids.astype(np.uint64) * np.uint64(2654435761)) & np.uint64(4**width - 1), width, 4, b'ACGT')
+
+
+def gene_names(n_genes: int):
+    return [f'ENSG{g:011d}' for g in range(n_genes)]
+
+
+def write_synth_bam(path: str, batch, n_contigs: int = 25, level: int = 6, n_threads: int = 8, index: bool = False) -> Dict:
+    """A coordinate-sorted BAM of a pipeline.SynthBatch (full record layout, with keys): Illumina-style read names,
+    tags NH HI AS nM CB UB GX (and the MD tag dyn_bam_write rebuilds).  Returns dict(n_records, gene_ids, refs)."""
+    from . import bamio
+    assert not batch.lean and batch.barcode is not None, 'write_synth_bam needs full records with keys'
+    n = batch.n_reads
+    blob = batch.records.cpu().numpy()
+    rec_off = batch.rec_off.cpu().numpy().view(np.uint32)
+    barcode = batch.barcode.cpu().numpy().astype(np.int64)
+    umi = batch.umi.cpu().numpy().view(np.uint64)
+    gene = batch.gene.cpu().numpy().astype(np.int64)
+    score = np.clip(batch.score.cpu().numpy(), 0, 255).astype(np.uint8)
+    ref_id = blob[rec_off[:-1].astype(np.int64) * 16 + 4].astype(np.int64)       # low byte of the header's ref_id (< 256 contigs)
+    order = np.argsort(ref_id, kind='stable').astype(np.int64)                   # positions already ascend with the index
+    # read names: SYN:<index>:<tile>:<x>:<y>
+    idx = np.arange(n, dtype=np.uint64)
+    name = np.concatenate([np.broadcast_to(np.frombuffer(b'SYN0001:7:HXXXXXXXX:1:', np.uint8), (n, 22)), _digits(idx % 2000 + 1101, 4, 10, b'0123456789'),
+                           np.broadcast_to(np.frombuffer(b':', np.uint8), (n, 1)), _digits((idx * 7919) % 30000, 5, 10, b'0123456789'),
+                           np.broadcast_to(np.frombuffer(b':', np.uint8), (n, 1)), _digits(idx, 9, 10, b'0123456789')], axis=1)
+    name_off = (np.arange(n + 1, dtype=np.uint64) * name.shape[1]).astype(np.uint32)
+    const = lambda b: np.broadcast_to(np.frombuffer(b, np.uint8), (n, len(b)))
+    aux = np.concatenate([const(b'NHC\x01HIC\x01ASC'), score[:, None], const(b'nMC\x00CBZ'), barcode_strings(barcode), const(b'\x00UBZ'),
+                          _digits(umi & np.uint64(4**12 - 1), 12, 4, b'ACGT'), const(b'\x00GXZENSG'), _digits(gene.astype(np.uint64), 11, 10, b'0123456789'),
+                          const(b'\x00')], axis=1)
+    aux_off = (np.arange(n + 1, dtype=np.uint64) * aux.shape[1]).astype(np.uint32)
+    refs = [(f'chr{c + 1}', 1 << 28) for c in range(n_contigs)]
+    bamio.write_bam(path, refs, blob, rec_off, order=order, names=(np.ascontiguousarray(name).tobytes(), name_off),
+                    aux=(np.ascontiguousarray(aux).tobytes(), aux_off), mapq=np.full(n, 255, np.uint8), level=level, n_threads=n_threads,
+                    index=index)
+    return dict(n_records=n, gene_ids=gene_names(batch.n_genes), refs=refs, order=order)

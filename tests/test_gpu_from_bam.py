@@ -1,0 +1,77 @@
+"""GPU: the whole path from a BAM FILE (pipeline.count_from_bam: streamed ingest -> tally per chunk -> UMI dedup -> p_e ->
+histograms -> EM) equals the same path on the packed records the file was written from -- with the device ingest
+(inflate + pack on the GPU) and with the host reader."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ref_path
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def synth_bam(tmp_path_factory):
+    from dynast_b200 import pipeline, synth
+    ctx = pipeline.Context.get(0)
+    batch = pipeline.SynthBatch(300_000, seed=91, n_barcodes=60, n_genes=400, device=0, lean=False, reads_per_umi=2.5)
+    path = str(tmp_path_factory.mktemp('bam') / 'synth.bam')
+    info = synth.write_synth_bam(path, batch, level=6, n_threads=4)
+    # the reference result: the same reads, in the file's order, through the device path
+    out = pipeline.TallyBuffers(batch.n_reads, 3 * batch.n_reads, device=0)
+    pipeline.tally_reads(ctx, batch.records, batch.rec_off, out, quality=27)
+    order = torch.from_numpy(info['order']).cuda()
+    want = pipeline.count_to_estimate(ctx, None, None, batch.barcode[order], batch.umi[order], batch.gene[order], batch.score[order],
+                                      batch.strand[order], 60, 400, None, cell_threshold=200, with_pi=False,
+                                      tallied=(out.counts[order], out.conv_n[order]))
+    torch.cuda.synchronize()
+    strand = batch.tables['gene_strand'].cpu().numpy()
+    return dict(path=path, info=info, want=want, strand=strand, n=batch.n_reads)
+
+
+@pytest.mark.parametrize('ingest,chunk_bytes', [('device', 8 << 20), ('host', 8 << 20), ('device', 256 << 20)])
+def test_count_from_bam_equals_packed_path(gpu_ctx, synth_bam, ingest, chunk_bytes):
+    from dynast_b200 import bamio, pipeline, synth
+    stats = {}
+    got = pipeline.count_from_bam(gpu_ctx, synth_bam['path'], synth_bam['info']['gene_ids'], synth_bam['strand'], cell_threshold=200,
+                                  with_pi=False, ingest=ingest, chunk_bytes=chunk_bytes, n_threads=4, stats=stats)
+    torch.cuda.synchronize()
+    want = synth_bam['want']
+    assert stats['records_seen'] == stats['units'] == synth_bam['n'] == got['n_reads_tallied']
+    assert int(got['selected'].numel()) == int(want['selected'].numel())
+    # dense barcode ids here are ranks of the 2-bit keys: map the generator's ids onto them
+    keys = [bamio.decode_key(k) for k in got['barcode_keys'].cpu().numpy()]
+    names = [bytes(r).decode() for r in synth.barcode_strings(np.arange(60))]
+    pos = [keys.index(nm) for nm in names]
+    for name in ('n_reads', 'p_e', 'p_c', 'em_status'):
+        a, b = want[name].cpu().numpy(), got[name].cpu().numpy()[pos]
+        assert np.array_equal(a, b, equal_nan=(a.dtype.kind == 'f')), name
+    assert (want['em_status'] == 0).sum() > 20
+    k, n, c, off = (x.cpu().numpy() for x in want['hist'])
+    k2, n2, c2, off2 = (x.cpu().numpy() for x in got['hist'])
+    for b in range(60):
+        j = pos[b]
+        assert np.array_equal(k[off[b]:off[b + 1]], k2[off2[j]:off2[j + 1]]) and np.array_equal(c[off[b]:off[b + 1]], c2[off2[j]:off2[j + 1]])
+
+
+def test_count_from_bam_auto_falls_back_to_the_host_reader(gpu_ctx, tmp_path):
+    """Records straddling BGZF blocks: the device path refuses, `auto` reads the file on the host; same tally."""
+    from dynast_b200 import bamio, pipeline
+    out = str(tmp_path / 'split.bam')
+    subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'make_bam.py'), ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'),
+                    out, '6'], check=True, capture_output=True)
+    with bamio.PackedBam(out, barcode_tag='CB', umi_tag='UB', require_gene=True, n_threads=2) as pb:
+        genes = sorted(set(pb.gene))
+        n = pb.n_units
+    stats = {}
+    t = pipeline.tally_bam(gpu_ctx, out, genes, ingest='auto', chunk_bytes=1 << 20, stats=stats)
+    assert stats['ingest'].startswith('host') and t['counts'].shape[0] == n == stats['units']
+    h = pipeline.tally_bam(gpu_ctx, out, genes, ingest='host', chunk_bytes=0)
+    assert torch.equal(t['counts'], h['counts']) and torch.equal(t['barcode_key'], h['barcode_key'])
+    with pytest.raises(Exception, match='straddle'):
+        pipeline.tally_bam(gpu_ctx, out, genes, ingest='device')
