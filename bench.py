@@ -215,20 +215,64 @@ def bind_near_gpu(index):
     return None
 
 
+def workload_config(args, world, numa=None):
+    return {
+        'workload': 'C2 synthetic scSLAM-seq-like 10x BAM records: 50M reads x 91 nt, 10k barcodes, TC, per GPU',
+        'reads_per_gpu': args.reads, 'barcodes_per_gpu': args.barcodes, 'read_len': 91, 'quality': 27,
+        'record_layout': 'full (Phred stream kept)' if args.full_records else
+                         'lean (single-end: Phred only at mismatches, inside the MD tokens; include/dynast_b200.h DYN_REC_LEAN)',
+        'l2_policy': 'inputs (~%.1f GB packed records per step) are far larger than the 126 MB L2' % (8.8 if args.full_records else 4.2),
+        'parallelism': f'read-range x{world}', 'cpus_bound_near_gpu': numa,
+    }
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's per-read tally (C restatement, oracle/tally_oracle.c) on all host threads.
+    Nothing of the product is imported here: the input comes from the oracle's own numpy generator."""
+    from oracle import synth_np
+    n_cores = os.cpu_count() or 1
+    sample = min(args.reads, args.cpu_sample_reads)
+    unit = min(sample, 1_000_000)          # generated once, tiled up to the sample size (the numpy generator does ~0.2 M reads/s)
+    blob1, off1 = synth_np.make_records(unit, seed=2001, lean=not args.full_records)
+    reps = max(1, sample // unit)
+    sample = reps * unit
+    blob = np.tile(blob1, reps)
+    rec_off = np.concatenate([off1[:-1].astype(np.int64) + r * int(off1[-1]) for r in range(reps)] + [[reps * int(off1[-1])]]).astype(np.uint32)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, _ = cpu_tally_baseline(blob, rec_off, n_cores)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sample / value,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': workload_config(args, int(os.environ.get('WORLD_SIZE', 1))),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': n_cores, 'kind': 'port',
+                         'sample': f'{sample} reads of the C2 workload per step (oracle/synth_np.py, same generative model); C '
+                                   'restatement of the reference tally (oracle/tally_oracle.c) on all host threads; the reference '
+                                   'itself is CPython + pysam and cannot run on this box'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     args = parse_args()
-    import torch
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    if args.impl == 'reference' and rank != 0:
-        return 0
+    if args.impl == 'reference':
+        return reference_arm(args) if rank == 0 else 0
+    import torch
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device; dynast_b200 has no CPU fallback'
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     numa = bind_near_gpu(local_rank) if world > 1 else None
     dist = None
-    if world > 1 and args.impl != 'reference':
+    if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
 
@@ -237,42 +281,7 @@ def main():
     ctx = Context.get(local_rank)
     n_cores = os.cpu_count() or 1
     n_reads = args.reads
-    config = {
-        'workload': 'C2 synthetic scSLAM-seq-like 10x BAM records: 50M reads x 91 nt, 10k barcodes, TC, per GPU',
-        'reads_per_gpu': n_reads, 'barcodes_per_gpu': args.barcodes, 'read_len': 91, 'quality': 27,
-        'record_layout': 'full (Phred stream kept)' if args.full_records else
-                         'lean (single-end: Phred only at mismatches, inside the MD tokens; include/dynast_b200.h DYN_REC_LEAN)',
-        'l2_policy': 'inputs (~%.1f GB packed records per step) are far larger than the 126 MB L2' % (8.8 if args.full_records else 4.2),
-        'parallelism': f'read-range x{world}', 'cpus_bound_near_gpu': numa,
-    }
-
-    # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
-    if args.impl == 'reference':
-        sample = min(n_reads, args.cpu_sample_reads)
-        batch = pipeline.SynthBatch(sample, seed=2001, n_barcodes=args.barcodes, device=local_rank, with_keys=False,
-                                    lean=not args.full_records)
-        blob = batch.records.cpu().numpy()
-        rec_off = batch.rec_off.cpu().numpy().view(np.uint32)
-        del batch
-        vals = []
-        for i in range(args.warmup + args.steps):
-            v, _ = cpu_tally_baseline(blob, rec_off, n_cores)
-            if i >= args.warmup:
-                vals.append(v)
-        value = float(np.mean(vals))
-        line = {
-            'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sample / value,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': config,
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': n_cores, 'kind': 'port',
-                             'sample': f'{sample} reads of the C2 workload per step; C restatement of the reference '
-                                       'tally (oracle/tally_oracle.c) on all host threads; the reference itself is '
-                                       'CPython + pysam and cannot run on this box'},
-            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        }
-        print(json.dumps(line))
-        return 0
+    config = workload_config(args, world, numa)
 
     # ---------------------------------------------------------------- workload (setup, untimed)
     batch = pipeline.SynthBatch(n_reads, seed=2001 + rank, n_barcodes=args.barcodes, device=local_rank,

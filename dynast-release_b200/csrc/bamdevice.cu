@@ -26,6 +26,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <deque>
@@ -40,7 +41,7 @@
 
 namespace {
 
-constexpr int kInfWarps = 8;          // warps per CTA of the inflate kernel (one Tables set each)
+constexpr int kInfWarps = 4;          // warps per CTA of the inflate kernel (one Tables set each)
 
 struct BlockDesc { uint32_t in_off, in_len, out_off, out_len; };
 
@@ -414,6 +415,9 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DYN_CUDA(cudaSetDevice(d->ctx->device));
     Staged *s = nullptr;
+    static const bool timing = getenv("DYN_BAM_DEV_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_enter = now();
     {
         std::unique_lock<std::mutex> l(d->mu);
         d->cv.wait(l, [&] { return !d->ready.empty() || d->finished; });
@@ -430,6 +434,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
         ~Release() { std::lock_guard<std::mutex> l(d->mu); d->free_list.push_back(s); d->cv.notify_all(); }
     } release{d, s};
     const int nb = (int)s->blocks.size();
+    auto t_staged = now();
     int rc;
     if ((rc = d->d_comp.ensure(s->len + 16))) return rc;
     if ((rc = d->d_blocks.ensure(sizeof(BlockDesc) * (size_t)nb))) return rc;
@@ -459,6 +464,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     DYN_CUDA(cudaMemcpyAsync(d->h_small, d->d_recbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaMemcpyAsync(d->h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaStreamSynchronize(stream));
+    auto t_inflated = now();
     const uint32_t n_rec = d->h_small[0];
     uint32_t status = d->h_small[1];
     auto status_error = [&](uint32_t st) -> int {
@@ -496,6 +502,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     DYN_CUDA(cudaMemcpyAsync(d->h_small + 2, d->d_scan.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaMemcpyAsync(d->h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaStreamSynchronize(stream));
+    auto t_parsed = now();
     status = d->h_small[1];
     if ((rc = status_error(status))) return rc;
     const unsigned long long tot = *reinterpret_cast<unsigned long long *>(d->h_small + 2);
@@ -530,6 +537,11 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     chunk->d_flag = uo.flag; chunk->d_gx_assigned = uo.gx_assigned;
     chunk->compressed_bytes = (int64_t)s->len;
     chunk->inflated_bytes = (int64_t)s->inflated;
+    if (timing) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "dyn_bam_dev_next: wait for the reader %.2f ms, H2D + inflate + index %.2f, parse + scan %.2f, pack %.2f  (%d blocks, %u records)\n",
+                ms(t_enter, t_staged), ms(t_staged, t_inflated), ms(t_inflated, t_parsed), ms(t_parsed, now()), nb, n_rec);
+    }
     return DYN_OK;
 }
 
