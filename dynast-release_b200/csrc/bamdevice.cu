@@ -86,16 +86,33 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *
                 const uint32_t my_pos = out_pos + incl - my_len;
                 if (lane < n && !is_match) dst[my_pos] = (uint8_t)e;
                 __syncwarp();
-                uint32_t mm = __ballot_sync(0xffffffffu, is_match);
-                while (mm) {
-                    const int i = __ffs((int)mm) - 1;
-                    mm &= mm - 1;
-                    const uint32_t ei = __shfl_sync(0xffffffffu, e, i), pi = __shfl_sync(0xffffffffu, my_pos, i);
-                    const uint32_t len = ei & 0x1ffu, dist = (ei >> 9) & 0xffffu;
-                    const uint8_t *src = dst + pi - dist;
-                    if (dist >= len) { for (uint32_t k = lane; k < len; k += 32) dst[pi + k] = src[k]; }
-                    else { for (uint32_t k = lane; k < len; k += 32) dst[pi + k] = src[k % dist]; }      // overlapping copy = a repeating pattern
+                const uint32_t all_matches = __ballot_sync(0xffffffffu, is_match);
+                if (all_matches) {
+                    // Matches are short (7 bytes on average in BAM data): a match whose source ends before the first match
+                    // output of this batch depends on nothing the other matches write, so all such matches are copied at
+                    // once, every lane walking its own match; the others (near or self-overlapping sources, long matches)
+                    // follow in stream order with the whole warp on each.
+                    const uint32_t first_pos = __shfl_sync(0xffffffffu, my_pos, __ffs((int)all_matches) - 1);
+                    const uint32_t len = e & 0x1ffu, dist = (e >> 9) & 0xffffu;
+                    const bool ready = is_match && len <= 32u && my_pos - dist + len <= first_pos;
+                    const uint32_t max_len = __reduce_max_sync(0xffffffffu, ready ? len : 0u);
+                    if (ready) {
+                        const uint8_t *src = dst + my_pos - dist;
+                        for (uint32_t k = 0; k < len; ++k) dst[my_pos + k] = src[k];
+                    }
+                    (void)max_len;
                     __syncwarp();
+                    uint32_t mm = __ballot_sync(0xffffffffu, is_match && !ready);
+                    while (mm) {
+                        const int i = __ffs((int)mm) - 1;
+                        mm &= mm - 1;
+                        const uint32_t ei = __shfl_sync(0xffffffffu, e, i), pi = __shfl_sync(0xffffffffu, my_pos, i);
+                        const uint32_t li = ei & 0x1ffu, di = (ei >> 9) & 0xffffu;
+                        const uint8_t *src = dst + pi - di;
+                        if (di >= li) { for (uint32_t k = lane; k < li; k += 32) dst[pi + k] = src[k]; }
+                        else { for (uint32_t k = lane; k < li; k += 32) dst[pi + k] = src[k % di]; }      // overlapping copy = a repeating pattern
+                        __syncwarp();
+                    }
                 }
             }
             if (phase == 2 && err == inflate::OK) {
@@ -231,7 +248,7 @@ struct dyn_bam_dev {
     // options
     bamrec::Tags tags{};
     int lean = 1;
-    size_t chunk_bytes = 256u << 20;
+    size_t chunk_bytes = 512u << 20;       // ~8 000 BGZF blocks: 1.7 waves of the inflate kernel's resident warps
     // header / file layout (host)
     std::string header_text;
     std::vector<char> ref_names;
@@ -447,7 +464,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     DYN_CUDA(cudaMemcpyAsync(d->d_blocks.p, s->blocks.data(), sizeof(BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, stream));
     // ---- k1: inflate, one warp per block
     {
-        const int ctas = std::min((nb + kInfWarps - 1) / kInfWarps, d->ctx->sm_count * 6);
+        const int ctas = std::min((nb + kInfWarps - 1) / kInfWarps, d->ctx->sm_count * 8);
         inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(d->d_comp.as<uint8_t>(), d->d_inflated.as<uint8_t>(), d->d_blocks.as<BlockDesc>(), nb,
                                                             d_small, d_small + 1);
         DYN_CUDA(cudaGetLastError());
@@ -577,7 +594,7 @@ extern "C" int dyn_inflate_blocks(dyn_ctx_t *ctx, const void *d_in, void *d_out,
     if (n_blocks == 0) return DYN_OK;
     DYN_ARG(d_in && d_out && d_block_desc && d_work && d_status, "null buffer");
     DYN_CUDA(cudaMemsetAsync(d_work, 0, 4, static_cast<cudaStream_t>(stream)));
-    const int ctas = std::min((n_blocks + kInfWarps - 1) / kInfWarps, ctx->sm_count * 6);
+    const int ctas = std::min((n_blocks + kInfWarps - 1) / kInfWarps, ctx->sm_count * 8);
     inflate_kernel<<<ctas, kInfWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t *>(d_in), static_cast<uint8_t *>(d_out),
                                                                                     reinterpret_cast<const BlockDesc *>(d_block_desc), n_blocks, d_work, d_status);
     DYN_CUDA(cudaGetLastError());

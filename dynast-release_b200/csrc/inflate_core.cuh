@@ -35,24 +35,30 @@ struct Tables {                    // per warp, in shared memory (~6.4 KB)
     uint32_t batch[kBatch];                // literal: byte; match: 1 << 31 | distance << 9 | length
 };
 
+// Bit reader: `buf` holds at least `cnt` valid bits of the stream (bits above them are a preview of the bytes that
+// follow, or of whatever lies behind the input -- the buffers are padded by 16 bytes); refill() loads 16 aligned bytes
+// and always leaves cnt >= 56, so that one Huffman symbol with its extra bits (15 + 5 + 15 + 13 = 48 bits at most)
+// never needs a check in between.  Reading past the end of the input is detected per batch from the bit position.
 struct BitReader {
-    const uint8_t *p, *end;
+    const uint8_t *p, *in, *end;
     uint64_t buf;
     int cnt;
-    bool overrun;
-    INF_HD void init(const uint8_t *in, uint32_t n) { p = in; end = in + n; buf = 0; cnt = 0; overrun = false; }
+    INF_HD void init(const uint8_t *src, uint32_t n) { p = in = src; end = src + n; buf = 0; cnt = 0; }
     INF_HD void refill() {
-        // word loads once the pointer is aligned
-        while (cnt <= 32) {
-            if ((((uintptr_t)p) & 3) == 0 && p + 4 <= end) { buf |= (uint64_t)(*reinterpret_cast<const uint32_t *>(p)) << cnt; p += 4; cnt += 32; }
-            else if (p < end) { buf |= (uint64_t)(*p++) << cnt; cnt += 8; }
-            else break;
-        }
+        const uintptr_t a = (uintptr_t)p;
+        const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+        const int sh = (int)(a & 7) * 8;
+        const uint64_t q0 = w[0], q1 = w[1];
+        const uint64_t v = sh ? ((q0 >> sh) | (q1 << (64 - sh))) : q0;
+        buf |= v << cnt;
+        const int take = (63 - cnt) >> 3;
+        p += take;
+        cnt += take * 8;
     }
     INF_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
-    INF_HD void drop(int n) { if (n > cnt) { overrun = true; n = cnt; } buf >>= n; cnt -= n; }
-    INF_HD uint32_t take(int n) { if (cnt < n) refill(); const uint32_t v = peek(n); drop(n); return v; }
-    INF_HD void align_byte() { drop(cnt & 7); }
+    INF_HD void drop(int n) { buf >>= n; cnt -= n; }
+    INF_HD uint32_t take(int n) { const uint32_t v = peek(n); drop(n); return v; }          // the caller keeps cnt >= n
+    INF_HD bool overrun() const { return (int64_t)(p - in) * 8 - cnt > (int64_t)(end - in) * 8; }
 };
 
 // RFC 1951 tables: once in constant memory for the device pass, once as plain host constants
@@ -122,7 +128,6 @@ INF_HD bool build(const uint8_t *lens, int n_sym, uint32_t *lut, int bits, uint1
 
 // one symbol in its resolved form (see Tables); `bits` = lookup width.  Returns ~0 on an invalid code.
 INF_HD uint32_t decode(BitReader &br, const uint32_t *lut, int bits, const uint16_t *count, const uint16_t *sorted, int kind) {
-    if (br.cnt < 15) br.refill();
     const uint32_t e = lut[br.peek(bits)];
     if (e & 15) { br.drop((int)(e & 15)); return e; }
     // code longer than the table: canonical walk, one bit at a time
@@ -155,10 +160,11 @@ INF_HD void state_init(State &s, const uint8_t *in, uint32_t in_len, uint32_t ou
 // Reads a block header and builds the tables of a Huffman block.
 INF_HD void begin_block(State &s, Tables &t) {
     BitReader &br = s.br;
+    br.refill();
     s.last = br.take(1) != 0;
     const uint32_t type = br.take(2);
     if (type == 0) {
-        br.align_byte();
+        br.drop(br.cnt & 7);              // to the next byte boundary
         // the bit buffer holds whole bytes now: put them back
         br.p -= br.cnt >> 3; br.buf = 0; br.cnt = 0;
         if (br.p + 4 > br.end) { s.err = ERR_INPUT; return; }
@@ -186,13 +192,14 @@ INF_HD void begin_block(State &s, Tables &t) {
         if (n_lit > 286 || n_dist > 30) { s.err = ERR_DATA; return; }
         uint8_t *cl = t.lens + 300;        // 19 scratch bytes behind the distance lengths
         for (int i = 0; i < 19; ++i) cl[i] = 0;
-        for (int i = 0; i < n_code; ++i) cl[INF_K(cl_order)[i]] = (uint8_t)br.take(3);
+        for (int i = 0; i < n_code; ++i) { if (br.cnt < 8) br.refill(); cl[INF_K(cl_order)[i]] = (uint8_t)br.take(3); }
         // the code-length code borrows the distance tables (7-bit lookup)
         if (!build(cl, 19, t.dist_lut, 7, t.dist_count, t.dist_sorted, KIND_CL)) { s.err = ERR_DATA; return; }
         int i = 0;
         while (i < n_lit + n_dist) {
+            if (br.cnt < 32) br.refill();
             const uint32_t e = decode(br, t.dist_lut, 7, t.dist_count, t.dist_sorted, KIND_CL);
-            if (e == ~0u || br.overrun) { s.err = ERR_DATA; return; }
+            if (e == ~0u || br.overrun()) { s.err = ERR_DATA; return; }
             const int sym = (int)(e >> 16);
             if (sym < 16) { t.lens[i++] = (uint8_t)sym; continue; }
             int rep, val = 0;
@@ -220,6 +227,7 @@ INF_HD int decode_batch(State &s, Tables &t, uint32_t *bytes) {
     uint32_t produced = 0;
     const uint32_t room = s.out_len - s.out_pos;
     while (n < kBatch) {
+        if (br.cnt < 48) br.refill();
         const uint32_t e = decode(br, t.lit_lut, kLitBits, t.lit_count, t.lit_sorted, KIND_LIT);
         const uint32_t kind = (e >> 4) & 3;
         if (kind == 1) {
@@ -239,7 +247,7 @@ INF_HD int decode_batch(State &s, Tables &t, uint32_t *bytes) {
         t.batch[n++] = (1u << 31) | (dist << 9) | len;
         produced += len;
     }
-    if (br.overrun && s.err == OK) s.err = ERR_INPUT;
+    if (s.err == OK && br.overrun()) s.err = ERR_INPUT;
     *bytes = produced;
     return n;
 }

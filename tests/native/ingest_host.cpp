@@ -30,15 +30,30 @@ extern "C" int host_inflate(const uint8_t *in, uint32_t in_len, uint8_t *dst, ui
                 acc += len[lane];
             }
             for (int lane = 0; lane < n; ++lane) if (!(t.batch[lane] >> 31)) dst[pos[lane]] = (uint8_t)t.batch[lane];
-            for (int i = 0; i < n; ++i) {
-                const uint32_t e = t.batch[i];
-                if (!(e >> 31)) continue;
-                const uint32_t l = e & 0x1ffu, dist = (e >> 9) & 0xffffu;
-                const uint8_t *src = dst + pos[i] - dist;
-                std::vector<uint8_t> tmp(l);
-                for (int lane = 0; lane < 32; ++lane)                 // every lane reads before any lane's write is needed
-                    for (uint32_t k = lane; k < l; k += 32) tmp[k] = dist >= l ? src[k] : src[k % dist];
-                memcpy(dst + pos[i], tmp.data(), l);
+            // the kernel's two match phases: "ready" matches (source ends before the first match output of the batch, at
+            // most 32 bytes) all at once -- played here in REVERSE lane order, which is only right if they really are
+            // independent of one another --, then the rest in stream order
+            int first = -1;
+            for (int lane = 0; lane < n; ++lane) if (t.batch[lane] >> 31) { first = lane; break; }
+            bool ready[32] = {false};
+            if (first >= 0) {
+                for (int lane = n - 1; lane >= 0; --lane) {
+                    const uint32_t e = t.batch[lane];
+                    if (!(e >> 31)) continue;
+                    const uint32_t l = e & 0x1ffu, dist = (e >> 9) & 0xffffu;
+                    ready[lane] = l <= 32u && pos[lane] - dist + l <= pos[first];
+                    if (ready[lane]) for (uint32_t k = 0; k < l; ++k) dst[pos[lane] + k] = dst[pos[lane] - dist + k];
+                }
+                for (int i = 0; i < n; ++i) {
+                    const uint32_t e = t.batch[i];
+                    if (!(e >> 31) || ready[i]) continue;
+                    const uint32_t l = e & 0x1ffu, dist = (e >> 9) & 0xffffu;
+                    const uint8_t *src = dst + pos[i] - dist;
+                    std::vector<uint8_t> tmp(l);
+                    for (int lane = 0; lane < 32; ++lane)                 // every lane reads before any lane's write is needed
+                        for (uint32_t k = lane; k < l; k += 32) tmp[k] = dist >= l ? src[k] : src[k % dist];
+                    memcpy(dst + pos[i], tmp.data(), l);
+                }
             }
         }
         if (phase == 2 && err == inflate::OK) {
