@@ -239,6 +239,22 @@ struct Staged {          // one run of BGZF blocks, compressed, in page-locked m
     bool last = false;
 };
 
+// Everything that is expensive to create (device buffers of several hundred MB, page-locked staging memory): a closed
+// reader parks its set in the context, the next one on that context picks it up (cudaMalloc / cudaHostAlloc of these
+// sizes take a few hundred milliseconds).
+struct IngestBuffers {
+    Staged staged[3];
+    DevBuf d_comp, d_blocks, d_inflated, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
+    struct OutSet { DevBuf blob, rec_off, bc, umi, gene, score, ref_id, pos, hi, flag, gxa; } out[2];
+    uint32_t *h_small = nullptr;          // page-locked landing zone
+    ~IngestBuffers() {
+        for (Staged &s : staged) if (s.bytes) cudaFreeHost(s.bytes);
+        if (h_small) cudaFreeHost(h_small);
+    }
+};
+
+void free_ingest_buffers(void *p) { delete static_cast<IngestBuffers *>(p); }
+
 }  // namespace
 
 struct dyn_bam_dev {
@@ -269,12 +285,8 @@ struct dyn_bam_dev {
     bool finished = false, stop = false;
     int err = 0;
     std::string err_msg;
-    Staged staged[3];
-    // device buffers: shared intermediates + two sets of outputs
-    DevBuf d_comp, d_blocks, d_inflated, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
-    struct OutSet { DevBuf blob, rec_off, bc, umi, gene, score, ref_id, pos, hi, flag, gxa; } out[2];
+    IngestBuffers *buf = nullptr;         // shared intermediates + two sets of outputs + staging
     int cur = 0;
-    uint32_t *h_small = nullptr;          // page-locked landing zone
     cudaEvent_t ev_copy = nullptr;
     int64_t records_seen = 0;
 
@@ -285,8 +297,12 @@ struct dyn_bam_dev {
         }
         cv.notify_all();
         if (reader.joinable()) reader.join();
-        for (Staged &s : staged) if (s.bytes) cudaFreeHost(s.bytes);
-        if (h_small) cudaFreeHost(h_small);
+        if (buf) {
+            cudaDeviceSynchronize();      // nothing may still read the buffers when the next reader takes them
+            std::lock_guard<std::recursive_mutex> l(ctx->mu);
+            if (!ctx->ingest_cache) { ctx->ingest_cache = buf; ctx->ingest_cache_free = free_ingest_buffers; }
+            else delete buf;
+        }
         if (ev_copy) cudaEventDestroy(ev_copy);
         if (fd >= 0) close(fd);
     }
@@ -415,10 +431,12 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
     }
     d->fd = open(path, O_RDONLY);
     if (d->fd < 0) { dyn_set_error("dyn_bam_dev_open: cannot open %s", path); return DYN_ERR_IO; }
-    DYN_CUDA(cudaHostAlloc((void **)&d->h_small, 256, cudaHostAllocDefault));
+    if (ctx->ingest_cache) { d->buf = static_cast<IngestBuffers *>(ctx->ingest_cache); ctx->ingest_cache = nullptr; }
+    else d->buf = new IngestBuffers();
+    if (!d->buf->h_small) DYN_CUDA(cudaHostAlloc((void **)&d->buf->h_small, 256, cudaHostAllocDefault));
     DYN_CUDA(cudaEventCreateWithFlags(&d->ev_copy, cudaEventDisableTiming));
-    if ((rc = d->d_small.ensure(256))) return rc;
-    for (Staged &s : d->staged) d->free_list.push_back(&s);
+    if ((rc = d->buf->d_small.ensure(256))) return rc;
+    for (Staged &s : d->buf->staged) d->free_list.push_back(&s);
     dyn_bam_dev *dp = d.release();
     dp->reader = std::thread(read_ahead, dp);
     *out = dp;
@@ -431,6 +449,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     CtxEnter enter_(d->ctx, stream_, false);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DYN_CUDA(cudaSetDevice(d->ctx->device));
+    IngestBuffers &B = *d->buf;
     Staged *s = nullptr;
     static const bool timing = getenv("DYN_BAM_DEV_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -453,37 +472,37 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     const int nb = (int)s->blocks.size();
     auto t_staged = now();
     int rc;
-    if ((rc = d->d_comp.ensure(s->len + 16))) return rc;
-    if ((rc = d->d_blocks.ensure(sizeof(BlockDesc) * (size_t)nb))) return rc;
-    if ((rc = d->d_inflated.ensure(s->inflated + 16))) return rc;
-    if ((rc = d->d_nrec.ensure(4 * (size_t)(nb + 1)))) return rc;
-    if ((rc = d->d_recbase.ensure(4 * (size_t)(nb + 1)))) return rc;
-    uint32_t *d_small = d->d_small.as<uint32_t>();      // [0] inflate work counter, [1] status, [2..3] scan totals
+    if ((rc = B.d_comp.ensure(s->len + 16))) return rc;
+    if ((rc = B.d_blocks.ensure(sizeof(BlockDesc) * (size_t)nb))) return rc;
+    if ((rc = B.d_inflated.ensure(s->inflated + 16))) return rc;
+    if ((rc = B.d_nrec.ensure(4 * (size_t)(nb + 1)))) return rc;
+    if ((rc = B.d_recbase.ensure(4 * (size_t)(nb + 1)))) return rc;
+    uint32_t *d_small = B.d_small.as<uint32_t>();      // [0] inflate work counter, [1] status, [2..3] scan totals
     DYN_CUDA(cudaMemsetAsync(d_small, 0, 64, stream));
-    DYN_CUDA(cudaMemcpyAsync(d->d_comp.p, s->bytes, s->len, cudaMemcpyHostToDevice, stream));
-    DYN_CUDA(cudaMemcpyAsync(d->d_blocks.p, s->blocks.data(), sizeof(BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, stream));
+    DYN_CUDA(cudaMemcpyAsync(B.d_comp.p, s->bytes, s->len, cudaMemcpyHostToDevice, stream));
+    DYN_CUDA(cudaMemcpyAsync(B.d_blocks.p, s->blocks.data(), sizeof(BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, stream));
     // ---- k1: inflate, one warp per block
     {
         const int ctas = std::min((nb + kInfWarps - 1) / kInfWarps, d->ctx->sm_count * 8);
-        inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(d->d_comp.as<uint8_t>(), d->d_inflated.as<uint8_t>(), d->d_blocks.as<BlockDesc>(), nb,
+        inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(B.d_comp.as<uint8_t>(), B.d_inflated.as<uint8_t>(), B.d_blocks.as<BlockDesc>(), nb,
                                                             d_small, d_small + 1);
         DYN_CUDA(cudaGetLastError());
     }
     // ---- k2: records per block, their prefix sum, the total
-    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_blocks.as<BlockDesc>(), nb, s->first_skip,
-                                                       d->d_nrec.as<uint32_t>(), nullptr, nullptr, d_small + 1);
+    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks.as<BlockDesc>(), nb, s->first_skip,
+                                                       B.d_nrec.as<uint32_t>(), nullptr, nullptr, d_small + 1);
     DYN_CUDA(cudaGetLastError());
-    DYN_CUDA(cudaMemsetAsync(d->d_nrec.as<uint32_t>() + nb, 0, 4, stream));
+    DYN_CUDA(cudaMemsetAsync(B.d_nrec.as<uint32_t>() + nb, 0, 4, stream));
     size_t tmp_bytes = 0;
-    DYN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d->d_nrec.as<uint32_t>(), d->d_recbase.as<uint32_t>(), nb + 1, stream));
-    if ((rc = d->d_tmp.ensure(tmp_bytes))) return rc;
-    DYN_CUDA(cub::DeviceScan::ExclusiveSum(d->d_tmp.p, tmp_bytes, d->d_nrec.as<uint32_t>(), d->d_recbase.as<uint32_t>(), nb + 1, stream));
-    DYN_CUDA(cudaMemcpyAsync(d->h_small, d->d_recbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, stream));
-    DYN_CUDA(cudaMemcpyAsync(d->h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, B.d_nrec.as<uint32_t>(), B.d_recbase.as<uint32_t>(), nb + 1, stream));
+    if ((rc = B.d_tmp.ensure(tmp_bytes))) return rc;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(B.d_tmp.p, tmp_bytes, B.d_nrec.as<uint32_t>(), B.d_recbase.as<uint32_t>(), nb + 1, stream));
+    DYN_CUDA(cudaMemcpyAsync(B.h_small, B.d_recbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaMemcpyAsync(B.h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaStreamSynchronize(stream));
     auto t_inflated = now();
-    const uint32_t n_rec = d->h_small[0];
-    uint32_t status = d->h_small[1];
+    const uint32_t n_rec = B.h_small[0];
+    uint32_t status = B.h_small[1];
     auto status_error = [&](uint32_t st) -> int {
         if (st & 0xeu) { dyn_set_error("dyn_bam_dev: inflate failed (corrupt BGZF block, status 0x%x)", st); return DYN_ERR_FORMAT; }
         if (st & (1u << 8)) { dyn_set_error("dyn_bam_dev: alignment records straddle BGZF blocks: use the host reader (dyn_bam_stream_*)"); return DYN_ERR_FORMAT; }
@@ -498,31 +517,31 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     d->records_seen += n_rec;
     chunk->n_records_seen = n_rec;
     chunk->end = s->last ? 1 : 0;
-    dyn_bam_dev::OutSet &os = d->out[d->cur];
+    IngestBuffers::OutSet &os = B.out[d->cur];
     d->cur ^= 1;
     if (n_rec == 0) return DYN_OK;
     // ---- k2 (positions), k3 (parse), scan
-    if ((rc = d->d_recat.ensure(4 * (size_t)n_rec))) return rc;
-    if ((rc = d->d_parsed.ensure(sizeof(bamrec::Parsed) * (size_t)n_rec))) return rc;
-    if ((rc = d->d_scan_in.ensure(8 * (size_t)(n_rec + 1)))) return rc;
-    if ((rc = d->d_scan.ensure(8 * (size_t)(n_rec + 1)))) return rc;
-    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_blocks.as<BlockDesc>(), nb, s->first_skip,
-                                                       nullptr, d->d_recbase.as<uint32_t>(), d->d_recat.as<uint32_t>(), d_small + 1);
+    if ((rc = B.d_recat.ensure(4 * (size_t)n_rec))) return rc;
+    if ((rc = B.d_parsed.ensure(sizeof(bamrec::Parsed) * (size_t)n_rec))) return rc;
+    if ((rc = B.d_scan_in.ensure(8 * (size_t)(n_rec + 1)))) return rc;
+    if ((rc = B.d_scan.ensure(8 * (size_t)(n_rec + 1)))) return rc;
+    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks.as<BlockDesc>(), nb, s->first_skip,
+                                                       nullptr, B.d_recbase.as<uint32_t>(), B.d_recat.as<uint32_t>(), d_small + 1);
     DYN_CUDA(cudaGetLastError());
-    parse_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_recat.as<uint32_t>(), n_rec, d->tags,
-                                                          d->d_parsed.as<bamrec::Parsed>(), d->d_scan_in.as<unsigned long long>(), d_small + 1);
+    parse_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_recat.as<uint32_t>(), n_rec, d->tags,
+                                                          B.d_parsed.as<bamrec::Parsed>(), B.d_scan_in.as<unsigned long long>(), d_small + 1);
     DYN_CUDA(cudaGetLastError());
-    DYN_CUDA(cudaMemsetAsync(d->d_scan_in.as<unsigned long long>() + n_rec, 0, 8, stream));
-    DYN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d->d_scan_in.as<unsigned long long>(), d->d_scan.as<unsigned long long>(), (int)(n_rec + 1), stream));
-    if ((rc = d->d_tmp.ensure(tmp_bytes))) return rc;
-    DYN_CUDA(cub::DeviceScan::ExclusiveSum(d->d_tmp.p, tmp_bytes, d->d_scan_in.as<unsigned long long>(), d->d_scan.as<unsigned long long>(), (int)(n_rec + 1), stream));
-    DYN_CUDA(cudaMemcpyAsync(d->h_small + 2, d->d_scan.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, stream));
-    DYN_CUDA(cudaMemcpyAsync(d->h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaMemsetAsync(B.d_scan_in.as<unsigned long long>() + n_rec, 0, 8, stream));
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, B.d_scan_in.as<unsigned long long>(), B.d_scan.as<unsigned long long>(), (int)(n_rec + 1), stream));
+    if ((rc = B.d_tmp.ensure(tmp_bytes))) return rc;
+    DYN_CUDA(cub::DeviceScan::ExclusiveSum(B.d_tmp.p, tmp_bytes, B.d_scan_in.as<unsigned long long>(), B.d_scan.as<unsigned long long>(), (int)(n_rec + 1), stream));
+    DYN_CUDA(cudaMemcpyAsync(B.h_small + 2, B.d_scan.as<unsigned long long>() + n_rec, 8, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaMemcpyAsync(B.h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaStreamSynchronize(stream));
     auto t_parsed = now();
-    status = d->h_small[1];
+    status = B.h_small[1];
     if ((rc = status_error(status))) return rc;
-    const unsigned long long tot = *reinterpret_cast<unsigned long long *>(d->h_small + 2);
+    const unsigned long long tot = *reinterpret_cast<unsigned long long *>(B.h_small + 2);
     const uint32_t n_units = (uint32_t)(tot >> 40);
     const unsigned long long total16 = tot & ((1ull << 40) - 1);
     if (total16 > 0xfffffff0ull) { dyn_set_error("dyn_bam_dev: chunk over 64 GiB of packed records"); return DYN_ERR_NOMEM; }
@@ -538,8 +557,8 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     uo.gene_idx = os.gene.as<int32_t>(); uo.score = os.score.as<int32_t>(); uo.ref_id = os.ref_id.as<int32_t>();
     uo.pos = os.pos.as<int32_t>(); uo.hi = os.hi.as<int32_t>(); uo.flag = os.flag.as<uint16_t>(); uo.gx_assigned = os.gxa.as<uint8_t>();
     if (n_units) {
-        pack_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(d->d_inflated.as<uint8_t>(), d->d_recat.as<uint32_t>(), n_rec, d->d_parsed.as<bamrec::Parsed>(),
-                                                             d->d_scan.as<unsigned long long>(), d->lean, d->gene_hash.as<unsigned long long>(),
+        pack_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_recat.as<uint32_t>(), n_rec, B.d_parsed.as<bamrec::Parsed>(),
+                                                             B.d_scan.as<unsigned long long>(), d->lean, d->gene_hash.as<unsigned long long>(),
                                                              d->gene_of_hash.as<int32_t>(), d->n_gene_hash, uo);
         DYN_CUDA(cudaGetLastError());
     }

@@ -56,6 +56,7 @@ extern "C" int dyn_ctx_destroy(dyn_ctx_t *ctx) {
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
     if (ctx->slot_ev) cudaEventDestroy(ctx->slot_ev);
+    if (ctx->ingest_cache && ctx->ingest_cache_free) ctx->ingest_cache_free(ctx->ingest_cache);
     delete ctx;
     return DYN_OK;
 }

@@ -50,6 +50,8 @@ struct dyn_ctx {
     cudaStream_t slot_stream[kScratchSlots];
     bool slot_used[kScratchSlots];
     cudaEvent_t slot_ev;
+    void *ingest_cache;                      // parked buffers of the device BAM ingest (bamdevice.cu)
+    void (*ingest_cache_free)(void *);
 };
 
 // Entered at the top of every C-ABI call that takes a context: serialises host threads on the context and tells

@@ -37,8 +37,9 @@ struct Tables {                    // per warp, in shared memory (~6.4 KB)
 
 // Bit reader: `buf` holds at least `cnt` valid bits of the stream (bits above them are a preview of the bytes that
 // follow, or of whatever lies behind the input -- the buffers are padded by 16 bytes); refill() loads 16 aligned bytes
-// and always leaves cnt >= 56, so that one Huffman symbol with its extra bits (15 + 5 + 15 + 13 = 48 bits at most)
-// never needs a check in between.  Reading past the end of the input is detected per batch from the bit position.
+// and always leaves cnt >= 56: one check in front of a literal / length symbol (20 bits at most) and one in front of
+// a distance (28 bits) are all the decode loop needs.  Reading past the end of the input is detected per batch from
+// the bit position.
 struct BitReader {
     const uint8_t *p, *in, *end;
     uint64_t buf;
@@ -227,7 +228,7 @@ INF_HD int decode_batch(State &s, Tables &t, uint32_t *bytes) {
     uint32_t produced = 0;
     const uint32_t room = s.out_len - s.out_pos;
     while (n < kBatch) {
-        if (br.cnt < 48) br.refill();
+        if (br.cnt < 20) br.refill();          // a literal / length code (<= 15 bits) and the length's extra bits (<= 5)
         const uint32_t e = decode(br, t.lit_lut, kLitBits, t.lit_count, t.lit_sorted, KIND_LIT);
         const uint32_t kind = (e >> 4) & 3;
         if (kind == 1) {
@@ -239,6 +240,7 @@ INF_HD int decode_batch(State &s, Tables &t, uint32_t *bytes) {
         if (e == ~0u) { s.err = ERR_DATA; break; }
         if (kind == 3) { s.phase = s.last ? 3 : 0; break; }
         const uint32_t len = (e >> 16) + br.take((int)((e >> 8) & 15));
+        if (br.cnt < 28) br.refill();          // a distance code (<= 15 bits) and its extra bits (<= 13)
         const uint32_t d = decode(br, t.dist_lut, kDistBits, t.dist_count, t.dist_sorted, KIND_DIST);
         if (d == ~0u) { s.err = ERR_DATA; break; }
         const uint32_t dist = (d >> 16) + br.take((int)((d >> 8) & 15));
