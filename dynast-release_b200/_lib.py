@@ -49,6 +49,8 @@ PROTOTYPES = {
     'dyn_unpack_reads': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_merge_kn': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     'dyn_bam_pack': (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
+    'dyn_bam_pack_ex': (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, _u32, C.POINTER(_vp)]),
+    'dyn_bam_peek': (_i32, [C.c_char_p, _i64, _vp, _i32, _vp, _vp, _vp]),
     'dyn_bam_result_free': (None, [_vp]),
     'dyn_bam_n_units': (_i64, [_vp]),
     'dyn_bam_n_records_seen': (_i64, [_vp]),
@@ -65,6 +67,7 @@ PROTOTYPES = {
     'dyn_bam_dev_n_refs': (_i64, [_vp]),
     'dyn_bam_dev_field': (_vp, [_vp, _i32, C.POINTER(_i64)]),
     'dyn_inflate_blocks': (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    'dyn_bam_write_ex': (_i32, [C.c_char_p, _vp]),
     'dyn_bam_write': (_i32, [C.c_char_p, C.c_char_p, _i32, C.POINTER(C.c_char_p), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _i32, _i32, _i32]),
     'dyn_synth_offsets': (_i32, [_vp, _vp, _i64, _vp, _vp]),
@@ -142,6 +145,16 @@ class BamStreamOpts(C.Structure):
     _fields_ = [('barcode_tag', C.c_char_p), ('umi_tag', C.c_char_p), ('gene_tag', C.c_char_p), ('require_gene', C.c_int32),
                 ('n_threads', C.c_int32), ('part', C.c_int32), ('n_parts', C.c_int32), ('chunk_bytes', C.c_int64),
                 ('lean', C.c_int32), ('keys', C.c_int32), ('gene_ids', C.POINTER(C.c_char_p)), ('n_gene_ids', C.c_int64)]
+
+
+class BamWriteOpts(C.Structure):
+    """dyn_bam_write_opts_t"""
+    _fields_ = [('header_text', C.c_char_p), ('n_ref', C.c_int32), ('ref_names', C.POINTER(C.c_char_p)), ('ref_lens', C.c_void_p),
+                ('h_records', C.c_void_p), ('h_rec_off', C.c_void_p), ('n_units', C.c_int64), ('h_order', C.c_void_p),
+                ('h_names', C.c_void_p), ('h_name_off', C.c_void_p), ('h_aux', C.c_void_p), ('h_aux_off', C.c_void_p),
+                ('h_mapq', C.c_void_p), ('h_flag', C.c_void_p), ('level', C.c_int32), ('n_threads', C.c_int32),
+                ('write_index', C.c_int32), ('reserved', C.c_int32), ('h_raw', C.c_void_p), ('h_raw_start', C.c_void_p),
+                ('h_raw_len', C.c_void_p), ('h_retag', C.c_void_p), ('h_retag_off', C.c_void_p), ('gene_tag', C.c_char_p)]
 
 
 class BamDevChunk(C.Structure):

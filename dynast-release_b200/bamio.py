@@ -10,7 +10,9 @@ from . import _lib
 _FIELDS = {'blob': (0, np.uint8), 'rec_off': (1, np.uint32), 'ref_id': (2, np.int32), 'pos': (3, np.int32),
            'flag': (4, np.uint16), 'hi': (5, np.int32), 'score': (6, np.int32), 'gx_assigned': (7, np.uint8),
            'paired': (8, np.uint8), 'ref_len': (9, np.int32)}
-_FIELDS.update({'barcode_key': (11, np.uint64), 'umi_key': (12, np.uint64), 'gene_idx': (13, np.int32)})
+_FIELDS.update({'barcode_key': (11, np.uint64), 'umi_key': (12, np.uint64), 'gene_idx': (13, np.int32), 'rec_index': (14, np.int64),
+                'raw': (30, np.uint8), 'raw_off': (31, np.uint32), 'raw_mate': (32, np.uint8), 'raw_mate_off': (33, np.uint32)})
+KEEP_RAW, KEEP_DUPLICATES = 0x1, 0x2
 _POOLS = {'read_id': (20, 21), 'barcode': (22, 23), 'umi': (24, 25), 'gene': (26, 27), 'ref_name': (28, 29)}
 
 
@@ -19,12 +21,12 @@ class PackedBam:
     string fields are decoded on demand."""
 
     def __init__(self, path: str, barcode_tag: Optional[str] = None, umi_tag: Optional[str] = None,
-                 gene_tag: Optional[str] = 'GX', require_gene: bool = False, n_threads: int = 8):
+                 gene_tag: Optional[str] = 'GX', require_gene: bool = False, n_threads: int = 8, flags: int = 0):
         self.lib = _lib.load()
         h = C.c_void_p()
         enc = lambda s: s.encode() if s else None
-        _lib.check(self.lib.dyn_bam_pack(path.encode(), enc(barcode_tag), enc(umi_tag), enc(gene_tag), int(require_gene),
-                                         int(n_threads), C.byref(h)))
+        _lib.check(self.lib.dyn_bam_pack_ex(path.encode(), enc(barcode_tag), enc(umi_tag), enc(gene_tag), int(require_gene),
+                                            int(n_threads), int(flags), C.byref(h)))
         self._adopt(h)
 
     def _adopt(self, h):
@@ -163,11 +165,25 @@ class BamStream:
         self.close()
 
 
+def peek(path: str, max_records: int = 500000):
+    """dyn_bam_peek: (set of aux tags, OR of the flags, records looked at) of the first records -- what
+    bam.get_tags_from_bam / check_bam_* (bam.py:447-570) learn about a BAM."""
+    lib = _lib.load()
+    buf = C.create_string_buffer(2 * 4096)
+    n_tags, flag_or, n_seen = C.c_int32(0), C.c_uint32(0), C.c_int64(0)
+    _lib.check(lib.dyn_bam_peek(path.encode(), int(max_records), buf, len(buf), C.byref(n_tags), C.byref(flag_or), C.byref(n_seen)))
+    raw = buf.raw[:2 * min(n_tags.value, 4096)]
+    return {raw[i:i + 2].decode() for i in range(0, len(raw), 2)}, int(flag_or.value), int(n_seen.value)
+
+
 def write_bam(path: str, refs, blob: np.ndarray, rec_off: np.ndarray, order=None, names=None, aux=None, mapq=None, flag=None,
-              header_text: Optional[str] = None, level: int = 6, n_threads: int = 8, index: bool = True):
-    """dyn_bam_write: packed records (full layout, no mates) -> a BAM file (+ .bai).  refs: [(name, length)];
+              header_text: Optional[str] = None, level: int = 6, n_threads: int = 8, index: bool = True, raw=None, raw_start=None,
+              raw_len=None, retag=None, gene_tag: Optional[str] = None):
+    """dyn_bam_write(_ex): packed records (full layout, no mates) -> a BAM file (+ .bai).  refs: [(name, length)];
     names: list of str or None ("r<i>"); aux: list of bytes (pre-encoded tags) or a (bytes, uint32 offsets) pair;
-    order: unit order in the file (coordinate order for a sorted BAM)."""
+    order: unit order in the file (coordinate order for a sorted BAM).  raw / raw_start / raw_len: units written from
+    BAM alignment records as they are (raw_len[u] > 0); retag: (bytes, uint32 offsets) of "gene\0name\0" per unit whose
+    gene tags are swapped first (swap_gene_tags, consensus.py:277-286)."""
     lib = _lib.load()
     n = len(rec_off) - 1
     if header_text is None:
@@ -193,9 +209,24 @@ def write_bam(path: str, refs, blob: np.ndarray, rec_off: np.ndarray, order=None
     mapq = None if mapq is None else np.ascontiguousarray(mapq, dtype=np.uint8)
     flag = None if flag is None else np.ascontiguousarray(flag, dtype=np.uint16)
     p = _lib.ptr
-    _lib.check(lib.dyn_bam_write(path.encode(), header_text.encode(), len(refs), C.cast(ref_names, C.POINTER(C.c_char_p)),
-                                 p(ref_lens), p(blob), p(rec_off), n, p(order), p(n_data), p(n_off), p(a_data), p(a_off), p(mapq),
-                                 p(flag), int(level), int(n_threads), int(bool(index))))
+    o = _lib.BamWriteOpts(header_text=header_text.encode(), n_ref=len(refs), ref_names=C.cast(ref_names, C.POINTER(C.c_char_p)),
+                          ref_lens=p(ref_lens), h_records=p(blob) if blob.size else None, h_rec_off=p(rec_off), n_units=n, h_order=p(order),
+                          h_names=p(n_data), h_name_off=p(n_off), h_aux=p(a_data), h_aux_off=p(a_off), h_mapq=p(mapq), h_flag=p(flag),
+                          level=int(level), n_threads=int(n_threads), write_index=int(bool(index)))
+    keep = [ref_names, ref_lens, blob, rec_off, order, n_data, n_off, a_data, a_off, mapq, flag]
+    if raw is not None:
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        raw_start = np.ascontiguousarray(raw_start, dtype=np.uint64)
+        raw_len = np.ascontiguousarray(raw_len, dtype=np.uint32)
+        o.h_raw, o.h_raw_start, o.h_raw_len = p(raw), p(raw_start), p(raw_len)
+        keep += [raw, raw_start, raw_len]
+    if retag is not None:
+        r_data, r_off = pool(retag)
+        o.h_retag, o.h_retag_off = p(r_data), p(r_off)
+        o.gene_tag = gene_tag.encode() if gene_tag else None
+        keep += [r_data, r_off]
+    _lib.check(lib.dyn_bam_write_ex(path.encode(), C.byref(o)))
+    del keep
     return path
 
 

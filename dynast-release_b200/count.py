@@ -66,6 +66,10 @@ def count(
     stats_path = os.path.join(out_dir, f'{constants.STATS_PREFIX}_{dt.datetime.strftime(start, "%Y%m%d_%H%M%S_%f")}.json')
     all_conversions = sorted(utils.flatten_iter(conversions))
 
+    # ---- BAM tags and alignment checks (count.py:91-135)
+    from .preprocessing import bam as bam_ops
+    tags = bam_ops.check_bam_tags(bam_path, umi_tag=umi_tag, barcode_tag=barcode_tag, gene_tag=gene_tag, n_threads=n_threads)
+
     # ---- parse BAM (count.py:138-171): skipped when the outputs exist and not --overwrite
     conversions_path = os.path.join(out_dir, constants.CONVERSIONS_FILENAME)
     index_path = os.path.join(out_dir, constants.CONVERSIONS_INDEX_FILENAME)
@@ -124,8 +128,9 @@ def count(
         for conv, by_contig in part.items():
             for contig, pos in by_contig.items():
                 snps.setdefault(conv, {}).setdefault(contig, set()).update(pos)
-    if umi_tag and dedup_mode == 'auto':
-        dedup_mode = 'exon' if consensus_bam else 'conversion'      # count.py:295-304 (RN tag present -> exon)
+    if umi_tag and dedup_mode == 'auto':      # count.py:295-304: a BAM of consensus reads (RN tag) prioritises exonic reads
+        is_consensus = (constants.BAM_CONSENSUS_READ_COUNT_TAG in tags) if consensus_bam is None else consensus_bam
+        dedup_mode = 'exon' if is_consensus else 'conversion'
     counts_path = preprocessing.count_conversions(
         conversions_path, alignments_path, index_path, counts_path, gene_infos, barcodes=barcodes, snps=snps, quality=quality,
         conversions=all_conversions, dedup_use_conversions=dedup_mode == 'conversion', n_threads=n_threads, temp_dir=temp_dir)

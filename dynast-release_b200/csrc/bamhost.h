@@ -113,6 +113,8 @@ struct dyn_bam_result {
     bamhost::Pool ref_name;
     std::vector<int32_t> ref_len;
     int64_t n_records_seen = 0;
+    std::vector<int64_t> rec_index;     // ordinal of the unit's (second-seen) record among all records of the file
+    bamhost::Pool raw, raw_mate;        // DYN_BAM_KEEP_RAW: the units' BAM alignment records as they are in the file
     void *extra = nullptr;          // stream chunks: dyn_bam_chunk_extra (bamstream.cpp)
 };
 

@@ -41,7 +41,14 @@ using namespace bamhost;
 
 extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const char *umi_tag, const char *gene_tag,
                             int require_gene, int n_threads, dyn_bam_result_t **out_result) {
+    return dyn_bam_pack_ex(path, barcode_tag, umi_tag, gene_tag, require_gene, n_threads, 0u, out_result);
+}
+
+extern "C" int dyn_bam_pack_ex(const char *path, const char *barcode_tag, const char *umi_tag, const char *gene_tag,
+                               int require_gene, int n_threads, uint32_t flags, dyn_bam_result_t **out_result) {
     if (!path || !out_result) { dyn_set_error("dyn_bam_pack: null argument"); return DYN_ERR_ARG; }
+    const bool keep_raw = (flags & DYN_BAM_KEEP_RAW) != 0;
+    const uint32_t skip_flags = 0x100u | 0x4u | ((flags & DYN_BAM_KEEP_DUPLICATES) ? 0u : 0x400u);
     if (barcode_tag && !barcode_tag[0]) barcode_tag = nullptr;
     if (umi_tag && !umi_tag[0]) umi_tag = nullptr;
     if (gene_tag && !gene_tag[0]) gene_tag = nullptr;
@@ -266,7 +273,8 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
                 std::vector<int32_t> ref_id, pos, hi, score;
                 std::vector<uint16_t> flag;
                 std::vector<uint8_t> gx_assigned;
-                Pool name, barcode, umi, gene;
+                Pool name, barcode, umi, gene, raw;
+                std::vector<int64_t> rec_index;
                 std::string error;
                 int err_code = 0;
             };
@@ -291,7 +299,7 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
                         const uint32_t l_read_name = rec[8], n_cigar = rd16(rec + 12), l_seq = rd32(rec + 16);
                         const uint16_t flag = rd16(rec + 14);
                         if (ref_id < 0) continue;
-                        if (flag & (0x100 | 0x4 | 0x400)) continue;
+                        if (flag & skip_flags) continue;
                         const size_t fixed = 32 + l_read_name + 4 * (size_t)n_cigar + (l_seq + 1) / 2 + l_seq;
                         if (fixed > block_size) { fail(pt, DYN_ERR_FORMAT, "dyn_bam_pack: corrupt record"); return; }
                         Aux a;
@@ -313,6 +321,8 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
                         pt.barcode.add(a.has_bc ? a.bc : "NA", a.has_bc ? a.bc_len : 2);
                         pt.umi.add(a.has_umi ? a.umi : "NA", a.has_umi ? a.umi_len : 2);
                         pt.gene.add(a.has_gx ? a.gx : "", a.has_gx ? a.gx_len : 0);
+                        pt.rec_index.push_back((int64_t)ri);
+                        if (keep_raw) pt.raw.add((const char *)rec, block_size);
                     }
                 }
             };
@@ -340,13 +350,15 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
             res->rec_off.assign(units + 1, 0);
             res->ref_id.resize(units); res->pos.resize(units); res->hi.resize(units); res->score.resize(units);
             res->flag.resize(units); res->gx_assigned.resize(units); res->paired.assign(units, 0);
-            Pool *dst_pool[4] = {&res->name, &res->barcode, &res->umi, &res->gene};
-            std::vector<size_t> pool0[4];
-            for (int k = 0; k < 4; ++k) {
+            res->rec_index.resize(units);
+            res->raw_mate.off.assign(units + 1, 0);
+            Pool *dst_pool[5] = {&res->name, &res->barcode, &res->umi, &res->gene, &res->raw};
+            std::vector<size_t> pool0[5];
+            for (int k = 0; k < 5; ++k) {
                 pool0[k].resize(n_parts);
                 size_t tot = 0;
                 for (size_t i = 0; i < n_parts; ++i) {
-                    const Pool &sp = k == 0 ? parts[i].name : (k == 1 ? parts[i].barcode : (k == 2 ? parts[i].umi : parts[i].gene));
+                    const Pool &sp = k == 0 ? parts[i].name : (k == 1 ? parts[i].barcode : (k == 2 ? parts[i].umi : (k == 3 ? parts[i].gene : parts[i].raw)));
                     pool0[k][i] = tot;
                     tot += sp.data.size();
                 }
@@ -372,9 +384,10 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
                         memcpy(res->score.data() + u0, pt.score.data(), 4 * nu);
                         memcpy(res->flag.data() + u0, pt.flag.data(), 2 * nu);
                         memcpy(res->gx_assigned.data() + u0, pt.gx_assigned.data(), nu);
+                        memcpy(res->rec_index.data() + u0, pt.rec_index.data(), 8 * nu);
                     }
-                    for (int k = 0; k < 4; ++k) {
-                        const Pool &sp = k == 0 ? pt.name : (k == 1 ? pt.barcode : (k == 2 ? pt.umi : pt.gene));
+                    for (int k = 0; k < (keep_raw ? 5 : 4); ++k) {
+                        const Pool &sp = k == 0 ? pt.name : (k == 1 ? pt.barcode : (k == 2 ? pt.umi : (k == 3 ? pt.gene : pt.raw)));
                         if (!sp.data.empty()) memcpy(dst_pool[k]->data.data() + pool0[k][i], sp.data.data(), sp.data.size());
                         for (size_t j = 0; j < nu; ++j) dst_pool[k]->off[u0 + j] = (uint32_t)(pool0[k][i] + sp.off[j]);
                     }
@@ -410,7 +423,7 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
         const uint16_t flag = rd16(rec + 14);
         if (ref_id != cur_ref) { pending.clear(); cur_ref = ref_id; }      // parse_read_contig runs per contig
         if (ref_id < 0) continue;                                           // bam.fetch(contig) never yields these
-        if (flag & (0x100 | 0x4 | 0x400)) continue;                         // bam.py:173: secondary, unmapped, duplicate
+        if (flag & skip_flags) continue;                                    // bam.py:173: secondary, unmapped, duplicate
         const size_t fixed = 32 + l_read_name + 4 * (size_t)n_cigar + (l_seq + 1) / 2 + l_seq;
         if (fixed > block_size) { delete res; dyn_set_error("dyn_bam_pack: corrupt record"); return DYN_ERR_FORMAT; }
         Aux a;
@@ -447,6 +460,11 @@ extern "C" int dyn_bam_pack(const char *path, const char *barcode_tag, const cha
         res->score.push_back((int32_t)a.as);
         res->gx_assigned.push_back(a.has_gx ? 1 : 0);
         res->paired.push_back(mate_rec ? 1 : 0);
+        res->rec_index.push_back(res->n_records_seen - 1);
+        if (keep_raw) {
+            res->raw.add((const char *)rec, block_size);
+            if (mate_rec) res->raw_mate.add((const char *)mate_rec, rd32(mate_rec - 4)); else res->raw_mate.add("", 0);
+        }
         res->name.add(name, name_len);
         res->barcode.add(a.has_bc ? a.bc : "NA", a.has_bc ? a.bc_len : 2);
         res->umi.add(a.has_umi ? a.umi : "NA", a.has_umi ? a.umi_len : 2);
@@ -497,6 +515,11 @@ extern "C" const void *dyn_bam_field(const dyn_bam_result_t *r, int field, int64
         case 9: vec(r->ref_len); break;
         case 10: p = r->header_text.data(); nb = r->header_text.size(); break;
         case 11: case 12: case 13: p = dyn_bam_chunk_field(r, field, &nb); break;
+        case 14: vec(r->rec_index); break;
+        case 30: vec(r->raw.data); break;
+        case 31: vec(r->raw.off); break;
+        case 32: vec(r->raw_mate.data); break;
+        case 33: vec(r->raw_mate.off); break;
         case 20: vec(r->name.data); break;
         case 21: vec(r->name.off); break;
         case 22: vec(r->barcode.data); break;
@@ -511,4 +534,96 @@ extern "C" const void *dyn_bam_field(const dyn_bam_result_t *r, int field, int64
     }
     if (n_bytes) *n_bytes = (int64_t)nb;
     return p;
+}
+
+// First `max_records` alignment records of a BAM: which aux tags occur, which flag bits occur (get_tags_from_bam,
+// check_bam_contains_secondary / _unmapped / _duplicate, check_bam_is_paired: dynast/preprocessing/bam.py:447-570).
+extern "C" int dyn_bam_peek(const char *path, int64_t max_records, char *tags_out, int32_t tags_capacity, int32_t *n_tags,
+                            uint32_t *flag_or, int64_t *n_seen) {
+    if (!path || !n_tags || !flag_or || !n_seen) { dyn_set_error("dyn_bam_peek: null argument"); return DYN_ERR_ARG; }
+    *n_tags = 0; *flag_or = 0; *n_seen = 0;
+    FILE *f = fopen(path, "rb");
+    if (!f) { dyn_set_error("dyn_bam_peek: cannot open %s", path); return DYN_ERR_IO; }
+    std::vector<uint8_t> data, comp;
+    std::vector<uint16_t> tags;
+    size_t p = 0;
+    bool header_done = false, eof = false;
+    auto more = [&]() -> bool {          // inflate one more BGZF block onto `data`
+        uint8_t h[18];
+        if (fread(h, 1, 18, f) != 18) { eof = true; return false; }
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return false;
+        const uint32_t xlen = rd16(h + 10);
+        std::vector<uint8_t> extra(xlen);
+        memcpy(extra.data(), h + 12, std::min<size_t>(6, xlen));
+        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f) != xlen - 6) return false;
+        uint32_t bsize = 0;
+        for (size_t x = 0; x + 4 <= xlen;) {
+            const uint32_t slen = rd16(extra.data() + x + 2);
+            if (extra[x] == 'B' && extra[x + 1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = rd16(extra.data() + x + 4);
+            x += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8 - 1) return false;
+        const size_t clen = (size_t)bsize + 1 - 12 - xlen - 8;
+        comp.resize(clen + 8);
+        if (fread(comp.data(), 1, clen + 8, f) != clen + 8) return false;
+        const uint32_t isize = rd32(comp.data() + clen + 4);
+        const size_t o = data.size();
+        data.resize(o + isize);
+        if (isize) {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) return false;
+            zs.next_in = comp.data(); zs.avail_in = (uInt)clen; zs.next_out = data.data() + o; zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END) return false;
+        }
+        return true;
+    };
+    auto need = [&](size_t n) -> bool { while (data.size() < n) if (!more()) return false; return true; };
+    int rc = DYN_OK;
+    if (!need(12) || memcmp(data.data(), "BAM\1", 4) != 0) { fclose(f); dyn_set_error("dyn_bam_peek: %s is not a BAM file", path); return DYN_ERR_FORMAT; }
+    p = 4;
+    const uint32_t l_text = rd32(data.data() + p); p += 4 + l_text;
+    if (need(p + 4)) {
+        const uint32_t n_ref = rd32(data.data() + p); p += 4;
+        header_done = true;
+        for (uint32_t r = 0; r < n_ref && header_done; ++r) {
+            if (!need(p + 4)) { header_done = false; break; }
+            const uint32_t l_name = rd32(data.data() + p);
+            p += 4 + l_name + 4;
+        }
+    }
+    while (header_done && *n_seen < max_records) {
+        if (!need(p + 4)) break;
+        const uint32_t bs = rd32(data.data() + p);
+        if (bs < 32 || !need(p + 4 + bs)) break;
+        const uint8_t *rec = data.data() + p + 4;
+        p += 4 + bs;
+        ++*n_seen;
+        *flag_or |= rd16(rec + 14);
+        const uint32_t l_name = rec[8], n_cigar = rd16(rec + 12), l_seq = rd32(rec + 16);
+        const size_t fixed = 32 + l_name + 4 * (size_t)n_cigar + (l_seq + 1) / 2 + l_seq;
+        if (fixed > bs) { rc = DYN_ERR_FORMAT; break; }
+        const uint8_t *a = rec + fixed, *end = rec + bs;
+        while (a + 3 <= end) {
+            const uint16_t tag = (uint16_t)(a[0] | (a[1] << 8));
+            if (std::find(tags.begin(), tags.end(), tag) == tags.end()) tags.push_back(tag);
+            const char ty = (char)a[2];
+            a += 3;
+            if (ty == 'A' || ty == 'c' || ty == 'C') a += 1;
+            else if (ty == 's' || ty == 'S') a += 2;
+            else if (ty == 'i' || ty == 'I' || ty == 'f') a += 4;
+            else if (ty == 'Z' || ty == 'H') { while (a < end && *a) ++a; ++a; }
+            else if (ty == 'B') { if (a + 5 > end) break; const char sub = (char)a[0]; const uint32_t cnt = rd32(a + 1); a += 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+            else break;
+        }
+        if (p > (64u << 20)) { data.erase(data.begin(), data.begin() + p); p = 0; }
+    }
+    fclose(f);
+    if (rc) { dyn_set_error("dyn_bam_peek: corrupt record in %s", path); return rc; }
+    *n_tags = (int32_t)tags.size();
+    for (size_t i = 0; i < tags.size() && (int32_t)(2 * i + 1) < tags_capacity; ++i) { tags_out[2 * i] = (char)(tags[i] & 0xff); tags_out[2 * i + 1] = (char)(tags[i] >> 8); }
+    (void)eof;
+    return DYN_OK;
 }

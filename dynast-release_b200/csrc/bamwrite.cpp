@@ -100,7 +100,75 @@ extern "C" int dyn_bam_write(const char *path, const char *header_text, int32_t 
                              const int64_t *h_order, const char *h_names, const uint32_t *h_name_off, const uint8_t *h_aux,
                              const uint32_t *h_aux_off, const uint8_t *h_mapq, const uint16_t *h_flag, int level, int n_threads,
                              int write_index) {
-    if (!path || !header_text || n_ref < 0 || n_units < 0 || (n_units && (!h_records || !h_rec_off))) {
+    dyn_bam_write_opts_t o;
+    memset(&o, 0, sizeof(o));
+    o.header_text = header_text; o.n_ref = n_ref; o.ref_names = ref_names; o.ref_lens = ref_lens;
+    o.h_records = h_records; o.h_rec_off = h_rec_off; o.n_units = n_units; o.h_order = h_order;
+    o.h_names = h_names; o.h_name_off = h_name_off; o.h_aux = h_aux; o.h_aux_off = h_aux_off; o.h_mapq = h_mapq; o.h_flag = h_flag;
+    o.level = level; o.n_threads = n_threads; o.write_index = write_index;
+    return dyn_bam_write_ex(path, &o);
+}
+
+namespace {
+
+// swap_gene_tags (dynast/preprocessing/consensus.py:277-286) on the aux bytes of a BAM record: the `gene_tag` tag is
+// dropped, GX is set to `gene` and -- when the gene has a name -- GN to it (a tag that is already there keeps its place,
+// a new one goes to the end).  Other tags keep their bytes.
+void retag(const uint8_t *aux, size_t n, const char *gene_tag, const char *gene, const char *name, std::vector<uint8_t> &out) {
+    const uint8_t *a = aux, *end = aux + n;
+    bool gx_done = false, gn_done = false;
+    auto z_tag = [&](const char *tag, const char *val) {
+        out.push_back((uint8_t)tag[0]); out.push_back((uint8_t)tag[1]); out.push_back('Z');
+        out.insert(out.end(), val, val + strlen(val)); out.push_back(0);
+    };
+    while (a + 3 <= end) {
+        const uint8_t *t0 = a;
+        const char ty = (char)a[2];
+        a += 3;
+        if (ty == 'A' || ty == 'c' || ty == 'C') a += 1;
+        else if (ty == 's' || ty == 'S') a += 2;
+        else if (ty == 'i' || ty == 'I' || ty == 'f') a += 4;
+        else if (ty == 'Z' || ty == 'H') { while (a < end && *a) ++a; ++a; }
+        else if (ty == 'B') { if (a + 5 > end) break; const char sub = (char)a[0]; const uint32_t cnt = rd32(a + 1); a += 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+        else break;
+        if (a > end) a = end;
+        const bool is_gene_tag = gene_tag && gene_tag[0] == (char)t0[0] && gene_tag[1] == (char)t0[1];
+        if (is_gene_tag) continue;
+        if (t0[0] == 'G' && t0[1] == 'X') { z_tag("GX", gene); gx_done = true; continue; }
+        if (t0[0] == 'G' && t0[1] == 'N' && name && name[0]) { z_tag("GN", name); gn_done = true; continue; }
+        out.insert(out.end(), t0, a);
+    }
+    if (!gx_done) z_tag("GX", gene);
+    if (!gn_done && name && name[0]) z_tag("GN", name);
+}
+
+}  // namespace
+
+extern "C" int dyn_bam_write_ex(const char *path, const dyn_bam_write_opts_t *opts) {
+    if (!path || !opts) { dyn_set_error("dyn_bam_write: null argument"); return DYN_ERR_ARG; }
+    const char *header_text = opts->header_text;
+    const int32_t n_ref = opts->n_ref;
+    const char *const *ref_names = opts->ref_names;
+    const int32_t *ref_lens = opts->ref_lens;
+    const void *h_records = opts->h_records;
+    const uint32_t *h_rec_off = opts->h_rec_off;
+    const int64_t n_units = opts->n_units;
+    const int64_t *h_order = opts->h_order;
+    const char *h_names = opts->h_names;
+    const uint32_t *h_name_off = opts->h_name_off;
+    const uint8_t *h_aux = opts->h_aux;
+    const uint32_t *h_aux_off = opts->h_aux_off;
+    const uint8_t *h_mapq = opts->h_mapq;
+    const uint16_t *h_flag = opts->h_flag;
+    const int level = opts->level, n_threads = opts->n_threads, write_index = opts->write_index;
+    const uint8_t *h_raw = opts->h_raw;
+    const uint64_t *h_raw_start = opts->h_raw_start;
+    const uint32_t *h_raw_len = opts->h_raw_len;
+    const char *h_retag = opts->h_retag;
+    const uint32_t *h_retag_off = opts->h_retag_off;
+    const char *gene_tag = (opts->gene_tag && opts->gene_tag[0] && opts->gene_tag[1]) ? opts->gene_tag : nullptr;
+    auto is_raw = [&](int64_t u) { return h_raw && h_raw_start && h_raw_len && h_raw_len[u] > 0; };
+    if (!header_text || n_ref < 0 || n_units < 0 || (n_units && !h_raw && (!h_records || !h_rec_off))) {
         dyn_set_error("dyn_bam_write: bad argument");
         return DYN_ERR_ARG;
     }
@@ -144,6 +212,38 @@ extern "C" int dyn_bam_write(const char *path, const char *header_text, int32_t 
             blocks.emplace_back();
             for (int64_t j = u0; j < u1; ++j) {
                 const int64_t u = h_order ? h_order[j] : j;
+                if (is_raw(u)) {
+                    // a record of the input file written through (consensus.py:420-422, 443-444, 476-478), its gene tags
+                    // swapped when asked to
+                    const uint8_t *r = h_raw + h_raw_start[u];
+                    const size_t rn = (size_t)h_raw_len[u];
+                    rec.clear();
+                    put32(rec, 0);
+                    const bool swap = h_retag && h_retag_off && h_retag_off[u + 1] > h_retag_off[u];
+                    if (!swap) rec.insert(rec.end(), r, r + rn);
+                    else {
+                        const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_sq = rd32(r + 16);
+                        const size_t fixed = 32 + l_name + 4 * (size_t)n_cig + (l_sq + 1) / 2 + l_sq;
+                        if (fixed > rn) { fail("dyn_bam_write: corrupt raw record"); return; }
+                        rec.insert(rec.end(), r, r + fixed);
+                        const char *g = h_retag + h_retag_off[u];
+                        const char *gn = g + strlen(g) + 1;
+                        retag(r + fixed, rn - fixed, gene_tag, g, gn < h_retag + h_retag_off[u + 1] ? gn : "", rec);
+                    }
+                    const uint32_t bs = (uint32_t)(rec.size() - 4);
+                    for (int i = 0; i < 4; ++i) rec[i] = (uint8_t)(bs >> (8 * i));
+                    if (!blocks.back().payload.empty() && blocks.back().payload.size() + rec.size() > kPayload) blocks.emplace_back();
+                    size_t o = 0;
+                    blocks.back().rec_at.push_back((uint32_t)blocks.back().payload.size());
+                    blocks.back().rec_unit.push_back(u);
+                    while (o < rec.size()) {
+                        if (blocks.back().payload.size() == kPayload) blocks.emplace_back();
+                        const size_t take = std::min(rec.size() - o, kPayload - blocks.back().payload.size());
+                        blocks.back().payload.insert(blocks.back().payload.end(), rec.begin() + o, rec.begin() + o + take);
+                        o += take;
+                    }
+                    continue;
+                }
                 const uint8_t *p = records + ((size_t)h_rec_off[u] << 4);
                 const int32_t pos = (int32_t)rd32(p), ref_id = (int32_t)rd32(p + 4);
                 const uint32_t l_seq = rd16(p + 8), n_cigar = rd16(p + 10), n_tok = rd16(p + 12);
@@ -237,12 +337,19 @@ extern "C" int dyn_bam_write(const char *path, const char *header_text, int32_t 
                 for (size_t k = 0; k < b.rec_at.size(); ++k) {
                     const uint64_t voff = (file_off << 16) | b.rec_at[k];
                     close_prev(voff);
-                    const uint8_t *p = records + ((size_t)h_rec_off[b.rec_unit[k]] << 4);
-                    const int32_t pos = (int32_t)rd32(p), ref_id = (int32_t)rd32(p + 4);
-                    const uint32_t n_cigar = rd16(p + 10);
+                    int32_t pos, ref_id;
+                    uint32_t n_cigar;
+                    const uint8_t *cg;
+                    if (is_raw(b.rec_unit[k])) {
+                        const uint8_t *r = h_raw + h_raw_start[b.rec_unit[k]];
+                        ref_id = (int32_t)rd32(r); pos = (int32_t)rd32(r + 4); n_cigar = rd16(r + 12); cg = r + 32 + r[8];
+                    } else {
+                        const uint8_t *p = records + ((size_t)h_rec_off[b.rec_unit[k]] << 4);
+                        pos = (int32_t)rd32(p); ref_id = (int32_t)rd32(p + 4); n_cigar = rd16(p + 10); cg = p + 16;
+                    }
                     int64_t span = 0;
                     for (uint32_t c = 0; c < n_cigar; ++c) {
-                        const uint32_t w = rd32(p + 16 + 4 * (size_t)c), op = w & 0xf;
+                        const uint32_t w = rd32(cg + 4 * (size_t)c), op = w & 0xf;
                         if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += w >> 4;
                     }
                     const int64_t end = pos + std::max<int64_t>(span, 1);

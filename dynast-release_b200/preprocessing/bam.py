@@ -53,6 +53,80 @@ def select_alignments(df_alignments: pd.DataFrame) -> Set[Tuple[str, int]]:
     return set(zip(sel['read_id'].astype(str), sel['index'].astype(int)))
 
 
+BAM_PEEK_READS = 500000          # dynast/config.py:44
+BAM_REQUIRED_TAGS = ['MD']
+BAM_READGROUP_TAG, BAM_BARCODE_TAG, BAM_UMI_TAG, BAM_GENE_TAG, BAM_CONSENSUS_READ_COUNT_TAG = 'RG', 'CB', 'UB', 'GX', 'RN'
+
+
+def get_tags_from_bam(bam_path: str, n_reads: int = 100000, n_threads: int = 8) -> Set[str]:
+    """bam.get_tags_from_bam (bam.py:447-466): the aux tags of the first `n_reads` records (dyn_bam_peek)."""
+    return bamio.peek(bam_path, n_reads)[0]
+
+
+def check_bam_tags_exist(bam_path: str, tags: List[str], n_reads: int = 100000, n_threads: int = 8) -> Tuple[bool, List[str]]:
+    """bam.check_bam_tags_exist (bam.py:469-497)."""
+    found = get_tags_from_bam(bam_path, n_reads)
+    missing = [t for t in tags if t not in found]
+    return not missing, missing
+
+
+def check_bam_is_paired(bam_path: str, n_reads: int = 100000, n_threads: int = 8) -> bool:
+    """bam.check_bam_is_paired (bam.py:500-517)."""
+    return bool(bamio.peek(bam_path, n_reads)[1] & 0x1)
+
+
+def check_bam_contains_secondary(bam_path: str, n_reads: int = 100000, n_threads: int = 8) -> bool:
+    """bam.check_bam_contains_secondary (bam.py:520-537)."""
+    return bool(bamio.peek(bam_path, n_reads)[1] & 0x100)
+
+
+def check_bam_contains_unmapped(bam_path: str, n_reads: int = BAM_PEEK_READS) -> bool:
+    """bam.check_bam_contains_unmapped (bam.py:540-553).  The reference asks the .bai for its unmapped counts; here the first
+    `n_reads` records are inspected, like the other checks."""
+    return bool(bamio.peek(bam_path, n_reads)[1] & 0x4)
+
+
+def check_bam_contains_duplicate(bam_path: str, n_reads: int = 100000, n_threads: int = 8) -> bool:
+    """bam.check_bam_contains_duplicate (bam.py:556-570)."""
+    return bool(bamio.peek(bam_path, n_reads)[1] & 0x400)
+
+
+def check_bam_tags(bam_path: str, umi_tag: Optional[str] = None, barcode_tag: Optional[str] = None, gene_tag: Optional[str] = 'GX',
+                   n_threads: int = 8) -> Set[str]:
+    """The tag / alignment checks at the top of count() and consensus() (count.py:86-135, consensus.py:52-100): warnings for
+    tags that are present but not asked for, an Exception for required tags that never occur, warnings for secondary /
+    unmapped / duplicate records.  Returns the tags found."""
+    import warnings
+    tags, flags, _ = bamio.peek(bam_path, BAM_PEEK_READS)
+    required = list(BAM_REQUIRED_TAGS)
+    hint = lambda opt, tag: warnings.warn(f"BAM contains reads with {tag} tag. Are you sure you didn't mean to provide `{opt} {tag}`?")
+    if barcode_tag:
+        required.append(barcode_tag)
+    elif BAM_BARCODE_TAG in tags:
+        hint('--barcode-tag', BAM_BARCODE_TAG)
+    elif BAM_READGROUP_TAG in tags:
+        hint('--barcode-tag', BAM_READGROUP_TAG)
+    if umi_tag:
+        required.append(umi_tag)
+    elif BAM_UMI_TAG in tags:
+        hint('--umi-tag', BAM_UMI_TAG)
+    if gene_tag:
+        required.append(gene_tag)
+    elif BAM_GENE_TAG in tags:
+        hint('--gene-tag', BAM_GENE_TAG)
+    missing = set(required) - tags
+    if missing:
+        raise Exception(f'First {BAM_PEEK_READS} reads in the BAM do not contain the following required tags: '
+                        f'{", ".join(sorted(missing))}. ')
+    if flags & 0x100:
+        warnings.warn('BAM contains secondary alignments, which will be ignored. Only primary alignments are considered.')
+    if flags & 0x4:
+        warnings.warn('BAM contains unmapped reads, which will be ignored.')
+    if flags & 0x400:
+        warnings.warn('BAM contains duplicate reads, which will be ignored.')
+    return tags
+
+
 def _check_tally_status(status: int, counts: np.ndarray):
     """DYN_ST_* bits of a quality-0 tally run -> the exception the reference would end in.  The kernel clamps the
     A/C/G/T content at 255 and skips IUPAC mismatches; the reference writes the true values to the CSVs and fails

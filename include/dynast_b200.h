@@ -396,6 +396,20 @@ int dyn_merge_kn(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count
 typedef struct dyn_bam_result dyn_bam_result_t;
 int dyn_bam_pack(const char *path, const char *barcode_tag, const char *umi_tag, const char *gene_tag, int require_gene,
                  int n_threads, dyn_bam_result_t **out_result);
+/* The same with options (the consensus caller's reader, consensus.py:361-380, filters differently and writes reads
+ * through unchanged): DYN_BAM_KEEP_DUPLICATES = duplicate-flagged records are units too (consensus.py:248-249 does not
+ * skip them), DYN_BAM_KEEP_RAW = the units' BAM alignment records are kept as they are in the file (fields 30/31: the
+ * unit's record, 32/33: its first-seen mate; chars / u32 offsets [n + 1]).  Field 14 (i64) is the ordinal of the unit's
+ * record among all records of the file -- enumerate(bam.fetch()) in the reference. */
+#define DYN_BAM_KEEP_RAW 0x1u
+#define DYN_BAM_KEEP_DUPLICATES 0x2u
+int dyn_bam_pack_ex(const char *path, const char *barcode_tag, const char *umi_tag, const char *gene_tag, int require_gene,
+                    int n_threads, uint32_t flags, dyn_bam_result_t **out_result);
+/* The first max_records records: the aux tags that occur (2 chars each into tags_out, *n_tags of them) and the OR of
+ * the flags -- bam.get_tags_from_bam, check_bam_contains_secondary / _unmapped / _duplicate, check_bam_is_paired
+ * (bam.py:447-570). */
+int dyn_bam_peek(const char *path, int64_t max_records, char *tags_out, int32_t tags_capacity, int32_t *n_tags,
+                 uint32_t *flag_or, int64_t *n_seen);
 void dyn_bam_result_free(dyn_bam_result_t *result);
 int64_t dyn_bam_n_units(const dyn_bam_result_t *result);
 int64_t dyn_bam_n_records_seen(const dyn_bam_result_t *result);
@@ -478,6 +492,34 @@ int dyn_inflate_blocks(dyn_ctx_t *ctx, const void *d_in, void *d_out, const uint
  * level = zlib level; write_index != 0 also writes <path>.bai (binning + linear index, SAM specification section 5).
  * Host call, all pointers are host pointers.
  * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const char *header_text;
+    int32_t n_ref;
+    const char *const *ref_names;
+    const int32_t *ref_lens;
+    const void *h_records;          /* packed units (may be NULL when every unit is raw) */
+    const uint32_t *h_rec_off;
+    int64_t n_units;
+    const int64_t *h_order;
+    const char *h_names;
+    const uint32_t *h_name_off;
+    const uint8_t *h_aux;
+    const uint32_t *h_aux_off;
+    const uint8_t *h_mapq;
+    const uint16_t *h_flag;
+    int32_t level, n_threads, write_index, reserved;
+    /* dyn_bam_write_ex only: unit u is written from the BAM alignment record h_raw[h_raw_start[u] .. + h_raw_len[u])
+     * (fixed fields .. aux, without its block_size) when h_raw_len[u] is not zero -- reads of the input file passed
+     * through by call_consensus (consensus.py:420-422) --, and with h_retag[h_retag_off[u] ..) = "gene id\0gene name\0"
+     * not empty its gene tags are swapped first (swap_gene_tags, consensus.py:277-286, with `gene_tag`). */
+    const uint8_t *h_raw;
+    const uint64_t *h_raw_start;
+    const uint32_t *h_raw_len;
+    const char *h_retag;
+    const uint32_t *h_retag_off;
+    const char *gene_tag;
+} dyn_bam_write_opts_t;
+int dyn_bam_write_ex(const char *path, const dyn_bam_write_opts_t *opts);
 int dyn_bam_write(const char *path, const char *header_text, int32_t n_ref, const char *const *ref_names,
                   const int32_t *ref_lens, const void *h_records, const uint32_t *h_rec_off, int64_t n_units,
                   const int64_t *h_order, const char *h_names, const uint32_t *h_name_off, const uint8_t *h_aux,
