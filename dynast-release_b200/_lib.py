@@ -154,7 +154,8 @@ class BamWriteOpts(C.Structure):
                 ('h_names', C.c_void_p), ('h_name_off', C.c_void_p), ('h_aux', C.c_void_p), ('h_aux_off', C.c_void_p),
                 ('h_mapq', C.c_void_p), ('h_flag', C.c_void_p), ('level', C.c_int32), ('n_threads', C.c_int32),
                 ('write_index', C.c_int32), ('reserved', C.c_int32), ('h_raw', C.c_void_p), ('h_raw_start', C.c_void_p),
-                ('h_raw_len', C.c_void_p), ('h_retag', C.c_void_p), ('h_retag_off', C.c_void_p), ('gene_tag', C.c_char_p)]
+                ('h_raw_len', C.c_void_p), ('h_retag', C.c_void_p), ('h_retag_off', C.c_void_p), ('gene_tag', C.c_char_p),
+                ('h_md', C.c_void_p), ('h_md_off', C.c_void_p)]
 
 
 class BamDevChunk(C.Structure):

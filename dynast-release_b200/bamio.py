@@ -178,7 +178,7 @@ def peek(path: str, max_records: int = 500000):
 
 def write_bam(path: str, refs, blob: np.ndarray, rec_off: np.ndarray, order=None, names=None, aux=None, mapq=None, flag=None,
               header_text: Optional[str] = None, level: int = 6, n_threads: int = 8, index: bool = True, raw=None, raw_start=None,
-              raw_len=None, retag=None, gene_tag: Optional[str] = None):
+              raw_len=None, retag=None, gene_tag: Optional[str] = None, md=None):
     """dyn_bam_write(_ex): packed records (full layout, no mates) -> a BAM file (+ .bai).  refs: [(name, length)];
     names: list of str or None ("r<i>"); aux: list of bytes (pre-encoded tags) or a (bytes, uint32 offsets) pair;
     order: unit order in the file (coordinate order for a sorted BAM).  raw / raw_start / raw_len: units written from
@@ -225,6 +225,10 @@ def write_bam(path: str, refs, blob: np.ndarray, rec_off: np.ndarray, order=None
         o.h_retag, o.h_retag_off = p(r_data), p(r_off)
         o.gene_tag = gene_tag.encode() if gene_tag else None
         keep += [r_data, r_off]
+    if md is not None:          # MD text per unit, written verbatim where not empty
+        m_data, m_off = pool(md)
+        o.h_md, o.h_md_off = p(m_data), p(m_off)
+        keep += [m_data, m_off]
     _lib.check(lib.dyn_bam_write_ex(path.encode(), C.byref(o)))
     del keep
     return path

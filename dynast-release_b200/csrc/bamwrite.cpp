@@ -75,12 +75,13 @@ int reg2bin(int64_t beg, int64_t end) {
 void md_text(const uint32_t *tok, uint32_t n_tok, uint32_t m_total, std::string &out) {
     static const char codes[] = "=ACMGRSVTWYHKDBN";
     out.clear();
-    uint32_t run_start = 0;
+    uint32_t run_start = 0, del_at = 0;
     bool prev_del = false;
     for (uint32_t i = 0; i < n_tok; ++i) {
         const uint32_t t = tok[i], aoff = t & 0xffff, code = (t >> 16) & 15;
         if ((t >> 20) & 1) {
-            if (!prev_del) { out += std::to_string(aoff - run_start); out += '^'; run_start = aoff; }
+            // the deleted bases of one D run share their aligned offset; another offset starts another ^ run
+            if (!prev_del || aoff != del_at) { out += std::to_string(aoff - run_start); out += '^'; run_start = aoff; del_at = aoff; }
             out += codes[code];
             prev_del = true;
         } else {
@@ -258,7 +259,9 @@ extern "C" int dyn_bam_write_ex(const char *path, const dyn_bam_write_opts_t *op
                     if (op == 0 || op == 7 || op == 8) { m_total += len; ref_span += len; }
                     else if (op == 2 || op == 3) ref_span += len;
                 }
-                md_text(reinterpret_cast<const uint32_t *>(tokb), n_tok, m_total, md);
+                if (opts->h_md && opts->h_md_off && opts->h_md_off[u + 1] > opts->h_md_off[u])
+                    md.assign(opts->h_md + opts->h_md_off[u], opts->h_md + opts->h_md_off[u + 1]);      // the caller's MD text, verbatim
+                else md_text(reinterpret_cast<const uint32_t *>(tokb), n_tok, m_total, md);
                 if (h_names) name.assign(h_names + h_name_off[u], h_names + h_name_off[u + 1]);
                 else name = "r" + std::to_string(u);
                 if (name.size() > 254) { fail("dyn_bam_write: read name longer than 254 characters"); return; }

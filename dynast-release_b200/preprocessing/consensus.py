@@ -155,12 +155,13 @@ def call_consensus(
     use_tag = gx_assigned if gene_tag else np.zeros(n, dtype=bool)
     cnt, which, genes = _find_genes(gene_infos, ref_names, ref_id, start, end, read_strand) if (n and (~use_tag).any()) else (
         np.zeros(n, np.int64), np.full(n, -1, np.int64), list(gene_infos))
+    # A gene tag the annotation does not know is legal as long as its groups stay singletons: swap_gene_tags uses
+    # gene_infos.get (:283); the flush loop (:436) and create_tags_and_strand (:447, 480) index gene_infos and raise.
+    n_known = len(genes)
+    genes = genes + sorted({g for g, t in zip(gene_s, use_tag) if t and g not in gene_infos})
     gene_index = {g: i for i, g in enumerate(genes)}
-    tagged = np.array([gene_index.get(g, -2) for g in gene_s], dtype=np.int64) if n else np.zeros(0, np.int64)
+    tagged = np.array([gene_index.get(g, -1) for g in gene_s], dtype=np.int64) if n else np.zeros(0, np.int64)
     gene_of = np.where(use_tag, tagged, np.where(cnt == 1, which, -1))
-    if (keep & use_tag & (tagged == -2)).any():
-        bad = sorted(set(gene_s[keep & use_tag & (tagged == -2)]))
-        raise KeyError(f'gene tag value not in gene_infos: {bad[:5]}')
     grouped = keep & (gene_of >= 0)
     through = keep & ~grouped
     # ---- UMI of a unit: the tag, or (mate start, read end) for pairs without one (:392-395), else nothing
@@ -175,7 +176,7 @@ def call_consensus(
     epoch = np.zeros(n, dtype=np.int64)
     n_flush = {}
     if len(g_rows):
-        chrom = {gi: str(gene_infos[genes[gi]]['chromosome']) for gi in np.unique(gene_of[g_rows])}
+        chrom = {gi: str(gene_infos[genes[gi]]['chromosome']) for gi in np.unique(gene_of[g_rows]) if gi < n_known}
         g_end = {gi: _segment(gene_infos[genes[gi]])[1] for gi in chrom}
         checkpoints = g_rows[rec_index[g_rows] % FLUSH_EVERY == 0]
         open_genes: List[int] = []          # insertion order of gx_barcode_umi_groups
@@ -194,6 +195,8 @@ def call_consensus(
             contig, leftmost = str(ref_names[ref_id[cp]]), int(start[cp])
             while open_genes:
                 gi = open_genes[0]
+                if gi >= n_known:
+                    raise KeyError(genes[gi])           # gene_infos[gene] at consensus.py:436
                 if chrom[gi] < contig or (chrom[gi] == contig and g_end[gi] <= leftmost):
                     open_genes.pop(0); in_dict.discard(gi)
                     events.append((gi, k))
@@ -227,6 +230,8 @@ def call_consensus(
     # ---- consensus on the device
     cons = None
     cg = np.flatnonzero(need_consensus)
+    if len(cg) and (g_gene[cg] >= n_known).any():
+        raise KeyError(genes[int(g_gene[cg][g_gene[cg] >= n_known][0])])       # gene_infos[gene] at consensus.py:447, 480
     if len(cg):
         gid = np.full(G, -1, dtype=np.int64)
         gid[cg] = np.arange(len(cg))
@@ -253,7 +258,7 @@ def call_consensus(
         if (status != 0).any():
             raise ValueError(f'consensus failed with status {sorted(set(status[status != 0].tolist()))}')
         cons = dict(records=out['records'].cpu().numpy(), off=out['off'].cpu().numpy().view(np.uint32), nm=out['nm'].cpu().numpy(),
-                    units=units, ugid=ugid, groups=cg)
+                    md=out['md'].cpu().numpy(), md_off=out['md_off'].cpu().numpy().view(np.uint32), units=units, ugid=ugid, groups=cg)
 
     # ---- output units: consensus records (packed), then the reads written through (raw)
     n_cons = len(cg)
@@ -319,7 +324,7 @@ def call_consensus(
         out_aux.append(b'')
         if su >= 0:
             g = genes[int(gene_of[su])]
-            retag.append(g.encode() + b'\0' + (gene_infos[g].get('gene_name') or '').encode() + b'\0')
+            retag.append(g.encode() + b'\0' + (gene_infos.get(g, {}).get('gene_name') or '').encode() + b'\0')
         else:
             retag.append(b'')
     retag = [b''] * n_cons + retag
@@ -333,9 +338,13 @@ def call_consensus(
         hd_line = '\t'.join(f + ['SO:coordinate'])
     header_out = '\n'.join([hd_line] + rest) + '\n'
     refs = [(str(nm), int(l)) for nm, l in zip(ref_names, ref_len)]
+    md = None
+    if cons is not None:        # the kernel's MD string is the reference's, character for character (consensus.py:124-161, 175)
+        md_off = np.concatenate([cons['md_off'][:n_cons + 1], np.full(n_total - n_cons, cons['md_off'][n_cons], dtype=np.uint32)])
+        md = (cons['md'][:int(cons['md_off'][n_cons])].tobytes() or b'\0', md_off)
     bamio.write_bam(out_path, refs, records_out, rec_off_out, order=order, names=out_names, aux=out_aux, mapq=np.full(n_total, 255, np.uint8),
                     flag=out_flag, header_text=header_out, level=6, n_threads=n_threads, index=True, raw=raw if len(raw) else np.zeros(1, np.uint8),
-                    raw_start=r_start, raw_len=r_len, retag=retag, gene_tag=gene_tag)
+                    raw_start=r_start, raw_len=r_len, retag=retag, gene_tag=gene_tag, md=md)
     return out_path
 
 

@@ -112,13 +112,14 @@ def md_from_tokens(tokens: Sequence[int], cigar: Sequence[Tuple[int, int]]) -> s
     i = 0
     m_total = sum(n for op, n in cigar if op in (0, 7, 8))
     prev_del = False
+    del_at = 0
     for t in tokens:
         aoff, code, is_del = t & 0xffff, (t >> 16) & 15, (t >> 20) & 1
         if is_del:
-            if not prev_del:
+            if not prev_del or aoff != del_at:      # another aligned offset: another ^ run
                 out.append(str(aoff - run_start))
                 out.append('^')
-                run_start = aoff
+                run_start = del_at = aoff
             out.append(SEQ_CODES[code])
             prev_del = True
         else:

@@ -518,6 +518,10 @@ typedef struct {
     const char *h_retag;
     const uint32_t *h_retag_off;
     const char *gene_tag;
+    /* MD text of unit u, h_md[h_md_off[u] .. h_md_off[u + 1]), written verbatim instead of being rebuilt from the tokens
+     * when not empty (dyn_consensus returns the reference's exact MD string, consensus.py:124-161, 175) */
+    const char *h_md;
+    const uint32_t *h_md_off;
 } dyn_bam_write_opts_t;
 int dyn_bam_write_ex(const char *path, const dyn_bam_write_opts_t *opts);
 int dyn_bam_write(const char *path, const char *header_text, int32_t n_ref, const char *const *ref_names,

@@ -233,6 +233,45 @@ def kn_csr(ctx, keys, count32, n_rows, n_groups):
     return t((k >> 10) & 0xfff, np.int32), t(k & 0x3ff, np.int32), t(c, np.int64), t(off, np.int64), t(total, np.int64)
 
 
+def consensus(ctx, records, item_rec16, group_off, quality=27, out_capacity_bytes=None):
+    """Stand-in for dyn_consensus: members decoded from their packed records, the oracle's call_consensus
+    (consensus.py:57-200), the result packed again."""
+    from dynast_b200 import records as rec
+    from oracle import bamio, consensus_oracle
+    blob, items, goff = _np(records), _np(item_rec16).astype(np.int64), _np(group_off).astype(np.int64)
+
+    def unpack(at16):
+        o = int(at16) * 16
+        pos, ref_id = int(np.frombuffer(blob[o:o + 4].tobytes(), '<i4')[0]), int(np.frombuffer(blob[o + 4:o + 8].tobytes(), '<i4')[0])
+        l_seq, n_cig, n_tok, flag = (int(x) for x in np.frombuffer(blob[o + 8:o + 16].tobytes(), '<u2'))
+        cig = np.frombuffer(blob[o + 16:o + 16 + 4 * n_cig].tobytes(), '<u4')
+        cigar = [(int(c & 0xf), int(c >> 4)) for c in cig]
+        toks = [int(x) for x in np.frombuffer(blob[o + 16 + 4 * n_cig:o + 16 + 4 * n_cig + 4 * n_tok].tobytes(), '<u4')]
+        so = o + 16 + 4 * n_cig + 4 * n_tok
+        sb = blob[so:so + (l_seq + 1) // 2]
+        seq = ''.join(rec.SEQ_CODES[sb[i >> 1] >> 4] if (i & 1) == 0 else rec.SEQ_CODES[sb[i >> 1] & 0xf] for i in range(l_seq))
+        qo = so + ((((l_seq + 1) // 2) + 3) & ~3)
+        return consensus_oracle.make_read('r', pos, cigar, seq, [int(x) for x in blob[qo:qo + l_seq]], rec.md_from_tokens(toks, cigar),
+                                          ref_id=ref_id, flag=flag & 0xfff)
+
+    packed, nm, status, mds = [], [], [], []
+    for g in range(len(goff) - 1):
+        members = [unpack(items[i]) for i in range(goff[g], goff[g + 1])]
+        if len({m.reference_id for m in members}) > 1:
+            packed.append(rec.pack_one(0, 0, 0, [], '', [], '0')); nm.append(0); status.append(4); mds.append(b'')
+            continue
+        c = consensus_oracle.call_consensus(members, quality=quality)
+        cigar = [(bamio.CIGAR_OPS.index(op), n) for op, n in c['cigar']]
+        packed.append(rec.pack_one(c['start'], members[0].reference_id, 0, cigar, c['seq'], c['qual'], c['md']))
+        nm.append(c['nm']); status.append(0); mds.append(c['md'].encode())
+    out_blob, off = rec.pack_units([[p] for p in packed]) if packed else (np.zeros(0, np.uint8), np.zeros(1, np.uint32))
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(d)))
+    md_off = np.zeros(len(packed) + 1, dtype=np.int32)
+    np.cumsum([len(m) for m in mds], out=md_off[1:])
+    return dict(records=t(out_blob, np.uint8), off=t(off.view(np.int32), np.int32), md=t(np.frombuffer(b''.join(mds), np.uint8), np.uint8),
+                md_off=t(md_off, np.int32), nm=t(nm, np.int32), status=t(status, np.int32))
+
+
 def install(monkeypatch):
     """Route the operator layer to the numpy stand-ins (torch CPU tensors)."""
     from dynast_b200 import _lib, device, pipeline
@@ -247,7 +286,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_lib, 'current_torch_device', lambda: torch.device('cpu'))
     monkeypatch.setattr(_lib, 'current_device_index', lambda: 0)
     for name in ('count_records', 'complement_counts', 'plan_splits', 'dedup', 'group_sums', 'rates_pe', 'alpha', 'aggregate_kn',
-                 'owner_partition', 'pack_reads', 'unpack_reads', 'merge_kn', 'kn_csr'):
+                 'owner_partition', 'pack_reads', 'unpack_reads', 'merge_kn', 'kn_csr', 'consensus'):
         monkeypatch.setattr(pipeline, name, globals()[name])
 
     def em_pc_host(k, n, count, off, p_e, nasc=False, device=0):
@@ -255,6 +294,7 @@ def install(monkeypatch):
         return p_c, status, np.zeros(len(p_e), dtype=np.int32)
 
     monkeypatch.setattr(device, 'em_pc_host', em_pc_host)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
     from dynast_b200.preprocessing import snp
     monkeypatch.setattr(snp, 'unique_counts', unique_counts_host)
 

@@ -1,4 +1,4 @@
-"""GPU: preprocessing.call_consensus / consensus() -- the whole consensus caller (dynast/preprocessing/consensus.py:227-494)
+"""CPU host logic (device stage replaced by the oracle) and GPU: preprocessing.call_consensus / consensus() -- the whole consensus caller (dynast/preprocessing/consensus.py:227-494)
 against its line-by-line restatement (oracle/consensus_oracle.py::call_consensus_bam): which reads are grouped, passed
 through or gene-tag-swapped, the periodic-flush quirk, consensus records (sequence, CIGAR, MD / NM, tags, names, strand),
 the coordinate order and the index of the BAM that comes out; then count() on that BAM picks dedup mode `exon` by
@@ -10,7 +10,6 @@ import pytest
 
 from helpers import gene_infos, ref_path
 
-pytestmark = pytest.mark.gpu
 
 
 def _canon_read(r, tags):
@@ -54,7 +53,7 @@ def _compare(bam_in, out, kw, infos):
     dict(umi_tag=None, barcode_tag='CB', gene_tag='GX', strand='reverse', quality=35),
     dict(umi_tag='UB', barcode_tag='CB', gene_tag=None, strand='forward'),         # genes by position only
 ])
-def test_call_consensus_matches_oracle_on_umi_fixture(gpu_ctx, tmp_path, kw):
+def test_call_consensus_matches_oracle_on_umi_fixture(backend, tmp_path, kw):
     from dynast_b200.preprocessing import call_consensus
     path = ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam')
     out = str(tmp_path / 'consensus.bam')
@@ -65,7 +64,7 @@ def test_call_consensus_matches_oracle_on_umi_fixture(gpu_ctx, tmp_path, kw):
     assert 'read' in kinds
 
 
-def test_call_consensus_paired_pseudo_umi(gpu_ctx, tmp_path):
+def test_call_consensus_paired_pseudo_umi(backend, tmp_path):
     """Smart-seq: no UMI tag, pairs grouped by (mate start, read end) (consensus.py:392-395); members = read, then mate."""
     from dynast_b200.preprocessing import call_consensus
     path = ref_path('smartseq_align', 'Aligned.sortedByCoord.out.bam')
@@ -76,20 +75,20 @@ def test_call_consensus_paired_pseudo_umi(gpu_ctx, tmp_path):
     assert sum(w[0] == 'cons' for w in want) > 10
 
 
-def _many_singletons(tmp_path, copies=8):
-    """The UMI fixture's reads `copies` times, every copy with its own read name and UMI: > 10 000 records whose groups
-    stay singletons, so that the flush at record 10 000 (consensus.py:432-452) has singletons to duplicate."""
+def _many_singletons(tmp_path, copies=40):
+    """The UMI fixture's gene-tagged reads `copies` times, every copy with its own read name and UMI: > 10 000 records
+    whose groups stay singletons, so that the flush at record 10 000 (consensus.py:432-452) has singletons to duplicate."""
     from oracle import bamio
     _, refs, reads = bamio.read_bam(ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'))
     recs = []
     for r in reads:
-        if r.reference_id < 0:
+        if r.reference_id < 0 or not (r.has_tag('CB') and r.has_tag('UB') and r.has_tag('GX')) or r.get_tag('CB') == '-':
             continue
         for k in range(copies):
             tags = []
             for t, v in r.tags.items():
                 if t == 'UB':
-                    v = v[:-2] + 'ACGT'[k % 4] + 'ACGT'[(k // 4) % 4]
+                    v = v[:-3] + 'ACGT'[k % 4] + 'ACGT'[(k // 4) % 4] + 'ACGT'[(k // 16) % 4]
                 tags.append((t, 'Z' if isinstance(v, str) else ('i' if isinstance(v, int) else 'A'), v))
             recs.append(bamio.encode_record(f'{r.query_name}_{k}', r.flag, r.reference_id, r.reference_start, r.mapping_quality, r.cigar,
                                             r.query_sequence, bytes(r.query_qualities), tags))
@@ -98,17 +97,19 @@ def _many_singletons(tmp_path, copies=8):
     return out
 
 
-def test_call_consensus_flush_quirk(gpu_ctx, tmp_path):
+def test_call_consensus_flush_quirk(backend, tmp_path):
     from dynast_b200.preprocessing import call_consensus
-    path = _many_singletons(tmp_path)
-    out = str(tmp_path / 'consensus.bam')
+    from oracle import bamio, consensus_oracle
     kw = dict(umi_tag='UB', barcode_tag='CB', gene_tag='GX', strand='forward')
+    path = _many_singletons(tmp_path)          # record 10 000 is a grouped read: the flush of consensus.py:432 runs
+    out = str(tmp_path / 'consensus.bam')
     call_consensus(path, out, gene_infos(), n_threads=3, **kw)
     want, got = _compare(path, out, kw, gene_infos())
     one_read_consensus = [w for w in want if w[0] == 'cons' and dict(w[8])['RN'] == '1']
     assert len(one_read_consensus) > 0          # the reference writes these singletons twice (no `continue` at :444)
 
 
+@pytest.mark.gpu
 def test_consensus_command_then_count_detects_consensus_bam(gpu_ctx, tmp_path):
     from dynast_b200 import bamio, consensus as consensus_cmd, count
     path = ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam')
