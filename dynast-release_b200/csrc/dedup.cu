@@ -141,6 +141,72 @@ __global__ void copy_u32_kernel(const uint32_t *src, uint32_t *dst, const long l
     if (i < n && i < *n_valid) dst[i] = src[i];
 }
 
+// ---- hash path: the winner of every (barcode, umi, gene) group by one atomicMax per read ---------------------------
+// Within a group the barcode (hence its place in the split-file order) and the gene's strand are the same for every
+// member, so the member that ends up last after the reference's stable sorts is the one with the largest
+// (priority, no-mismatch flag, BAM index): 63 bits, one 64-bit atomicMax into an open-addressing table keyed by the
+// group key.  No sort over all reads: only the survivors (less than half of them in UMI data) are sorted afterwards.
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+__device__ __forceinline__ unsigned long long mix_key(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ unsigned long long priority_of(const DedupIn &in, long long i) {
+    uint4 c = in.counts[i];
+    if (in.strand[i]) c = complement_row(c);
+    const uint32_t w[3] = {c.x, c.y, c.z};
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j)
+        if ((in.conv_mask >> j) & 1u) sum += (w[j >> 2] >> ((j & 3) << 3)) & 0xffu;
+    const unsigned long long has = (in.use_conversions && sum > 0) ? 1u : 0u;
+    return (has << 29) | ((unsigned long long)(in.transcriptome[i] != 0) << 28) | ((unsigned long long)in.score[i] << 12) | (sum & 0xfffu);
+}
+
+__global__ void hash_insert_kernel(DedupIn in, const unsigned long long *group_key, unsigned long long *tkeys, unsigned long long *tvals,
+                                   unsigned long long mask, uint32_t *slot_of) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const unsigned long long k = group_key[i];
+    const unsigned long long w = (priority_of(in, i) << 33) | ((unsigned long long)(in.conv_n[i] == 0) << 32) | (unsigned long long)i;
+    unsigned long long h = mix_key(k) & mask;
+    for (;;) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkeys + h);
+        if (cur == kEmptyKey) cur = atomicCAS(tkeys + h, kEmptyKey, k);
+        if (cur == kEmptyKey || cur == k) break;
+        h = (h + 1) & mask;
+    }
+    atomicMax(tvals + h, w);
+    slot_of[i] = (uint32_t)h;
+}
+
+__global__ void hash_winner_kernel(DedupIn in, const unsigned long long *tvals, const uint32_t *slot_of, uint8_t *flag, uint32_t *iota) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    flag[i] = (uint32_t)tvals[slot_of[i]] == (uint32_t)i;      // the winner's BAM index sits in the low word
+    iota[i] = (uint32_t)i;
+}
+
+// dedup sort key (see sort_key_kernel) of the surviving reads only
+__global__ void survivor_key_kernel(DedupIn in, const uint32_t *winners, long long n_out, int low_bits, unsigned long long *key) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    const long long i = winners[j];
+    const unsigned long long ord = in.ord_of_barcode ? in.ord_of_barcode[in.barcode[i]] : 0u;
+    key[j] = (priority_of(in, i) << low_bits) | (ord << 2) | ((unsigned long long)(in.strand[i] != 0) << 1) | (unsigned long long)(in.conv_n[i] == 0);
+}
+
+__global__ void survivor_final_key_kernel(DedupIn in, const uint32_t *winners, long long n_out, const unsigned long long *extra, int extra_bits,
+                                          unsigned long long *key) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    const uint32_t r = winners[j];
+    const unsigned long long split = in.split_of_barcode ? in.split_of_barcode[in.barcode[r]] : 0u;
+    key[j] = ((((split << 1) | (unsigned long long)(in.strand[r] != 0))) << extra_bits) | (extra ? extra[r] : 0ull);
+}
+
 inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 inline int bits_for(uint64_t max_value) {
@@ -217,6 +283,79 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
     const bool has_hi = d_key_hi != nullptr && key_hi_bits > 0;
     const size_t n = (size_t)n_reads;
 
+    DedupIn in;
+    in.counts = reinterpret_cast<const uint4 *>(d_counts);
+    in.strand = d_strand; in.transcriptome = d_transcriptome; in.score = d_score; in.conv_n = d_conv_n;
+    in.barcode = d_barcode; in.ord_of_barcode = d_ord_of_barcode; in.split_of_barcode = d_split_of_barcode;
+    in.n = n_reads; in.conv_mask = conv_mask & 0xfffu; in.use_conversions = use_conversions;
+    const unsigned g = grid_for(n_reads);
+    if (!d_final_extra) final_extra_bits = 0;
+    if (n_splits < 1 || !d_split_of_barcode) n_splits = 1;
+    const int top_bits = bits_for((uint64_t)(2 * n_splits));
+    DYN_ARG(final_extra_bits >= 0 && top_bits + final_extra_bits <= 64, "final key does not fit 64 bits");
+
+    // ---- hash path (64-bit group keys; the all-ones key is the table's empty mark): one atomicMax per read finds the
+    //      winners, only the survivors are sorted.  DYN_DEDUP_SORT=1 forces the three-sort path below.
+    static const bool force_sort = getenv("DYN_DEDUP_SORT") != nullptr;
+    if (!has_hi && key_lo_bits < 64 && !force_sort) {
+        size_t cap = 1;
+        while (cap < 2 * n) cap <<= 1;
+        size_t tmp_bytes = 0, t = 0;
+        {
+            cub::DoubleBuffer<uint32_t> v32(nullptr, nullptr);
+            cub::DoubleBuffer<unsigned long long> k64(nullptr, nullptr);
+            cub::DeviceRadixSort::SortPairs(nullptr, t, k64, v32, n_reads, 0, 64, stream);
+            tmp_bytes = t;
+            cub::DeviceSelect::Flagged(nullptr, t, (uint32_t *)nullptr, (uint8_t *)nullptr, (uint32_t *)nullptr, (long long *)nullptr, n_reads, stream);
+            if (t > tmp_bytes) tmp_bytes = t;
+        }
+        unsigned long long *tkeys, *tvals, *ka, *kb;
+        uint32_t *slot_of, *iota, *wa, *wb;
+        uint8_t *flag;
+        void *tmp;
+        Arena ar;
+        for (int pass = 0; pass < 2; ++pass) {
+            tkeys = ar.take<unsigned long long>(cap); tvals = ar.take<unsigned long long>(cap);
+            slot_of = ar.take<uint32_t>(n); iota = ar.take<uint32_t>(n);
+            wa = ar.take<uint32_t>(n); wb = ar.take<uint32_t>(n);
+            ka = ar.take<unsigned long long>(n); kb = ar.take<unsigned long long>(n);
+            flag = ar.take<uint8_t>(n);
+            tmp = ar.take<uint8_t>(tmp_bytes);
+            if (pass == 0) {
+                void *base = nullptr;
+                int rc = dyn_ctx_scratch(ctx, 8, ar.used + 256, &base);
+                if (rc) return rc;
+                ar = Arena(base);
+            }
+        }
+        DYN_CUDA(cudaMemsetAsync(tkeys, 0xff, 8 * cap, stream));
+        DYN_CUDA(cudaMemsetAsync(tvals, 0, 8 * cap, stream));
+        hash_insert_kernel<<<g, kBlock, 0, stream>>>(in, reinterpret_cast<const unsigned long long *>(d_key_lo), tkeys, tvals, cap - 1, slot_of);
+        hash_winner_kernel<<<g, kBlock, 0, stream>>>(in, tvals, slot_of, flag, iota);
+        t = tmp_bytes;
+        DYN_CUDA(cub::DeviceSelect::Flagged(tmp, t, iota, flag, wa, reinterpret_cast<long long *>(d_n_out), n_reads, stream));
+        long long *h_n = reinterpret_cast<long long *>(ctx->h_small + 16);
+        DYN_CUDA(cudaMemcpyAsync(h_n, d_n_out, 8, cudaMemcpyDeviceToHost, stream));
+        DYN_CUDA(cudaStreamSynchronize(stream));          // the survivor sorts are sized by their number
+        const long long n_out = *h_n;
+        if (n_out == 0) return DYN_OK;
+        const unsigned go = grid_for(n_out);
+        const int low_bits = (d_ord_of_barcode ? bits_for((uint64_t)(n_barcodes > 0 ? n_barcodes - 1 : 0)) : 0) + 2;
+        survivor_key_kernel<<<go, kBlock, 0, stream>>>(in, wa, n_out, low_bits, ka);
+        cub::DoubleBuffer<unsigned long long> k(ka, kb);
+        cub::DoubleBuffer<uint32_t> v(wa, wb);
+        t = tmp_bytes;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k, v, n_out, 0, low_bits + 30, stream));
+        survivor_final_key_kernel<<<go, kBlock, 0, stream>>>(in, v.Current(), n_out, reinterpret_cast<const unsigned long long *>(d_final_extra),
+                                                             final_extra_bits, k.Alternate());
+        cub::DoubleBuffer<unsigned long long> k2(k.Alternate(), k.Current());
+        t = tmp_bytes;
+        DYN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t, k2, v, n_out, 0, top_bits + final_extra_bits, stream));
+        DYN_CUDA(cudaMemcpyAsync(d_out_idx, v.Current(), 4 * (size_t)n_out, cudaMemcpyDeviceToDevice, stream));
+        DYN_CUDA(cudaGetLastError());
+        return DYN_OK;
+    }
+
     size_t tmp_bytes = 0, t = 0;
     {
         cub::DoubleBuffer<uint32_t> k32(nullptr, nullptr), v32(nullptr, nullptr);
@@ -248,13 +387,6 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
             ar = Arena(base);
         }
     }
-
-    DedupIn in;
-    in.counts = reinterpret_cast<const uint4 *>(d_counts);
-    in.strand = d_strand; in.transcriptome = d_transcriptome; in.score = d_score; in.conv_n = d_conv_n;
-    in.barcode = d_barcode; in.ord_of_barcode = d_ord_of_barcode; in.split_of_barcode = d_split_of_barcode;
-    in.n = n_reads; in.conv_mask = conv_mask & 0xfffu; in.use_conversions = use_conversions;
-    const unsigned g = grid_for(n_reads);
 
     // 1 + 2. dedup sort: one stable sort of the reads (BAM order) by [priority | barcode order | strand | no-mismatch]
     //        -> `order` = read indices, ascending (priority, split-file order)
@@ -303,10 +435,6 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
     // 5. per split: forward-strand genes first, then reverse (stable); padding keys sort to the end
     // (an optional per-read extra key orders rows inside a (split, strand) block: the no-UMI path sorts by
     // (barcode, GX), conversion.py:193-196)
-    if (!d_final_extra) final_extra_bits = 0;
-    if (n_splits < 1 || !d_split_of_barcode) n_splits = 1;
-    const int top_bits = bits_for((uint64_t)(2 * n_splits));
-    DYN_ARG(final_extra_bits >= 0 && top_bits + final_extra_bits <= 64, "final key does not fit 64 bits");
     const unsigned long long pad = (top_bits + final_extra_bits == 64) ? ~0ull : ((unsigned long long)(2 * n_splits) << final_extra_bits);
     final_key_kernel<<<g, kBlock, 0, stream>>>(in, winners, reinterpret_cast<const long long *>(d_n_out), pad,
                                                reinterpret_cast<const unsigned long long *>(d_final_extra), final_extra_bits, k64a);

@@ -167,3 +167,30 @@ def test_group_key(gpu_ctx):
         check(gpu_ctx.lib.dyn_group_key(gpu_ctx.handle, ptr(bc), ptr(umi), ptr(gene), n, umi_bits, gene_bits, ptr(key), _stream()))
         want = (bc.to(torch.int64) << (umi_bits + gene_bits)) | ((umi & ((1 << umi_bits) - 1)) << gene_bits) | gene.to(torch.int64)
         assert torch.equal(key, want)
+
+
+@pytest.mark.parametrize('n,n_barcodes,n_umis', [(1, 1, 1), (300_000, 37, 900), (200_000, 3, 20)])
+def test_dedup_hash_path_equals_the_stable_sort_definition(gpu_ctx, n, n_barcodes, n_umis):
+    """dyn_dedup_umi's atomicMax winner selection against the numpy restatement of the reference's stable sorts
+    (tests/fake_device.py::dedup: conversion.py:225-243, 541-606) on tie-heavy groups: identical survivor list, in order."""
+    import fake_device
+    from dynast_b200 import pipeline
+    g = torch.Generator().manual_seed(n + n_barcodes)
+    dev = torch.device('cuda', 0)
+    barcode = torch.randint(0, n_barcodes, (n,), generator=g, dtype=torch.int32)
+    umi = torch.randint(0, n_umis, (n,), generator=g, dtype=torch.int64)
+    gene = torch.randint(0, 50, (n,), generator=g, dtype=torch.int32)
+    strand = (gene % 2).to(torch.uint8)
+    counts = torch.randint(0, 3, (n, 16), generator=g, dtype=torch.uint8)
+    counts[:, :12] = counts[:, :12] * (torch.rand((n, 12), generator=g) < 0.15)
+    score = torch.randint(50, 54, (n,), generator=g, dtype=torch.int16)          # few distinct scores: many priority ties
+    transcriptome = (torch.rand(n, generator=g) < 0.7).to(torch.uint8)
+    conv_n = counts[:, :12].sum(dim=1).to(torch.int16)
+    key = (barcode.to(torch.int64) << 40) | (umi << 8) | gene.to(torch.int64)
+    for use_conv in (True, False):
+        want = fake_device.dedup(None, key, counts, strand, transcriptome, score, conv_n, barcode, n_barcodes, conversions=('TC',),
+                                 use_conversions=use_conv, key_lo_bits=48, split_threshold=20000)
+        got = pipeline.dedup(gpu_ctx, key.to(dev), counts.to(dev), strand.to(dev), transcriptome.to(dev), score.to(dev), conv_n.to(dev),
+                             barcode.to(dev), n_barcodes, conversions=('TC',), use_conversions=use_conv, key_lo_bits=48, split_threshold=20000)
+        torch.cuda.synchronize()
+        assert torch.equal(got.cpu().to(torch.int64), want.to(torch.int64))
