@@ -142,10 +142,11 @@ __global__ void copy_u32_kernel(const uint32_t *src, uint32_t *dst, const long l
 }
 
 // ---- hash path: the winner of every (barcode, umi, gene) group by one atomicMax per read ---------------------------
-// Within a group the barcode (hence its place in the split-file order) and the gene's strand are the same for every
-// member, so the member that ends up last after the reference's stable sorts is the one with the largest
-// (priority, no-mismatch flag, BAM index): 63 bits, one 64-bit atomicMax into an open-addressing table keyed by the
-// group key.  No sort over all reads: only the survivors (less than half of them in UMI data) are sorted afterwards.
+// Within a group the barcode (hence its place in the split-file order) is the same for every member, so the member
+// that ends up last after the reference's stable sorts is the one with the largest (priority, gene strand, no-mismatch
+// flag, BAM index) -- 30 + 1 + 1 + 32 bits: one 64-bit atomicMax into an open-addressing table keyed by the group key
+// (the strand differs inside a group only on the no-UMI path, whose groups are read ids: conversion.py:148-200).
+// Key and value share a 16-byte slot, so a read touches one 32-byte sector of the table.  No sort over all reads: only the survivors (less than half of them in UMI data) are sorted afterwards.
 constexpr unsigned long long kEmptyKey = ~0ull;
 
 __device__ __forceinline__ unsigned long long mix_key(unsigned long long x) {
@@ -165,27 +166,34 @@ __device__ __forceinline__ unsigned long long priority_of(const DedupIn &in, lon
     return (has << 29) | ((unsigned long long)(in.transcriptome[i] != 0) << 28) | ((unsigned long long)in.score[i] << 12) | (sum & 0xfffu);
 }
 
-__global__ void hash_insert_kernel(DedupIn in, const unsigned long long *group_key, unsigned long long *tkeys, unsigned long long *tvals,
-                                   unsigned long long mask, uint32_t *slot_of) {
+__global__ void hash_init_kernel(ulonglong2 *table, unsigned long long cap) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < cap) table[i] = make_ulonglong2(kEmptyKey, 0ull);
+}
+
+__global__ void hash_insert_kernel(DedupIn in, const unsigned long long *group_key, ulonglong2 *table, unsigned long long mask,
+                                   uint32_t *slot_of) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= in.n) return;
     const unsigned long long k = group_key[i];
-    const unsigned long long w = (priority_of(in, i) << 33) | ((unsigned long long)(in.conv_n[i] == 0) << 32) | (unsigned long long)i;
+    const unsigned long long w = (priority_of(in, i) << 34) | ((unsigned long long)(in.strand[i] != 0) << 33) |
+                                 ((unsigned long long)(in.conv_n[i] == 0) << 32) | (unsigned long long)i;
     unsigned long long h = mix_key(k) & mask;
     for (;;) {
-        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkeys + h);
-        if (cur == kEmptyKey) cur = atomicCAS(tkeys + h, kEmptyKey, k);
+        unsigned long long *slot_key = &table[h].x;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(slot_key);
+        if (cur == kEmptyKey) cur = atomicCAS(slot_key, kEmptyKey, k);
         if (cur == kEmptyKey || cur == k) break;
         h = (h + 1) & mask;
     }
-    atomicMax(tvals + h, w);
+    atomicMax(&table[h].y, w);
     slot_of[i] = (uint32_t)h;
 }
 
-__global__ void hash_winner_kernel(DedupIn in, const unsigned long long *tvals, const uint32_t *slot_of, uint8_t *flag, uint32_t *iota) {
+__global__ void hash_winner_kernel(DedupIn in, const ulonglong2 *table, const uint32_t *slot_of, uint8_t *flag, uint32_t *iota) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= in.n) return;
-    flag[i] = (uint32_t)tvals[slot_of[i]] == (uint32_t)i;      // the winner's BAM index sits in the low word
+    flag[i] = (uint32_t)table[slot_of[i]].y == (uint32_t)i;      // the winner's BAM index sits in the low word
     iota[i] = (uint32_t)i;
 }
 
@@ -309,13 +317,14 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
             cub::DeviceSelect::Flagged(nullptr, t, (uint32_t *)nullptr, (uint8_t *)nullptr, (uint32_t *)nullptr, (long long *)nullptr, n_reads, stream);
             if (t > tmp_bytes) tmp_bytes = t;
         }
-        unsigned long long *tkeys, *tvals, *ka, *kb;
+        ulonglong2 *table;
+        unsigned long long *ka, *kb;
         uint32_t *slot_of, *iota, *wa, *wb;
         uint8_t *flag;
         void *tmp;
         Arena ar;
         for (int pass = 0; pass < 2; ++pass) {
-            tkeys = ar.take<unsigned long long>(cap); tvals = ar.take<unsigned long long>(cap);
+            table = ar.take<ulonglong2>(cap);
             slot_of = ar.take<uint32_t>(n); iota = ar.take<uint32_t>(n);
             wa = ar.take<uint32_t>(n); wb = ar.take<uint32_t>(n);
             ka = ar.take<unsigned long long>(n); kb = ar.take<unsigned long long>(n);
@@ -328,10 +337,9 @@ extern "C" int dyn_dedup_umi(dyn_ctx_t *ctx, const uint64_t *d_key_hi, const uin
                 ar = Arena(base);
             }
         }
-        DYN_CUDA(cudaMemsetAsync(tkeys, 0xff, 8 * cap, stream));
-        DYN_CUDA(cudaMemsetAsync(tvals, 0, 8 * cap, stream));
-        hash_insert_kernel<<<g, kBlock, 0, stream>>>(in, reinterpret_cast<const unsigned long long *>(d_key_lo), tkeys, tvals, cap - 1, slot_of);
-        hash_winner_kernel<<<g, kBlock, 0, stream>>>(in, tvals, slot_of, flag, iota);
+        hash_init_kernel<<<(unsigned)((cap + kBlock - 1) / kBlock), kBlock, 0, stream>>>(table, cap);
+        hash_insert_kernel<<<g, kBlock, 0, stream>>>(in, reinterpret_cast<const unsigned long long *>(d_key_lo), table, cap - 1, slot_of);
+        hash_winner_kernel<<<g, kBlock, 0, stream>>>(in, table, slot_of, flag, iota);
         t = tmp_bytes;
         DYN_CUDA(cub::DeviceSelect::Flagged(tmp, t, iota, flag, wa, reinterpret_cast<long long *>(d_n_out), n_reads, stream));
         long long *h_n = reinterpret_cast<long long *>(ctx->h_small + 16);

@@ -1,7 +1,7 @@
 """`dynast estimate` -- thin orchestrator with the stage order, options and output files of
 dynast/estimate.py:15-429 (reference), calling the B200 operators of dynast_b200.estimation.
 
-Not carried over: `--downsample*` (host-side row sampling, utils.py:307-347) -- raises NotImplementedError.
+`--downsample*` is the reference's host-side row sampling (utils.py:307-347), reproduced with the same numpy generator.
 The AnnData object is written only when `anndata` is importable; the layers / obs columns are returned either way."""
 import datetime as dt
 import gzip
@@ -44,8 +44,6 @@ def estimate(
     seed: Optional[int] = None,
 ):
     """estimate.estimate (estimate.py:15-429). Returns the results object (AnnData or utils.Results; None for --control)."""
-    if downsample:
-        raise NotImplementedError('--downsample is not part of the B200 hot path')
     t0 = time.time()
     start = dt.datetime.now()
     os.makedirs(out_dir, exist_ok=True)
@@ -79,6 +77,12 @@ def estimate(
             group_cells.setdefault(g, []).append(b)
         df_unc = df_unc[df_unc['barcode'].isin(groups.keys())].reset_index(drop=True)
         df_unc['group'] = df_unc['barcode'].map(groups).astype('category')
+
+    if downsample:          # estimate.py:129-152
+        is_count = int(downsample) == downsample
+        by = {'cell': ['barcode'], 'group': ['group']}.get(downsample_mode)
+        df_unc = utils.downsample_counts(df_unc, proportion=None if is_count else downsample, count=int(downsample) if is_count else None,
+                                         seed=seed, group_by=by)
 
     transcriptome_any = bool(df_unc['transcriptome'].any())
     transcriptome_all = bool(df_unc['transcriptome'].all())

@@ -21,6 +21,26 @@ def flatten_iter(it):
             yield x
 
 
+def downsample_counts(df_counts: pd.DataFrame, proportion: Optional[float] = None, count: Optional[int] = None,
+                      seed: Optional[int] = None, group_by: Optional[List[str]] = None) -> pd.DataFrame:
+    """utils.downsample_counts (utils.py:307-347): rows kept are drawn with numpy's Generator.choice(shuffle=False,
+    replace=False), seeded like the reference, so that the same seed keeps the same rows."""
+    rng = np.random.default_rng(seed)
+    if not group_by:
+        if bool(proportion) == bool(count):
+            raise Exception('Only one of `proportion` or `count` must be provided.')
+        n_keep = int(df_counts.shape[0] * proportion) if proportion is not None else count
+        return df_counts.iloc[rng.choice(df_counts.shape[0], n_keep, shuffle=False, replace=False)]
+    if not count:
+        raise Exception('`count` must be provided when using `group_by`')
+    parts = []
+    for _, df_group in df_counts.groupby(group_by, sort=False, observed=True):
+        if df_group.shape[0] > count:
+            df_group = df_group.iloc[rng.choice(df_group.shape[0], count, shuffle=False, replace=False)]
+        parts.append(df_group)
+    return pd.concat(parts)
+
+
 def counts_to_matrix(df_counts: pd.DataFrame, barcodes: List[str], features: List[str], barcode_column: str = 'barcode',
                      feature_column: str = 'GX') -> sparse.csr_matrix:
     """utils.counts_to_matrix (utils.py:350-380): reads per (barcode, feature) as a float32 CSR matrix with rows /
