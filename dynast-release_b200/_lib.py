@@ -39,6 +39,7 @@ PROTOTYPES = {
     'dyn_aggregate_kn': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _u32, _u32, _u32, _i32, _i32, _i32, _vp, _vp, _vp,
                                 _vp, _vp]),
     'dyn_kn_csr': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'dyn_kn_csr_pairs': (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_pi_fit': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'dyn_consensus': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'dyn_coverage': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),

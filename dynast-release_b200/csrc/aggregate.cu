@@ -218,6 +218,32 @@ __global__ void kn_csr_kernel(const unsigned long long *key, const uint32_t *cou
     }
 }
 
+// ---- CSR over the (group, gene) pairs that OCCUR (the per-(cell, gene) fit of pi.py:253-296 with group_by = [barcode,
+// GX]): rows sorted by key, a pair = the key without its 22 (k, n) bits.  Pair j gets rows [off[j], off[j + 1]).
+__global__ void pair_head_kernel(const unsigned long long *key, const long long *n_rows_p, long long max_rows, uint32_t *head) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= max_rows) return;
+    head[i] = (i < *n_rows_p && (i == 0 || (key[i] >> 22) != (key[i - 1] >> 22))) ? 1u : 0u;
+}
+
+__global__ void pair_fill_kernel(const unsigned long long *key, const uint32_t *count, const long long *n_rows_p, const uint32_t *head,
+                                 const uint32_t *pair_of_row, long long max_rows, int32_t *k, int32_t *n, long long *cnt, long long *off,
+                                 unsigned long long *pair_key, unsigned long long *total, long long *n_pairs) {
+    const long long n_rows = *n_rows_p;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n_rows) {
+        const unsigned long long kk = key[i];
+        k[i] = (int32_t)((kk >> 10) & 0xfff);
+        n[i] = (int32_t)(kk & 0x3ff);
+        cnt[i] = (long long)count[i];
+        const uint32_t p = pair_of_row[i] - 1u;      // inclusive head count -> 0-based pair number
+        if (head[i]) { off[p] = i; pair_key[p] = kk >> 22; }
+        atomicAdd(total + p, (unsigned long long)count[i]);
+        if (i == n_rows - 1) { off[p + 1] = n_rows; *n_pairs = (long long)p + 1; }
+    }
+    if (i == 0 && n_rows == 0) { off[0] = 0; *n_pairs = 0; }
+}
+
 // ---- a16: alpha = (reads with a conversion / reads) / pi_c   (alpha.py:72-84)
 __global__ void alpha_kernel(const unsigned long long *n_reads, const unsigned long long *n_with, const double *pi_c,
                              long long n_groups, double *alpha) {
@@ -375,6 +401,48 @@ extern "C" int dyn_alpha(dyn_ctx_t *ctx, const uint64_t *d_n_reads, const uint64
     alpha_kernel<<<grid_for(n_groups), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const unsigned long long *>(d_n_reads), reinterpret_cast<const unsigned long long *>(d_n_with),
         d_pi_c, n_groups, d_alpha);
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}
+
+extern "C" int dyn_kn_csr_pairs(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count, const int64_t *d_n_rows,
+                                int64_t max_rows, int32_t *d_k, int32_t *d_n, int64_t *d_cnt, int64_t *d_off, uint64_t *d_pair_key,
+                                uint64_t *d_total, int64_t *d_n_pairs, void *stream_) {
+    DYN_ARG(ctx != nullptr, "null context");
+    CtxEnter enter_(ctx, stream_);
+    DYN_ARG(max_rows >= 0 && max_rows < 0x7fffffffLL, "max_rows out of range");
+    DYN_ARG(d_n_rows && d_off && d_n_pairs, "null buffer");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DYN_CUDA(cudaMemsetAsync(d_n_pairs, 0, 8, stream));
+    DYN_CUDA(cudaMemsetAsync(d_off, 0, 8, stream));
+    if (max_rows == 0) return DYN_OK;
+    DYN_ARG(d_keys && d_count && d_k && d_n && d_cnt && d_pair_key && d_total, "null rows");
+    DYN_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint64_t) * (size_t)max_rows, stream));
+    size_t tmp_bytes = 0;
+    DYN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_rows, stream));
+    uint32_t *head, *pair_of_row;
+    void *tmp;
+    Arena ar;
+    for (int pass = 0; pass < 2; ++pass) {
+        head = ar.take<uint32_t>((size_t)max_rows);
+        pair_of_row = ar.take<uint32_t>((size_t)max_rows);
+        tmp = ar.take<uint8_t>(tmp_bytes);
+        if (pass == 0) {
+            void *base = nullptr;
+            int rc = dyn_ctx_scratch(ctx, 9, ar.used + 256, &base);
+            if (rc) return rc;
+            ar = Arena(base);
+        }
+    }
+    pair_head_kernel<<<grid_for(max_rows), kBlock, 0, stream>>>(reinterpret_cast<const unsigned long long *>(d_keys),
+                                                                reinterpret_cast<const long long *>(d_n_rows), max_rows, head);
+    // pair index of a row = (number of heads up to and including it) - 1
+    DYN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, head, pair_of_row, (int)max_rows, stream));
+    pair_fill_kernel<<<grid_for(max_rows), kBlock, 0, stream>>>(
+        reinterpret_cast<const unsigned long long *>(d_keys), d_count, reinterpret_cast<const long long *>(d_n_rows), head, pair_of_row,
+        max_rows, d_k, d_n, reinterpret_cast<long long *>(d_cnt), reinterpret_cast<long long *>(d_off),
+        reinterpret_cast<unsigned long long *>(d_pair_key), reinterpret_cast<unsigned long long *>(d_total),
+        reinterpret_cast<long long *>(d_n_pairs));
     DYN_CUDA(cudaGetLastError());
     return DYN_OK;
 }

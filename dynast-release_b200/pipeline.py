@@ -309,6 +309,24 @@ def kn_csr(ctx: Context, keys, count32, n_rows, n_groups: int):
     return k[:m], n[:m], c[:m], off, total[:n_groups]
 
 
+def kn_csr_pairs(ctx: Context, keys, count32, n_rows):
+    """dyn_kn_csr_pairs on key-sorted rows WITH gene bits -> (k, n, count, off [P + 1], pair_key [P], total [P]): one CSR
+    row per (group, gene) pair that occurs -- the groups of the per-(cell, gene) fit (pi.py:253-296)."""
+    dev = keys.device
+    m = keys.numel()
+    k = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+    n = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+    c = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    off = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+    pair_key = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    total = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    n_pairs = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(ctx.lib.dyn_kn_csr_pairs(ctx.handle, ptr(keys), ptr(count32), ptr(n_rows), m, ptr(k), ptr(n), ptr(c), ptr(off), ptr(pair_key),
+                                   ptr(total), ptr(n_pairs), _stream()))
+    P = int(n_pairs.item())
+    return k[:m], n[:m], c[:m], off[:P + 1], pair_key[:P], total[:P]
+
+
 READ_ROW_BYTES = 40
 
 
@@ -422,7 +440,8 @@ def consensus(ctx: Context, records: torch.Tensor, item_rec16: torch.Tensor, gro
 def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score, strand, n_barcodes: int, n_genes: int,
                       out: TallyBuffers, conversions=('TC',), quality: int = 27, umi_bits: int = 24,
                       cell_threshold: int = 1000, with_pi: bool = True, timings: Optional[dict] = None, group=None,
-                      exchange: bool = False, tallied=None, transcriptome=None):
+                      exchange: bool = False, tallied=None, transcriptome=None, method: str = 'alpha',
+                      cell_gene_threshold: int = 16):
     """Runs every stage of the path on device tensors (the packed records of one GPU's read range plus the
     interned barcode / umi / gene ids of its reads).  Mirrors count() then estimate(method='alpha') of the
     reference: count_conversions (count.py:306) -> estimate_p_e (estimate.py:197-234) -> aggregate_counts
@@ -431,6 +450,9 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
     exchange=True (multi-GPU, read-range sharding): `barcode` holds GLOBAL barcode ids and n_barcodes the global
     count; after the tally every read's row goes to rank barcode % world (distributed.exchange_reads) and the rest
     of the path runs on the barcodes this rank owns (local id = global id // world).
+    method = 'pi_g' adds the per-(cell, gene) fit of estimate(method='pi_g') (estimate.py:282-327, pi.py:253-296): every
+    (barcode, gene) pair with at least `cell_gene_threshold` reads gets its own (alpha, beta, pi) from the barcode's p_e /
+    p_c -- result keys `pi_g` [P, 3], `pi_g_status`, `pi_g_pair` (barcode << gene_bits | gene), `pi_g_reads`.
     tallied = (counts [n, 16] uint8, conv_n [n] int16): the tally already ran (tally_bam streams it chunk by chunk while
     the BAM is being read) and records / rec_off / out are not used; transcriptome = the reads' gene-tag-present flag."""
     dev = barcode.device
@@ -503,6 +525,19 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
         pi_c = torch.where(ok & (pi_status == 0), abp[:, 2], torch.full_like(p_c, float('nan')))
         res.update(pi=abp, pi_status=pi_status, alpha=alpha(ctx, n_reads, n_with, pi_c))
         mark('pi')
+    if method == 'pi_g':
+        rows_g = aggregate_kn(ctx, counts, strand, barcode, gene, n_barcodes, n_genes, conversions, sel=sel, first_appearance=False)
+        gk, gn, gc, goff, pair_key, pair_total = kn_csr_pairs(ctx, rows_g['keys'], rows_g['count32'], rows_g['n_rows'])
+        bc_of_pair = pair_key >> gene_bits
+        fit = (em_status[bc_of_pair] == 0) & (pair_total >= cell_gene_threshold)
+        pc_g = torch.where(fit, p_c[bc_of_pair], torch.full_like(p_c[bc_of_pair], float('nan')))
+        pe_g = torch.nan_to_num(p_e[bc_of_pair], nan=0.0)
+        glens = goff[1:] - goff[:-1]
+        g_max = int(glens.max().item()) if glens.numel() else 1
+        abp_g, st_g = pi_fit(ctx, gk, gn, gc, goff, pe_g, pc_g, max_cells=g_max)
+        st_g = torch.where(fit, st_g, torch.full_like(st_g, -1))          # -1: below the threshold / no p_c for the barcode
+        res.update(pi_g=abp_g, pi_g_status=st_g, pi_g_pair=pair_key, pi_g_reads=pair_total, pi_g_hist=(gk, gn, gc, goff))
+        mark('pi_g')
     if timings is not None:
         stream.synchronize()
         for (_, a), (name, b) in zip(marks[:-1], marks[1:]):

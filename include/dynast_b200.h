@@ -272,6 +272,13 @@ int dyn_aggregate_kn(dyn_ctx_t *ctx, const uint8_t *d_counts, const uint8_t *d_s
 int dyn_kn_csr(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count, const int64_t *d_n_rows,
                int64_t max_rows, int64_t n_groups, int32_t *d_k, int32_t *d_n, int64_t *d_cnt, int64_t *d_off,
                uint64_t *d_total, void *stream);
+/* The same for key-sorted rows WITH a gene field: the input of the per-(cell, gene) fit (estimate_pi with group_by =
+ * [barcode, GX], pi.py:253-296; estimate.py:282-327 method 'pi_g').  Only the (group, gene) pairs that occur get a CSR
+ * row: pair j has key d_pair_key[j] = group << gene_bits | gene, triplets [d_off[j], d_off[j + 1]) and d_total[j]
+ * reads; *d_n_pairs pairs in all (device scalar).  Outputs need room for max_rows (+ 1 for d_off) entries. */
+int dyn_kn_csr_pairs(dyn_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_count, const int64_t *d_n_rows,
+                     int64_t max_rows, int32_t *d_k, int32_t *d_n, int64_t *d_cnt, int64_t *d_off, uint64_t *d_pair_key,
+                     uint64_t *d_total, int64_t *d_n_pairs, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a15: batched labeled-fraction fit -- posterior means of (alpha, beta, pi_g) of dynast/models/pi.stan

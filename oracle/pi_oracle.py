@@ -56,3 +56,32 @@ def posterior_means(k, n, count, p_e, p_c, n_gl=40):
         wt = np.exp(lw + np.log(m0) - sc)
         Z += wt; Ea += wt * al; Eb += wt * be; Ep += wt * m1 / m0
     return Ea / Z, Eb / Z, Ep / Z
+
+
+def posterior_means_sampled(k, n, count, p_e, p_c, draws=2_000_000, seed=0):
+    """The same posterior means by plain Monte Carlo, independent of any quadrature: (log_alpha, log_beta) ~ U(-3, 3)^2
+    and pi ~ Beta(alpha, beta) are drawn from the PRIOR of pi.stan (pi.stan:20-25) and weighted by the likelihood
+    (pi.stan:27-33) -- self-normalised importance sampling.  Returns (alpha, beta, pi, effective sample size); the
+    Monte-Carlo error is about sd / sqrt(ESS)."""
+    rng = np.random.default_rng(seed)
+    k = np.asarray(k, dtype=np.float64); n = np.asarray(n, dtype=np.float64); c = np.asarray(count, dtype=np.float64)
+    keep = (c > 0) & (n > 0)
+    k, n, c = k[keep], n[keep], c[keep]
+    la = k * np.log(p_c) + (n - k) * np.log1p(-p_c)
+    lb = k * np.log(p_e) + (n - k) * np.log1p(-p_e)
+    m = np.maximum(la, lb)
+    a, b = np.exp(la - m), np.exp(lb - m)
+    tot = np.zeros(4)
+    w2 = 0.0
+    lmax = None
+    for _ in range(max(1, draws // 200_000)):
+        al = np.exp(rng.uniform(-3, 3, 200_000))
+        be = np.exp(rng.uniform(-3, 3, 200_000))
+        pi = np.clip(rng.beta(al, be), 1e-300, 1 - 1e-16)
+        ll = (c[None, :] * np.log(pi[:, None] * a[None, :] + (1.0 - pi[:, None]) * b[None, :])).sum(axis=1)
+        if lmax is None:
+            lmax = ll.max()
+        w = np.exp(ll - lmax)
+        tot += np.array([w.sum(), (w * al).sum(), (w * be).sum(), (w * pi).sum()])
+        w2 += (w * w).sum()
+    return tot[1] / tot[0], tot[2] / tot[0], tot[3] / tot[0], tot[0]**2 / w2
