@@ -262,6 +262,44 @@ def reference_arm(args):
     return 0
 
 
+def multi_gpu_bit_equal(ctx, dist, rank, world, device, local_rank):
+    """ONE global batch, sharded by read range over the ranks and pushed through the whole path with the per-read
+    exchange, against the same batch on one GPU: per-barcode read counts, p_e, EM status and p_c must be identical bit
+    for bit.  Returns True / False on every rank."""
+    import torch
+    from dynast_b200 import distributed, pipeline
+    n_reads, n_bc = 2_000_000, 503
+    b = pipeline.SynthBatch(n_reads, seed=77, n_barcodes=n_bc, n_genes=300, device=local_rank, reads_per_umi=3.0)
+
+    def run(lo, hi, exchange):
+        off = b.rec_off[lo:hi + 1].to(torch.int64) & 0xffffffff
+        rec = b.records[int(off[0]) * 16:int(off[-1]) * 16]
+        out = pipeline.TallyBuffers(hi - lo, 4 * (hi - lo) + 1024, device=local_rank)
+        return pipeline.count_to_estimate(ctx, rec, (off - off[0]).to(torch.int32), b.barcode[lo:hi], b.umi[lo:hi], b.gene[lo:hi],
+                                          b.score[lo:hi], b.strand[lo:hi], n_bc, b.n_genes, out, cell_threshold=50, with_pi=False,
+                                          exchange=exchange)
+
+    def columns(res):       # [4, n] int64: read count, p_e bits, EM status, p_c bits where the fit succeeded
+        ok = res['em_status'] == 0
+        return torch.stack([res['n_reads'].to(torch.int64), res['p_e'].view(torch.int64), res['em_status'].to(torch.int64),
+                            torch.where(ok, res['p_c'].view(torch.int64), torch.zeros_like(res['p_c'].view(torch.int64)))])
+
+    lo, hi = distributed.read_range(n_reads, rank, world)
+    mine = columns(run(lo, hi, True))                 # barcodes rank, rank + world, ...
+    per = (n_bc + world - 1) // world
+    pad = torch.zeros((4, per), dtype=torch.int64, device=device)
+    pad[:, :mine.shape[1]] = mine
+    every = torch.empty((world, 4, per), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(every, pad)
+    same = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == 0:
+        whole = columns(run(0, n_reads, False))
+        sharded = every.permute(1, 2, 0).reshape(4, per * world)[:, :n_bc]      # barcode g sits at [g // world] of rank g % world
+        same[0] = int(torch.equal(whole, sharded))
+    dist.broadcast(same, src=0)
+    return bool(same.item())
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -614,6 +652,11 @@ def main():
               'dtype': 'f64 E step / f32 M step (as the reference)',
               'exchange': 'none (1 GPU)' if dist is None else 'all-to-all of (barcode,k,n) keys + counts to the barcode owner, device merge + CSR, all-gather of p_c: inside the timed region'}
 
+    # ---------------------------------------------------------------- N > 1: the sharded path against one GPU, bit for bit
+    bit_equal = None
+    if dist is not None:
+        bit_equal = multi_gpu_bit_equal(ctx, dist, rank, world, device, local_rank)
+
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, N = 1)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -646,7 +689,7 @@ def main():
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config, 'gpu_launches': 2 * args.steps,
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'e2e_bam': e2e_bam, 'em': em, 'pipeline': pipe, 'consensus': cons, 'clocks': clocks,
-            'conversions_per_read': n_conv / n_reads,
+            'conversions_per_read': n_conv / n_reads, 'multi_gpu_bit_equal': bit_equal,
         }
         print(json.dumps(line))
     if dist is not None:

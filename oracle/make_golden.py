@@ -320,6 +320,31 @@ def adata_golden():
     print('adata_golden', len(out), 'arrays')
 
 
+def smartseq_counts_tc():
+    """counts_TC.csv of the Smart-seq fixture as `dynast count --conversion TC` writes it: count() passes
+    conversions=['TC'] to count_conversions (count.py:306-318), which changes the tie order of the no-UMI path; the
+    committed fixture was written with conversions=None (what the reference's own test_conversions_paired reproduces).
+    The REFERENCE's count_conversions runs here on the fixture's conversions / alignments / index files."""
+    import tempfile
+    from dynast.preprocessing import conversion as conv
+    import shutil
+    genes = refstub.read_genes() if hasattr(refstub, 'read_genes') else None
+    if genes is None:
+        import pickle
+        with gzip.open(refstub.fixture('genes.pkl.gz'), 'rb') as f:
+            genes = pickle.load(f)
+    tmp = tempfile.mkdtemp()
+    src = refstub.fixture('smartseq_count')
+    op = os.path.join(tmp, 'counts_TC.csv')
+    conv.count_conversions(os.path.join(src, 'conversions.csv'), os.path.join(src, 'alignments.csv'), os.path.join(src, 'conversions.idx'),
+                           op, genes, quality=27, conversions=['TC'], dedup_use_conversions=True, n_threads=2, temp_dir=tmp)
+    out_dir = os.path.join(GOLD, 'smartseq_count_tc')
+    os.makedirs(out_dir, exist_ok=True)
+    _write_gz(os.path.join(out_dir, 'counts_TC.csv.gz'), open(op).read())
+    print('smartseq_count_tc', len(open(op).read().splitlines()) - 1, 'rows')
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     refstub.install()
     os.makedirs(GOLD, exist_ok=True)
@@ -329,6 +354,7 @@ def main():
     synth_counts()
     pi_golden()
     adata_golden()
+    smartseq_counts_tc()
 
 
 if __name__ == '__main__':

@@ -23,8 +23,10 @@ def test_count_smartseq_no_splicing(gpu_ctx, tmp_path):
     for name in ('conversions.csv', 'alignments.csv'):
         assert open(os.path.join(out, name)).read() == ref_text('smartseq_count', name), name
     # count() passes conversions={'TC'} to count_conversions (count.py:306-318), which changes the tie order of the
-    # no-UMI path; the committed fixture was written with conversions=None (what the reference's own
-    # test_conversions_paired reproduces, and tests/test_count_ops.py checks byte for byte): same rows here
+    # no-UMI path relative to the committed fixture (written with conversions=None): compared byte for byte with what the
+    # REFERENCE's count_conversions writes for conversions=['TC'] (oracle/make_golden.py::smartseq_counts_tc)
+    from helpers import golden_text
+    assert open(os.path.join(out, 'counts_TC.csv')).read() == golden_text('smartseq_count_tc', 'counts_TC.csv')
     assert sorted(open(os.path.join(out, 'counts_TC.csv')).read().splitlines()) == sorted(ref_text('smartseq_count', 'counts_TC.csv').splitlines())
     a = pd.read_csv(os.path.join(out, 'rates.csv')).sort_values('barcode').reset_index(drop=True)
     b = pd.read_csv(io.StringIO(ref_text('smartseq_count', 'rates.csv'))).sort_values('barcode').reset_index(drop=True)
