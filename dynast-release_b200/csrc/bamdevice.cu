@@ -237,6 +237,7 @@ struct Staged {          // one run of BGZF blocks, compressed, in page-locked m
     size_t inflated = 0;
     uint32_t first_skip = 0;
     bool last = false;
+    int dev_slot = -1;       // >= 0: the compressed bytes are (being) copied to device buffer pair `dev_slot`
 };
 
 // Everything that is expensive to create (device buffers of several hundred MB, page-locked staging memory): a closed
@@ -244,12 +245,15 @@ struct Staged {          // one run of BGZF blocks, compressed, in page-locked m
 // sizes take a few hundred milliseconds).
 struct IngestBuffers {
     Staged staged[3];
-    DevBuf d_comp, d_blocks, d_inflated, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
+    DevBuf d_comp[2], d_blocks[2];        // double buffered: chunk i + 1 is copied while chunk i is inflated
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    DevBuf d_inflated, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
     struct OutSet { DevBuf blob, rec_off, bc, umi, gene, score, ref_id, pos, hi, flag, gxa; } out[2];
     uint32_t *h_small = nullptr;          // page-locked landing zone
     ~IngestBuffers() {
         for (Staged &s : staged) if (s.bytes) cudaFreeHost(s.bytes);
         if (h_small) cudaFreeHost(h_small);
+        for (cudaEvent_t e : ev_copy) if (e) cudaEventDestroy(e);
     }
 };
 
@@ -264,7 +268,7 @@ struct dyn_bam_dev {
     // options
     bamrec::Tags tags{};
     int lean = 1;
-    size_t chunk_bytes = 512u << 20;       // ~8 000 BGZF blocks: 1.7 waves of the inflate kernel's resident warps
+    size_t chunk_bytes = 1024u << 20;      // ~16 000 BGZF blocks: 3.5 waves of the inflate kernel's resident warps
     // header / file layout (host)
     std::string header_text;
     std::vector<char> ref_names;
@@ -286,8 +290,7 @@ struct dyn_bam_dev {
     int err = 0;
     std::string err_msg;
     IngestBuffers *buf = nullptr;         // shared intermediates + two sets of outputs + staging
-    int cur = 0;
-    cudaEvent_t ev_copy = nullptr;
+    int cur = 0, copy_slot = 0;
     int64_t records_seen = 0;
 
     ~dyn_bam_dev() {
@@ -298,12 +301,12 @@ struct dyn_bam_dev {
         cv.notify_all();
         if (reader.joinable()) reader.join();
         if (buf) {
-            cudaDeviceSynchronize();      // nothing may still read the buffers when the next reader takes them
+            cudaDeviceSynchronize();      // nothing may still read (or fill) the buffers when the next reader takes them
+            for (Staged &st : buf->staged) st.dev_slot = -1;
             std::lock_guard<std::recursive_mutex> l(ctx->mu);
             if (!ctx->ingest_cache) { ctx->ingest_cache = buf; ctx->ingest_cache_free = free_ingest_buffers; }
             else delete buf;
         }
-        if (ev_copy) cudaEventDestroy(ev_copy);
         if (fd >= 0) close(fd);
     }
 };
@@ -434,12 +437,26 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
     if (ctx->ingest_cache) { d->buf = static_cast<IngestBuffers *>(ctx->ingest_cache); ctx->ingest_cache = nullptr; }
     else d->buf = new IngestBuffers();
     if (!d->buf->h_small) DYN_CUDA(cudaHostAlloc((void **)&d->buf->h_small, 256, cudaHostAllocDefault));
-    DYN_CUDA(cudaEventCreateWithFlags(&d->ev_copy, cudaEventDisableTiming));
+    for (cudaEvent_t &e : d->buf->ev_copy) if (!e) DYN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if ((rc = d->buf->d_small.ensure(256))) return rc;
     for (Staged &s : d->buf->staged) d->free_list.push_back(&s);
     dyn_bam_dev *dp = d.release();
     dp->reader = std::thread(read_ahead, dp);
     *out = dp;
+    return DYN_OK;
+}
+
+// Starts the host -> device copy of a staged run of blocks on the context's copy stream (device buffer pair `slot`).
+static int issue_copy(dyn_bam_dev *d, Staged *s, int slot) {
+    IngestBuffers &B = *d->buf;
+    int rc;
+    if ((rc = B.d_comp[slot].ensure(s->len + 16))) return rc;
+    if ((rc = B.d_blocks[slot].ensure(sizeof(BlockDesc) * s->blocks.size()))) return rc;
+    cudaStream_t cs = d->ctx->copy_stream[0];
+    DYN_CUDA(cudaMemcpyAsync(B.d_comp[slot].p, s->bytes, s->len, cudaMemcpyHostToDevice, cs));
+    DYN_CUDA(cudaMemcpyAsync(B.d_blocks[slot].p, s->blocks.data(), sizeof(BlockDesc) * s->blocks.size(), cudaMemcpyHostToDevice, cs));
+    DYN_CUDA(cudaEventRecord(B.ev_copy[slot], cs));
+    s->dev_slot = slot;
     return DYN_OK;
 }
 
@@ -467,29 +484,44 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     }
     struct Release {        // the staging buffer goes back to the reader when this call is done with it
         dyn_bam_dev *d; Staged *s;
-        ~Release() { std::lock_guard<std::mutex> l(d->mu); d->free_list.push_back(s); d->cv.notify_all(); }
+        ~Release() { std::lock_guard<std::mutex> l(d->mu); s->dev_slot = -1; d->free_list.push_back(s); d->cv.notify_all(); }
     } release{d, s};
     const int nb = (int)s->blocks.size();
     auto t_staged = now();
     int rc;
-    if ((rc = B.d_comp.ensure(s->len + 16))) return rc;
-    if ((rc = B.d_blocks.ensure(sizeof(BlockDesc) * (size_t)nb))) return rc;
+    if (s->dev_slot < 0) {      // not copied ahead (first chunk, or the reader was not ahead of us)
+        if ((rc = issue_copy(d, s, d->copy_slot))) return rc;
+        d->copy_slot ^= 1;
+    }
+    const int slot = s->dev_slot;
     if ((rc = B.d_inflated.ensure(s->inflated + 16))) return rc;
     if ((rc = B.d_nrec.ensure(4 * (size_t)(nb + 1)))) return rc;
     if ((rc = B.d_recbase.ensure(4 * (size_t)(nb + 1)))) return rc;
     uint32_t *d_small = B.d_small.as<uint32_t>();      // [0] inflate work counter, [1] status, [2..3] scan totals
     DYN_CUDA(cudaMemsetAsync(d_small, 0, 64, stream));
-    DYN_CUDA(cudaMemcpyAsync(B.d_comp.p, s->bytes, s->len, cudaMemcpyHostToDevice, stream));
-    DYN_CUDA(cudaMemcpyAsync(B.d_blocks.p, s->blocks.data(), sizeof(BlockDesc) * (size_t)nb, cudaMemcpyHostToDevice, stream));
+    DYN_CUDA(cudaStreamWaitEvent(stream, B.ev_copy[slot], 0));
     // ---- k1: inflate, one warp per block
     {
         const int ctas = std::min((nb + kInfWarps - 1) / kInfWarps, d->ctx->sm_count * 8);
-        inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(B.d_comp.as<uint8_t>(), B.d_inflated.as<uint8_t>(), B.d_blocks.as<BlockDesc>(), nb,
+        inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(B.d_comp[slot].as<uint8_t>(), B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb,
                                                             d_small, d_small + 1);
         DYN_CUDA(cudaGetLastError());
     }
+    {
+        // the next run of blocks, if the reader has it already, crosses PCIe while this one is inflated (the other buffer
+        // pair is free: its chunk was inflated before the previous call returned)
+        Staged *ahead = nullptr;
+        {
+            std::lock_guard<std::mutex> l(d->mu);
+            if (!d->ready.empty() && d->ready.front()->dev_slot < 0) ahead = d->ready.front();
+        }
+        if (ahead) {
+            if ((rc = issue_copy(d, ahead, d->copy_slot))) return rc;
+            d->copy_slot ^= 1;
+        }
+    }
     // ---- k2: records per block, their prefix sum, the total
-    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks.as<BlockDesc>(), nb, s->first_skip,
+    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb, s->first_skip,
                                                        B.d_nrec.as<uint32_t>(), nullptr, nullptr, d_small + 1);
     DYN_CUDA(cudaGetLastError());
     DYN_CUDA(cudaMemsetAsync(B.d_nrec.as<uint32_t>() + nb, 0, 4, stream));
@@ -525,7 +557,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     if ((rc = B.d_parsed.ensure(sizeof(bamrec::Parsed) * (size_t)n_rec))) return rc;
     if ((rc = B.d_scan_in.ensure(8 * (size_t)(n_rec + 1)))) return rc;
     if ((rc = B.d_scan.ensure(8 * (size_t)(n_rec + 1)))) return rc;
-    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks.as<BlockDesc>(), nb, s->first_skip,
+    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb, s->first_skip,
                                                        nullptr, B.d_recbase.as<uint32_t>(), B.d_recat.as<uint32_t>(), d_small + 1);
     DYN_CUDA(cudaGetLastError());
     parse_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_recat.as<uint32_t>(), n_rec, d->tags,

@@ -550,7 +550,7 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
 # --------------------------------------------------------------------------------------------------
 def tally_bam(ctx: Context, path: str, gene_ids, barcode_tag: Optional[str] = 'CB', umi_tag: Optional[str] = 'UB',
               gene_tag: str = 'GX', require_gene: bool = True, quality: int = 27, nasc: bool = False, part: int = 0,
-              n_parts: int = 1, chunk_bytes: int = 256 << 20, ingest: str = 'device', n_threads: int = 8, snps=None,
+              n_parts: int = 1, chunk_bytes: int = 0, ingest: str = 'device', n_threads: int = 8, snps=None,
               stats: Optional[dict] = None):
     """Streams block range `part` of `n_parts` of a coordinate-sorted BAM through the tally: every chunk of the reader
     (bamio.DeviceBamStream: inflate + pack on the GPU; bamio.BamStream: on the host cores, then cudaMemcpyAsync from
