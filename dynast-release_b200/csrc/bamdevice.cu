@@ -22,6 +22,7 @@
 // records straddling blocks) are reported with DYN_ERR_FORMAT; callers fall back to dyn_bam_stream_*.
 #include <cub/cub.cuh>
 #include <fcntl.h>
+#include <zlib.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -47,9 +48,9 @@ struct BlockDesc { uint32_t in_off, in_len, out_off, out_len; };
 
 __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *in, uint8_t *out, const BlockDesc *blocks, int n_blocks,
                                                                 unsigned int *next_block, uint32_t *status) {
-    __shared__ inflate::Tables tables[kInfWarps];
+    __shared__ dinflate::Tables tables[kInfWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    inflate::Tables &t = tables[wid];
+    dinflate::Tables &t = tables[wid];
     for (;;) {
         int b = 0;
         if (lane == 0) b = (int)atomicAdd(next_block, 1u);
@@ -57,15 +58,15 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *
         if (b >= n_blocks) return;
         const BlockDesc bd = blocks[b];
         uint8_t *dst = out + bd.out_off;
-        inflate::State s;
-        inflate::state_init(s, in + bd.in_off, bd.in_len, bd.out_len);
+        dinflate::State s;
+        dinflate::state_init(s, in + bd.in_off, bd.in_len, bd.out_len);
         if (bd.out_len == 0) s.phase = 3;
         for (;;) {
             int n = 0;
             uint32_t bytes = 0;
             if (lane == 0) {
-                if (s.err == inflate::OK && s.phase == 0) inflate::begin_block(s, t);
-                if (s.err == inflate::OK && s.phase == 1) n = inflate::decode_batch(s, t, &bytes);
+                if (s.err == dinflate::OK && s.phase == 0) dinflate::begin_block(s, t);
+                if (s.err == dinflate::OK && s.phase == 1) n = dinflate::decode_batch(s, t, &bytes);
             }
             __syncwarp();
             n = __shfl_sync(0xffffffffu, n, 0);
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *
                     }
                 }
             }
-            if (phase == 2 && err == inflate::OK) {
+            if (phase == 2 && err == dinflate::OK) {
                 // stored block: a plain copy by the warp
                 const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)s.br.p, 0);
                 const uint32_t len = __shfl_sync(0xffffffffu, s.stored_left, 0);
@@ -126,11 +127,11 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *
             }
             if (lane == 0) s.out_pos += bytes;
             const int phase2 = __shfl_sync(0xffffffffu, s.phase, 0);
-            if (err != inflate::OK || phase2 == 3) break;
+            if (err != dinflate::OK || phase2 == 3) break;
         }
         if (lane == 0) {
             uint32_t st = (uint32_t)s.err;
-            if (st == 0 && s.out_pos != bd.out_len) st = inflate::ERR_OUTPUT;
+            if (st == 0 && s.out_pos != bd.out_len) st = dinflate::ERR_OUTPUT;
             if (st) atomicOr(status, 1u << st);
         }
         __syncwarp();
@@ -274,9 +275,9 @@ struct dyn_bam_dev {
     std::vector<char> ref_names;
     std::vector<uint32_t> ref_name_off{0};
     std::vector<int32_t> ref_len;
-    struct FileBlock { size_t start, in_off, in_len, out_len; };
-    std::vector<FileBlock> blocks;         // this part's blocks
-    size_t next_block = 0;
+    size_t pos = 0, end = 0;               // this part: the BGZF blocks that start in [pos, end) of the file
+    bool first_chunk = true;
+    double ratio = 0.5;                    // compressed / inflated bytes seen so far (sizes the next read)
     uint32_t first_skip = 0;
     // gene table
     DevBuf gene_hash, gene_of_hash;
@@ -323,6 +324,21 @@ bool pread_all(int fd, uint8_t *dst, size_t len, size_t off) {
     return true;
 }
 
+// BGZF block header at p?  *blen = its length in the file
+inline bool bgzf_header(const uint8_t *p, size_t avail, size_t *blen) {
+    if (avail < 18 || p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return false;
+    const uint32_t xlen = bamrec::ld16(p + 10);
+    if (avail < 12 + (size_t)xlen) return false;
+    for (size_t x = 12; x + 4 <= 12 + (size_t)xlen;) {
+        const uint32_t slen = bamrec::ld16(p + x + 2);
+        if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2) { *blen = (size_t)bamrec::ld16(p + x + 4) + 1; return *blen >= 12 + (size_t)xlen + 8; }
+        x += 4 + slen;
+    }
+    return false;
+}
+
+// The reader thread: reads the next slab of the file straight into page-locked staging memory and lists the BGZF
+// blocks it holds by hopping over their BSIZE fields there -- the file is never scanned up front.
 void read_ahead(dyn_bam_dev *d) {
     for (;;) {
         Staged *s = nullptr;
@@ -330,19 +346,15 @@ void read_ahead(dyn_bam_dev *d) {
             std::unique_lock<std::mutex> l(d->mu);
             d->cv.wait(l, [&] { return d->stop || !d->free_list.empty(); });
             if (d->stop) return;
-            if (d->next_block >= d->blocks.size()) { d->finished = true; d->cv.notify_all(); return; }
+            if (d->pos >= d->end) { d->finished = true; d->cv.notify_all(); return; }
             s = d->free_list.front();
             d->free_list.pop_front();
         }
-        size_t b1 = d->next_block, acc = 0;
-        while (b1 < d->blocks.size() && (b1 == d->next_block || acc + d->blocks[b1].out_len <= d->chunk_bytes)) acc += d->blocks[b1++].out_len;
-        const size_t f0 = d->blocks[d->next_block].start;
-        const size_t f1 = b1 < d->blocks.size() ? d->blocks[b1].start : d->blocks[b1 - 1].in_off + d->blocks[b1 - 1].in_len + 8;
-        s->len = f1 - f0;
+        const size_t want = std::min(d->file_len - d->pos, (size_t)((double)d->chunk_bytes * d->ratio * 1.05) + (1u << 20));
         bool ok = true;
-        if (s->cap < s->len) {
+        if (s->cap < want) {
             if (s->bytes) cudaFreeHost(s->bytes);
-            s->cap = s->len + s->len / 4 + (1 << 20);
+            s->cap = want + want / 4 + (1 << 20);
             if (cudaHostAlloc((void **)&s->bytes, s->cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); s->bytes = nullptr; s->cap = 0; ok = false; }
         }
         if (ok) {
@@ -352,35 +364,97 @@ void read_ahead(dyn_bam_dev *d) {
             std::vector<char> good(nt, 1);
             for (int t = 0; t < nt; ++t)
                 th.emplace_back([&, t] {
-                    const size_t a = s->len * t / nt, b = s->len * (t + 1) / nt;
-                    good[t] = pread_all(d->fd, s->bytes + a, b - a, f0 + a) ? 1 : 0;
+                    const size_t a = want * t / nt, b = want * (t + 1) / nt;
+                    good[t] = pread_all(d->fd, s->bytes + a, b - a, d->pos + a) ? 1 : 0;
                 });
             for (auto &t : th) t.join();
             for (char g : good) ok &= g != 0;
         }
         s->blocks.clear();
         s->inflated = 0;
-        for (size_t b = d->next_block; b < b1; ++b) {
-            const dyn_bam_dev::FileBlock &fb = d->blocks[b];
-            s->blocks.push_back(BlockDesc{(uint32_t)(fb.in_off - f0), (uint32_t)fb.in_len, (uint32_t)s->inflated, (uint32_t)fb.out_len});
-            s->inflated += fb.out_len;
+        size_t q = 0;
+        bool corrupt = false;
+        while (ok && d->pos + q < d->end) {
+            size_t blen = 0;
+            if (want - q < 18) break;
+            if (!bgzf_header(s->bytes + q, want - q, &blen)) { corrupt = true; break; }
+            if (q + blen > want) break;                                  // the block continues behind this slab
+            const uint32_t xlen = bamrec::ld16(s->bytes + q + 10);
+            const uint32_t isize = bamrec::ld32(s->bytes + q + blen - 4);
+            if (!s->blocks.empty() && s->inflated + isize > d->chunk_bytes) break;
+            s->blocks.push_back(BlockDesc{(uint32_t)(q + 12 + xlen), (uint32_t)(blen - 12 - xlen - 8), (uint32_t)s->inflated, isize});
+            s->inflated += isize;
+            q += blen;
         }
-        s->first_skip = d->next_block == 0 ? d->first_skip : 0;
-        d->next_block = b1;
-        s->last = b1 >= d->blocks.size();
+        if (ok && !corrupt && s->blocks.empty()) corrupt = true;        // not even one whole block in a slab of > 1 MiB
+        s->len = q;
+        if (s->inflated) d->ratio = std::max(0.05, std::min(1.2, (double)q / (double)s->inflated));
+        s->first_skip = d->first_chunk ? d->first_skip : 0;
+        d->first_chunk = false;
+        d->pos += q;
+        s->last = d->pos >= d->end;
         std::lock_guard<std::mutex> l(d->mu);
-        if (!ok) { d->err = DYN_ERR_IO; d->err_msg = "dyn_bam_dev: reading the BAM failed"; d->finished = true; d->cv.notify_all(); return; }
+        if (!ok || corrupt) {
+            d->err = corrupt ? DYN_ERR_FORMAT : DYN_ERR_IO;
+            d->err_msg = corrupt ? "dyn_bam_dev: corrupt BGZF block" : "dyn_bam_dev: reading the BAM failed";
+            d->finished = true; d->cv.notify_all();
+            return;
+        }
         d->ready.push_back(s);
         d->cv.notify_all();
     }
 }
 
+// Inflates BGZF blocks on the host from file offset `at` on until `need` inflated bytes are there (header parsing,
+// record-boundary guess at a part's start).  *next = file offset behind the last block taken; lens = their inflated sizes.
+bool host_inflate_from(dyn_bam_dev *d, size_t at, size_t need, std::vector<uint8_t> &out, std::vector<size_t> *lens, size_t *next) {
+    std::vector<uint8_t> raw;
+    while (out.size() < need && at < d->file_len) {
+        uint8_t head[32];
+        const size_t hn = std::min<size_t>(32, d->file_len - at);
+        if (!pread_all(d->fd, head, hn, at)) return false;
+        size_t blen = 0;
+        if (!bgzf_header(head, hn, &blen) || at + blen > d->file_len) return false;
+        raw.resize(blen);
+        if (!pread_all(d->fd, raw.data(), blen, at)) return false;
+        const uint32_t xlen = bamrec::ld16(raw.data() + 10), isize = bamrec::ld32(raw.data() + blen - 4);
+        const size_t o = out.size();
+        out.resize(o + isize);
+        if (isize) {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) return false;
+            zs.next_in = raw.data() + 12 + xlen; zs.avail_in = (uInt)(blen - 12 - xlen - 8);
+            zs.next_out = out.data() + o; zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END) return false;
+        }
+        if (lens) lens->push_back(isize);
+        at += blen;
+    }
+    if (next) *next = at;
+    return true;
+}
+
+// First BGZF block that starts at or after file offset `from` (magic bytes, confirmed by the headers of the blocks behind it)
+size_t find_block_start(dyn_bam_dev *d, size_t from) {
+    if (from >= d->file_len) return d->file_len;
+    const size_t n = std::min<size_t>(d->file_len - from, 4u << 16);
+    std::vector<uint8_t> w(n);
+    if (!pread_all(d->fd, w.data(), n, from)) return d->file_len;
+    for (size_t o = 0; o + 18 <= n; ++o) {
+        size_t q = o, hops = 0, blen = 0;
+        while (q + 18 <= n && bgzf_header(w.data() + q, n - q, &blen)) { q += blen; ++hops; if (hops >= 3) break; }
+        if (hops >= 3 || (hops >= 1 && from + q == d->file_len)) return from + o;
+    }
+    return d->file_len;
+}
+
 }  // namespace
 
-// helpers of bamstream.cpp (block table, header, part boundaries) reused through the stream object
-extern "C" int dyn_bam_stream_layout(const char *path, int part, int n_parts, int64_t *n_blocks, const uint64_t **starts,
-                                     const uint64_t **in_offs, const uint64_t **in_lens, const uint64_t **out_lens, uint32_t *first_skip,
-                                     dyn_bam_stream_t **holder);
+// bamstream.cpp: the record-boundary guesser at a part's start
+size_t dyn_bam_guess_offset(const uint8_t *data, size_t n, size_t len0, int32_t n_ref, bool at_eof);
 
 extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_stream_opts_t *o, dyn_bam_dev_t **out) {
     DYN_ARG(ctx != nullptr && path && o && out, "null argument");
@@ -394,25 +468,102 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
     d->lean = o->lean != 0;
     d->tags.lean = d->lean;
     if (o->chunk_bytes > 0) d->chunk_bytes = (size_t)o->chunk_bytes;
-    // ---- file layout through the host stream reader's code (block table, header, part boundary guesser)
-    int64_t nb = 0;
-    const uint64_t *starts, *in_offs, *in_lens, *out_lens;
-    dyn_bam_stream_t *holder = nullptr;
-    int rc = dyn_bam_stream_layout(path, o->part, o->n_parts, &nb, &starts, &in_offs, &in_lens, &out_lens, &d->first_skip, &holder);
-    if (rc) return rc;
-    for (int64_t i = 0; i < nb; ++i) d->blocks.push_back({(size_t)starts[i], (size_t)in_offs[i], (size_t)in_lens[i], (size_t)out_lens[i]});
+    d->fd = open(path, O_RDONLY);
+    if (d->fd < 0) { dyn_set_error("dyn_bam_dev_open: cannot open %s", path); return DYN_ERR_IO; }
     {
-        int64_t n = 0;
-        const char *t = static_cast<const char *>(dyn_bam_stream_field(holder, 10, &n));
-        d->header_text.assign(t ? t : "", (size_t)n);
-        const char *names = static_cast<const char *>(dyn_bam_stream_field(holder, 28, &n));
-        d->ref_names.assign(names, names + n);
-        const uint32_t *offs = static_cast<const uint32_t *>(dyn_bam_stream_field(holder, 29, &n));
-        d->ref_name_off.assign(offs, offs + n / 4);
-        const int32_t *lens = static_cast<const int32_t *>(dyn_bam_stream_field(holder, 9, &n));
-        d->ref_len.assign(lens, lens + n / 4);
+        struct stat sb;
+        if (fstat(d->fd, &sb) != 0) { dyn_set_error("dyn_bam_dev_open: cannot stat %s", path); return DYN_ERR_IO; }
+        d->file_len = (size_t)sb.st_size;
     }
-    dyn_bam_stream_close(holder);
+    // ---- header (inflated on the host: a few blocks), then this part's byte range of the file
+    size_t c0 = 0;            // file offset of the block in which the first alignment record starts
+    uint32_t skip0 = 0;       // ... and that record's offset inside it
+    {
+        std::vector<uint8_t> h;
+        std::vector<size_t> lens;
+        std::vector<size_t> starts;
+        size_t at = 0;
+        auto need = [&](size_t nbytes) -> bool {
+            while (h.size() < nbytes && at < d->file_len) {
+                starts.push_back(at);
+                std::vector<size_t> one;
+                size_t nx = at;
+                if (!host_inflate_from(d.get(), at, h.size() + 1, h, &one, &nx) || nx == at) return false;
+                // host_inflate_from may take several blocks when some are empty: record each of them
+                size_t o = starts.back();
+                starts.pop_back();
+                for (size_t k = 0; k < one.size(); ++k) { starts.push_back(o); lens.push_back(one[k]); o = 0; }
+                // only the first start is exact; empty blocks in a header are not expected -- recompute starts below
+                at = nx;
+            }
+            return h.size() >= nbytes;
+        };
+        if (!need(12) || memcmp(h.data(), "BAM\1", 4) != 0) { dyn_set_error("dyn_bam_dev_open: %s is not a BAM file", path); return DYN_ERR_FORMAT; }
+        size_t p = 4;
+        const uint32_t l_text = bamrec::ld32(h.data() + p); p += 4;
+        if (!need(p + l_text + 4)) { dyn_set_error("dyn_bam_dev_open: truncated header"); return DYN_ERR_FORMAT; }
+        d->header_text.assign((const char *)h.data() + p, l_text); p += l_text;
+        const uint32_t n_ref = bamrec::ld32(h.data() + p); p += 4;
+        for (uint32_t r = 0; r < n_ref; ++r) {
+            if (!need(p + 4)) { dyn_set_error("dyn_bam_dev_open: truncated reference list"); return DYN_ERR_FORMAT; }
+            const uint32_t l_name = bamrec::ld32(h.data() + p); p += 4;
+            if (!need(p + l_name + 4)) { dyn_set_error("dyn_bam_dev_open: truncated reference list"); return DYN_ERR_FORMAT; }
+            d->ref_names.insert(d->ref_names.end(), (const char *)h.data() + p, (const char *)h.data() + p + (l_name ? l_name - 1 : 0));
+            d->ref_name_off.push_back((uint32_t)d->ref_names.size());
+            p += l_name;
+            d->ref_len.push_back((int32_t)bamrec::ld32(h.data() + p)); p += 4;
+        }
+        // walk the blocks again to find the one that holds inflated offset p
+        size_t fo = 0, io = 0;
+        for (;;) {
+            if (fo >= d->file_len) { c0 = d->file_len; skip0 = 0; break; }
+            uint8_t head[32];
+            const size_t hn = std::min<size_t>(32, d->file_len - fo);
+            size_t blen = 0;
+            if (!pread_all(d->fd, head, hn, fo) || !bgzf_header(head, hn, &blen)) { dyn_set_error("dyn_bam_dev_open: corrupt BGZF block in %s", path); return DYN_ERR_FORMAT; }
+            uint8_t tail[4];
+            if (!pread_all(d->fd, tail, 4, fo + blen - 4)) { dyn_set_error("dyn_bam_dev_open: truncated file"); return DYN_ERR_FORMAT; }
+            const size_t isize = bamrec::ld32(tail);
+            if (p < io + isize) { c0 = fo; skip0 = (uint32_t)(p - io); break; }
+            io += isize; fo += blen;
+            if (p == io) { c0 = fo; skip0 = 0; break; }
+        }
+    }
+    DYN_ARG(o->n_parts >= 1 && o->part >= 0 && o->part < o->n_parts, "part out of range");
+    const size_t span = d->file_len - c0;
+    auto bound = [&](int part) -> size_t {
+        if (part <= 0) return c0;
+        if (part >= o->n_parts) return d->file_len;
+        return find_block_start(d.get(), c0 + (size_t)((double)span * part / o->n_parts));
+    };
+    d->pos = bound(o->part);
+    d->end = bound(o->part + 1);
+    d->first_skip = o->part == 0 ? skip0 : 0;
+    if (o->part > 0) {
+        // the first record that STARTS in this part (blocks in which none starts belong to the previous part's last record)
+        while (d->pos < d->end) {
+            std::vector<uint8_t> buf;
+            std::vector<size_t> lens;
+            size_t nx = d->pos;
+            if (!host_inflate_from(d.get(), d->pos, 1, buf, &lens, &nx)) { dyn_set_error("dyn_bam_dev_open: inflate failed in %s", path); return DYN_ERR_FORMAT; }
+            const size_t len0 = lens.empty() ? 0 : lens[0];
+            size_t first_next = d->pos;
+            {   // file offset behind the first block
+                uint8_t head[32];
+                const size_t hn = std::min<size_t>(32, d->file_len - d->pos);
+                size_t blen = 0;
+                if (!pread_all(d->fd, head, hn, d->pos) || !bgzf_header(head, hn, &blen)) { dyn_set_error("dyn_bam_dev_open: corrupt BGZF block in %s", path); return DYN_ERR_FORMAT; }
+                first_next = d->pos + blen;
+            }
+            buf.resize(len0);
+            size_t nx2 = first_next;
+            if (!host_inflate_from(d.get(), first_next, len0 + (2u << 16), buf, nullptr, &nx2)) { dyn_set_error("dyn_bam_dev_open: inflate failed in %s", path); return DYN_ERR_FORMAT; }
+            const size_t off = dyn_bam_guess_offset(buf.data(), buf.size(), len0, (int32_t)d->ref_len.size(), nx2 >= d->file_len);
+            if (off < len0) { d->first_skip = (uint32_t)off; break; }
+            d->pos = first_next;
+        }
+    }
+    int rc = DYN_OK;
     // ---- gene table: FNV hashes of the ids, sorted; two ids with one hash cannot be told apart on the device
     {
         std::vector<std::pair<uint64_t, int32_t>> hs;
@@ -432,8 +583,6 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
             DYN_CUDA(cudaMemcpy(d->gene_of_hash.p, g.data(), 4 * g.size(), cudaMemcpyHostToDevice));
         }
     }
-    d->fd = open(path, O_RDONLY);
-    if (d->fd < 0) { dyn_set_error("dyn_bam_dev_open: cannot open %s", path); return DYN_ERR_IO; }
     if (ctx->ingest_cache) { d->buf = static_cast<IngestBuffers *>(ctx->ingest_cache); ctx->ingest_cache = nullptr; }
     else d->buf = new IngestBuffers();
     if (!d->buf->h_small) DYN_CUDA(cudaHostAlloc((void **)&d->buf->h_small, 256, cudaHostAllocDefault));

@@ -276,6 +276,30 @@ int read_header(dyn_bam_stream *s, size_t *first_block, size_t *first_off) {
     return DYN_OK;
 }
 
+}  // namespace
+
+// Offset, inside the first len0 bytes of an inflated buffer, of the first alignment record that starts there: the chain of
+// plausible records from it must run to the end of the buffer (len0 when none does).  Shared with bamdevice.cu.
+size_t dyn_bam_guess_offset(const uint8_t *data, size_t n, size_t len0, int32_t n_ref, bool at_eof) {
+    struct View { const uint8_t *p; size_t n; size_t size() const { return n; } const uint8_t *data() const { return p; } } buf{data, n};
+    for (size_t o = 0; o < len0; ++o) {
+        size_t q = o, n_ok = 0;
+        bool good = true;
+        while (q < buf.size()) {
+            size_t sz = 0;
+            if (buf.size() - q < 36) { good = at_eof ? false : true; break; }
+            if (!sane_record(buf.data() + q, buf.size() - q, n_ref, &sz)) { good = false; break; }
+            if (q + sz > buf.size()) { good = !at_eof; break; }
+            q += sz; ++n_ok;
+        }
+        if (q == buf.size()) good = true;
+        if (good && (n_ok >= 4 || (at_eof && q == buf.size() && n_ok >= 1))) return o;
+    }
+    return len0;
+}
+
+namespace {
+
 // Offset inside block `b` of the first record that starts there (a chain of plausible records must reach block b + 2).
 bool guess_record_start(dyn_bam_stream *s, size_t b, size_t *off) {
     std::vector<uint8_t> buf;
@@ -286,20 +310,7 @@ bool guess_record_start(dyn_bam_stream *s, size_t b, size_t *off) {
     if (!inflate_until(s, bb, buf, want)) return false;           // + the next ones
     const bool at_eof = bb >= s->blocks.size();
     const int32_t n_ref = (int32_t)s->ref_len.size();
-    for (size_t o = 0; o < len0; ++o) {
-        size_t q = o, n_ok = 0;
-        bool good = true;
-        while (q < buf.size()) {
-            size_t sz = 0;
-            if (buf.size() - q < 36) { good = at_eof ? false : true; break; }
-            if (!sane_record(buf.data() + q, buf.size() - q, n_ref, &sz)) { good = false; break; }
-            if (q + sz > buf.size()) { good = !at_eof; break; }   // runs past what was inflated: plausible unless the file ends
-            q += sz; ++n_ok;
-        }
-        if (q == buf.size()) good = true;
-        if (good && (n_ok >= 4 || (at_eof && q == buf.size() && n_ok >= 1))) { *off = o; return true; }
-    }
-    *off = len0;       // no record starts in this block (one huge record spans it)
+    *off = dyn_bam_guess_offset(buf.data(), buf.size(), len0, n_ref, at_eof);
     return true;
 }
 

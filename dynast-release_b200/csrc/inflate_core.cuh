@@ -17,7 +17,7 @@
 #define INF_HD inline
 #endif
 
-namespace inflate {
+namespace dinflate {
 
 constexpr int kLitBits = 10, kDistBits = 8, kBatch = 32;
 
@@ -254,4 +254,4 @@ INF_HD int decode_batch(State &s, Tables &t, uint32_t *bytes) {
     return n;
 }
 
-}  // namespace inflate
+}  // namespace dinflate

@@ -9,15 +9,15 @@
 #include "../../dynast-release_b200/csrc/inflate_core.cuh"
 
 extern "C" int host_inflate(const uint8_t *in, uint32_t in_len, uint8_t *dst, uint32_t out_len) {
-    static inflate::Tables t;
-    inflate::State s;
-    inflate::state_init(s, in, in_len, out_len);
+    static dinflate::Tables t;
+    dinflate::State s;
+    dinflate::state_init(s, in, in_len, out_len);
     if (out_len == 0) s.phase = 3;
     for (;;) {
         int n = 0;
         uint32_t bytes = 0;
-        if (s.err == inflate::OK && s.phase == 0) inflate::begin_block(s, t);
-        if (s.err == inflate::OK && s.phase == 1) n = inflate::decode_batch(s, t, &bytes);
+        if (s.err == dinflate::OK && s.phase == 0) dinflate::begin_block(s, t);
+        if (s.err == dinflate::OK && s.phase == 1) n = dinflate::decode_batch(s, t, &bytes);
         const int err = s.err, phase = s.phase;
         const uint32_t out_pos = s.out_pos;
         if (n > 0) {
@@ -56,15 +56,15 @@ extern "C" int host_inflate(const uint8_t *in, uint32_t in_len, uint8_t *dst, ui
                 }
             }
         }
-        if (phase == 2 && err == inflate::OK) {
+        if (phase == 2 && err == dinflate::OK) {
             memcpy(dst + out_pos, s.br.p, s.stored_left);
             s.br.p += s.stored_left; s.out_pos += s.stored_left; s.stored_left = 0; s.phase = s.last ? 3 : 0;
         }
         s.out_pos += bytes;
-        if (err != inflate::OK || s.phase == 3) break;
+        if (err != dinflate::OK || s.phase == 3) break;
     }
     if (s.err) return s.err;
-    return s.out_pos == out_len ? 0 : inflate::ERR_OUTPUT;
+    return s.out_pos == out_len ? 0 : dinflate::ERR_OUTPUT;
 }
 
 // Records of one inflated chunk (record chain walked here), parsed and packed by the device cores.
