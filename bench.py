@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument('--skip-consensus', action='store_true')
     ap.add_argument('--consensus-reads', type=int, default=20_000_000, help='C3-like reads per GPU for the consensus stage')
     ap.add_argument('--no-emit', action='store_true', help='diagnostic: counters only, no mismatch records')
+    ap.add_argument('--c5', action='store_true', help='also run config C5 per GPU: 62.5 M reads, 125 k barcodes, TC + AG labelling groups')
     ap.add_argument('--skip-bam', action='store_true')
     ap.add_argument('--bam-reads', type=int, default=16_000_000, help='records per GPU of the synthetic BAM of the from-file leg')
     ap.add_argument('--bam-level', type=int, default=1, help='zlib level of that BAM (STAR writes level 1, samtools sort level 6)')
@@ -493,6 +494,33 @@ def main():
                 'note': 'includes the host round trips of the dedup split plan and the EM / pi shape discovery'}
         del res
 
+    # ---------------------------------------------------------------- C5 (behind --c5): dual labelling, 1 M barcodes over 8 GPUs
+    c5 = None
+    if args.c5:
+        n5, b5 = 62_500_000, 125_000
+        g5 = pipeline.SynthBatch(n5, seed=2005 + rank, n_barcodes=b5, device=local_rank, lean=not args.full_records)
+        o5 = pipeline.TallyBuffers(n5, int(n5 * 1.5) + 1024, device=local_rank)
+
+        def run5(t=None):
+            return pipeline.count_to_estimate(ctx, g5.records, g5.rec_off, g5.barcode, g5.umi, g5.gene, g5.score, g5.strand, b5, g5.n_genes, o5,
+                                              conversions=('AG', 'TC'), conversion_groups=[('TC',), ('AG',)], cell_threshold=300, timings=t)
+
+        run5()
+        barrier()
+        ms5, t5 = [], []
+        for _ in range(3):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tt = {}
+            a0.record(stream); r5 = run5(tt); a1.record(stream)
+            barrier()
+            ms5.append(a0.elapsed_time(a1)); t5.append(tt)
+        mid = int(np.argsort(ms5)[1])
+        c5 = {'workload': 'C5 per GPU: 62.5 M reads, 125 k barcodes, --conversion TC --conversion AG (two aggregate / EM / pi passes)',
+              'value': world * n5 / (ms5[mid] * 1e-3), 'unit': UNIT, 'ms': ms5[mid], 'rep_ms': ms5, 'stage_ms': t5[mid],
+              'barcodes_with_p_c': {k_: int((v['em_status'] == 0).sum().item()) for k_, v in r5['groups'].items()}}
+        del g5, o5, r5
+        torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- from a BAM FILE: ingest -> tally -> dedup -> estimate
     e2e_bam = None
     if not args.skip_bam:
@@ -576,6 +604,7 @@ def main():
             keep = torch.repeat_interleave(multi, counts)
             goff = torch.zeros(int(multi.sum().item()) + 1, dtype=torch.int64, device=device)
             goff[1:] = torch.cumsum(counts[multi], 0)
+            group_items.keys = uk[multi]
             return (cb.rec_off[order[keep]]).contiguous(), goff
 
         items, goff = group_items()
@@ -589,10 +618,32 @@ def main():
         c2.record(stream)
         barrier()
         ok = bool((cres['status'] == 0).all().item())
+        # C3 continues with `dynast count` on the consensus reads (dedup mode `exon`, count.py:295-304): tally + UMI dedup
+        n_cons = int(goff.numel() - 1)
+        gk = group_items.keys
+        c_bc, c_umi, c_gene = (gk >> 39).to(torch.int32), (gk >> 15) & 0xffffff, (gk & 0x7fff).to(torch.int32)
+        c_out = pipeline.TallyBuffers(n_cons, 2 * n_cons + 1024, device=local_rank)
+        c_strand = cb.tables['gene_strand'][c_gene.long()]
+        c3, c4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c3.record(stream)
+        pipeline.tally_reads(ctx, cres['records'], cres['off'], c_out, quality=27)
+        ckey = torch.empty(n_cons, dtype=torch.int64, device=device)
+        pipeline.check(ctx.lib.dyn_group_key(ctx.handle, pipeline.ptr(c_bc), pipeline.ptr(c_umi.contiguous()), pipeline.ptr(c_gene), n_cons, 24, 15,
+                                             pipeline.ptr(ckey), pipeline._stream()))
+        c_sel = pipeline.dedup(ctx, ckey, c_out.counts, c_strand, torch.ones(n_cons, dtype=torch.uint8, device=device),
+                               torch.full((n_cons,), 91, dtype=torch.int16, device=device), c_out.conv_n, c_bc, 2 * args.barcodes,
+                               conversions=('TC',), use_conversions=False, key_lo_bits=15 + 24 + 15)
+        c4.record(stream)
+        barrier()
+        count_ms = c3.elapsed_time(c4)
         cons = {'metric': 'member reads/s, UMI consensus (per-group shared-memory accumulation, tuple sort for scattered groups, assemble)',
                 'value': world * int(items.numel()) / (c1.elapsed_time(c2) * 1e-3), 'unit': UNIT, 'ms_consensus': c1.elapsed_time(c2),
                 'ms_grouping': c0.elapsed_time(c1), 'reads': nc, 'member_reads': int(items.numel()), 'groups': int(goff.numel() - 1),
-                'all_status_ok': ok, 'workload': 'C3-like: 91-nt reads, 3.5 reads per (barcode, UMI, gene) group, starts within 300 nt'}
+                'all_status_ok': ok, 'workload': 'C3-like: 91-nt reads, 3.5 reads per (barcode, UMI, gene) group, starts within 300 nt',
+                'count_on_consensus_ms': count_ms, 'count_on_consensus_rows': int(c_sel.numel()),
+                'count_on_consensus_note': 'tally of the consensus records + UMI dedup in mode `exon` (the RN tag of a consensus BAM '
+                                           'selects it, count.py:295-304): the second half of config C3',
+                'c3_value': world * int(items.numel()) / ((c1.elapsed_time(c2) + c0.elapsed_time(c1) + count_ms) * 1e-3)}
         del cb, cres, items, goff, key
         torch.cuda.empty_cache()
 
@@ -688,7 +739,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': config, 'gpu_launches': 2 * args.steps,
-            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'e2e_bam': e2e_bam, 'em': em, 'pipeline': pipe, 'consensus': cons, 'clocks': clocks,
+            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'e2e_bam': e2e_bam, 'c5': c5, 'em': em, 'pipeline': pipe, 'consensus': cons, 'clocks': clocks,
             'conversions_per_read': n_conv / n_reads, 'multi_gpu_bit_equal': bit_equal,
         }
         print(json.dumps(line))

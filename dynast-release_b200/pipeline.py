@@ -441,7 +441,7 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
                       out: TallyBuffers, conversions=('TC',), quality: int = 27, umi_bits: int = 24,
                       cell_threshold: int = 1000, with_pi: bool = True, timings: Optional[dict] = None, group=None,
                       exchange: bool = False, tallied=None, transcriptome=None, method: str = 'alpha',
-                      cell_gene_threshold: int = 16):
+                      cell_gene_threshold: int = 16, conversion_groups=None):
     """Runs every stage of the path on device tensors (the packed records of one GPU's read range plus the
     interned barcode / umi / gene ids of its reads).  Mirrors count() then estimate(method='alpha') of the
     reference: count_conversions (count.py:306) -> estimate_p_e (estimate.py:197-234) -> aggregate_counts
@@ -453,6 +453,10 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
     method = 'pi_g' adds the per-(cell, gene) fit of estimate(method='pi_g') (estimate.py:282-327, pi.py:253-296): every
     (barcode, gene) pair with at least `cell_gene_threshold` reads gets its own (alpha, beta, pi) from the barcode's p_e /
     p_c -- result keys `pi_g` [P, 3], `pi_g_status`, `pi_g_pair` (barcode << gene_bits | gene), `pi_g_reads`.
+    conversion_groups (dual labelling, e.g. [('TC',), ('AG',)] for `--conversion TC --conversion AG`): `conversions` is then
+    the flattened set (dedup priority and the p_e columns use all of them, count.py:306, p_e.py:82-89) and histograms, EM,
+    pi and alpha run once per group on the reads WITHOUT any conversion of the other groups (estimate.py:248-255); the
+    per-group results sit in res['groups'][name] and the top-level keys hold the first group's.
     tallied = (counts [n, 16] uint8, conv_n [n] int16): the tally already ran (tally_bam streams it chunk by chunk while
     the BAM is being read) and records / rec_off / out are not used; transcriptome = the reads' gene-tag-present flag."""
     dev = barcode.device
@@ -497,10 +501,16 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
     pe_cols = [c for c in CONVERSION_COLUMNS if c[0] not in {x[0] for x in conversions}]
     if not pe_cols:      # the labelled conversions start with all four bases (p_e.py:84-91): every non-induced column
         pe_cols = [c for c in CONVERSION_COLUMNS if c not in set(conversions)]
-    sums, n_reads, n_with = group_sums(ctx, counts, strand, barcode, n_barcodes, sel=sel, conversions=conversions)
+    group_list = [tuple(g) for g in conversion_groups] if conversion_groups else [tuple(conversions)]
+    all_convs = tuple(conversions)
+    first = group_list[0]
+    # n_with (alpha's "new" reads, alpha.py:75) counts reads with a conversion of THIS group; the sums are all 16 columns
+    sums, n_reads, n_with = group_sums(ctx, counts, strand, barcode, n_barcodes, sel=sel, conversions=first)
     rates, p_e = rates_pe(ctx, sums, pe_conversions=pe_cols)
     mark('p_e')
-    rows = aggregate_kn(ctx, counts, strand, barcode, None, n_barcodes, 0, conversions, sel=sel, first_appearance=False)
+    others = tuple(c for c in all_convs if c not in first)
+    rows = aggregate_kn(ctx, counts, strand, barcode, None, n_barcodes, 0, first, sel=sel, first_appearance=False,
+                        exclude=others if conversion_groups else None)
     k, nn, c, off, total = kn_csr(ctx, rows['keys'], rows['count32'], rows['n_rows'], n_barcodes)
     mark('aggregate')
     # estimate_p_c skips barcodes below the read threshold (p_c.py:215-217): give them an empty histogram
@@ -525,6 +535,30 @@ def count_to_estimate(ctx: Context, records, rec_off, barcode, umi, gene, score,
         pi_c = torch.where(ok & (pi_status == 0), abp[:, 2], torch.full_like(p_c, float('nan')))
         res.update(pi=abp, pi_status=pi_status, alpha=alpha(ctx, n_reads, n_with, pi_c))
         mark('pi')
+    if conversion_groups:
+        name = lambda g: '_'.join(sorted(g))
+        res['groups'] = {name(first): {k_: res[k_] for k_ in ('p_c', 'em_status', 'hist', 'pi', 'pi_status', 'alpha') if k_ in res}}
+        for g in group_list[1:]:
+            og = tuple(c_ for c_ in all_convs if c_ not in g)
+            r2 = aggregate_kn(ctx, counts, strand, barcode, None, n_barcodes, 0, g, sel=sel, first_appearance=False, exclude=og)
+            k2, n2, c2, off2, total2 = kn_csr(ctx, r2['keys'], r2['count32'], r2['n_rows'], n_barcodes)
+            lens2 = off2[1:] - off2[:-1]
+            keep2 = total2 >= cell_threshold
+            offk = torch.zeros_like(off2)
+            offk[1:] = torch.cumsum(torch.where(keep2, lens2, torch.zeros_like(lens2)), 0)
+            rk = torch.repeat_interleave(keep2, lens2)
+            pc2, st2, _ = em_pc(ctx, k2[rk].contiguous(), n2[rk].contiguous(), c2[rk].contiguous(), offk, p_e)
+            st2 = torch.where(keep2, st2, torch.full_like(st2, -1))
+            entry = dict(p_c=pc2, em_status=st2, hist=(k2, n2, c2, off2))
+            if with_pi:
+                ok2 = st2 == 0
+                abp2, ps2 = pi_fit(ctx, k2, n2, c2, off2, torch.nan_to_num(p_e, nan=0.0), torch.where(ok2, pc2, torch.full_like(pc2, float('nan'))),
+                                   max_cells=int(lens2.max().item()) if lens2.numel() else 1)
+                _, _, nw2 = group_sums(ctx, counts, strand, barcode, n_barcodes, sel=sel, conversions=g)
+                pic2 = torch.where(ok2 & (ps2 == 0), abp2[:, 2], torch.full_like(pc2, float('nan')))
+                entry.update(pi=abp2, pi_status=ps2, alpha=alpha(ctx, n_reads, nw2, pic2))
+            res['groups'][name(g)] = entry
+        mark('other_groups')
     if method == 'pi_g':
         rows_g = aggregate_kn(ctx, counts, strand, barcode, gene, n_barcodes, n_genes, conversions, sel=sel, first_appearance=False)
         gk, gn, gc, goff, pair_key, pair_total = kn_csr_pairs(ctx, rows_g['keys'], rows_g['count32'], rows_g['n_rows'])

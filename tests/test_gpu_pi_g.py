@@ -76,3 +76,40 @@ def test_estimate_pi_g_on_fixture(gpu_ctx, tmp_path):
     assert len(m) == len(want) == len(got)                  # the same (cell, gene) groups
     assert np.abs(m['pi'] - m['pi_ref']).mean() < 0.03
     assert {'X_l_TC', 'X_n_TC'} <= set(res.layers) and any(k.endswith('_pi_g') or 'est' in k for k in res.layers)
+
+
+def test_device_path_dual_conversion_groups(gpu_ctx):
+    """`--conversion TC --conversion AG`: the histogram of each labelling group only holds reads WITHOUT a conversion of
+    the other group (estimate.py:248-255); dedup and p_e use the flattened set (count.py:306, p_e.py:82-89)."""
+    from dynast_b200 import pipeline
+    b = pipeline.SynthBatch(300_000, seed=23, n_barcodes=10, n_genes=30, device=0, reads_per_umi=1.2)
+    out = pipeline.TallyBuffers(b.n_reads, 3 * b.n_reads, device=0)
+    res = pipeline.count_to_estimate(gpu_ctx, b.records, b.rec_off, b.barcode, b.umi, b.gene, b.score, b.strand, 10, 30, out,
+                                     conversions=('AG', 'TC'), conversion_groups=[('TC',), ('AG',)], cell_threshold=500)
+    one = pipeline.count_to_estimate(gpu_ctx, b.records, b.rec_off, b.barcode, b.umi, b.gene, b.score, b.strand, 10, 30, out,
+                                     conversions=('AG', 'TC'), cell_threshold=500, with_pi=False)
+    torch.cuda.synchronize()
+    assert torch.equal(res['selected'], one['selected'])
+    np.testing.assert_array_equal(res['p_e'].cpu().numpy(), one['p_e'].cpu().numpy())
+    sel = res['selected'].long()
+    counts = out.counts[sel].cpu().numpy().astype(np.int64)
+    strand = b.strand[sel].cpu().numpy()
+    comp = counts.copy()
+    comp[strand != 0, :12] = counts[strand != 0, :12][:, ::-1]
+    comp[strand != 0, 12:] = counts[strand != 0, 12:][:, ::-1]
+    df = pd.DataFrame(comp, columns=pipeline.CONVERSION_COLUMNS + pipeline.BASE_COLUMNS)
+    df['barcode'] = b.barcode[sel].cpu().numpy()
+    assert set(res['groups']) == {'TC', 'AG'}
+    for conv, other, base in (('TC', 'AG', 'T'), ('AG', 'TC', 'A')):
+        g = res['groups'][conv]
+        k, n, c, off = (t.cpu().numpy() for t in g['hist'])
+        sub = df[df[other] == 0]
+        want = sub.groupby(['barcode', conv, base]).size()
+        got = {(bc, int(k[j]), int(n[j])): int(c[j]) for bc in range(10) for j in range(off[bc], off[bc + 1])}
+        assert got == {(int(bc), int(kk), int(nn)): int(v) for (bc, kk, nn), v in want.items()}
+        new = df[df[conv] > 0].groupby('barcode').size().reindex(range(10), fill_value=0).to_numpy()
+        total = df.groupby('barcode').size().reindex(range(10), fill_value=0).to_numpy()
+        ok = (g['em_status'].cpu().numpy() == 0) & (g['pi_status'].cpu().numpy() == 0)
+        assert ok.sum() >= 5
+        pi_c = g['pi'].cpu().numpy()[:, 2]
+        np.testing.assert_allclose(g['alpha'].cpu().numpy()[ok], (new / total / pi_c)[ok], rtol=1e-9)
