@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--no-emit', action='store_true', help='diagnostic: counters only, no mismatch records')
     ap.add_argument('--c5', action='store_true', help='also run config C5 per GPU: 62.5 M reads, 125 k barcodes, TC + AG labelling groups')
     ap.add_argument('--skip-bam', action='store_true')
+    ap.add_argument('--skip-other-layout', action='store_true')
     ap.add_argument('--bam-reads', type=int, default=16_000_000, help='records per GPU of the synthetic BAM of the from-file leg')
     ap.add_argument('--bam-level', type=int, default=1, help='zlib level of that BAM (STAR writes level 1, samtools sort level 6)')
     ap.add_argument('--full-records', action='store_true',
@@ -385,6 +386,31 @@ def main():
                 'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': alg_bytes, 'kernel': 'tally_kernel',
                 'peak_source': peak_src, 'algorithmic_bytes_per_read': alg_bytes / n_reads}
 
+    # the same kernel on the other record layout of the same reads (same seed): the lean layout halves the bytes a read needs,
+    # the kernel's time does not change (it is bound by instruction issue), so its HBM fraction halves
+    if not args.skip_other_layout:
+        other = pipeline.SynthBatch(n_reads, seed=2001 + rank, n_barcodes=args.barcodes, device=local_rank,
+                                    barcode_base=rank * args.barcodes, lean=bool(args.full_records))
+        for _ in range(3):
+            pipeline.tally_reads(ctx, other.records, other.rec_off, out, quality=27, emit_conv=not args.no_emit)
+        barrier()
+        oe = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        oe[0].record(stream)
+        for i in range(args.steps):
+            pipeline.tally_reads(ctx, other.records, other.rec_off, out, quality=27, emit_conv=not args.no_emit)
+            oe[i + 1].record(stream)
+        barrier()
+        o_ms = float(np.mean([oe[i].elapsed_time(oe[i + 1]) for i in range(args.steps)]))
+        o_bytes = other.algorithmic_input_bytes() + n_reads * (16 + 4 + 2) + int(out.scalars[0].item()) * 12
+        roofline['other_layout'] = {'record_layout': 'lean' if args.full_records else 'full (Phred stream kept)', 'ms_per_launch': o_ms,
+                                    'reads_per_s': n_reads / (o_ms * 1e-3), 'algorithmic_bytes_per_read': o_bytes / n_reads,
+                                    'achieved': o_bytes / (o_ms * 1e-3) / 1e9, 'frac': o_bytes / (o_ms * 1e-3) / 1e9 / peak}
+        del other
+        torch.cuda.empty_cache()
+        for _ in range(2):      # leave `out` holding the main batch's results for the legs below
+            step()
+        barrier()
+
     # ---------------------------------------------------------------- e2e through the host-buffer C-ABI
     e2e = None
     if not args.skip_e2e:
@@ -517,6 +543,7 @@ def main():
         mid = int(np.argsort(ms5)[1])
         c5 = {'workload': 'C5 per GPU: 62.5 M reads, 125 k barcodes, --conversion TC --conversion AG (two aggregate / EM / pi passes)',
               'value': world * n5 / (ms5[mid] * 1e-3), 'unit': UNIT, 'ms': ms5[mid], 'rep_ms': ms5, 'stage_ms': t5[mid],
+              'reads_after_dedup': int(r5['selected'].numel()),
               'barcodes_with_p_c': {k_: int((v['em_status'] == 0).sum().item()) for k_, v in r5['groups'].items()}}
         del g5, o5, r5
         torch.cuda.empty_cache()
@@ -624,23 +651,33 @@ def main():
         c_bc, c_umi, c_gene = (gk >> 39).to(torch.int32), (gk >> 15) & 0xffffff, (gk & 0x7fff).to(torch.int32)
         c_out = pipeline.TallyBuffers(n_cons, 2 * n_cons + 1024, device=local_rank)
         c_strand = cb.tables['gene_strand'][c_gene.long()]
-        c3, c4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c3.record(stream)
-        pipeline.tally_reads(ctx, cres['records'], cres['off'], c_out, quality=27)
         ckey = torch.empty(n_cons, dtype=torch.int64, device=device)
-        pipeline.check(ctx.lib.dyn_group_key(ctx.handle, pipeline.ptr(c_bc), pipeline.ptr(c_umi.contiguous()), pipeline.ptr(c_gene), n_cons, 24, 15,
-                                             pipeline.ptr(ckey), pipeline._stream()))
-        c_sel = pipeline.dedup(ctx, ckey, c_out.counts, c_strand, torch.ones(n_cons, dtype=torch.uint8, device=device),
-                               torch.full((n_cons,), 91, dtype=torch.int16, device=device), c_out.conv_n, c_bc, 2 * args.barcodes,
-                               conversions=('TC',), use_conversions=False, key_lo_bits=15 + 24 + 15)
-        c4.record(stream)
+        c_score = torch.full((n_cons,), 91, dtype=torch.int16, device=device)
+        c_tr = torch.ones(n_cons, dtype=torch.uint8, device=device)
+        c3, c3b, c4 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+
+        def count_on_consensus():
+            c3.record(stream)
+            pipeline.tally_reads(ctx, cres['records'], cres['off'], c_out, quality=27)
+            c3b.record(stream)
+            pipeline.check(ctx.lib.dyn_group_key(ctx.handle, pipeline.ptr(c_bc), pipeline.ptr(c_umi), pipeline.ptr(c_gene), n_cons, 24, 15,
+                                                 pipeline.ptr(ckey), pipeline._stream()))
+            sel_ = pipeline.dedup(ctx, ckey, c_out.counts, c_strand, c_tr, c_score, c_out.conv_n, c_bc, 2 * args.barcodes,
+                                  conversions=('TC',), use_conversions=False, key_lo_bits=15 + 24 + 15)
+            c4.record(stream)
+            return sel_
+
+        c_umi = c_umi.contiguous()
+        count_on_consensus()            # warm-up: scratch of this size class is allocated on first use
+        barrier()
+        c_sel = count_on_consensus()
         barrier()
         count_ms = c3.elapsed_time(c4)
         cons = {'metric': 'member reads/s, UMI consensus (per-group shared-memory accumulation, tuple sort for scattered groups, assemble)',
                 'value': world * int(items.numel()) / (c1.elapsed_time(c2) * 1e-3), 'unit': UNIT, 'ms_consensus': c1.elapsed_time(c2),
                 'ms_grouping': c0.elapsed_time(c1), 'reads': nc, 'member_reads': int(items.numel()), 'groups': int(goff.numel() - 1),
                 'all_status_ok': ok, 'workload': 'C3-like: 91-nt reads, 3.5 reads per (barcode, UMI, gene) group, starts within 300 nt',
-                'count_on_consensus_ms': count_ms, 'count_on_consensus_rows': int(c_sel.numel()),
+                'count_on_consensus_ms': count_ms, 'count_on_consensus_tally_ms': c3.elapsed_time(c3b), 'count_on_consensus_rows': int(c_sel.numel()),
                 'count_on_consensus_note': 'tally of the consensus records + UMI dedup in mode `exon` (the RN tag of a consensus BAM '
                                            'selects it, count.py:295-304): the second half of config C3',
                 'c3_value': world * int(items.numel()) / ((c1.elapsed_time(c2) + c0.elapsed_time(c1) + count_ms) * 1e-3)}
