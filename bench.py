@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument('--consensus-reads', type=int, default=20_000_000, help='C3-like reads per GPU for the consensus stage')
     ap.add_argument('--no-emit', action='store_true', help='diagnostic: counters only, no mismatch records')
     ap.add_argument('--c5', action='store_true', help='also run config C5 per GPU: 62.5 M reads, 125 k barcodes, TC + AG labelling groups')
+    ap.add_argument('--bam-max-total', type=int, default=48_000_000, help='cap of the BAM leg\'s file over all GPUs (records)')
     ap.add_argument('--skip-bam', action='store_true')
     ap.add_argument('--skip-other-layout', action='store_true')
     ap.add_argument('--bam-reads', type=int, default=16_000_000, help='records per GPU of the synthetic BAM of the from-file leg')
@@ -552,8 +553,26 @@ def main():
     e2e_bam = None
     if not args.skip_bam:
         from dynast_b200 import synth
-        n_bam = args.bam_reads * world
-        shm = '/dev/shm' if os.path.isdir('/dev/shm') else '/tmp'
+        # one file for the whole job, capped so that writing it (rank 0's host cores, untimed) and holding it in memory stay
+        # bounded at N = 8: beyond the cap the per-GPU share shrinks and the JSON says so (records_per_gpu)
+        n_bam = min(args.bam_reads * world, max(args.bam_max_total, args.bam_reads)) // world * world
+        need = int(n_bam * 150 * 1.15)
+        shm = None
+        for cand in ('/dev/shm', '/tmp'):
+            try:
+                import shutil
+                if os.path.isdir(cand) and shutil.disk_usage(cand).free > need:
+                    shm = cand
+                    break
+            except OSError:
+                pass
+        if dist is not None:        # rank 0 decides where the file goes (or that there is no room for it)
+            where = [shm]
+            dist.broadcast_object_list(where, src=0)
+            shm = where[0]
+    if not args.skip_bam and shm is None:
+        e2e_bam = {'value': None, 'unit': UNIT, 'skipped': f'no room for a {need >> 20} MiB BAM in /dev/shm or /tmp'}
+    elif not args.skip_bam:
         bam_path = os.path.join(shm, f'dyn_bench_{os.getuid()}_{n_bam}_{args.bam_level}.bam')
         t_gen = time.perf_counter()
         if rank == 0:       # one coordinate-sorted file for the whole job; every rank then takes its block range of it
@@ -601,7 +620,7 @@ def main():
         size = os.path.getsize(bam_path)
         e2e_bam = {'metric': 'aligned reads/s from a coordinate-sorted BAM FILE: BGZF inflate + record packing + tally + UMI dedup + p_e + '
                              '(k,n) histograms + EM + pi/alpha',
-                   'value': n_bam / dt, 'unit': UNIT, 'records': n_bam, 's': dt, 'rep_s': runs, 'statistic': 'median of 3 after one warm-up',
+                   'value': n_bam / dt, 'unit': UNIT, 'records': n_bam, 'records_per_gpu': n_bam // world, 's': dt, 'rep_s': runs, 'statistic': 'median of 3 after one warm-up',
                    'ingest': st.get('ingest'), 'file_bytes': size, 'bytes_per_record': size / n_bam, 'zlib_level': args.bam_level,
                    'file_on': shm, 'h2d_bytes_per_step': int(st.get('compressed_bytes', 0)), 'reads_after_dedup': int(tallied[1].item()),
                    'barcodes_with_p_c': int(tallied[2].item()),

@@ -48,6 +48,12 @@ PROTOTYPES = {
     'dyn_owner_partition': (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     'dyn_pack_reads': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_unpack_reads': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'dyn_peer_alloc': (_i32, [_vp, _i64, C.POINTER(_vp), _vp]),
+    'dyn_peer_open': (_i32, [_vp, _vp, C.POINTER(_vp)]),
+    'dyn_peer_close': (_i32, [_vp, _vp]),
+    'dyn_peer_free': (_i32, [_vp, _vp]),
+    'dyn_push_plan': (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    'dyn_push_reads': (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dyn_merge_kn': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     'dyn_bam_pack': (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
     'dyn_bam_pack_ex': (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, _u32, C.POINTER(_vp)]),

@@ -9,6 +9,7 @@ results are gathered back.  Works with NCCL (device tensors) and
 with gloo (CPU tensors; used by the CPU tests for the exchange logic)."""
 from typing import Callable, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -106,14 +107,137 @@ def exchange_by_owner(owner: torch.Tensor, *columns: torch.Tensor, group=None):
     return out
 
 
-def exchange_reads(ctx, barcode, umi, gene, score16, conv_n, strand, counts, world: int, transcriptome=None, group=None):
-    """The per-read exchange before UMI dedup on device tensors, as ONE all-to-all: the local reads
-    are partitioned by owner = barcode % world (dyn_owner_partition), their columns gathered into 40-byte rows
-    (dyn_pack_reads), the rows exchanged (all_to_all_single over NCCL / NVLink), and unpacked on the receiving side
-    (dyn_unpack_reads).  Rows of one source rank keep their order and sources arrive in rank order, so contiguous
-    ascending read ranges stay in global read order -- what the "last row wins" tie rule of dedup needs.
+PUSH_TILE = 256          # DYN_PUSH_TILE
+PUSH_MAX_WORLD = 16      # DYN_PUSH_MAX_WORLD
+
+
+class PeerExchange:
+    """The per-read exchange with the transfer fused into the gather kernel: every rank's receive buffer is a cudaMalloc'ed
+    block whose cudaIpc handle the other ranks of the node open, and dyn_push_reads writes each read's 40-byte row straight
+    into the buffer of rank barcode % world over NVLink -- no permutation, no send buffer, no all-to-all on the data path.
+    Protocol of one exchange (all on the caller's stream): dyn_push_plan -> all_gather of the per-owner counts (tiny; a rank
+    passes it only after every rank has finished reading its receive buffer of the previous exchange) -> dyn_push_reads ->
+    barrier (a one-element all_reduce: completes after every rank's push kernel has) -> dyn_unpack_reads.
+    One instance per (context, process group); the buffers grow collectively when an exchange needs more room."""
+
+    _instances = {}
+
+    @classmethod
+    def get(cls, ctx, group=None):
+        key = (id(ctx), id(group))
+        if key not in cls._instances:
+            cls._instances[key] = cls(ctx, group)
+        return cls._instances[key]
+
+    def __init__(self, ctx, group=None):
+        self.ctx, self.group = ctx, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.capacity = 0
+        self.mine = None
+        self.peers = [None] * self.world
+        self.usable = self.world <= PUSH_MAX_WORLD
+
+    def _release(self):
+        import ctypes as C
+        for r, p in enumerate(self.peers):
+            if p and r != self.rank:
+                self.ctx.lib.dyn_peer_close(self.ctx.handle, C.c_void_p(p))
+        if self.mine:
+            self.ctx.lib.dyn_peer_free(self.ctx.handle, C.c_void_p(self.mine))
+        self.mine, self.peers, self.capacity = None, [None] * self.world, 0
+
+    def _grow(self, rows: int, device):
+        """Collective: every rank (re)allocates `rows` rows and opens everybody else's handle."""
+        import ctypes as C
+        from ._lib import check
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)                 # nobody is still writing into a buffer that is about to go away
+        self._release()
+        p = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        rc = self.ctx.lib.dyn_peer_alloc(self.ctx.handle, int(rows) * 40, C.byref(p), handle)
+        ok = torch.tensor([1 if rc == 0 else 0], device=device)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        every = torch.empty((self.world, 64), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if not bool(ok.item()):
+            if rc == 0:
+                self.ctx.lib.dyn_peer_free(self.ctx.handle, p)
+            self.usable = False
+            return False
+        self.mine = p.value
+        handles = every.cpu().numpy()
+        opened = 1
+        for r in range(self.world):
+            if r == self.rank:
+                self.peers[r] = self.mine
+                continue
+            q = C.c_void_p()
+            buf = (C.c_uint8 * 64)(*handles[r].tolist())
+            if self.ctx.lib.dyn_peer_open(self.ctx.handle, buf, C.byref(q)) != 0:
+                opened = 0
+                break
+            self.peers[r] = q.value
+        ok = torch.tensor([opened], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if not bool(ok.item()):
+            self._release()
+            self.usable = False
+            return False
+        self.capacity = int(rows)
+        return True
+
+    def exchange(self, barcode, umi, gene, score16, conv_n, strand, counts, transcriptome=None):
+        """Returns the dict of received columns (pipeline.unpack_reads), or None when peer memory is not available on this
+        node (the caller then takes the all-to-all path; the decision is collective)."""
+        import ctypes as C
+        from . import pipeline
+        from ._lib import check, ptr
+        if not self.usable:
+            return None
+        ctx, world, dev = self.ctx, self.world, barcode.device
+        n = barcode.numel()
+        n_tiles = (n + PUSH_TILE - 1) // PUSH_TILE
+        tile_base = torch.empty(max(n_tiles * world, 1), dtype=torch.int32, device=dev)
+        owner_counts = torch.empty(world, dtype=torch.int64, device=dev)
+        check(ctx.lib.dyn_push_plan(ctx.handle, ptr(barcode), n, world, ptr(tile_base), ptr(owner_counts), pipeline._stream()))
+        matrix = torch.empty((world, world), dtype=torch.int64, device=dev)          # [source, owner]
+        dist.all_gather_into_tensor(matrix, owner_counts, group=self.group)
+        m = matrix.cpu().numpy()
+        need = int(m.sum(axis=0).max())
+        if need > self.capacity and not self._grow(int(need * 1.25) + 1024, dev):
+            return None
+        starts = np.concatenate([[0], np.cumsum(m[self.rank])[:-1]])
+        dst_base = (C.c_int64 * world)(*[int(m[:self.rank, o].sum()) - int(starts[o]) for o in range(world)])
+        peers = (C.c_void_p * world)(*self.peers)
+        check(ctx.lib.dyn_push_reads(ctx.handle, ptr(tile_base), n, world, ptr(counts), ptr(barcode), ptr(umi), ptr(gene), ptr(score16),
+                                     ptr(conv_n), ptr(strand), ptr(transcriptome), peers, dst_base, pipeline._stream()))
+        done = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(done, group=self.group)        # on the stream, after the push kernel: every rank's rows have landed
+        n_recv = int(m[:, self.rank].sum())
+        rows = pipeline.DevicePointer(self.mine, (n_recv, 40), dev)
+        return pipeline.unpack_reads(ctx, rows)
+
+
+def exchange_reads(ctx, barcode, umi, gene, score16, conv_n, strand, counts, world: int, transcriptome=None, group=None,
+                   mode=None):
+    """The per-read exchange before UMI dedup on device tensors.  Rows of one source rank keep their order and
+    sources arrive in rank order, so contiguous ascending read ranges stay in global read order -- what the "last row
+    wins" tie rule of dedup needs.  Two transports with identical results:
+      'push'  (default on CUDA tensors, one node): PeerExchange -- rows are stored into the owner's memory over NVLink by
+              the kernel that gathers them;
+      'nccl'  (DYN_EXCHANGE=nccl, CPU / gloo tests, or when peer memory cannot be mapped): the local reads are partitioned
+              by owner (dyn_owner_partition), gathered into 40-byte rows (dyn_pack_reads), exchanged in ONE
+              all_to_all_single and unpacked (dyn_unpack_reads).
     Returns the dict of received columns (see pipeline.unpack_reads)."""
+    import os
     from . import pipeline
+    mode = mode or os.environ.get('DYN_EXCHANGE', 'push')
+    if world > 1 and mode == 'push' and barcode.is_cuda:
+        got = PeerExchange.get(ctx, group).exchange(barcode, umi, gene, score16, conv_n, strand, counts, transcriptome)
+        if got is not None:
+            return got
     perm, owner_counts = pipeline.owner_partition(ctx, barcode, world)
     rows = pipeline.pack_reads(ctx, perm, counts, barcode, umi, gene, score16, conv_n, strand, transcriptome)
     if world == 1:

@@ -372,7 +372,17 @@ def pack_reads(ctx: Context, perm, counts, barcode, umi, gene, score16, conv_n, 
     return rows
 
 
-def unpack_reads(ctx: Context, rows: torch.Tensor):
+class DevicePointer:
+    """A raw device allocation dressed up for ptr(): what dyn_peer_alloc returns (not a torch tensor)."""
+
+    def __init__(self, address: int, shape, device):
+        self.address, self.shape, self.device = int(address), tuple(shape), device
+
+    def data_ptr(self) -> int:
+        return self.address
+
+
+def unpack_reads(ctx: Context, rows):
     """dyn_unpack_reads -> dict(counts uint8 [n,16], barcode int32, umi int64, gene int32, score int16, conv_n int16
     (bit pattern uint16), strand uint8, transcriptome uint8)."""
     n = rows.shape[0]

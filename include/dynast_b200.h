@@ -382,6 +382,30 @@ int dyn_pack_reads(dyn_ctx_t *ctx, const uint32_t *d_perm, int64_t n, const uint
 int dyn_unpack_reads(dyn_ctx_t *ctx, const void *d_rows, int64_t n, uint8_t *d_counts, uint32_t *d_barcode, uint64_t *d_umi,
                      uint32_t *d_gene, int16_t *d_score, uint16_t *d_conv_n, uint8_t *d_strand, uint8_t *d_transcriptome,
                      void *stream);
+/* The same exchange fused with the transfer (peer stores over NVLink instead of pack + all-to-all): every rank's receive
+ * buffer is mapped into the other ranks of the node (cudaIpc), and the rows are written straight where dedup reads them.
+ *   dyn_peer_alloc / dyn_peer_open / dyn_peer_close / dyn_peer_free: a cudaMalloc'ed buffer + its 64-byte IPC handle; the
+ *                        handle opened in ANOTHER process of the node gives that process a device pointer to the buffer
+ *   dyn_push_plan:       d_tile_base[world * ceil(n / DYN_PUSH_TILE)] u32 (owner-major) = stable position of every
+ *                        (owner, tile) run in the order dyn_owner_partition would produce; d_owner_counts[world] as there
+ *   dyn_push_reads:      row of read i (layout of dyn_pack_reads) -> peer_rows[owner] + DYN_READ_ROW_BYTES * (dst_base[owner]
+ *                        + its stable position), peer_rows / dst_base: HOST arrays [world]; dst_base[o] = rows of lower ranks
+ *                        bound for o  -  first position of owner o in my order (may be negative).  The caller orders the
+ *                        ranks around the call (distributed.PeerExchange: the count all-gather before, a barrier after).
+ * ------------------------------------------------------------------------------------------------ */
+#define DYN_PUSH_TILE 256
+#define DYN_PUSH_MAX_WORLD 16
+#define DYN_PEER_HANDLE_BYTES 64
+int dyn_peer_alloc(dyn_ctx_t *ctx, int64_t bytes, void **d_ptr, void *handle_out);
+int dyn_peer_open(dyn_ctx_t *ctx, const void *handle, void **d_ptr);
+int dyn_peer_close(dyn_ctx_t *ctx, void *d_ptr);
+int dyn_peer_free(dyn_ctx_t *ctx, void *d_ptr);
+int dyn_push_plan(dyn_ctx_t *ctx, const uint32_t *d_barcode, int64_t n, int world, uint32_t *d_tile_base, uint64_t *d_owner_counts,
+                  void *stream);
+int dyn_push_reads(dyn_ctx_t *ctx, const uint32_t *d_tile_base, int64_t n, int world, const uint8_t *d_counts,
+                   const uint32_t *d_barcode, const uint64_t *d_umi, const uint32_t *d_gene, const int16_t *d_score,
+                   const uint16_t *d_conv_n, const uint8_t *d_strand, const uint8_t *d_transcriptome, void *const *peer_rows,
+                   const int64_t *dst_base, void *stream);
 /* The histogram exchange before the EM when no per-read exchange ran (no UMI stage): every rank holds
  * partial (group, k, n) -> reads rows of its read range (dyn_aggregate_kn keys with gene_bits == 0: group << 22 |
  * k << 10 | n) and sends them to rank group % world.  dyn_merge_kn turns what a rank received -- unsorted, the same

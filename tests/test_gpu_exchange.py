@@ -46,6 +46,48 @@ def test_partition_pack_unpack(gpu_ctx, n, world):
     assert torch.equal(back['umi'].cpu(), cols['umi']) and bool((back['transcriptome'] == 1).all())
 
 
+@pytest.mark.parametrize('n,world', [(1, 2), (255, 2), (257, 3), (300000, 8), (70001, 16)])
+def test_push_equals_partition_pack(gpu_ctx, n, world):
+    """dyn_push_plan + dyn_push_reads (the fused exchange) put every row where dyn_owner_partition + dyn_pack_reads + an
+    all-to-all would: here all `world` receive buffers live on this GPU, and this rank plays source `me` of `world` with
+    made-up row counts from the lower ranks (dst_base)."""
+    import ctypes as C
+    from dynast_b200 import pipeline
+    from dynast_b200._lib import check, ptr
+    ctx = gpu_ctx
+    g = torch.Generator().manual_seed(3 * n + world)
+    d = dict(barcode=torch.randint(0, 5000, (n,), generator=g).to(torch.int32).cuda(),
+             umi=torch.randint(0, 1 << 40, (n,), generator=g).cuda(),
+             gene=torch.randint(0, 30000, (n,), generator=g).to(torch.int32).cuda(),
+             score=torch.randint(-300, 300, (n,), generator=g).to(torch.int16).cuda(),
+             conv_n=torch.randint(0, 40000, (n,), generator=g).to(torch.int16).cuda(),
+             strand=torch.randint(0, 2, (n,), generator=g).to(torch.uint8).cuda(),
+             transcriptome=torch.randint(0, 2, (n,), generator=g).to(torch.uint8).cuda(),
+             counts=torch.randint(0, 256, (n, 16), generator=g).to(torch.uint8).cuda())
+    perm, cnt = pipeline.owner_partition(ctx, d['barcode'], world)
+    want = pipeline.pack_reads(ctx, perm, d['counts'], d['barcode'], d['umi'], d['gene'], d['score'], d['conv_n'], d['strand'],
+                               d['transcriptome']).cpu()
+    n_tiles = (n + 255) // 256
+    tile_base = torch.empty(max(n_tiles * world, 1), dtype=torch.int32, device='cuda')
+    cnt2 = torch.empty(world, dtype=torch.int64, device='cuda')
+    check(ctx.lib.dyn_push_plan(ctx.handle, ptr(d['barcode']), n, world, ptr(tile_base), ptr(cnt2), pipeline._stream()))
+    assert torch.equal(cnt2, cnt)
+    cnt = cnt.cpu().numpy()
+    start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    before = [(7 * o + 3) % 11 for o in range(world)]                 # rows "lower ranks" already sent to owner o
+    bufs = [torch.full((before[o] + int(cnt[o]) + 5, 40), 0xee, dtype=torch.uint8, device='cuda') for o in range(world)]
+    peers = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    dst_base = (C.c_int64 * world)(*[before[o] - int(start[o]) for o in range(world)])
+    check(ctx.lib.dyn_push_reads(ctx.handle, ptr(tile_base), n, world, ptr(d['counts']), ptr(d['barcode']), ptr(d['umi']), ptr(d['gene']),
+                                 ptr(d['score']), ptr(d['conv_n']), ptr(d['strand']), ptr(d['transcriptome']), peers, dst_base,
+                                 pipeline._stream()))
+    torch.cuda.synchronize()
+    for o in range(world):
+        got = bufs[o].cpu()
+        assert bool((got[:before[o]] == 0xee).all()) and bool((got[before[o] + int(cnt[o]):] == 0xee).all())
+        assert torch.equal(got[before[o]:before[o] + int(cnt[o])], want[int(start[o]):int(start[o]) + int(cnt[o])]), o
+
+
 def _run(rank, world, port, n_reads, n_barcodes, out_dir):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -68,6 +110,15 @@ def _run(rank, world, port, n_reads, n_barcodes, out_dir):
                                      b.strand[lo:hi], n_barcodes, b.n_genes, out, cell_threshold=50, with_pi=False,
                                      exchange=world > 1)
     k, n, c, off_h = res['hist']
+    if world > 1:       # the fused peer-store exchange ran (not the all-to-all fall-back), and both transports agree row for row
+        px = distributed.PeerExchange.get(ctx, None)
+        assert px.usable and px.capacity > 0, 'peer memory exchange not in use'
+        sc = b.score[lo:hi].to(torch.int16)
+        args = (ctx, b.barcode[lo:hi], b.umi[lo:hi], b.gene[lo:hi], sc, out.conv_n, b.strand[lo:hi], out.counts, world)
+        via_push = distributed.exchange_reads(*args, mode='push')
+        via_nccl = distributed.exchange_reads(*args, mode='nccl')
+        for key_ in via_nccl:
+            assert torch.equal(via_push[key_], via_nccl[key_]), key_
     np.savez(os.path.join(out_dir, f'r{world}_{rank}.npz'), p_e=res['p_e'].cpu().numpy(), p_c=res['p_c'].cpu().numpy(),
              st=res['em_status'].cpu().numpy(), n_reads=res['n_reads'].cpu().numpy(), k=k.cpu().numpy(), n=n.cpu().numpy(),
              c=c.cpu().numpy(), off=off_h.cpu().numpy(), n_sel=int(res['selected'].numel()), n_local=int(res['n_local_reads']))
