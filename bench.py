@@ -303,6 +303,16 @@ def multi_gpu_bit_equal(ctx, dist, rank, world, device, local_rank):
     return bool(same.item())
 
 
+def exchange_transport(ctx):
+    """Which transport the per-read exchange of the pipeline leg used (distributed.exchange_reads)."""
+    from dynast_b200 import distributed
+    px = distributed.PeerExchange._instances.get((id(ctx), id(None)))
+    if px is not None and px.usable and px.capacity > 0:
+        return ('40-byte per-read rows stored straight into the memory of rank barcode % world over NVLink by the gather kernel '
+                '(dyn_push_reads, cudaIpc peer buffers); NCCL only for the counts and the barrier')
+    return 'all-to-all of 40-byte per-read rows to rank barcode % world before dedup (dyn_pack_reads + NCCL all_to_all_single)'
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -517,7 +527,7 @@ def main():
                 'stage_ms': timings, 'repetitions': reps, 'statistic': 'median repetition', 'rep_ms': [float(x) for x in rep_ms],
                 'reads_after_dedup': int(res['selected'].numel()),
                 'barcodes_with_p_c': int((res['em_status'] == 0).sum().item()),
-                'exchange': ('all-to-all of 40-byte per-read rows to rank barcode % world before dedup (NCCL)' if xchg else None),
+                'exchange': (exchange_transport(ctx) if xchg else None),
                 'note': 'includes the host round trips of the dedup split plan and the EM / pi shape discovery'}
         del res
 
