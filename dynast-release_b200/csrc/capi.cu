@@ -281,15 +281,36 @@ extern "C" int dyn_split_plan(const uint64_t *h_first_pos, const uint32_t *h_n_r
     *h_n_splits = 1;
     if (n_barcodes == 0) return DYN_OK;
     DYN_ARG(h_first_pos && h_n_reads && h_ord_of_barcode && h_split_of_barcode, "null buffer");
-    std::vector<int64_t> order((size_t)n_barcodes);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        const uint64_t fa = h_n_reads[a] ? h_first_pos[a] : ~0ull, fb = h_n_reads[b] ? h_first_pos[b] : ~0ull;
-        return fa < fb;
-    });
+    // barcodes in first-appearance order: a stable LSD radix sort of (first position, barcode) on 16-bit digits (the
+    // comparison sorts this replaces cost 24 ms at 125 k barcodes -- two thirds of the dedup stage of config C5)
+    const size_t B = (size_t)n_barcodes;
+    std::vector<uint64_t> key(B), key2(B);
+    std::vector<uint32_t> order(B), order2(B);
+    uint64_t all_or = 0, all_and = ~0ull;
+    for (size_t b = 0; b < B; ++b) {
+        key[b] = h_n_reads[b] ? h_first_pos[b] : ~0ull;
+        order[b] = (uint32_t)b;
+        all_or |= key[b];
+        all_and &= key[b];
+    }
+    std::vector<uint32_t> hist(65536);
+    for (int shift = 0; shift < 64; shift += 16) {
+        if ((((all_or ^ all_and) >> shift) & 0xffffu) == 0) continue;          // every key has the same digit here
+        std::fill(hist.begin(), hist.end(), 0u);
+        for (size_t i = 0; i < B; ++i) ++hist[(key[i] >> shift) & 0xffffu];
+        uint32_t acc = 0;
+        for (auto &h : hist) { const uint32_t c = h; h = acc; acc += c; }
+        for (size_t i = 0; i < B; ++i) {
+            const uint32_t at = hist[(key[i] >> shift) & 0xffffu]++;
+            key2[at] = key[i];
+            order2[at] = order[i];
+        }
+        key.swap(key2);
+        order.swap(order2);
+    }
     int64_t n_splits = 0, cur = -1, cur_size = 0;
-    for (int64_t i = 0; i < n_barcodes; ++i) {
-        const int64_t b = order[i];
+    for (size_t i = 0; i < B; ++i) {
+        const uint32_t b = order[i];
         h_split_of_barcode[b] = 0;
         if (!h_n_reads[b]) continue;
         if ((int64_t)h_n_reads[b] > threshold) h_split_of_barcode[b] = (uint32_t)n_splits++;        // its own split
@@ -300,16 +321,14 @@ extern "C" int dyn_split_plan(const uint64_t *h_first_pos, const uint32_t *h_n_r
             if (cur_size > threshold) { cur = -1; cur_size = 0; }
         }
     }
-    // split-file order: by split, then first appearance
-    std::vector<int64_t> rank_of((size_t)n_barcodes);
-    for (int64_t i = 0; i < n_barcodes; ++i) rank_of[order[i]] = i;
-    std::vector<int64_t> by_split((size_t)n_barcodes);
-    std::iota(by_split.begin(), by_split.end(), 0);
-    std::stable_sort(by_split.begin(), by_split.end(), [&](int64_t a, int64_t b) {
-        if (h_split_of_barcode[a] != h_split_of_barcode[b]) return h_split_of_barcode[a] < h_split_of_barcode[b];
-        return rank_of[a] < rank_of[b];
-    });
-    for (int64_t i = 0; i < n_barcodes; ++i) h_ord_of_barcode[by_split[i]] = (uint32_t)i;
+    // split-file order: by split, then first appearance -- a counting sort of the first-appearance order by split id
+    std::vector<uint32_t> start((size_t)std::max<int64_t>(n_splits, 1) + 1, 0u);
+    for (size_t b = 0; b < B; ++b) ++start[h_split_of_barcode[b] + 1];
+    for (size_t q = 1; q < start.size(); ++q) start[q] += start[q - 1];
+    for (size_t i = 0; i < B; ++i) {
+        const uint32_t b = order[i];
+        h_ord_of_barcode[b] = start[h_split_of_barcode[b]]++;
+    }
     *h_n_splits = n_splits > 0 ? n_splits : 1;
     return DYN_OK;
 }

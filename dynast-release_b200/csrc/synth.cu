@@ -75,7 +75,21 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
     const int gene = cdf_search(P.gene_cdf, P.n_genes, gg.uniform());
     const unsigned long long umi = gg.next() & ((P.umi_len >= 32) ? ~0ull : ((1ull << (2 * P.umi_len)) - 1));
     const bool rev_gene = P.gene_strand[gene] != 0;
-    const bool labelled = g.uniform() < P.gene_pi[gene];
+    // pos_span < 0 (config C3, consensus input): the reads of a UMI group are fragments of ONE molecule -- they start within
+    // 300 nt of the group's anchor, the reference base is a function of (contig, position), the molecule is labelled or not
+    // as a whole and carries its conversions at fixed positions; only sequencing errors, N calls and qualities are per read
+    const bool clustered = P.pos_span < 0;
+    const int contig = P.gene_contig[gene];
+    int32_t pos0 = 0;
+    if (clustered) {
+        Rng gp(P.seed, (unsigned long long)idx, 3);
+        pos0 = (int32_t)(mix64(grp ^ 0x5bd1e995ull) % (unsigned long long)(-P.pos_span)) + (int32_t)(gp.next() % 300);
+    }
+    bool labelled = g.uniform() < P.gene_pi[gene];
+    if (clustered) labelled = Rng(P.seed, grp, 4).uniform() < P.gene_pi[gene];
+    const unsigned long long ref_key = mix64(P.seed ^ ((unsigned long long)(uint32_t)contig << 40));
+    const unsigned long long mol_key = mix64(P.seed ^ mix64(grp + 0x1234567ull));
+    long long rp = pos0;
     const float u_kind = g.uniform();
     uint32_t cig[3];
     int n_cig;
@@ -106,9 +120,11 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
         if (op == 0) {
             for (int j = 0; j < len; ++j) {
                 const unsigned long long r = g.next();
-                const int gb = (int)(r & 3);
+                const int gb = clustered ? (int)(mix64(ref_key + (unsigned long long)rp) & 3) : (int)(r & 3);
                 int b = gb;
-                const float u1 = (float)((r >> 8) & 0xffffff) * (1.0f / 16777216.0f);
+                const float u1 = clustered ? (float)(mix64(mol_key ^ (unsigned long long)rp) >> 40) * (1.0f / 16777216.0f)
+                                           : (float)((r >> 8) & 0xffffff) * (1.0f / 16777216.0f);
+                ++rp;
                 const float u2 = (float)((r >> 32) & 0xffffff) * (1.0f / 16777216.0f);
                 if (labelled && gb == conv_from && u1 < pc) b = conv_to;
                 if (u2 < pe3) b = (gb + 1 + (int)(u2 / (float)P.p_e)) & 3;
@@ -128,8 +144,13 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
                 ++qp;
             }
         } else if (op == 2) {
-            for (int j = 0; j < len; ++j)
-                if (n_tok < kMaxTok) tok[n_tok++] = (uint32_t)aligned | ((uint32_t)code[g.next() & 3] << 16) | (1u << 20);
+            for (int j = 0; j < len; ++j) {
+                const int db = clustered ? (int)(mix64(ref_key + (unsigned long long)rp) & 3) : (int)(g.next() & 3);
+                ++rp;
+                if (n_tok < kMaxTok) tok[n_tok++] = (uint32_t)aligned | ((uint32_t)code[db] << 16) | (1u << 20);
+            }
+        } else if (op == 3) {
+            rp += len;
         } else if (op == 1 || op == 4) {
             for (int j = 0; j < len; ++j) {
                 const unsigned long long r = g.next();
@@ -151,8 +172,8 @@ __device__ size_t gen_record(const SynthParams &P, long long idx, uint8_t *out, 
         // pos_span > 0: reads laid out in index order over the span (a coordinate-sorted BAM);
         // pos_span < 0: the reads of a UMI group start within 300 nt of the group's anchor (config C3: consensus input)
         if (P.pos_span > 0) h.pos = (int32_t)(((unsigned long long)idx * (unsigned long long)P.pos_span) / 0x100000000ull);
-        else h.pos = (int32_t)(mix64(grp ^ 0x5bd1e995ull) % (unsigned long long)(-P.pos_span)) + (int32_t)(g.next() % 300);
-        h.ref_id = P.gene_contig[gene];
+        else h.pos = pos0;
+        h.ref_id = contig;
         h.l_seq = (uint16_t)L; h.n_cigar = (uint16_t)n_cig; h.n_tok = (uint16_t)n_tok;
         h.flag = (uint16_t)(((g.next() & 1) ? 16 : 0) | (P.lean ? DYN_REC_LEAN : 0));
         *reinterpret_cast<uint4 *>(out) = *reinterpret_cast<uint4 *>(&h);

@@ -26,3 +26,23 @@ r = pipeline.consensus(ctx, cb.records, items, goff)
 e1.record()
 torch.cuda.synchronize()
 print('ms', e0.elapsed_time(e1), 'member reads/s', items.numel() / e0.elapsed_time(e1) * 1e3, 'groups', goff.numel() - 1)
+# the count stage on the consensus records (second half of config C3): sizes, CIGAR shapes, tally time, parked units
+rec_off = r['off']
+n_cons = rec_off.numel() - 1
+sizes = (rec_off[1:] - rec_off[:-1]).to(torch.int64) * 16
+hdr = r['records'].view(torch.int32)
+w = (rec_off[:-1].to(torch.int64) & 0xffffffff) * 4
+l_seq = hdr[w + 2] & 0xffff
+n_cig = (hdr[w + 2] >> 16) & 0xffff
+n_tok = hdr[w + 3] & 0xffff
+print('consensus records', n_cons, 'bytes mean/max', float(sizes.float().mean()), int(sizes.max()), 'l_seq mean/max', float(l_seq.float().mean()),
+      int(l_seq.max()), 'n_cigar mean/max', float(n_cig.float().mean()), int(n_cig.max()), 'n_tok mean/max', float(n_tok.float().mean()), int(n_tok.max()))
+out = pipeline.TallyBuffers(n_cons, 2 * n_cons + 1024, device=0)
+for _ in range(2):
+    pipeline.tally_reads(ctx, r['records'], rec_off, out, quality=27)
+torch.cuda.synchronize()
+e0.record()
+pipeline.tally_reads(ctx, r['records'], rec_off, out, quality=27)
+e1.record()
+torch.cuda.synchronize()
+print('tally of the consensus records: ms', e0.elapsed_time(e1), 'records/s', n_cons / e0.elapsed_time(e1) * 1e3, 'status', int(out.scalars[1].item()))
