@@ -51,6 +51,9 @@ namespace {
 #ifndef DYN_TALLY_SLOTS
 #define DYN_TALLY_SLOTS 8
 #endif
+#ifndef DYN_TALLY_MIN_STAGE
+#define DYN_TALLY_MIN_STAGE 8192   // bytes: smaller tiles than this are not worth a bulk copy of their own
+#endif
 #ifndef DYN_TALLY_MIN_CTAS
 #define DYN_TALLY_MIN_CTAS 12
 #endif
@@ -644,6 +647,11 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                 if (lane == 0) { wmask[c] = 0u; wpre[c] = warp_recs; }
                 __syncwarp();
             }
+            // one global atomic per warp reserves the output range of its 32 reads; issued as soon as the count is known, so
+            // that its round trip (11 % of the stall samples when it sat right before the copy-out) hides behind the
+            // gather, the CTA barrier and the next tile's copy issue below
+            unsigned long long wbase = 0ull;
+            if (emit && lane == 0 && warp_recs) wbase = atomicAdd(p.conv_total, (unsigned long long)warp_recs);
             // records among the warp's events [0, x)
             auto recs_before = [&](int x) { return wpre[x >> 5] + (uint32_t)__popc(wmask[x >> 5] & ((1u << (x & 31)) - 1u)); };
 
@@ -680,10 +688,6 @@ __global__ void __launch_bounds__(kThreads, DYN_TALLY_MIN_CTAS) tally_kernel(con
                 }
                 pre_issued = true;
             }
-            // one global atomic per warp reserves the output range of its 32 reads; its latency hides behind the
-            // counter stores
-            unsigned long long wbase = 0ull;
-            if (emit && lane == 0 && warp_recs) wbase = atomicAdd(p.conv_total, (unsigned long long)warp_recs);
             if (inrange && !slow) store_counts(p, r, ca, cc, cg, ct, w0, w1, w2, status);
             status_acc |= status;
 
@@ -923,7 +927,7 @@ extern "C" int dyn_tally_reads(dyn_ctx_t *ctx, const void *d_records, const uint
     size_t stage = ((size_t)kThreads * hint16 * 16 + DYN_TALLY_SLACK + 255) & ~(size_t)255;
     const size_t max_stage = ctx->smem_optin - kFixedSmem - 1024;
     if (stage > max_stage) stage = max_stage & ~(size_t)1023;
-    if (stage < 8192) stage = 8192;
+    if (stage < DYN_TALLY_MIN_STAGE) stage = DYN_TALLY_MIN_STAGE;
     p.stage_bytes = (uint32_t)stage;
     p.n_tiles = (n_reads + kThreads - 1) / kThreads;
     const size_t smem = stage + kFixedSmem;
