@@ -27,6 +27,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <chrono>
 #include <condition_variable>
 #include <memory>
@@ -39,12 +40,134 @@
 #include "bamrec_core.cuh"
 #include "common.cuh"
 #include "inflate_core.cuh"
+#include "inflate_lane.cuh"
+
+struct dyn_bam_dev;
+int issue_copy_if_free(dyn_bam_dev *d);
+static int inflate_warps_per_sm();
 
 namespace {
 
 constexpr int kInfWarps = 4;          // warps per CTA of the inflate kernel (one Tables set each)
 
 struct BlockDesc { uint32_t in_off, in_len, out_off, out_len; };
+
+#ifndef DYN_INF_QUORUM
+#define DYN_INF_QUORUM 1        // lanes that must be waiting at a block header before the header path is taken ...
+#endif
+#ifndef DYN_INF_WAIT
+#define DYN_INF_WAIT 0          // ... unless one of them has waited this many rounds, or no lane is decoding
+#endif
+
+// Pass 1 -- one LANE per BGZF block (inflate_lane.cuh): one-warp CTAs, each lane pulls blocks off the work counter and
+// advances its own Huffman decoder one round per iteration, writing tokens; the lanes meet again after every round.
+__global__ void __launch_bounds__(32) inflate_lanes_kernel(const uint8_t *in, uint32_t *tokens, uint32_t *n_tok, const BlockDesc *blocks,
+                                                           int n_blocks, unsigned int *next_block, uint32_t *status, uint16_t *global_tables) {
+    namespace dl = dinflate::lane;
+    extern __shared__ uint16_t lane_tables[];                  // [dl::kUnitsAll][32], or none:
+    // with the tables in global memory (L1 / L2 hold the entries in use) the warps per SM are not bound by shared memory:
+    // the pass is bound by the latency of one lane's dependent instructions, so lanes in flight are what it needs
+    uint16_t *tb = global_tables ? global_tables + (size_t)blockIdx.x * dl::kUnitsAll * 32 : lane_tables;
+    const dl::Mem<32> m{tb + threadIdx.x};
+    dl::Lane s;
+    s.state = dl::ST_END; s.err = dinflate::OK; s.op = s.out_len = 0; s.npend = 0; s.nt = 0;
+    int cur = -1;                                              // -1 nothing yet, -2 the counter ran out
+    int waited = 0;
+    for (;;) {
+        if (s.state == dl::ST_END && cur != -2) {
+            if (cur >= 0) {
+                const int err = dl::finish(s);
+                n_tok[cur] = err ? 0u : s.nt;                  // pass 2 skips a block that failed
+                if (err) atomicOr(status, 1u << err);
+            }
+            const int b = (int)atomicAdd(next_block, 1u);
+            if (b < n_blocks) {
+                cur = b;
+                const BlockDesc bd = blocks[b];
+                dl::lane_init(s, in + bd.in_off, bd.in_len, tokens + bd.out_off, bd.out_len);
+            } else cur = -2;
+        }
+        const bool live = cur >= 0 && s.state != dl::ST_END;
+        const bool at_header = live && s.state == dl::ST_HEADER;
+        bool go = at_header;
+        if (DYN_INF_QUORUM > 1) {
+            // the header path is thousands of instructions long: lanes wait so that several take it in one go
+            const unsigned hdr = __ballot_sync(0xffffffffu, at_header);
+            const unsigned busy = __ballot_sync(0xffffffffu, live && !at_header);
+            const unsigned urgent = __ballot_sync(0xffffffffu, at_header && waited >= DYN_INF_WAIT);
+            go = at_header && (busy == 0u || __popc(hdr) >= DYN_INF_QUORUM || urgent != 0u);
+        }
+        if (go) { dl::header(s, m); waited = 0; }
+        else if (at_header) ++waited;
+        else if (live) dl::round(s, m);
+        if (__all_sync(0xffffffffu, cur == -2)) break;
+    }
+}
+
+// Pass 2 -- one WARP per block: 32 tokens at a time into bytes.  Output positions by a prefix sum over the token
+// lengths; literals and matches whose source ends before the first match output of the batch (they depend on nothing
+// the batch's other matches write) lane-parallel, the remaining matches in stream order with the whole warp on each.
+constexpr int kLzWarps = 8;
+__global__ void __launch_bounds__(kLzWarps * 32) lz_kernel(const uint32_t *tokens, const uint32_t *n_tok, uint8_t *out, const BlockDesc *blocks,
+                                                          int n_blocks, unsigned int *next_block) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = (int)atomicAdd(next_block, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_blocks) return;
+        const BlockDesc bd = blocks[b];
+        const uint32_t *tok = tokens + bd.out_off;
+        const uint32_t nt = n_tok[b];
+        uint8_t *dst = out + bd.out_off;
+        uint32_t out_pos = 0;
+        uint32_t e_next = lane < nt ? tok[lane] : 0u;
+        for (uint32_t base = 0; base < nt; base += 32) {
+            const uint32_t n = nt - base < 32u ? nt - base : 32u;
+            const uint32_t e = e_next;
+            if (base + 32 < nt) e_next = base + 32 + lane < nt ? tok[base + 32 + lane] : 0u;       // the next batch is on its way
+            const bool live = (uint32_t)lane < n;
+            const bool is_match = live && (e >> 31);
+            const uint32_t my_len = live ? (is_match ? (e & 0x1ffu) : ((e >> 29) & 3u) + 1u) : 0u;
+            uint32_t incl = my_len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t my_pos = out_pos + incl - my_len;
+            if (live && !is_match) {
+                dst[my_pos] = (uint8_t)e;
+                if (my_len > 1) dst[my_pos + 1] = (uint8_t)(e >> 8);
+                if (my_len > 2) dst[my_pos + 2] = (uint8_t)(e >> 16);
+            }
+            __syncwarp();
+            const uint32_t all_matches = __ballot_sync(0xffffffffu, is_match);
+            if (all_matches) {
+                const uint32_t first_pos = __shfl_sync(0xffffffffu, my_pos, __ffs((int)all_matches) - 1);
+                const uint32_t len = e & 0x1ffu, dist = (e >> 9) & 0xffffu;
+                const bool ready = is_match && len <= 32u && my_pos - dist + len <= first_pos;
+                if (ready) {
+                    const uint8_t *src = dst + my_pos - dist;
+                    for (uint32_t k = 0; k < len; ++k) dst[my_pos + k] = src[k];
+                }
+                __syncwarp();
+                uint32_t mm = __ballot_sync(0xffffffffu, is_match && !ready);
+                while (mm) {
+                    const int i = __ffs((int)mm) - 1;
+                    mm &= mm - 1;
+                    const uint32_t ei = __shfl_sync(0xffffffffu, e, i), pi = __shfl_sync(0xffffffffu, my_pos, i);
+                    const uint32_t li = ei & 0x1ffu, di = (ei >> 9) & 0xffffu;
+                    const uint8_t *src = dst + pi - di;
+                    if (di >= li) { for (uint32_t k = lane; k < li; k += 32) dst[pi + k] = src[k]; }
+                    else { for (uint32_t k = lane; k < li; k += 32) dst[pi + k] = src[k % di]; }      // overlapping copy = a repeating pattern
+                    __syncwarp();
+                }
+            }
+            out_pos += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *in, uint8_t *out, const BlockDesc *blocks, int n_blocks,
                                                                 unsigned int *next_block, uint32_t *status) {
@@ -248,7 +371,7 @@ struct IngestBuffers {
     Staged staged[3];
     DevBuf d_comp[2], d_blocks[2];        // double buffered: chunk i + 1 is copied while chunk i is inflated
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-    DevBuf d_inflated, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
+    DevBuf d_inflated, d_tokens, d_ntok, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
     struct OutSet { DevBuf blob, rec_off, bc, umi, gene, score, ref_id, pos, hi, flag, gxa; } out[2];
     uint32_t *h_small = nullptr;          // page-locked landing zone
     ~IngestBuffers() {
@@ -269,7 +392,8 @@ struct dyn_bam_dev {
     // options
     bamrec::Tags tags{};
     int lean = 1;
-    size_t chunk_bytes = 1024u << 20;      // ~16 000 BGZF blocks: 3.5 waves of the inflate kernel's resident warps
+    size_t chunk_bytes = 0xf0000000u;      // inflated bytes per chunk (below 4 GiB: 32-bit offsets), and
+    size_t chunk_blocks = 0;               // BGZF blocks per chunk: ONE wave of the Huffman pass (a lane per block, 96 lanes per SM)
     // header / file layout (host)
     std::string header_text;
     std::vector<char> ref_names;
@@ -292,6 +416,7 @@ struct dyn_bam_dev {
     std::string err_msg;
     IngestBuffers *buf = nullptr;         // shared intermediates + two sets of outputs + staging
     int cur = 0, copy_slot = 0;
+    bool slot_busy[2] = {false, false};    // (under mu) the device buffer pair holds a slab that is not inflated yet
     int64_t records_seen = 0;
 
     ~dyn_bam_dev() {
@@ -340,6 +465,7 @@ inline bool bgzf_header(const uint8_t *p, size_t avail, size_t *blen) {
 // The reader thread: reads the next slab of the file straight into page-locked staging memory and lists the BGZF
 // blocks it holds by hopping over their BSIZE fields there -- the file is never scanned up front.
 void read_ahead(dyn_bam_dev *d) {
+    cudaSetDevice(d->ctx->device);
     for (;;) {
         Staged *s = nullptr;
         {
@@ -350,7 +476,16 @@ void read_ahead(dyn_bam_dev *d) {
             s = d->free_list.front();
             d->free_list.pop_front();
         }
-        const size_t want = std::min(d->file_len - d->pos, (size_t)((double)d->chunk_bytes * d->ratio * 1.05) + (1u << 20));
+        // blocks of this chunk: at most one wave of the Huffman pass, and the rest of the range in equal parts (a last chunk
+        // of a few blocks would take as long as a full one: the pass is bound by the latency of one block)
+        size_t block_cap = d->chunk_blocks;
+        if (block_cap) {
+            const double est_blocks = (double)(d->end - d->pos) / (d->ratio * 65280.0) + 1.0;
+            const double n_chunks = std::ceil(est_blocks / (double)block_cap);
+            block_cap = std::min(block_cap, (size_t)std::ceil(est_blocks / n_chunks * 1.02) + 8);
+        }
+        const size_t inflated_cap = block_cap ? std::min(d->chunk_bytes, block_cap * (size_t)65536) : d->chunk_bytes;
+        const size_t want = std::min(d->file_len - d->pos, (size_t)((double)inflated_cap * d->ratio * 1.05) + (1u << 20));
         bool ok = true;
         if (s->cap < want) {
             if (s->bytes) cudaFreeHost(s->bytes);
@@ -359,7 +494,7 @@ void read_ahead(dyn_bam_dev *d) {
         }
         if (ok) {
             // the file range is read by a few threads: one pread stream does not saturate a page cache / NVMe
-            const int nt = 4;
+            static const int nt = [] { const char *e = getenv("DYN_BAM_READ_THREADS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
             std::vector<std::thread> th;
             std::vector<char> good(nt, 1);
             for (int t = 0; t < nt; ++t)
@@ -381,7 +516,7 @@ void read_ahead(dyn_bam_dev *d) {
             if (q + blen > want) break;                                  // the block continues behind this slab
             const uint32_t xlen = bamrec::ld16(s->bytes + q + 10);
             const uint32_t isize = bamrec::ld32(s->bytes + q + blen - 4);
-            if (!s->blocks.empty() && s->inflated + isize > d->chunk_bytes) break;
+            if (!s->blocks.empty() && (s->inflated + isize > d->chunk_bytes || (block_cap && s->blocks.size() >= block_cap))) break;
             s->blocks.push_back(BlockDesc{(uint32_t)(q + 12 + xlen), (uint32_t)(blen - 12 - xlen - 8), (uint32_t)s->inflated, isize});
             s->inflated += isize;
             q += blen;
@@ -401,6 +536,8 @@ void read_ahead(dyn_bam_dev *d) {
             return;
         }
         d->ready.push_back(s);
+        // straight on to the GPU if a device buffer pair is free: the copy then runs under the inflate of the slab before
+        if (issue_copy_if_free(d) != DYN_OK) { d->err = DYN_ERR_CUDA; d->err_msg = "dyn_bam_dev: host to device copy failed"; d->finished = true; }
         d->cv.notify_all();
     }
 }
@@ -468,6 +605,8 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
     d->lean = o->lean != 0;
     d->tags.lean = d->lean;
     if (o->chunk_bytes > 0) d->chunk_bytes = (size_t)o->chunk_bytes;
+    d->chunk_bytes = std::min(d->chunk_bytes, (size_t)0xf0000000u);      // block offsets inside a chunk are 32 bits wide
+    d->chunk_blocks = (size_t)ctx->sm_count * inflate_warps_per_sm() * 32;
     d->fd = open(path, O_RDONLY);
     if (d->fd < 0) { dyn_set_error("dyn_bam_dev_open: cannot open %s", path); return DYN_ERR_IO; }
     {
@@ -596,6 +735,47 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
 }
 
 // Starts the host -> device copy of a staged run of blocks on the context's copy stream (device buffer pair `slot`).
+// Warps (of 32 decoding lanes) per SM of the Huffman pass: up to 3 keep their tables in shared memory, more keep them in
+// global memory (DYN_INF_WARPS).
+static int inflate_warps_per_sm() {
+    static const int w = [] { const char *e = getenv("DYN_INF_WARPS"); const int v = e ? atoi(e) : 12; return v < 1 ? 1 : (v > 24 ? 24 : v); }();
+    return w;
+}
+
+// The inflate launch: two passes, Huffman with one lane per block then LZ77 with one warp per block (default), or
+// DYN_INFLATE=warp for the one-pass one-warp-per-block kernel they replaced.  d_tokens: as many u32 as inflated bytes,
+// d_ntok: one u32 per block, work: two zeroed counters.
+static int launch_inflate(dyn_ctx *ctx, const uint8_t *in, uint8_t *out, const BlockDesc *blocks, int nb, uint32_t *d_tokens, uint32_t *d_ntok,
+                          uint32_t *work, uint32_t *status, cudaStream_t stream) {
+    static const bool by_warp = [] { const char *e = getenv("DYN_INFLATE"); return e && !strcmp(e, "warp"); }();
+    if (by_warp) {
+        const int ctas = std::min((nb + kInfWarps - 1) / kInfWarps, ctx->sm_count * 8);
+        inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(in, out, blocks, nb, work, status);
+    } else {
+        const size_t table_bytes = sizeof(uint16_t) * dinflate::lane::kUnitsAll * 32;
+        static bool configured = false;
+        if (!configured) {
+            DYN_CUDA(cudaFuncSetAttribute(inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+            configured = true;
+        }
+        const int warps = inflate_warps_per_sm();
+        const int ctas = std::min((nb + 31) / 32, ctx->sm_count * warps);
+        uint16_t *tables = nullptr;
+        if (warps > 3) {
+            void *p = nullptr;
+            int rc = dyn_ctx_scratch(ctx, 18, table_bytes * (size_t)ctas, &p);
+            if (rc) return rc;
+            tables = static_cast<uint16_t *>(p);
+        }
+        inflate_lanes_kernel<<<ctas, 32, tables ? 0 : table_bytes, stream>>>(in, d_tokens, d_ntok, blocks, nb, work, status, tables);
+        DYN_CUDA(cudaGetLastError());
+        const int lz_ctas = std::min((nb + kLzWarps - 1) / kLzWarps, ctx->sm_count * 8);
+        lz_kernel<<<lz_ctas, kLzWarps * 32, 0, stream>>>(d_tokens, d_ntok, out, blocks, nb, work + 4);
+    }
+    DYN_CUDA(cudaGetLastError());
+    return DYN_OK;
+}
+
 static int issue_copy(dyn_bam_dev *d, Staged *s, int slot) {
     IngestBuffers &B = *d->buf;
     int rc;
@@ -606,6 +786,19 @@ static int issue_copy(dyn_bam_dev *d, Staged *s, int slot) {
     DYN_CUDA(cudaMemcpyAsync(B.d_blocks[slot].p, s->blocks.data(), sizeof(BlockDesc) * s->blocks.size(), cudaMemcpyHostToDevice, cs));
     DYN_CUDA(cudaEventRecord(B.ev_copy[slot], cs));
     s->dev_slot = slot;
+    return DYN_OK;
+}
+
+// (d->mu held) starts the host to device copy of the first staged slab that has none yet, if the next buffer pair is free
+int issue_copy_if_free(dyn_bam_dev *d) {
+    for (Staged *s : d->ready) {
+        if (s->dev_slot >= 0) continue;
+        if (d->slot_busy[d->copy_slot]) return DYN_OK;
+        int rc = issue_copy(d, s, d->copy_slot);
+        if (rc) return rc;
+        d->slot_busy[d->copy_slot] = true;
+        d->copy_slot ^= 1;
+    }
     return DYN_OK;
 }
 
@@ -631,15 +824,24 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
         s = d->ready.front();
         d->ready.pop_front();
     }
-    struct Release {        // the staging buffer goes back to the reader when this call is done with it
-        dyn_bam_dev *d; Staged *s;
-        ~Release() { std::lock_guard<std::mutex> l(d->mu); s->dev_slot = -1; d->free_list.push_back(s); d->cv.notify_all(); }
+    struct Release {        // the staging buffer goes back to the reader when this call is done with it, and the device
+        dyn_bam_dev *d; Staged *s;      // buffer pair (compressed bytes + block descriptors, read up to the index kernels) is free for the next copy
+        ~Release() {
+            std::lock_guard<std::mutex> l(d->mu);
+            if (s->dev_slot >= 0) d->slot_busy[s->dev_slot] = false;
+            s->dev_slot = -1;
+            d->free_list.push_back(s);
+            issue_copy_if_free(d);
+            d->cv.notify_all();
+        }
     } release{d, s};
     const int nb = (int)s->blocks.size();
     auto t_staged = now();
     int rc;
-    if (s->dev_slot < 0) {      // not copied ahead (first chunk, or the reader was not ahead of us)
+    if (s->dev_slot < 0) {      // not copied ahead: both buffer pairs were busy when the reader staged it
+        std::lock_guard<std::mutex> l(d->mu);
         if ((rc = issue_copy(d, s, d->copy_slot))) return rc;
+        d->slot_busy[d->copy_slot] = true;
         d->copy_slot ^= 1;
     }
     const int slot = s->dev_slot;
@@ -648,27 +850,20 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     if ((rc = B.d_recbase.ensure(4 * (size_t)(nb + 1)))) return rc;
     uint32_t *d_small = B.d_small.as<uint32_t>();      // [0] inflate work counter, [1] status, [2..3] scan totals
     DYN_CUDA(cudaMemsetAsync(d_small, 0, 64, stream));
+    static cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (timing && !tev[0]) for (auto &e : tev) cudaEventCreate(&e);
+    if (timing) cudaEventRecord(tev[0], stream);
     DYN_CUDA(cudaStreamWaitEvent(stream, B.ev_copy[slot], 0));
+    if (timing) cudaEventRecord(tev[1], stream);
     // ---- k1: inflate, one warp per block
     {
-        const int ctas = std::min((nb + kInfWarps - 1) / kInfWarps, d->ctx->sm_count * 8);
-        inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(B.d_comp[slot].as<uint8_t>(), B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb,
-                                                            d_small, d_small + 1);
-        DYN_CUDA(cudaGetLastError());
+        if ((rc = B.d_tokens.ensure(4 * (s->inflated + 16)))) return rc;
+        if ((rc = B.d_ntok.ensure(4 * (size_t)(nb + 1)))) return rc;
+        if ((rc = launch_inflate(d->ctx, B.d_comp[slot].as<uint8_t>(), B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb,
+                                 B.d_tokens.as<uint32_t>(), B.d_ntok.as<uint32_t>(), d_small, d_small + 1, stream)))
+            return rc;
     }
-    {
-        // the next run of blocks, if the reader has it already, crosses PCIe while this one is inflated (the other buffer
-        // pair is free: its chunk was inflated before the previous call returned)
-        Staged *ahead = nullptr;
-        {
-            std::lock_guard<std::mutex> l(d->mu);
-            if (!d->ready.empty() && d->ready.front()->dev_slot < 0) ahead = d->ready.front();
-        }
-        if (ahead) {
-            if ((rc = issue_copy(d, ahead, d->copy_slot))) return rc;
-            d->copy_slot ^= 1;
-        }
-    }
+    if (timing) cudaEventRecord(tev[2], stream);
     // ---- k2: records per block, their prefix sum, the total
     index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb, s->first_skip,
                                                        B.d_nrec.as<uint32_t>(), nullptr, nullptr, d_small + 1);
@@ -680,8 +875,16 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     DYN_CUDA(cub::DeviceScan::ExclusiveSum(B.d_tmp.p, tmp_bytes, B.d_nrec.as<uint32_t>(), B.d_recbase.as<uint32_t>(), nb + 1, stream));
     DYN_CUDA(cudaMemcpyAsync(B.h_small, B.d_recbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaMemcpyAsync(B.h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
+    auto t_launched = now();
+    if (timing) cudaEventRecord(tev[3], stream);
     DYN_CUDA(cudaStreamSynchronize(stream));
     auto t_inflated = now();
+    if (timing) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]); cudaEventElapsedTime(&c, tev[2], tev[3]);
+        fprintf(stderr, "   on the stream: wait for the H2D copy %.2f ms, inflate (both passes) %.2f, index + scan %.2f; host: launches done after %.2f ms\n", a, b, c,
+                std::chrono::duration<double, std::milli>(t_launched - t_staged).count());
+    }
     const uint32_t n_rec = B.h_small[0];
     uint32_t status = B.h_small[1];
     auto status_error = [&](uint32_t st) -> int {
@@ -793,10 +996,22 @@ extern "C" int dyn_inflate_blocks(dyn_ctx_t *ctx, const void *d_in, void *d_out,
     DYN_ARG(n_blocks >= 0, "negative n_blocks");
     if (n_blocks == 0) return DYN_OK;
     DYN_ARG(d_in && d_out && d_block_desc && d_work && d_status, "null buffer");
-    DYN_CUDA(cudaMemsetAsync(d_work, 0, 4, static_cast<cudaStream_t>(stream)));
-    const int ctas = std::min((n_blocks + kInfWarps - 1) / kInfWarps, ctx->sm_count * 8);
-    inflate_kernel<<<ctas, kInfWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t *>(d_in), static_cast<uint8_t *>(d_out),
-                                                                                    reinterpret_cast<const BlockDesc *>(d_block_desc), n_blocks, d_work, d_status);
-    DYN_CUDA(cudaGetLastError());
-    return DYN_OK;
+    // scratch of the two-pass decoder: work counters, tokens per block, one token word per output byte (the descriptors are
+    // read back for the output size: a test / tool entry, not the ingest path)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<BlockDesc> h((size_t)n_blocks);
+    DYN_CUDA(cudaMemcpyAsync(h.data(), d_block_desc, sizeof(BlockDesc) * (size_t)n_blocks, cudaMemcpyDeviceToHost, st));
+    DYN_CUDA(cudaStreamSynchronize(st));
+    size_t out_bytes = 0;
+    for (const BlockDesc &bd : h) out_bytes = std::max(out_bytes, (size_t)bd.out_off + bd.out_len);
+    void *scratch = nullptr;
+    const size_t ntok_at = 256, tok_at = (ntok_at + 4 * (size_t)n_blocks + 255) & ~(size_t)255;
+    int rc = dyn_ctx_scratch(ctx, 17, tok_at + 4 * (out_bytes + 16), &scratch);
+    if (rc) return rc;
+    uint8_t *base = static_cast<uint8_t *>(scratch);
+    DYN_CUDA(cudaMemsetAsync(base, 0, 64, st));
+    DYN_CUDA(cudaMemsetAsync(d_work, 0, 4, st));
+    return launch_inflate(ctx, static_cast<const uint8_t *>(d_in), static_cast<uint8_t *>(d_out), reinterpret_cast<const BlockDesc *>(d_block_desc),
+                          n_blocks, reinterpret_cast<uint32_t *>(base + tok_at), reinterpret_cast<uint32_t *>(base + ntok_at),
+                          reinterpret_cast<uint32_t *>(base), d_status, st);
 }

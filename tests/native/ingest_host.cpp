@@ -7,6 +7,7 @@
 
 #include "../../dynast-release_b200/csrc/bamrec_core.cuh"
 #include "../../dynast-release_b200/csrc/inflate_core.cuh"
+#include "../../dynast-release_b200/csrc/inflate_lane.cuh"
 
 extern "C" int host_inflate(const uint8_t *in, uint32_t in_len, uint8_t *dst, uint32_t out_len) {
     static dinflate::Tables t;
@@ -65,6 +66,14 @@ extern "C" int host_inflate(const uint8_t *in, uint32_t in_len, uint8_t *dst, ui
     }
     if (s.err) return s.err;
     return s.out_pos == out_len ? 0 : dinflate::ERR_OUTPUT;
+}
+
+// The one-lane-per-block decoder of inflate_lanes_kernel on one "lane" (tables not interleaved).
+extern "C" int host_inflate_lane(const uint8_t *in, uint32_t in_len, uint8_t *dst, uint32_t out_len) {
+    static uint16_t tables[dinflate::lane::kUnitsAll];
+    const dinflate::lane::Mem<1> m{tables};
+    std::vector<uint32_t> tok(out_len + 1);
+    return dinflate::lane::inflate_block(m, in, in_len, tok.data(), dst, out_len);
 }
 
 // Records of one inflated chunk (record chain walked here), parsed and packed by the device cores.

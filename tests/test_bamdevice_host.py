@@ -24,17 +24,22 @@ def shim(tmp_path_factory):
                    check=True)
     lib = C.CDLL(out)
     lib.host_inflate.restype = C.c_int
+    lib.host_inflate_lane.restype = C.c_int
     lib.host_parse_pack.restype = C.c_long
     lib.host_fnv1a.restype = C.c_uint64
     lib.host_fnv1a.argtypes = [C.c_char_p]
     return lib
 
 
-def _inflate(shim, comp: bytes, n_out: int, shift: int = 0):
-    out = np.zeros(n_out + 8, dtype=np.uint8)
-    src = np.zeros(len(comp) + 48, dtype=np.uint8)          # the bit reader loads aligned 16-byte pieces: padded input
-    src[shift:shift + len(comp)] = np.frombuffer(comp, dtype=np.uint8)
-    rc = shim.host_inflate(C.c_void_p(src.ctypes.data + shift), C.c_uint32(len(comp)), C.c_void_p(out.ctypes.data), C.c_uint32(n_out))
+DECODERS = ['host_inflate_lane', 'host_inflate']          # one lane per block (the kernel in use), one warp per block
+
+
+def _inflate(shim, comp: bytes, n_out: int, shift: int = 0, fn: str = 'host_inflate_lane'):
+    out = np.full(n_out + 64, 0x5a, dtype=np.uint8)
+    src = np.full(len(comp) + 48, 0xa5, dtype=np.uint8)     # the bit readers load aligned words: padded input (not zeros:
+    src[shift:shift + len(comp)] = np.frombuffer(comp, dtype=np.uint8)      # nothing behind the payload may matter)
+    rc = getattr(shim, fn)(C.c_void_p(src.ctypes.data + shift), C.c_uint32(len(comp)), C.c_void_p(out.ctypes.data), C.c_uint32(n_out))
+    assert bool((out[n_out:] == 0x5a).all()), 'wrote behind the output block'
     return rc, bytes(out[:n_out])
 
 
@@ -54,18 +59,20 @@ def bgzf_payloads(path):
         o += bsize
 
 
+@pytest.mark.parametrize('fn', DECODERS)
 @pytest.mark.parametrize('align', ['SRR11683995_align', 'smartseq_align', 'nasc_align'])
-def test_inflate_core_on_bgzf_blocks(shim, align):
+def test_inflate_core_on_bgzf_blocks(shim, align, fn):
     n = 0
     for comp, isize in bgzf_payloads(ref_path(align, 'Aligned.sortedByCoord.out.bam')):
-        rc, got = _inflate(shim, comp, isize, shift=n % 8)          # payloads start at any byte alignment
+        rc, got = _inflate(shim, comp, isize, shift=n % 8, fn=fn)          # payloads start at any byte alignment
         assert rc == 0
         assert got == zlib.decompress(comp, -15)
         n += 1
     assert n > 3
 
 
-def test_inflate_core_stream_kinds(shim):
+@pytest.mark.parametrize('fn', DECODERS)
+def test_inflate_core_stream_kinds(shim, fn):
     rng = np.random.default_rng(0)
     texts = [
         b'',
@@ -81,19 +88,26 @@ def test_inflate_core_stream_kinds(shim):
         for level in (0, 1, 6, 9):
             for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
                 comp = _raw_deflate(data, level, strategy)
-                rc, got = _inflate(shim, comp, len(data))
-                assert rc == 0 and got == data, (len(data), level, strategy)
+                for shift in (0, 3):
+                    rc, got = _inflate(shim, comp, len(data), shift=shift, fn=fn)
+                    assert rc == 0 and got == data, (len(data), level, strategy, shift)
 
 
-def test_inflate_core_rejects_corrupt_input(shim):
+@pytest.mark.parametrize('fn', DECODERS)
+def test_inflate_core_rejects_corrupt_input(shim, fn):
     data = bytes(np.random.default_rng(1).integers(65, 70, 30000, dtype=np.uint8))
     comp = _raw_deflate(data)
-    assert _inflate(shim, comp, len(data) - 10)[0] != 0          # output larger than announced
-    assert _inflate(shim, comp, len(data) + 10)[0] != 0          # ... and smaller
-    assert _inflate(shim, comp[:len(comp) // 2], len(data))[0] != 0      # truncated input
+    assert _inflate(shim, comp, len(data) - 10, fn=fn)[0] != 0          # output larger than announced
+    assert _inflate(shim, comp, len(data) + 10, fn=fn)[0] != 0          # ... and smaller
+    assert _inflate(shim, comp[:len(comp) // 2], len(data), fn=fn)[0] != 0      # truncated input
     bad = bytearray(comp)
     bad[0] |= 0x06                                                # block type 3
-    assert _inflate(shim, bytes(bad), len(data))[0] != 0
+    assert _inflate(shim, bytes(bad), len(data), fn=fn)[0] != 0
+    # random garbage must end (with an error or by chance without), never hang or write out of bounds
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        junk = bytes(rng.integers(0, 256, int(rng.integers(1, 400)), dtype=np.uint8))
+        _inflate(shim, junk, int(rng.integers(0, 3000)), fn=fn)
 
 
 @pytest.mark.parametrize('lean', [1, 0])
