@@ -251,12 +251,13 @@ class DeviceBamStream:
 
     def __init__(self, ctx, path: str, barcode_tag: Optional[str] = None, umi_tag: Optional[str] = None,
                  gene_tag: Optional[str] = 'GX', require_gene: bool = False, part: int = 0, n_parts: int = 1,
-                 chunk_bytes: int = 0, lean: bool = True, gene_ids: Optional[List[str]] = None):
+                 chunk_bytes: int = 0, lean: bool = True, gene_ids: Optional[List[str]] = None, n_threads: int = 0):
+        """n_threads: host threads that read the file into page-locked memory (0: the library's default, 16)."""
         self.ctx = ctx
         self.lib = ctx.lib
         enc = lambda s: s.encode() if s else None
         o = _lib.BamStreamOpts(barcode_tag=enc(barcode_tag), umi_tag=enc(umi_tag), gene_tag=enc(gene_tag),
-                               require_gene=int(require_gene), n_threads=1, part=int(part), n_parts=int(n_parts),
+                               require_gene=int(require_gene), n_threads=int(n_threads), part=int(part), n_parts=int(n_parts),
                                chunk_bytes=int(chunk_bytes), lean=int(lean), keys=1)
         self._gene_ids = None
         if gene_ids is not None:

@@ -55,6 +55,9 @@ struct BlockDesc { uint32_t in_off, in_len, out_off, out_len; };
 #ifndef DYN_INF_QUORUM
 #define DYN_INF_QUORUM 1        // lanes that must be waiting at a block header before the header path is taken ...
 #endif
+#ifndef DYN_INF_ROUNDS
+#define DYN_INF_ROUNDS 4         // Huffman codes per lane between two looks at the lanes' states
+#endif
 #ifndef DYN_INF_WAIT
 #define DYN_INF_WAIT 0          // ... unless one of them has waited this many rounds, or no lane is decoding
 #endif
@@ -99,7 +102,12 @@ __global__ void __launch_bounds__(32) inflate_lanes_kernel(const uint8_t *in, ui
         }
         if (go) { dl::header(s, m); waited = 0; }
         else if (at_header) ++waited;
-        else if (live) dl::round(s, m);
+        else if (live) {
+            // a few rounds per trip through the bookkeeping above (a lane that reaches a header or its block's end
+            // idles for the rest of them: round() does nothing in those states)
+#pragma unroll 1
+            for (int k = 0; k < DYN_INF_ROUNDS; ++k) dl::round(s, m);
+        }
         if (__all_sync(0xffffffffu, cur == -2)) break;
     }
 }
@@ -393,6 +401,7 @@ struct dyn_bam_dev {
     bamrec::Tags tags{};
     int lean = 1;
     size_t chunk_bytes = 0xf0000000u;      // inflated bytes per chunk (below 4 GiB: 32-bit offsets), and
+    int read_threads = 16;                 // pread threads of the reader (opts->n_threads; DYN_BAM_READ_THREADS overrides)
     size_t chunk_blocks = 0;               // BGZF blocks per chunk: ONE wave of the Huffman pass (a lane per block, 96 lanes per SM)
     // header / file layout (host)
     std::string header_text;
@@ -492,18 +501,34 @@ void read_ahead(dyn_bam_dev *d) {
             s->cap = want + want / 4 + (1 << 20);
             if (cudaHostAlloc((void **)&s->bytes, s->cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); s->bytes = nullptr; s->cap = 0; ok = false; }
         }
+        // If a device buffer pair is free the slab goes to the GPU stripe by stripe WHILE it is being read (the copy of a
+        // 1 GB slab takes 18 ms over PCIe: behind the read it would be 18 ms in which the GPU has nothing to inflate)
+        int stream_slot = -1;
         if (ok) {
-            // the file range is read by a few threads: one pread stream does not saturate a page cache / NVMe
-            static const int nt = [] { const char *e = getenv("DYN_BAM_READ_THREADS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
-            std::vector<std::thread> th;
-            std::vector<char> good(nt, 1);
-            for (int t = 0; t < nt; ++t)
-                th.emplace_back([&, t] {
-                    const size_t a = want * t / nt, b = want * (t + 1) / nt;
-                    good[t] = pread_all(d->fd, s->bytes + a, b - a, d->pos + a) ? 1 : 0;
-                });
-            for (auto &t : th) t.join();
-            for (char g : good) ok &= g != 0;
+            std::lock_guard<std::mutex> l(d->mu);
+            if (!d->slot_busy[d->copy_slot]) { stream_slot = d->copy_slot; d->slot_busy[stream_slot] = true; d->copy_slot ^= 1; }
+        }
+        if (stream_slot >= 0 && d->buf->d_comp[stream_slot].ensure(want + 16) != DYN_OK) ok = false;
+        if (ok) {
+            // the file range is read by several threads: one pread stream does not saturate a page cache / NVMe
+            static const int env_nt = [] { const char *e = getenv("DYN_BAM_READ_THREADS"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 64 ? 64 : v); }();
+            const int nt = env_nt ? env_nt : d->read_threads;
+            const size_t stripe = (size_t)128 << 20;
+            for (size_t a0 = 0; ok && a0 < want; a0 += stripe) {
+                const size_t len = std::min(stripe, want - a0);
+                std::vector<std::thread> th;
+                std::vector<char> good(nt, 1);
+                for (int t = 0; t < nt; ++t)
+                    th.emplace_back([&, t] {
+                        const size_t a = a0 + len * t / nt, b = a0 + len * (t + 1) / nt;
+                        good[t] = pread_all(d->fd, s->bytes + a, b - a, d->pos + a) ? 1 : 0;
+                    });
+                for (auto &t : th) t.join();
+                for (char g : good) ok &= g != 0;
+                if (ok && stream_slot >= 0 &&
+                    cudaMemcpyAsync(d->buf->d_comp[stream_slot].as<uint8_t>() + a0, s->bytes + a0, len, cudaMemcpyHostToDevice, d->ctx->copy_stream[0]) != cudaSuccess)
+                    ok = false;
+            }
         }
         s->blocks.clear();
         s->inflated = 0;
@@ -530,10 +555,20 @@ void read_ahead(dyn_bam_dev *d) {
         s->last = d->pos >= d->end;
         std::lock_guard<std::mutex> l(d->mu);
         if (!ok || corrupt) {
+            if (stream_slot >= 0) d->slot_busy[stream_slot] = false;
             d->err = corrupt ? DYN_ERR_FORMAT : DYN_ERR_IO;
             d->err_msg = corrupt ? "dyn_bam_dev: corrupt BGZF block" : "dyn_bam_dev: reading the BAM failed";
             d->finished = true; d->cv.notify_all();
             return;
+        }
+        if (stream_slot >= 0) {      // the compressed bytes are on their way already: block descriptors, then the event the inflate waits on
+            IngestBuffers &B = *d->buf;
+            if (B.d_blocks[stream_slot].ensure(sizeof(BlockDesc) * s->blocks.size()) != DYN_OK ||
+                cudaMemcpyAsync(B.d_blocks[stream_slot].p, s->blocks.data(), sizeof(BlockDesc) * s->blocks.size(), cudaMemcpyHostToDevice, d->ctx->copy_stream[0]) != cudaSuccess ||
+                cudaEventRecord(B.ev_copy[stream_slot], d->ctx->copy_stream[0]) != cudaSuccess) {
+                d->err = DYN_ERR_CUDA; d->err_msg = "dyn_bam_dev: host to device copy failed"; d->finished = true;
+            }
+            s->dev_slot = stream_slot;
         }
         d->ready.push_back(s);
         // straight on to the GPU if a device buffer pair is free: the copy then runs under the inflate of the slab before
@@ -607,6 +642,7 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
     if (o->chunk_bytes > 0) d->chunk_bytes = (size_t)o->chunk_bytes;
     d->chunk_bytes = std::min(d->chunk_bytes, (size_t)0xf0000000u);      // block offsets inside a chunk are 32 bits wide
     d->chunk_blocks = (size_t)ctx->sm_count * inflate_warps_per_sm() * 32;
+    if (o->n_threads > 0) d->read_threads = std::min(o->n_threads, 64);
     d->fd = open(path, O_RDONLY);
     if (d->fd < 0) { dyn_set_error("dyn_bam_dev_open: cannot open %s", path); return DYN_ERR_IO; }
     {
@@ -727,7 +763,7 @@ extern "C" int dyn_bam_dev_open(dyn_ctx_t *ctx, const char *path, const dyn_bam_
     if (!d->buf->h_small) DYN_CUDA(cudaHostAlloc((void **)&d->buf->h_small, 256, cudaHostAllocDefault));
     for (cudaEvent_t &e : d->buf->ev_copy) if (!e) DYN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if ((rc = d->buf->d_small.ensure(256))) return rc;
-    for (Staged &s : d->buf->staged) d->free_list.push_back(&s);
+    for (Staged &s : d->buf->staged) { s.dev_slot = -1; d->free_list.push_back(&s); }
     dyn_bam_dev *dp = d.release();
     dp->reader = std::thread(read_ahead, dp);
     *out = dp;

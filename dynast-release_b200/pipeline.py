@@ -620,7 +620,7 @@ def tally_bam(ctx: Context, path: str, gene_ids, barcode_tag: Optional[str] = 'C
 
     def run_device():
         nonlocal seen, units, compressed, inflated
-        with bamio.DeviceBamStream(ctx, path, lean=True, gene_ids=list(gene_ids), **kw) as st:
+        with bamio.DeviceBamStream(ctx, path, lean=True, gene_ids=list(gene_ids), n_threads=n_threads, **kw) as st:
             for ch in st:
                 seen += ch['n_records_seen']; compressed += ch['compressed_bytes']; inflated += ch['inflated_bytes']
                 n = ch['n_units']

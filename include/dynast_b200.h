@@ -485,7 +485,8 @@ const void *dyn_bam_stream_field(const dyn_bam_stream_t *stream, int field, int6
  * inflates it, one thread per alignment record filters / tokenises / packs it; only the compressed bytes cross PCIe.
  * Takes coordinate-sorted single-end BAMs whose BGZF blocks end on record boundaries (htslib / samtools / STAR write
  * them so); anything else is refused with DYN_ERR_FORMAT and belongs to dyn_bam_stream_*.  Options as for
- * dyn_bam_stream_open (keys are always produced, n_threads is ignored, gene_ids gives the gene index).
+ * dyn_bam_stream_open (keys are always produced, n_threads = host threads that read the file into page-locked memory, 0 = 16;
+ * gene_ids gives the gene index).
  * dyn_bam_dev_next fills *chunk with DEVICE pointers to one chunk's units -- packed records, offsets (n_units + 1),
  * keys as in dyn_bam_stream chunks (fields 11-13), AS, reference id, position, HI, flag, gene-tag-present -- valid until
  * the second-next call; chunk->end is 1 on the last chunk of the range and 2 (nothing else set) on calls past it.  The call runs on `stream` and

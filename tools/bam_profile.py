@@ -12,7 +12,7 @@ path = '/dev/shm/dyn_prof.bam'
 gen = pipeline.SynthBatch(n, seed=2002, device=0, lean=False)
 info = synth.write_synth_bam(path, gen, level=1, n_threads=os.cpu_count())
 strand = gen.tables['gene_strand'].cpu().numpy(); del gen; torch.cuda.empty_cache()
-kw = dict(barcode_tag='CB', umi_tag='UB', gene_tag='GX', require_gene=True)
+kw = dict(barcode_tag='CB', umi_tag='UB', gene_tag='GX', require_gene=True, n_threads=16)
 for rep in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     with bamio.DeviceBamStream(ctx, path, lean=True, gene_ids=info['gene_ids'], **kw) as st:
