@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument('--bam-max-total', type=int, default=48_000_000, help='cap of the BAM leg\'s file over all GPUs (records)')
     ap.add_argument('--skip-bam', action='store_true')
     ap.add_argument('--skip-other-layout', action='store_true')
+    ap.add_argument('--skip-pi-g', action='store_true')
     ap.add_argument('--bam-reads', type=int, default=16_000_000, help='records per GPU of the synthetic BAM of the from-file leg')
     ap.add_argument('--bam-level', type=int, default=1, help='zlib level of that BAM (STAR writes level 1, samtools sort level 6)')
     ap.add_argument('--full-records', action='store_true',
@@ -530,6 +531,26 @@ def main():
                 'exchange': (exchange_transport(ctx) if xchg else None),
                 'note': 'includes the host round trips of the dedup split plan and the EM / pi shape discovery'}
         del res
+        # estimate(method='pi_g'): one fit per (cell, gene) pair with >= 16 reads, batched on the device (pi.py:253-296 runs one
+        # Stan optimisation per pair in a process pool)
+        if world == 1 and not args.skip_pi_g:
+            def run_pi_g(t=None):
+                return pipeline.count_to_estimate(ctx, batch.records, batch.rec_off, p_bc, batch.umi, batch.gene, batch.score, batch.strand,
+                                                  p_nb, batch.n_genes, out, timings=t, method='pi_g', cell_gene_threshold=16)
+            run_pi_g()
+            barrier()
+            tg = {}
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            rg = run_pi_g(tg)
+            g1.record(stream)
+            barrier()
+            fitted = int((rg['pi_g_status'] >= 0).sum().item())
+            pipe['pi_g'] = {'metric': '(cell, gene) pairs/s, labeled-fraction fit per pair (estimate method pi_g)', 'pairs': int(rg['pi_g_pair'].numel()),
+                            'pairs_fitted': fitted, 'pairs_ok': int((rg['pi_g_status'] == 0).sum().item()), 'ms_pi_g_stage': tg.get('pi_g'),
+                            'value': fitted / (tg['pi_g'] * 1e-3) if tg.get('pi_g') else None, 'unit': 'pairs/s', 'ms_whole_path': g0.elapsed_time(g1),
+                            'threshold': 'pairs with at least 16 reads of barcodes whose p_c was estimated'}
+            del rg
 
     # ---------------------------------------------------------------- C5 (behind --c5): dual labelling, 1 M barcodes over 8 GPUs
     c5 = None

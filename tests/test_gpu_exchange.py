@@ -106,13 +106,19 @@ def _run(rank, world, port, n_reads, n_barcodes, out_dir):
     rec = b.records[int(off[0]) * 16:int(off[-1]) * 16]
     rec_off = (off - off[0]).to(torch.int32)
     out = pipeline.TallyBuffers(hi - lo, 4 * (hi - lo) + 1024, device=rank)
+    if world > 1:       # a small exchange first: the peer buffers of the real one then have to GROW (collectively)
+        z = lambda n, dt: torch.zeros(n, dtype=dt, device=rank)
+        small = distributed.exchange_reads(ctx, b.barcode[lo:lo + 500], b.umi[lo:lo + 500], b.gene[lo:lo + 500], z(500, torch.int16), z(500, torch.int16),
+                                           b.strand[lo:lo + 500], torch.zeros((500, 16), dtype=torch.uint8, device=rank), world, mode='push')
+        assert int((small['barcode'] % world == rank).all()) == 1
+        cap_small = distributed.PeerExchange.get(ctx, None).capacity
     res = pipeline.count_to_estimate(ctx, rec, rec_off, b.barcode[lo:hi], b.umi[lo:hi], b.gene[lo:hi], b.score[lo:hi],
                                      b.strand[lo:hi], n_barcodes, b.n_genes, out, cell_threshold=50, with_pi=False,
                                      exchange=world > 1)
     k, n, c, off_h = res['hist']
     if world > 1:       # the fused peer-store exchange ran (not the all-to-all fall-back), and both transports agree row for row
         px = distributed.PeerExchange.get(ctx, None)
-        assert px.usable and px.capacity > 0, 'peer memory exchange not in use'
+        assert px.usable and px.capacity > cap_small > 0, 'peer memory exchange not in use, or its buffers did not grow'
         sc = b.score[lo:hi].to(torch.int16)
         args = (ctx, b.barcode[lo:hi], b.umi[lo:hi], b.gene[lo:hi], sc, out.conv_n, b.strand[lo:hi], out.counts, world)
         via_push = distributed.exchange_reads(*args, mode='push')
