@@ -640,6 +640,10 @@ def main():
             st = {}
             r, dt = bam_run('auto', st)
             runs.append(dt)
+            if os.environ.get('DYN_BENCH_DEBUG'):
+                ms_ = torch.cuda.memory_stats()
+                sys.stderr.write('bam rep %.3f s: device_alloc %d device_free %d reserved %.1f GB\n' % (
+                    dt, ms_.get('num_device_alloc', -1), ms_.get('num_device_free', -1), ms_.get('reserved_bytes.all.current', 0) / 1e9))
         dt = float(np.median(runs))
         tallied = torch.tensor([r['n_reads_tallied'], int(r['selected'].numel()), int((r['em_status'] == 0).sum().item())], device=device)
         if dist is not None:

@@ -703,25 +703,35 @@ def count_from_bam(ctx: Context, path: str, gene_ids, gene_strand, conversions=(
         raise ValueError('malformed alignment record (CIGAR / MD / sequence disagree)')
     if t['gene_idx'].numel() and int(t['gene_idx'].min().item()) < 0:
         raise KeyError('a read carries no gene tag or one that is not in gene_ids (KeyError in complement_counts, conversion.py:116)')
-    bc_keys = torch.unique(t['barcode_key'])
-    if world > 1:       # one global, sorted barcode table: dense ids agree on every rank (owner = id % world)
+    def global_unique(keys):
+        """Sorted distinct values of `keys` over all ranks: dense ids (searchsorted) then agree on every rank."""
+        u = torch.unique(keys)
+        if world == 1:
+            return u
         import torch.distributed as dist
-        n_max = torch.tensor([bc_keys.numel()], dtype=torch.int64, device=dev)
+        n_max = torch.tensor([u.numel()], dtype=torch.int64, device=dev)
         dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=group)
-        pad = torch.full((int(n_max.item()),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
-        pad[:bc_keys.numel()] = bc_keys
+        sentinel = torch.iinfo(torch.int64).max
+        pad = torch.full((int(n_max.item()),), sentinel, dtype=torch.int64, device=dev)
+        pad[:u.numel()] = u
         every = torch.empty(world * pad.numel(), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(every, pad, group=group)
-        bc_keys = torch.unique(every)
-        bc_keys = bc_keys[bc_keys != torch.iinfo(torch.int64).max]
+        u = torch.unique(every)
+        return u[u != sentinel]
+
+    bc_keys = global_unique(t['barcode_key'])       # owner of a barcode = its dense id % world
     barcode = torch.searchsorted(bc_keys, t['barcode_key']).to(torch.int32)
     n_barcodes = int(bc_keys.numel())
     umi = t['umi_key']
-    umi_bits = max(1, int(umi.max().item()).bit_length()) if umi.numel() else 1
+    umi_max = umi.max().reshape(1) if umi.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
+    if world > 1:       # the group key is packed on the OWNER's side of the exchange: every rank must use the same widths
+        import torch.distributed as dist
+        dist.all_reduce(umi_max, op=dist.ReduceOp.MAX, group=group)
+    umi_bits = max(1, int(umi_max.item()).bit_length())
     gene_bits, bc_bits = _bits(max(len(gene_ids) - 1, 0)), _bits(max(n_barcodes - 1, 0))
     if umi_bits + gene_bits + bc_bits > 64:      # long UMIs: dense ids instead of the 2-bit value
-        u, inv = torch.unique(umi, return_inverse=True)
-        umi, umi_bits = inv.to(torch.int64), _bits(max(int(u.numel()) - 1, 0))
+        u = global_unique(umi)
+        umi, umi_bits = torch.searchsorted(u, umi).to(torch.int64), _bits(max(int(u.numel()) - 1, 0))
     strand_table = torch.as_tensor(np.ascontiguousarray(gene_strand, dtype=np.uint8), device=dev)
     strand = strand_table[t['gene_idx'].long()]
     res = count_to_estimate(ctx, None, None, barcode, umi, t['gene_idx'], t['score'], strand, n_barcodes, len(gene_ids), None,

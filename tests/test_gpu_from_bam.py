@@ -75,3 +75,57 @@ def test_count_from_bam_auto_falls_back_to_the_host_reader(gpu_ctx, tmp_path):
     assert torch.equal(t['counts'], h['counts']) and torch.equal(t['barcode_key'], h['barcode_key'])
     with pytest.raises(Exception, match='straddle'):
         pipeline.tally_bam(gpu_ctx, out, genes, ingest='device')
+
+
+def _bam_rank(rank, world, port, path, gene_ids, strand, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import conftest  # noqa: F401  (package alias)
+    import torch.distributed as dist
+    from dynast_b200 import pipeline
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    ctx = pipeline.Context.get(rank)
+    stats = {}
+    got = pipeline.count_from_bam(ctx, path, gene_ids, strand, cell_threshold=200, with_pi=False, group=dist.group.WORLD, chunk_bytes=8 << 20,
+                                  n_threads=2, stats=stats)
+    torch.cuda.synchronize()
+    k, n, c, off = (x.cpu().numpy() for x in got['hist'])
+    np.savez(os.path.join(out_dir, f'bam_r{rank}.npz'), keys=got['barcode_keys'].cpu().numpy(), n_reads=got['n_reads'].cpu().numpy(),
+             p_e=got['p_e'].cpu().numpy(), p_c=got['p_c'].cpu().numpy(), st=got['em_status'].cpu().numpy(), n_sel=int(got['selected'].numel()),
+             units=stats['units'], k=k, n=n, c=c, off=off)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_one_bam_on_two_gpus_equals_one_gpu(synth_bam, tmp_path):
+    """Two ranks take the two block ranges of ONE file (device ingest), intern barcodes globally, exchange every read's row to
+    the barcode's owner and run the rest of the path on the barcodes they own: per barcode the same reads, p_e, histograms
+    and p_c as one GPU over the whole file, bit for bit."""
+    import torch.multiprocessing as mp
+    from dynast_b200 import bamio, synth
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_bam_rank, args=(2, port, synth_bam['path'], synth_bam['info']['gene_ids'], synth_bam['strand'], str(tmp_path)), nprocs=2, join=True)
+    parts = [np.load(tmp_path / f'bam_r{r}.npz') for r in range(2)]
+    want = synth_bam['want']
+    assert sum(int(p['units']) for p in parts) == synth_bam['n']
+    assert sum(int(p['n_sel']) for p in parts) == int(want['selected'].numel())
+    assert np.array_equal(parts[0]['keys'], parts[1]['keys'])                      # one global barcode table
+    keys = [bamio.decode_key(k) for k in parts[0]['keys']]
+    names = [bytes(r).decode() for r in synth.barcode_strings(np.arange(60))]
+    w = {name: want[name].cpu().numpy() for name in ('n_reads', 'p_e', 'p_c', 'em_status')}
+    k, n, c, off = (x.cpu().numpy() for x in want['hist'])
+    checked = 0
+    for b, nm in enumerate(names):
+        g = keys.index(nm)                     # global dense id: owner g % 2, local id g // 2
+        p, j = parts[g % 2], g // 2
+        assert w['n_reads'][b] == p['n_reads'][j] and w['em_status'][b] == p['st'][j]
+        assert w['p_e'][b] == p['p_e'][j] or (np.isnan(w['p_e'][b]) and np.isnan(p['p_e'][j]))
+        assert np.array_equal(k[off[b]:off[b + 1]], p['k'][p['off'][j]:p['off'][j + 1]])
+        assert np.array_equal(c[off[b]:off[b + 1]], p['c'][p['off'][j]:p['off'][j + 1]])
+        if w['em_status'][b] == 0:
+            assert w['p_c'][b] == p['p_c'][j]
+            checked += 1
+    assert checked > 20
