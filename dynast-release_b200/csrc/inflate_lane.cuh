@@ -31,11 +31,24 @@
 namespace dinflate {
 namespace lane {
 
-constexpr int kLitBits = 9, kDistBits = 7, kCopy = 8;
-constexpr int kLitLut = 0, kDistLut = 512, kLitSorted = 640, kDistSorted = 928, kLitCount = 960, kDistCount = 976, kUnits = 992;
+#ifndef DYN_INF_LIT_BITS
+#define DYN_INF_LIT_BITS 9
+#endif
+#ifndef DYN_INF_DIST_BITS
+#define DYN_INF_DIST_BITS 7
+#endif
+constexpr int kLitBits = DYN_INF_LIT_BITS, kDistBits = DYN_INF_DIST_BITS, kCopy = 8;
+static_assert(kLitBits >= 6 && kLitBits <= 12 && kDistBits >= 5 && kDistBits <= 10, "lookup widths");
+constexpr int kLitLut = 0, kDistLut = 1 << kLitBits, kLitSorted = kDistLut + (1 << kDistBits), kDistSorted = kLitSorted + 288,
+              kLitCount = kDistSorted + 32, kDistCount = kLitCount + 16, kUnits = kDistCount + 16;
 // where the canonical walk stands after the lookup width: `index` in count[0] (symbols without a code: nothing else reads
 // it), `first` here -- [0] literal / length code, [1] distance code, [2] code-length code
-constexpr int kWalkFirst = 992, kUnitsAll = 996;
+constexpr int kWalkFirst = kUnits;
+// While a dynamic header is read, its 320 code lengths and the 7-bit lookup of the code-length code need a home: inside the
+// two lookup tables when those are wide enough (they are built afterwards), else in a scratch region of their own
+constexpr bool kOverlay = kLitBits >= 9 && kDistBits >= 7;
+constexpr int kLens = kOverlay ? kLitLut : kWalkFirst + 4, kClLut = kOverlay ? kDistLut : kLens + 320;
+constexpr int kUnitsAll = kOverlay ? kWalkFirst + 4 : kClLut + 128;
 
 template <int STRIDE>
 struct Mem {
@@ -212,7 +225,7 @@ INF_HD void header(Lane &s, const Mem<STRIDE> &m) {
     }
     if (type == 3) return fail(s, ERR_DATA);
     int n_lit = 288, n_dist = 30;
-    const int lens = kLitLut;                          // 288 literal / length + 32 distance code lengths
+    const int lens = kLens;                            // 288 literal / length + 32 distance code lengths
     if (type == 1) {
         for (int i = 0; i < 288; ++i) m.set(lens + i, i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
         for (int i = 0; i < 32; ++i) m.set(lens + 288 + i, i < 30 ? 5 : 0);
@@ -224,13 +237,13 @@ INF_HD void header(Lane &s, const Mem<STRIDE> &m) {
         const int cl = kLitSorted;                     // 19 lengths of the code-length code, staged where nothing lives yet
         for (int i = 0; i < 19; ++i) m.set(cl + i, 0);
         for (int i = 0; i < n_code; ++i) { refill(s); m.set(cl + INF_K(cl_order)[i], take(s, 3)); }
-        if (!build(m, cl, 19, kDistLut, 7, kDistCount, kDistSorted, kWalkFirst + 2)) return fail(s, ERR_DATA);
+        if (!build(m, cl, 19, kClLut, 7, kDistCount, kDistSorted, kWalkFirst + 2)) return fail(s, ERR_DATA);
         int i = 0;
         uint32_t prev = 0;
         const int n_all = n_lit + n_dist;
         while (i < n_all) {
             refill(s);
-            const int sym = decode_sym(s, m, kDistLut, 7, kDistCount, kDistSorted, kWalkFirst + 2);
+            const int sym = decode_sym(s, m, kClLut, 7, kDistCount, kDistSorted, kWalkFirst + 2);
             if (sym < 0 || sym > 18 || overrun(s)) return fail(s, ERR_DATA);
             if (sym < 16) { prev = (uint32_t)sym; m.set(lens + (i < n_lit ? i : 288 + (i - n_lit)), prev); ++i; continue; }
             int rep;

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope='module')
 def shim(tmp_path_factory):
     out = str(tmp_path_factory.mktemp('native') / 'ingest_host.so')
-    subprocess.run(['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-o', out, os.path.join(ROOT, 'tests', 'native', 'ingest_host.cpp')],
+    subprocess.run(['g++', '-O1', '-std=c++17'] + os.environ.get('DYN_TEST_CXXFLAGS', '').split() + [ '-shared', '-fPIC', '-o', out, os.path.join(ROOT, 'tests', 'native', 'ingest_host.cpp')],
                    check=True)
     lib = C.CDLL(out)
     lib.host_inflate.restype = C.c_int
