@@ -53,13 +53,14 @@ constexpr int kInfWarps = 4;          // warps per CTA of the inflate kernel (on
 struct BlockDesc { uint32_t in_off, in_len, out_off, out_len; };
 
 #ifndef DYN_INF_QUORUM
-#define DYN_INF_QUORUM 1        // lanes that must be waiting at a block header before the header path is taken ...
+#define DYN_INF_QUORUM 8        // lanes that must be waiting at a block header before the header path is taken ...
 #endif
 #ifndef DYN_INF_ROUNDS
-#define DYN_INF_ROUNDS 4         // Huffman codes per lane between two looks at the lanes' states
+#define DYN_INF_ROUNDS 8         // Huffman codes per lane between two looks at the lanes' states
 #endif
 #ifndef DYN_INF_WAIT
-#define DYN_INF_WAIT 0          // ... unless one of them has waited this many rounds, or no lane is decoding
+#define DYN_INF_WAIT 32         // ... unless one of them has waited this many trips, or no lane is decoding (measured: 38-41 ->
+                                // 33-36 ms per chunk against taking every header at once; 16 / 24 lanes or longer waits: no better)
 #endif
 
 // Pass 1 -- one LANE per BGZF block (inflate_lane.cuh): one-warp CTAs, each lane pulls blocks off the work counter and
