@@ -1,7 +1,7 @@
 #!/bin/bash
 timeout 600 python -m pytest tests/test_gpu_exchange.py -x -q -rs 2>&1 | tail -4 > gpurun_out/r2_2gpu_test.log; cat gpurun_out/r2_2gpu_test.log
 N=${1:-2}
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N $2 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err
 tail -3 gpurun_out/r2_bench_${N}gpu.err
 python - <<PY
 import json
@@ -11,5 +11,5 @@ print('value %.3e' % j['value'], 'e2e', j['e2e'] and j['e2e'].get('value'), 'bit
 print('e2e_bam', j['e2e_bam'] and {k: j['e2e_bam'].get(k) for k in ('value', 's', 'rep_s', 'ingest', 'sharding', 'records')})
 print('pipeline', j['pipeline'] and (j['pipeline']['ms'], j['pipeline']['stage_ms'], j['pipeline']['exchange']))
 print('em', j['em'] and (j['em']['value'], j['em']['ms']))
-print('cons', j['consensus'] and (j['consensus']['value'], j['consensus']['c3_value']))
+print('cons', j['consensus'] and (j['consensus']['value'], j['consensus']['c3_value'])); print('c5', j.get('c5'))
 PY
