@@ -2,15 +2,16 @@
 // host ingest's ceiling calls for: zlib on the host cores tops out near 1.5e7 records/s per box, two orders of
 // magnitude below what the tally takes from HBM).
 //
-// Replaces, for coordinate-sorted single-end BAMs whose BGZF blocks end on record boundaries (what htslib, samtools
-// and STAR write), everything the reference gets from pysam / htslib between the file and the per-read loop of
+// Replaces, for coordinate-sorted single-end BAMs (BGZF blocks that end on record boundaries, as htslib writes them, or
+// anywhere, as STAR's sorted BAMs do), everything the reference gets from pysam / htslib between the file and the per-read loop of
 // dynast/preprocessing/bam.py:253-312:
 //   host    a reader thread copies the COMPRESSED bytes of the next run of BGZF blocks into page-locked staging
 //           memory and lists the blocks (BSIZE / ISIZE hops, no inflate); cudaMemcpyAsync moves them -- PCIe carries
 //           ~90 B per record instead of the ~280 B of the inflated stream;
 //   k1      inflate_kernel: ONE WARP PER BGZF BLOCK (inflate_core.cuh: lane 0 decodes Huffman symbols through
 //           shared-memory lookup tables, the warp writes literals lane-parallel and copies matches cooperatively);
-//   k2      index kernels: one thread per block walks its record chain (count, then positions after a scan);
+//   k2      chain kernels: one thread per block finds the first record that starts in it, walks its records (count, then
+//           positions after a scan); where one block's walk ends the next one's must begin (checked);
 //   k3      parse_kernel: one thread per record -- read filter, aux-tag scan (MD / HI / AS / barcode / UMI / gene),
 //           2-bit barcode / UMI keys, FNV hash of the gene id, packed size;
 //   scan    unit index and record offset of every kept record (one cub::DeviceScan over count << 40 | size);
@@ -18,8 +19,8 @@
 //           Phred folded in for the lean layout, 4-bit sequence) and the unit's keys; the gene id's hash is looked
 //           up in the sorted table of the caller's gene list.
 // The chunk that comes out is what dyn_bam_stream_next returns with keys = 1, but resident in HBM: the tally, the
-// velocity kernel and everything downstream read it where it lies.  Files this path does not take (paired records,
-// records straddling blocks) are reported with DYN_ERR_FORMAT; callers fall back to dyn_bam_stream_*.
+// velocity kernel and everything downstream read it where it lies.  Files this path does not take (paired records)
+// are reported with DYN_ERR_FORMAT; callers fall back to dyn_bam_stream_*.
 #include <cub/cub.cuh>
 #include <fcntl.h>
 #include <zlib.h>
@@ -270,29 +271,101 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_kernel(const uint8_t *
     }
 }
 
-// ---- record chain: one thread per block.  pass 0: count the records that start in the block and check that the
-// chain ends exactly at the block's end; pass 1: write their offsets.
-__global__ void index_kernel(const uint8_t *data, const BlockDesc *blocks, int n_blocks, uint32_t first_skip, uint32_t *n_rec,
-                             const uint32_t *rec_base, uint32_t *rec_at, uint32_t *status) {
+// ---- record chain.  A chunk's inflated bytes form ONE stream S = [bytes carried over from the chunk before | block 0 |
+// block 1 | ...]; htslib ends BGZF blocks on record boundaries, STAR's sorted BAMs do not (bgzf_write per record, no flush),
+// so a record may start in one block and end blocks later -- or in the next chunk.
+//   chain_start_kernel  one thread per block: the offset (in S) of the first record that STARTS in the block.  Block 0
+//                       knows it (the stream begins at a record; first_skip at the start of a range); the others try their
+//                       own first byte, then scan: a start is believed when four plausible records follow one another.
+//   chain_walk_kernel   pass 0: walks the records that start in the block, counts them, leaves the offset where the next
+//                       block's records begin; pass 1: writes the offsets.
+//   chain_check_kernel  induction: where block b's walk ended is where the next block that has a start said it starts --
+//                       so every guess is either the true chain or reported (status bit 8: the host reader takes the file).
+//                       The last block's end is the start of the bytes to carry into the next chunk.
+// Records that start at or after `limit` (blocks read beyond the end of a range to complete its last record) are not counted.
+constexpr uint32_t kNoStart = 0xffffffffu;
+constexpr uint32_t kCarryRoom = 1u << 20;      // head room in front of a chunk's blocks for the bytes carried over
+
+__device__ __forceinline__ bool plausible_record(const uint8_t *p, unsigned long long avail, int n_ref, uint32_t *size) {
+    if (avail < 36) return false;
+    const uint32_t bs = bamrec::ld32(p);
+    if (bs < 32 || bs > (1u << 26)) return false;
+    const int32_t ref = (int32_t)bamrec::ld32(p + 4), pos = (int32_t)bamrec::ld32(p + 8), next_ref = (int32_t)bamrec::ld32(p + 24),
+                  next_pos = (int32_t)bamrec::ld32(p + 28);
+    if (ref < -1 || ref >= n_ref || pos < -1 || next_ref < -1 || next_ref >= n_ref || next_pos < -1) return false;
+    const uint32_t l_name = p[12], n_cigar = bamrec::ld16(p + 16), l_seq = bamrec::ld32(p + 20);
+    if (l_name < 1 || l_seq > (1u << 26)) return false;
+    const unsigned long long fixed = 32ull + l_name + 4ull * n_cigar + ((unsigned long long)l_seq + 1) / 2 + l_seq;
+    if (fixed > bs) return false;
+    if (36ull + l_name <= avail && p[36 + l_name - 1] != 0) return false;
+    *size = 4 + bs;
+    return true;
+}
+
+__global__ void chain_start_kernel(const uint8_t *S, uint32_t carry_len, uint32_t stream_len, const BlockDesc *blocks, int n_blocks, uint32_t s0,
+                                   int n_ref, uint32_t *start) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
-    const BlockDesc bd = blocks[b];
-    const uint8_t *p = data + bd.out_off;
-    uint32_t q = b == 0 ? first_skip : 0u, n = 0;
+    const uint32_t lo = carry_len + blocks[b].out_off, hi = lo + blocks[b].out_len;
+    if (b == 0) { start[0] = s0 < hi ? s0 : kNoStart; return; }
+    uint32_t found = kNoStart;
+    for (uint32_t o = lo; o < hi && found == kNoStart; ++o) {
+        uint32_t q = o;
+        int ok = 0;
+        bool good = true;
+        while (ok < 4) {
+            uint32_t size = 0;
+            if (q >= stream_len || stream_len - q < 36) { good = ok >= 1; break; }       // ran into the end of the stream
+            if (!plausible_record(S + q, stream_len - q, n_ref, &size)) { good = false; break; }
+            ++ok;
+            if ((unsigned long long)q + size >= stream_len) break;
+            q += size;
+        }
+        if (good && ok >= 1) found = o;
+    }
+    start[b] = found;
+}
+
+__global__ void chain_walk_kernel(const uint8_t *S, uint32_t carry_len, uint32_t stream_len, uint32_t limit, const BlockDesc *blocks, int n_blocks,
+                                  const uint32_t *start, uint32_t *n_rec, uint32_t *end, const uint32_t *rec_base, uint32_t *rec_at, uint32_t *status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint32_t lo = carry_len + blocks[b].out_off;
+    uint32_t hi = lo + blocks[b].out_len;
+    if (hi > limit) hi = limit;
+    uint32_t q = start[b], n = 0;
     uint32_t *dst = rec_at ? rec_at + rec_base[b] : nullptr;
-    bool paired = false;
-    while (q + 4 <= bd.out_len) {
-        const uint32_t bs = bamrec::ld32(p + q);
-        if (bs < 32 || q + 4 + bs > bd.out_len) break;
-        paired |= (bamrec::ld16(p + q + 4 + 14) & 0x1) != 0;
-        if (dst) dst[n] = bd.out_off + q;
-        ++n;
-        q += 4 + bs;
+    bool paired = false, bad = false;
+    if (q != kNoStart) {
+        while (q < hi) {
+            if (stream_len - q < 4) break;                                  // the size field itself is cut: carried over
+            const uint32_t bs = bamrec::ld32(S + q);
+            if (bs < 32) { bad = true; break; }
+            if ((unsigned long long)q + 4 + bs > stream_len) break;         // incomplete: carried over
+            paired |= (bamrec::ld16(S + q + 4 + 14) & 0x1) != 0;
+            if (dst) dst[n] = q;
+            ++n;
+            q += 4 + bs;
+        }
     }
     if (!dst) {
         n_rec[b] = n;
-        if (q != bd.out_len) atomicOr(status, 1u << 8);       // a record straddles BGZF blocks
+        end[b] = q;
+        if (bad) atomicOr(status, 1u << 16);
         if (paired) atomicOr(status, 1u << 9);                // paired records: mate pairing is the host path's
+    }
+}
+
+__global__ void chain_check_kernel(const uint32_t *start, const uint32_t *end, int n_blocks, uint32_t limit, uint32_t *carry_start, uint32_t *status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks || start[b] == kNoStart) return;
+    int nb = b + 1;
+    while (nb < n_blocks && start[nb] == kNoStart) ++nb;
+    if (nb < n_blocks) {
+        // a walk that stopped at the limit (or on an incomplete record) has nothing to hand on
+        if (end[b] < limit && end[b] != start[nb]) atomicOr(status, 1u << 8);
+    } else {
+        *carry_start = end[b];              // the last block in which a record starts
     }
 }
 
@@ -369,6 +442,7 @@ struct Staged {          // one run of BGZF blocks, compressed, in page-locked m
     std::vector<BlockDesc> blocks;
     size_t inflated = 0;
     uint32_t first_skip = 0;
+    int n_extra = 0;         // trailing blocks that lie BEHIND the range: read so that the range's last record is whole
     bool last = false;
     int dev_slot = -1;       // >= 0: the compressed bytes are (being) copied to device buffer pair `dev_slot`
 };
@@ -380,7 +454,7 @@ struct IngestBuffers {
     Staged staged[3];
     DevBuf d_comp[2], d_blocks[2];        // double buffered: chunk i + 1 is copied while chunk i is inflated
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-    DevBuf d_inflated, d_tokens, d_ntok, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
+    DevBuf d_inflated, d_carry, d_start, d_end, d_tokens, d_ntok, d_nrec, d_recbase, d_recat, d_parsed, d_scan_in, d_scan, d_tmp, d_small;
     struct OutSet { DevBuf blob, rec_off, bc, umi, gene, score, ref_id, pos, hi, flag, gxa; } out[2];
     uint32_t *h_small = nullptr;          // page-locked landing zone
     ~IngestBuffers() {
@@ -426,6 +500,7 @@ struct dyn_bam_dev {
     std::string err_msg;
     IngestBuffers *buf = nullptr;         // shared intermediates + two sets of outputs + staging
     int cur = 0, copy_slot = 0;
+    uint32_t carry_len = 0;                // bytes of an unfinished record carried from the previous chunk (in d_carry)
     bool slot_busy[2] = {false, false};    // (under mu) the device buffer pair holds a slab that is not inflated yet
     int64_t records_seen = 0;
 
@@ -495,7 +570,8 @@ void read_ahead(dyn_bam_dev *d) {
             block_cap = std::min(block_cap, (size_t)std::ceil(est_blocks / n_chunks * 1.02) + 8);
         }
         const size_t inflated_cap = block_cap ? std::min(d->chunk_bytes, block_cap * (size_t)65536) : d->chunk_bytes;
-        const size_t want = std::min(d->file_len - d->pos, (size_t)((double)inflated_cap * d->ratio * 1.05) + (1u << 20));
+        size_t want = std::min(d->file_len - d->pos, (size_t)((double)inflated_cap * d->ratio * 1.05) + (1u << 20));
+        if (d->pos + want >= d->end) want = std::min(d->file_len - d->pos, std::max(want, d->end - d->pos + 3 * (size_t)65536));    // + the blocks behind the range
         bool ok = true;
         if (s->cap < want) {
             if (s->bytes) cudaFreeHost(s->bytes);
@@ -548,11 +624,28 @@ void read_ahead(dyn_bam_dev *d) {
             q += blen;
         }
         if (ok && !corrupt && s->blocks.empty()) corrupt = true;        // not even one whole block in a slab of > 1 MiB
+        const size_t q_range = q;
+        s->n_extra = 0;
+        if (ok && !corrupt && d->pos + q >= d->end) {
+            // the range ends here: its last record may end in the blocks behind it (BGZF blocks need not end on record
+            // boundaries) -- two more blocks come along; no record that STARTS in them is taken
+            while (s->n_extra < 2 && d->pos + q < d->file_len) {
+                size_t blen = 0;
+                if (want - q < 18 || !bgzf_header(s->bytes + q, want - q, &blen) || q + blen > want) break;
+                const uint32_t xlen = bamrec::ld16(s->bytes + q + 10);
+                const uint32_t isize = bamrec::ld32(s->bytes + q + blen - 4);
+                if (isize == 0) break;                                      // the end-of-file marker
+                s->blocks.push_back(BlockDesc{(uint32_t)(q + 12 + xlen), (uint32_t)(blen - 12 - xlen - 8), (uint32_t)s->inflated, isize});
+                s->inflated += isize;
+                q += blen;
+                ++s->n_extra;
+            }
+        }
         s->len = q;
         if (s->inflated) d->ratio = std::max(0.05, std::min(1.2, (double)q / (double)s->inflated));
         s->first_skip = d->first_chunk ? d->first_skip : 0;
         d->first_chunk = false;
-        d->pos += q;
+        d->pos += q_range;
         s->last = d->pos >= d->end;
         std::lock_guard<std::mutex> l(d->mu);
         if (!ok || corrupt) {
@@ -882,7 +975,17 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
         d->copy_slot ^= 1;
     }
     const int slot = s->dev_slot;
-    if ((rc = B.d_inflated.ensure(s->inflated + 16))) return rc;
+    // the chunk's stream S: [carried bytes | block 0 | block 1 | ...], the blocks inflated behind kCarryRoom bytes of head room
+    const uint32_t carry_len = d->carry_len;
+    if ((rc = B.d_inflated.ensure(kCarryRoom + s->inflated + 16))) return rc;
+    if ((rc = B.d_carry.ensure(kCarryRoom))) return rc;
+    if ((rc = B.d_start.ensure(4 * (size_t)(nb + 1))) || (rc = B.d_end.ensure(4 * (size_t)(nb + 1)))) return rc;
+    uint8_t *const inflated_at = B.d_inflated.as<uint8_t>() + kCarryRoom;
+    const uint8_t *const S = inflated_at - carry_len;
+    if ((size_t)carry_len + s->inflated > 0xfffffff0ull) { dyn_set_error("dyn_bam_dev: chunk over 4 GiB"); return DYN_ERR_NOMEM; }
+    const uint32_t stream_len = carry_len + (uint32_t)s->inflated;
+    const uint32_t limit = s->n_extra > 0 ? carry_len + s->blocks[(size_t)(nb - s->n_extra)].out_off : stream_len;
+    const uint32_t s0 = carry_len ? 0u : s->first_skip;
     if ((rc = B.d_nrec.ensure(4 * (size_t)(nb + 1)))) return rc;
     if ((rc = B.d_recbase.ensure(4 * (size_t)(nb + 1)))) return rc;
     uint32_t *d_small = B.d_small.as<uint32_t>();      // [0] inflate work counter, [1] status, [2..3] scan totals
@@ -896,14 +999,20 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     {
         if ((rc = B.d_tokens.ensure(4 * (s->inflated + 16)))) return rc;
         if ((rc = B.d_ntok.ensure(4 * (size_t)(nb + 1)))) return rc;
-        if ((rc = launch_inflate(d->ctx, B.d_comp[slot].as<uint8_t>(), B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb,
+        if ((rc = launch_inflate(d->ctx, B.d_comp[slot].as<uint8_t>(), inflated_at, B.d_blocks[slot].as<BlockDesc>(), nb,
                                  B.d_tokens.as<uint32_t>(), B.d_ntok.as<uint32_t>(), d_small, d_small + 1, stream)))
             return rc;
     }
     if (timing) cudaEventRecord(tev[2], stream);
-    // ---- k2: records per block, their prefix sum, the total
-    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb, s->first_skip,
-                                                       B.d_nrec.as<uint32_t>(), nullptr, nullptr, d_small + 1);
+    // ---- k2: where the records start (per block, checked by induction), how many start in each block, their prefix sum
+    if (carry_len) DYN_CUDA(cudaMemcpyAsync(inflated_at - carry_len, B.d_carry.p, carry_len, cudaMemcpyDeviceToDevice, stream));
+    const int n_ref = (int)d->ref_len.size();
+    B.h_small[8] = kNoStart;
+    DYN_CUDA(cudaMemcpyAsync(d_small + 5, B.h_small + 8, 4, cudaMemcpyHostToDevice, stream));
+    chain_start_kernel<<<(nb + 63) / 64, 64, 0, stream>>>(S, carry_len, stream_len, B.d_blocks[slot].as<BlockDesc>(), nb, s0, n_ref, B.d_start.as<uint32_t>());
+    chain_walk_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(S, carry_len, stream_len, limit, B.d_blocks[slot].as<BlockDesc>(), nb, B.d_start.as<uint32_t>(),
+                                                            B.d_nrec.as<uint32_t>(), B.d_end.as<uint32_t>(), nullptr, nullptr, d_small + 1);
+    chain_check_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_start.as<uint32_t>(), B.d_end.as<uint32_t>(), nb, limit, d_small + 5, d_small + 1);
     DYN_CUDA(cudaGetLastError());
     DYN_CUDA(cudaMemsetAsync(B.d_nrec.as<uint32_t>() + nb, 0, 4, stream));
     size_t tmp_bytes = 0;
@@ -912,6 +1021,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     DYN_CUDA(cub::DeviceScan::ExclusiveSum(B.d_tmp.p, tmp_bytes, B.d_nrec.as<uint32_t>(), B.d_recbase.as<uint32_t>(), nb + 1, stream));
     DYN_CUDA(cudaMemcpyAsync(B.h_small, B.d_recbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, stream));
     DYN_CUDA(cudaMemcpyAsync(B.h_small + 1, d_small + 1, 4, cudaMemcpyDeviceToHost, stream));
+    DYN_CUDA(cudaMemcpyAsync(B.h_small + 5, d_small + 5, 4, cudaMemcpyDeviceToHost, stream));
     auto t_launched = now();
     if (timing) cudaEventRecord(tev[3], stream);
     DYN_CUDA(cudaStreamSynchronize(stream));
@@ -926,7 +1036,7 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     uint32_t status = B.h_small[1];
     auto status_error = [&](uint32_t st) -> int {
         if (st & 0xeu) { dyn_set_error("dyn_bam_dev: inflate failed (corrupt BGZF block, status 0x%x)", st); return DYN_ERR_FORMAT; }
-        if (st & (1u << 8)) { dyn_set_error("dyn_bam_dev: alignment records straddle BGZF blocks: use the host reader (dyn_bam_stream_*)"); return DYN_ERR_FORMAT; }
+        if (st & (1u << 8)) { dyn_set_error("dyn_bam_dev: the record chain could not be established block by block (straddle): use the host reader (dyn_bam_stream_*)"); return DYN_ERR_FORMAT; }
         if (st & (1u << 9)) { dyn_set_error("dyn_bam_dev: paired records: use the host reader (dyn_bam_stream_*)"); return DYN_ERR_FORMAT; }
         if (st & (1u << 16)) { dyn_set_error("dyn_bam_dev: corrupt record or aux data"); return DYN_ERR_FORMAT; }
         if (st & (1u << 17)) { dyn_set_error("dyn_bam_dev: alignment without HI / AS tag (KeyError in the reference, bam.py:295-296)"); return DYN_ERR_FORMAT; }
@@ -935,21 +1045,41 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
         return DYN_OK;
     };
     if ((rc = status_error(status))) return rc;
+    // what is left of the stream behind the last whole record goes to the next chunk (a record that starts in this chunk
+    // and ends in the next); the last chunk of a range has read the blocks behind the range for that
+    uint32_t carry_start = B.h_small[5];
+    if (carry_start == kNoStart) {
+        if (stream_len > s0) { dyn_set_error("dyn_bam_dev: no alignment record starts in a chunk of %u bytes", stream_len); return DYN_ERR_FORMAT; }
+        carry_start = stream_len;
+    }
+    uint32_t carry_next = 0;
+    if (!s->last) {
+        carry_next = stream_len - std::min(carry_start, stream_len);
+        if (carry_next > kCarryRoom) { dyn_set_error("dyn_bam_dev: an alignment record of more than %u bytes straddles chunks", kCarryRoom); return DYN_ERR_FORMAT; }
+    } else if (carry_start < limit) {
+        dyn_set_error("dyn_bam_dev: the last alignment record of the range is cut off (truncated file, or a record longer than the %d blocks read behind the range)", s->n_extra);
+        return DYN_ERR_FORMAT;
+    }
+    auto keep_carry = [&]() -> int {      // on the stream, behind every kernel that reads this chunk's stream
+        if (carry_next) DYN_CUDA(cudaMemcpyAsync(B.d_carry.p, S + carry_start, carry_next, cudaMemcpyDeviceToDevice, stream));
+        d->carry_len = carry_next;
+        return DYN_OK;
+    };
     d->records_seen += n_rec;
     chunk->n_records_seen = n_rec;
     chunk->end = s->last ? 1 : 0;
     IngestBuffers::OutSet &os = B.out[d->cur];
     d->cur ^= 1;
-    if (n_rec == 0) return DYN_OK;
+    if (n_rec == 0) return keep_carry();
     // ---- k2 (positions), k3 (parse), scan
     if ((rc = B.d_recat.ensure(4 * (size_t)n_rec))) return rc;
     if ((rc = B.d_parsed.ensure(sizeof(bamrec::Parsed) * (size_t)n_rec))) return rc;
     if ((rc = B.d_scan_in.ensure(8 * (size_t)(n_rec + 1)))) return rc;
     if ((rc = B.d_scan.ensure(8 * (size_t)(n_rec + 1)))) return rc;
-    index_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_blocks[slot].as<BlockDesc>(), nb, s->first_skip,
-                                                       nullptr, B.d_recbase.as<uint32_t>(), B.d_recat.as<uint32_t>(), d_small + 1);
+    chain_walk_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(S, carry_len, stream_len, limit, B.d_blocks[slot].as<BlockDesc>(), nb, B.d_start.as<uint32_t>(),
+                                                            nullptr, nullptr, B.d_recbase.as<uint32_t>(), B.d_recat.as<uint32_t>(), d_small + 1);
     DYN_CUDA(cudaGetLastError());
-    parse_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_recat.as<uint32_t>(), n_rec, d->tags,
+    parse_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(S, B.d_recat.as<uint32_t>(), n_rec, d->tags,
                                                           B.d_parsed.as<bamrec::Parsed>(), B.d_scan_in.as<unsigned long long>(), d_small + 1);
     DYN_CUDA(cudaGetLastError());
     DYN_CUDA(cudaMemsetAsync(B.d_scan_in.as<unsigned long long>() + n_rec, 0, 8, stream));
@@ -978,12 +1108,13 @@ extern "C" int dyn_bam_dev_next(dyn_bam_dev_t *d, dyn_bam_dev_chunk_t *chunk, vo
     uo.gene_idx = os.gene.as<int32_t>(); uo.score = os.score.as<int32_t>(); uo.ref_id = os.ref_id.as<int32_t>();
     uo.pos = os.pos.as<int32_t>(); uo.hi = os.hi.as<int32_t>(); uo.flag = os.flag.as<uint16_t>(); uo.gx_assigned = os.gxa.as<uint8_t>();
     if (n_units) {
-        pack_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(B.d_inflated.as<uint8_t>(), B.d_recat.as<uint32_t>(), n_rec, B.d_parsed.as<bamrec::Parsed>(),
+        pack_kernel<<<(n_rec + 127) / 128, 128, 0, stream>>>(S, B.d_recat.as<uint32_t>(), n_rec, B.d_parsed.as<bamrec::Parsed>(),
                                                              B.d_scan.as<unsigned long long>(), d->lean, d->gene_hash.as<unsigned long long>(),
                                                              d->gene_of_hash.as<int32_t>(), d->n_gene_hash, uo);
         DYN_CUDA(cudaGetLastError());
     }
     const uint32_t end16 = (uint32_t)total16;
+    if ((rc = keep_carry())) return rc;
     DYN_CUDA(cudaMemcpyAsync(uo.rec_off + n_units, &end16, 4, cudaMemcpyHostToDevice, stream));
     DYN_CUDA(cudaStreamSynchronize(stream));       // (&end16 is a stack variable; the staging buffer is released on return)
     chunk->n_units = n_units;

@@ -483,8 +483,10 @@ const void *dyn_bam_stream_field(const dyn_bam_stream_t *stream, int field, int6
 /* ------------------------------------------------------------------------------------------------
  * Device ingest: the same block range, inflated and packed ON THE GPU (csrc/bamdevice.cu) -- one warp per BGZF block
  * inflates it, one thread per alignment record filters / tokenises / packs it; only the compressed bytes cross PCIe.
- * Takes coordinate-sorted single-end BAMs whose BGZF blocks end on record boundaries (htslib / samtools / STAR write
- * them so); anything else is refused with DYN_ERR_FORMAT and belongs to dyn_bam_stream_*.  Options as for
+ * Takes coordinate-sorted single-end BAMs; BGZF blocks need not end on record boundaries (htslib's do, STAR's sorted BAMs
+ * do not): the record chain is established per block on the device and checked by induction, a record that starts in one
+ * chunk and ends in the next is carried over, the last record of a range is completed from the blocks behind the range.
+ * Paired records are refused with DYN_ERR_FORMAT (mate pairing is dyn_bam_stream_*'s).  Options as for
  * dyn_bam_stream_open (keys are always produced, n_threads = host threads that read the file into page-locked memory, 0 = 16;
  * gene_ids gives the gene index).
  * dyn_bam_dev_next fills *chunk with DEVICE pointers to one chunk's units -- packed records, offsets (n_units + 1),

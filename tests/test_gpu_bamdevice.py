@@ -137,11 +137,15 @@ def test_device_ingest_equals_host_reader_on_fixture(gpu_ctx, lean):
         assert got[k] == want[k], k
 
 
-@pytest.mark.parametrize('n_parts,chunk_bytes', [(1, 0), (1, 300_000), (3, 200_000)])
-def test_device_ingest_chunks_and_parts(gpu_ctx, tmp_path, n_parts, chunk_bytes):
+@pytest.mark.parametrize('blocks', ['aligned', 'straddling'])
+@pytest.mark.parametrize('n_parts,chunk_bytes', [(1, 0), (1, 300_000), (3, 200_000), (5, 70_000)])
+def test_device_ingest_chunks_and_parts(gpu_ctx, tmp_path, n_parts, chunk_bytes, blocks):
+    """Chunks and range parts of a file whose BGZF blocks end on record boundaries (htslib) and of one cut every 64 KB
+    wherever that falls (STAR's sorted BAMs): records that straddle blocks, chunks and parts are taken once, by the part /
+    chunk they start in."""
     out = str(tmp_path / 'big.bam')
     subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'make_bam.py'), ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'),
-                    out, '40', 'aligned'], check=True, capture_output=True)
+                    out, '40'] + (['aligned'] if blocks == 'aligned' else []), check=True, capture_output=True)
     genes = _genes(out)
     kw = dict(barcode_tag='CB', umi_tag='UB', gene_tag='GX', require_gene=True)
     want, seen = _host_chunks(out, True, genes, **kw)
@@ -158,9 +162,29 @@ def test_device_ingest_refuses_what_it_cannot_take(gpu_ctx, tmp_path):
     with pytest.raises(_lib.DynastB200Error, match='paired'):
         with bamio.DeviceBamStream(gpu_ctx, ref_path('smartseq_align', 'Aligned.sortedByCoord.out.bam'), barcode_tag='RG') as st:
             list(st)
-    out = str(tmp_path / 'split.bam')
+    # a file cut off in the middle of a record
+    out = str(tmp_path / 'cut.bam')
     subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'make_bam.py'), ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'),
                     out, '5'], check=True, capture_output=True)
-    with pytest.raises(_lib.DynastB200Error, match='straddle'):
+    raw = open(out, 'rb').read()
+    o, starts = 0, []
+    while o < len(raw):
+        starts.append(o)
+        o += int.from_bytes(raw[o + 16:o + 18], 'little') + 1
+
+    def left_over(n_blocks):            # bytes behind the last whole record when only the first n_blocks are kept
+        data = b''.join(zlib.decompress(raw[a + 12 + int.from_bytes(raw[a + 10:a + 12], 'little'):b - 8], -15) for a, b in zip(starts[:n_blocks], starts[1:]))
+        p = 8 + struct.unpack_from('<i', data, 4)[0]
+        n_ref = struct.unpack_from('<i', data, p)[0]
+        p += 4
+        for _ in range(n_ref):
+            p += 8 + struct.unpack_from('<i', data, p)[0]
+        while p + 4 <= len(data) and p + 4 + struct.unpack_from('<i', data, p)[0] <= len(data):
+            p += 4 + struct.unpack_from('<i', data, p)[0]
+        return len(data) - p
+
+    keep = next(k for k in range(len(starts) // 2, len(starts) - 1) if left_over(k) > 0)
+    open(out, 'wb').write(raw[:starts[keep]])                       # whole blocks, but the last record is incomplete
+    with pytest.raises(_lib.DynastB200Error, match='cut off|straddle'):
         with bamio.DeviceBamStream(gpu_ctx, out, barcode_tag='CB', umi_tag='UB') as st:
             list(st)

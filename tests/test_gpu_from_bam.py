@@ -59,8 +59,21 @@ def test_count_from_bam_equals_packed_path(gpu_ctx, synth_bam, ingest, chunk_byt
         assert np.array_equal(k[off[b]:off[b + 1]], k2[off2[j]:off2[j + 1]]) and np.array_equal(c[off[b]:off[b + 1]], c2[off2[j]:off2[j + 1]])
 
 
-def test_count_from_bam_auto_falls_back_to_the_host_reader(gpu_ctx, tmp_path):
-    """Records straddling BGZF blocks: the device path refuses, `auto` reads the file on the host; same tally."""
+def test_count_from_bam_auto_falls_back_to_the_host_reader(gpu_ctx):
+    """Paired records: the device path refuses, `auto` reads the file on the host."""
+    from dynast_b200 import bamio, pipeline
+    path = ref_path('smartseq_align', 'Aligned.sortedByCoord.out.bam')
+    with bamio.PackedBam(path, barcode_tag='RG', require_gene=False, n_threads=2) as pb:
+        n = pb.n_units
+    stats = {}
+    t = pipeline.tally_bam(gpu_ctx, path, [], barcode_tag='RG', umi_tag=None, require_gene=False, ingest='auto', stats=stats)
+    assert stats['ingest'].startswith('host') and t['counts'].shape[0] == n == stats['units']
+    with pytest.raises(Exception, match='paired'):
+        pipeline.tally_bam(gpu_ctx, path, [], barcode_tag='RG', umi_tag=None, require_gene=False, ingest='device')
+
+
+def test_tally_bam_on_straddling_blocks_equals_the_host_reader(gpu_ctx, tmp_path):
+    """Records straddling BGZF blocks (what STAR writes): device ingest and host reader give the same tally."""
     from dynast_b200 import bamio, pipeline
     out = str(tmp_path / 'split.bam')
     subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'make_bam.py'), ref_path('SRR11683995_align', 'Aligned.sortedByCoord.out.bam'),
@@ -69,12 +82,10 @@ def test_count_from_bam_auto_falls_back_to_the_host_reader(gpu_ctx, tmp_path):
         genes = sorted(set(pb.gene))
         n = pb.n_units
     stats = {}
-    t = pipeline.tally_bam(gpu_ctx, out, genes, ingest='auto', chunk_bytes=1 << 20, stats=stats)
-    assert stats['ingest'].startswith('host') and t['counts'].shape[0] == n == stats['units']
+    t = pipeline.tally_bam(gpu_ctx, out, genes, ingest='device', chunk_bytes=1 << 20, stats=stats)
+    assert t['counts'].shape[0] == n == stats['units']
     h = pipeline.tally_bam(gpu_ctx, out, genes, ingest='host', chunk_bytes=0)
     assert torch.equal(t['counts'], h['counts']) and torch.equal(t['barcode_key'], h['barcode_key'])
-    with pytest.raises(Exception, match='straddle'):
-        pipeline.tally_bam(gpu_ctx, out, genes, ingest='device')
 
 
 def _bam_rank(rank, world, port, path, gene_ids, strand, out_dir):
