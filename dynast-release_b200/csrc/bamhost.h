@@ -138,11 +138,29 @@ inline bool tokenize_md(const char *md, size_t md_len, const uint8_t *cigar, uin
     toks.clear();
     uint64_t aoff = 0, val = 0, n_del = 0;
     bool in_del = false, ok = true;
+    // The letters behind a '^' that are deleted bases are as many as the CIGAR's next D operation has -- zero counts between
+    // them are skipped, letters behind them are mismatches.  dynast's consensus (consensus.py:116-176) appends a count only
+    // when it is non-zero or a mismatch came last, and never forgets that mismatch inside a deletion: two deleted bases and
+    // a mismatch come out as "148^TAA" (no "0"), a mismatch and three deleted bases as "56C0^G0T0C" -- and a count on its
+    // consensus BAM has to read both.
+    uint32_t d_cursor = 0, del_left = 0;
+    auto next_deletion = [&]() -> uint32_t {
+        while (d_cursor < n_cigar) {
+            const uint32_t w = rd32(cigar + 4 * (size_t)d_cursor++);
+            if ((w & 0xf) == 2) return w >> 4;
+        }
+        return 0;
+    };
     for (size_t i = 0; i < md_len; ++i) {
         const char ch = md[i];
         if (ch >= '0' && ch <= '9') { val = val * 10 + (uint64_t)(ch - '0'); in_del = false; }
-        else if (ch == '^') { aoff += val; val = 0; in_del = true; }
-        else if (in_del) { toks.push_back((uint32_t)std::min<uint64_t>(aoff, 0xffff) | (letter_code(ch) << 16) | (1u << 20)); ++n_del; }
+        else if (ch == '^') { aoff += val; val = 0; in_del = true; del_left = next_deletion(); }
+        else if (del_left > 0) {
+            if (val) ok = false;              // matched bases inside a deletion
+            val = 0;
+            toks.push_back((uint32_t)std::min<uint64_t>(aoff, 0xffff) | (letter_code(ch) << 16) | (1u << 20));
+            ++n_del; --del_left;
+        }
         else {
             aoff += val; val = 0;
             if (aoff > 0xffff) ok = false;

@@ -184,13 +184,24 @@ REC_HD void pack_record(const uint8_t *base, uint32_t at, const Parsed &pr, int 
         }
     };
     const bool keep_tokens = pr.n_tok > 0;
+    // behind a '^', as many letters as the CIGAR's next D operation has are deleted bases, zero counts between them skipped;
+    // letters behind them are mismatches (bamhost.h tokenize_md)
+    uint32_t d_cursor = 0, del_left = 0;
     for (uint32_t i = 0; md[i]; ++i) {
         const uint8_t ch = md[i];
         if (ch >= '0' && ch <= '9') { val = val * 10 + (uint64_t)(ch - '0'); in_del = false; }
-        else if (ch == '^') { aoff += val; val = 0; in_del = true; }
-        else if (in_del) {
+        else if (ch == '^') {
+            aoff += val; val = 0; in_del = true; del_left = 0;
+            while (d_cursor < n_cigar) {
+                const uint32_t w = ld32(cigar + 4 * (size_t)d_cursor++);
+                if ((w & 0xf) == 2) { del_left = w >> 4; break; }
+            }
+        }
+        else if (del_left > 0) {
+            if (val) ok = false;
+            val = 0;
             if (keep_tokens && nt < pr.n_tok) ot[nt] = (uint32_t)(aoff < 0xffff ? aoff : 0xffff) | (letter_code(ch) << 16) | (1u << 20);
-            ++nt; ++n_del;
+            ++nt; ++n_del; --del_left;
         } else {
             aoff += val; val = 0;
             if (aoff > 0xffff) ok = false;

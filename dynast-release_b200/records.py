@@ -22,13 +22,18 @@ def tokenize_md(md: str, cigar: Sequence[Tuple[int, int]]):
     """MD tag text -> (tokens, consistent): one uint32 per MD letter, in MD order -- aligned (M/=/X) offset in
     bits 0..15, reference base (BAM 4-bit code) in bits 16..19, bit 20 for a deleted base (^XYZ run).
     `consistent` is False when the tag disagrees with the CIGAR (matched + mismatched bases != M/=/X length or
-    deleted letters != D length); pysam raises on such records."""
+    deleted letters != D length); pysam raises on such records.  One deviation from a purely lexical reading, below."""
     toks = []
     aoff = 0
     val = 0
     in_del = False
     n_del = 0
     ok = True
+    # Behind a '^', as many letters as the CIGAR's next D operation has are deleted bases (zero counts between them skipped),
+    # letters behind them are mismatches: dynast's consensus writes two deleted bases + a mismatch as "148^TAA" (no "0") and
+    # a mismatch + three deleted bases as "56C0^G0T0C" (consensus.py:116-176).
+    deletions = iter(n for op, n in cigar if op == 2)
+    del_left = 0
     for ch in md:
         if ch.isdigit():
             val = val * 10 + int(ch)
@@ -37,11 +42,16 @@ def tokenize_md(md: str, cigar: Sequence[Tuple[int, int]]):
             aoff += val
             val = 0
             in_del = True
+            del_left = next(deletions, 0)
         else:
             code = _CODE.get(ch, 0)
-            if in_del:
+            if del_left > 0:
+                if val:
+                    ok = False              # matched bases inside a deletion
+                val = 0
                 toks.append((min(aoff, 0xffff)) | (code << 16) | (1 << 20))
                 n_del += 1
+                del_left -= 1
             else:
                 aoff += val
                 val = 0

@@ -206,7 +206,11 @@ def write_synth_bam(path: str, batch, n_contigs: int = 25, level: int = 6, n_thr
     gene = batch.gene.cpu().numpy().astype(np.int64)
     score = np.clip(batch.score.cpu().numpy(), 0, 255).astype(np.uint8)
     ref_id = blob[rec_off[:-1].astype(np.int64) * 16 + 4].astype(np.int64)       # low byte of the header's ref_id (< 256 contigs)
-    order = np.argsort(ref_id, kind='stable').astype(np.int64)                   # positions already ascend with the index
+    pos = blob.view(np.int32)[rec_off[:-1].astype(np.int64) * 4]
+    if bool((np.diff(pos) >= 0).all()):
+        order = np.argsort(ref_id, kind='stable').astype(np.int64)               # positions already ascend with the index
+    else:                                                                        # clustered batches (UMI groups around random anchors)
+        order = np.lexsort((pos, ref_id)).astype(np.int64)
     # read names: SYN:<index>:<tile>:<x>:<y>
     idx = np.arange(n, dtype=np.uint64)
     name = np.concatenate([np.broadcast_to(np.frombuffer(b'SYN0001:7:HXXXXXXXX:1:', np.uint8), (n, 22)), _digits(idx % 2000 + 1101, 4, 10, b'0123456789'),

@@ -188,3 +188,20 @@ def test_device_ingest_refuses_what_it_cannot_take(gpu_ctx, tmp_path):
     with pytest.raises(_lib.DynastB200Error, match='cut off|straddle'):
         with bamio.DeviceBamStream(gpu_ctx, out, barcode_tag='CB', umi_tag='UB') as st:
             list(st)
+
+
+@pytest.mark.parametrize('lean', [True, False])
+def test_device_packer_reads_a_mismatch_glued_to_a_deletion(gpu_ctx, tmp_path, lean):
+    """dynast's consensus writes "10^TAA10" for two deleted bases followed by a mismatch (no "0" in between): the device
+    tokenizer takes the D operation's length from the CIGAR, like the host packers (tests/test_bampack.py)."""
+    from test_bampack import _crafted_md_bam
+    path = str(tmp_path / 'md.bam')
+    _crafted_md_bam(path)
+    kw = dict(barcode_tag='CB', umi_tag='UB', gene_tag='GX', require_gene=True)
+    want, seen = _host_chunks(path, lean, ['ENSG1'], **kw)
+    got, seen_d, _ = _device_chunks(gpu_ctx, path, lean, ['ENSG1'], **kw)
+    assert seen == seen_d == 5
+    for k in want:
+        assert got[k] == want[k], k
+    flags = [int.from_bytes(r[14:16], 'little') for r in got['records']]
+    assert [bool(f & 0x4000) for f in flags] == [False, False, True, False, False]
