@@ -1,5 +1,5 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_exchange.py -x -q -rs 2>&1 | tail -4 > gpurun_out/r2_2gpu_test.log; cat gpurun_out/r2_2gpu_test.log
+timeout 900 python -m pytest tests/test_gpu_exchange.py tests/test_gpu_from_bam.py -x -q -rs 2>&1 | tail -4 > gpurun_out/r2_2gpu_test.log; cat gpurun_out/r2_2gpu_test.log
 N=${1:-2}
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N $2 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err
 tail -3 gpurun_out/r2_bench_${N}gpu.err
