@@ -883,12 +883,9 @@ static int launch_inflate(dyn_ctx *ctx, const uint8_t *in, uint8_t *out, const B
         inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(in, out, blocks, nb, work, status);
     } else {
         const size_t table_bytes = sizeof(uint16_t) * dinflate::lane::kUnitsAll * 32;
-        static bool configured = false;
-        if (!configured) {
-            DYN_CUDA(cudaFuncSetAttribute(inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-            configured = true;
-        }
         const int warps = inflate_warps_per_sm();
+        if (warps <= 3)       // tables in shared memory (a per-device attribute: set on every launch, it is cheap)
+            DYN_CUDA(cudaFuncSetAttribute(inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
         const int ctas = std::min((nb + 31) / 32, ctx->sm_count * warps);
         uint16_t *tables = nullptr;
         if (warps > 3) {
