@@ -66,8 +66,24 @@ class PackedBam:
         fd, fo = _POOLS[name]
         data = self._raw(fd, np.uint8).tobytes()
         off = self._raw(fo, np.uint32)
-        out = np.empty(len(off) - 1, dtype=object)
-        for i in range(len(off) - 1):
+        n = len(off) - 1
+        out = np.empty(n, dtype=object)
+        if n == 0:
+            return out
+        lens = np.diff(off.astype(np.int64))
+        if lens.min() == lens.max() and lens[0] > 0 and int(off[0]) == 0 and data.isascii():
+            # one width (barcodes, UMIs, most gene ids): a fixed-width view decodes them all at once
+            width = int(lens[0])
+            fixed = np.frombuffer(data, dtype=f'S{width}', count=n)
+            if not (np.frombuffer(data, dtype=np.uint8, count=n * width).reshape(n, width)[:, -1] == 0).any():      # 'S' strips trailing NULs
+                out[:] = fixed.astype(f'U{width}')
+                return out
+        if data.isascii():          # byte offsets are character offsets: one decode, then slices
+            text = data.decode()
+            o = off.tolist()
+            out[:] = [text[a:b] for a, b in zip(o[:-1], o[1:])]
+            return out
+        for i in range(n):
             out[i] = data[off[i]:off[i + 1]].decode()
         return out
 
