@@ -883,8 +883,12 @@ static int launch_inflate(dyn_ctx *ctx, const uint8_t *in, uint8_t *out, const B
         inflate_kernel<<<ctas, kInfWarps * 32, 0, stream>>>(in, out, blocks, nb, work, status);
     } else {
         const size_t table_bytes = sizeof(uint16_t) * dinflate::lane::kUnitsAll * 32;
-        const int warps = inflate_warps_per_sm();
-        if (warps <= 3)       // tables in shared memory (a per-device attribute: set on every launch, it is cheap)
+        // Few blocks (a small file, one rank's share of a file split many ways): every block gets a lane even with three warps per
+        // SM, and then the tables fit shared memory, where a lookup costs a third of an L1 / L2 one (22 vs 33 ms per wave)
+        static const bool adaptive = getenv("DYN_INF_WARPS") == nullptr;
+        int warps = inflate_warps_per_sm();
+        if (adaptive && nb <= ctx->sm_count * 3 * 32) warps = 3;
+        if (warps <= 3)       // (a per-device attribute: set on every launch, it is cheap)
             DYN_CUDA(cudaFuncSetAttribute(inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
         const int ctas = std::min((nb + 31) / 32, ctx->sm_count * warps);
         uint16_t *tables = nullptr;
