@@ -71,6 +71,14 @@ def test_inflate_core_on_bgzf_blocks(shim, align, fn):
     assert n > 3
 
 
+def _fibonacci_text(rng, n):
+    """Byte frequencies that fall like Fibonacci numbers: the Huffman code of such a text is as deep as it gets."""
+    w = np.array([1, 1] + [0] * 30, dtype=np.float64)
+    for i in range(2, 32):
+        w[i] = w[i - 1] + w[i - 2]
+    return bytes(rng.choice(np.arange(32, dtype=np.uint8), n, p=w / w.sum()))
+
+
 @pytest.mark.parametrize('fn', DECODERS)
 def test_inflate_core_stream_kinds(shim, fn):
     rng = np.random.default_rng(0)
@@ -83,6 +91,8 @@ def test_inflate_core_stream_kinds(shim, fn):
         (b'ACGT' * 7 + b'\x00\x01\x02' * 5) * 700,
         bytes(rng.choice(np.arange(256, dtype=np.uint8), 65280, p=np.r_[[0.5], np.full(255, 0.5 / 255)])),   # long codes (> 10 bits)
         b'x' * 65280,                                            # distance 1 runs
+        _fibonacci_text(rng, 65000),                            # code lengths up to zlib's limit of 15 bits
+        bytes(rng.integers(0, 256, 30000, dtype=np.uint8)) * 2 + b'tail',   # a 30 000-byte match distance, 258-byte matches
     ]
     for data in texts:
         for level in (0, 1, 6, 9):
