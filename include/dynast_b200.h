@@ -481,8 +481,9 @@ int64_t dyn_bam_stream_n_refs(const dyn_bam_stream_t *stream);
 const void *dyn_bam_stream_field(const dyn_bam_stream_t *stream, int field, int64_t *n_bytes);
 
 /* ------------------------------------------------------------------------------------------------
- * Device ingest: the same block range, inflated and packed ON THE GPU (csrc/bamdevice.cu) -- one warp per BGZF block
- * inflates it, one thread per alignment record filters / tokenises / packs it; only the compressed bytes cross PCIe.
+ * Device ingest: the same block range, inflated and packed ON THE GPU (csrc/bamdevice.cu) -- BGZF blocks are inflated in
+ * two passes (Huffman codes to tokens with one lane per block, tokens to bytes with one warp per block), one thread per
+ * alignment record filters / tokenises / packs it; only the compressed bytes cross PCIe.
  * Takes coordinate-sorted single-end BAMs; BGZF blocks need not end on record boundaries (htslib's do, STAR's sorted BAMs
  * do not): the record chain is established per block on the device and checked by induction, a record that starts in one
  * chunk and ends in the next is carried over, the last record of a range is completed from the blocks behind the range.
@@ -493,7 +494,8 @@ const void *dyn_bam_stream_field(const dyn_bam_stream_t *stream, int field, int6
  * keys as in dyn_bam_stream chunks (fields 11-13), AS, reference id, position, HI, flag, gene-tag-present -- valid until
  * the second-next call; chunk->end is 1 on the last chunk of the range and 2 (nothing else set) on calls past it.  The call runs on `stream` and
  * synchronises it (chunk sizes come back from the device).
- * dyn_inflate_blocks: the inflate kernel alone on raw deflate payloads in device memory; d_block_desc = n_blocks x
+ * dyn_inflate_blocks: the inflate kernels alone on raw deflate payloads in device memory (the descriptors are read back
+ * for the output size, so the call synchronises the stream); d_block_desc = n_blocks x
  * {in_off, in_len, out_off, out_len} (u32), *d_status gets bit (1 << code) of inflate error codes 1 data, 2 input,
  * 3 output size; d_work is a scratch u32.
  * ------------------------------------------------------------------------------------------------ */
