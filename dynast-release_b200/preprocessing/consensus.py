@@ -21,6 +21,7 @@ Rules restated from the reference (each is checked against oracle/consensus_orac
   * consensus record (:179-200, 288-325): name = sha256 of the members' names, MAPQ 255, flag 16 iff the consensus
     strand is '-', tags AS (sum) NH HI RN [barcode] [UMI] [GX GN when a member carries the gene tag] [RS RI] NM MD.
 """
+import functools
 import hashlib
 import struct
 from typing import Dict, List, Optional
@@ -60,6 +61,7 @@ def _header_fields(blob: np.ndarray, at16: np.ndarray):
     return pos, ref_id, n_cigar, span
 
 
+@functools.lru_cache(maxsize=1 << 16)
 def _int_tag(tag: str, v: int) -> bytes:
     """An integer tag with the smallest type that holds it (what pysam's set_tags picks)."""
     v = int(v)
@@ -70,6 +72,7 @@ def _int_tag(tag: str, v: int) -> bytes:
     return tag.encode() + code.encode() + struct.pack('<' + fmt, v)
 
 
+@functools.lru_cache(maxsize=1 << 16)
 def _z_tag(tag: str, v: str) -> bytes:
     return tag.encode() + b'Z' + v.encode() + b'\0'
 
@@ -304,7 +307,7 @@ def call_consensus(
                     if info.get('gene_name'):
                         aux += _z_tag('GN', info['gene_name'])
             if add_RS_RI:
-                aux += _z_tag('RS', ';'.join(member_names)) + _z_tag('RI', ';'.join(str(x) for x in member_hi))
+                aux += _z_tag.__wrapped__('RS', ';'.join(member_names)) + _z_tag.__wrapped__('RI', ';'.join(str(x) for x in member_hi))      # (unique: not cached)
             aux += _int_tag('NM', int(cons['nm'][j]))
             out_aux.append(aux)
             out_names.append(hashlib.sha256(''.join(member_names).encode('utf-8')).hexdigest())
